@@ -1,0 +1,694 @@
+/*
+ * ngp_oracle.c — CPU ORACLE for the NextGP.jl marker-effect Gibbs sweep.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the checker, never the product: it
+ * may be imported / linked / executed only from tests/, from
+ * __graft_entry__.smoke() and from bench.py's cpu_baseline / --impl reference
+ * legs.  Nothing under nextgp.jl_b200/ links to or calls it.
+ *
+ * PARITY UNPINNED: the reference ships no tests, fixtures or golden vectors
+ * (/root/reference/test/runtests.jl:4-7 is an empty @testset) and Julia is not
+ * installed, so this restatement cannot be checked against reference outputs.
+ * It is pinned only by (i) the hyper-parameter transcripts in the reference
+ * docs (docs/src/BWGR/BWGR.md:52-55 etc., see tests/test_oracle.py), (ii) an
+ * independent numpy restatement (oracle/restate_numpy.py) and (iii) the
+ * Philox4x32-10 known-answer vectors of Random123.
+ *
+ * What it restates (all file:line under /root/reference/src):
+ *   - iteration order                    samplers.jl:32-53
+ *   - residual variance draw             functions.jl:523-525
+ *   - intercept (single-column X) draw   functions.jl:39-47
+ *   - BayesPR sweep                      functions.jl:118-137
+ *   - BayesB  sweep                      functions.jl:157-195
+ *   - BayesC  sweep                      functions.jl:197-236
+ *   - multi-breed (Tuple) BayesPR        functions.jl:140-154, 513-516
+ *   - sampleBeta / sampleVarBetaPR / samplePi   functions.jl:493-495, 509-511, 531-533
+ *   - column norms mpm                   mme.jl:305-307
+ *   - centring                           prepMatVec.jl:129
+ * The memory behaviour deliberately mimics the reference: dense fp64
+ * column-major centred genotypes, add-back axpy, dot, subtract axpy, and for
+ * BayesB/BayesC a SECOND dot on the (optional) Mp copy for included loci.
+ *
+ * Third-party arithmetic that is not in /root/reference: Distributions.jl
+ * (compat 0.25.58, Project.toml:29) Normal / Chisq / Beta / MvNormal /
+ * InverseWishart samplers and Julia's Xoshiro256++ default RNG.  Julia's
+ * (unseeded) bit-stream cannot be reproduced; parity is therefore defined at
+ * the VARIATE level: every draw is an explicit input ("replay"), or comes from
+ * the counter-based Philox4x32-10 stream specified in DESIGN.md §RNG, whose
+ * transforms are restated here independently of the CUDA implementation:
+ *   Normal   : Box-Muller on two 53-bit uniforms
+ *   Chisq(v) : 2*Gamma(v/2), Gamma by Marsaglia & Tsang (2000)
+ *   Beta(a,b): Ga/(Ga+Gb)
+ *   MvNormal : mean + chol(C)_lower * z
+ *   InvWishart(df,S): Bartlett factor of Wishart(df, S^-1), inverted
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011; Random123 reference).      */
+/* ------------------------------------------------------------------------- */
+static inline void philox_round(uint32_t c[4], const uint32_t k[2])
+{
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0];
+    const uint32_t n1 = lo1;
+    const uint32_t n2 = hi0 ^ c[3] ^ k[1];
+    const uint32_t n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+void ngo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    uint32_t k[2] = {key[0], key[1]};
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k);
+        k[0] += 0x9E3779B9u;
+        k[1] += 0xBB67AE85u;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+/* Stream layout:
+ *   key  = (seed lo32, seed hi32)
+ *   ctr0 = index (marker, region, ...)
+ *   ctr1 = purpose | attempt<<8 | set_id<<20 | component<<26
+ *   ctr2 = iteration (1-based)
+ *   ctr3 = chain id                                                      */
+enum {
+    NGO_P_CHI2_E = 0, NGO_P_Z_MU = 1, NGO_P_U = 2, NGO_P_Z = 3,
+    NGO_P_CHI2_B = 4, NGO_P_PI_A = 5, NGO_P_PI_B = 6, NGO_P_IW = 7
+};
+
+typedef struct { uint64_t seed; uint32_t chain; uint32_t iter; uint32_t set_id; } ngo_stream;
+
+static inline void stream_words(const ngo_stream* s, uint32_t purpose, uint32_t idx,
+                                uint32_t attempt, uint32_t comp, uint32_t w[4])
+{
+    uint32_t ctr[4], key[2];
+    ctr[0] = idx;
+    ctr[1] = purpose | (attempt << 8) | (s->set_id << 20) | (comp << 26);
+    ctr[2] = s->iter;
+    ctr[3] = s->chain;
+    key[0] = (uint32_t)(s->seed & 0xffffffffu);
+    key[1] = (uint32_t)(s->seed >> 32);
+    ngo_philox4x32_10(ctr, key, w);
+}
+
+/* 53-bit uniform strictly inside (0,1) */
+static inline double u53(uint32_t hi, uint32_t lo)
+{
+    const double two26 = 67108864.0;
+    return (((double)(hi >> 5)) * two26 + (double)(lo >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+static double stream_uniform(const ngo_stream* s, uint32_t purpose, uint32_t idx, uint32_t attempt, uint32_t comp)
+{
+    uint32_t w[4];
+    stream_words(s, purpose, idx, attempt, comp, w);
+    return u53(w[0], w[1]);
+}
+
+static double stream_normal(const ngo_stream* s, uint32_t purpose, uint32_t idx, uint32_t attempt, uint32_t comp)
+{
+    uint32_t w[4];
+    stream_words(s, purpose, idx, attempt, comp, w);
+    const double u1 = u53(w[0], w[1]);
+    const double u2 = u53(w[2], w[3]);
+    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}
+
+/* Marsaglia-Tsang Gamma(shape>=1, scale 1); attempt 2t -> normal, 2t+1 -> uniform */
+static double stream_gamma(const ngo_stream* s, uint32_t purpose, uint32_t idx, uint32_t comp, double shape)
+{
+    const double d = shape - 1.0 / 3.0;
+    const double c = 1.0 / sqrt(9.0 * d);
+    for (uint32_t t = 0; t < 2048; ++t) {
+        const double x = stream_normal(s, purpose, idx, 2 * t, comp);
+        const double u = stream_uniform(s, purpose, idx, 2 * t + 1, comp);
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return d * v;
+    }
+    return d; /* unreachable in practice */
+}
+
+static double stream_chisq(const ngo_stream* s, uint32_t purpose, uint32_t idx, uint32_t comp, double df)
+{
+    return 2.0 * stream_gamma(s, purpose, idx, comp, 0.5 * df);
+}
+
+/* exported scalar generators (tests compare the CUDA stream against these) */
+double ngo_stream_uniform(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t set_id, uint32_t purpose, uint32_t idx)
+{ ngo_stream s = {seed, chain, iter, set_id}; return stream_uniform(&s, purpose, idx, 0, 0); }
+double ngo_stream_normal(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t set_id, uint32_t purpose, uint32_t idx, uint32_t comp)
+{ ngo_stream s = {seed, chain, iter, set_id}; return stream_normal(&s, purpose, idx, 0, comp); }
+double ngo_stream_chisq(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t set_id, uint32_t purpose, uint32_t idx, uint32_t comp, double df)
+{ ngo_stream s = {seed, chain, iter, set_id}; return stream_chisq(&s, purpose, idx, comp, df); }
+double ngo_stream_beta(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t set_id, double a, double b)
+{
+    ngo_stream s = {seed, chain, iter, set_id};
+    const double ga = stream_gamma(&s, NGO_P_PI_A, 0, 0, a);
+    const double gb = stream_gamma(&s, NGO_P_PI_B, 0, 0, b);
+    return ga / (ga + gb);
+}
+
+/* ------------------------------------------------------------------------- */
+/* level-1 kernels with the reference's memory behaviour (OpenBLAS daxpy/ddot) */
+/* ------------------------------------------------------------------------- */
+static int g_threads = 1;
+void ngo_set_threads(int t)
+{
+    g_threads = t < 1 ? 1 : t;
+#ifdef _OPENMP
+    omp_set_num_threads(g_threads);
+#endif
+}
+int ngo_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+static double ddot(int64_t n, const double* x, const double* y)
+{
+    double s = 0.0;
+    if (g_threads > 1 && n >= 8192) {
+#pragma omp parallel for reduction(+ : s) schedule(static)
+        for (int64_t i = 0; i < n; ++i) s += x[i] * y[i];
+    } else {
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        int64_t i = 0;
+        for (; i + 3 < n; i += 4) {
+            s0 += x[i] * y[i]; s1 += x[i + 1] * y[i + 1];
+            s2 += x[i + 2] * y[i + 2]; s3 += x[i + 3] * y[i + 3];
+        }
+        for (; i < n; ++i) s0 += x[i] * y[i];
+        s = (s0 + s1) + (s2 + s3);
+    }
+    return s;
+}
+
+static void daxpy(int64_t n, double a, const double* x, double* y)
+{
+    if (a == 0.0) return; /* OpenBLAS daxpy returns early when alpha == 0 */
+    if (g_threads > 1 && n >= 8192) {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) y[i] += a * x[i];
+    } else {
+        for (int64_t i = 0; i < n; ++i) y[i] += a * x[i];
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* data preparation: prepMatVec.jl:129 (centre), mme.jl:305-307 (mpm)          */
+/* ------------------------------------------------------------------------- */
+/* codes: int8 column-major n x p (values 0/1/2) -> centred fp64 X, means, mpm */
+void ngo_center_codes(int64_t n, int64_t p, const int8_t* codes, double* X, double* mean, double* mpm)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < p; ++j) {
+        const int8_t* g = codes + j * n;
+        double s = 0.0;
+        for (int64_t i = 0; i < n; ++i) s += (double)g[i];
+        const double m = s / (double)n; /* mean(thisM,dims=1) */
+        double* x = X + j * n;
+        for (int64_t i = 0; i < n; ++i) x[i] = (double)g[i] - m;
+        if (mean) mean[j] = m;
+        if (mpm) {
+            double d = 0.0;
+            for (int64_t i = 0; i < n; ++i) d += x[i] * x[i]; /* dot(c,c) */
+            mpm[j] = d;
+        }
+    }
+}
+
+void ngo_center_f64(int64_t n, int64_t p, double* X, double* mean, double* mpm)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < p; ++j) {
+        double* x = X + j * n;
+        double s = 0.0;
+        for (int64_t i = 0; i < n; ++i) s += x[i];
+        const double m = s / (double)n;
+        for (int64_t i = 0; i < n; ++i) x[i] -= m;
+        if (mean) mean[j] = m;
+        if (mpm) {
+            double d = 0.0;
+            for (int64_t i = 0; i < n; ++i) d += x[i] * x[i];
+            mpm[j] = d;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* model structs (mirrored by ctypes in oracle/oracle.py)                      */
+/* ------------------------------------------------------------------------- */
+enum { NGO_BAYESPR = 0, NGO_BAYESB = 1, NGO_BAYESC = 2 };
+
+typedef struct {
+    int64_t n, p;
+    const double* X;          /* n x p column-major, centred                      */
+    const double* Mp;         /* second copy (mme.jl:308) or NULL -> reuse X      */
+    const double* mpm;        /* p                                                */
+    const double* lhs0;       /* p or NULL (mme.jl:314-322)                       */
+    const double* rhs0;       /* p or NULL                                        */
+    int32_t method;           /* NGO_BAYES*                                       */
+    int32_t est_pi;
+    int64_t n_regions;        /* BayesPR only                                     */
+    const int64_t* region_off;/* n_regions+1, 0-based half-open                   */
+    double df, scale;         /* mme.jl:492-506                                   */
+    int32_t set_id;
+    int32_t pad_;
+} ngo_set;
+
+typedef struct {
+    double* beta;             /* p                                                */
+    int64_t* delta;           /* p (Int64, mme.jl:444)                            */
+    double* varBeta;          /* PR: n_regions ; B: p ; C: 1                      */
+    double piHat[2];          /* [not fitted, fitted] mme.jl:359,371              */
+    double logPi[2];
+} ngo_set_state;
+
+/* variates of ONE iteration for ONE marker set.  u,z (and chi2_b for PR/B) are
+ * always filled before the sweep (by ngo_fill_marker_variates or by the caller
+ * when replaying); chi2_b[0] for BayesC and beta_pi depend on the chain state
+ * and are generated lazily unless replay != 0.  Generated values are stored,
+ * so after the call the struct is the replay log of the iteration.           */
+typedef struct {
+    int32_t replay;
+    int32_t pad_;
+    uint64_t seed;
+    uint32_t chain, iter;
+    double* u;                /* p  (B, C)                                        */
+    double* z;                /* p                                                */
+    double* chi2_b;           /* PR: n_regions ; B: p ; C: 1                      */
+    double* beta_pi;          /* 1                                                */
+} ngo_variates;
+
+void ngo_fill_marker_variates(const ngo_set* S, ngo_variates* V)
+{
+    ngo_stream s = {V->seed, V->chain, V->iter, (uint32_t)S->set_id};
+    const int64_t p = S->p;
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < p; ++j) {
+        if (S->method != NGO_BAYESPR && V->u) V->u[j] = stream_uniform(&s, NGO_P_U, (uint32_t)j, 0, 0);
+        V->z[j] = stream_normal(&s, NGO_P_Z, (uint32_t)j, 0, 0);
+        if (S->method == NGO_BAYESB) V->chi2_b[j] = stream_chisq(&s, NGO_P_CHI2_B, (uint32_t)j, 0, S->df + 1.0);
+    }
+    if (S->method == NGO_BAYESPR) {
+#pragma omp parallel for schedule(static)
+        for (int64_t r = 0; r < S->n_regions; ++r) {
+            const double k = (double)(S->region_off[r + 1] - S->region_off[r]);
+            V->chi2_b[r] = stream_chisq(&s, NGO_P_CHI2_B, (uint32_t)r, 0, S->df + k);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* residual variance: functions.jl:523-525, called at samplers.jl:32-35        */
+/* ------------------------------------------------------------------------- */
+double ngo_sample_varE(int64_t n, const double* e, double df_e, double scale_e,
+                       int replay, uint64_t seed, uint32_t chain, uint32_t iter, double* chi2_e)
+{
+    if (!replay) {
+        ngo_stream s = {seed, chain, iter, 0};
+        *chi2_e = stream_chisq(&s, NGO_P_CHI2_E, 0, 0, df_e + (double)n);
+    }
+    return (df_e * scale_e + ddot(n, e, e)) / (*chi2_e);
+}
+
+/* ------------------------------------------------------------------------- */
+/* intercept = single-column fixed effect of ones: functions.jl:39-47          */
+/*   ycorr += 1*b ; rhs = (1'ycorr)*iVarE + rhs0 ; lhs = n*iVarE + lhs0 ;      */
+/*   b ~ N(lhs\rhs, sqrt(inv(lhs))) ; ycorr -= 1*b                             */
+/* ------------------------------------------------------------------------- */
+double ngo_sample_intercept(int64_t n, double* e, double mu_old, double varE, double lhs0, double rhs0,
+                            int replay, uint64_t seed, uint32_t chain, uint32_t iter, double* z_mu)
+{
+    const double iVarE = 1.0 / varE;
+    double sum = 0.0;
+    for (int64_t i = 0; i < n; ++i) { e[i] += mu_old; sum += e[i]; }
+    const double rhs = sum * iVarE + rhs0;
+    const double lhs = (double)n * iVarE + lhs0;
+    const double meanMu = rhs / lhs;
+    if (!replay) {
+        ngo_stream s = {seed, chain, iter, 0};
+        *z_mu = stream_normal(&s, NGO_P_Z_MU, 0, 0, 0);
+    }
+    const double mu = meanMu + sqrt(1.0 / lhs) * (*z_mu);
+    for (int64_t i = 0; i < n; ++i) e[i] -= mu;
+    return mu;
+}
+
+/* sampleVarBetaPR: functions.jl:509-511 */
+static double sample_var_beta(double scale, double df, const double* b, int64_t k, double regionSizeOrNLoci, double chi2)
+{
+    (void)regionSizeOrNLoci; /* enters only through the df of chi2 */
+    return (scale * df + ddot(k, b, b)) / chi2;
+}
+
+/* ------------------------------------------------------------------------- */
+/* BayesPR sweep: functions.jl:118-137                                         */
+/* ------------------------------------------------------------------------- */
+static void sweep_PR(const ngo_set* S, ngo_set_state* T, double* e, double varE, ngo_variates* V)
+{
+    const int64_t n = S->n;
+    const double* Mp = S->Mp ? S->Mp : S->X;
+    const double iVarE = 1.0 / varE;
+    for (int64_t r = 0; r < S->n_regions; ++r) {
+        const int64_t j0 = S->region_off[r], j1 = S->region_off[r + 1];
+        const double iVarBeta = 1.0 / T->varBeta[r];
+        for (int64_t j = j0; j < j1; ++j) {
+            const double* x = S->X + j * n;
+            daxpy(n, T->beta[j], x, e);                                   /* :128 */
+            const double rhs = ddot(n, Mp + j * n, e) * iVarE + (S->rhs0 ? S->rhs0[j] : 0.0);      /* :129 */
+            const double lhs = S->mpm[j] * iVarE + (S->lhs0 ? S->lhs0[j] : 0.0) + iVarBeta;        /* :130 */
+            const double meanBeta = rhs / lhs;                            /* :131 */
+            T->beta[j] = meanBeta + sqrt(1.0 / lhs) * V->z[j];            /* :132, :493-495 */
+            daxpy(n, -1.0 * T->beta[j], x, e);                            /* :133 */
+        }
+        T->varBeta[r] = sample_var_beta(S->scale, S->df, T->beta + j0, j1 - j0, (double)(j1 - j0), V->chi2_b[r]); /* :135 */
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* BayesB sweep: functions.jl:157-195                                          */
+/* ------------------------------------------------------------------------- */
+static void sweep_B(const ngo_set* S, ngo_set_state* T, double* e, double varE, ngo_variates* V)
+{
+    const int64_t n = S->n, p = S->p;
+    const double* Mp = S->Mp ? S->Mp : S->X;
+    int64_t nLoci = 0;
+    for (int64_t j = 0; j < p; ++j) {
+        const double iVarE = 1.0 / varE;
+        const double iVarBeta = 1.0 / T->varBeta[j];                      /* Inf when varBeta == 0.0 */
+        const double* x = S->X + j * n;
+        daxpy(n, T->beta[j], x, e);                                       /* :167 */
+        const double rrr = ddot(n, x, e);                                 /* :168 */
+        const double v0 = S->mpm[j] * varE;                               /* :169 */
+        const double v1 = (S->mpm[j] * S->mpm[j]) * T->varBeta[j] + v0;   /* :170 */
+        const double logDelta0 = -0.5 * (log(v0) + (rrr * rrr) / v0) + T->logPi[0];
+        const double logDelta1 = -0.5 * (log(v1) + (rrr * rrr) / v1) + T->logPi[1];
+        const double probDelta1 = 1.0 / (1.0 + exp(logDelta0 - logDelta1));
+        if (V->u[j] < probDelta1) {                                       /* :174 strict < */
+            T->delta[j] = 1;
+            nLoci += 1;
+            const double rhs = ddot(n, Mp + j * n, e) * iVarE + (S->rhs0 ? S->rhs0[j] : 0.0);      /* :177 */
+            const double lhs = S->mpm[j] * iVarE + (S->lhs0 ? S->lhs0[j] : 0.0) + iVarBeta;        /* :178 */
+            const double meanBeta = rhs / lhs;                            /* lhs\rhs ; rhs/Inf == 0 */
+            T->beta[j] = meanBeta + sqrt(1.0 / lhs) * V->z[j];            /* one normal consumed */
+            daxpy(n, -1.0 * T->beta[j], x, e);                            /* :181 */
+            T->varBeta[j] = sample_var_beta(S->scale, S->df, T->beta + j, 1, 1.0, V->chi2_b[j]);   /* :182 */
+        } else {
+            T->beta[j] = 0.0;
+            T->delta[j] = 0;
+            T->varBeta[j] = 0.0;                                          /* :186 */
+        }
+    }
+    if (S->est_pi) {                                                      /* :189-193 */
+        if (!V->replay) {
+            *V->beta_pi = ngo_stream_beta(V->seed, V->chain, V->iter, (uint32_t)S->set_id,
+                                          (double)nLoci + 1.0, (double)(p - nLoci) + 1.0);
+        }
+        const double piIn = *V->beta_pi;
+        T->piHat[0] = 1.0 - piIn; T->piHat[1] = piIn;
+        T->logPi[0] = log(1.0 - piIn); T->logPi[1] = log(piIn);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* BayesC sweep: functions.jl:197-236                                          */
+/* ------------------------------------------------------------------------- */
+static void sweep_C(const ngo_set* S, ngo_set_state* T, double* e, double varE, ngo_variates* V)
+{
+    const int64_t n = S->n, p = S->p;
+    const double* Mp = S->Mp ? S->Mp : S->X;
+    int64_t nLoci = 0;
+    const double iVarE = 1.0 / varE;
+    const double iVarBeta = 1.0 / T->varBeta[0];
+    for (int64_t j = 0; j < p; ++j) {
+        const double* x = S->X + j * n;
+        daxpy(n, T->beta[j], x, e);                                       /* :207 */
+        const double rrr = ddot(n, x, e);                                 /* :208 */
+        const double v0 = S->mpm[j] * varE;
+        const double v1 = (S->mpm[j] * S->mpm[j]) * T->varBeta[0] + v0;
+        const double logDelta0 = -0.5 * (log(v0) + (rrr * rrr) / v0) + T->logPi[0];
+        const double logDelta1 = -0.5 * (log(v1) + (rrr * rrr) / v1) + T->logPi[1];
+        const double probDelta1 = 1.0 / (1.0 + exp(logDelta0 - logDelta1));
+        if (V->u[j] < probDelta1) {                                       /* :216 */
+            T->delta[j] = 1;
+            nLoci += 1;
+            const double rhs = ddot(n, Mp + j * n, e) * iVarE;            /* :219, rhs0 NOT added */
+            const double lhs = S->mpm[j] * iVarE + (S->lhs0 ? S->lhs0[j] : 0.0) + iVarBeta;        /* :220 */
+            const double meanBeta = rhs / lhs;
+            T->beta[j] = meanBeta + sqrt(1.0 / lhs) * V->z[j];
+            daxpy(n, -1.0 * T->beta[j], x, e);                            /* :223 */
+        } else {
+            T->beta[j] = 0.0;
+            T->delta[j] = 0;
+        }
+    }
+    if (!V->replay) {
+        ngo_stream s = {V->seed, V->chain, V->iter, (uint32_t)S->set_id};
+        V->chi2_b[0] = stream_chisq(&s, NGO_P_CHI2_B, 0, 0, S->df + (double)nLoci);
+    }
+    T->varBeta[0] = sample_var_beta(S->scale, S->df, T->beta, p, (double)nLoci, V->chi2_b[0]);     /* :230 */
+    if (S->est_pi) {                                                      /* :231-235 */
+        if (!V->replay) {
+            *V->beta_pi = ngo_stream_beta(V->seed, V->chain, V->iter, (uint32_t)S->set_id,
+                                          (double)nLoci + 1.0, (double)(p - nLoci) + 1.0);
+        }
+        const double piIn = *V->beta_pi;
+        T->piHat[0] = 1.0 - piIn; T->piHat[1] = piIn;
+        T->logPi[0] = log(1.0 - piIn); T->logPi[1] = log(piIn);
+    }
+}
+
+/* M[mSet].funct(mSet,M,beta,delta,ycorr,varE,varBeta) — samplers.jl:52 */
+int ngo_sweep(const ngo_set* S, ngo_set_state* T, double* e, double varE, ngo_variates* V)
+{
+    switch (S->method) {
+    case NGO_BAYESPR: sweep_PR(S, T, e, varE, V); return 0;
+    case NGO_BAYESB:  sweep_B(S, T, e, varE, V);  return 0;
+    case NGO_BAYESC:  sweep_C(S, T, e, varE, V);  return 0;
+    default: return -1;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* whole-chain driver for ONE marker set + intercept (samplers.jl:29-53),      */
+/* used for CPU-baseline timing and for native-stream parity runs.            */
+/* trace_* (optional, n_iter rows) record the state after every iteration.    */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    double df_e, scale_e;     /* mme.jl:87-94 */
+    int32_t has_intercept, pad_;
+    double mu_lhs0, mu_rhs0;
+} ngo_fixed;
+
+int ngo_run(const ngo_set* S, ngo_set_state* T, const ngo_fixed* F, double* e, double* mu, double* varE_io,
+            uint64_t seed, uint32_t chain, uint32_t iter0, int32_t n_iter,
+            double* scratch_u, double* scratch_z, double* scratch_chi2, /* sized like ngo_variates arrays */
+            double* trace_beta, double* trace_varE, double* trace_mu, double* trace_varBeta, double* trace_pi,
+            int64_t* trace_delta)
+{
+    const int64_t nvar = S->method == NGO_BAYESPR ? S->n_regions : (S->method == NGO_BAYESB ? S->p : 1);
+    for (int32_t it = 0; it < n_iter; ++it) {
+        const uint32_t iter = iter0 + (uint32_t)it;
+        double chi2_e = 0.0, z_mu = 0.0, beta_pi = 0.0;
+        const double varE = ngo_sample_varE(S->n, e, F->df_e, F->scale_e, 0, seed, chain, iter, &chi2_e);
+        if (F->has_intercept) *mu = ngo_sample_intercept(S->n, e, *mu, varE, F->mu_lhs0, F->mu_rhs0, 0, seed, chain, iter, &z_mu);
+        ngo_variates V;
+        V.replay = 0; V.pad_ = 0; V.seed = seed; V.chain = chain; V.iter = iter;
+        V.u = scratch_u; V.z = scratch_z; V.chi2_b = scratch_chi2; V.beta_pi = &beta_pi;
+        ngo_fill_marker_variates(S, &V);
+        if (ngo_sweep(S, T, e, varE, &V)) return -1;
+        *varE_io = varE;
+        if (trace_beta) memcpy(trace_beta + (int64_t)it * S->p, T->beta, sizeof(double) * (size_t)S->p);
+        if (trace_delta) memcpy(trace_delta + (int64_t)it * S->p, T->delta, sizeof(int64_t) * (size_t)S->p);
+        if (trace_varE) trace_varE[it] = varE;
+        if (trace_mu) trace_mu[it] = *mu;
+        if (trace_varBeta) memcpy(trace_varBeta + (int64_t)it * nvar, T->varBeta, sizeof(double) * (size_t)nvar);
+        if (trace_pi) { trace_pi[2 * it] = T->piHat[0]; trace_pi[2 * it + 1] = T->piHat[1]; }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* multi-breed (Tuple) BayesPR: functions.jl:140-154, 513-516; mme.jl:448-467  */
+/* k marker sets share loci; per locus the k effects are drawn jointly.       */
+/*   Xk[b] : n x p centred matrix of breed b ; beta: k x p (row b = breed b)   */
+/*   varBeta: n_regions x k x k (row-major per region)                         */
+/*   z: p x k normals ; iw_z / iw_chi2: Bartlett variates per region           */
+/* ------------------------------------------------------------------------- */
+static int chol_lower(int k, const double* A, double* L)
+{
+    memset(L, 0, sizeof(double) * (size_t)(k * k));
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = A[i * k + j];
+            for (int t = 0; t < j; ++t) s -= L[i * k + t] * L[j * k + t];
+            if (i == j) { if (s <= 0.0) return -1; L[i * k + i] = sqrt(s); }
+            else L[i * k + j] = s / L[j * k + j];
+        }
+    return 0;
+}
+
+static int inv_spd(int k, const double* A, double* Ainv)
+{
+    double L[64], Li[64];
+    if (k > 8 || chol_lower(k, A, L)) return -1;
+    memset(Li, 0, sizeof(Li));
+    for (int c = 0; c < k; ++c) {              /* Li = L^-1 (lower) */
+        Li[c * k + c] = 1.0 / L[c * k + c];
+        for (int i = c + 1; i < k; ++i) {
+            double s = 0.0;
+            for (int t = c; t < i; ++t) s -= L[i * k + t] * Li[t * k + c];
+            Li[i * k + c] = s / L[i * k + i];
+        }
+    }
+    for (int i = 0; i < k; ++i)                /* Ainv = Li' Li */
+        for (int j = 0; j < k; ++j) {
+            double s = 0.0;
+            for (int t = (i > j ? i : j); t < k; ++t) s += Li[t * k + i] * Li[t * k + j];
+            Ainv[i * k + j] = s;
+        }
+    return 0;
+}
+
+typedef struct {
+    int64_t n, p;
+    int32_t k, set_id;
+    const double* const* Xk;  /* k pointers, each n x p centred column-major      */
+    int64_t n_regions;
+    const int64_t* region_off;
+    double df;                /* 3 + k, mme.jl:493                                */
+    const double* scale;      /* k x k, v*(df-k-1), mme.jl:501                    */
+} ngo_mb_set;
+
+typedef struct {
+    int32_t replay, pad_;
+    uint64_t seed;
+    uint32_t chain, iter;
+    double* z;                /* p x k                                            */
+    double* iw_chi2;          /* n_regions x k   (Bartlett diagonal, df-i)        */
+    double* iw_z;             /* n_regions x k x k (strict lower used)            */
+} ngo_mb_variates;
+
+void ngo_mb_fill_variates(const ngo_mb_set* S, ngo_mb_variates* V)
+{
+    ngo_stream s = {V->seed, V->chain, V->iter, (uint32_t)S->set_id};
+    const int k = S->k;
+    for (int64_t j = 0; j < S->p; ++j)
+        for (int c = 0; c < k; ++c) V->z[j * k + c] = stream_normal(&s, NGO_P_Z, (uint32_t)j, 0, (uint32_t)c);
+    for (int64_t r = 0; r < S->n_regions; ++r) {
+        const double dfr = S->df + (double)(S->region_off[r + 1] - S->region_off[r]);
+        for (int i = 0; i < k; ++i) {
+            V->iw_chi2[r * k + i] = stream_chisq(&s, NGO_P_IW, (uint32_t)r, (uint32_t)(i * k + i), dfr - (double)i);
+            for (int j = 0; j < k; ++j)
+                V->iw_z[(r * k + i) * k + j] = (j < i) ? stream_normal(&s, NGO_P_IW, (uint32_t)r, 0, (uint32_t)(i * k + j)) : 0.0;
+        }
+    }
+}
+
+/* Sigma ~ InvWishart(df, Psi): W = (L A)(L A)' ~ Wishart(df, Psi^-1) with L = chol(Psi^-1),
+ * A lower Bartlett factor (A_ii = sqrt(chi2(df-i)), A_ij = N(0,1), i>j); Sigma = W^-1.    */
+static int inv_wishart_bartlett(int k, const double* Psi, const double* chi2, const double* zl, double* Sigma)
+{
+    double Pinv[64], L[64], A[64], LA[64], W[64];
+    if (inv_spd(k, Psi, Pinv) || chol_lower(k, Pinv, L)) return -1;
+    memset(A, 0, sizeof(A));
+    for (int i = 0; i < k; ++i) {
+        A[i * k + i] = sqrt(chi2[i]);
+        for (int j = 0; j < i; ++j) A[i * k + j] = zl[i * k + j];
+    }
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) {
+            double s = 0.0;
+            for (int t = 0; t < k; ++t) s += L[i * k + t] * A[t * k + j];
+            LA[i * k + j] = s;
+        }
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) {
+            double s = 0.0;
+            for (int t = 0; t < k; ++t) s += LA[i * k + t] * LA[j * k + t];
+            W[i * k + j] = s;
+        }
+    return inv_spd(k, W, Sigma);
+}
+
+int ngo_mb_sweep(const ngo_mb_set* S, double* beta /* k x p */, double* varBeta /* R x k x k */,
+                 double* e, double varE, ngo_mb_variates* V)
+{
+    const int64_t n = S->n, p = S->p;
+    const int k = S->k;
+    if (k > 8) return -1;
+    for (int64_t r = 0; r < S->n_regions; ++r) {
+        const int64_t j0 = S->region_off[r], j1 = S->region_off[r + 1];
+        double invB[64];
+        if (inv_spd(k, varBeta + r * k * k, invB)) return -2;             /* :143 */
+        for (int64_t j = j0; j < j1; ++j) {
+            double RHS[8], MtM[64], LHS[64], C[64], Lc[64], mean[8];
+            for (int b = 0; b < k; ++b) daxpy(n, beta[b * p + j], S->Xk[b] + j * n, e);           /* :145 */
+            for (int b = 0; b < k; ++b) RHS[b] = ddot(n, S->Xk[b] + j * n, e) / varE;            /* :146 */
+            for (int a = 0; a < k; ++a)
+                for (int b = 0; b < k; ++b) {
+                    MtM[a * k + b] = ddot(n, S->Xk[a] + j * n, S->Xk[b] + j * n);                /* mpm: mme.jl:464 */
+                    LHS[a * k + b] = MtM[a * k + b] / varE + invB[a * k + b];
+                }
+            if (inv_spd(k, LHS, C)) return -3;                            /* :147 */
+            for (int a = 0; a < k; ++a) { double s = 0; for (int b = 0; b < k; ++b) s += C[a * k + b] * RHS[b]; mean[a] = s; }
+            if (chol_lower(k, C, Lc)) return -4;
+            for (int a = 0; a < k; ++a) {                                 /* :149 MvNormal(mean, C) */
+                double s = mean[a];
+                for (int b = 0; b <= a; ++b) s += Lc[a * k + b] * V->z[j * k + b];
+                beta[a * p + j] = s;
+            }
+            for (int b = 0; b < k; ++b) daxpy(n, -beta[b * p + j], S->Xk[b] + j * n, e);          /* :150 */
+        }
+        double Psi[64];                                                   /* :152, :513-516 */
+        for (int a = 0; a < k; ++a)
+            for (int b = 0; b < k; ++b) {
+                double s = S->scale[a * k + b];
+                for (int64_t j = j0; j < j1; ++j) s += beta[a * p + j] * beta[b * p + j];
+                Psi[a * k + b] = s;
+            }
+        if (inv_wishart_bartlett(k, Psi, V->iw_chi2 + r * k, V->iw_z + r * k * k, varBeta + r * k * k)) return -5;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* synthetic genotype generator (SURVEY Appendix C / DESIGN.md §synthetic):    */
+/* code(i,j) from Philox word (i&3) of counter (i>>2, j, 0, 0x47454e4f) under  */
+/* key = seed, compared with per-column 32-bit thresholds.                    */
+/* ------------------------------------------------------------------------- */
+void ngo_synth_codes(uint64_t seed, int64_t n, int64_t j0, int64_t j1,
+                     const uint32_t* thr0, const uint32_t* thr1, int8_t* out /* n x (j1-j0) col-major */)
+{
+    const uint32_t key[2] = {(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32)};
+#pragma omp parallel for schedule(static)
+    for (int64_t j = j0; j < j1; ++j) {
+        int8_t* g = out + (j - j0) * n;
+        for (int64_t i4 = 0; i4 < n; i4 += 4) {
+            uint32_t ctr[4] = {(uint32_t)(i4 >> 2), (uint32_t)j, 0u, 0x47454e4fu}, w[4];
+            ngo_philox4x32_10(ctr, key, w);
+            for (int t = 0; t < 4 && i4 + t < n; ++t)
+                g[i4 + t] = (int8_t)((w[t] >= thr0[j]) + (w[t] >= thr1[j]));
+        }
+    }
+}
