@@ -1,0 +1,188 @@
+/*
+ * ngp.h — C ABI of libngp.so: the B200-native (sm_100a) marker-effect Gibbs
+ * sweep that slots in behind NextGP.jl's per-marker-set sampler.
+ *
+ * Every entry point cites the reference interface it replaces (file:line under
+ * the NextGP.jl v1.2.0 tree).  Plain pointers and sizes only; every export
+ * returns 0 on success and a negative NGP_E* code otherwise, with the text in
+ * ngp_last_error().  There is NO CPU backend: without a CUDA device every
+ * compute entry point fails with NGP_ECUDA.
+ *
+ * One handle = one chain on one GPU.  A handle is not thread-safe.
+ * Host buffers are borrowed for the duration of a call only.
+ */
+#ifndef NGP_H_
+#define NGP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGP_ABI_VERSION 1
+#define NGP_MAX_SETS 8
+
+typedef struct ngp_handle ngp_handle;
+
+enum ngp_status {
+    NGP_OK = 0,
+    NGP_EINVAL = -1,   /* bad argument / call order                         */
+    NGP_ECUDA = -2,    /* CUDA runtime error (text in ngp_last_error)        */
+    NGP_EDATA = -3,    /* genotype value outside {0,1,2} (missing -> reject; */
+                       /* the reference drops such columns, prepMatVec.jl:118)*/
+    NGP_ERANGE = -4,   /* fixed-point reduction overflow guard tripped       */
+    NGP_ENOMEM = -5,
+    NGP_EUNSUPPORTED = -6
+};
+
+/* priorVCV[pSet].name dispatch of mme.jl:331,350,362 */
+enum ngp_method { NGP_BAYESPR = 0, NGP_BAYESB = 1, NGP_BAYESC = 2 };
+
+/* host input formats for ngp_upload_genotypes */
+enum ngp_geno_format {
+    NGP_GENO_I8 = 0,      /* int8 codes 0/1/2, column-major, leading dimension ld        */
+    NGP_GENO_F64 = 1,     /* Float64 0.0/1.0/2.0 (raw, NOT centred), column-major, ld     */
+                          /*   = the Matrix{Float64} of prepMatVec.jl:120 before :129     */
+    NGP_GENO_PACKED2 = 2  /* 2-bit codes, 4 per byte, LSB first, columns padded to bytes; */
+                          /*   ld = bytes per column (>= ceil(n/4))                       */
+};
+
+/* device storage of the genotype codes */
+enum ngp_storage {
+    NGP_STORE_I8 = 0,     /* one byte per code, row-panelled column-major                */
+    NGP_STORE_2BIT = 1    /* four codes per byte, row-panelled column-major              */
+};
+
+/* kernel variants (ngp_configure key NGP_CFG_KERNEL) */
+enum ngp_kernel {
+    NGP_KERNEL_BLOCKED = 0,  /* blocked exact sweep: one grid-wide reduction per block of markers */
+    NGP_KERNEL_LITERAL = 1   /* one grid-wide reduction per marker (north-star baseline design)   */
+};
+
+enum ngp_config_key {
+    NGP_CFG_KERNEL = 0,        /* enum ngp_kernel                                           */
+    NGP_CFG_BLOCK = 1,         /* markers per block: 32 or 64 (0 = auto)                    */
+    NGP_CFG_MIN_ROWS = 2,      /* minimum rows per CTA when choosing the panel count        */
+    NGP_CFG_MAX_CTAS = 3       /* cap on CTAs (0 = one per SM); must be set before upload   */
+};
+
+/* -------------------------------------------------------------------------
+ * Prior of one marker set: what mme.getMME! derives from priorVCV[pSet]
+ * (mme.jl:324-373 method wiring, :492-506 df/scale, :513-520 initial varBeta).
+ * ------------------------------------------------------------------------- */
+typedef struct ngp_prior {
+    int32_t method;              /* enum ngp_method                                          */
+    int32_t est_pi;              /* BayesB/C: estimatePi (mme.jl:358,370)                     */
+    double df;                   /* 3 + size(v,1) = 4 (mme.jl:493)                            */
+    double scale;                /* v*(df-2)/df (mme.jl:501)                                  */
+    double var_init;             /* v: initial value of every variance slot (mme.jl:516)      */
+    double pi_in;                /* BayesB/C: prior inclusion probability (mme.jl:351,363)    */
+    int64_t n_regions;           /* BayesPR: length(regionArray) (mme.jl:335-348); B/C: ignored */
+    const int64_t* region_off;   /* BayesPR: n_regions+1 offsets, 0-based half-open; NULL = one region */
+    const double* lhs0;          /* p or NULL: M[pSet][:lhs] summary-stat precision (mme.jl:314-322) */
+    const double* rhs0;          /* p or NULL: M[pSet][:rhs]                                   */
+} ngp_prior;
+
+/* Variate log of n_iter iterations for replay parity: the sampler
+ * consumes these instead of its Philox stream.  Layout is row-major
+ * [iteration][index].  Set s uses u[s], z[s], chi2_b[s], beta_pi[s].           */
+typedef struct ngp_replay {
+    int32_t n_iter;
+    int32_t n_sets;
+    const double* chi2_e;                  /* [n_iter]       functions.jl:524               */
+    const double* z_mu;                    /* [n_iter]       functions.jl:45                */
+    const double* u[NGP_MAX_SETS];         /* [n_iter][p]    functions.jl:174,216 (B/C)     */
+    const double* z[NGP_MAX_SETS];         /* [n_iter][p]    functions.jl:494               */
+    const double* chi2_b[NGP_MAX_SETS];    /* [n_iter][nvar] functions.jl:510 (nvar: PR=n_regions, B=p, C=1) */
+    const double* beta_pi[NGP_MAX_SETS];   /* [n_iter]       functions.jl:532               */
+} ngp_replay;
+
+/* Chain state, the arguments M[mSet].funct mutates (functions.jl:118,157,197)
+ * plus what runSampler! keeps between iterations (samplers.jl:23).  NULL
+ * members are skipped.                                                          */
+typedef struct ngp_state {
+    int64_t n;                             /* individuals                                    */
+    int32_t n_sets;
+    int32_t pad_;
+    double* e;                             /* [n] ycorr                                      */
+    double mu;                             /* b[intercept]                                   */
+    double varE;
+    int64_t iter;                          /* iterations completed on this handle            */
+    double* beta[NGP_MAX_SETS];            /* [p]                                            */
+    int64_t* delta[NGP_MAX_SETS];          /* [p] Int64 like mme.jl:444                      */
+    double* varBeta[NGP_MAX_SETS];         /* [nvar]                                         */
+    double pi[NGP_MAX_SETS][2];            /* piHat = [not fitted, fitted] (mme.jl:359,371)   */
+} ngp_state;
+
+typedef struct ngp_timing {
+    double last_run_ms;          /* device time of the last ngp_run / ngp_sweep kernel (CUDA events) */
+    int64_t launches;            /* kernels launched by this handle since creation              */
+    int32_t ctas, threads;       /* geometry of the sweep kernel                                */
+    int32_t block, rows_per_cta; /* markers per block, rows per CTA panel                        */
+    int64_t smem_bytes;
+} ngp_timing;
+
+/* ---- lifetime ------------------------------------------------------------ */
+int ngp_abi_version(void);
+int ngp_device_count(void);
+int ngp_create(int device, ngp_handle** out);
+int ngp_destroy(ngp_handle* h);
+const char* ngp_last_error(const ngp_handle* h);   /* h may be NULL: error of the last failed ngp_create */
+int ngp_configure(ngp_handle* h, int key, int64_t value);
+/* run on a caller-owned CUDA stream (cudaStream_t as void*); NULL = handle's own stream */
+int ngp_set_stream(ngp_handle* h, void* cuda_stream);
+
+/* ---- data: replaces prepMatVec.prep's SNP branch output M[arg1][:data]
+ *      (prepMatVec.jl:116-131) and getMME!'s mpm/Mp (mme.jl:299-311).
+ *      Packs on device, computes column sums, means, mpm and block Gram.   -- */
+int ngp_upload_genotypes(ngp_handle* h, int set_id, int64_t n, int64_t p,
+                         const void* data, int fmt, int64_t ld, int storage);
+/* synthetic codes generated on device: code(i,j) =
+ * (w>=thr0[j]) + (w>=thr1[j]) with w = word (i&3) of Philox4x32-10(key=seed,
+ * ctr=(i>>2, j, 0, 0x47454e4f)).  Bit-identical to oracle ngo_synth_codes.  */
+int ngp_synth_genotypes(ngp_handle* h, int set_id, int64_t n, int64_t p, uint64_t seed,
+                        const uint32_t* thr0, const uint32_t* thr1, int storage);
+/* unpack device storage back to int8 column-major (bit-exact round-trip tests) */
+int ngp_download_genotypes(ngp_handle* h, int set_id, int64_t j0, int64_t j1, int8_t* out);
+/* mean_j (prepMatVec.jl:129) and mpm_j = X_j'X_j of the centred column (mme.jl:305-307) */
+int ngp_get_column_stats(ngp_handle* h, int set_id, double* mean, double* mpm);
+
+/* host 2-bit codec (format NGP_GENO_PACKED2); returns NGP_EDATA on a code outside 0..2 */
+int ngp_pack2(const int8_t* codes, int64_t n, int64_t p, int64_t ld_in, uint8_t* out, int64_t ld_out);
+int ngp_unpack2(const uint8_t* packed, int64_t n, int64_t p, int64_t ld_in, int8_t* out, int64_t ld_out);
+
+/* ---- model: replaces the state getMME! allocates (mme.jl:57,87-94,443-444,492-520) */
+int ngp_set_phenotype(ngp_handle* h, const double* y, int64_t n);            /* ycorr = deepcopy(Y) */
+int ngp_set_residual_prior(ngp_handle* h, double df_e, double scale_e);      /* E[:df], E[:scale]  */
+/* single-column fixed effect of ones (functions.jl:39-47); lhs0/rhs0 = X[xSet][:lhs/:rhs] */
+int ngp_set_intercept(ngp_handle* h, int enabled, double lhs0, double rhs0);
+int ngp_set_prior(ngp_handle* h, int set_id, const ngp_prior* prior);
+
+/* ---- variates --------------------------------------------------------------- */
+int ngp_set_rng(ngp_handle* h, uint64_t seed, uint32_t chain_id);            /* Philox4x32-10 key / stream */
+int ngp_set_replay(ngp_handle* h, const ngp_replay* log);                    /* NULL = back to Philox */
+
+/* ---- sampling ---------------------------------------------------------------
+ * ngp_run replaces n_iter trips of the loop body of samplers.runSampler!
+ * (samplers.jl:29-53): varE -> intercept -> every marker set, all on device. */
+int ngp_run(ngp_handle* h, int32_t n_iter);
+/* ngp_sweep replaces ONE call M[mSet].funct(mSet,M,beta,delta,ycorr,varE,varBeta)
+ * (samplers.jl:52; functions.jl:118,157,197): host buffers in, mutated in place. */
+int ngp_sweep(ngp_handle* h, int set_id, double* ycorr, double varE,
+              double* beta, int64_t* delta, double* varBeta, double* piHat);
+int ngp_get_state(ngp_handle* h, ngp_state* out);
+int ngp_set_state(ngp_handle* h, const ngp_state* in);
+/* running posterior sums since the last reset: sum(beta), sum(beta^2), sum(delta) per marker */
+int ngp_reset_posterior(ngp_handle* h);
+int ngp_get_posterior(ngp_handle* h, int set_id, int64_t* n_samples, double* sum_beta, double* sum_beta2, double* sum_delta);
+int ngp_get_timing(ngp_handle* h, ngp_timing* out);
+
+/* stream self-test: fills out[0..n) with the handle's variates of one purpose
+ * (purpose: 2=uniform 3=normal 4=chisq(df)) for iteration iter, set set_id.   */
+int ngp_debug_variates(ngp_handle* h, int set_id, uint32_t iter, int purpose, double df, int64_t n, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGP_H_ */

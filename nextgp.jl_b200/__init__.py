@@ -1,0 +1,12 @@
+"""nextgp.jl_b200 — B200-native (sm_100a) marker-effect Gibbs sweep behind NextGP.jl's sampler slot.
+
+Holds only what the hot path needs: csrc/ (CUDA kernels + the C ABI of include/ngp.h, built in-tree
+to libngp.so) and the host-side mirror of the reference interface (api.py).  No CPU fallback."""
+from . import _lib
+from ._lib import (BAYESB, BAYESC, BAYESPR, GENO_F64, GENO_I8, GENO_PACKED2, KERNEL_BLOCKED, KERNEL_LITERAL, NgpError, build)
+from .api import (BayesB, BayesC, BayesPR, MarkerTerm, Random, Sampler, SummaryStatistics, getMME, outMCMC, prep2RegionData,
+                  prep_snp, runLMEM, runSampler, summaryMCMC)
+from . import synth
+
+__all__ = ["Sampler", "runLMEM", "getMME", "runSampler", "BayesPR", "BayesB", "BayesC", "Random", "SummaryStatistics",
+           "outMCMC", "summaryMCMC", "prep_snp", "prep2RegionData", "MarkerTerm", "synth", "build", "NgpError"]

@@ -1,0 +1,132 @@
+"""ctypes binding of libngp.so (include/ngp.h).  Fails loudly when the CUDA library is missing:
+there is no CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+SO_PATH = os.path.join(_HERE, "libngp.so")
+CSRC = os.path.join(_HERE, "csrc")
+HEADER = os.path.join(_ROOT, "include", "ngp.h")
+
+NGP_MAX_SETS = 8
+BAYESPR, BAYESB, BAYESC = 0, 1, 2
+GENO_I8, GENO_F64, GENO_PACKED2 = 0, 1, 2
+STORE_I8, STORE_2BIT = 0, 1
+KERNEL_BLOCKED, KERNEL_LITERAL = 0, 1
+CFG_KERNEL, CFG_BLOCK, CFG_MIN_ROWS, CFG_MAX_CTAS = 0, 1, 2, 3
+OK, EINVAL, ECUDA, EDATA, ERANGE, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class NgpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libngp error {code}: {msg}")
+        self.code = code
+
+
+class Prior(C.Structure):
+    _fields_ = [("method", C.c_int32), ("est_pi", C.c_int32), ("df", C.c_double), ("scale", C.c_double),
+                ("var_init", C.c_double), ("pi_in", C.c_double), ("n_regions", C.c_int64),
+                ("region_off", C.c_void_p), ("lhs0", C.c_void_p), ("rhs0", C.c_void_p)]
+
+
+class Replay(C.Structure):
+    _fields_ = [("n_iter", C.c_int32), ("n_sets", C.c_int32), ("chi2_e", C.c_void_p), ("z_mu", C.c_void_p),
+                ("u", C.c_void_p * NGP_MAX_SETS), ("z", C.c_void_p * NGP_MAX_SETS),
+                ("chi2_b", C.c_void_p * NGP_MAX_SETS), ("beta_pi", C.c_void_p * NGP_MAX_SETS)]
+
+
+class State(C.Structure):
+    _fields_ = [("n", C.c_int64), ("n_sets", C.c_int32), ("pad_", C.c_int32), ("e", C.c_void_p),
+                ("mu", C.c_double), ("varE", C.c_double), ("iter", C.c_int64),
+                ("beta", C.c_void_p * NGP_MAX_SETS), ("delta", C.c_void_p * NGP_MAX_SETS),
+                ("varBeta", C.c_void_p * NGP_MAX_SETS), ("pi", (C.c_double * 2) * NGP_MAX_SETS)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("last_run_ms", C.c_double), ("launches", C.c_int64), ("ctas", C.c_int32), ("threads", C.c_int32),
+                ("block", C.c_int32), ("rows_per_cta", C.c_int32), ("smem_bytes", C.c_int64)]
+
+
+def sources() -> list[str]:
+    return [os.path.join(CSRC, "ngp_api.cu")]
+
+
+def _stale() -> bool:
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = [HEADER] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> nextgp.jl_b200/libngp.so (in-tree, travels to the GPU box)."""
+    if force or _stale():
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + sources()
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        if verbose:
+            sys.stderr.write(r.stderr)
+    return SO_PATH
+
+
+_lib = None
+
+_SIGS = {
+    "ngp_abi_version": (C.c_int, []),
+    "ngp_device_count": (C.c_int, []),
+    "ngp_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "ngp_destroy": (C.c_int, [C.c_void_p]),
+    "ngp_last_error": (C.c_char_p, [C.c_void_p]),
+    "ngp_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
+    "ngp_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ngp_upload_genotypes": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int]),
+    "ngp_synth_genotypes": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]),
+    "ngp_download_genotypes": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
+    "ngp_get_column_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ngp_pack2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
+    "ngp_unpack2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
+    "ngp_set_phenotype": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "ngp_set_residual_prior": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "ngp_set_intercept": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
+    "ngp_set_prior": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Prior)]),
+    "ngp_set_rng": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32]),
+    "ngp_set_replay": (C.c_int, [C.c_void_p, C.POINTER(Replay)]),
+    "ngp_run": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ngp_sweep": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ngp_get_state": (C.c_int, [C.c_void_p, C.POINTER(State)]),
+    "ngp_set_state": (C.c_int, [C.c_void_p, C.POINTER(State)]),
+    "ngp_reset_posterior": (C.c_int, [C.c_void_p]),
+    "ngp_get_posterior": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ngp_get_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
+    "ngp_debug_variates": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_double, C.c_int64, C.c_void_p]),
+}
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_SIGS)
+
+
+def lib() -> C.CDLL:
+    """Loads libngp.so.  Raises if it has not been built — never falls back to anything else."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(nvcc, sm_100a).  nextgp.jl_b200 has no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib

@@ -1,0 +1,544 @@
+"""Host-side mirror of NextGP.jl's interface for the marker-effect path, on top of the C ABI.
+
+The reference is Julia (absent from this image), so the host side is written in Python with the
+reference's own names and argument meaning; the Julia `ccall` shim a maintainer would add is in
+INTEGRATION.md / julia/NextGPB200.jl.  Citations are file:line under NextGP.jl v1.2.0 `src/`.
+
+  BayesPR / BayesB / BayesC / Random / SummaryStatistics   runTime.jl:30-76,135-152
+  prep_snp            prepMatVec.jl:113-134 (read text, drop columns with missing, centring is done on device)
+  prep2RegionData     misc.jl:163-215
+  getMME              mme.jl:87-94 (E), :286-446 (marker wiring), :492-520 (df/scale/varBeta), :543-595 (headers)
+  runSampler          samplers.jl:23-106
+  runLMEM             MCMC.jl:31-41
+  outMCMC             outFiles.jl:17-21
+  summaryMCMC         misc.jl:241-244
+  Sampler             the handle: one chain on one GPU (ngp_create ... ngp_destroy)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import shutil
+from dataclasses import dataclass, field
+from typing import Any
+
+import numpy as np
+
+from . import _lib as L
+
+
+# ----------------------------------------------------------------------------- prior types (runTime.jl)
+@dataclass
+class BayesPRType:
+    r: int
+    v: float
+    name: str = "BayesPR"
+
+
+@dataclass
+class BayesBType:
+    pi: float
+    v: float
+    name: str = "BayesB"
+    estimatePi: bool = False
+
+
+@dataclass
+class BayesCType:
+    pi: float
+    v: float
+    name: str = "BayesC"
+    estimatePi: bool = False
+
+
+@dataclass
+class RandomEffectType:
+    str: Any
+    v: float
+    type: int = 1
+
+
+@dataclass
+class SummaryStatistics:
+    m: Any
+    v: Any
+
+
+def BayesPR(r: int, v: float, name: str = "BayesPR") -> BayesPRType:
+    """runTime.jl:36-45 — r: 1 per-SNP variance, 99 per chromosome, 9999 one common variance, else window size."""
+    return BayesPRType(int(r), float(v), name)
+
+
+def BayesB(pi: float, v: float, name: str = "BayesB", estimatePi: bool = False) -> BayesBType:
+    """runTime.jl:55-61 — pi is the proportion of SNPs INCLUDED."""
+    return BayesBType(float(pi), float(v), name, bool(estimatePi))
+
+
+def BayesC(pi: float, v: float, name: str = "BayesC", estimatePi: bool = False) -> BayesCType:
+    """runTime.jl:70-76"""
+    return BayesCType(float(pi), float(v), name, bool(estimatePi))
+
+
+def Random(str_: Any, v: float, type: int = 1) -> RandomEffectType:
+    """runTime.jl:141-146"""
+    return RandomEffectType(str_, float(v), type)
+
+
+# ----------------------------------------------------------------------------- output (outFiles.jl)
+def outMCMC(folder: str, thisVar: str, output) -> None:
+    """Append row(s) to <folder>/<thisVar>Out, tab-delimited like writedlm (outFiles.jl:17-21)."""
+    arr = np.asarray(output)
+    if arr.ndim == 0:
+        arr = arr.reshape(1, 1)
+    elif arr.ndim == 1:
+        arr = arr.reshape(1, -1)
+    with open(os.path.join(folder, f"{thisVar}Out"), "a") as f:
+        for row in arr:
+            f.write("\t".join(_fmt(x) for x in row) + "\n")
+
+
+def _fmt(x) -> str:
+    if isinstance(x, (str, np.str_)):
+        return str(x)
+    if isinstance(x, (int, np.integer)):
+        return str(int(x))
+    return repr(float(x))
+
+
+def summaryMCMC(param: str, outFolder: str = os.path.join(os.getcwd(), "outMCMC")) -> np.ndarray:
+    """Posterior mean of every column of <outFolder>/<param>Out (misc.jl:241-244)."""
+    data = np.loadtxt(os.path.join(outFolder, f"{param}Out"), delimiter="\t", skiprows=1, ndmin=2)
+    return data.mean(axis=0, keepdims=True)
+
+
+def folderHandler(outFolder: str) -> None:
+    """misc.jl:221-232: an existing output folder is removed."""
+    if os.path.isdir(outFolder):
+        shutil.rmtree(outFolder)
+    os.mkdir(outFolder)
+
+
+# ----------------------------------------------------------------------------- ingest (prepMatVec.jl:113-134)
+def prep_snp(path_or_matrix) -> np.ndarray:
+    """Space-delimited text, no header -> int8 codes (n,p) Fortran order.  Columns containing a missing
+    or non-{0,1,2} value are dropped (the reference drops columns with `missing`, prepMatVec.jl:118).
+    Centring (prepMatVec.jl:129) happens on device: the library stores raw codes + column means."""
+    if isinstance(path_or_matrix, np.ndarray):
+        raw = np.asarray(path_or_matrix, dtype=np.float64)
+    else:
+        rows = []
+        with open(path_or_matrix) as f:
+            for line in f:
+                toks = line.rstrip("\n").split(" ")
+                rows.append([_tok(t) for t in toks])
+        raw = np.array(rows, dtype=np.float64)
+    keep = ~np.isnan(raw).any(axis=0)
+    raw = raw[:, keep]
+    ok = np.isin(raw, (0.0, 1.0, 2.0)).all(axis=0)
+    if not ok.all():
+        raise ValueError("genotype codes must be 0/1/2 for packed storage; columns %s are not" % np.where(~ok)[0][:10])
+    return np.asfortranarray(raw.astype(np.int8))
+
+
+def _tok(t: str) -> float:
+    t = t.strip()
+    if t == "" or t.upper() in ("NA", "NAN", "MISSING"):
+        return float("nan")
+    return float(t)
+
+
+def prep2RegionData(outPutFolder: str | None, markerSet: str, mapFile, fixedRegSize: int) -> np.ndarray:
+    """misc.jl:163-215.  mapFile: path of a delimited file with header snpID,snpOrder,chrID (or a dict of
+    arrays).  Returns 0-based half-open region offsets (the reference returns Vector{UnitRange})."""
+    if isinstance(mapFile, dict):
+        snp_id, snp_order, chr_id = (np.asarray(mapFile[k]) for k in ("snpID", "snpOrder", "chrID"))
+    else:
+        with open(mapFile) as f:
+            header = re.split(r"[,\t ]", f.readline().strip())
+            cols = {h: [] for h in header}
+            for line in f:
+                for h, tok in zip(header, re.split(r"[,\t ]", line.strip())):
+                    cols[h].append(tok)
+        snp_id = np.asarray(cols["snpID"])
+        snp_order = np.asarray(cols["snpOrder"])
+        chr_id = np.asarray(cols["chrID"], dtype=np.int64)
+    p = len(chr_id)
+    if fixedRegSize == 99:
+        group = chr_id.astype(np.int64).copy()
+        n_reg = len(np.unique(chr_id))
+    elif fixedRegSize == 9999:
+        group = np.ones(p, dtype=np.int64)
+        n_reg = 1
+    else:
+        group = np.empty(p, dtype=np.int64)
+        acc = 0
+        pos = 0
+        _, first = np.unique(chr_id, return_index=True)
+        for c in chr_id[np.sort(first)]:
+            tot = int(np.sum(chr_id == c))
+            nreg = -(-tot // fixedRegSize)
+            g = np.repeat(np.arange(acc + 1, acc + nreg + 1), fixedRegSize)[:tot]
+            group[pos:pos + tot] = g
+            acc += nreg
+            pos += tot
+        n_reg = acc
+    if outPutFolder is not None:
+        with open(os.path.join(outPutFolder, f"groupInfo_{markerSet}.txt"), "w") as f:
+            f.write("snpID\tsnpOrder\tchrID\tgroupID\n")
+            for a, b, c, g in zip(snp_id, snp_order, chr_id, group):
+                f.write(f"{a}\t{b}\t{c}\t{g}\n")
+    offs = [int(np.searchsorted(group, g, "left")) for g in range(1, n_reg + 1)] + [p]
+    return np.asarray(offs, dtype=np.int64)
+
+
+# ----------------------------------------------------------------------------- the handle
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+class Sampler:
+    """One chain on one GPU.  Thin, explicit wrapper over the C ABI (include/ngp.h)."""
+
+    def __init__(self, device: int = 0, kernel: str = "blocked", block: int = 0, min_rows: int = 0, max_ctas: int = 0):
+        self._lib = L.lib()
+        hp = C.c_void_p()
+        rc = self._lib.ngp_create(device, C.byref(hp))
+        if rc != 0:
+            raise L.NgpError(rc, self._lib.ngp_last_error(None).decode())
+        self._h = hp
+        self.sets: dict[int, dict] = {}
+        self.n = 0
+        self._keep = []
+        self.configure(L.CFG_KERNEL, L.KERNEL_BLOCKED if kernel == "blocked" else L.KERNEL_LITERAL)
+        if block:
+            self.configure(L.CFG_BLOCK, block)
+        if min_rows:
+            self.configure(L.CFG_MIN_ROWS, min_rows)
+        if max_ctas:
+            self.configure(L.CFG_MAX_CTAS, max_ctas)
+
+    # -- plumbing
+    def _ck(self, rc: int) -> None:
+        if rc != 0:
+            raise L.NgpError(rc, self._lib.ngp_last_error(self._h).decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.ngp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def configure(self, key: int, value: int) -> None:
+        self._ck(self._lib.ngp_configure(self._h, key, value))
+
+    def set_kernel(self, kernel: str) -> None:
+        self.configure(L.CFG_KERNEL, L.KERNEL_BLOCKED if kernel == "blocked" else L.KERNEL_LITERAL)
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        self._ck(self._lib.ngp_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    # -- data
+    def upload_genotypes(self, set_id: int, data: np.ndarray, fmt: int | None = None, n: int | None = None) -> None:
+        if fmt is None:
+            fmt = L.GENO_F64 if data.dtype == np.float64 else L.GENO_I8
+        if fmt == L.GENO_PACKED2:
+            assert n is not None and data.dtype == np.uint8
+            data = np.asfortranarray(data)
+            ld, p = data.shape
+        else:
+            data = np.asfortranarray(data, dtype=np.float64 if fmt == L.GENO_F64 else np.int8)
+            n, p = data.shape
+            ld = n
+        self._ck(self._lib.ngp_upload_genotypes(self._h, set_id, n, p, _p(data), fmt, ld, L.STORE_I8))
+        self.n = n
+        self.sets[set_id] = {"p": p}
+
+    def synth_genotypes(self, set_id: int, n: int, p: int, seed: int, thr0: np.ndarray, thr1: np.ndarray) -> None:
+        thr0 = np.ascontiguousarray(thr0, dtype=np.uint32)
+        thr1 = np.ascontiguousarray(thr1, dtype=np.uint32)
+        self._ck(self._lib.ngp_synth_genotypes(self._h, set_id, n, p, C.c_uint64(seed), _p(thr0), _p(thr1), L.STORE_I8))
+        self.n = n
+        self.sets[set_id] = {"p": p}
+
+    def download_genotypes(self, set_id: int, j0: int = 0, j1: int | None = None) -> np.ndarray:
+        p = self.sets[set_id]["p"]
+        j1 = p if j1 is None else j1
+        out = np.empty((self.n, j1 - j0), dtype=np.int8, order="F")
+        self._ck(self._lib.ngp_download_genotypes(self._h, set_id, j0, j1, _p(out)))
+        return out
+
+    def column_stats(self, set_id: int):
+        p = self.sets[set_id]["p"]
+        mean, mpm = np.empty(p), np.empty(p)
+        self._ck(self._lib.ngp_get_column_stats(self._h, set_id, _p(mean), _p(mpm)))
+        return mean, mpm
+
+    # -- model
+    def set_phenotype(self, y: np.ndarray) -> None:
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        self._ck(self._lib.ngp_set_phenotype(self._h, _p(y), len(y)))
+
+    def set_residual_prior(self, df_e: float, scale_e: float) -> None:
+        self._ck(self._lib.ngp_set_residual_prior(self._h, df_e, scale_e))
+
+    def set_intercept(self, enabled: bool = True, lhs0: float = 0.0, rhs0: float = 0.0) -> None:
+        self._ck(self._lib.ngp_set_intercept(self._h, int(enabled), lhs0, rhs0))
+
+    def set_prior(self, set_id: int, method: int, df: float, scale: float, var_init: float, pi_in: float = 0.0,
+                  est_pi: bool = False, region_off: np.ndarray | None = None, lhs0: np.ndarray | None = None,
+                  rhs0: np.ndarray | None = None) -> None:
+        pr = L.Prior()
+        pr.method, pr.est_pi, pr.df, pr.scale, pr.var_init, pr.pi_in = method, int(est_pi), df, scale, var_init, pi_in
+        p = self.sets[set_id]["p"]
+        if region_off is not None:
+            region_off = np.ascontiguousarray(region_off, dtype=np.int64)
+            pr.n_regions, pr.region_off = len(region_off) - 1, _p(region_off)
+        if lhs0 is not None:
+            lhs0 = np.ascontiguousarray(lhs0, dtype=np.float64)
+            pr.lhs0 = _p(lhs0)
+        if rhs0 is not None:
+            rhs0 = np.ascontiguousarray(rhs0, dtype=np.float64)
+            pr.rhs0 = _p(rhs0)
+        self._ck(self._lib.ngp_set_prior(self._h, set_id, C.byref(pr)))
+        nvar = (len(region_off) - 1 if region_off is not None else 1) if method == L.BAYESPR else (p if method == L.BAYESB else 1)
+        self.sets[set_id].update(method=method, nvar=nvar, est_pi=bool(est_pi))
+
+    def set_rng(self, seed: int, chain_id: int = 0) -> None:
+        self._ck(self._lib.ngp_set_rng(self._h, C.c_uint64(seed), chain_id))
+
+    def set_replay(self, logs: list[dict] | None) -> None:
+        """logs: list (one per iteration) of the oracle's variate-log dicts
+        {chi2_e, z_mu, sets:[{u,z,chi2_b,beta_pi}]}; None switches back to Philox."""
+        if logs is None:
+            self._ck(self._lib.ngp_set_replay(self._h, None))
+            return
+        rp = L.Replay()
+        ni = len(logs)
+        rp.n_iter, rp.n_sets = ni, len(logs[0]["sets"])
+        keep = []
+        chi2_e = np.array([g["chi2_e"] for g in logs], dtype=np.float64)
+        z_mu = np.array([g.get("z_mu", 0.0) for g in logs], dtype=np.float64)
+        keep += [chi2_e, z_mu]
+        rp.chi2_e, rp.z_mu = _p(chi2_e), _p(z_mu)
+        for s in range(rp.n_sets):
+            u = np.ascontiguousarray(np.stack([g["sets"][s]["u"] for g in logs]), dtype=np.float64)
+            z = np.ascontiguousarray(np.stack([g["sets"][s]["z"] for g in logs]), dtype=np.float64)
+            cb = np.ascontiguousarray(np.stack([g["sets"][s]["chi2_b"] for g in logs]), dtype=np.float64)
+            bp = np.array([g["sets"][s]["beta_pi"] for g in logs], dtype=np.float64)
+            keep += [u, z, cb, bp]
+            rp.u[s], rp.z[s], rp.chi2_b[s], rp.beta_pi[s] = _p(u), _p(z), _p(cb), _p(bp)
+        self._ck(self._lib.ngp_set_replay(self._h, C.byref(rp)))
+
+    # -- sampling
+    def run(self, n_iter: int = 1) -> None:
+        self._ck(self._lib.ngp_run(self._h, n_iter))
+
+    def sweep(self, set_id: int, ycorr: np.ndarray, varE: float, beta: np.ndarray, delta: np.ndarray,
+              varBeta: np.ndarray, piHat: np.ndarray | None = None) -> None:
+        """M[mSet].funct(mSet,M,beta,delta,ycorr,varE,varBeta): host arrays, mutated in place."""
+        for a, dt in ((ycorr, np.float64), (beta, np.float64), (delta, np.int64), (varBeta, np.float64)):
+            assert a.dtype == dt and a.flags.c_contiguous
+        self._ck(self._lib.ngp_sweep(self._h, set_id, _p(ycorr), varE, _p(beta), _p(delta), _p(varBeta), _p(piHat)))
+
+    def state(self, want_e: bool = True) -> dict:
+        st = L.State()
+        e = np.empty(self.n) if want_e else None
+        st.e = _p(e)
+        bufs = {}
+        for s, info in self.sets.items():
+            if "method" not in info:
+                continue
+            b, d, v = np.empty(info["p"]), np.empty(info["p"], dtype=np.int64), np.empty(info["nvar"])
+            bufs[s] = (b, d, v)
+            st.beta[s], st.delta[s], st.varBeta[s] = _p(b), _p(d), _p(v)
+        self._ck(self._lib.ngp_get_state(self._h, C.byref(st)))
+        return {"e": e, "mu": st.mu, "varE": st.varE, "iter": st.iter,
+                "sets": {s: {"beta": b, "delta": d, "varBeta": v, "piHat": np.array([st.pi[s][0], st.pi[s][1]])}
+                         for s, (b, d, v) in bufs.items()}}
+
+    def set_state(self, e=None, mu=0.0, varE=0.0, iter=0, sets: dict | None = None) -> None:
+        st = L.State()
+        keep = []
+        if e is not None:
+            e = np.ascontiguousarray(e, dtype=np.float64); keep.append(e); st.e = _p(e)
+        st.mu, st.varE, st.iter = mu, varE, iter
+        for s, d in (sets or {}).items():
+            for key, dt, fld in (("beta", np.float64, st.beta), ("delta", np.int64, st.delta), ("varBeta", np.float64, st.varBeta)):
+                if key in d:
+                    a = np.ascontiguousarray(d[key], dtype=dt); keep.append(a); fld[s] = _p(a)
+            ph = d.get("piHat", (0.5, 0.5))
+            st.pi[s][0], st.pi[s][1] = ph[0], ph[1]
+        self._ck(self._lib.ngp_set_state(self._h, C.byref(st)))
+
+    def reset_posterior(self) -> None:
+        self._ck(self._lib.ngp_reset_posterior(self._h))
+
+    def posterior(self, set_id: int) -> dict:
+        p = self.sets[set_id]["p"]
+        n = C.c_int64()
+        sb, sb2, sd = np.empty(p), np.empty(p), np.empty(p)
+        self._ck(self._lib.ngp_get_posterior(self._h, set_id, C.byref(n), _p(sb), _p(sb2), _p(sd)))
+        k = max(n.value, 1)
+        return {"n": n.value, "mean_beta": sb / k, "mean_beta2": sb2 / k, "mean_delta": sd / k}
+
+    def timing(self) -> dict:
+        t = L.Timing()
+        self._ck(self._lib.ngp_get_timing(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in L.Timing._fields_}
+
+    def debug_variates(self, set_id: int, it: int, purpose: int, df: float, n: int) -> np.ndarray:
+        out = np.empty(n)
+        self._ck(self._lib.ngp_debug_variates(self._h, set_id, it, purpose, df, n, _p(out)))
+        return out
+
+
+# ----------------------------------------------------------------------------- getMME / runSampler / runLMEM
+@dataclass
+class MarkerTerm:
+    name: str
+    codes: np.ndarray            # int8 (n,p)
+    map: Any = None              # map file path / dict or None
+    levels: list = field(default_factory=list)
+
+
+def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict, summaryStat: dict | None, outPut: str | None,
+           intercept: bool = True):
+    """mme.getMME! for intercept + marker sets: derives df/scale/regions (mme.jl:87-94, 324-373, 492-520), uploads
+    everything through the C ABI and writes the header rows of the output files (mme.jl:543-595)."""
+    summaryStat = summaryStat or {}
+    if "e" not in priorVCV:
+        priorVCV = dict(priorVCV, e=Random("I", 100.0))                       # mme.jl:79-84
+    e_prior = priorVCV["e"]
+    if not (e_prior.str in ("I", [], None, "")):
+        raise NotImplementedError("weighted residuals (E.str == \"D\") stay in Julia: SURVEY §8(f3)")
+    df_e = 4.0
+    scale_e = 0.0005 if e_prior.v == 0.0 else e_prior.v * (df_e - 2.0) / df_e  # mme.jl:87-94
+    info = []
+    for sid, term in enumerate(M):
+        sampler.upload_genotypes(sid, term.codes)
+        p = term.codes.shape[1]
+        pr = priorVCV.get(term.name)
+        lhs0 = rhs0 = None
+        if term.name in summaryStat:                                           # mme.jl:314-322
+            ss = summaryStat[term.name]
+            v = np.asarray(ss.v, dtype=np.float64)
+            v = np.diag(v) if v.ndim == 2 else np.broadcast_to(v, (p,))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                lhs0 = 1.0 / v
+                rhs0 = lhs0 * np.broadcast_to(np.asarray(ss.m, dtype=np.float64), (p,))
+            lhs0 = np.where(np.isinf(lhs0), 0.0, lhs0)
+            rhs0 = np.where(np.isnan(rhs0), 0.0, rhs0)
+        if pr is None:                                                         # mme.jl:324-329, 503-504, 518
+            method, v, region_off, pi, est = L.BAYESPR, 0.05, None, 0.0, False
+            name = "BayesPR"
+        else:
+            name, v = pr.name, pr.v
+            pi, est = getattr(pr, "pi", 0.0), getattr(pr, "estimatePi", False)
+            if name == "BayesPR":
+                method = L.BAYESPR
+                if term.map is None or (isinstance(term.map, str) and term.map == ""):   # mme.jl:334-343
+                    if pr.r == 1:
+                        region_off = np.arange(p + 1, dtype=np.int64)
+                    elif pr.r == 9999:
+                        region_off = None
+                    else:
+                        raise ValueError("Please enter a valid region size (1 or 9999)")
+                else:
+                    region_off = prep2RegionData(outPut, term.name, term.map, pr.r)      # mme.jl:345-347
+            elif name == "BayesB":
+                method, region_off = L.BAYESB, None
+            elif name == "BayesC":
+                method, region_off = L.BAYESC, None
+            else:
+                raise NotImplementedError(f"{name} stays in Julia: SURVEY §8(f2)")
+        df = 3.0 + 1.0                                                          # mme.jl:493 (scalar v)
+        scale = v * (df - 2.0) / df                                             # mme.jl:501
+        sampler.set_prior(sid, method, df, scale, v, pi_in=pi, est_pi=est, region_off=region_off, lhs0=lhs0, rhs0=rhs0)
+        nvar = sampler.sets[sid]["nvar"]
+        info.append({"name": term.name, "method": name, "p": p, "nvar": nvar, "df": df, "scale": scale})
+    sampler.set_phenotype(Y)
+    sampler.set_residual_prior(df_e, scale_e)
+    sampler.set_intercept(intercept)
+    if outPut is not None:                                                       # header rows, mme.jl:543-595
+        outMCMC(outPut, "b", [["(Intercept)"]] if intercept else [[]])
+        for term, inf in zip(M, info):
+            levels = term.levels or [f"M{i}" for i in range(1, inf["p"] + 1)]
+            outMCMC(outPut, f"beta{term.name}", [levels])
+            outMCMC(outPut, f"delta{term.name}", [levels])
+            if inf["method"] in ("BayesB", "BayesC"):
+                outMCMC(outPut, f"pi{term.name}", [["pi1", "pi2"]])
+        for term, inf in zip(M, info):
+            outMCMC(outPut, f"var{term.name}", [[f"reg_{r}" for r in range(1, inf["nvar"] + 1)]])
+        outMCMC(outPut, "varE", [["e"]])
+    return {"df_e": df_e, "scale_e": scale_e, "sets": info}
+
+
+def runSampler(sampler: Sampler, M: list[MarkerTerm], info: dict, chainLength: int, burnIn: int, outputFreq: int, outPut: str | None,
+               intercept: bool = True, on_sample=None) -> None:
+    """samplers.runSampler! (samplers.jl:23-106): iterations run on device in batches that end on a kept iteration;
+    kept samples are written in the order of samplers.jl:57-103."""
+    these2Keep = list(range(burnIn + outputFreq, chainLength + 1, outputFreq))   # samplers.jl:26
+    done = 0
+    if burnIn > 0:
+        sampler.run(min(burnIn, chainLength))
+        done = min(burnIn, chainLength)
+    sampler.reset_posterior()                                                    # device-side posterior sums exclude burn-in
+    for it in these2Keep:
+        sampler.run(it - done)
+        done = it
+        st = sampler.state(want_e=False)
+        if outPut is not None:
+            outMCMC(outPut, "b", [[st["mu"]]] if intercept else [[]])
+            outMCMC(outPut, "varE", st["varE"])
+            for sid, (term, inf) in enumerate(zip(M, info["sets"])):
+                outMCMC(outPut, f"beta{term.name}", st["sets"][sid]["beta"])
+                outMCMC(outPut, f"delta{term.name}", st["sets"][sid]["delta"])
+                if inf["method"] in ("BayesB", "BayesC"):
+                    outMCMC(outPut, f"pi{term.name}", st["sets"][sid]["piHat"])
+            for sid, term in enumerate(M):
+                outMCMC(outPut, f"var{term.name}", st["sets"][sid]["varBeta"])
+        if on_sample is not None:
+            on_sample(it, st)
+    if done < chainLength:
+        sampler.run(chainLength - done)
+
+
+_SNP_RE = re.compile(r"SNP\(\s*([A-Za-z_]\w*)\s*,\s*([^,\)]+?)\s*(?:,\s*([^\)]+?)\s*)?\)")
+
+
+def runLMEM(formula: str, userData, nChain: int, nBurn: int, nThin: int, outFolder: str = "outMCMC", VCV: dict | None = None,
+            summaryStat: dict | None = None, device: int = 0, seed: int = 0, chain_id: int = 0, matrices: dict | None = None,
+            sampler: Sampler | None = None) -> Sampler:
+    """MCMC.runLMEM (MCMC.jl:31-41) for formulas of the form  "y ~ 1 + SNP(M,geno.txt[,map.txt]) [+ SNP(...)]".
+    userData: mapping with the response column.  matrices: optional {name: ndarray of codes} instead of files.
+    Any other term (fixed covariates, PED, (1|g), GBLUP) stays in Julia — use ngp_sweep from the Julia shim."""
+    VCV = VCV or {}
+    lhs, rhs = [s.strip() for s in formula.split("~")]
+    terms = [t.strip() for t in re.split(r"\+(?![^(]*\))", rhs)]
+    intercept = False
+    M: list[MarkerTerm] = []
+    for t in terms:
+        if t == "1":
+            intercept = True
+        elif t == "0" or t == "-1":
+            intercept = False
+        else:
+            m = _SNP_RE.fullmatch(t)
+            if not m:
+                raise NotImplementedError(f"term '{t}' is outside the B200 hot path (stays in Julia)")
+            name, path, mp = m.group(1), m.group(2).strip("\"'"), (m.group(3) or "").strip("\"'")
+            codes = prep_snp(matrices[name]) if (matrices and name in matrices) else prep_snp(path)
+            M.append(MarkerTerm(name, codes, mp or None))
+    Y = np.asarray(userData[lhs], dtype=np.float64)
+    folderHandler(outFolder)
+    sampler = sampler or Sampler(device)
+    sampler.set_rng(seed, chain_id)
+    info = getMME(sampler, Y, M, VCV, summaryStat, outFolder, intercept=intercept)
+    runSampler(sampler, M, info, nChain, nBurn, nThin, outFolder, intercept=intercept)
+    return sampler

@@ -1,0 +1,948 @@
+// ngp_api.cu — C ABI of libngp.so (include/ngp.h) and the set-up kernels:
+// genotype packing into the row-panelled layout, column statistics (mean, mpm =
+// X_j'X_j, replacing /root/reference/src/mme.jl:305-307), block Gram matrices,
+// synthetic-genotype generator, unpacking for round-trip tests.
+//
+// There is no CPU code path for any sampler arithmetic in this library.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/ngp.h"
+#include "ngp_sweep.cuh"
+
+using namespace ngp;
+
+// ============================================================================= set-up kernels
+namespace {
+
+__device__ __forceinline__ int block_sum_int(int v, int* scratch)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int s = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += scratch[i];
+    __syncthreads();
+    return s;
+}
+
+// one CTA per column of the chunk: validate, encode, scatter into the panel layout, column sums
+template <int FMT>
+__global__ void pack_kernel(const void* __restrict__ src, int64_t ld, int64_t n, int64_t j0, int R, int64_t p_pad,
+                            uint8_t* __restrict__ geno, int32_t* __restrict__ colsum, int32_t* __restrict__ colsumsq,
+                            int* __restrict__ err)
+{
+    __shared__ int scratch[32];
+    const int64_t jc = blockIdx.x, j = j0 + jc;
+    int s = 0, ss = 0, bad = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        int g;
+        if (FMT == NGP_GENO_I8) {
+            g = reinterpret_cast<const int8_t*>(src)[jc * ld + i];
+        } else if (FMT == NGP_GENO_F64) {
+            const double x = reinterpret_cast<const double*>(src)[jc * ld + i];
+            g = (x == 0.0) ? 0 : (x == 1.0) ? 1 : (x == 2.0) ? 2 : -1;
+        } else {
+            g = (reinterpret_cast<const uint8_t*>(src)[jc * ld + (i >> 2)] >> (2 * (int)(i & 3))) & 3;
+        }
+        if (g < 0 || g > 2) { bad = 1; g = 0; }
+        s += g; ss += g * g;
+        const int64_t t = i / R;
+        const int r = (int)(i - t * R);
+        geno[(t * p_pad + j) * R + r] = enc_code(g);
+    }
+    s = block_sum_int(s, scratch);
+    ss = block_sum_int(ss, scratch);
+    if (bad) atomicOr(err, 1);
+    if (threadIdx.x == 0) { colsum[j] = s; colsumsq[j] = ss; }
+}
+
+__global__ void colstats_kernel(int64_t n, int64_t p, int64_t p_pad, const int32_t* colsum, const int32_t* colsumsq,
+                                double* mean, double* d)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p_pad) return;
+    if (j < p) {
+        const double s = (double)colsum[j], ss = (double)colsumsq[j], nn = (double)n;
+        mean[j] = s / nn;                         // mean(thisM,dims=1), prepMatVec.jl:129
+        d[j] = (nn * ss - s * s) / nn;            // sum (g - mean)^2 = dot(c,c), mme.jl:306 (integer-exact numerator)
+    } else { mean[j] = 0.0; d[j] = 0.0; }
+}
+
+// raw block Gram G[k][a][b] = sum_i g_ia g_ib over all panels; one CTA (16x16 threads) per block of B markers
+template <int B>
+__global__ void __launch_bounds__(256) gram_kernel(const uint8_t* __restrict__ geno, int T, int R, int64_t p_pad,
+                                                   int32_t* __restrict__ gram)
+{
+    extern __shared__ __align__(16) unsigned char gsm[];
+    constexpr int TB = B / 16;
+    const int k = blockIdx.x, tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int W = R >> 2;
+    int acc[TB][TB];
+#pragma unroll
+    for (int i = 0; i < TB; ++i)
+#pragma unroll
+        for (int q = 0; q < TB; ++q) acc[i][q] = 0;
+    const int nvec = (B * R) >> 4;
+    for (int t = 0; t < T; ++t) {
+        const uint4* src = reinterpret_cast<const uint4*>(geno + ((int64_t)t * p_pad + (int64_t)k * B) * R);
+        uint4* dst = reinterpret_cast<uint4*>(gsm);
+        for (int v = threadIdx.x; v < nvec; v += 256) dst[v] = __ldg(src + v);
+        __syncthreads();
+        const uint32_t* tw = reinterpret_cast<const uint32_t*>(gsm);
+        for (int w = 0; w < W; ++w) {
+            int a[TB], b[TB];
+#pragma unroll
+            for (int i = 0; i < TB; ++i) {
+                a[i] = (int)((tw[(ty * TB + i) * W + w] >> 2) & 0x03030303u);
+                b[i] = (int)((tw[(tx * TB + i) * W + w] >> 2) & 0x03030303u);
+            }
+#pragma unroll
+            for (int i = 0; i < TB; ++i)
+#pragma unroll
+                for (int q = 0; q < TB; ++q) acc[i][q] = __dp4a(a[i], b[q], acc[i][q]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TB; ++i)
+#pragma unroll
+        for (int q = 0; q < TB; ++q) gram[(int64_t)k * B * B + (ty * TB + i) * B + tx * TB + q] = acc[i][q];
+}
+
+__global__ void synth_kernel(uint32_t key0, uint32_t key1, int64_t n, int64_t j0, int64_t ncols,
+                             const uint32_t* __restrict__ thr0, const uint32_t* __restrict__ thr1, int8_t* __restrict__ out)
+{
+    const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int64_t jc = blockIdx.y;
+    if (i4 >= n || jc >= ncols) return;
+    const int64_t j = j0 + jc;
+    uint32_t w[4];
+    philox4x32_10((uint32_t)(i4 >> 2), (uint32_t)j, 0u, 0x47454e4fu, key0, key1, w);
+    const uint32_t a = thr0[j], b = thr1[j];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (i4 + q < n) out[jc * n + i4 + q] = (int8_t)((w[q] >= a) + (w[q] >= b));
+}
+
+__global__ void unpack_kernel(const uint8_t* __restrict__ geno, int64_t n, int R, int64_t p_pad, int64_t j0, int64_t ncols,
+                              int8_t* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t jc = blockIdx.y;
+    if (i >= n || jc >= ncols) return;
+    const int64_t t = i / R;
+    out[jc * n + i] = (int8_t)dec_code(geno[(t * p_pad + j0 + jc) * R + (i - t * R)]);
+}
+
+__global__ void region_of_kernel(const int64_t* region_off, int64_t n_regions, int32_t* region_of)
+{
+    for (int64_t r = blockIdx.x; r < n_regions; r += gridDim.x)
+        for (int64_t j = region_off[r] + threadIdx.x; j < region_off[r + 1]; j += blockDim.x) region_of[j] = (int32_t)r;
+}
+
+__global__ void fill_kernel(double* x, int64_t n, double v)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+__global__ void fill_i32_kernel(int32_t* x, int64_t n, int32_t v)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+
+__global__ void debug_variates_kernel(uint32_t key0, uint32_t key1, uint32_t chain, uint32_t iter, uint32_t set_id,
+                                      int purpose, double df, int64_t n, double* out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Stream st{key0, key1, chain, iter, set_id};
+    double v;
+    if (purpose == P_U) v = stream_uniform(st, P_U, (uint32_t)i);
+    else if (purpose == P_Z) v = stream_normal(st, P_Z, (uint32_t)i);
+    else if (purpose == P_PI_A) v = stream_beta(st, df, (double)(i + 1));
+    else v = stream_chisq(st, P_CHI2_B, (uint32_t)i, 0, df);
+    out[i] = v;
+}
+
+}  // namespace
+
+// ============================================================================= handle
+struct SetHost {
+    bool have_geno = false, have_prior = false;
+    int64_t p = 0, p_pad = 0, nvar = 0, n_regions = 0;
+    int method = 0, est_pi = 0, storage = 0;
+    double df = 4.0, scale = 0.0, var_init = 0.0, pi_in = 0.0;
+    uint8_t* geno = nullptr;
+    int32_t *gram = nullptr, *colsum = nullptr, *colsumsq = nullptr, *delta = nullptr, *region_of = nullptr;
+    double *d = nullptr, *mean = nullptr, *beta = nullptr, *varBeta = nullptr, *pi = nullptr, *consts = nullptr;
+    double *lhs0 = nullptr, *rhs0 = nullptr, *sum_beta = nullptr, *sum_beta2 = nullptr, *sum_delta = nullptr;
+    int64_t* region_off = nullptr;
+    double *rp_u = nullptr, *rp_z = nullptr, *rp_chi2b = nullptr, *rp_betapi = nullptr;
+};
+
+struct ngp_handle {
+    int device = 0;
+    cudaDeviceProp prop{};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    // geometry
+    int64_t n = 0;
+    int T = 0, R = 0, B = 0, stages = 0;
+    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0;
+    SmemLayout L{};
+    // model
+    SetHost sets[NGP_MAX_SETS];
+    int n_sets = 0;
+    double* e = nullptr;
+    bool have_y = false;
+    double df_e = 4.0, scale_e = 0.0;
+    int has_mu = 0;
+    double mu_lhs0 = 0.0, mu_rhs0 = 0.0;
+    SetDev* sets_dev = nullptr;
+    bool sets_dirty = true;
+    Scalars* sc = nullptr;
+    SyncArea* sync = nullptr;
+    // variates
+    uint64_t seed = 0;
+    uint32_t chain = 0;
+    int replay = 0, replay_iters = 0;
+    int64_t replay_base = 0;
+    double *rp_chi2_e = nullptr, *rp_z_mu = nullptr;
+    // stats
+    int64_t launches = 0;
+    bool timed = false;
+};
+
+static std::string g_create_err;
+
+static int fail(ngp_handle* h, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(h, NGP_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// every copy / memset is ordered on the handle's stream (own stream is non-blocking, so the
+// legacy default stream would NOT be ordered against the sweep kernel)
+static cudaError_t cpy(ngp_handle* h, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind)
+{
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, h->stream);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(h->stream);
+}
+static cudaError_t zero(ngp_handle* h, void* dst, int v, size_t bytes) { return cudaMemsetAsync(dst, v, bytes, h->stream); }
+
+template <class Tp>
+static cudaError_t dalloc(Tp** p, size_t count)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(Tp));
+}
+
+static void free_set(SetHost& s)
+{
+    cudaFree(s.geno); cudaFree(s.gram); cudaFree(s.colsum); cudaFree(s.colsumsq); cudaFree(s.delta); cudaFree(s.region_of);
+    cudaFree(s.d); cudaFree(s.mean); cudaFree(s.beta); cudaFree(s.varBeta); cudaFree(s.pi); cudaFree(s.consts);
+    cudaFree(s.lhs0); cudaFree(s.rhs0); cudaFree(s.sum_beta); cudaFree(s.sum_beta2); cudaFree(s.sum_delta);
+    cudaFree(s.region_off); cudaFree(s.rp_u); cudaFree(s.rp_z); cudaFree(s.rp_chi2b); cudaFree(s.rp_betapi);
+    s = SetHost();
+}
+
+extern "C" {
+
+int ngp_abi_version(void) { return NGP_ABI_VERSION; }
+
+int ngp_device_count(void)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+const char* ngp_last_error(const ngp_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int ngp_create(int device, ngp_handle** out)
+{
+    ngp_handle* h = nullptr;
+    if (!out) return fail(h, NGP_EINVAL, "ngp_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(h, NGP_ECUDA, "ngp_create: no CUDA device (%s); libngp has no CPU fallback",
+                    ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+    }
+    if (device < 0 || device >= count) return fail(h, NGP_EINVAL, "ngp_create: device %d out of range [0,%d)", device, count);
+    ngp_handle* nh = new ngp_handle();
+    nh->device = device;
+    h = nullptr;
+    CU(cudaSetDevice(device));
+    CU(cudaGetDeviceProperties(&nh->prop, device));
+    if (nh->prop.major < 10) {
+        int maj = nh->prop.major, mnr = nh->prop.minor;
+        delete nh;
+        return fail(h, NGP_EUNSUPPORTED, "ngp_create: device is sm_%d%d; libngp is built for sm_100a only", maj, mnr);
+    }
+    h = nh;
+    CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    CU(cudaMalloc((void**)&h->sc, sizeof(Scalars)));
+    CU(zero(h, h->sc, 0, sizeof(Scalars)));
+    CU(cudaMalloc((void**)&h->sync, sizeof(SyncArea)));
+    CU(zero(h, h->sync, 0, sizeof(SyncArea)));
+    CU(cudaMalloc((void**)&h->sets_dev, sizeof(SetDev) * NGP_MAX_SETS));
+    *out = h;
+    return NGP_OK;
+}
+
+int ngp_destroy(ngp_handle* h)
+{
+    if (!h) return NGP_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& s : h->sets) free_set(s);
+    cudaFree(h->e); cudaFree(h->sc); cudaFree(h->sync); cudaFree(h->sets_dev);
+    cudaFree(h->rp_chi2_e); cudaFree(h->rp_z_mu);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return NGP_OK;
+}
+
+int ngp_configure(ngp_handle* h, int key, int64_t value)
+{
+    if (!h) return NGP_EINVAL;
+    switch (key) {
+    case NGP_CFG_KERNEL:
+        if (value != NGP_KERNEL_BLOCKED && value != NGP_KERNEL_LITERAL) return fail(h, NGP_EINVAL, "ngp_configure: unknown kernel %lld", (long long)value);
+        h->cfg_kernel = (int)value; return NGP_OK;
+    case NGP_CFG_BLOCK:
+        if (h->T) return fail(h, NGP_EINVAL, "ngp_configure: block size must be set before the first upload");
+        if (value != 0 && value != 32 && value != 64) return fail(h, NGP_EINVAL, "ngp_configure: block must be 0, 32 or 64");
+        h->cfg_block = (int)value; return NGP_OK;
+    case NGP_CFG_MIN_ROWS:
+        if (h->T) return fail(h, NGP_EINVAL, "ngp_configure: min rows must be set before the first upload");
+        if (value < 8) return fail(h, NGP_EINVAL, "ngp_configure: min rows must be >= 8");
+        h->cfg_min_rows = (int)value; return NGP_OK;
+    case NGP_CFG_MAX_CTAS:
+        if (h->T) return fail(h, NGP_EINVAL, "ngp_configure: max CTAs must be set before the first upload");
+        if (value < 0) return fail(h, NGP_EINVAL, "ngp_configure: max CTAs must be >= 0");
+        h->cfg_max_ctas = (int)value; return NGP_OK;
+    default: return fail(h, NGP_EINVAL, "ngp_configure: unknown key %d", key);
+    }
+}
+
+int ngp_set_stream(ngp_handle* h, void* cuda_stream)
+{
+    if (!h) return NGP_EINVAL;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return NGP_OK;
+}
+
+// ----------------------------------------------------------------------------- geometry
+static int choose_geometry(ngp_handle* h, int64_t n)
+{
+    const int sms = h->prop.multiProcessorCount;
+    int maxc = h->cfg_max_ctas ? std::min(h->cfg_max_ctas, sms) : sms;
+    maxc = std::min(maxc, kMaxCtas);
+    int64_t want = (n + h->cfg_min_rows - 1) / h->cfg_min_rows;
+    int T = (int)std::max<int64_t>(1, std::min<int64_t>(maxc, want));
+    int64_t R8 = (n + 8LL * T - 1) / (8LL * T);
+    if (R8 % 2 == 0) R8 += 1;                      // R = 8*odd: conflict-free 64-bit smem column reads
+    const int64_t R = 8 * R8;
+    const size_t cap = h->prop.sharedMemPerBlockOptin;
+    const int candB[2] = {64, 32};
+    const int candS[2] = {3, 2};
+    for (int bi = 0; bi < 2; ++bi) {
+        if (h->cfg_block && candB[bi] != h->cfg_block) continue;
+        for (int si = 0; si < 2; ++si) {
+            SmemLayout L = smem_layout((int)R, candB[bi], candS[si]);
+            if ((size_t)L.total + 1024 <= cap) {
+                h->n = n; h->T = T; h->R = (int)R; h->B = candB[bi]; h->stages = candS[si]; h->L = L;
+                return NGP_OK;
+            }
+        }
+    }
+    return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA: the panel tile does not fit in %zu bytes of shared memory",
+                (long long)n, (long long)R, cap);
+}
+
+static int finish_upload(ngp_handle* h, SetHost& S)
+{
+    const int64_t p_pad = S.p_pad;
+    CU(dalloc(&S.mean, p_pad));
+    CU(dalloc(&S.d, p_pad));
+    colstats_kernel<<<(unsigned)((p_pad + 255) / 256), 256, 0, h->stream>>>(h->n, S.p, p_pad, S.colsum, S.colsumsq, S.mean, S.d);
+    CU(cudaGetLastError());
+    const int nblk = (int)(p_pad / h->B);
+    CU(dalloc(&S.gram, (size_t)nblk * h->B * h->B));
+    const size_t gsm = (size_t)h->B * h->R;
+    if (h->B == 64) {
+        CU(cudaFuncSetAttribute(gram_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+        gram_kernel<64><<<nblk, 256, gsm, h->stream>>>(S.geno, h->T, h->R, p_pad, S.gram);
+    } else {
+        CU(cudaFuncSetAttribute(gram_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+        gram_kernel<32><<<nblk, 256, gsm, h->stream>>>(S.geno, h->T, h->R, p_pad, S.gram);
+    }
+    CU(cudaGetLastError());
+    CU(dalloc(&S.consts, (size_t)nblk * kNF * h->B));
+    CU(dalloc(&S.beta, p_pad));
+    CU(dalloc(&S.delta, p_pad));
+    CU(cudaMemsetAsync(S.beta, 0, sizeof(double) * p_pad, h->stream));
+    fill_i32_kernel<<<(unsigned)((p_pad + 255) / 256), 256, 0, h->stream>>>(S.delta, p_pad, 1);   // delta = ones (mme.jl:444)
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    S.have_geno = true;
+    S.have_prior = false;
+    h->sets_dirty = true;
+    return NGP_OK;
+}
+
+static int begin_upload(ngp_handle* h, int set_id, int64_t n, int64_t p, int storage)
+{
+    if (!h) return NGP_EINVAL;
+    if (set_id < 0 || set_id >= NGP_MAX_SETS) return fail(h, NGP_EINVAL, "set_id %d out of range", set_id);
+    if (n <= 0 || p <= 0) return fail(h, NGP_EINVAL, "n and p must be positive");
+    if (p > 0x7fffffffLL || n > 0x7fffffffLL) return fail(h, NGP_EINVAL, "n and p must fit in 31 bits");
+    if (storage != NGP_STORE_I8) return fail(h, NGP_EUNSUPPORTED, "device storage %d is not available in this build (use NGP_STORE_I8)", storage);
+    CU(cudaSetDevice(h->device));
+    if (h->T == 0) {
+        int rc = choose_geometry(h, n);
+        if (rc) return rc;
+        CU(dalloc(&h->e, (size_t)h->T * h->R));
+        CU(zero(h, h->e, 0, sizeof(double) * (size_t)h->T * h->R));
+    } else if (n != h->n) {
+        return fail(h, NGP_EINVAL, "all marker sets of a handle must have n = %lld individuals (got %lld)", (long long)h->n, (long long)n);
+    }
+    SetHost& S = h->sets[set_id];
+    free_set(S);
+    S.p = p;
+    S.p_pad = ((p + kMaxB - 1) / kMaxB) * kMaxB;
+    S.storage = storage;
+    const size_t gbytes = (size_t)h->T * S.p_pad * h->R;
+    CU(dalloc(&S.geno, gbytes));
+    CU(cudaMemsetAsync(S.geno, 0xF0, gbytes, h->stream));          // code 0 everywhere (pad rows / pad markers)
+    CU(dalloc(&S.colsum, S.p_pad));
+    CU(dalloc(&S.colsumsq, S.p_pad));
+    CU(cudaMemsetAsync(S.colsum, 0, sizeof(int32_t) * S.p_pad, h->stream));
+    CU(cudaMemsetAsync(S.colsumsq, 0, sizeof(int32_t) * S.p_pad, h->stream));
+    h->n_sets = std::max(h->n_sets, set_id + 1);
+    return NGP_OK;
+}
+
+int ngp_upload_genotypes(ngp_handle* h, int set_id, int64_t n, int64_t p, const void* data, int fmt, int64_t ld, int storage)
+{
+    if (!h) return NGP_EINVAL;
+    if (!data) return fail(h, NGP_EINVAL, "ngp_upload_genotypes: data is NULL");
+    if (fmt != NGP_GENO_I8 && fmt != NGP_GENO_F64 && fmt != NGP_GENO_PACKED2) return fail(h, NGP_EINVAL, "unknown genotype format %d", fmt);
+    const int64_t min_ld = (fmt == NGP_GENO_PACKED2) ? (n + 3) / 4 : n;
+    if (ld < min_ld) return fail(h, NGP_EINVAL, "ld = %lld is smaller than a column (%lld)", (long long)ld, (long long)min_ld);
+    int rc = begin_upload(h, set_id, n, p, storage);
+    if (rc) return rc;
+    SetHost& S = h->sets[set_id];
+    const size_t elem = (fmt == NGP_GENO_F64) ? 8 : 1;
+    const size_t colbytes = (size_t)ld * elem;
+    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(p, (int64_t)((256u << 20) / colbytes)));
+    chunk = std::min<int64_t>(chunk, 65535);
+    void* stage = nullptr;
+    int* derr = nullptr;
+    CU(cudaMalloc(&stage, colbytes * chunk));
+    CU(cudaMalloc((void**)&derr, sizeof(int)));
+    CU(cudaMemsetAsync(derr, 0, sizeof(int), h->stream));
+    for (int64_t j0 = 0; j0 < p; j0 += chunk) {
+        const int64_t nc = std::min(chunk, p - j0);
+        CU(cudaMemcpyAsync(stage, (const char*)data + (size_t)j0 * colbytes, colbytes * nc, cudaMemcpyHostToDevice, h->stream));
+        if (fmt == NGP_GENO_I8) pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, S.p_pad, S.geno, S.colsum, S.colsumsq, derr);
+        else if (fmt == NGP_GENO_F64) pack_kernel<NGP_GENO_F64><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, S.p_pad, S.geno, S.colsum, S.colsumsq, derr);
+        else pack_kernel<NGP_GENO_PACKED2><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, S.p_pad, S.geno, S.colsum, S.colsumsq, derr);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));     // the pageable source buffer is borrowed per chunk
+    }
+    int herr = 0;
+    CU(cpy(h, &herr, derr, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(stage); cudaFree(derr);
+    if (herr) { free_set(S); return fail(h, NGP_EDATA, "genotype value outside {0,1,2} (missing data must be removed before upload)"); }
+    return finish_upload(h, S);
+}
+
+int ngp_synth_genotypes(ngp_handle* h, int set_id, int64_t n, int64_t p, uint64_t seed, const uint32_t* thr0, const uint32_t* thr1, int storage)
+{
+    if (!h) return NGP_EINVAL;
+    if (!thr0 || !thr1) return fail(h, NGP_EINVAL, "ngp_synth_genotypes: thresholds are NULL");
+    int rc = begin_upload(h, set_id, n, p, storage);
+    if (rc) return rc;
+    SetHost& S = h->sets[set_id];
+    uint32_t *d0 = nullptr, *d1 = nullptr;
+    int8_t* stage = nullptr;
+    int* derr = nullptr;
+    CU(cudaMalloc((void**)&d0, sizeof(uint32_t) * p));
+    CU(cudaMalloc((void**)&d1, sizeof(uint32_t) * p));
+    CU(cpy(h, d0, thr0, sizeof(uint32_t) * p, cudaMemcpyHostToDevice));
+    CU(cpy(h, d1, thr1, sizeof(uint32_t) * p, cudaMemcpyHostToDevice));
+    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(p, (int64_t)((512u << 20) / (size_t)n)));
+    chunk = std::min<int64_t>(chunk, 65535);
+    CU(cudaMalloc((void**)&stage, (size_t)n * chunk));
+    CU(cudaMalloc((void**)&derr, sizeof(int)));
+    CU(cudaMemsetAsync(derr, 0, sizeof(int), h->stream));
+    for (int64_t j0 = 0; j0 < p; j0 += chunk) {
+        const int64_t nc = std::min(chunk, p - j0);
+        dim3 grid((unsigned)(((n + 3) / 4 + 255) / 256), (unsigned)nc);
+        synth_kernel<<<grid, 256, 0, h->stream>>>((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), n, j0, nc, d0, d1, stage);
+        CU(cudaGetLastError());
+        pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, n, n, j0, h->R, S.p_pad, S.geno, S.colsum, S.colsumsq, derr);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(stage); cudaFree(derr); cudaFree(d0); cudaFree(d1);
+    return finish_upload(h, S);
+}
+
+int ngp_download_genotypes(ngp_handle* h, int set_id, int64_t j0, int64_t j1, int8_t* out)
+{
+    if (!h || set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_geno) return fail(h, NGP_EINVAL, "ngp_download_genotypes: no such set");
+    SetHost& S = h->sets[set_id];
+    if (j0 < 0 || j1 > S.p || j0 >= j1 || !out) return fail(h, NGP_EINVAL, "ngp_download_genotypes: bad column range");
+    CU(cudaSetDevice(h->device));
+    const int64_t n = h->n;
+    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(j1 - j0, (int64_t)((256u << 20) / (size_t)n)));
+    chunk = std::min<int64_t>(chunk, 65535);
+    int8_t* stage = nullptr;
+    CU(cudaMalloc((void**)&stage, (size_t)n * chunk));
+    for (int64_t c0 = j0; c0 < j1; c0 += chunk) {
+        const int64_t nc = std::min(chunk, j1 - c0);
+        dim3 grid((unsigned)((n + 255) / 256), (unsigned)nc);
+        unpack_kernel<<<grid, 256, 0, h->stream>>>(S.geno, n, h->R, S.p_pad, c0, nc, stage);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out + (size_t)(c0 - j0) * n, stage, (size_t)n * nc, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    cudaFree(stage);
+    return NGP_OK;
+}
+
+int ngp_get_column_stats(ngp_handle* h, int set_id, double* mean, double* mpm)
+{
+    if (!h || set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_geno) return fail(h, NGP_EINVAL, "ngp_get_column_stats: no such set");
+    SetHost& S = h->sets[set_id];
+    CU(cudaSetDevice(h->device));
+    if (mean) CU(cpy(h, mean, S.mean, sizeof(double) * S.p, cudaMemcpyDeviceToHost));
+    if (mpm) CU(cpy(h, mpm, S.d, sizeof(double) * S.p, cudaMemcpyDeviceToHost));
+    return NGP_OK;
+}
+
+// ----------------------------------------------------------------------------- host 2-bit codec
+int ngp_pack2(const int8_t* codes, int64_t n, int64_t p, int64_t ld_in, uint8_t* out, int64_t ld_out)
+{
+    if (!codes || !out || n < 0 || p < 0 || ld_in < n || ld_out < (n + 3) / 4) return NGP_EINVAL;
+    for (int64_t j = 0; j < p; ++j) {
+        const int8_t* c = codes + j * ld_in;
+        uint8_t* o = out + j * ld_out;
+        memset(o, 0, (size_t)ld_out);
+        for (int64_t i = 0; i < n; ++i) {
+            const int g = c[i];
+            if (g < 0 || g > 2) return NGP_EDATA;
+            o[i >> 2] |= (uint8_t)(g << (2 * (i & 3)));
+        }
+    }
+    return NGP_OK;
+}
+
+int ngp_unpack2(const uint8_t* packed, int64_t n, int64_t p, int64_t ld_in, int8_t* out, int64_t ld_out)
+{
+    if (!packed || !out || n < 0 || p < 0 || ld_in < (n + 3) / 4 || ld_out < n) return NGP_EINVAL;
+    for (int64_t j = 0; j < p; ++j) {
+        const uint8_t* c = packed + j * ld_in;
+        int8_t* o = out + j * ld_out;
+        for (int64_t i = 0; i < n; ++i) {
+            const int g = (c[i >> 2] >> (2 * (i & 3))) & 3;
+            if (g > 2) return NGP_EDATA;
+            o[i] = (int8_t)g;
+        }
+    }
+    return NGP_OK;
+}
+
+// ----------------------------------------------------------------------------- model
+int ngp_set_phenotype(ngp_handle* h, const double* y, int64_t n)
+{
+    if (!h || !y) return fail(h, NGP_EINVAL, "ngp_set_phenotype: NULL argument");
+    if (h->T == 0) return fail(h, NGP_EINVAL, "ngp_set_phenotype: upload a marker set first (it fixes n)");
+    if (n != h->n) return fail(h, NGP_EINVAL, "ngp_set_phenotype: n = %lld but the genotypes have %lld rows", (long long)n, (long long)h->n);
+    CU(cudaSetDevice(h->device));
+    CU(zero(h, h->e, 0, sizeof(double) * (size_t)h->T * h->R));
+    CU(cpy(h, h->e, y, sizeof(double) * n, cudaMemcpyHostToDevice));     // ycorr = deepcopy(Y), mme.jl:57
+    Scalars z{};
+    CU(cpy(h, h->sc, &z, sizeof z, cudaMemcpyHostToDevice));
+    h->have_y = true;
+    return NGP_OK;
+}
+
+int ngp_set_residual_prior(ngp_handle* h, double df_e, double scale_e)
+{
+    if (!h) return NGP_EINVAL;
+    if (!(df_e > 0.0) || !(scale_e >= 0.0)) return fail(h, NGP_EINVAL, "ngp_set_residual_prior: df must be > 0 and scale >= 0");
+    h->df_e = df_e; h->scale_e = scale_e;
+    return NGP_OK;
+}
+
+int ngp_set_intercept(ngp_handle* h, int enabled, double lhs0, double rhs0)
+{
+    if (!h) return NGP_EINVAL;
+    h->has_mu = enabled ? 1 : 0; h->mu_lhs0 = lhs0; h->mu_rhs0 = rhs0;
+    return NGP_OK;
+}
+
+int ngp_set_prior(ngp_handle* h, int set_id, const ngp_prior* pr)
+{
+    if (!h || !pr) return fail(h, NGP_EINVAL, "ngp_set_prior: NULL argument");
+    if (set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_geno) return fail(h, NGP_EINVAL, "ngp_set_prior: upload genotypes of set %d first", set_id);
+    SetHost& S = h->sets[set_id];
+    if (pr->method != NGP_BAYESPR && pr->method != NGP_BAYESB && pr->method != NGP_BAYESC) return fail(h, NGP_EINVAL, "ngp_set_prior: unknown method %d", pr->method);
+    if (!(pr->df > 0.0) || !(pr->var_init >= 0.0)) return fail(h, NGP_EINVAL, "ngp_set_prior: df must be > 0 and var_init >= 0");
+    if (pr->method != NGP_BAYESPR && !(pr->pi_in > 0.0 && pr->pi_in < 1.0)) return fail(h, NGP_EINVAL, "ngp_set_prior: pi_in must be inside (0,1)");
+    CU(cudaSetDevice(h->device));
+    S.method = pr->method; S.est_pi = pr->est_pi ? 1 : 0; S.df = pr->df; S.scale = pr->scale; S.var_init = pr->var_init; S.pi_in = pr->pi_in;
+    cudaFree(S.region_off); S.region_off = nullptr;
+    cudaFree(S.region_of); S.region_of = nullptr;
+    S.n_regions = 0;
+    if (pr->method == NGP_BAYESPR) {
+        if (pr->region_off && pr->n_regions >= 1) {
+            if (pr->region_off[0] != 0 || pr->region_off[pr->n_regions] != S.p) return fail(h, NGP_EINVAL, "ngp_set_prior: region offsets must start at 0 and end at p");
+            for (int64_t r = 0; r < pr->n_regions; ++r)
+                if (pr->region_off[r + 1] <= pr->region_off[r]) return fail(h, NGP_EINVAL, "ngp_set_prior: empty or unordered region %lld", (long long)r);
+            S.n_regions = pr->n_regions;
+        } else S.n_regions = 1;
+        S.nvar = S.n_regions;
+        if (S.n_regions > 1) {
+            CU(dalloc(&S.region_off, S.n_regions + 1));
+            CU(cpy(h, S.region_off, pr->region_off, sizeof(int64_t) * (S.n_regions + 1), cudaMemcpyHostToDevice));
+            CU(dalloc(&S.region_of, S.p_pad));
+            CU(zero(h, S.region_of, 0, sizeof(int32_t) * S.p_pad));
+            region_of_kernel<<<(unsigned)std::min<int64_t>(S.n_regions, 4096), 128, 0, h->stream>>>(S.region_off, S.n_regions, S.region_of);
+            CU(cudaGetLastError());
+        }
+    } else if (pr->method == NGP_BAYESB) S.nvar = S.p;
+    else S.nvar = 1;
+    CU(dalloc(&S.varBeta, S.nvar));
+    fill_kernel<<<(unsigned)((S.nvar + 255) / 256), 256, 0, h->stream>>>(S.varBeta, S.nvar, pr->var_init);     // mme.jl:516
+    CU(cudaGetLastError());
+    CU(dalloc(&S.pi, 4));
+    double pi4[4] = {0.0, 1.0, -INFINITY, 0.0};
+    if (pr->method != NGP_BAYESPR) { pi4[0] = 1.0 - pr->pi_in; pi4[1] = pr->pi_in; pi4[2] = log(1.0 - pr->pi_in); pi4[3] = log(pr->pi_in); }   // mme.jl:351,359
+    CU(cudaMemcpyAsync(S.pi, pi4, sizeof pi4, cudaMemcpyHostToDevice, h->stream));
+    cudaFree(S.lhs0); S.lhs0 = nullptr; cudaFree(S.rhs0); S.rhs0 = nullptr;
+    if (pr->lhs0) { CU(dalloc(&S.lhs0, S.p)); CU(cudaMemcpyAsync(S.lhs0, pr->lhs0, sizeof(double) * S.p, cudaMemcpyHostToDevice, h->stream)); }
+    if (pr->rhs0) { CU(dalloc(&S.rhs0, S.p)); CU(cudaMemcpyAsync(S.rhs0, pr->rhs0, sizeof(double) * S.p, cudaMemcpyHostToDevice, h->stream)); }
+    CU(dalloc(&S.sum_beta, S.p_pad)); CU(dalloc(&S.sum_beta2, S.p_pad)); CU(dalloc(&S.sum_delta, S.p_pad));
+    CU(cudaMemsetAsync(S.sum_beta, 0, sizeof(double) * S.p_pad, h->stream));
+    CU(cudaMemsetAsync(S.sum_beta2, 0, sizeof(double) * S.p_pad, h->stream));
+    CU(cudaMemsetAsync(S.sum_delta, 0, sizeof(double) * S.p_pad, h->stream));
+    CU(cudaMemsetAsync(S.beta, 0, sizeof(double) * S.p_pad, h->stream));                                          // mme.jl:443
+    fill_i32_kernel<<<(unsigned)((S.p_pad + 255) / 256), 256, 0, h->stream>>>(S.delta, S.p_pad, 1);               // mme.jl:444
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    S.have_prior = true;
+    h->sets_dirty = true;
+    return NGP_OK;
+}
+
+int ngp_set_rng(ngp_handle* h, uint64_t seed, uint32_t chain_id)
+{
+    if (!h) return NGP_EINVAL;
+    h->seed = seed; h->chain = chain_id;
+    return NGP_OK;
+}
+
+int ngp_set_replay(ngp_handle* h, const ngp_replay* log)
+{
+    if (!h) return NGP_EINVAL;
+    CU(cudaSetDevice(h->device));
+    h->replay = 0; h->replay_iters = 0;
+    if (!log) { h->sets_dirty = true; return NGP_OK; }
+    if (log->n_iter <= 0 || !log->chi2_e) return fail(h, NGP_EINVAL, "ngp_set_replay: n_iter must be > 0 and chi2_e non-NULL");
+    const int ni = log->n_iter;
+    CU(dalloc(&h->rp_chi2_e, ni));
+    CU(dalloc(&h->rp_z_mu, ni));
+    CU(cpy(h, h->rp_chi2_e, log->chi2_e, sizeof(double) * ni, cudaMemcpyHostToDevice));
+    if (log->z_mu) CU(cpy(h, h->rp_z_mu, log->z_mu, sizeof(double) * ni, cudaMemcpyHostToDevice));
+    else if (h->has_mu) return fail(h, NGP_EINVAL, "ngp_set_replay: z_mu is required when the intercept is enabled");
+    for (int s = 0; s < h->n_sets; ++s) {
+        SetHost& S = h->sets[s];
+        if (!S.have_geno) continue;
+        if (!S.have_prior) return fail(h, NGP_EINVAL, "ngp_set_replay: set the prior of set %d first", s);
+        if (s >= log->n_sets || !log->z[s] || !log->chi2_b[s]) return fail(h, NGP_EINVAL, "ngp_set_replay: z / chi2_b missing for set %d", s);
+        CU(dalloc(&S.rp_z, (size_t)ni * S.p));
+        CU(cpy(h, S.rp_z, log->z[s], sizeof(double) * (size_t)ni * S.p, cudaMemcpyHostToDevice));
+        CU(dalloc(&S.rp_chi2b, (size_t)ni * S.nvar));
+        CU(cpy(h, S.rp_chi2b, log->chi2_b[s], sizeof(double) * (size_t)ni * S.nvar, cudaMemcpyHostToDevice));
+        if (S.method != NGP_BAYESPR) {
+            if (!log->u[s]) return fail(h, NGP_EINVAL, "ngp_set_replay: u missing for set %d", s);
+            CU(dalloc(&S.rp_u, (size_t)ni * S.p));
+            CU(cpy(h, S.rp_u, log->u[s], sizeof(double) * (size_t)ni * S.p, cudaMemcpyHostToDevice));
+            if (S.est_pi) {
+                if (!log->beta_pi[s]) return fail(h, NGP_EINVAL, "ngp_set_replay: beta_pi missing for set %d", s);
+                CU(dalloc(&S.rp_betapi, ni));
+                CU(cpy(h, S.rp_betapi, log->beta_pi[s], sizeof(double) * ni, cudaMemcpyHostToDevice));
+            }
+        }
+    }
+    Scalars sc;
+    CU(cpy(h, &sc, h->sc, sizeof sc, cudaMemcpyDeviceToHost));
+    h->replay = 1; h->replay_iters = ni; h->replay_base = sc.iter;
+    h->sets_dirty = true;
+    return NGP_OK;
+}
+
+// ----------------------------------------------------------------------------- launch
+static int sync_sets(ngp_handle* h)
+{
+    if (!h->sets_dirty) return NGP_OK;
+    SetDev sd[NGP_MAX_SETS];
+    memset(sd, 0, sizeof sd);
+    for (int s = 0; s < h->n_sets; ++s) {
+        const SetHost& S = h->sets[s];
+        if (!S.have_geno || !S.have_prior) continue;
+        SetDev& D = sd[s];
+        D.p = S.p; D.p_pad = S.p_pad; D.method = S.method; D.est_pi = S.est_pi; D.n_regions = S.n_regions; D.nvar = S.nvar;
+        D.df = S.df; D.scale = S.scale; D.geno = S.geno; D.gram = S.gram; D.colsum = S.colsum; D.d = S.d; D.mean = S.mean;
+        D.beta = S.beta; D.delta = S.delta; D.varBeta = S.varBeta; D.pi = S.pi; D.region_of = S.region_of; D.region_off = S.region_off;
+        D.lhs0 = S.lhs0; D.rhs0 = S.rhs0; D.consts = S.consts;
+        D.rp_u = S.rp_u; D.rp_z = S.rp_z; D.rp_chi2b = S.rp_chi2b; D.rp_betapi = S.rp_betapi;
+        D.sum_beta = S.sum_beta; D.sum_beta2 = S.sum_beta2; D.sum_delta = S.sum_delta;
+    }
+    CU(cudaMemcpyAsync(h->sets_dev, sd, sizeof sd, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->sets_dirty = false;
+    return NGP_OK;
+}
+
+static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_mu, double varE_in, int accumulate)
+{
+    CU(cudaSetDevice(h->device));
+    if (!h->have_y) return fail(h, NGP_EINVAL, "no phenotype / residual on the device (ngp_set_phenotype or ngp_sweep)");
+    int active = 0;
+    for (int s = 0; s < h->n_sets; ++s)
+        if ((set_mask >> s) & 1) {
+            if (!h->sets[s].have_geno || !h->sets[s].have_prior) return fail(h, NGP_EINVAL, "marker set %d has no genotypes or no prior", s);
+            ++active;
+        }
+    if (!active) return fail(h, NGP_EINVAL, "no marker set to sample");
+    if (h->replay) {
+        Scalars sc;
+        CU(cpy(h, &sc, h->sc, sizeof sc, cudaMemcpyDeviceToHost));
+        if (sc.iter - h->replay_base + n_iter > h->replay_iters) return fail(h, NGP_EINVAL, "replay log exhausted (%d iterations)", h->replay_iters);
+    }
+    int rc = sync_sets(h);
+    if (rc) return rc;
+    Params P{};
+    P.n = h->n; P.T = h->T; P.R = h->R; P.B = h->B; P.n_sets = h->n_sets; P.stages = h->stages; P.kernel = h->cfg_kernel;
+    P.e = h->e; P.sets = h->sets_dev; P.sc = h->sc; P.sync = h->sync;
+    P.df_e = h->df_e; P.scale_e = h->scale_e; P.has_mu = h->has_mu; P.do_varE = do_varE; P.do_mu = do_mu; P.set_mask = set_mask;
+    P.mu_lhs0 = h->mu_lhs0; P.mu_rhs0 = h->mu_rhs0; P.varE_in = varE_in; P.n_iter = n_iter; P.replay = h->replay;
+    P.replay_base = h->replay_base; P.rp_chi2_e = h->rp_chi2_e; P.rp_z_mu = h->rp_z_mu;
+    P.key0 = (uint32_t)(h->seed & 0xffffffffu); P.key1 = (uint32_t)(h->seed >> 32); P.chain = h->chain; P.accumulate = accumulate;
+    const void* kfn = (h->B == 64) ? (const void*)gibbs_kernel<64> : (const void*)gibbs_kernel<32>;
+    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->L.total));
+    int per_sm = 0;
+    if (h->B == 64) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_kernel<64>, kThreads, h->L.total));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_kernel<32>, kThreads, h->L.total));
+    if (per_sm * h->prop.multiProcessorCount < h->T)
+        return fail(h, NGP_EUNSUPPORTED, "cooperative grid of %d CTAs does not fit (%d per SM x %d SMs)", h->T, per_sm, h->prop.multiProcessorCount);
+    CU(cudaMemsetAsync(h->sync, 0, sizeof(SyncArea), h->stream));
+    void* args[] = {&P};
+    CU(cudaEventRecord(h->ev0, h->stream));
+    CU(cudaLaunchCooperativeKernel(kfn, dim3(h->T), dim3(kThreads), args, (size_t)h->L.total, h->stream));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    h->launches += 1;
+    h->timed = true;
+    CU(cudaStreamSynchronize(h->stream));
+    int kerr = 0;
+    CU(cpy(h, &kerr, &h->sync->err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (kerr) return fail(h, NGP_ERANGE, "fixed-point reduction range exceeded (residual grew by more than 2^8 within an iteration)");
+    return NGP_OK;
+}
+
+int ngp_run(ngp_handle* h, int32_t n_iter)
+{
+    if (!h) return NGP_EINVAL;
+    if (n_iter <= 0) return fail(h, NGP_EINVAL, "ngp_run: n_iter must be positive");
+    int mask = 0;
+    for (int s = 0; s < h->n_sets; ++s) if (h->sets[s].have_geno) mask |= 1 << s;
+    return launch(h, n_iter, mask, 1, 1, 0.0, 1);
+}
+
+static int push_set_state(ngp_handle* h, int s, const double* beta, const int64_t* delta, const double* varBeta, const double* piHat)
+{
+    SetHost& S = h->sets[s];
+    if (beta) CU(cpy(h, S.beta, beta, sizeof(double) * S.p, cudaMemcpyHostToDevice));
+    if (delta) {
+        std::vector<int32_t> d32((size_t)S.p);
+        for (int64_t j = 0; j < S.p; ++j) d32[(size_t)j] = (int32_t)delta[j];
+        CU(cpy(h, S.delta, d32.data(), sizeof(int32_t) * S.p, cudaMemcpyHostToDevice));
+    }
+    if (varBeta) CU(cpy(h, S.varBeta, varBeta, sizeof(double) * S.nvar, cudaMemcpyHostToDevice));
+    if (piHat && S.method != NGP_BAYESPR) {
+        double pi4[4] = {piHat[0], piHat[1], log(piHat[0]), log(piHat[1])};
+        CU(cpy(h, S.pi, pi4, sizeof pi4, cudaMemcpyHostToDevice));
+    }
+    return NGP_OK;
+}
+
+static int pull_set_state(ngp_handle* h, int s, double* beta, int64_t* delta, double* varBeta, double* piHat)
+{
+    SetHost& S = h->sets[s];
+    if (beta) CU(cpy(h, beta, S.beta, sizeof(double) * S.p, cudaMemcpyDeviceToHost));
+    if (delta) {
+        std::vector<int32_t> d32((size_t)S.p);
+        CU(cpy(h, d32.data(), S.delta, sizeof(int32_t) * S.p, cudaMemcpyDeviceToHost));
+        for (int64_t j = 0; j < S.p; ++j) delta[j] = d32[(size_t)j];
+    }
+    if (varBeta) CU(cpy(h, varBeta, S.varBeta, sizeof(double) * S.nvar, cudaMemcpyDeviceToHost));
+    if (piHat) {
+        double pi4[4];
+        CU(cpy(h, pi4, S.pi, sizeof pi4, cudaMemcpyDeviceToHost));
+        piHat[0] = pi4[0]; piHat[1] = pi4[1];
+    }
+    return NGP_OK;
+}
+
+int ngp_sweep(ngp_handle* h, int set_id, double* ycorr, double varE, double* beta, int64_t* delta, double* varBeta, double* piHat)
+{
+    if (!h) return NGP_EINVAL;
+    if (set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_geno || !h->sets[set_id].have_prior)
+        return fail(h, NGP_EINVAL, "ngp_sweep: marker set %d is not ready", set_id);
+    if (!ycorr || !(varE > 0.0)) return fail(h, NGP_EINVAL, "ngp_sweep: ycorr must be non-NULL and varE > 0");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->e, ycorr, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_y = true;
+    int rc = push_set_state(h, set_id, beta, delta, varBeta, piHat);
+    if (rc) return rc;
+    rc = launch(h, 1, 1 << set_id, 0, 0, varE, 0);
+    if (rc) return rc;
+    CU(cpy(h, ycorr, h->e, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
+    return pull_set_state(h, set_id, beta, delta, varBeta, piHat);
+}
+
+int ngp_get_state(ngp_handle* h, ngp_state* out)
+{
+    if (!h || !out) return fail(h, NGP_EINVAL, "ngp_get_state: NULL argument");
+    CU(cudaSetDevice(h->device));
+    Scalars sc;
+    CU(cpy(h, &sc, h->sc, sizeof sc, cudaMemcpyDeviceToHost));
+    out->n = h->n; out->n_sets = h->n_sets; out->mu = sc.mu; out->varE = sc.varE; out->iter = sc.iter;
+    if (out->e && h->e) CU(cpy(h, out->e, h->e, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < h->n_sets; ++s) {
+        if (!h->sets[s].have_geno || !h->sets[s].have_prior) continue;
+        int rc = pull_set_state(h, s, out->beta[s], out->delta[s], out->varBeta[s], out->pi[s]);
+        if (rc) return rc;
+    }
+    return NGP_OK;
+}
+
+int ngp_set_state(ngp_handle* h, const ngp_state* in)
+{
+    if (!h || !in) return fail(h, NGP_EINVAL, "ngp_set_state: NULL argument");
+    if (h->T == 0) return fail(h, NGP_EINVAL, "ngp_set_state: upload a marker set first");
+    CU(cudaSetDevice(h->device));
+    Scalars sc;
+    CU(cpy(h, &sc, h->sc, sizeof sc, cudaMemcpyDeviceToHost));
+    sc.mu = in->mu; sc.varE = in->varE; sc.iter = in->iter;
+    CU(cpy(h, h->sc, &sc, sizeof sc, cudaMemcpyHostToDevice));
+    if (in->e) { CU(cpy(h, h->e, in->e, sizeof(double) * h->n, cudaMemcpyHostToDevice)); h->have_y = true; }
+    for (int s = 0; s < h->n_sets; ++s) {
+        if (!h->sets[s].have_geno || !h->sets[s].have_prior) continue;
+        int rc = push_set_state(h, s, in->beta[s], in->delta[s], in->varBeta[s], in->pi[s]);
+        if (rc) return rc;
+    }
+    return NGP_OK;
+}
+
+int ngp_reset_posterior(ngp_handle* h)
+{
+    if (!h) return NGP_EINVAL;
+    CU(cudaSetDevice(h->device));
+    for (int s = 0; s < h->n_sets; ++s) {
+        SetHost& S = h->sets[s];
+        if (!S.sum_beta) continue;
+        CU(zero(h, S.sum_beta, 0, sizeof(double) * S.p_pad));
+        CU(zero(h, S.sum_beta2, 0, sizeof(double) * S.p_pad));
+        CU(zero(h, S.sum_delta, 0, sizeof(double) * S.p_pad));
+    }
+    Scalars sc;
+    CU(cpy(h, &sc, h->sc, sizeof sc, cudaMemcpyDeviceToHost));
+    sc.n_post = 0;
+    CU(cpy(h, h->sc, &sc, sizeof sc, cudaMemcpyHostToDevice));
+    return NGP_OK;
+}
+
+int ngp_get_posterior(ngp_handle* h, int set_id, int64_t* n_samples, double* sum_beta, double* sum_beta2, double* sum_delta)
+{
+    if (!h || set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].sum_beta) return fail(h, NGP_EINVAL, "ngp_get_posterior: no such set");
+    CU(cudaSetDevice(h->device));
+    SetHost& S = h->sets[set_id];
+    Scalars sc;
+    CU(cpy(h, &sc, h->sc, sizeof sc, cudaMemcpyDeviceToHost));
+    if (n_samples) *n_samples = sc.n_post;
+    if (sum_beta) CU(cpy(h, sum_beta, S.sum_beta, sizeof(double) * S.p, cudaMemcpyDeviceToHost));
+    if (sum_beta2) CU(cpy(h, sum_beta2, S.sum_beta2, sizeof(double) * S.p, cudaMemcpyDeviceToHost));
+    if (sum_delta) CU(cpy(h, sum_delta, S.sum_delta, sizeof(double) * S.p, cudaMemcpyDeviceToHost));
+    return NGP_OK;
+}
+
+int ngp_get_timing(ngp_handle* h, ngp_timing* out)
+{
+    if (!h || !out) return fail(h, NGP_EINVAL, "ngp_get_timing: NULL argument");
+    memset(out, 0, sizeof *out);
+    out->launches = h->launches; out->ctas = h->T; out->threads = kThreads; out->block = h->B; out->rows_per_cta = h->R;
+    out->smem_bytes = h->L.total;
+    if (h->timed) {
+        float ms = 0.f;
+        CU(cudaEventSynchronize(h->ev1));
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        out->last_run_ms = ms;
+    }
+    return NGP_OK;
+}
+
+int ngp_debug_variates(ngp_handle* h, int set_id, uint32_t iter, int purpose, double df, int64_t n, double* out)
+{
+    if (!h || !out || n <= 0) return fail(h, NGP_EINVAL, "ngp_debug_variates: bad argument");
+    CU(cudaSetDevice(h->device));
+    double* d = nullptr;
+    CU(cudaMalloc((void**)&d, sizeof(double) * n));
+    debug_variates_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>((uint32_t)(h->seed & 0xffffffffu), (uint32_t)(h->seed >> 32),
+                                                                              h->chain, iter, (uint32_t)set_id, purpose, df, n, d);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    return NGP_OK;
+}
+
+}  // extern "C"

@@ -36,7 +36,7 @@
  * the VARIATE level: every draw is an explicit input ("replay"), or comes from
  * the counter-based Philox4x32-10 stream specified in DESIGN.md §RNG, whose
  * transforms are restated here independently of the CUDA implementation:
- *   Normal   : Box-Muller on two 53-bit uniforms
+ *   Normal   : Box-Muller on two 52-bit uniforms
  *   Chisq(v) : 2*Gamma(v/2), Gamma by Marsaglia & Tsang (2000)
  *   Beta(a,b): Ga/(Ga+Gb)
  *   MvNormal : mean + chol(C)_lower * z
@@ -104,11 +104,11 @@ static inline void stream_words(const ngo_stream* s, uint32_t purpose, uint32_t 
     ngo_philox4x32_10(ctr, key, w);
 }
 
-/* 53-bit uniform strictly inside (0,1) */
+/* 52-bit uniform strictly inside (0,1): (k + 1/2) * 2^-52, k in [0, 2^52) — every value exact in fp64 */
 static inline double u53(uint32_t hi, uint32_t lo)
 {
     const double two26 = 67108864.0;
-    return (((double)(hi >> 5)) * two26 + (double)(lo >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+    return (((double)(hi >> 6)) * two26 + (double)(lo >> 6) + 0.5) * (1.0 / 4503599627370496.0);
 }
 
 static double stream_uniform(const ngo_stream* s, uint32_t purpose, uint32_t idx, uint32_t attempt, uint32_t comp)

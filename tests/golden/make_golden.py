@@ -1,0 +1,44 @@
+"""Generates tests/golden/*.npz: oracle chains on small seeded problems (inputs are regenerated from the
+seed; the fixture stores the variate log and the per-iteration states).  The reference has no golden
+vectors of its own (test/runtests.jl is empty) and cannot run here (no Julia), so these pin the ORACLE
+against regressions and give the GPU tests a committed target that does not need the oracle .so.
+Run:  python tests/golden/make_golden.py"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+from common import make_problem, oracle_chain  # noqa: E402
+
+CASES = {
+    "bayespr_rr": dict(n=300, p=150, seed=101, method=0, v=0.01, iters=25),
+    "bayespr_regions": dict(n=257, p=130, seed=102, method=0, v=0.01, iters=25, region_off=[0, 40, 41, 100, 130]),
+    "bayesb": dict(n=300, p=150, seed=103, method=1, v=0.05, pi=0.1, est_pi=True, iters=25),
+    "bayesc_pi": dict(n=311, p=200, seed=104, method=2, v=0.05, pi=0.05, est_pi=True, iters=25),
+}
+
+
+def main():
+    for name, c in CASES.items():
+        prob = make_problem(c["n"], c["p"], c["seed"])
+        ro = np.array(c["region_off"], dtype=np.int64) if "region_off" in c else None
+        ch, S = oracle_chain(prob, c["method"], c["v"], pi=c.get("pi", 0.0), est_pi=c.get("est_pi", False), region_off=ro)
+        out = {k: [] for k in ("chi2_e", "z_mu", "u", "z", "chi2_b", "beta_pi", "beta", "delta", "varBeta", "varE", "mu", "pi")}
+        for _ in range(c["iters"]):
+            log = ch.iteration(seed=c["seed"], chain=3)
+            s = log["sets"][0]
+            for k in ("chi2_e", "z_mu"):
+                out[k].append(log[k])
+            for k in ("u", "z", "chi2_b", "beta_pi"):
+                out[k].append(np.array(s[k]))
+            out["beta"].append(S.beta.copy()); out["delta"].append(S.delta.copy()); out["varBeta"].append(S.varBeta.copy())
+            out["varE"].append(ch.varE); out["mu"].append(ch.mu); out["pi"].append(S.piHat.copy())
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), e_final=ch.e, **{k: np.array(v) for k, v in out.items()})
+        print(name, "varE", ch.varE, "nIn", int(S.delta.sum()))
+
+
+if __name__ == "__main__":
+    main()
