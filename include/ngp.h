@@ -178,6 +178,11 @@ int ngp_reset_posterior(ngp_handle* h);
 int ngp_get_posterior(ngp_handle* h, int set_id, int64_t* n_samples, double* sum_beta, double* sum_beta2, double* sum_delta);
 int ngp_get_timing(ngp_handle* h, ngp_timing* out);
 
+/* per-CTA cycle counters of the last launch, 8 int64 per CTA (thread 0 of each CTA, blocked kernel):
+ * [0] TMA wait [1] dot phase [2] reduce+arrive [3] grid-barrier wait [4] scalar chain [5] axpy
+ * [6] markers whose effect changed [7] speculative evaluations.  Returns the number of CTAs written. */
+int ngp_get_profile(ngp_handle* h, int64_t* out, int32_t max_ctas);
+
 /* stream self-test: fills out[0..n) with the handle's variates of one purpose
  * (purpose: 2=uniform 3=normal 4=chisq(df)) for iteration iter, set set_id.   */
 int ngp_debug_variates(ngp_handle* h, int set_id, uint32_t iter, int purpose, double df, int64_t n, double* out);

@@ -108,6 +108,7 @@ _SIGS = {
     "ngp_reset_posterior": (C.c_int, [C.c_void_p]),
     "ngp_get_posterior": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]),
     "ngp_get_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
+    "ngp_get_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "ngp_debug_variates": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_double, C.c_int64, C.c_void_p]),
 }
 

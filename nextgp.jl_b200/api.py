@@ -392,6 +392,14 @@ class Sampler:
         self._ck(self._lib.ngp_get_timing(self._h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in L.Timing._fields_}
 
+    def profile(self) -> np.ndarray:
+        """(ctas, 8) int64 cycle counters of the last launch, see ngp_get_profile."""
+        out = np.zeros((160, 8), dtype=np.int64)
+        nc = self._lib.ngp_get_profile(self._h, _p(out), 160)
+        if nc < 0:
+            self._ck(nc)
+        return out[:nc]
+
     def debug_variates(self, set_id: int, it: int, purpose: int, df: float, n: int) -> np.ndarray:
         out = np.empty(n)
         self._ck(self._lib.ngp_debug_variates(self._h, set_id, it, purpose, df, n, _p(out)))

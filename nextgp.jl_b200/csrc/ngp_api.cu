@@ -930,6 +930,15 @@ int ngp_get_timing(ngp_handle* h, ngp_timing* out)
     return NGP_OK;
 }
 
+int ngp_get_profile(ngp_handle* h, int64_t* out, int32_t max_ctas)
+{
+    if (!h || !out || max_ctas <= 0) return fail(h, NGP_EINVAL, "ngp_get_profile: bad argument");
+    CU(cudaSetDevice(h->device));
+    const int nc = std::min<int>(max_ctas, h->T);
+    CU(cpy(h, out, h->sync->prof, sizeof(long long) * 8 * nc, cudaMemcpyDeviceToHost));
+    return nc;
+}
+
 int ngp_debug_variates(ngp_handle* h, int set_id, uint32_t iter, int purpose, double df, int64_t n, double* out)
 {
     if (!h || !out || n <= 0) return fail(h, NGP_EINVAL, "ngp_debug_variates: bad argument");

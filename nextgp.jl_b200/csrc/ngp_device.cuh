@@ -62,6 +62,7 @@ struct SyncArea {
     unsigned long long pad0[15];
     long long acc[kSlots * (kMaxB + 1) * kAccStride];   // fixed-point reduction accumulators (monotonic)
     double part[kMaxCtas * 2];                  // phase-0 partials (e'e, sum e) per CTA
+    long long prof[kMaxCtas * 8];               // per-CTA cycle counters of the last launch (thread 0): see ngp_get_profile
     int err;
 };
 

@@ -172,6 +172,9 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     }
     __syncthreads();
 
+    long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cycles: 0 tma-wait 1 dot 2 reduce+arrive 3 barrier-wait 4 chain 5 axpy 6 nnz 7 spec-evals
+    long long tc = clock64();
+#define NGP_TICK(i) do { const long long now__ = clock64(); pf[i] += now__ - tc; tc = now__; } while (0)
     long long gk = 0;        // running tile count (mbarrier stage / parity)
     long long rk = 0;        // running reduction count (accumulator slot)
     double mu = P.sc->mu;
@@ -280,7 +283,9 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     const double* cst = reinterpret_cast<const double*>(smem + L.off_cst + stg * L.cst_bytes);
                     const int slot = (int)(rk % kSlots);
                     long long* acc = sy->acc + (int64_t)slot * (kMaxB + 1) * kAccStride;
+                    tc = clock64();
                     mbar_wait(&mbar[stg], par);
+                    NGP_TICK(0);
 
                     // ---- b) partial dots: lane <-> marker, warps split the rows
                     {
@@ -303,6 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         red[rc * B + mg * 32 + lane] = (a0 + a1) + (a2 + a3);
                     }
                     __syncthreads();
+                    NGP_TICK(1);
                     if (tid < B) {
                         double A = 0.0;
                         for (int c = 0; c < RC; ++c) A += red[c * B + tid];
@@ -313,11 +319,13 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     __syncthreads();
                     gs.nbar++;
                     if (tid == 0) gs.arrive();
+                    NGP_TICK(2);
 
                     // ---- c) the dependent scalar updates of the block (warp 0, redundantly in every CTA)
                     int nnz = 0;
                     if (warp == 0) {
                         gs.wait_warp();
+                        NGP_TICK(3);
                         constexpr int NB = MG;
                         double r[NB], bold[NB], dd[NB], cs[NB], bnew[NB];
                         bool inc[NB];
@@ -343,6 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             const double cC = cst[F_C * B + q], cQ = cst[F_QSZ * B + q];
                             int start = 0;
                             while (start < 32) {
+                                pf[7]++;
                                 const double rr = fma(dd[b], bold[b], r[b]);        // add-back fused: x'(e + x b) = x'e + d b
                                 const double dl = fma(cB, rr * rr, cA);
                                 const bool in = dl < cT;                            // NaN -> excluded, like rand() < NaN
@@ -390,6 +399,8 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             }
                         }
                         if (lane == 0) misc[40] = (double)nnz;
+                        pf[6] += nnz;
+                        NGP_TICK(4);
                     }
                     __syncthreads();
                     nnz = (int)misc[40];
@@ -408,6 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         }
                     }
                     __syncthreads();
+                    NGP_TICK(5);
                     if (tid == 0 && k + S_ < nblk) issue(k + S_, gk + S_);
                 }
             } else {
@@ -542,6 +554,9 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 
     __syncthreads();
     for (int r = tid; r < nrow; r += kThreads) P.e[row0 + r] = e_s[r];
+    if (tid == 0)
+        for (int i = 0; i < 8; ++i) sy->prof[t * 8 + i] = pf[i];
+#undef NGP_TICK
 }
 
 }  // namespace ngp

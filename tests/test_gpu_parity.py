@@ -316,7 +316,7 @@ def test_runLMEM_writes_reference_output_files(gpu, tmp_path):
     assert files == ["bOut", "betaMOut", "deltaMOut", "groupInfo_M.txt", "varEOut", "varMOut"]
     beta = np.loadtxt(os.path.join(out, "betaMOut"), delimiter="\t", skiprows=1)
     assert beta.shape == (4, 50)                     # kept iterations 30,40,50,60 (samplers.jl:26)
-    assert open(os.path.join(out, "varMOut")).readline().strip().split("\t") == [f"reg_{r}" for r in range(1, 7)]
+    assert open(os.path.join(out, "varMOut")).readline().strip().split("\t") == [f"reg_{r}" for r in range(1, 6)]   # chromosomes of 20,20,10 SNPs in windows of 10
     assert ngp.summaryMCMC("varE", outFolder=out).shape == (1, 1)
     # final state equals an oracle chain with the same native stream
     ro = ngp.prep2RegionData(None, "M", str(mp), 10)
