@@ -24,7 +24,8 @@ constexpr int kMaxB = 64;              // markers per block (32 or 64)
 constexpr int kNF = 10;                // per-marker constant fields
 constexpr int kSlots = 2;              // reduction accumulator ring
 constexpr int kAccStride = 32;         // int64 units between accumulators (256 B: distinct L2 slices)
-constexpr int kMaxCtas = 160;
+constexpr int kMaxCtas = 160;          // < 256: the low byte of an accumulator counts arrivals
+constexpr int kCntBits = 8;
 
 // fields of the per-iteration marker constants, stored [block][field][B]
 enum Field { F_A = 0, F_B = 1, F_T = 2, F_C = 3, F_QSZ = 4, F_D = 5, F_BOLD = 6, F_MEAN = 7, F_CS = 8, F_CHI = 9 };
@@ -104,6 +105,12 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
 {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(c) : "memory");
+    return v;
+}
+__device__ __forceinline__ long long ld_relaxed_s64(const long long* p)     // LDG.STRONG.GPU, no L1, no fence
+{
+    long long v;
+    asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

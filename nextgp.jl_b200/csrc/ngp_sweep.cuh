@@ -12,9 +12,11 @@
 //   a) TMA (cp.async.bulk) has prefetched the panel's B*R-byte tile, the block's
 //      raw Gram G = sum_i g_ia g_ib and its per-marker constants into smem;
 //   b) every CTA forms its B partial sums A_j = sum_i (1 + g_ij/4) e_i with one
-//      PRMT + one DFMA per code, converts them to fixed point and adds them into
-//      global int64 accumulators (associative => bit-reproducible), then arrives
-//      on the grid barrier: ONE grid-wide reduction per B markers;
+//      PRMT + one DFMA per code, converts them to fixed point and adds
+//      (value << 8) + 1 into global int64 accumulators with one RED each: integer
+//      adds are associative (bit-reproducible) and the low byte counts arrivals, so
+//      the accumulator is its own barrier - no fence, no separate counter: ONE
+//      grid-wide reduction per B markers, whose latency is one RED + one poll;
 //   c) warp 0 of every CTA redundantly runs the B dependent scalar updates
 //        r_j <- 4(A_j - S) - m_j S - sum_{k<j} Gc_jk dbeta_k ,  Gc = G - s_j s_k / n
 //      (identical inputs + identical code => identical results, no broadcast);
@@ -89,7 +91,8 @@ struct GridSync {
     __device__ __forceinline__ void wait_warp()     // whole warp polls
     {
         const unsigned long long target = nbar * (unsigned long long)T;
-        while (ld_acquire(counter) < target) { }
+        while ((unsigned long long)ld_relaxed_s64(reinterpret_cast<const long long*>(counter)) < target) { }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");      // acquire once, not one CCTL.IVALL per poll
     }
 };
 
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                 double M = 2.0 * sqrt(nn) * (sqrt(a) + sqrt(nn) * fabs(dmu));
                 if (!(M > 1e-300)) M = 1e-300;
                 int ex; (void)frexp(M, &ex);
-                int sh = 62 - 8 - ex;
+                int sh = 62 - kCntBits - 8 - ex;          // 8 count bits + 2^8 headroom for growth of ||e|| inside the iteration
                 sh = max(-1000, min(1000, sh));
                 misc[32] = varE; misc[33] = dmu; misc[34] = b + nn * dmu; misc[35] = (double)sh; misc[36] = mu;
             }
@@ -313,30 +316,38 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         double A = 0.0;
                         for (int c = 0; c < RC; ++c) A += red[c * B + tid];
                         const double xs = A * fx_scale;
-                        if (!(fabs(xs) < 2305843009213693952.0)) atomicOr(&sy->err, 1);
-                        red_add_u64(acc + tid * kAccStride, __double2ll_rn(xs));
+                        if (!(fabs(xs) < 9007199254740992.0)) atomicOr(&sy->err, 1);     // 2^53 << 8 still fits
+                        red_add_u64(acc + tid * kAccStride, (__double2ll_rn(xs) << kCntBits) + 1);
                     }
-                    __syncthreads();
-                    gs.nbar++;
-                    if (tid == 0) gs.arrive();
                     NGP_TICK(2);
 
                     // ---- c) the dependent scalar updates of the block (warp 0, redundantly in every CTA)
                     int nnz = 0;
                     if (warp == 0) {
-                        gs.wait_warp();
-                        NGP_TICK(3);
                         constexpr int NB = MG;
                         double r[NB], bold[NB], dd[NB], cs[NB], bnew[NB];
                         bool inc[NB];
+                        long long curv[NB];
+                        {   // every lane polls its own accumulators until all T CTAs have added theirs
+                            bool done;
+                            do {
+                                done = true;
+#pragma unroll
+                                for (int b = 0; b < NB; ++b) {
+                                    const int q = b * 32 + lane;
+                                    curv[b] = ld_relaxed_s64(acc + q * kAccStride);
+                                    done = done && (((curv[b] - prev[slot * (kMaxB + 1) + q]) & 0xFF) == (long long)P.T);
+                                }
+                            } while (!__all_sync(0xffffffffu, done));
+                        }
+                        NGP_TICK(3);
 #pragma unroll
                         for (int b = 0; b < NB; ++b) {
                             {
                                 const int q = b * 32 + lane;
-                                const long long cur = __ldcg(acc + q * kAccStride);
                                 long long* pv = prev + slot * (kMaxB + 1) + q;
-                                const double A = (double)(cur - *pv) * fx_inv;
-                                *pv = cur;
+                                const double A = (double)((curv[b] - *pv - (long long)P.T) >> kCntBits) * fx_inv;
+                                *pv = curv[b];
                                 r[b] = 4.0 * (A - Stot) - cst[F_MEAN * B + q] * Stot;     // x_j'e
                                 bold[b] = cst[F_BOLD * B + q];
                                 dd[b] = cst[F_D * B + q];
@@ -390,11 +401,6 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                     if (S.method != 0) S.delta[j] = inc[b] ? 1 : 0;
                                     if (S.method == 1)                                  // functions.jl:182,186
                                         S.varBeta[j] = inc[b] ? (S.scale * S.df + bnew[b] * bnew[b]) / cst[F_CHI * B + q] : 0.0;
-                                    if (P.accumulate) {
-                                        S.sum_beta[j] += bnew[b];
-                                        S.sum_beta2[j] = fma(bnew[b], bnew[b], S.sum_beta2[j]);
-                                        S.sum_delta[j] += (S.method == 0) ? 1.0 : (inc[b] ? 1.0 : 0.0);
-                                    }
                                 }
                             }
                         }
@@ -441,22 +447,20 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         a = fma(dec_byte(w.y, 2), ep[6], a); a = fma(dec_byte(w.y, 3), ep[7], a);
                     }
                     block_sum2(a, dummy, misc);
-                    gs.nbar++;
                     if (tid == 0) {
                         const double xs = a * fx_scale;
-                        if (!(fabs(xs) < 2305843009213693952.0)) atomicOr(&sy->err, 1);
-                        red_add_u64(acc, __double2ll_rn(xs));
-                        gs.arrive();
+                        if (!(fabs(xs) < 9007199254740992.0)) atomicOr(&sy->err, 1);
+                        red_add_u64(acc, (__double2ll_rn(xs) << kCntBits) + 1);
                     }
                     if (warp == 0) {
                         const double* c = S.consts + (j / B) * (int64_t)(kNF * B) + (j % B);
                         const double cA = __ldcg(c + F_A * B), cB = __ldcg(c + F_B * B), cT = __ldcg(c + F_T * B);
                         const double cC = __ldcg(c + F_C * B), cQ = __ldcg(c + F_QSZ * B), d = __ldcg(c + F_D * B);
                         const double bold = __ldcg(c + F_BOLD * B), mean = __ldcg(c + F_MEAN * B), chi = __ldcg(c + F_CHI * B);
-                        gs.wait_warp();
-                        const long long cur = __ldcg(acc);
                         long long* pv = prev + slot * (kMaxB + 1);
-                        const double A = (double)(cur - *pv) * fx_inv;
+                        long long cur;
+                        do { cur = ld_relaxed_s64(acc); } while (((cur - *pv) & 0xFF) != (long long)P.T);
+                        const double A = (double)((cur - *pv - (long long)P.T) >> kCntBits) * fx_inv;
                         __syncwarp();
                         if (lane == 0) *pv = cur;
                         const double r = 4.0 * (A - Stot) - mean * Stot;
@@ -472,11 +476,6 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                 S.beta[j] = bn;
                                 if (S.method != 0) S.delta[j] = in ? 1 : 0;
                                 if (S.method == 1) S.varBeta[j] = in ? (S.scale * S.df + bn * bn) / chi : 0.0;
-                                if (P.accumulate) {
-                                    S.sum_beta[j] += bn;
-                                    S.sum_beta2[j] = fma(bn, bn, S.sum_beta2[j]);
-                                    S.sum_delta[j] += (S.method == 0) ? 1.0 : (in ? 1.0 : 0.0);
-                                }
                             }
                         }
                     }
@@ -524,13 +523,24 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     }
                 }
             }
-            if (regional) {
-                // beta of this sweep was written by CTA 0: one barrier, then regions are spread over all warps
+            if (regional || P.accumulate) {
+                // beta / delta of this sweep were written by CTA 0 (plain stores, off the critical path): one grid
+                // barrier, then the posterior sums and the region variances are spread over the whole grid
                 __syncthreads();
                 gs.nbar++;
                 if (tid == 0) gs.arrive();
                 if (warp == 0) gs.wait_warp();
                 __syncthreads();
+            }
+            if (P.accumulate) {
+                for (int64_t j = (int64_t)t * kThreads + tid; j < S.p; j += (int64_t)P.T * kThreads) {
+                    const double bj = __ldcg(&S.beta[j]);
+                    S.sum_beta[j] += bj;
+                    S.sum_beta2[j] = fma(bj, bj, S.sum_beta2[j]);
+                    S.sum_delta[j] += (S.method == 0) ? 1.0 : (double)__ldcg(&S.delta[j]);
+                }
+            }
+            if (regional) {
                 Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)s};
                 for (int64_t rg = (int64_t)t * kWarps + warp; rg < S.n_regions; rg += (int64_t)P.T * kWarps) {
                     const int64_t j0 = S.region_off[rg], j1 = S.region_off[rg + 1];
