@@ -178,9 +178,12 @@ int ngp_reset_posterior(ngp_handle* h);
 int ngp_get_posterior(ngp_handle* h, int set_id, int64_t* n_samples, double* sum_beta, double* sum_beta2, double* sum_delta);
 int ngp_get_timing(ngp_handle* h, ngp_timing* out);
 
-/* per-CTA cycle counters of the last launch, 8 int64 per CTA (thread 0 of each CTA, blocked kernel):
- * [0] TMA wait [1] dot phase [2] reduce+arrive [3] grid-barrier wait [4] scalar chain [5] axpy
- * [6] markers whose effect changed [7] speculative evaluations.  Returns the number of CTAs written. */
+/* per-CTA cycle counters of the last launch, 16 int64 per CTA (clock64; blocked kernel).
+ * chain warp (thread 0): [0] tile wait [3] accumulator poll [4] scalar chain [5] wait for workers
+ *                        [6] markers whose effect changed [7] speculative evaluations
+ *                        [8] phase 0 (varE, intercept) [9] phase 1 (marker constants) [11] phase 3 [12] TMA issue
+ * first worker warp (thread 32): [1] dot + RED [2] axpy [10] wait for the chain warp.
+ * Returns the number of CTAs written. */
 int ngp_get_profile(ngp_handle* h, int64_t* out, int32_t max_ctas);
 
 /* stream self-test: fills out[0..n) with the handle's variates of one purpose

@@ -393,8 +393,8 @@ class Sampler:
         return {k: getattr(t, k) for k, _ in L.Timing._fields_}
 
     def profile(self) -> np.ndarray:
-        """(ctas, 8) int64 cycle counters of the last launch, see ngp_get_profile."""
-        out = np.zeros((160, 8), dtype=np.int64)
+        """(ctas, 16) int64 cycle counters of the last launch, see ngp_get_profile."""
+        out = np.zeros((160, 16), dtype=np.int64)
         nc = self._lib.ngp_get_profile(self._h, _p(out), 160)
         if nc < 0:
             self._ck(nc)

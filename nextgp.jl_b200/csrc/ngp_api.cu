@@ -77,45 +77,60 @@ __global__ void colstats_kernel(int64_t n, int64_t p, int64_t p_pad, const int32
     } else { mean[j] = 0.0; d[j] = 0.0; }
 }
 
-// raw block Gram G[k][a][b] = sum_i g_ia g_ib over all panels; one CTA (16x16 threads) per block of B markers
+// raw block Grams over all panels, one CTA (16x16 threads) per block k of B markers:
+//   gram [k][a][b] = sum_i g_{kB+a,i} g_{kB+b,i}          (inside the block)
+//   gramx[k][a][b] = sum_i g_{(k-1)B+a,i} g_{kB+b,i}      (previous block x this block; zeros for k = 0)
+// integer-exact (__dp4a on the 2-bit codes), built once per upload.
 template <int B>
 __global__ void __launch_bounds__(256) gram_kernel(const uint8_t* __restrict__ geno, int T, int R, int64_t p_pad,
-                                                   int32_t* __restrict__ gram)
+                                                   uint8_t* __restrict__ blk, int32_t* __restrict__ gramx)
 {
     extern __shared__ __align__(16) unsigned char gsm[];
     constexpr int TB = B / 16;
     const int k = blockIdx.x, tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int W = R >> 2;
-    int acc[TB][TB];
+    int acc[TB][TB], accx[TB][TB];
 #pragma unroll
     for (int i = 0; i < TB; ++i)
 #pragma unroll
-        for (int q = 0; q < TB; ++q) acc[i][q] = 0;
+        for (int q = 0; q < TB; ++q) { acc[i][q] = 0; accx[i][q] = 0; }
     const int nvec = (B * R) >> 4;
+    uint4* dst = reinterpret_cast<uint4*>(gsm);
     for (int t = 0; t < T; ++t) {
         const uint4* src = reinterpret_cast<const uint4*>(geno + ((int64_t)t * p_pad + (int64_t)k * B) * R);
-        uint4* dst = reinterpret_cast<uint4*>(gsm);
         for (int v = threadIdx.x; v < nvec; v += 256) dst[v] = __ldg(src + v);
+        if (k > 0) {
+            const uint4* srcp = reinterpret_cast<const uint4*>(geno + ((int64_t)t * p_pad + (int64_t)(k - 1) * B) * R);
+            for (int v = threadIdx.x; v < nvec; v += 256) dst[nvec + v] = __ldg(srcp + v);
+        }
         __syncthreads();
         const uint32_t* tw = reinterpret_cast<const uint32_t*>(gsm);
+        const uint32_t* tp = tw + (B * R >> 2);
         for (int w = 0; w < W; ++w) {
-            int a[TB], b[TB];
+            int a[TB], b[TB], ap[TB];
 #pragma unroll
             for (int i = 0; i < TB; ++i) {
                 a[i] = (int)((tw[(ty * TB + i) * W + w] >> 2) & 0x03030303u);
                 b[i] = (int)((tw[(tx * TB + i) * W + w] >> 2) & 0x03030303u);
+                ap[i] = (k > 0) ? (int)((tp[(ty * TB + i) * W + w] >> 2) & 0x03030303u) : 0;
             }
 #pragma unroll
             for (int i = 0; i < TB; ++i)
 #pragma unroll
-                for (int q = 0; q < TB; ++q) acc[i][q] = __dp4a(a[i], b[q], acc[i][q]);
+                for (int q = 0; q < TB; ++q) {
+                    acc[i][q] = __dp4a(a[i], b[q], acc[i][q]);
+                    accx[i][q] = __dp4a(ap[i], b[q], accx[i][q]);
+                }
         }
         __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < TB; ++i)
 #pragma unroll
-        for (int q = 0; q < TB; ++q) gram[(int64_t)k * B * B + (ty * TB + i) * B + tx * TB + q] = acc[i][q];
+        for (int q = 0; q < TB; ++q) {
+            reinterpret_cast<int32_t*>(blk + (int64_t)k * blk_bytes(B))[(ty * TB + i) * B + tx * TB + q] = acc[i][q];
+            gramx[(int64_t)k * B * B + (ty * TB + i) * B + tx * TB + q] = accx[i][q];
+        }
 }
 
 __global__ void synth_kernel(uint32_t key0, uint32_t key1, int64_t n, int64_t j0, int64_t ncols,
@@ -182,9 +197,9 @@ struct SetHost {
     int64_t p = 0, p_pad = 0, nvar = 0, n_regions = 0;
     int method = 0, est_pi = 0, storage = 0;
     double df = 4.0, scale = 0.0, var_init = 0.0, pi_in = 0.0;
-    uint8_t* geno = nullptr;
-    int32_t *gram = nullptr, *colsum = nullptr, *colsumsq = nullptr, *delta = nullptr, *region_of = nullptr;
-    double *d = nullptr, *mean = nullptr, *beta = nullptr, *varBeta = nullptr, *pi = nullptr, *consts = nullptr;
+    uint8_t *geno = nullptr, *blk = nullptr;
+    int32_t *gramx = nullptr, *colsum = nullptr, *colsumsq = nullptr, *delta = nullptr, *region_of = nullptr;
+    double *d = nullptr, *mean = nullptr, *beta = nullptr, *varBeta = nullptr, *pi = nullptr;
     double *lhs0 = nullptr, *rhs0 = nullptr, *sum_beta = nullptr, *sum_beta2 = nullptr, *sum_delta = nullptr;
     int64_t* region_off = nullptr;
     double *rp_u = nullptr, *rp_z = nullptr, *rp_chi2b = nullptr, *rp_betapi = nullptr;
@@ -262,8 +277,8 @@ static cudaError_t dalloc(Tp** p, size_t count)
 
 static void free_set(SetHost& s)
 {
-    cudaFree(s.geno); cudaFree(s.gram); cudaFree(s.colsum); cudaFree(s.colsumsq); cudaFree(s.delta); cudaFree(s.region_of);
-    cudaFree(s.d); cudaFree(s.mean); cudaFree(s.beta); cudaFree(s.varBeta); cudaFree(s.pi); cudaFree(s.consts);
+    cudaFree(s.geno); cudaFree(s.blk); cudaFree(s.gramx); cudaFree(s.colsum); cudaFree(s.colsumsq); cudaFree(s.delta); cudaFree(s.region_of);
+    cudaFree(s.d); cudaFree(s.mean); cudaFree(s.beta); cudaFree(s.varBeta); cudaFree(s.pi);
     cudaFree(s.lhs0); cudaFree(s.rhs0); cudaFree(s.sum_beta); cudaFree(s.sum_beta2); cudaFree(s.sum_delta);
     cudaFree(s.region_off); cudaFree(s.rp_u); cudaFree(s.rp_z); cudaFree(s.rp_chi2b); cudaFree(s.rp_betapi);
     s = SetHost();
@@ -377,7 +392,7 @@ static int choose_geometry(ngp_handle* h, int64_t n)
     const int64_t R = 8 * R8;
     const size_t cap = h->prop.sharedMemPerBlockOptin;
     const int candB[2] = {64, 32};
-    const int candS[2] = {3, 2};
+    const int candS[2] = {4, 3};                   // look-ahead pipeline: tiles k-1, k, k+1 live + one in flight
     for (int bi = 0; bi < 2; ++bi) {
         if (h->cfg_block && candB[bi] != h->cfg_block) continue;
         for (int si = 0; si < 2; ++si) {
@@ -400,17 +415,18 @@ static int finish_upload(ngp_handle* h, SetHost& S)
     colstats_kernel<<<(unsigned)((p_pad + 255) / 256), 256, 0, h->stream>>>(h->n, S.p, p_pad, S.colsum, S.colsumsq, S.mean, S.d);
     CU(cudaGetLastError());
     const int nblk = (int)(p_pad / h->B);
-    CU(dalloc(&S.gram, (size_t)nblk * h->B * h->B));
-    const size_t gsm = (size_t)h->B * h->R;
+    CU(dalloc(&S.blk, (size_t)nblk * blk_bytes(h->B)));
+    CU(zero(h, S.blk, 0, (size_t)nblk * blk_bytes(h->B)));
+    CU(dalloc(&S.gramx, (size_t)nblk * h->B * h->B));
+    const size_t gsm = 2 * (size_t)h->B * h->R;
     if (h->B == 64) {
         CU(cudaFuncSetAttribute(gram_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-        gram_kernel<64><<<nblk, 256, gsm, h->stream>>>(S.geno, h->T, h->R, p_pad, S.gram);
+        gram_kernel<64><<<nblk, 256, gsm, h->stream>>>(S.geno, h->T, h->R, p_pad, S.blk, S.gramx);
     } else {
         CU(cudaFuncSetAttribute(gram_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-        gram_kernel<32><<<nblk, 256, gsm, h->stream>>>(S.geno, h->T, h->R, p_pad, S.gram);
+        gram_kernel<32><<<nblk, 256, gsm, h->stream>>>(S.geno, h->T, h->R, p_pad, S.blk, S.gramx);
     }
     CU(cudaGetLastError());
-    CU(dalloc(&S.consts, (size_t)nblk * kNF * h->B));
     CU(dalloc(&S.beta, p_pad));
     CU(dalloc(&S.delta, p_pad));
     CU(cudaMemsetAsync(S.beta, 0, sizeof(double) * p_pad, h->stream));
@@ -729,9 +745,9 @@ static int sync_sets(ngp_handle* h)
         if (!S.have_geno || !S.have_prior) continue;
         SetDev& D = sd[s];
         D.p = S.p; D.p_pad = S.p_pad; D.method = S.method; D.est_pi = S.est_pi; D.n_regions = S.n_regions; D.nvar = S.nvar;
-        D.df = S.df; D.scale = S.scale; D.geno = S.geno; D.gram = S.gram; D.colsum = S.colsum; D.d = S.d; D.mean = S.mean;
+        D.df = S.df; D.scale = S.scale; D.geno = S.geno; D.blk = S.blk; D.gramx = S.gramx; D.colsum = S.colsum; D.d = S.d; D.mean = S.mean;
         D.beta = S.beta; D.delta = S.delta; D.varBeta = S.varBeta; D.pi = S.pi; D.region_of = S.region_of; D.region_off = S.region_off;
-        D.lhs0 = S.lhs0; D.rhs0 = S.rhs0; D.consts = S.consts;
+        D.lhs0 = S.lhs0; D.rhs0 = S.rhs0;
         D.rp_u = S.rp_u; D.rp_z = S.rp_z; D.rp_chi2b = S.rp_chi2b; D.rp_betapi = S.rp_betapi;
         D.sum_beta = S.sum_beta; D.sum_beta2 = S.sum_beta2; D.sum_delta = S.sum_delta;
     }
@@ -935,7 +951,7 @@ int ngp_get_profile(ngp_handle* h, int64_t* out, int32_t max_ctas)
     if (!h || !out || max_ctas <= 0) return fail(h, NGP_EINVAL, "ngp_get_profile: bad argument");
     CU(cudaSetDevice(h->device));
     const int nc = std::min<int>(max_ctas, h->T);
-    CU(cpy(h, out, h->sync->prof, sizeof(long long) * 8 * nc, cudaMemcpyDeviceToHost));
+    CU(cpy(h, out, h->sync->prof, sizeof(long long) * kProf * nc, cudaMemcpyDeviceToHost));
     return nc;
 }
 

@@ -18,11 +18,14 @@
 
 namespace ngp {
 
-constexpr int kThreads = 256;          // sweep kernel: 8 warps
+constexpr int kThreads = 320;          // sweep kernel: warp 0 = chain warp, warps 1..8 = workers, warp 9 = TMA producer
 constexpr int kWarps = kThreads / 32;
+constexpr int kWorkerWarps = 8;
+constexpr int kProducerWarp = kWorkerWarps + 1;
+constexpr int kProf = 16;              // cycle counters per CTA (ngp_get_profile)
 constexpr int kMaxB = 64;              // markers per block (32 or 64)
 constexpr int kNF = 10;                // per-marker constant fields
-constexpr int kSlots = 2;              // reduction accumulator ring
+constexpr int kSlots = 4;              // reduction accumulator ring (look-ahead 1 needs >= 4)
 constexpr int kAccStride = 32;         // int64 units between accumulators (256 B: distinct L2 slices)
 constexpr int kMaxCtas = 160;          // < 256: the low byte of an accumulator counts arrivals
 constexpr int kCntBits = 8;
@@ -36,7 +39,9 @@ struct SetDev {
     int64_t n_regions, nvar;
     double df, scale;
     const uint8_t* geno;       // [T][p_pad][R]
-    const int32_t* gram;       // [p_pad/B][B][B] raw sum g_a g_b
+    uint8_t* blk;              // [p_pad/B] records {int32 gram[B][B]; double consts[kNF][B]}: raw Gram inside block k
+                               //   (sum_i g_a g_b) + the per-iteration marker constants, one TMA bulk copy per block
+    const int32_t* gramx;      // [p_pad/B][B][B] raw sum g_a g_b, a in block k-1, b in block k (block 0: zeros)
     const int32_t* colsum;     // [p_pad]
     const double* d;           // [p_pad] mpm
     const double* mean;        // [p_pad]
@@ -48,7 +53,6 @@ struct SetDev {
     const int64_t* region_off; // [n_regions+1] or null
     const double* lhs0;        // [p] or null
     const double* rhs0;        // [p] or null
-    double* consts;            // [p_pad/B][kNF][B]
     const double* rp_u;        // replay arrays (device) or null
     const double* rp_z;
     const double* rp_chi2b;
@@ -63,7 +67,8 @@ struct SyncArea {
     unsigned long long pad0[15];
     long long acc[kSlots * (kMaxB + 1) * kAccStride];   // fixed-point reduction accumulators (monotonic)
     double part[kMaxCtas * 2];                  // phase-0 partials (e'e, sum e) per CTA
-    long long prof[kMaxCtas * 8];               // per-CTA cycle counters of the last launch (thread 0): see ngp_get_profile
+    int zero16[16];                             // runtime zeros (low words of the fp64 code operands, see dec_byte_z)
+    long long prof[kMaxCtas * kProf];           // per-CTA cycle counters of the last launch: see ngp_get_profile
     int err;
 };
 
@@ -149,6 +154,14 @@ __device__ __forceinline__ double dec_byte(uint32_t w, int k)
     const uint32_t hi = __byte_perm(w, 0x3F000000u, 0x7044u | ((uint32_t)k << 8));
     return __hiloint2double((int)hi, 0);
 }
+// same with the low word taken from a register that holds a RUNTIME zero: the compiler cannot fold it, so it keeps
+// the zero in the even register of the operand pair and the PRMT writes the odd one in place (no MOV per code)
+__device__ __forceinline__ double dec_byte_z(uint32_t w, int k, int z)
+{
+    const uint32_t hi = __byte_perm(w, 0x3F000000u, 0x7044u | ((uint32_t)k << 8));
+    return __hiloint2double((int)hi, z);
+}
+__host__ __device__ __forceinline__ int blk_bytes(int B) { return B * B * 4 + kNF * B * 8; }
 __host__ __device__ __forceinline__ uint8_t enc_code(int g) { return (uint8_t)(0xF0 | (g << 2)); }
 __host__ __device__ __forceinline__ int dec_code(uint8_t b) { return (b >> 2) & 3; }
 

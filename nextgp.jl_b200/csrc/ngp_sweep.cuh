@@ -6,25 +6,23 @@
 //   phase 1  per-marker constants + variates for every marker set (grid-parallel)
 //   phase 2  the marker sweep (functions.jl:118-137 / 157-195 / 197-236), CTA t owning
 //            row panel t of the genotypes and of the residual e (resident in smem)
-//   phase 3  variance components and pi (functions.jl:509-511, 531-533)
+//   phase 3  variance components and pi (functions.jl:509-511, 531-533), posterior sums
 //
-// Phase 2, blocked exact sweep:  for a block of B markers
-//   a) TMA (cp.async.bulk) has prefetched the panel's B*R-byte tile, the block's
-//      raw Gram G = sum_i g_ia g_ib and its per-marker constants into smem;
-//   b) every CTA forms its B partial sums A_j = sum_i (1 + g_ij/4) e_i with one
-//      PRMT + one DFMA per code, converts them to fixed point and adds
-//      (value << 8) + 1 into global int64 accumulators with one RED each: integer
-//      adds are associative (bit-reproducible) and the low byte counts arrivals, so
-//      the accumulator is its own barrier - no fence, no separate counter: ONE
-//      grid-wide reduction per B markers, whose latency is one RED + one poll;
-//   c) warp 0 of every CTA redundantly runs the B dependent scalar updates
-//        r_j <- 4(A_j - S) - m_j S - sum_{k<j} Gc_jk dbeta_k ,  Gc = G - s_j s_k / n
-//      (identical inputs + identical code => identical results, no broadcast);
-//      for the mixture priors the 32 lanes evaluate 32 markers speculatively and
-//      only serialise on markers whose effect actually changes;
-//   d) all threads apply e -= sum_j dbeta_j (g_j - m_j) from the SAME smem tile,
-//      so every column is read from HBM once per sweep.
-// The "literal" variant does a) - d) per marker from registers with one grid-wide
+// Phase 2, blocked exact sweep with one block of look-ahead.
+// Warp 0 of every CTA is the "chain warp", warps 1..8 are "workers".  In step k
+//   workers : e -= X_{k-1} dbeta_{k-1}            (tile k-1 still in smem: column read from HBM once)
+//             A_{k+1} = sum_i (1 + g/4) e_i        (tile k+1, prefetched by TMA; one PRMT + one DFMA per code)
+//             fixed point, RED (value<<8)+1 into the global int64 accumulators of block k+1:
+//             integer adds are associative (bit-reproducible) and the low byte counts arrivals,
+//             so an accumulator is its own barrier - no fence, no counter, no grid-wide stall;
+//   chain   : polls the accumulators of block k (their REDs were issued one step earlier),
+//             r_j = 4(A_j - S) - m_j S - [cross-Gram rows of block k-1] dbeta_{k-1} - [Gram rows of block k] dbeta_k,
+//             runs the B dependent scalar updates redundantly in every CTA (identical inputs and code =>
+//             identical results, no broadcast); mixture priors: 32 lanes evaluate 32 markers speculatively
+//             and serialise only on markers whose effect actually changes.
+// The dots of block k+1 therefore never wait for the chain of block k: its effect on them is restored
+// exactly by G_{k+1,k} dbeta_k (integer Gram, precomputed once).
+// The "literal" variant does dot / reduce / draw / axpy per marker from registers with one grid-wide
 // reduction per marker (the north-star baseline whose sync cost we report).
 #pragma once
 #include "ngp_device.cuh"
@@ -32,8 +30,8 @@
 namespace ngp {
 
 struct SmemLayout {
-    int off_e, off_tile, off_gram, off_cst, off_red, off_prev, off_nzdb, off_nzidx, off_misc, off_mbar, total;
-    int tile_bytes, gram_bytes, cst_bytes;
+    int off_e, off_tile, off_blk, off_red, off_prev, off_nzdb, off_nzcs, off_nzidx, off_outb, off_outv, off_outi, off_misc, off_mbar, total;
+    int tile_bytes, blk_bytes;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(int R, int B, int stages)
@@ -41,16 +39,18 @@ __host__ __device__ inline SmemLayout smem_layout(int R, int B, int stages)
     SmemLayout L;
     int o = 0;
     L.tile_bytes = B * R;
-    L.gram_bytes = B * B * 4;
-    L.cst_bytes = kNF * B * 8;
+    L.blk_bytes = blk_bytes(B);
     L.off_e = o;      o += R * 8;
     L.off_tile = o;   o += stages * L.tile_bytes;
-    L.off_gram = o;   o += stages * L.gram_bytes;
-    L.off_cst = o;    o += stages * L.cst_bytes;
-    L.off_red = o;    o += kWarps * 32 * 8;
+    L.off_blk = o;    o += stages * L.blk_bytes;
+    L.off_red = o;    o += 2 * kWorkerWarps * kMaxB * 8;
     L.off_prev = o;   o += kSlots * (kMaxB + 1) * 8;
-    L.off_nzdb = o;   o += kMaxB * 8;
-    L.off_nzidx = o;  o += kMaxB * 4;
+    L.off_nzdb = o;   o += 2 * kMaxB * 8;
+    L.off_nzcs = o;   o += 2 * kMaxB * 8;
+    L.off_nzidx = o;  o += 2 * kMaxB * 4;
+    L.off_outb = o;   o += 2 * kMaxB * 8;
+    L.off_outv = o;   o += 2 * kMaxB * 8;
+    L.off_outi = o;   o += 2 * kMaxB * 4;
     L.off_misc = o;   o += 64 * 8;
     L.off_mbar = o;   o += 8 * 8;
     L.total = o;
@@ -79,6 +79,8 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch
     __syncthreads();
     a = sa; b = sb;
 }
+
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerWarps * 32) : "memory"); }
 
 struct GridSync {
     unsigned long long* counter;
@@ -109,7 +111,7 @@ __device__ __forceinline__ void prep_marker(const Params& P, const SetDev& S, in
                                             uint32_t iter, int64_t rp_row)
 {
     const int B = P.B;
-    double* c = S.consts + (j / B) * (int64_t)(kNF * B) + (j % B);
+    double* c = reinterpret_cast<double*>(S.blk + (j / B) * (int64_t)blk_bytes(B) + B * B * 4) + (j % B);
     double fA = 0.0, fB = 0.0, fT = -INFINITY, fC = 0.0, fQSZ = 0.0, fD = 0.0, fBOLD = 0.0, fMEAN = 0.0, fCS = 0.0, fCHI = 1.0;
     if (j < S.p) {
         const double d = S.d[j];
@@ -157,11 +159,16 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     double* e_s = reinterpret_cast<double*>(smem + L.off_e);
     double* red = reinterpret_cast<double*>(smem + L.off_red);
     long long* prev = reinterpret_cast<long long*>(smem + L.off_prev);
-    double* nz_db = reinterpret_cast<double*>(smem + L.off_nzdb);
-    int* nz_idx = reinterpret_cast<int*>(smem + L.off_nzidx);
-    double* misc = reinterpret_cast<double*>(smem + L.off_misc);
+    double* nz_db = reinterpret_cast<double*>(smem + L.off_nzdb);      // [2][kMaxB]  4*dbeta of the changed markers of a block
+    double* nz_cs = reinterpret_cast<double*>(smem + L.off_nzcs);      // [2][kMaxB]  their column sums
+    int* nz_idx = reinterpret_cast<int*>(smem + L.off_nzidx);          // [2][kMaxB]  their index inside the block
+    double* out_b = reinterpret_cast<double*>(smem + L.off_outb);      // [2][kMaxB] staged outputs of a block (written to HBM by the producer warp of CTA 0)
+    double* out_v = reinterpret_cast<double*>(smem + L.off_outv);
+    int* out_i = reinterpret_cast<int*>(smem + L.off_outi);
+    double* misc = reinterpret_cast<double*>(smem + L.off_misc);       // [0..17] block_sum scratch, [32..] scalars, [40+2i] nnz, [41+2i] K
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L.off_mbar);
     SyncArea* sy = P.sync;
+    constexpr int NB = B >> 5;             // 32-marker groups per block (lane <-> marker b*32 + lane)
 
     GridSync gs{&sy->counter, 0ull, (unsigned)P.T};
     const int64_t row0 = (int64_t)t * R;
@@ -175,17 +182,21 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     }
     __syncthreads();
 
-    long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cycles: 0 tma-wait 1 dot 2 reduce+arrive 3 barrier-wait 4 chain 5 axpy 6 nnz 7 spec-evals
+    // cycle counters (thread 0 = chain warp, thread 32 = first worker warp), see ngp_get_profile
+    long long pf[kProf];
+#pragma unroll
+    for (int i = 0; i < kProf; ++i) pf[i] = 0;
     long long tc = clock64();
 #define NGP_TICK(i) do { const long long now__ = clock64(); pf[i] += now__ - tc; tc = now__; } while (0)
-    long long gk = 0;        // running tile count (mbarrier stage / parity)
-    long long rk = 0;        // running reduction count (accumulator slot)
+    unsigned gk = 0;         // tile ring position in [0, 2*stages): stage = gk mod stages, mbarrier parity = (gk div stages) & 1
+    unsigned rk = 0;         // running reduction count (accumulator slot = rk & (kSlots-1))
     double mu = P.sc->mu;
     const long long iter0 = P.sc->iter;
 
     for (int it = 0; it < P.n_iter; ++it) {
         const uint32_t iter = (uint32_t)(iter0 + it + 1);
         const int64_t rp_row = (int64_t)iter - 1 - P.replay_base;
+        tc = clock64();
 
         // ------------------------------------------------------------------ phase 0
         double ee = 0.0, se = 0.0;
@@ -236,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         mu = misc[36];
         const double fx_scale = ldexp(1.0, sh), fx_inv = ldexp(1.0, -sh);
         if (dmu != 0.0) for (int r = tid; r < nrow; r += kThreads) e_s[r] += dmu;
+        NGP_TICK(8);
 
         // ------------------------------------------------------------------ phase 1
         for (int s = 0; s < P.n_sets; ++s) {
@@ -249,6 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         if (tid == 0) gs.arrive();
         if (warp == 0) gs.wait_warp();
         __syncthreads();
+        NGP_TICK(9);
 
         // ------------------------------------------------------------------ phase 2 + 3 per marker set
         for (int s = 0; s < P.n_sets; ++s) {
@@ -256,78 +269,158 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
             const SetDev& S = P.sets[s];
             const int nblk = (int)(S.p_pad / B);
             const double inv_n = 1.0 / (double)P.n;
+            // hot-loop copies of the set descriptor (it lives in global memory; the volatile polls would force reloads)
+            const int method = S.method;
+            const int64_t p_real = S.p;
+            double* const beta_g = S.beta;
+            int32_t* const delta_g = S.delta;
+            double* const vb_g = S.varBeta;
+            const int32_t* const gramx_g = S.gramx;
+            const uint8_t* const blk_g = S.blk;
+            const double sdf = S.scale * S.df;
             double acc_bb = 0.0, acc_n = 0.0;          // warp 0: per-lane partials of beta'beta and nLoci
+            tc = clock64();
 
             if (P.kernel == 0) {
-                // ============================ blocked exact sweep ============================
+                // ============================ blocked exact sweep, one block of look-ahead ============================
                 const uint8_t* gbase = S.geno + (int64_t)t * S.p_pad * R;
-                auto issue = [&](int k, long long g) {
-                    const int stg = (int)(g % S_);
-                    mbar_expect_tx(&mbar[stg], (uint32_t)(L.tile_bytes + L.gram_bytes + L.cst_bytes));
+                // stages is 3 or 4: no runtime integer division on the per-block path
+                auto stage_of = [&](int k) { const unsigned x = gk + (unsigned)k; return (int)(S_ == 4 ? (x & 3u) : (x % 3u)); };
+                auto parity_of = [&](int k) { const unsigned x = gk + (unsigned)k; return (uint32_t)((S_ == 4 ? (x >> 2) : (x / 3u)) & 1u); };
+                auto issue = [&](int k) {
+                    const int stg = stage_of(k);
+                    mbar_expect_tx(&mbar[stg], (uint32_t)(L.tile_bytes + L.blk_bytes));
                     bulk_g2s(smem + L.off_tile + stg * L.tile_bytes, gbase + (int64_t)k * B * R, (uint32_t)L.tile_bytes, &mbar[stg]);
-                    bulk_g2s(smem + L.off_gram + stg * L.gram_bytes, S.gram + (int64_t)k * B * B, (uint32_t)L.gram_bytes, &mbar[stg]);
-                    bulk_g2s(smem + L.off_cst + stg * L.cst_bytes, S.consts + (int64_t)k * kNF * B, (uint32_t)L.cst_bytes, &mbar[stg]);
+                    bulk_g2s(smem + L.off_blk + stg * L.blk_bytes, blk_g + (int64_t)k * L.blk_bytes, (uint32_t)L.blk_bytes, &mbar[stg]);
                 };
-                if (tid == 0) {
+                if (tid == kProducerWarp * 32) {
                     fence_proxy_async();     // consts were written through the generic proxy by other CTAs
-                    for (int k = 0; k < min(S_, nblk); ++k) issue(k, gk + k);
+                    for (int k = 0; k < min(S_, nblk); ++k) issue(k);
                 }
-                constexpr int MG = B >> 5;             // marker groups of 32
-                constexpr int RC = kWarps / MG;        // row chunks
-                const int mg = warp % MG, rc = warp / MG;
+                if (tid == 0) { misc[40] = 0.0; misc[42] = 0.0; }      // nnz of the two nz lists
+                const int wtid = tid - 32;                  // worker thread id (0..255), negative in the chain warp
+                const int ww = warp - 1;                    // worker warp id
                 const int ngrp = R >> 3;
-                const int g0 = (rc * ngrp) / RC, g1 = ((rc + 1) * ngrp) / RC;
+                const int g0 = (ww * ngrp) / kWorkerWarps, g1 = ((ww + 1) * ngrp) / kWorkerWarps;
 
-                for (int k = 0; k < nblk; ++k, ++gk, ++rk) {
-                    const int stg = (int)(gk % S_);
-                    const uint32_t par = (uint32_t)((gk / S_) & 1);
+                int zl[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) zl[i] = __ldg(&sy->zero16[i]);      // runtime zeros, see dec_byte_z
+                const int r_lo = 8 * g0, r_hi = min(8 * g1, nrow);               // the rows this worker warp owns (dot AND axpy)
+
+                // partial sums of block kk over this warp's rows: lane <-> markers lane, 32+lane
+                auto worker_dot = [&](int kk) {
+                    const int stg = stage_of(kk);
+                    mbar_wait(&mbar[stg], parity_of(kk));
                     const uint8_t* tile = smem + L.off_tile + stg * L.tile_bytes;
-                    const int32_t* gram = reinterpret_cast<const int32_t*>(smem + L.off_gram + stg * L.gram_bytes);
-                    const double* cst = reinterpret_cast<const double*>(smem + L.off_cst + stg * L.cst_bytes);
-                    const int slot = (int)(rk % kSlots);
-                    long long* acc = sy->acc + (int64_t)slot * (kMaxB + 1) * kAccStride;
-                    tc = clock64();
-                    mbar_wait(&mbar[stg], par);
-                    NGP_TICK(0);
-
-                    // ---- b) partial dots: lane <-> marker, warps split the rows
-                    {
-                        const uint8_t* col = tile + (mg * 32 + lane) * R;
-                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll 2
-                        for (int g = g0; g < g1; ++g) {
-                            const uint2 w = *reinterpret_cast<const uint2*>(col + 8 * g);
-                            const double2* ep = reinterpret_cast<const double2*>(e_s + 8 * g);
-                            const double2 e01 = ep[0], e23 = ep[1], e45 = ep[2], e67 = ep[3];
-                            a0 = fma(dec_byte(w.x, 0), e01.x, a0);
-                            a1 = fma(dec_byte(w.x, 1), e01.y, a1);
-                            a2 = fma(dec_byte(w.x, 2), e23.x, a2);
-                            a3 = fma(dec_byte(w.x, 3), e23.y, a3);
-                            a0 = fma(dec_byte(w.y, 0), e45.x, a0);
-                            a1 = fma(dec_byte(w.y, 1), e45.y, a1);
-                            a2 = fma(dec_byte(w.y, 2), e67.x, a2);
-                            a3 = fma(dec_byte(w.y, 3), e67.y, a3);
+                    double* redk = red + (kk & 1) * (kWorkerWarps * kMaxB);     // double-buffered: one barrier per block
+                    double a[NB][4];
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) { a[b][0] = a[b][1] = a[b][2] = a[b][3] = 0.0; }
+                    for (int g = g0; g < g1; ++g) {
+                        const double2* ep = reinterpret_cast<const double2*>(e_s + 8 * g);
+                        const double2 e01 = ep[0], e23 = ep[1], e45 = ep[2], e67 = ep[3];
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) {
+                            const uint2 w = *reinterpret_cast<const uint2*>(tile + (b * 32 + lane) * R + 8 * g);
+                            a[b][0] = fma(dec_byte_z(w.x, 0, zl[0]), e01.x, a[b][0]);
+                            a[b][1] = fma(dec_byte_z(w.x, 1, zl[1]), e01.y, a[b][1]);
+                            a[b][2] = fma(dec_byte_z(w.x, 2, zl[2]), e23.x, a[b][2]);
+                            a[b][3] = fma(dec_byte_z(w.x, 3, zl[3]), e23.y, a[b][3]);
+                            a[b][0] = fma(dec_byte_z(w.y, 0, zl[4]), e45.x, a[b][0]);
+                            a[b][1] = fma(dec_byte_z(w.y, 1, zl[5]), e45.y, a[b][1]);
+                            a[b][2] = fma(dec_byte_z(w.y, 2, zl[6]), e67.x, a[b][2]);
+                            a[b][3] = fma(dec_byte_z(w.y, 3, zl[7]), e67.y, a[b][3]);
                         }
-                        red[rc * B + mg * 32 + lane] = (a0 + a1) + (a2 + a3);
                     }
-                    __syncthreads();
-                    NGP_TICK(1);
-                    if (tid < B) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) redk[ww * B + b * 32 + lane] = (a[b][0] + a[b][1]) + (a[b][2] + a[b][3]);
+                    worker_bar();
+                    if (wtid < B) {
                         double A = 0.0;
-                        for (int c = 0; c < RC; ++c) A += red[c * B + tid];
+#pragma unroll
+                        for (int c = 0; c < kWorkerWarps; ++c) A += redk[c * B + wtid];
                         const double xs = A * fx_scale;
                         if (!(fabs(xs) < 9007199254740992.0)) atomicOr(&sy->err, 1);     // 2^53 << 8 still fits
-                        red_add_u64(acc + tid * kAccStride, (__double2ll_rn(xs) << kCntBits) + 1);
+                        long long* acc = sy->acc + (int64_t)((rk + (unsigned)kk) & (kSlots - 1)) * (kMaxB + 1) * kAccStride;
+                        red_add_u64(acc + wtid * kAccStride, (__double2ll_rn(xs) << kCntBits) + 1);
                     }
-                    NGP_TICK(2);
+                };
+                // e -= sum_q dbeta_q (g_q - m_q) for the changed markers of block kk, from its smem tile;
+                // every worker warp updates exactly the rows its own dots read, so no CTA-wide barrier is needed
+                auto worker_axpy = [&](int kk) {
+                    const int li = kk & 1;
+                    const int nnz = (int)misc[40 + 2 * li];
+                    if (nnz == 0) return;
+                    const double K = misc[41 + 2 * li];
+                    const uint8_t* tile = smem + L.off_tile + stage_of(kk) * L.tile_bytes;
+                    for (int r = r_lo + lane; r < r_hi; r += 32) {
+                        double sacc = 0.0;
+                        for (int q = 0; q < nnz; ++q) {
+                            const uint32_t byte = tile[nz_idx[li * kMaxB + q] * R + r];
+                            sacc = fma(nz_db[li * kMaxB + q], dec_byte(byte, 0), sacc);
+                        }
+                        e_s[r] -= (sacc - K);
+                    }
+                    __syncwarp();
+                };
 
-                    // ---- c) the dependent scalar updates of the block (warp 0, redundantly in every CTA)
-                    int nnz = 0;
-                    if (warp == 0) {
-                        constexpr int NB = MG;
+                // staged outputs of block kk -> HBM (producer warp of CTA 0; plain coalesced stores)
+                auto write_out = [&](int kk) {
+                    const int li = kk & 1;
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const int q = b * 32 + lane;
+                        const int64_t j = (int64_t)kk * B + q;
+                        if (j < p_real) {
+                            beta_g[j] = out_b[li * kMaxB + q];
+                            if (method != 0) delta_g[j] = out_i[li * kMaxB + q];
+                            if (method == 1) vb_g[j] = out_v[li * kMaxB + q];
+                        }
+                    }
+                };
+
+                // ---- prologue: partial sums of block 0
+                if (warp >= 1 && warp <= kWorkerWarps) worker_dot(0);
+                __syncthreads();
+                if (tid == 32) NGP_TICK(1);
+
+                for (int k = 0; k < nblk; ++k) {
+                    if (warp == kProducerWarp) {
+                        // ================= TMA producer: tile k-2 was applied in step k-1, refill its stage =================
+                        if (lane == 0 && k >= 2 && k - 2 + S_ < nblk) issue(k - 2 + S_);
+                        if (t == 0 && k >= 1) write_out(k - 1);
+                    } else if (warp != 0) {
+                        // ================= workers =================
+                        if (k >= 1) worker_axpy(k - 1);
+                        if (tid == 32) NGP_TICK(2);
+                        if (k + 1 < nblk) worker_dot(k + 1);
+                        if (tid == 32) NGP_TICK(1);
+                    } else {
+                        // ================= chain warp =================
+                        const int stg = stage_of(k);
+                        tc = clock64();
+                        mbar_wait(&mbar[stg], parity_of(k));
+                        NGP_TICK(0);
+                        const int32_t* gram = reinterpret_cast<const int32_t*>(smem + L.off_blk + stg * L.blk_bytes);
+                        const double* cst = reinterpret_cast<const double*>(smem + L.off_blk + stg * L.blk_bytes + B * B * 4);
+                        const int slot = (int)((rk + (unsigned)k) & (kSlots - 1));
+                        const long long* acc = sy->acc + (int64_t)slot * (kMaxB + 1) * kAccStride;
+                        const int lp = (k & 1) ^ 1;                  // nz list of block k-1
+                        const int npend = (k >= 1) ? (int)misc[40 + 2 * lp] : 0;
                         double r[NB], bold[NB], dd[NB], cs[NB], bnew[NB];
                         bool inc[NB];
                         long long curv[NB];
+                        // cross-Gram rows of the markers changed in block k-1: issue the loads BEFORE polling so that
+                        // the two L2 round trips overlap
+                        constexpr int MAXP = 4;
+                        int gxv[MAXP][NB];
+                        const int32_t* gx = gramx_g + (int64_t)k * B * B;
+#pragma unroll
+                        for (int q0 = 0; q0 < MAXP; ++q0)
+#pragma unroll
+                            for (int b = 0; b < NB; ++b)
+                                gxv[q0][b] = (q0 < npend) ? __ldg(gx + nz_idx[lp * kMaxB + q0] * B + b * 32 + lane) : 0;
                         {   // every lane polls its own accumulators until all T CTAs have added theirs
                             bool done;
                             do {
@@ -343,23 +436,45 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         NGP_TICK(3);
 #pragma unroll
                         for (int b = 0; b < NB; ++b) {
-                            {
-                                const int q = b * 32 + lane;
-                                long long* pv = prev + slot * (kMaxB + 1) + q;
-                                const double A = (double)((curv[b] - *pv - (long long)P.T) >> kCntBits) * fx_inv;
-                                *pv = curv[b];
-                                r[b] = 4.0 * (A - Stot) - cst[F_MEAN * B + q] * Stot;     // x_j'e
-                                bold[b] = cst[F_BOLD * B + q];
-                                dd[b] = cst[F_D * B + q];
-                                cs[b] = cst[F_CS * B + q];
-                                bnew[b] = 0.0; inc[b] = false;
+                            const int q = b * 32 + lane;
+                            long long* pv = prev + slot * (kMaxB + 1) + q;
+                            const double A = (double)((curv[b] - *pv - (long long)P.T) >> kCntBits) * fx_inv;
+                            *pv = curv[b];
+                            cs[b] = cst[F_CS * B + q];
+                            r[b] = 4.0 * (A - Stot) - cst[F_MEAN * B + q] * Stot;     // x_j'e for the e of one block ago
+                            bold[b] = cst[F_BOLD * B + q];
+                            dd[b] = cst[F_D * B + q];
+                            bnew[b] = 0.0; inc[b] = false;
+                        }
+                        // the partial sums were formed before block k-1 was applied to e: restore exactly with the cross Gram
+#pragma unroll
+                        for (int q0 = 0; q0 < MAXP; ++q0) {
+                            if (q0 < npend) {
+                                const double dbf = 0.25 * nz_db[lp * kMaxB + q0];
+                                const double csf = nz_cs[lp * kMaxB + q0];
+#pragma unroll
+                                for (int b = 0; b < NB; ++b) r[b] = fma(-((double)gxv[q0][b] - csf * cs[b] * inv_n), dbf, r[b]);
                             }
                         }
+                        for (int q0 = MAXP; q0 < npend; ++q0) {
+                            const int f = nz_idx[lp * kMaxB + q0];
+                            const double dbf = 0.25 * nz_db[lp * kMaxB + q0];
+                            const double csf = nz_cs[lp * kMaxB + q0];
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) {
+                                const double gc = (double)__ldg(gx + f * B + b * 32 + lane) - csf * cs[b] * inv_n;
+                                r[b] = fma(-gc, dbf, r[b]);
+                            }
+                        }
+                        int nnz = 0;
+                        double K = 0.0;
+                        const int li = k & 1;
 #pragma unroll
                         for (int b = 0; b < NB; ++b) {
                             const int q = b * 32 + lane;
                             const double cA = cst[F_A * B + q], cB = cst[F_B * B + q], cT = cst[F_T * B + q];
                             const double cC = cst[F_C * B + q], cQ = cst[F_QSZ * B + q];
+                            const double mq = cst[F_MEAN * B + q];
                             int start = 0;
                             while (start < 32) {
                                 pf[7]++;
@@ -375,6 +490,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                 if (f == 32) break;
                                 const double dbf = __shfl_sync(0xffffffffu, db, f);
                                 const double csf = __shfl_sync(0xffffffffu, cs[b], f);
+                                const double mf = __shfl_sync(0xffffffffu, mq, f);
                                 const int32_t* grow = gram + (b * 32 + f) * B;
 #pragma unroll
                                 for (int bb = 0; bb < NB; ++bb) {
@@ -383,57 +499,50 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                         if (bb > b || lane > f) r[bb] = fma(-gc, dbf, r[bb]);
                                     }
                                 }
-                                if (lane == 0) { nz_idx[nnz] = b * 32 + f; nz_db[nnz] = dbf; }
+                                if (lane == 0) {
+                                    nz_idx[li * kMaxB + nnz] = b * 32 + f;
+                                    nz_db[li * kMaxB + nnz] = 4.0 * dbf;
+                                    nz_cs[li * kMaxB + nnz] = csf;
+                                }
+                                K = fma(4.0 * dbf, 1.0 + 0.25 * mf, K);
                                 ++nnz;
                                 start = f + 1;
                             }
                         }
-                        // outputs of the block
+                        if (lane == 0) { misc[40 + 2 * li] = (double)nnz; misc[41 + 2 * li] = K; }
+                        // outputs of the block: staged in smem, written to HBM by the producer warp of CTA 0 in the next step
 #pragma unroll
                         for (int b = 0; b < NB; ++b) {
-                            {
-                                const int q = b * 32 + lane;
-                                const int64_t j = (int64_t)k * B + q;
-                                acc_bb = fma(bnew[b], bnew[b], acc_bb);
-                                if (S.method != 0) acc_n += inc[b] ? 1.0 : 0.0;
-                                if (t == 0 && j < S.p) {
-                                    S.beta[j] = bnew[b];
-                                    if (S.method != 0) S.delta[j] = inc[b] ? 1 : 0;
-                                    if (S.method == 1)                                  // functions.jl:182,186
-                                        S.varBeta[j] = inc[b] ? (S.scale * S.df + bnew[b] * bnew[b]) / cst[F_CHI * B + q] : 0.0;
-                                }
+                            const int q = b * 32 + lane;
+                            acc_bb = fma(bnew[b], bnew[b], acc_bb);
+                            if (method != 0) acc_n += inc[b] ? 1.0 : 0.0;
+                            if (t == 0) {
+                                out_b[li * kMaxB + q] = bnew[b];
+                                out_i[li * kMaxB + q] = inc[b] ? 1 : 0;
+                                if (method == 1)                                    // functions.jl:182,186
+                                    out_v[li * kMaxB + q] = inc[b] ? (sdf + bnew[b] * bnew[b]) / cst[F_CHI * B + q] : 0.0;
                             }
                         }
-                        if (lane == 0) misc[40] = (double)nnz;
                         pf[6] += nnz;
                         NGP_TICK(4);
                     }
                     __syncthreads();
-                    nnz = (int)misc[40];
-
-                    // ---- d) e -= sum_q dbeta_q (g_q - m_q), from the same smem tile
-                    if (nnz > 0) {
-                        double K = 0.0;    // sum_q 4 dbeta_q (1 + m_q/4)
-                        for (int q = 0; q < nnz; ++q) K = fma(4.0 * nz_db[q], 1.0 + 0.25 * cst[F_MEAN * B + nz_idx[q]], K);
-                        for (int rr0 = tid; rr0 < nrow; rr0 += kThreads) {
-                            double sacc = 0.0;
-                            for (int q = 0; q < nnz; ++q) {
-                                const uint32_t byte = tile[nz_idx[q] * R + rr0];
-                                sacc = fma(4.0 * nz_db[q], dec_byte(byte, 0), sacc);
-                            }
-                            e_s[rr0] -= (sacc - K);
-                        }
-                    }
-                    __syncthreads();
-                    NGP_TICK(5);
-                    if (tid == 0 && k + S_ < nblk) issue(k + S_, gk + S_);
+                    if (tid == 0) NGP_TICK(5);
+                    if (tid == 32) NGP_TICK(10);
+                    // tile k-1 is no longer needed (its axpy ran in this step): refill its stage
                 }
+                // ---- epilogue: apply the last block
+                if (warp >= 1 && warp <= kWorkerWarps) worker_axpy(nblk - 1);
+                if (warp == kProducerWarp && t == 0) write_out(nblk - 1);
+                __syncthreads();
+                gk = (gk + (unsigned)nblk) % (2u * (unsigned)S_);
+                rk += (unsigned)nblk;
             } else {
                 // ============================ literal per-marker sweep ============================
                 const int ngrp = R >> 3;
                 for (int64_t j = 0; j < S.p; ++j, ++rk) {
                     const uint8_t* col = S.geno + ((int64_t)t * S.p_pad + j) * R;
-                    const int slot = (int)(rk % kSlots);
+                    const int slot = (int)(rk & (kSlots - 1));
                     long long* acc = sy->acc + (int64_t)slot * (kMaxB + 1) * kAccStride;
                     uint2 w0 = make_uint2(0xF0F0F0F0u, 0xF0F0F0F0u);
                     double a = 0.0, dummy = 0.0;
@@ -453,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         red_add_u64(acc, (__double2ll_rn(xs) << kCntBits) + 1);
                     }
                     if (warp == 0) {
-                        const double* c = S.consts + (j / B) * (int64_t)(kNF * B) + (j % B);
+                        const double* c = reinterpret_cast<const double*>(S.blk + (j / B) * (int64_t)blk_bytes(B) + B * B * 4) + (j % B);
                         const double cA = __ldcg(c + F_A * B), cB = __ldcg(c + F_B * B), cT = __ldcg(c + F_T * B);
                         const double cC = __ldcg(c + F_C * B), cQ = __ldcg(c + F_QSZ * B), d = __ldcg(c + F_D * B);
                         const double bold = __ldcg(c + F_BOLD * B), mean = __ldcg(c + F_MEAN * B), chi = __ldcg(c + F_CHI * B);
@@ -501,6 +610,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                 }
                 // (only lane 0 accumulated acc_bb / acc_n in the literal path; the other lanes hold 0)
             }
+            if (tid == 0) { tc = clock64(); }
 
             // ------------------------------------------------------------------ phase 3
             const bool regional = (S.method == 0 && S.n_regions > 1);
@@ -554,6 +664,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     }
                 }
             }
+            if (tid == 0) NGP_TICK(11);
         }   // sets
 
         if (t == 0 && tid == 0) {
@@ -564,8 +675,14 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 
     __syncthreads();
     for (int r = tid; r < nrow; r += kThreads) P.e[row0 + r] = e_s[r];
-    if (tid == 0)
-        for (int i = 0; i < 8; ++i) sy->prof[t * 8 + i] = pf[i];
+    if (tid == 0) {
+        const int own[] = {0, 3, 4, 5, 6, 7, 8, 9, 11};
+        for (int i : own) sy->prof[t * kProf + i] = pf[i];
+    }
+    if (tid == 32) {
+        const int own[] = {1, 2, 10};
+        for (int i : own) sy->prof[t * kProf + i] = pf[i];
+    }
 #undef NGP_TICK
 }
 

@@ -12,7 +12,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nextgp.jl_b200 as ngp  # noqa: E402
 from bench import CONFIGS, SEED0  # noqa: E402
 
-NAMES = ["tma_wait", "dot", "reduce_arrive", "barrier_wait", "chain", "axpy", "changed_effects", "spec_evals"]
+NAMES = ["tile_wait", "w_dot_red", "w_axpy", "acc_poll", "chain", "chain_waits_workers", "changed_effects", "spec_evals",
+         "phase0", "phase1", "w_waits_chain", "phase3", "tma_issue", "x13", "x14", "x15"]
 
 
 def main():
