@@ -1,0 +1,131 @@
+# NextGPB200.jl — Julia-side shim that puts libngp.so (B200, sm_100a) behind NextGP.jl's marker-set sampler.
+#
+# UNTESTED IN THIS REPOSITORY: the build image has no Julia (SURVEY F5).  The same C ABI (include/ngp.h) is exercised
+# end to end from Python (tests/test_gpu_parity.py); this file is the binding a NextGP.jl maintainer would add.
+#
+# Two levels, as in INTEGRATION.md:
+#   sweep level : b200_funct(h, set)  -> a function with the signature of M[mSet].funct (functions.jl:118,157,197)
+#   run level   : runLMEM_b200(...)   -> replaces MCMC.runLMEM (MCMC.jl:31-41) for intercept + SNP(...) models:
+#                 prep / getMME! stay NextGP's own; only runSampler! is replaced.
+module NextGPB200
+
+using NextGP, DelimitedFiles
+
+const libngp = get(ENV, "LIBNGP", joinpath(@__DIR__, "..", "nextgp.jl_b200", "libngp.so"))
+
+const NGP_BAYESPR, NGP_BAYESB, NGP_BAYESC = Cint(0), Cint(1), Cint(2)
+const NGP_GENO_F64, NGP_STORE_I8 = Cint(1), Cint(0)
+const NGP_MAX_SETS = 8
+
+struct NgpPrior            # mirrors struct ngp_prior
+    method::Cint; est_pi::Cint
+    df::Cdouble; scale::Cdouble; var_init::Cdouble; pi_in::Cdouble
+    n_regions::Int64
+    region_off::Ptr{Int64}; lhs0::Ptr{Cdouble}; rhs0::Ptr{Cdouble}
+end
+
+mutable struct NgpState    # mirrors struct ngp_state
+    n::Int64; n_sets::Cint; pad::Cint
+    e::Ptr{Cdouble}; mu::Cdouble; varE::Cdouble; iter::Int64
+    beta::NTuple{NGP_MAX_SETS,Ptr{Cdouble}}
+    delta::NTuple{NGP_MAX_SETS,Ptr{Int64}}
+    varBeta::NTuple{NGP_MAX_SETS,Ptr{Cdouble}}
+    pi::NTuple{2 * NGP_MAX_SETS,Cdouble}
+end
+
+function check(h, rc)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:ngp_last_error, libngp), Cstring, (Ptr{Cvoid},), h))
+    error("libngp error $rc: $msg")          # Julia exceptions, like mme.jl:77,343
+end
+
+function create(device::Integer = 0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:ngp_create, libngp), Cint, (Cint, Ref{Ptr{Cvoid}}), device, h)
+    rc == 0 || error("libngp: " * unsafe_string(ccall((:ngp_last_error, libngp), Cstring, (Ptr{Cvoid},), C_NULL)))
+    return h[]
+end
+destroy(h) = ccall((:ngp_destroy, libngp), Cint, (Ptr{Cvoid},), h)
+
+"""Upload M[pSet].data of getMME! (centred Matrix{Float64}): the codes are data .+ column means of the raw file;
+pass the RAW 0/1/2 matrix (before prepMatVec.jl:129) — the library centres on device."""
+function upload!(h, set::Integer, raw::Matrix{Float64})
+    n, p = size(raw)
+    check(h, ccall((:ngp_upload_genotypes, libngp), Cint,
+                   (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Cint, Int64, Cint),
+                   h, set, n, p, raw, NGP_GENO_F64, n, NGP_STORE_I8))
+end
+
+function method_id(name::String)
+    name == "BayesPR" && return NGP_BAYESPR
+    name == "BayesB" && return NGP_BAYESB
+    name == "BayesC" && return NGP_BAYESC
+    error("$name is not on the B200 hot path (stays in Julia)")
+end
+
+"""Translate one entry of the NamedTuple dictionary M returned by getMME! (mme.jl:598-601) into ngp_set_prior."""
+function set_prior!(h, set::Integer, Mset, v0::Float64)
+    offs = Int64[first(r) - 1 for r in Mset.regionArray]; push!(offs, last(Mset.regionArray[end]))
+    isPR = Mset.method == "BayesPR"
+    pi_in = isPR ? 0.0 : Mset.piHat[2]
+    GC.@preserve offs begin
+        pr = NgpPrior(method_id(Mset.method), isPR ? 0 : Cint(Mset.estPi), Mset.df, Mset.scale, v0, pi_in,
+                      isPR ? length(offs) - 1 : 0, isPR ? pointer(offs) : C_NULL, pointer(Mset.lhs), pointer(Mset.rhs))
+        check(h, ccall((:ngp_set_prior, libngp), Cint, (Ptr{Cvoid}, Cint, Ref{NgpPrior}), h, set, pr))
+    end
+end
+
+"""Sweep-level drop-in: returns a function with the signature of M[mSet].funct (samplers.jl:52)."""
+function b200_funct(h, set::Integer)
+    return function (mSet, M, beta, delta, ycorr, varE, varBeta)
+        pos = M[mSet].pos
+        b = vec(beta[pos]); d = vec(delta[pos]); vb = varBeta[mSet]
+        piHat = haskey(M[mSet], :piHat) ? vec(M[mSet].piHat) : C_NULL
+        check(h, ccall((:ngp_sweep, libngp), Cint,
+                       (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Int64}, Ptr{Cdouble}, Ptr{Cdouble}),
+                       h, set, ycorr, varE, b, d, vb, piHat))
+        haskey(M[mSet], :logPi) && (M[mSet].logPi .= log.(M[mSet].piHat))
+        nothing
+    end
+end
+
+"""Run-level replacement of samplers.runSampler! (samplers.jl:23-106) for X = intercept only, Z = empty.
+Same positional arguments; writes the same <outPut>/*Out rows in the order of samplers.jl:57-103."""
+function runSampler_b200!(h, ycorr, nData, E, X, b, Z, u, varU, M, beta, varBeta, delta, chainLength, burnIn, outputFreq, outPut;
+                          raw::Dict, seed::UInt64 = UInt64(0), chain::UInt32 = UInt32(0))
+    isempty(Z) || error("random effects stay in Julia: use b200_funct at sweep level")
+    sets = collect(keys(M))
+    for (s, mSet) in enumerate(sets)
+        upload!(h, s - 1, raw[mSet]); set_prior!(h, s - 1, M[mSet], varBeta[mSet][1])
+    end
+    check(h, ccall((:ngp_set_phenotype, libngp), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64), h, ycorr, nData))
+    check(h, ccall((:ngp_set_residual_prior, libngp), Cint, (Ptr{Cvoid}, Cdouble, Cdouble), h, E.df, E.scale))
+    check(h, ccall((:ngp_set_intercept, libngp), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cdouble), h, isempty(X) ? 0 : 1, 0.0, 0.0))
+    check(h, ccall((:ngp_set_rng, libngp), Cint, (Ptr{Cvoid}, UInt64, UInt32), h, seed, chain))
+    these2Keep = collect((burnIn + outputFreq):outputFreq:chainLength)
+    done = 0
+    for it in these2Keep
+        check(h, ccall((:ngp_run, libngp), Cint, (Ptr{Cvoid}, Int32), h, it - done)); done = it
+        st = NgpState(nData, length(sets), 0, pointer(ycorr), 0.0, 0.0, 0,
+                      ntuple(i -> i <= length(sets) ? pointer(beta[M[sets[i]].pos]) : Ptr{Cdouble}(C_NULL), NGP_MAX_SETS),
+                      ntuple(i -> i <= length(sets) ? pointer(delta[M[sets[i]].pos]) : Ptr{Int64}(C_NULL), NGP_MAX_SETS),
+                      ntuple(i -> i <= length(sets) ? pointer(varBeta[sets[i]]) : Ptr{Cdouble}(C_NULL), NGP_MAX_SETS),
+                      ntuple(_ -> 0.0, 2 * NGP_MAX_SETS))
+        check(h, ccall((:ngp_get_state, libngp), Cint, (Ptr{Cvoid}, Ref{NgpState}), h, st))
+        isempty(b) || (b[1] = st.mu)
+        NextGP.IO.outMCMC(outPut, "b", b'); NextGP.IO.outMCMC(outPut, "varE", st.varE)
+        for (s, mSet) in enumerate(sets)
+            NextGP.IO.outMCMC(outPut, "beta$mSet", beta[M[mSet].pos]); NextGP.IO.outMCMC(outPut, "delta$mSet", delta[M[mSet].pos])
+            if M[mSet].method in ("BayesB", "BayesC")
+                M[mSet].piHat .= [st.pi[2s-1] st.pi[2s]]; NextGP.IO.outMCMC(outPut, "pi$mSet", [M[mSet].piHat])
+            end
+        end
+        for mSet in sets
+            NextGP.IO.outMCMC(outPut, "var$mSet", hcat(reduce(hcat, varBeta[mSet])...))
+        end
+    end
+    done < chainLength && check(h, ccall((:ngp_run, libngp), Cint, (Ptr{Cvoid}, Int32), h, chainLength - done))
+    nothing
+end
+
+end # module
