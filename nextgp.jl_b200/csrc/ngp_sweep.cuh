@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                 auto worker_dot = [&](int kk) {
                     const int stg = stage_of(kk);
                     mbar_wait(&mbar[stg], parity_of(kk));
+                    if (tid == 32) NGP_TICK(12);
                     const uint8_t* tile = smem + L.off_tile + stg * L.tile_bytes;
                     double* redk = red + (kk & 1) * (kWorkerWarps * kMaxB);     // double-buffered: one barrier per block
                     double a[NB][4];
@@ -335,7 +336,9 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     }
 #pragma unroll
                     for (int b = 0; b < NB; ++b) redk[ww * B + b * 32 + lane] = (a[b][0] + a[b][1]) + (a[b][2] + a[b][3]);
+                    if (tid == 32) NGP_TICK(13);
                     worker_bar();
+                    if (tid == 32) NGP_TICK(14);
                     if (wtid < B) {
                         double A = 0.0;
 #pragma unroll
@@ -680,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         for (int i : own) sy->prof[t * kProf + i] = pf[i];
     }
     if (tid == 32) {
-        const int own[] = {1, 2, 10};
+        const int own[] = {1, 2, 10, 12, 13, 14};
         for (int i : own) sy->prof[t * kProf + i] = pf[i];
     }
 #undef NGP_TICK

@@ -13,7 +13,7 @@ import nextgp.jl_b200 as ngp  # noqa: E402
 from bench import CONFIGS, SEED0  # noqa: E402
 
 NAMES = ["tile_wait", "w_dot_red", "w_axpy", "acc_poll", "chain", "chain_waits_workers", "changed_effects", "spec_evals",
-         "phase0", "phase1", "w_waits_chain", "phase3", "tma_issue", "x13", "x14", "x15"]
+         "phase0", "phase1", "w_waits_chain", "phase3", "w_tile_wait", "w_dot_loop", "w_dot_bar", "x15"]
 
 
 def main():
