@@ -284,7 +284,7 @@ def main():
                            "l2": f"genotype matrix {n * p / 1e9:.2f} GB per sweep vs 126 MB L2 (inputs larger than L2, no flush needed)"
                                  if n * p > 4e8 else "inputs fit in L2 (cache-resident workload; HBM roofline not meaningful)",
                            "gibbs_iters_per_s": world * args.steps / (ms_all * 1e-3),
-                           "geometry": {k: tm[k] for k in ("ctas", "threads", "block", "rows_per_cta", "smem_bytes")}},
+                           "geometry": {k: tm[k] for k in ("ctas", "threads", "block", "rows_per_cta", "smem_bytes", "lookahead", "near_depth", "tile_stages", "record_stages")}},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "kernel": "ngp::gibbs_kernel (one launch = one Gibbs iteration)", "kernel_ms": k_ms,
                              "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},

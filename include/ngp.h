@@ -50,8 +50,8 @@ enum ngp_geno_format {
 
 /* device storage of the genotype codes */
 enum ngp_storage {
-    NGP_STORE_I8 = 0,     /* one byte per code, row-panelled column-major                */
-    NGP_STORE_2BIT = 1    /* four codes per byte, row-panelled column-major              */
+    NGP_STORE_I8 = 0,     /* one byte per code, row panels x marker blocks, tiles in INT8-MMA operand order */
+    NGP_STORE_2BIT = 1    /* four codes per byte (capacity mode; not built yet: NGP_EUNSUPPORTED)            */
 };
 
 /* kernel variants (ngp_configure key NGP_CFG_KERNEL) */
@@ -62,9 +62,15 @@ enum ngp_kernel {
 
 enum ngp_config_key {
     NGP_CFG_KERNEL = 0,        /* enum ngp_kernel                                           */
-    NGP_CFG_BLOCK = 1,         /* markers per block: 32 or 64 (0 = auto)                    */
-    NGP_CFG_MIN_ROWS = 2,      /* minimum rows per CTA when choosing the panel count        */
-    NGP_CFG_MAX_CTAS = 3       /* cap on CTAs (0 = one per SM); must be set before upload   */
+    NGP_CFG_BLOCK = 1,         /* markers per block: 16, 32 or 64 (0 = auto)                */
+    NGP_CFG_MIN_ROWS = 2,      /* minimum rows per worker CTA when choosing the panel count */
+    NGP_CFG_MAX_CTAS = 3,      /* cap on CTAs incl. the chain CTA (0 = one per SM)          */
+    NGP_CFG_LOOKAHEAD = 4,     /* blocks of look-ahead D of the blocked sweep (0 = auto)    */
+    NGP_CFG_TILE_STAGES = 5,   /* genotype tile ring stages per worker CTA, >= D+2 (0 = auto) */
+    NGP_CFG_NEAR = 6,          /* cross-Gram distances kept in the chain CTA's block record (0 = auto) */
+                               /* keys 1..6 must be set before the first upload             */
+    NGP_CFG_PROFILE = 7,       /* 1 = launch the instrumented kernel (cycle counters for ngp_get_profile) */
+    NGP_CFG_DEBUG = 8          /* timing experiments that decouple the kernel's roles; RESULTS ARE INVALID when non-zero */
 };
 
 /* -------------------------------------------------------------------------
@@ -121,6 +127,7 @@ typedef struct ngp_timing {
     int32_t ctas, threads;       /* geometry of the sweep kernel                                */
     int32_t block, rows_per_cta; /* markers per block, rows per CTA panel                        */
     int64_t smem_bytes;
+    int32_t lookahead, near_depth, tile_stages, record_stages;
 } ngp_timing;
 
 /* ---- lifetime ------------------------------------------------------------ */
@@ -178,11 +185,14 @@ int ngp_reset_posterior(ngp_handle* h);
 int ngp_get_posterior(ngp_handle* h, int set_id, int64_t* n_samples, double* sum_beta, double* sum_beta2, double* sum_delta);
 int ngp_get_timing(ngp_handle* h, ngp_timing* out);
 
-/* per-CTA cycle counters of the last launch, 16 int64 per CTA (clock64; blocked kernel).
- * chain warp (thread 0): [0] tile wait [3] accumulator poll [4] scalar chain [5] wait for workers
- *                        [6] markers whose effect changed [7] speculative evaluations
- *                        [8] phase 0 (varE, intercept) [9] phase 1 (marker constants) [11] phase 3 [12] TMA issue
- * first worker warp (thread 32): [1] dot + RED [2] axpy [10] wait for the chain warp.
+/* per-CTA cycle counters of the last launch, 24 int64 per CTA (clock64; blocked kernel).  The last CTA is the
+ * chain CTA, the others are worker CTAs.
+ * worker CTA (thread 0):  [1] IMMA dots + limb combine [2] axpy + re-quantise [10] wait for the changed-effect list
+ *                         [14] wait for the TMA tile [15] CTA combine + RED
+ * chain CTA  (thread 0):  [0] wait for the block record [3] wait for r_base (prep warps) [4] scalar chain
+ *                         [6] markers whose effect changed [7] speculative evaluations
+ *            (first prep warp): [12] far corrections [13] accumulator poll
+ * every CTA  (thread 0):  [8] phase 0 (varE, intercept) [9] phase 1 (marker constants) [11] phase 3
  * Returns the number of CTAs written. */
 int ngp_get_profile(ngp_handle* h, int64_t* out, int32_t max_ctas);
 

@@ -18,7 +18,7 @@ BAYESPR, BAYESB, BAYESC = 0, 1, 2
 GENO_I8, GENO_F64, GENO_PACKED2 = 0, 1, 2
 STORE_I8, STORE_2BIT = 0, 1
 KERNEL_BLOCKED, KERNEL_LITERAL = 0, 1
-CFG_KERNEL, CFG_BLOCK, CFG_MIN_ROWS, CFG_MAX_CTAS = 0, 1, 2, 3
+CFG_KERNEL, CFG_BLOCK, CFG_MIN_ROWS, CFG_MAX_CTAS, CFG_LOOKAHEAD, CFG_TILE_STAGES, CFG_NEAR, CFG_PROFILE, CFG_DEBUG = 0, 1, 2, 3, 4, 5, 6, 7, 8
 OK, EINVAL, ECUDA, EDATA, ERANGE, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -52,7 +52,8 @@ class State(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("last_run_ms", C.c_double), ("launches", C.c_int64), ("ctas", C.c_int32), ("threads", C.c_int32),
-                ("block", C.c_int32), ("rows_per_cta", C.c_int32), ("smem_bytes", C.c_int64)]
+                ("block", C.c_int32), ("rows_per_cta", C.c_int32), ("smem_bytes", C.c_int64),
+                ("lookahead", C.c_int32), ("near_depth", C.c_int32), ("tile_stages", C.c_int32), ("record_stages", C.c_int32)]
 
 
 def sources() -> list[str]:

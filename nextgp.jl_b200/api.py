@@ -200,7 +200,8 @@ def _p(a):
 class Sampler:
     """One chain on one GPU.  Thin, explicit wrapper over the C ABI (include/ngp.h)."""
 
-    def __init__(self, device: int = 0, kernel: str = "blocked", block: int = 0, min_rows: int = 0, max_ctas: int = 0):
+    def __init__(self, device: int = 0, kernel: str = "blocked", block: int = 0, min_rows: int = 0, max_ctas: int = 0,
+                 lookahead: int = 0, tile_stages: int = 0, near: int = 0):
         self._lib = L.lib()
         hp = C.c_void_p()
         rc = self._lib.ngp_create(device, C.byref(hp))
@@ -217,6 +218,12 @@ class Sampler:
             self.configure(L.CFG_MIN_ROWS, min_rows)
         if max_ctas:
             self.configure(L.CFG_MAX_CTAS, max_ctas)
+        if lookahead:
+            self.configure(L.CFG_LOOKAHEAD, lookahead)
+        if tile_stages:
+            self.configure(L.CFG_TILE_STAGES, tile_stages)
+        if near:
+            self.configure(L.CFG_NEAR, near)
 
     # -- plumbing
     def _ck(self, rc: int) -> None:
@@ -393,8 +400,8 @@ class Sampler:
         return {k: getattr(t, k) for k, _ in L.Timing._fields_}
 
     def profile(self) -> np.ndarray:
-        """(ctas, 16) int64 cycle counters of the last launch, see ngp_get_profile."""
-        out = np.zeros((160, 16), dtype=np.int64)
+        """(ctas, 24) int64 cycle counters of the last launch, see ngp_get_profile."""
+        out = np.zeros((160, 24), dtype=np.int64)
         nc = self._lib.ngp_get_profile(self._h, _p(out), 160)
         if nc < 0:
             self._ck(nc)

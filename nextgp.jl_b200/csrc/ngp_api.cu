@@ -34,14 +34,17 @@ __device__ __forceinline__ int block_sum_int(int v, int* scratch)
     return s;
 }
 
-// one CTA per column of the chunk: validate, encode, scatter into the panel layout, column sums
+// one CTA per column of the chunk: validate, scatter into the tiled fragment-ordered layout, column sums
 template <int FMT>
-__global__ void pack_kernel(const void* __restrict__ src, int64_t ld, int64_t n, int64_t j0, int R, int64_t p_pad,
+__global__ void pack_kernel(const void* __restrict__ src, int64_t ld, int64_t n, int64_t j0, int R, int B, int64_t nblk,
                             uint8_t* __restrict__ geno, int32_t* __restrict__ colsum, int32_t* __restrict__ colsumsq,
                             int* __restrict__ err)
 {
     __shared__ int scratch[32];
     const int64_t jc = blockIdx.x, j = j0 + jc;
+    const int64_t k = j / B;
+    const int q = (int)(j - k * B);
+    const int64_t tile_bytes = (int64_t)B * R;
     int s = 0, ss = 0, bad = 0;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
         int g;
@@ -57,7 +60,7 @@ __global__ void pack_kernel(const void* __restrict__ src, int64_t ld, int64_t n,
         s += g; ss += g * g;
         const int64_t t = i / R;
         const int r = (int)(i - t * R);
-        geno[(t * p_pad + j) * R + r] = enc_code(g);
+        geno[(t * nblk + k) * tile_bytes + byte_off(B, q, r)] = (uint8_t)g;
     }
     s = block_sum_int(s, scratch);
     ss = block_sum_int(ss, scratch);
@@ -77,60 +80,43 @@ __global__ void colstats_kernel(int64_t n, int64_t p, int64_t p_pad, const int32
     } else { mean[j] = 0.0; d[j] = 0.0; }
 }
 
-// raw block Grams over all panels, one CTA (16x16 threads) per block k of B markers:
-//   gram [k][a][b] = sum_i g_{kB+a,i} g_{kB+b,i}          (inside the block)
-//   gramx[k][a][b] = sum_i g_{(k-1)B+a,i} g_{kB+b,i}      (previous block x this block; zeros for k = 0)
-// integer-exact (__dp4a on the 2-bit codes), built once per upload.
+// raw banded Gram over all panels, one CTA per block k of B markers, on the INT8 tensor cores (integer-exact):
+//   gx[k][d][a][b] = sum_i g_{(k-d)B+a,i} g_{kB+b,i},   d = 0..D   (zeros for k < d)
+// A work item is one 16x8 output tile (d, 16 markers a, 8 markers b); both operands come straight from the
+// fragment-ordered tiles (the A atom is 512 contiguous bytes; a B register is one tile word of the other block).
 template <int B>
-__global__ void __launch_bounds__(256) gram_kernel(const uint8_t* __restrict__ geno, int T, int R, int64_t p_pad,
-                                                   uint8_t* __restrict__ blk, int32_t* __restrict__ gramx)
+__global__ void __launch_bounds__(256) gram_kernel(const uint8_t* __restrict__ geno, int Tw, int R, int64_t nblk, int D,
+                                                   int32_t* __restrict__ gx)
 {
-    extern __shared__ __align__(16) unsigned char gsm[];
-    constexpr int TB = B / 16;
-    const int k = blockIdx.x, tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int W = R >> 2;
-    int acc[TB][TB], accx[TB][TB];
-#pragma unroll
-    for (int i = 0; i < TB; ++i)
-#pragma unroll
-        for (int q = 0; q < TB; ++q) { acc[i][q] = 0; accx[i][q] = 0; }
-    const int nvec = (B * R) >> 4;
-    uint4* dst = reinterpret_cast<uint4*>(gsm);
-    for (int t = 0; t < T; ++t) {
-        const uint4* src = reinterpret_cast<const uint4*>(geno + ((int64_t)t * p_pad + (int64_t)k * B) * R);
-        for (int v = threadIdx.x; v < nvec; v += 256) dst[v] = __ldg(src + v);
-        if (k > 0) {
-            const uint4* srcp = reinterpret_cast<const uint4*>(geno + ((int64_t)t * p_pad + (int64_t)(k - 1) * B) * R);
-            for (int v = threadIdx.x; v < nvec; v += 256) dst[nvec + v] = __ldg(srcp + v);
-        }
-        __syncthreads();
-        const uint32_t* tw = reinterpret_cast<const uint32_t*>(gsm);
-        const uint32_t* tp = tw + (B * R >> 2);
-        for (int w = 0; w < W; ++w) {
-            int a[TB], b[TB], ap[TB];
-#pragma unroll
-            for (int i = 0; i < TB; ++i) {
-                a[i] = (int)((tw[(ty * TB + i) * W + w] >> 2) & 0x03030303u);
-                b[i] = (int)((tw[(tx * TB + i) * W + w] >> 2) & 0x03030303u);
-                ap[i] = (k > 0) ? (int)((tp[(ty * TB + i) * W + w] >> 2) & 0x03030303u) : 0;
-            }
-#pragma unroll
-            for (int i = 0; i < TB; ++i)
-#pragma unroll
-                for (int q = 0; q < TB; ++q) {
-                    acc[i][q] = __dp4a(a[i], b[q], acc[i][q]);
-                    accx[i][q] = __dp4a(ap[i], b[q], accx[i][q]);
+    constexpr int MG = B / 16, NBG = B / 8;
+    const int64_t k = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, tt = lane & 3;
+    const int nchunk = R >> 5;
+    const int64_t tile_bytes = (int64_t)B * R;
+    const int items = (D + 1) * MG * NBG;
+    for (int item = warp; item < items; item += 8) {
+        const int d = item / (MG * NBG), rem = item - d * (MG * NBG), mg = rem / NBG, nb = rem - mg * NBG;
+        int acc[4] = {0, 0, 0, 0};
+        if (k - d >= 0) {
+            const int qb = nb * 8 + g;
+            for (int t = 0; t < Tw; ++t) {
+                const uint8_t* ta = geno + ((int64_t)t * nblk + (k - d)) * tile_bytes;
+                const uint32_t* tb = reinterpret_cast<const uint32_t*>(geno + ((int64_t)t * nblk + k) * tile_bytes);
+#pragma unroll 4
+                for (int c = 0; c < nchunk; ++c) {
+                    const uint4 a = __ldg(reinterpret_cast<const uint4*>(ta + ((size_t)(c * MG + mg) * 32 + lane) * 16));
+                    const uint32_t b0 = __ldg(tb + word_off(B, qb, 8 * c + tt));
+                    const uint32_t b1 = __ldg(tb + word_off(B, qb, 8 * c + 4 + tt));
+                    imma16832(acc, a, b0, b1);
                 }
+            }
         }
-        __syncthreads();
+        int32_t* out = gx + ((k * (D + 1) + d) * B) * (int64_t)B;
+        const int a0 = mg * 16 + g, b0i = nb * 8 + 2 * tt;
+        out[a0 * B + b0i] = acc[0]; out[a0 * B + b0i + 1] = acc[1];
+        out[(a0 + 8) * B + b0i] = acc[2]; out[(a0 + 8) * B + b0i + 1] = acc[3];
     }
-#pragma unroll
-    for (int i = 0; i < TB; ++i)
-#pragma unroll
-        for (int q = 0; q < TB; ++q) {
-            reinterpret_cast<int32_t*>(blk + (int64_t)k * blk_bytes(B))[(ty * TB + i) * B + tx * TB + q] = acc[i][q];
-            gramx[(int64_t)k * B * B + (ty * TB + i) * B + tx * TB + q] = accx[i][q];
-        }
 }
 
 __global__ void synth_kernel(uint32_t key0, uint32_t key1, int64_t n, int64_t j0, int64_t ncols,
@@ -148,14 +134,14 @@ __global__ void synth_kernel(uint32_t key0, uint32_t key1, int64_t n, int64_t j0
         if (i4 + q < n) out[jc * n + i4 + q] = (int8_t)((w[q] >= a) + (w[q] >= b));
 }
 
-__global__ void unpack_kernel(const uint8_t* __restrict__ geno, int64_t n, int R, int64_t p_pad, int64_t j0, int64_t ncols,
+__global__ void unpack_kernel(const uint8_t* __restrict__ geno, int64_t n, int R, int B, int64_t nblk, int64_t j0, int64_t ncols,
                               int8_t* __restrict__ out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t jc = blockIdx.y;
     if (i >= n || jc >= ncols) return;
-    const int64_t t = i / R;
-    out[jc * n + i] = (int8_t)dec_code(geno[(t * p_pad + j0 + jc) * R + (i - t * R)]);
+    const int64_t j = j0 + jc, k = j / B, t = i / R;
+    out[jc * n + i] = (int8_t)geno[(t * nblk + k) * ((int64_t)B * R) + byte_off(B, (int)(j - k * B), (int)(i - t * R))];
 }
 
 __global__ void region_of_kernel(const int64_t* region_off, int64_t n_regions, int32_t* region_of)
@@ -197,8 +183,9 @@ struct SetHost {
     int64_t p = 0, p_pad = 0, nvar = 0, n_regions = 0;
     int method = 0, est_pi = 0, storage = 0;
     double df = 4.0, scale = 0.0, var_init = 0.0, pi_in = 0.0;
-    uint8_t *geno = nullptr, *blk = nullptr;
-    int32_t *gramx = nullptr, *colsum = nullptr, *colsumsq = nullptr, *delta = nullptr, *region_of = nullptr;
+    uint8_t* geno = nullptr;
+    double* consts = nullptr;
+    int32_t *gx = nullptr, *colsum = nullptr, *colsumsq = nullptr, *delta = nullptr, *region_of = nullptr;
     double *d = nullptr, *mean = nullptr, *beta = nullptr, *varBeta = nullptr, *pi = nullptr;
     double *lhs0 = nullptr, *rhs0 = nullptr, *sum_beta = nullptr, *sum_beta2 = nullptr, *sum_delta = nullptr;
     int64_t* region_off = nullptr;
@@ -213,8 +200,8 @@ struct ngp_handle {
     std::string err;
     // geometry
     int64_t n = 0;
-    int T = 0, R = 0, B = 0, stages = 0;
-    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0;
+    int Tw = 0, R = 0, B = 0, D = 0, DN = 0, NT = 0, NR = 0;      // worker CTAs (grid = Tw + 1), rows per panel, block, look-ahead, near depth, tile stages
+    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0;
     SmemLayout L{};
     // model
     SetHost sets[NGP_MAX_SETS];
@@ -277,7 +264,7 @@ static cudaError_t dalloc(Tp** p, size_t count)
 
 static void free_set(SetHost& s)
 {
-    cudaFree(s.geno); cudaFree(s.blk); cudaFree(s.gramx); cudaFree(s.colsum); cudaFree(s.colsumsq); cudaFree(s.delta); cudaFree(s.region_of);
+    cudaFree(s.geno); cudaFree(s.consts); cudaFree(s.gx); cudaFree(s.colsum); cudaFree(s.colsumsq); cudaFree(s.delta); cudaFree(s.region_of);
     cudaFree(s.d); cudaFree(s.mean); cudaFree(s.beta); cudaFree(s.varBeta); cudaFree(s.pi);
     cudaFree(s.lhs0); cudaFree(s.rhs0); cudaFree(s.sum_beta); cudaFree(s.sum_beta2); cudaFree(s.sum_delta);
     cudaFree(s.region_off); cudaFree(s.rp_u); cudaFree(s.rp_z); cudaFree(s.rp_chi2b); cudaFree(s.rp_betapi);
@@ -357,17 +344,33 @@ int ngp_configure(ngp_handle* h, int key, int64_t value)
         if (value != NGP_KERNEL_BLOCKED && value != NGP_KERNEL_LITERAL) return fail(h, NGP_EINVAL, "ngp_configure: unknown kernel %lld", (long long)value);
         h->cfg_kernel = (int)value; return NGP_OK;
     case NGP_CFG_BLOCK:
-        if (h->T) return fail(h, NGP_EINVAL, "ngp_configure: block size must be set before the first upload");
-        if (value != 0 && value != 32 && value != 64) return fail(h, NGP_EINVAL, "ngp_configure: block must be 0, 32 or 64");
+        if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: block size must be set before the first upload");
+        if (value != 0 && value != 16 && value != 32 && value != 64) return fail(h, NGP_EINVAL, "ngp_configure: block must be 0, 16, 32 or 64");
         h->cfg_block = (int)value; return NGP_OK;
     case NGP_CFG_MIN_ROWS:
-        if (h->T) return fail(h, NGP_EINVAL, "ngp_configure: min rows must be set before the first upload");
+        if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: min rows must be set before the first upload");
         if (value < 8) return fail(h, NGP_EINVAL, "ngp_configure: min rows must be >= 8");
         h->cfg_min_rows = (int)value; return NGP_OK;
     case NGP_CFG_MAX_CTAS:
-        if (h->T) return fail(h, NGP_EINVAL, "ngp_configure: max CTAs must be set before the first upload");
-        if (value < 0) return fail(h, NGP_EINVAL, "ngp_configure: max CTAs must be >= 0");
+        if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: max CTAs must be set before the first upload");
+        if (value < 0 || value == 1) return fail(h, NGP_EINVAL, "ngp_configure: max CTAs must be 0 (one per SM) or >= 2 (workers + the chain CTA)");
         h->cfg_max_ctas = (int)value; return NGP_OK;
+    case NGP_CFG_DEBUG:
+        h->cfg_debug = (int)value; return NGP_OK;
+    case NGP_CFG_PROFILE:
+        h->cfg_profile = value ? 1 : 0; return NGP_OK;
+    case NGP_CFG_LOOKAHEAD:
+        if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: look-ahead must be set before the first upload");
+        if (value < 0 || value > kMaxD) return fail(h, NGP_EINVAL, "ngp_configure: look-ahead must be in [0,%d] (0 = auto)", kMaxD);
+        h->cfg_lookahead = (int)value; return NGP_OK;
+    case NGP_CFG_TILE_STAGES:
+        if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: tile stages must be set before the first upload");
+        if (value < 0 || value > kMaxD + 8) return fail(h, NGP_EINVAL, "ngp_configure: tile stages must be in [0,%d] (0 = auto)", kMaxD + 8);
+        h->cfg_tile_stages = (int)value; return NGP_OK;
+    case NGP_CFG_NEAR:
+        if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: near depth must be set before the first upload");
+        if (value < 0 || value > kMaxD) return fail(h, NGP_EINVAL, "ngp_configure: near depth must be in [0,%d] (0 = auto)", kMaxD);
+        h->cfg_near = (int)value; return NGP_OK;
     default: return fail(h, NGP_EINVAL, "ngp_configure: unknown key %d", key);
     }
 }
@@ -385,26 +388,42 @@ static int choose_geometry(ngp_handle* h, int64_t n)
     const int sms = h->prop.multiProcessorCount;
     int maxc = h->cfg_max_ctas ? std::min(h->cfg_max_ctas, sms) : sms;
     maxc = std::min(maxc, kMaxCtas);
-    int64_t want = (n + h->cfg_min_rows - 1) / h->cfg_min_rows;
-    int T = (int)std::max<int64_t>(1, std::min<int64_t>(maxc, want));
-    int64_t R8 = (n + 8LL * T - 1) / (8LL * T);
-    if (R8 % 2 == 0) R8 += 1;                      // R = 8*odd: conflict-free 64-bit smem column reads
-    const int64_t R = 8 * R8;
+    if (maxc < 2) return fail(h, NGP_EUNSUPPORTED, "the sweep kernel needs at least 2 co-resident CTAs (device has %d SMs)", sms);
+    const int maxw = maxc - 1;                     // one CTA runs the scalar chain
+    const int64_t want = (n + h->cfg_min_rows - 1) / h->cfg_min_rows;
+    int Tw = (int)std::max<int64_t>(1, std::min<int64_t>(maxw, want));
+    const int64_t R = 32 * ((n + 32LL * Tw - 1) / (32LL * Tw));      // rows per panel: whole 32-row MMA chunks
+    Tw = (int)((n + R - 1) / R);                                    // no empty panels
     const size_t cap = h->prop.sharedMemPerBlockOptin;
-    const int candB[2] = {64, 32};
-    const int candS[2] = {4, 3};                   // look-ahead pipeline: tiles k-1, k, k+1 live + one in flight
-    for (int bi = 0; bi < 2; ++bi) {
-        if (h->cfg_block && candB[bi] != h->cfg_block) continue;
-        for (int si = 0; si < 2; ++si) {
-            SmemLayout L = smem_layout((int)R, candB[bi], candS[si]);
-            if ((size_t)L.total + 1024 <= cap) {
-                h->n = n; h->T = T; h->R = (int)R; h->B = candB[bi]; h->stages = candS[si]; h->L = L;
-                return NGP_OK;
+    int B = h->cfg_block;
+    if (!B) B = (64 * R <= 12288) ? 64 : (32 * R <= 16384) ? 32 : 16;
+    const int64_t maxR = 4LL * kUpdThreads * (B == 16 ? kUpdGroups : 1);     // residual rows an updater warp group holds in registers
+    if (R > maxR)
+        return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA; block %d supports at most %lld (use block 16 for up to %d)",
+                    (long long)n, (long long)R, B, (long long)maxR, 4 * kUpdThreads * kUpdGroups);
+    int DN = h->cfg_near ? h->cfg_near : (B == 64 ? 1 : B == 32 ? 3 : 6);
+    int D = h->cfg_lookahead ? h->cfg_lookahead : (B == 64 ? 6 : B == 32 ? 12 : 20);
+    D = std::min(D, kNzRing - 2);
+    for (;; ) {
+        DN = std::max(1, std::min(DN, D));
+        int NT = h->cfg_tile_stages ? std::max(h->cfg_tile_stages, D + 2) : D + 4;
+        // shrink the record ring of the chain CTA, the tile ring, then the look-ahead, until both CTA roles fit
+        for (;;) {
+            for (int NR = kRecStages; NR >= 2; NR >>= 1) {
+                SmemLayout L = smem_layout((int)R, B, NT, DN, NR);
+                if ((size_t)L.total + 1024 <= cap) {
+                    h->n = n; h->Tw = Tw; h->R = (int)R; h->B = B; h->D = D; h->DN = DN; h->NT = NT; h->NR = NR; h->L = L;
+                    return NGP_OK;
+                }
             }
+            if (NT > D + 2) --NT; else break;
         }
+        if (DN > 1) { --DN; continue; }
+        if (D > 1) { --D; continue; }
+        break;
     }
-    return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA: the panel tile does not fit in %zu bytes of shared memory",
-                (long long)n, (long long)R, cap);
+    return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA: the panel tiles (block %d) do not fit in %zu bytes of shared memory",
+                (long long)n, (long long)R, B, cap);
 }
 
 static int finish_upload(ngp_handle* h, SetHost& S)
@@ -414,18 +433,13 @@ static int finish_upload(ngp_handle* h, SetHost& S)
     CU(dalloc(&S.d, p_pad));
     colstats_kernel<<<(unsigned)((p_pad + 255) / 256), 256, 0, h->stream>>>(h->n, S.p, p_pad, S.colsum, S.colsumsq, S.mean, S.d);
     CU(cudaGetLastError());
-    const int nblk = (int)(p_pad / h->B);
-    CU(dalloc(&S.blk, (size_t)nblk * blk_bytes(h->B)));
-    CU(zero(h, S.blk, 0, (size_t)nblk * blk_bytes(h->B)));
-    CU(dalloc(&S.gramx, (size_t)nblk * h->B * h->B));
-    const size_t gsm = 2 * (size_t)h->B * h->R;
-    if (h->B == 64) {
-        CU(cudaFuncSetAttribute(gram_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-        gram_kernel<64><<<nblk, 256, gsm, h->stream>>>(S.geno, h->T, h->R, p_pad, S.blk, S.gramx);
-    } else {
-        CU(cudaFuncSetAttribute(gram_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-        gram_kernel<32><<<nblk, 256, gsm, h->stream>>>(S.geno, h->T, h->R, p_pad, S.blk, S.gramx);
-    }
+    const int64_t nblk = p_pad / h->B;
+    CU(dalloc(&S.consts, (size_t)nblk * kNF * h->B));
+    CU(zero(h, S.consts, 0, sizeof(double) * (size_t)nblk * kNF * h->B));
+    CU(dalloc(&S.gx, (size_t)nblk * (h->D + 1) * h->B * h->B));
+    if (h->B == 64) gram_kernel<64><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx);
+    else if (h->B == 32) gram_kernel<32><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx);
+    else gram_kernel<16><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx);
     CU(cudaGetLastError());
     CU(dalloc(&S.beta, p_pad));
     CU(dalloc(&S.delta, p_pad));
@@ -447,11 +461,11 @@ static int begin_upload(ngp_handle* h, int set_id, int64_t n, int64_t p, int sto
     if (p > 0x7fffffffLL || n > 0x7fffffffLL) return fail(h, NGP_EINVAL, "n and p must fit in 31 bits");
     if (storage != NGP_STORE_I8) return fail(h, NGP_EUNSUPPORTED, "device storage %d is not available in this build (use NGP_STORE_I8)", storage);
     CU(cudaSetDevice(h->device));
-    if (h->T == 0) {
+    if (h->Tw == 0) {
         int rc = choose_geometry(h, n);
         if (rc) return rc;
-        CU(dalloc(&h->e, (size_t)h->T * h->R));
-        CU(zero(h, h->e, 0, sizeof(double) * (size_t)h->T * h->R));
+        CU(dalloc(&h->e, (size_t)h->Tw * h->R));
+        CU(zero(h, h->e, 0, sizeof(double) * (size_t)h->Tw * h->R));
     } else if (n != h->n) {
         return fail(h, NGP_EINVAL, "all marker sets of a handle must have n = %lld individuals (got %lld)", (long long)h->n, (long long)n);
     }
@@ -460,9 +474,9 @@ static int begin_upload(ngp_handle* h, int set_id, int64_t n, int64_t p, int sto
     S.p = p;
     S.p_pad = ((p + kMaxB - 1) / kMaxB) * kMaxB;
     S.storage = storage;
-    const size_t gbytes = (size_t)h->T * S.p_pad * h->R;
+    const size_t gbytes = (size_t)h->Tw * S.p_pad * h->R;
     CU(dalloc(&S.geno, gbytes));
-    CU(cudaMemsetAsync(S.geno, 0xF0, gbytes, h->stream));          // code 0 everywhere (pad rows / pad markers)
+    CU(cudaMemsetAsync(S.geno, 0, gbytes, h->stream));             // code 0 everywhere (pad rows / pad markers)
     CU(dalloc(&S.colsum, S.p_pad));
     CU(dalloc(&S.colsumsq, S.p_pad));
     CU(cudaMemsetAsync(S.colsum, 0, sizeof(int32_t) * S.p_pad, h->stream));
@@ -493,9 +507,9 @@ int ngp_upload_genotypes(ngp_handle* h, int set_id, int64_t n, int64_t p, const 
     for (int64_t j0 = 0; j0 < p; j0 += chunk) {
         const int64_t nc = std::min(chunk, p - j0);
         CU(cudaMemcpyAsync(stage, (const char*)data + (size_t)j0 * colbytes, colbytes * nc, cudaMemcpyHostToDevice, h->stream));
-        if (fmt == NGP_GENO_I8) pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, S.p_pad, S.geno, S.colsum, S.colsumsq, derr);
-        else if (fmt == NGP_GENO_F64) pack_kernel<NGP_GENO_F64><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, S.p_pad, S.geno, S.colsum, S.colsumsq, derr);
-        else pack_kernel<NGP_GENO_PACKED2><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, S.p_pad, S.geno, S.colsum, S.colsumsq, derr);
+        if (fmt == NGP_GENO_I8) pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr);
+        else if (fmt == NGP_GENO_F64) pack_kernel<NGP_GENO_F64><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr);
+        else pack_kernel<NGP_GENO_PACKED2><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(h->stream));     // the pageable source buffer is borrowed per chunk
     }
@@ -530,7 +544,7 @@ int ngp_synth_genotypes(ngp_handle* h, int set_id, int64_t n, int64_t p, uint64_
         dim3 grid((unsigned)(((n + 3) / 4 + 255) / 256), (unsigned)nc);
         synth_kernel<<<grid, 256, 0, h->stream>>>((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), n, j0, nc, d0, d1, stage);
         CU(cudaGetLastError());
-        pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, n, n, j0, h->R, S.p_pad, S.geno, S.colsum, S.colsumsq, derr);
+        pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, n, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr);
         CU(cudaGetLastError());
     }
     CU(cudaStreamSynchronize(h->stream));
@@ -552,7 +566,7 @@ int ngp_download_genotypes(ngp_handle* h, int set_id, int64_t j0, int64_t j1, in
     for (int64_t c0 = j0; c0 < j1; c0 += chunk) {
         const int64_t nc = std::min(chunk, j1 - c0);
         dim3 grid((unsigned)((n + 255) / 256), (unsigned)nc);
-        unpack_kernel<<<grid, 256, 0, h->stream>>>(S.geno, n, h->R, S.p_pad, c0, nc, stage);
+        unpack_kernel<<<grid, 256, 0, h->stream>>>(S.geno, n, h->R, h->B, S.p_pad / h->B, c0, nc, stage);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out + (size_t)(c0 - j0) * n, stage, (size_t)n * nc, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -607,10 +621,10 @@ int ngp_unpack2(const uint8_t* packed, int64_t n, int64_t p, int64_t ld_in, int8
 int ngp_set_phenotype(ngp_handle* h, const double* y, int64_t n)
 {
     if (!h || !y) return fail(h, NGP_EINVAL, "ngp_set_phenotype: NULL argument");
-    if (h->T == 0) return fail(h, NGP_EINVAL, "ngp_set_phenotype: upload a marker set first (it fixes n)");
+    if (h->Tw == 0) return fail(h, NGP_EINVAL, "ngp_set_phenotype: upload a marker set first (it fixes n)");
     if (n != h->n) return fail(h, NGP_EINVAL, "ngp_set_phenotype: n = %lld but the genotypes have %lld rows", (long long)n, (long long)h->n);
     CU(cudaSetDevice(h->device));
-    CU(zero(h, h->e, 0, sizeof(double) * (size_t)h->T * h->R));
+    CU(zero(h, h->e, 0, sizeof(double) * (size_t)h->Tw * h->R));
     CU(cpy(h, h->e, y, sizeof(double) * n, cudaMemcpyHostToDevice));     // ycorr = deepcopy(Y), mme.jl:57
     Scalars z{};
     CU(cpy(h, h->sc, &z, sizeof z, cudaMemcpyHostToDevice));
@@ -745,7 +759,7 @@ static int sync_sets(ngp_handle* h)
         if (!S.have_geno || !S.have_prior) continue;
         SetDev& D = sd[s];
         D.p = S.p; D.p_pad = S.p_pad; D.method = S.method; D.est_pi = S.est_pi; D.n_regions = S.n_regions; D.nvar = S.nvar;
-        D.df = S.df; D.scale = S.scale; D.geno = S.geno; D.blk = S.blk; D.gramx = S.gramx; D.colsum = S.colsum; D.d = S.d; D.mean = S.mean;
+        D.df = S.df; D.scale = S.scale; D.geno = S.geno; D.gx = S.gx; D.consts = S.consts; D.colsum = S.colsum; D.d = S.d; D.mean = S.mean;
         D.beta = S.beta; D.delta = S.delta; D.varBeta = S.varBeta; D.pi = S.pi; D.region_of = S.region_of; D.region_off = S.region_off;
         D.lhs0 = S.lhs0; D.rhs0 = S.rhs0;
         D.rp_u = S.rp_u; D.rp_z = S.rp_z; D.rp_chi2b = S.rp_chi2b; D.rp_betapi = S.rp_betapi;
@@ -776,30 +790,33 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     int rc = sync_sets(h);
     if (rc) return rc;
     Params P{};
-    P.n = h->n; P.T = h->T; P.R = h->R; P.B = h->B; P.n_sets = h->n_sets; P.stages = h->stages; P.kernel = h->cfg_kernel;
+    P.n = h->n; P.Tw = h->Tw; P.R = h->R; P.B = h->B; P.n_sets = h->n_sets; P.kernel = h->cfg_kernel;
+    P.D = h->D; P.DN = h->DN; P.NT = h->NT; P.NR = h->NR;
     P.e = h->e; P.sets = h->sets_dev; P.sc = h->sc; P.sync = h->sync;
     P.df_e = h->df_e; P.scale_e = h->scale_e; P.has_mu = h->has_mu; P.do_varE = do_varE; P.do_mu = do_mu; P.set_mask = set_mask;
     P.mu_lhs0 = h->mu_lhs0; P.mu_rhs0 = h->mu_rhs0; P.varE_in = varE_in; P.n_iter = n_iter; P.replay = h->replay;
     P.replay_base = h->replay_base; P.rp_chi2_e = h->rp_chi2_e; P.rp_z_mu = h->rp_z_mu;
     P.key0 = (uint32_t)(h->seed & 0xffffffffu); P.key1 = (uint32_t)(h->seed >> 32); P.chain = h->chain; P.accumulate = accumulate;
-    const void* kfn = (h->B == 64) ? (const void*)gibbs_kernel<64> : (const void*)gibbs_kernel<32>;
+    P.debug = h->cfg_debug;
+#define NGP_PICK(PROF, DBG) ((h->B == 64) ? (const void*)gibbs_kernel<64, PROF, DBG> : (h->B == 32) ? (const void*)gibbs_kernel<32, PROF, DBG> : (const void*)gibbs_kernel<16, PROF, DBG>)
+    const void* kfn = h->cfg_debug ? NGP_PICK(false, true) : h->cfg_profile ? NGP_PICK(true, false) : NGP_PICK(false, false);
+#undef NGP_PICK
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->L.total));
     int per_sm = 0;
-    if (h->B == 64) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_kernel<64>, kThreads, h->L.total));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_kernel<32>, kThreads, h->L.total));
-    if (per_sm * h->prop.multiProcessorCount < h->T)
-        return fail(h, NGP_EUNSUPPORTED, "cooperative grid of %d CTAs does not fit (%d per SM x %d SMs)", h->T, per_sm, h->prop.multiProcessorCount);
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, h->L.total));
+    if (per_sm * h->prop.multiProcessorCount < h->Tw + 1)
+        return fail(h, NGP_EUNSUPPORTED, "cooperative grid of %d CTAs does not fit (%d per SM x %d SMs)", h->Tw + 1, per_sm, h->prop.multiProcessorCount);
     CU(cudaMemsetAsync(h->sync, 0, sizeof(SyncArea), h->stream));
     void* args[] = {&P};
     CU(cudaEventRecord(h->ev0, h->stream));
-    CU(cudaLaunchCooperativeKernel(kfn, dim3(h->T), dim3(kThreads), args, (size_t)h->L.total, h->stream));
+    CU(cudaLaunchCooperativeKernel(kfn, dim3(h->Tw + 1), dim3(kThreads), args, (size_t)h->L.total, h->stream));
     CU(cudaEventRecord(h->ev1, h->stream));
     h->launches += 1;
     h->timed = true;
     CU(cudaStreamSynchronize(h->stream));
     int kerr = 0;
     CU(cpy(h, &kerr, &h->sync->err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (kerr) return fail(h, NGP_ERANGE, "fixed-point reduction range exceeded (residual grew by more than 2^8 within an iteration)");
+    if (kerr) return fail(h, NGP_ERANGE, "fixed-point reduction range exceeded (residual grew by more than 2^4 within an iteration)");
     return NGP_OK;
 }
 
@@ -884,7 +901,7 @@ int ngp_get_state(ngp_handle* h, ngp_state* out)
 int ngp_set_state(ngp_handle* h, const ngp_state* in)
 {
     if (!h || !in) return fail(h, NGP_EINVAL, "ngp_set_state: NULL argument");
-    if (h->T == 0) return fail(h, NGP_EINVAL, "ngp_set_state: upload a marker set first");
+    if (h->Tw == 0) return fail(h, NGP_EINVAL, "ngp_set_state: upload a marker set first");
     CU(cudaSetDevice(h->device));
     Scalars sc;
     CU(cpy(h, &sc, h->sc, sizeof sc, cudaMemcpyDeviceToHost));
@@ -935,8 +952,8 @@ int ngp_get_timing(ngp_handle* h, ngp_timing* out)
 {
     if (!h || !out) return fail(h, NGP_EINVAL, "ngp_get_timing: NULL argument");
     memset(out, 0, sizeof *out);
-    out->launches = h->launches; out->ctas = h->T; out->threads = kThreads; out->block = h->B; out->rows_per_cta = h->R;
-    out->smem_bytes = h->L.total;
+    out->launches = h->launches; out->ctas = h->Tw ? h->Tw + 1 : 0; out->threads = kThreads; out->block = h->B; out->rows_per_cta = h->R;
+    out->smem_bytes = h->L.total; out->lookahead = h->D; out->near_depth = h->DN; out->tile_stages = h->NT; out->record_stages = h->NR;
     if (h->timed) {
         float ms = 0.f;
         CU(cudaEventSynchronize(h->ev1));
@@ -950,7 +967,7 @@ int ngp_get_profile(ngp_handle* h, int64_t* out, int32_t max_ctas)
 {
     if (!h || !out || max_ctas <= 0) return fail(h, NGP_EINVAL, "ngp_get_profile: bad argument");
     CU(cudaSetDevice(h->device));
-    const int nc = std::min<int>(max_ctas, h->T);
+    const int nc = std::min<int>(max_ctas, h->Tw + 1);
     CU(cpy(h, out, h->sync->prof, sizeof(long long) * kProf * nc, cudaMemcpyDeviceToHost));
     return nc;
 }

@@ -1,16 +1,15 @@
 // ngp_device.cuh — device-side data structures and small PTX wrappers of libngp.
 //
-// HBM layout of one marker set ("row-panelled column-major"):
-//   the n individuals are cut into T row panels of R rows (R = 8*odd), panel t is
-//   owned by CTA t of the persistent sweep kernel; inside a panel the markers are
-//   consecutive and each marker's R codes are contiguous:
-//       geno[(t * p_pad + j) * R + r]      row i = t*R + r, marker j
-//   so a block of B consecutive markers of one panel is ONE contiguous B*R-byte
-//   chunk that a single cp.async.bulk (TMA) brings into shared memory, and every
-//   column is read from HBM exactly once per sweep.
-//   A stored byte is 0xF0 | (code << 2): placed in bits 16..23 of the high word
-//   of an fp64 (under 0x3F in bits 24..31) it IS the double 1 + code/4, so one
-//   PRMT turns a code into an FMA operand (no I2F on the hot path).
+// HBM layout of one marker set ("row-panelled, block-tiled, fragment-ordered"):
+//   the n individuals are cut into Tw row panels of R rows (R = multiple of 32), panel t is owned by worker CTA t
+//   of the persistent sweep kernel; the p markers are cut into blocks of B.  The B x R codes of (panel t, block k)
+//   are ONE contiguous B*R-byte tile
+//       geno[(t * nblk + k) * B * R + byte_off(B, q, r)]      marker k*B + q, row t*R + r
+//   that a single cp.async.bulk (TMA) brings into shared memory, so every column is read from HBM exactly
+//   once per sweep.  Inside a tile the bytes are stored in the operand order of the INT8 tensor-core
+//   instruction mma.sync.m16n8k32 (A = 16 markers x 32 rows, row-major): the four 32-bit A registers of a lane
+//   are 16 contiguous bytes, so the dot phase loads its operands with one conflict-free LDS.128 per MMA.
+//   A stored byte is the plain code 0/1/2.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
@@ -18,17 +17,32 @@
 
 namespace ngp {
 
-constexpr int kThreads = 320;          // sweep kernel: warp 0 = chain warp, warps 1..8 = workers, warp 9 = TMA producer
-constexpr int kWarps = kThreads / 32;
-constexpr int kWorkerWarps = 8;
-constexpr int kProducerWarp = kWorkerWarps + 1;
-constexpr int kProf = 16;              // cycle counters per CTA (ngp_get_profile)
-constexpr int kMaxB = 64;              // markers per block (32 or 64)
+// ---- CTA geometry of the sweep kernel: worker CTAs 0..Tw-1 own row panels, CTA Tw runs the scalar chain
+constexpr int kUpdWarps = 4;           // worker CTA: warps 0..3 "updaters": residual rows in registers, axpy + re-quantise
+constexpr int kUpdThreads = kUpdWarps * 32;
+constexpr int kUpdGroups = 4;          //             4-row groups per updater thread: R <= 4 * kUpdThreads * kUpdGroups = 2048
+constexpr int kDotWarps = 8;           //             warps 4..11 "dot warps": each owns whole blocks (IMMA dots + RED)
+constexpr int kFirstDotWarp = kUpdWarps;
+constexpr int kTmaWarp = 12;           //             warp 12 lane 0: TMA producer of the tile ring
+constexpr int kPollWarp = 13;          //             warp 13: receives the changed-effect lists of the chain CTA
+constexpr int kWarps = 14;
+constexpr int kThreads = kWarps * 32;  // chain CTA: warp 0 chain, warp 1 TMA producer of the block records, warps 2..9 "prep" warps
+constexpr int kPrepWarps = 8;          //            (poll accumulators, cross-Gram corrections of distance >= 2 -> r_base)
+constexpr int kFirstPrepWarp = 2;
+constexpr int kLimbVers = 4;           // versions of the fixed-point residual kept per worker CTA
+
+constexpr int kProf = 24;              // cycle counters per CTA (ngp_get_profile)
+constexpr int kMaxB = 64;              // markers per block: 16, 32 or 64
 constexpr int kNF = 10;                // per-marker constant fields
-constexpr int kSlots = 4;              // reduction accumulator ring (look-ahead 1 needs >= 4)
-constexpr int kAccStride = 32;         // int64 units between accumulators (256 B: distinct L2 slices)
+constexpr int kMaxD = 24;              // maximum look-ahead depth (blocks)
+constexpr int kSlots = 32;             // accumulator ring (blocks in flight <= D+1), multiple of kPrepWarps
 constexpr int kMaxCtas = 160;          // < 256: the low byte of an accumulator counts arrivals
 constexpr int kCntBits = 8;
+constexpr int kNzRing = 32;            // rings indexed by the global block number (lists, versions, dot-done flags): >= D+2
+constexpr int kNzSmem = 4;             // worker-CTA smem ring of received lists
+constexpr int kRecStages = 8;          // chain CTA: maximum stages of the block-record ring (TMA)
+constexpr int kLLEntryWords = 5;       // idx, dbeta lo/hi, K lo/hi
+constexpr int kLLSlotWords = 1 + kLLEntryWords * kMaxB + 3;   // header + entries, padded to a multiple of 4 words
 
 // fields of the per-iteration marker constants, stored [block][field][B]
 enum Field { F_A = 0, F_B = 1, F_T = 2, F_C = 3, F_QSZ = 4, F_D = 5, F_BOLD = 6, F_MEAN = 7, F_CS = 8, F_CHI = 9 };
@@ -38,10 +52,9 @@ struct SetDev {
     int32_t method, est_pi;
     int64_t n_regions, nvar;
     double df, scale;
-    const uint8_t* geno;       // [T][p_pad][R]
-    uint8_t* blk;              // [p_pad/B] records {int32 gram[B][B]; double consts[kNF][B]}: raw Gram inside block k
-                               //   (sum_i g_a g_b) + the per-iteration marker constants, one TMA bulk copy per block
-    const int32_t* gramx;      // [p_pad/B][B][B] raw sum g_a g_b, a in block k-1, b in block k (block 0: zeros)
+    const uint8_t* geno;       // [Tw][p_pad/B] tiles of B*R bytes
+    const int32_t* gx;         // [p_pad/B][D+1][B][B]: gx[k][d][a][b] = raw sum_i g_a g_b, a in block k-d, b in block k (zeros for k < d)
+    double* consts;            // [p_pad/B][kNF][B] per-iteration marker constants (phase 1)
     const int32_t* colsum;     // [p_pad]
     const double* d;           // [p_pad] mpm
     const double* mean;        // [p_pad]
@@ -62,12 +75,12 @@ struct SetDev {
     double* sum_delta;
 };
 
-struct SyncArea {
+struct SyncArea {              // zeroed before every launch
     unsigned long long counter;                 // grid-barrier arrivals, monotonic within a launch
     unsigned long long pad0[15];
-    long long acc[kSlots * (kMaxB + 1) * kAccStride];   // fixed-point reduction accumulators (monotonic)
+    long long acc[kSlots * kMaxB];              // fixed-point reduction accumulators (monotonic; low byte counts arrivals)
+    unsigned long long ll[kNzRing * kLLSlotWords];   // changed-effect lists chain CTA -> worker CTAs; every 8-byte word = {payload32, seq32}
     double part[kMaxCtas * 2];                  // phase-0 partials (e'e, sum e) per CTA
-    int zero16[16];                             // runtime zeros (low words of the fp64 code operands, see dec_byte_z)
     long long prof[kMaxCtas * kProf];           // per-CTA cycle counters of the last launch: see ngp_get_profile
     int err;
 };
@@ -80,8 +93,11 @@ struct Scalars {          // device-resident chain scalars
 
 struct Params {
     int64_t n;
-    int32_t T, R, B, n_sets, stages, kernel;
-    double* e;                 // [T*R]
+    int32_t Tw;                // worker CTAs (row panels); the grid has Tw + 1 CTAs
+    int32_t R, B, n_sets, kernel;
+    int32_t D, DN, NT, NR;     // look-ahead depth (blocks), near depth (cross-Grams kept in the block record), tile ring stages,
+                               // block-record ring stages of the chain CTA (power of two <= kRecStages)
+    double* e;                 // [Tw*R]
     const SetDev* sets;        // device array
     Scalars* sc;
     SyncArea* sync;
@@ -95,7 +111,24 @@ struct Params {
     const double* rp_z_mu;
     uint32_t key0, key1, chain;
     int32_t accumulate;        // add to posterior sums
+    int32_t debug;             // timing experiments (NGP_CFG_DEBUG), see ngp_sweep.cuh
 };
+
+// ----------------------------------------------------------------------------- tile layout
+// 32-bit word (rows 4*wr .. 4*wr+3 of the panel) of marker q of a block, in units of words.
+// mma.m16n8k32 A fragment: lane = 4*g + t holds a0 = A[g][4t..4t+3], a1 = A[g+8][4t..], a2 = A[g][16+4t..], a3 = A[g+8][16+4t..]
+// The same word is a B-fragment register of the transposed product (Gram set-up kernel): b0/b1 = rows 4t.. / 16+4t.. of column g.
+__host__ __device__ __forceinline__ int word_off(int B, int q, int wr)
+{
+    const int c = wr >> 3, wq = wr & 7;                 // chunk of 32 rows, word inside the chunk
+    const int mg = q >> 4, qq = q & 15, g = qq & 7, hi8 = qq >> 3;
+    const int a_idx = ((wq >> 2) << 1) | hi8, t = wq & 3;
+    return (((c * (B >> 4) + mg) * 32 + g * 4 + t) << 2) | a_idx;
+}
+__host__ __device__ __forceinline__ int byte_off(int B, int q, int r) { return (word_off(B, q, r >> 2) << 2) | (r & 3); }
+
+__host__ __device__ __forceinline__ int consts_bytes(int B) { return kNF * B * 8; }
+__host__ __device__ __forceinline__ int gram_bytes(int B) { return B * B * 4; }
 
 // ----------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void red_add_u64(long long* addr, long long v)
@@ -106,17 +139,21 @@ __device__ __forceinline__ void arrive_release(unsigned long long* c)
 {
     asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(c) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* c)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(c) : "memory");
-    return v;
-}
 __device__ __forceinline__ long long ld_relaxed_s64(const long long* p)     // LDG.STRONG.GPU, no L1, no fence
 {
     long long v;
     asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -127,6 +164,10 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
@@ -148,21 +189,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// stored byte k of word w -> the double 1 + code/4
-__device__ __forceinline__ double dec_byte(uint32_t w, int k)
+// INT8 tensor-core MMA, D(16x8,s32) += A(16x32,s8,row) * B(32x8,s8,col)   (SASS: IMMA.16832.S8.S8)
+__device__ __forceinline__ void imma16832(int (&c)[4], const uint4& a, uint32_t b0, uint32_t b1)
 {
-    const uint32_t hi = __byte_perm(w, 0x3F000000u, 0x7044u | ((uint32_t)k << 8));
-    return __hiloint2double((int)hi, 0);
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
-// same with the low word taken from a register that holds a RUNTIME zero: the compiler cannot fold it, so it keeps
-// the zero in the even register of the operand pair and the PRMT writes the odd one in place (no MOV per code)
-__device__ __forceinline__ double dec_byte_z(uint32_t w, int k, int z)
-{
-    const uint32_t hi = __byte_perm(w, 0x3F000000u, 0x7044u | ((uint32_t)k << 8));
-    return __hiloint2double((int)hi, z);
-}
-__host__ __device__ __forceinline__ int blk_bytes(int B) { return B * B * 4 + kNF * B * 8; }
-__host__ __device__ __forceinline__ uint8_t enc_code(int g) { return (uint8_t)(0xF0 | (g << 2)); }
-__host__ __device__ __forceinline__ int dec_code(uint8_t b) { return (b >> 2) & 3; }
+
+// A ring cursor: stage index + mbarrier phase parity, advanced once per use
+struct Ring {
+    int s;
+    uint32_t ph;
+    __device__ __forceinline__ void adv(int n) { if (++s == n) { s = 0; ph ^= 1u; } }
+};
 
 }  // namespace ngp

@@ -4,56 +4,80 @@
 // (/root/reference/src/samplers.jl:32-53) on device:
 //   phase 0  e'e and 1'e  -> varE (functions.jl:523-525), intercept (functions.jl:39-47)
 //   phase 1  per-marker constants + variates for every marker set (grid-parallel)
-//   phase 2  the marker sweep (functions.jl:118-137 / 157-195 / 197-236), CTA t owning
-//            row panel t of the genotypes and of the residual e (resident in smem)
+//   phase 2  the marker sweep (functions.jl:118-137 / 157-195 / 197-236)
 //   phase 3  variance components and pi (functions.jl:509-511, 531-533), posterior sums
 //
-// Phase 2, blocked exact sweep with one block of look-ahead.
-// Warp 0 of every CTA is the "chain warp", warps 1..8 are "workers".  In step k
-//   workers : e -= X_{k-1} dbeta_{k-1}            (tile k-1 still in smem: column read from HBM once)
-//             A_{k+1} = sum_i (1 + g/4) e_i        (tile k+1, prefetched by TMA; one PRMT + one DFMA per code)
-//             fixed point, RED (value<<8)+1 into the global int64 accumulators of block k+1:
-//             integer adds are associative (bit-reproducible) and the low byte counts arrivals,
-//             so an accumulator is its own barrier - no fence, no counter, no grid-wide stall;
-//   chain   : polls the accumulators of block k (their REDs were issued one step earlier),
-//             r_j = 4(A_j - S) - m_j S - [cross-Gram rows of block k-1] dbeta_{k-1} - [Gram rows of block k] dbeta_k,
-//             runs the B dependent scalar updates redundantly in every CTA (identical inputs and code =>
-//             identical results, no broadcast); mixture priors: 32 lanes evaluate 32 markers speculatively
-//             and serialise only on markers whose effect actually changes.
-// The dots of block k+1 therefore never wait for the chain of block k: its effect on them is restored
-// exactly by G_{k+1,k} dbeta_k (integer Gram, precomputed once).
-// The "literal" variant does dot / reduce / draw / axpy per marker from registers with one grid-wide
-// reduction per marker (the north-star baseline whose sync cost we report).
+// Phase 2, blocked exact sweep with D blocks of look-ahead.  The grid is Tw worker CTAs + 1 chain CTA.
+//   worker CTA t : owns row panel t of the genotypes (TMA tile ring in smem, each column read from HBM once per sweep)
+//                  and of the residual e.  Roles inside the CTA run decoupled, handing work over through mbarriers:
+//                  * updater warps hold e in REGISTERS (4 consecutive rows per thread), apply the changed effects of
+//                    block ja,  e -= dbeta (g - mean),  from one 32-bit tile word per changed marker, and write a new
+//                    VERSION of the fixed-point residual (8 signed byte limbs per row, B-operand order of the MMA);
+//                  * dot warps each own whole blocks: for block j the warp reads version j-D-1 of the limbs and forms
+//                    A_j[q] = sum_i g_iq e_i  as an exact integer dot on the INT8 tensor cores (mma.sync.m16n8k32:
+//                    A = 16 markers x 32 rows of codes, B = 32 rows x 8 limbs), combines the limbs to int64 and RED-adds
+//                    (value<<8)+1 into a global accumulator: integer adds are associative (bit-reproducible) and the low
+//                    byte counts arrivals, so an accumulator is its own barrier.  8 blocks are in flight per CTA;
+//                  * one lane drives the TMA tile ring, one warp receives the changed-effect lists.
+//   chain CTA    : prep warps poll the accumulators of block m, r = A/2^s - mean*1'e, and restore exactly the effect of
+//                  the blocks m-D..m-2 that the dots have not seen:  r -= Gc[a][q] dbeta_a  with the integer cross-Gram
+//                  (precomputed once): distances DN+1..D from HBM/L2, distances 2..DN from the TMA'd block record.
+//                  The chain warp applies distance 1 and the block's own Gram, runs the B dependent scalar updates
+//                  (mixture priors: 32 lanes evaluate 32 markers speculatively and serialise only on markers whose effect
+//                  actually changes) and publishes the changed effects {q, dbeta, dbeta*mean} to the worker CTAs through a
+//                  global ring of 8-byte {payload, sequence} words (no fence on either side).
+// The "literal" variant does dot / reduce / draw / axpy per marker with one grid-wide reduction per marker (the
+// north-star baseline whose sync cost we report).
 #pragma once
 #include "ngp_device.cuh"
 
 namespace ngp {
 
-struct SmemLayout {
-    int off_e, off_tile, off_blk, off_red, off_prev, off_nzdb, off_nzcs, off_nzidx, off_outb, off_outv, off_outi, off_misc, off_mbar, total;
-    int tile_bytes, blk_bytes;
+template <int B>
+struct NzListT {                // changed effects of one block
+    int nnz, pad;
+    int idx[B];
+    double db[B];               // dbeta
+    double aux[B];              // worker side: dbeta * mean ; chain side: column sum of the marker
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int R, int B, int stages)
+struct SmemLayout {
+    // worker CTA
+    int w_e, w_limb, w_tile, w_nz, w_vbuf, w_bar;
+    // chain CTA
+    int c_rec, c_rbase, c_nz, c_prev, c_bar;
+    int misc, total;
+    int tile_bytes, rec_bytes, limb_bytes, nz_bytes;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(int R, int B, int NT, int DN, int NR)
 {
     SmemLayout L;
-    int o = 0;
     L.tile_bytes = B * R;
-    L.blk_bytes = blk_bytes(B);
-    L.off_e = o;      o += R * 8;
-    L.off_tile = o;   o += stages * L.tile_bytes;
-    L.off_blk = o;    o += stages * L.blk_bytes;
-    L.off_red = o;    o += 2 * kWorkerWarps * kMaxB * 8;
-    L.off_prev = o;   o += kSlots * (kMaxB + 1) * 8;
-    L.off_nzdb = o;   o += 2 * kMaxB * 8;
-    L.off_nzcs = o;   o += 2 * kMaxB * 8;
-    L.off_nzidx = o;  o += 2 * kMaxB * 4;
-    L.off_outb = o;   o += 2 * kMaxB * 8;
-    L.off_outv = o;   o += 2 * kMaxB * 8;
-    L.off_outi = o;   o += 2 * kMaxB * 4;
-    L.off_misc = o;   o += 64 * 8;
-    L.off_mbar = o;   o += 8 * 8;
-    L.total = o;
+    L.rec_bytes = (1 + DN) * gram_bytes(B) + consts_bytes(B);
+    L.limb_bytes = R * 8;
+    L.nz_bytes = 8 + 20 * B;
+    int o = 0;
+    L.misc = o;    o += 96 * 8;
+    const int base = o;
+    // worker
+    L.w_e = o;     o += R * 8;
+    L.w_limb = o;  o += kLimbVers * L.limb_bytes;
+    L.w_nz = o;    o += kNzSmem * L.nz_bytes;
+    L.w_vbuf = o;  o += kNzRing * 4;
+    L.w_bar = o;   o += (2 * NT + 2 * kNzSmem + 2 * kNzRing) * 8;
+    o = (o + 127) & ~127;
+    L.w_tile = o;  o += NT * L.tile_bytes;
+    const int wtot = o;
+    // chain
+    o = base;
+    L.c_bar = o;   o += (2 * kRecStages + 2 * kPrepWarps + kNzRing) * 8;
+    L.c_rbase = o; o += kPrepWarps * B * 8;
+    L.c_prev = o;  o += kSlots * B * 8;
+    L.c_nz = o;    o += kNzRing * L.nz_bytes;
+    o = (o + 127) & ~127;
+    L.c_rec = o;   o += NR * L.rec_bytes;
+    L.total = o > wtot ? o : wtot;
     return L;
 }
 
@@ -79,8 +103,6 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch
     __syncthreads();
     a = sa; b = sb;
 }
-
-__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerWarps * 32) : "memory"); }
 
 struct GridSync {
     unsigned long long* counter;
@@ -111,7 +133,7 @@ __device__ __forceinline__ void prep_marker(const Params& P, const SetDev& S, in
                                             uint32_t iter, int64_t rp_row)
 {
     const int B = P.B;
-    double* c = reinterpret_cast<double*>(S.blk + (j / B) * (int64_t)blk_bytes(B) + B * B * 4) + (j % B);
+    double* c = S.consts + (j / B) * (int64_t)(kNF * B) + (j % B);
     double fA = 0.0, fB = 0.0, fT = -INFINITY, fC = 0.0, fQSZ = 0.0, fD = 0.0, fBOLD = 0.0, fMEAN = 0.0, fCS = 0.0, fCHI = 1.0;
     if (j < S.p) {
         const double d = S.d[j];
@@ -147,60 +169,126 @@ __device__ __forceinline__ void prep_marker(const Params& P, const SetDev& S, in
     c[F_D * B] = fD; c[F_BOLD * B] = fBOLD; c[F_MEAN * B] = fMEAN; c[F_CS * B] = fCS; c[F_CHI * B] = fCHI;
 }
 
+// ----------------------------------------------------------------------------- fixed-point residual limbs
+// Rows 4*rg .. 4*rg+3 of e -> 8 signed byte limbs per row in the B-fragment order of mma.m16n8k32: inside the 256-byte
+// record of a 32-row chunk, word [half][n][tt] (XOR-swizzled by half) holds limb n of rows 32c + 16*half + 4*tt + (0..3).
+// e_fx = rint(e * 2^sh) = sum_n d_n 256^n (mod 2^64) with d_n in [-128,127]: the balanced digits are the bytes of
+// (e_fx + 0x0080808080808080) ^ 0x0080808080808080.
+__device__ __forceinline__ void quantise4(const double (&e)[4], uint32_t* limb, int rg, double fx_scale)
+{
+    const int c = rg >> 3, half = (rg >> 2) & 1, tt = rg & 3;
+    const unsigned long long bias = 0x0080808080808080ull;
+    const unsigned long long x0 = ((unsigned long long)__double2ll_rn(e[0] * fx_scale) + bias) ^ bias;
+    const unsigned long long x1 = ((unsigned long long)__double2ll_rn(e[1] * fx_scale) + bias) ^ bias;
+    const unsigned long long x2 = ((unsigned long long)__double2ll_rn(e[2] * fx_scale) + bias) ^ bias;
+    const unsigned long long x3 = ((unsigned long long)__double2ll_rn(e[3] * fx_scale) + bias) ^ bias;
+    uint32_t* dst = limb + c * 64 + half * 32;
+    const int sw = half << 2;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {          // low / high 32 bits: limbs 4h .. 4h+3
+        const uint32_t a0 = (uint32_t)(x0 >> (32 * h)), a1 = (uint32_t)(x1 >> (32 * h));
+        const uint32_t a2 = (uint32_t)(x2 >> (32 * h)), a3 = (uint32_t)(x3 >> (32 * h));
+        const uint32_t t0 = __byte_perm(a0, a1, 0x5140), t1 = __byte_perm(a2, a3, 0x5140);
+        const uint32_t t2 = __byte_perm(a0, a1, 0x7362), t3 = __byte_perm(a2, a3, 0x7362);
+        dst[(((4 * h + 0) << 2) | tt) ^ sw] = __byte_perm(t0, t1, 0x5410);
+        dst[(((4 * h + 1) << 2) | tt) ^ sw] = __byte_perm(t0, t1, 0x7632);
+        dst[(((4 * h + 2) << 2) | tt) ^ sw] = __byte_perm(t2, t3, 0x5410);
+        dst[(((4 * h + 3) << 2) | tt) ^ sw] = __byte_perm(t2, t3, 0x7632);
+    }
+}
+
 // ----------------------------------------------------------------------------- the kernel
-template <int B>
+template <int B, bool PROF, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NB = (B + 31) / 32;      // markers per lane of a chain / prep warp (lane <-> marker b*32 + lane)
+    constexpr int MG = B / 16;             // 16-marker MMA groups per block
+    constexpr int UG = (B == 16) ? kUpdGroups : 1;   // 4-row groups per updater thread (B = 32 / 64 are chosen for R <= 512)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = blockIdx.x;
-    const int R = P.R, S_ = P.stages;
-    const SmemLayout L = smem_layout(R, B, S_);
-    double* e_s = reinterpret_cast<double*>(smem + L.off_e);
-    double* red = reinterpret_cast<double*>(smem + L.off_red);
-    long long* prev = reinterpret_cast<long long*>(smem + L.off_prev);
-    double* nz_db = reinterpret_cast<double*>(smem + L.off_nzdb);      // [2][kMaxB]  4*dbeta of the changed markers of a block
-    double* nz_cs = reinterpret_cast<double*>(smem + L.off_nzcs);      // [2][kMaxB]  their column sums
-    int* nz_idx = reinterpret_cast<int*>(smem + L.off_nzidx);          // [2][kMaxB]  their index inside the block
-    double* out_b = reinterpret_cast<double*>(smem + L.off_outb);      // [2][kMaxB] staged outputs of a block (written to HBM by the producer warp of CTA 0)
-    double* out_v = reinterpret_cast<double*>(smem + L.off_outv);
-    int* out_i = reinterpret_cast<int*>(smem + L.off_outi);
-    double* misc = reinterpret_cast<double*>(smem + L.off_misc);       // [0..17] block_sum scratch, [32..] scalars, [40+2i] nnz, [41+2i] K
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L.off_mbar);
+    const int Tw = P.Tw;
+    const bool is_chain = (t == Tw);
+    const int R = P.R, D = P.D, DN = P.DN, NT = P.NT, NR = P.NR;
+    const SmemLayout L = smem_layout(R, B, NT, DN, NR);
+    // timing experiments only (results are garbage): 1 workers ignore the lists, 2 prep warps skip the accumulator poll,
+    // 4 chain warp skips corrections + scalar updates, 8 workers skip the dots and the RED
+    const int dbg = DBG ? P.debug : 0;
+    double* misc = reinterpret_cast<double*>(smem + L.misc);     // [0..27] block_sum scratch, [32..] scalars, [48..] literal-kernel prev
     SyncArea* sy = P.sync;
-    constexpr int NB = B >> 5;             // 32-marker groups per block (lane <-> marker b*32 + lane)
 
-    GridSync gs{&sy->counter, 0ull, (unsigned)P.T};
+    typedef NzListT<B> NzList;
+    // worker views
+    double* e_s = reinterpret_cast<double*>(smem + L.w_e);
+    uint32_t* limb = reinterpret_cast<uint32_t*>(smem + L.w_limb);                          // [kLimbVers][R*2] words
+    NzList* wnz = reinterpret_cast<NzList*>(smem + L.w_nz);
+    int* vbuf = reinterpret_cast<int*>(smem + L.w_vbuf);                                    // [kNzRing] limb version holding the state after block g
+    uint64_t* tile_full = reinterpret_cast<uint64_t*>(smem + L.w_bar);
+    uint64_t* tile_free = tile_full + NT;
+    uint64_t* nz_full = tile_free + NT;
+    uint64_t* nz_free = nz_full + kNzSmem;
+    uint64_t* ver_full = nz_free + kNzSmem;                                                 // [kNzRing] block g applied to e
+    uint64_t* dot_done = ver_full + kNzRing;                                                // [kNzRing] dots of block g formed
+    // chain views
+    uint64_t* rec_full = reinterpret_cast<uint64_t*>(smem + L.c_bar);
+    uint64_t* rec_free = rec_full + kRecStages;
+    uint64_t* rb_full = rec_free + kRecStages;
+    uint64_t* rb_free = rb_full + kPrepWarps;
+    uint64_t* nzc_full = rb_free + kPrepWarps;
+    double* rbase = reinterpret_cast<double*>(smem + L.c_rbase);                            // [kPrepWarps][B]
+    long long* prev = reinterpret_cast<long long*>(smem + L.c_prev);                        // [kSlots][B]
+    NzList* cnz = reinterpret_cast<NzList*>(smem + L.c_nz);
+
+    GridSync gs{&sy->counter, 0ull, (unsigned)(Tw + 1)};
     const int64_t row0 = (int64_t)t * R;
-    const int nrow = (int)max((int64_t)0, min((int64_t)R, P.n - row0));   // real rows of this panel
+    const int nrow = is_chain ? 0 : (int)max((int64_t)0, min((int64_t)R, P.n - row0));    // real rows of this panel
+    const int nchunk = R >> 5;
 
-    for (int r = tid; r < R; r += kThreads) e_s[r] = (r < nrow) ? P.e[row0 + r] : 0.0;
-    for (int q = tid; q < kSlots * (kMaxB + 1); q += kThreads) prev[q] = 0;
+    if (!is_chain) {
+        for (int r = tid; r < R; r += kThreads) e_s[r] = (r < nrow) ? P.e[row0 + r] : 0.0;
+    } else {
+        for (int q = tid; q < kSlots * B; q += kThreads) prev[q] = 0;
+    }
+    if (tid < kSlots) reinterpret_cast<long long*>(misc + 48)[tid] = 0;      // literal kernel: previous accumulator values
     if (tid == 0) {
-        for (int s = 0; s < S_; ++s) mbar_init(&mbar[s], 1);
+        if (!is_chain) {
+            for (int s = 0; s < NT; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_free[s], kUpdWarps); }
+            for (int s = 0; s < kNzSmem; ++s) { mbar_init(&nz_full[s], 1); mbar_init(&nz_free[s], kUpdWarps); }
+            for (int s = 0; s < kNzRing; ++s) { mbar_init(&ver_full[s], kUpdWarps); mbar_init(&dot_done[s], 1); }
+        } else {
+            for (int s = 0; s < kRecStages; ++s) { mbar_init(&rec_full[s], 1); mbar_init(&rec_free[s], 1); }
+            for (int s = 0; s < kPrepWarps; ++s) { mbar_init(&rb_full[s], 1); mbar_init(&rb_free[s], 1); }
+            for (int s = 0; s < kNzRing; ++s) mbar_init(&nzc_full[s], 1);
+        }
         fence_mbar_init();
     }
     __syncthreads();
 
-    // cycle counters (thread 0 = chain warp, thread 32 = first worker warp), see ngp_get_profile
+    // cycle counters, see ngp_get_profile
     long long pf[kProf];
 #pragma unroll
     for (int i = 0; i < kProf; ++i) pf[i] = 0;
-    long long tc = clock64();
-#define NGP_TICK(i) do { const long long now__ = clock64(); pf[i] += now__ - tc; tc = now__; } while (0)
-    unsigned gk = 0;         // tile ring position in [0, 2*stages): stage = gk mod stages, mbarrier parity = (gk div stages) & 1
-    unsigned rk = 0;         // running reduction count (accumulator slot = rk & (kSlots-1))
+    long long tc = 0;
+#define NGP_TICK(i) do { if constexpr (PROF) { const long long now__ = clock64(); pf[i] += now__ - tc; tc = now__; } } while (0)
+
+    // ring cursors: every role advances its cursors once per block, so they stay consistent across sweeps
+    Ring r_ta{0, 0}, r_tp{0, 0};                  // tile ring: updater (release), TMA producer
+    Ring r_nzw{0, 0}, r_nzp{0, 0};                // worker nz list ring: consumer (updaters), producer (poll warp)
+    Ring r_rec{0, 0};                             // chain CTA record ring (TMA producer cursor)
+    unsigned tiles_issued = 0, recs_issued = 0, nz_recv = 0, rb_uses = 0;
+    unsigned gblk = 0;       // blocks processed before the current sweep (all sets, all iterations of this launch)
+    unsigned rk = 0;         // literal kernel: running reduction count
     double mu = P.sc->mu;
     const long long iter0 = P.sc->iter;
 
     for (int it = 0; it < P.n_iter; ++it) {
         const uint32_t iter = (uint32_t)(iter0 + it + 1);
         const int64_t rp_row = (int64_t)iter - 1 - P.replay_base;
-        tc = clock64();
+        if constexpr (PROF) tc = clock64();
 
         // ------------------------------------------------------------------ phase 0
         double ee = 0.0, se = 0.0;
-        for (int r = tid; r < R; r += kThreads) { const double x = e_s[r]; ee = fma(x, x, ee); se += x; }
+        if (!is_chain) for (int r = tid; r < R; r += kThreads) { const double x = e_s[r]; ee = fma(x, x, ee); se += x; }
         block_sum2(ee, se, misc);
         if (tid == 0) {
             sy->part[2 * t] = ee; sy->part[2 * t + 1] = se;
@@ -209,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         if (warp == 0) {
             gs.wait_warp();
             double a = 0.0, b = 0.0;
-            for (int c = lane; c < P.T; c += 32) { a += __ldcg(&sy->part[2 * c]); b += __ldcg(&sy->part[2 * c + 1]); }
+            for (int c = lane; c < Tw; c += 32) { a += __ldcg(&sy->part[2 * c]); b += __ldcg(&sy->part[2 * c + 1]); }
             a = warp_sum(a); b = warp_sum(b);
             if (lane == 0) {
                 double varE = P.varE_in;
@@ -229,12 +317,13 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     dmu = mu - mu_new;
                     mu = mu_new;
                 }
-                // fixed-point scale of the sweep reductions: |sum g e| <= 2 sqrt(n) ||e||
+                // fixed-point scale of the sweep reductions: |sum_i g_i e_i| <= 2 sqrt(n) ||e|| (Cauchy-Schwarz), 2^4 headroom
+                // for growth of ||e|| inside the iteration, 8 count bits: the grid total stays below 2^55
                 const double nn = (double)P.n;
                 double M = 2.0 * sqrt(nn) * (sqrt(a) + sqrt(nn) * fabs(dmu));
                 if (!(M > 1e-300)) M = 1e-300;
                 int ex; (void)frexp(M, &ex);
-                int sh = 62 - kCntBits - 8 - ex;          // 8 count bits + 2^8 headroom for growth of ||e|| inside the iteration
+                int sh = 62 - kCntBits - 4 - ex;
                 sh = max(-1000, min(1000, sh));
                 misc[32] = varE; misc[33] = dmu; misc[34] = b + nn * dmu; misc[35] = (double)sh; misc[36] = mu;
             }
@@ -247,13 +336,13 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         mu = misc[36];
         const double fx_scale = ldexp(1.0, sh), fx_inv = ldexp(1.0, -sh);
         if (dmu != 0.0) for (int r = tid; r < nrow; r += kThreads) e_s[r] += dmu;
-        NGP_TICK(8);
+        if (tid == 0) NGP_TICK(8);
 
         // ------------------------------------------------------------------ phase 1
         for (int s = 0; s < P.n_sets; ++s) {
             if (!((P.set_mask >> s) & 1)) continue;
             const SetDev& S = P.sets[s];
-            for (int64_t j = (int64_t)t * kThreads + tid; j < S.p_pad; j += (int64_t)P.T * kThreads)
+            for (int64_t j = (int64_t)t * kThreads + tid; j < S.p_pad; j += (int64_t)(Tw + 1) * kThreads)
                 prep_marker(P, S, s, j, varE, iter, rp_row);
         }
         __syncthreads();
@@ -261,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         if (tid == 0) gs.arrive();
         if (warp == 0) gs.wait_warp();
         __syncthreads();
-        NGP_TICK(9);
+        if (tid == 0) NGP_TICK(9);
 
         // ------------------------------------------------------------------ phase 2 + 3 per marker set
         for (int s = 0; s < P.n_sets; ++s) {
@@ -269,313 +358,513 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
             const SetDev& S = P.sets[s];
             const int nblk = (int)(S.p_pad / B);
             const double inv_n = 1.0 / (double)P.n;
-            // hot-loop copies of the set descriptor (it lives in global memory; the volatile polls would force reloads)
             const int method = S.method;
             const int64_t p_real = S.p;
-            double* const beta_g = S.beta;
-            int32_t* const delta_g = S.delta;
-            double* const vb_g = S.varBeta;
-            const int32_t* const gramx_g = S.gramx;
-            const uint8_t* const blk_g = S.blk;
-            const double sdf = S.scale * S.df;
-            double acc_bb = 0.0, acc_n = 0.0;          // warp 0: per-lane partials of beta'beta and nLoci
-            tc = clock64();
+            double acc_bb = 0.0, acc_n = 0.0;          // chain warp: per-lane partials of beta'beta and nLoci
+            if constexpr (PROF) tc = clock64();
 
             if (P.kernel == 0) {
-                // ============================ blocked exact sweep, one block of look-ahead ============================
-                const uint8_t* gbase = S.geno + (int64_t)t * S.p_pad * R;
-                // stages is 3 or 4: no runtime integer division on the per-block path
-                auto stage_of = [&](int k) { const unsigned x = gk + (unsigned)k; return (int)(S_ == 4 ? (x & 3u) : (x % 3u)); };
-                auto parity_of = [&](int k) { const unsigned x = gk + (unsigned)k; return (uint32_t)((S_ == 4 ? (x >> 2) : (x / 3u)) & 1u); };
-                auto issue = [&](int k) {
-                    const int stg = stage_of(k);
-                    mbar_expect_tx(&mbar[stg], (uint32_t)(L.tile_bytes + L.blk_bytes));
-                    bulk_g2s(smem + L.off_tile + stg * L.tile_bytes, gbase + (int64_t)k * B * R, (uint32_t)L.tile_bytes, &mbar[stg]);
-                    bulk_g2s(smem + L.off_blk + stg * L.blk_bytes, blk_g + (int64_t)k * L.blk_bytes, (uint32_t)L.blk_bytes, &mbar[stg]);
-                };
-                if (tid == kProducerWarp * 32) {
-                    fence_proxy_async();     // consts were written through the generic proxy by other CTAs
-                    for (int k = 0; k < min(S_, nblk); ++k) issue(k);
-                }
-                if (tid == 0) { misc[40] = 0.0; misc[42] = 0.0; }      // nnz of the two nz lists
-                const int wtid = tid - 32;                  // worker thread id (0..255), negative in the chain warp
-                const int ww = warp - 1;                    // worker warp id
-                const int ngrp = R >> 3;
-                const int g0 = (ww * ngrp) / kWorkerWarps, g1 = ((ww + 1) * ngrp) / kWorkerWarps;
-
-                int zl[8];
+                // ======================================================================================================
+                //                                  blocked exact sweep, look-ahead D
+                // ======================================================================================================
+                if (!is_chain) {
+                    // ====================================================================== worker CTA
+                    const uint8_t* gbase = S.geno + (int64_t)t * nblk * L.tile_bytes;
+                    unsigned char* tiles = smem + L.w_tile;
+                    const int lwords = R * 2;                                 // words per limb version
+                    // residual rows of the updater threads: e_s -> registers, version 0 of the limbs
+                    double er[UG][4];
+                    if (warp < kUpdWarps) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) zl[i] = __ldg(&sy->zero16[i]);      // runtime zeros, see dec_byte_z
-                const int r_lo = 8 * g0, r_hi = min(8 * g1, nrow);               // the rows this worker warp owns (dot AND axpy)
-
-                // partial sums of block kk over this warp's rows: lane <-> markers lane, 32+lane
-                auto worker_dot = [&](int kk) {
-                    const int stg = stage_of(kk);
-                    mbar_wait(&mbar[stg], parity_of(kk));
-                    if (tid == 32) NGP_TICK(12);
-                    const uint8_t* tile = smem + L.off_tile + stg * L.tile_bytes;
-                    double* redk = red + (kk & 1) * (kWorkerWarps * kMaxB);     // double-buffered: one barrier per block
-                    double a[NB][4];
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) { a[b][0] = a[b][1] = a[b][2] = a[b][3] = 0.0; }
-                    for (int g = g0; g < g1; ++g) {
-                        const double2* ep = reinterpret_cast<const double2*>(e_s + 8 * g);
-                        const double2 e01 = ep[0], e23 = ep[1], e45 = ep[2], e67 = ep[3];
-#pragma unroll
-                        for (int b = 0; b < NB; ++b) {
-                            const uint2 w = *reinterpret_cast<const uint2*>(tile + (b * 32 + lane) * R + 8 * g);
-                            a[b][0] = fma(dec_byte_z(w.x, 0, zl[0]), e01.x, a[b][0]);
-                            a[b][1] = fma(dec_byte_z(w.x, 1, zl[1]), e01.y, a[b][1]);
-                            a[b][2] = fma(dec_byte_z(w.x, 2, zl[2]), e23.x, a[b][2]);
-                            a[b][3] = fma(dec_byte_z(w.x, 3, zl[3]), e23.y, a[b][3]);
-                            a[b][0] = fma(dec_byte_z(w.y, 0, zl[4]), e45.x, a[b][0]);
-                            a[b][1] = fma(dec_byte_z(w.y, 1, zl[5]), e45.y, a[b][1]);
-                            a[b][2] = fma(dec_byte_z(w.y, 2, zl[6]), e67.x, a[b][2]);
-                            a[b][3] = fma(dec_byte_z(w.y, 3, zl[7]), e67.y, a[b][3]);
-                        }
-                    }
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) redk[ww * B + b * 32 + lane] = (a[b][0] + a[b][1]) + (a[b][2] + a[b][3]);
-                    if (tid == 32) NGP_TICK(13);
-                    worker_bar();
-                    if (tid == 32) NGP_TICK(14);
-                    if (wtid < B) {
-                        double A = 0.0;
-#pragma unroll
-                        for (int c = 0; c < kWorkerWarps; ++c) A += redk[c * B + wtid];
-                        const double xs = A * fx_scale;
-                        if (!(fabs(xs) < 9007199254740992.0)) atomicOr(&sy->err, 1);     // 2^53 << 8 still fits
-                        long long* acc = sy->acc + (int64_t)((rk + (unsigned)kk) & (kSlots - 1)) * (kMaxB + 1) * kAccStride;
-                        red_add_u64(acc + wtid * kAccStride, (__double2ll_rn(xs) << kCntBits) + 1);
-                    }
-                };
-                // e -= sum_q dbeta_q (g_q - m_q) for the changed markers of block kk, from its smem tile;
-                // every worker warp updates exactly the rows its own dots read, so no CTA-wide barrier is needed
-                auto worker_axpy = [&](int kk) {
-                    const int li = kk & 1;
-                    const int nnz = (int)misc[40 + 2 * li];
-                    if (nnz == 0) return;
-                    const double K = misc[41 + 2 * li];
-                    const uint8_t* tile = smem + L.off_tile + stage_of(kk) * L.tile_bytes;
-                    for (int r = r_lo + lane; r < r_hi; r += 32) {
-                        double sacc = 0.0;
-                        for (int q = 0; q < nnz; ++q) {
-                            const uint32_t byte = tile[nz_idx[li * kMaxB + q] * R + r];
-                            sacc = fma(nz_db[li * kMaxB + q], dec_byte(byte, 0), sacc);
-                        }
-                        e_s[r] -= (sacc - K);
-                    }
-                    __syncwarp();
-                };
-
-                // staged outputs of block kk -> HBM (producer warp of CTA 0; plain coalesced stores)
-                auto write_out = [&](int kk) {
-                    const int li = kk & 1;
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        const int q = b * 32 + lane;
-                        const int64_t j = (int64_t)kk * B + q;
-                        if (j < p_real) {
-                            beta_g[j] = out_b[li * kMaxB + q];
-                            if (method != 0) delta_g[j] = out_i[li * kMaxB + q];
-                            if (method == 1) vb_g[j] = out_v[li * kMaxB + q];
-                        }
-                    }
-                };
-
-                // ---- prologue: partial sums of block 0
-                if (warp >= 1 && warp <= kWorkerWarps) worker_dot(0);
-                __syncthreads();
-                if (tid == 32) NGP_TICK(1);
-
-                for (int k = 0; k < nblk; ++k) {
-                    if (warp == kProducerWarp) {
-                        // ================= TMA producer: tile k-2 was applied in step k-1, refill its stage =================
-                        if (lane == 0 && k >= 2 && k - 2 + S_ < nblk) issue(k - 2 + S_);
-                        if (t == 0 && k >= 1) write_out(k - 1);
-                    } else if (warp != 0) {
-                        // ================= workers =================
-                        if (k >= 1) worker_axpy(k - 1);
-                        if (tid == 32) NGP_TICK(2);
-                        if (k + 1 < nblk) worker_dot(k + 1);
-                        if (tid == 32) NGP_TICK(1);
-                    } else {
-                        // ================= chain warp =================
-                        const int stg = stage_of(k);
-                        tc = clock64();
-                        mbar_wait(&mbar[stg], parity_of(k));
-                        NGP_TICK(0);
-                        const int32_t* gram = reinterpret_cast<const int32_t*>(smem + L.off_blk + stg * L.blk_bytes);
-                        const double* cst = reinterpret_cast<const double*>(smem + L.off_blk + stg * L.blk_bytes + B * B * 4);
-                        const int slot = (int)((rk + (unsigned)k) & (kSlots - 1));
-                        const long long* acc = sy->acc + (int64_t)slot * (kMaxB + 1) * kAccStride;
-                        const int lp = (k & 1) ^ 1;                  // nz list of block k-1
-                        const int npend = (k >= 1) ? (int)misc[40 + 2 * lp] : 0;
-                        double r[NB], bold[NB], dd[NB], cs[NB], bnew[NB];
-                        bool inc[NB];
-                        long long curv[NB];
-                        // cross-Gram rows of the markers changed in block k-1: issue the loads BEFORE polling so that
-                        // the two L2 round trips overlap
-                        constexpr int MAXP = 4;
-                        int gxv[MAXP][NB];
-                        const int32_t* gx = gramx_g + (int64_t)k * B * B;
-#pragma unroll
-                        for (int q0 = 0; q0 < MAXP; ++q0)
-#pragma unroll
-                            for (int b = 0; b < NB; ++b)
-                                gxv[q0][b] = (q0 < npend) ? __ldg(gx + nz_idx[lp * kMaxB + q0] * B + b * 32 + lane) : 0;
-                        {   // every lane polls its own accumulators until all T CTAs have added theirs
-                            bool done;
-                            do {
-                                done = true;
-#pragma unroll
-                                for (int b = 0; b < NB; ++b) {
-                                    const int q = b * 32 + lane;
-                                    curv[b] = ld_relaxed_s64(acc + q * kAccStride);
-                                    done = done && (((curv[b] - prev[slot * (kMaxB + 1) + q]) & 0xFF) == (long long)P.T);
-                                }
-                            } while (!__all_sync(0xffffffffu, done));
-                        }
-                        NGP_TICK(3);
-#pragma unroll
-                        for (int b = 0; b < NB; ++b) {
-                            const int q = b * 32 + lane;
-                            long long* pv = prev + slot * (kMaxB + 1) + q;
-                            const double A = (double)((curv[b] - *pv - (long long)P.T) >> kCntBits) * fx_inv;
-                            *pv = curv[b];
-                            cs[b] = cst[F_CS * B + q];
-                            r[b] = 4.0 * (A - Stot) - cst[F_MEAN * B + q] * Stot;     // x_j'e for the e of one block ago
-                            bold[b] = cst[F_BOLD * B + q];
-                            dd[b] = cst[F_D * B + q];
-                            bnew[b] = 0.0; inc[b] = false;
-                        }
-                        // the partial sums were formed before block k-1 was applied to e: restore exactly with the cross Gram
-#pragma unroll
-                        for (int q0 = 0; q0 < MAXP; ++q0) {
-                            if (q0 < npend) {
-                                const double dbf = 0.25 * nz_db[lp * kMaxB + q0];
-                                const double csf = nz_cs[lp * kMaxB + q0];
-#pragma unroll
-                                for (int b = 0; b < NB; ++b) r[b] = fma(-((double)gxv[q0][b] - csf * cs[b] * inv_n), dbf, r[b]);
+                        for (int k = 0; k < UG; ++k) {
+                            const int rg = tid + k * kUpdThreads;
+                            if (4 * rg < R) {
+                                const double2 a01 = *reinterpret_cast<const double2*>(e_s + 4 * rg), a23 = *reinterpret_cast<const double2*>(e_s + 4 * rg + 2);
+                                er[k][0] = a01.x; er[k][1] = a01.y; er[k][2] = a23.x; er[k][3] = a23.y;
+                                quantise4(er[k], limb, rg, fx_scale);
                             }
                         }
-                        for (int q0 = MAXP; q0 < npend; ++q0) {
-                            const int f = nz_idx[lp * kMaxB + q0];
-                            const double dbf = 0.25 * nz_db[lp * kMaxB + q0];
-                            const double csf = nz_cs[lp * kMaxB + q0];
-#pragma unroll
-                            for (int b = 0; b < NB; ++b) {
-                                const double gc = (double)__ldg(gx + f * B + b * 32 + lane) - csf * cs[b] * inv_n;
-                                r[b] = fma(-gc, dbf, r[b]);
-                            }
-                        }
-                        int nnz = 0;
-                        double K = 0.0;
-                        const int li = k & 1;
-#pragma unroll
-                        for (int b = 0; b < NB; ++b) {
-                            const int q = b * 32 + lane;
-                            const double cA = cst[F_A * B + q], cB = cst[F_B * B + q], cT = cst[F_T * B + q];
-                            const double cC = cst[F_C * B + q], cQ = cst[F_QSZ * B + q];
-                            const double mq = cst[F_MEAN * B + q];
-                            int start = 0;
-                            while (start < 32) {
-                                pf[7]++;
-                                const double rr = fma(dd[b], bold[b], r[b]);        // add-back fused: x'(e + x b) = x'e + d b
-                                const double dl = fma(cB, rr * rr, cA);
-                                const bool in = dl < cT;                            // NaN -> excluded, like rand() < NaN
-                                const double bn = in ? fma(rr, cC, cQ) : 0.0;
-                                const double db = bn - bold[b];
-                                const bool act = lane >= start;
-                                const unsigned m = __ballot_sync(0xffffffffu, act && (db != 0.0));
-                                const int f = m ? (__ffs(m) - 1) : 32;
-                                if (act && lane <= f) { bnew[b] = bn; inc[b] = in; }
-                                if (f == 32) break;
-                                const double dbf = __shfl_sync(0xffffffffu, db, f);
-                                const double csf = __shfl_sync(0xffffffffu, cs[b], f);
-                                const double mf = __shfl_sync(0xffffffffu, mq, f);
-                                const int32_t* grow = gram + (b * 32 + f) * B;
-#pragma unroll
-                                for (int bb = 0; bb < NB; ++bb) {
-                                    if (bb >= b) {
-                                        const double gc = (double)grow[bb * 32 + lane] - csf * cs[bb] * inv_n;
-                                        if (bb > b || lane > f) r[bb] = fma(-gc, dbf, r[bb]);
-                                    }
-                                }
-                                if (lane == 0) {
-                                    nz_idx[li * kMaxB + nnz] = b * 32 + f;
-                                    nz_db[li * kMaxB + nnz] = 4.0 * dbf;
-                                    nz_cs[li * kMaxB + nnz] = csf;
-                                }
-                                K = fma(4.0 * dbf, 1.0 + 0.25 * mf, K);
-                                ++nnz;
-                                start = f + 1;
-                            }
-                        }
-                        if (lane == 0) { misc[40 + 2 * li] = (double)nnz; misc[41 + 2 * li] = K; }
-                        // outputs of the block: staged in smem, written to HBM by the producer warp of CTA 0 in the next step
-#pragma unroll
-                        for (int b = 0; b < NB; ++b) {
-                            const int q = b * 32 + lane;
-                            acc_bb = fma(bnew[b], bnew[b], acc_bb);
-                            if (method != 0) acc_n += inc[b] ? 1.0 : 0.0;
-                            if (t == 0) {
-                                out_b[li * kMaxB + q] = bnew[b];
-                                out_i[li * kMaxB + q] = inc[b] ? 1 : 0;
-                                if (method == 1)                                    // functions.jl:182,186
-                                    out_v[li * kMaxB + q] = inc[b] ? (sdf + bnew[b] * bnew[b]) / cst[F_CHI * B + q] : 0.0;
-                            }
-                        }
-                        pf[6] += nnz;
-                        NGP_TICK(4);
                     }
                     __syncthreads();
-                    if (tid == 0) NGP_TICK(5);
-                    if (tid == 32) NGP_TICK(10);
-                    // tile k-1 is no longer needed (its axpy ran in this step): refill its stage
+                    if (warp < kUpdWarps) {
+                        // ------------------------------------------------------------------ updater warps
+                        int cur = 0;                       // limb version holding the current state of e
+                        int sup[kLimbVers];                // block at which a version was superseded (its last reader is the dot of block sup + D)
+#pragma unroll
+                        for (int v = 0; v < kLimbVers; ++v) sup[v] = -1;
+                        for (int ja = 0; ja < nblk; ++ja) {
+                            const unsigned gidx = gblk + (unsigned)ja;
+                            if (!(dbg & 1)) mbar_wait(&nz_full[r_nzw.s], r_nzw.ph);
+                            if (tid == 0) NGP_TICK(10);
+                            const NzList& nl = wnz[r_nzw.s];
+                            const int nnz = (dbg & 1) ? 0 : nl.nnz;
+                            if (nnz > 0) {
+                                // e -= sum_q dbeta_q (g_q - mean_q): one tile word = the 4 codes of this thread's rows
+                                const int nv = (cur + 1 == kLimbVers) ? 0 : cur + 1;
+                                int sv = -1;
+#pragma unroll
+                                for (int v = 0; v < kLimbVers; ++v) if (v == nv) sv = sup[v];
+                                if (sv >= 0) {
+                                    const int jl = min(sv + D, nblk - 1);          // last dot that reads version nv
+                                    if (jl > ja) {                                  // dots <= ja are complete (their list exists)
+                                        const unsigned gl = gblk + (unsigned)jl;
+                                        mbar_wait(&dot_done[gl & (kNzRing - 1)], (gl / kNzRing) & 1u);
+                                    }
+                                }
+                                if (tid == 0) NGP_TICK(5);
+                                const uint32_t* tw = reinterpret_cast<const uint32_t*>(tiles + r_ta.s * L.tile_bytes);
+#pragma unroll
+                                for (int k = 0; k < UG; ++k) {
+                                    const int rg = tid + k * kUpdThreads;
+                                    if (4 * rg < R) {
+                                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                                        for (int i = 0; i < nnz; ++i) {
+                                            const uint32_t w = tw[word_off(B, nl.idx[i], rg)];
+                                            const double db = nl.db[i], kk = nl.aux[i];
+                                            s0 += fma(db, (double)(w & 0xff), -kk);
+                                            s1 += fma(db, (double)((w >> 8) & 0xff), -kk);
+                                            s2 += fma(db, (double)((w >> 16) & 0xff), -kk);
+                                            s3 += fma(db, (double)(w >> 24), -kk);
+                                        }
+                                        const int r0 = 4 * rg;
+                                        if (r0 < nrow) er[k][0] -= s0;
+                                        if (r0 + 1 < nrow) er[k][1] -= s1;
+                                        if (r0 + 2 < nrow) er[k][2] -= s2;
+                                        if (r0 + 3 < nrow) er[k][3] -= s3;
+                                        quantise4(er[k], limb + nv * lwords, rg, fx_scale);
+                                    }
+                                }
+#pragma unroll
+                                for (int v = 0; v < kLimbVers; ++v) if (v == cur) sup[v] = ja;
+                                cur = nv;
+                            }
+                            if (tid == 0) vbuf[gidx & (kNzRing - 1)] = cur;
+                            __syncwarp();
+                            if (lane == 0) {
+                                mbar_arrive(&ver_full[gidx & (kNzRing - 1)]);
+                                mbar_arrive(&tile_free[r_ta.s]);
+                                if (!(dbg & 1)) mbar_arrive(&nz_free[r_nzw.s]);
+                            }
+                            r_ta.adv(NT); r_nzw.adv(kNzSmem);
+                            if (tid == 0) NGP_TICK(2);
+                        }
+                        // registers -> e_s (phases 0 and 3 and the next sweep read the master copy from smem)
+#pragma unroll
+                        for (int k = 0; k < UG; ++k) {
+                            const int rg = tid + k * kUpdThreads;
+                            if (4 * rg < R) {
+                                *reinterpret_cast<double2*>(e_s + 4 * rg) = make_double2(er[k][0], er[k][1]);
+                                *reinterpret_cast<double2*>(e_s + 4 * rg + 2) = make_double2(er[k][2], er[k][3]);
+                            }
+                        }
+                    } else if (warp < kFirstDotWarp + kDotWarps) {
+                        // ------------------------------------------------------------------ dot warps: whole blocks, 8 in flight
+                        const int dw = warp - kFirstDotWarp;
+                        const int g = lane >> 2, tt = lane & 3;
+                        const long long plim = (1LL << 55) / Tw;
+                        const int j0 = (int)((unsigned)(dw - (int)(gblk & (kDotWarps - 1))) & (kDotWarps - 1));    // first j with (gblk+j) % kDotWarps == dw
+                        int tslot = (int)((gblk + (unsigned)j0) % (unsigned)NT);
+                        uint32_t tph = ((gblk + (unsigned)j0) / (unsigned)NT) & 1u;
+                        constexpr int CH = (MG >= 4) ? 1 : 4 / MG;          // independent accumulator chains per marker group
+                        for (int j = j0; j < nblk; j += kDotWarps) {
+                            const unsigned gidx = gblk + (unsigned)j;
+                            const int ja = j - D - 1;
+                            int ver = 0;
+                            if (ja >= 0) {
+                                const unsigned ga = gblk + (unsigned)ja;
+                                mbar_wait(&ver_full[ga & (kNzRing - 1)], (ga / kNzRing) & 1u);
+                                ver = vbuf[ga & (kNzRing - 1)];
+                            }
+                            if (tid == kFirstDotWarp * 32) NGP_TICK(14);
+                            mbar_wait(&tile_full[tslot], tph);
+                            if (tid == kFirstDotWarp * 32) NGP_TICK(20);
+                            if (!(dbg & 8)) {
+                                const unsigned char* tile = tiles + tslot * L.tile_bytes;
+                                const uint32_t* lv = limb + ver * lwords;
+                                int acc[MG][CH][4];
+#pragma unroll
+                                for (int mg = 0; mg < MG; ++mg)
+#pragma unroll
+                                    for (int ch = 0; ch < CH; ++ch) { acc[mg][ch][0] = acc[mg][ch][1] = acc[mg][ch][2] = acc[mg][ch][3] = 0; }
+                                for (int c0 = 0; c0 < nchunk; c0 += CH) {
+#pragma unroll
+                                    for (int ch = 0; ch < CH; ++ch) {
+                                        const int c = c0 + ch;
+                                        if (c < nchunk) {
+                                            const uint32_t b0 = lv[c * 64 + lane], b1 = lv[c * 64 + 32 + (lane ^ 4)];
+#pragma unroll
+                                            for (int mg = 0; mg < MG; ++mg) {
+                                                const uint4 a = *reinterpret_cast<const uint4*>(tile + ((size_t)(c * MG + mg) * 32 + lane) * 16);
+                                                imma16832(acc[mg][ch], a, b0, b1);
+                                            }
+                                        }
+                                    }
+                                }
+                                if (tid == kFirstDotWarp * 32) NGP_TICK(1);
+                                long long* accg = sy->acc + (gidx & (kSlots - 1)) * kMaxB;
+#pragma unroll
+                                for (int mg = 0; mg < MG; ++mg) {
+                                    int c4[4];
+#pragma unroll
+                                    for (int x = 0; x < 4; ++x) {
+                                        c4[x] = acc[mg][0][x];
+#pragma unroll
+                                        for (int ch = 1; ch < CH; ++ch) c4[x] += acc[mg][ch][x];
+                                    }
+                                    // lane holds limbs 2tt, 2tt+1 of markers g and g+8: sum_n c_n 256^n (mod 2^64)
+                                    unsigned long long v0 = ((unsigned long long)(long long)c4[0] << (16 * tt)) + ((unsigned long long)(long long)c4[1] << (16 * tt + 8));
+                                    unsigned long long v1 = ((unsigned long long)(long long)c4[2] << (16 * tt)) + ((unsigned long long)(long long)c4[3] << (16 * tt + 8));
+                                    v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+                                    v0 += __shfl_xor_sync(0xffffffffu, v0, 2); v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+                                    // lanes tt = 0 / tt = 1 add the sums of markers g / g+8 of this CTA's panel
+                                    if (tt < 2) {
+                                        const long long sa = (long long)(tt ? v1 : v0);
+                                        if (sa >= plim || sa <= -plim) atomicOr(&sy->err, 1);
+                                        red_add_u64(accg + mg * 16 + g + 8 * tt, (long long)((unsigned long long)sa << kCntBits) + 1);
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&dot_done[gidx & (kNzRing - 1)]);
+                            tslot += kDotWarps;
+                            while (tslot >= NT) { tslot -= NT; tph ^= 1u; }
+                            if (tid == kFirstDotWarp * 32) NGP_TICK(15);
+                        }
+                    } else if (warp == kTmaWarp) {
+                        // ------------------------------------------------------------------ TMA producer of the tile ring
+                        if (lane == 0) {
+                            for (int i = 0; i < nblk; ++i) {
+                                if (tiles_issued >= (unsigned)NT) mbar_wait(&tile_free[r_tp.s], r_tp.ph ^ 1u);
+                                mbar_expect_tx(&tile_full[r_tp.s], (uint32_t)L.tile_bytes);
+                                bulk_g2s(tiles + r_tp.s * L.tile_bytes, gbase + (int64_t)i * L.tile_bytes, (uint32_t)L.tile_bytes, &tile_full[r_tp.s]);
+                                r_tp.adv(NT); ++tiles_issued;
+                            }
+                        }
+                    } else {
+                        // ------------------------------------------------------------------ poll warp: changed-effect lists
+                        for (int ja = 0; ja < ((dbg & 1) ? 0 : nblk); ++ja) {
+                            const unsigned gidx = gblk + (unsigned)ja;
+                            const uint32_t seq = gidx + 1u;
+                            const unsigned long long* sw = sy->ll + (size_t)(gidx & (kNzRing - 1)) * kLLSlotWords;
+                            if (nz_recv >= (unsigned)kNzSmem) mbar_wait(&nz_free[r_nzp.s], r_nzp.ph ^ 1u);
+                            NzList& nl = wnz[r_nzp.s];
+                            int need = 1 << 30, nnz = 0;
+                            for (int base = 0; base < need; base += 32) {
+                                unsigned long long w;
+                                for (;;) {
+                                    w = ld_relaxed_u64(sw + base + lane);
+                                    const bool ok = (uint32_t)(w >> 32) == seq;
+                                    if (base == 0) {
+                                        const unsigned long long hdr = __shfl_sync(0xffffffffu, w, 0);
+                                        if ((uint32_t)(hdr >> 32) != seq) continue;
+                                        nnz = (int)(uint32_t)hdr;
+                                        need = 1 + kLLEntryWords * nnz;
+                                    }
+                                    if (__all_sync(0xffffffffu, ok || (base + lane >= need))) break;
+                                }
+                                const int wi = base + lane;
+                                if (wi >= 1 && wi < need) {
+                                    const int en = (wi - 1) / kLLEntryWords, f = (wi - 1) - en * kLLEntryWords;
+                                    const uint32_t pay = (uint32_t)w;
+                                    if (f == 0) nl.idx[en] = (int)pay;
+                                    else if (f <= 2) reinterpret_cast<uint32_t*>(&nl.db[en])[f - 1] = pay;
+                                    else reinterpret_cast<uint32_t*>(&nl.aux[en])[f - 3] = pay;
+                                }
+                            }
+                            if (lane == 0) nl.nnz = nnz;
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&nz_full[r_nzp.s]);
+                            r_nzp.adv(kNzSmem); ++nz_recv;
+                        }
+                    }
+                } else {
+                    // ====================================================================== chain CTA
+                    unsigned char* recs = smem + L.c_rec;
+                    const int32_t* const gx_g = S.gx;
+                    const size_t gx_blk = (size_t)(D + 1) * B * B;
+                    if (warp == 0) {
+                        // ------------------------------------------------------------------ chain warp
+                        double* const beta_g = S.beta;
+                        int32_t* const delta_g = S.delta;
+                        double* const vb_g = S.varBeta;
+                        const double sdf = S.scale * S.df;
+                        for (int m = 0; m < nblk; ++m) {
+                            const unsigned gidx = gblk + (unsigned)m;
+                            if constexpr (PROF) tc = clock64();
+                            const int rs = (int)(gidx & (kPrepWarps - 1));
+                            // r_base of block m is published after its record has landed (the prep warp waited for it)
+                            mbar_wait(&rb_full[rs], (gidx / kPrepWarps) & 1u);
+                            NGP_TICK(3);
+                            const unsigned rcs = gidx & (unsigned)(NR - 1);      // record ring stage
+                            const unsigned char* rec = recs + rcs * L.rec_bytes;
+                            const int32_t* gram = reinterpret_cast<const int32_t*>(rec);
+                            const double* cst = reinterpret_cast<const double*>(rec + (1 + DN) * gram_bytes(B));
+                            double r[NB], bold[NB], dd[NB], cs[NB], bnew[NB];
+                            bool inc[NB], live[NB];
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) {
+                                const int q = b * 32 + lane;
+                                live[b] = q < B;
+                                const int qq = live[b] ? q : 0;
+                                r[b] = rbase[rs * B + qq];
+                                cs[b] = cst[F_CS * B + qq];
+                                bold[b] = live[b] ? cst[F_BOLD * B + qq] : 0.0;
+                                dd[b] = cst[F_D * B + qq];
+                                bnew[b] = 0.0; inc[b] = false;
+                            }
+                            NGP_TICK(4);
+                            // cross-Gram correction of distance 1 (block m-1), rows from the block record
+                            if (m >= 1 && DN >= 1 && !(dbg & 4)) {
+                                const NzList& pl = cnz[(gidx - 1u) & (kNzRing - 1)];
+                                const int np = pl.nnz;
+                                const int32_t* gd = gram + B * B;
+                                for (int i = 0; i < np; ++i) {
+                                    const int a = pl.idx[i];
+                                    const double dbf = pl.db[i], csf = pl.aux[i];
+#pragma unroll
+                                    for (int b = 0; b < NB; ++b)
+                                        if (live[b]) r[b] = fma(-((double)gd[a * B + b * 32 + lane] - csf * cs[b] * inv_n), dbf, r[b]);
+                                }
+                            }
+                            NGP_TICK(16);
+                            NzList& ml = cnz[gidx & (kNzRing - 1)];
+                            unsigned long long* llw = sy->ll + (size_t)(gidx & (kNzRing - 1)) * kLLSlotWords;
+                            const unsigned long long seqhi = (unsigned long long)(gidx + 1u) << 32;
+                            int nnz = 0;
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) {
+                                const int q = b * 32 + lane, qq = live[b] ? q : 0;
+                                const double cA = cst[F_A * B + qq], cB = cst[F_B * B + qq];
+                                const double cT = live[b] ? cst[F_T * B + qq] : -INFINITY;
+                                const double cC = cst[F_C * B + qq], cQ = cst[F_QSZ * B + qq];
+                                const double mq = cst[F_MEAN * B + qq];
+                                int start = (dbg & 4) ? 32 : 0;
+                                while (start < 32) {
+                                    if constexpr (PROF) pf[7]++;
+                                    const double rr = fma(dd[b], bold[b], r[b]);        // add-back fused: x'(e + x b) = x'e + d b
+                                    const double dl = fma(cB, rr * rr, cA);
+                                    const bool in = dl < cT;                            // NaN -> excluded, like rand() < NaN
+                                    const double bn = in ? fma(rr, cC, cQ) : 0.0;
+                                    const double db = bn - bold[b];
+                                    const bool act = lane >= start;
+                                    const unsigned mk = __ballot_sync(0xffffffffu, act && (db != 0.0));
+                                    const int f = mk ? (__ffs(mk) - 1) : 32;
+                                    if (act && lane <= f) { bnew[b] = bn; inc[b] = in; }
+                                    if (f == 32) break;
+                                    const double dbf = __shfl_sync(0xffffffffu, db, f);
+                                    const double csf = __shfl_sync(0xffffffffu, cs[b], f);
+                                    const double mf = __shfl_sync(0xffffffffu, mq, f);
+                                    const int32_t* grow = gram + (b * 32 + f) * B;
+#pragma unroll
+                                    for (int bb = 0; bb < NB; ++bb) {
+                                        if (bb >= b && live[bb]) {
+                                            const double gc = (double)grow[bb * 32 + lane] - csf * cs[bb] * inv_n;
+                                            if (bb > b || lane > f) r[bb] = fma(-gc, dbf, r[bb]);
+                                        }
+                                    }
+                                    if (lane == 0) {
+                                        ml.idx[nnz] = b * 32 + f; ml.db[nnz] = dbf; ml.aux[nnz] = csf;
+                                        // publish to the worker CTAs: {payload32, seq32} words, any order, no fence
+                                        const unsigned long long dbb = (unsigned long long)__double_as_longlong(dbf);
+                                        const unsigned long long kkb = (unsigned long long)__double_as_longlong(dbf * mf);
+                                        unsigned long long* ew = llw + 1 + kLLEntryWords * nnz;
+                                        st_relaxed_u64(ew + 0, seqhi | (unsigned long long)(uint32_t)(b * 32 + f));
+                                        st_relaxed_u64(ew + 1, seqhi | (dbb & 0xffffffffull));
+                                        st_relaxed_u64(ew + 2, seqhi | (dbb >> 32));
+                                        st_relaxed_u64(ew + 3, seqhi | (kkb & 0xffffffffull));
+                                        st_relaxed_u64(ew + 4, seqhi | (kkb >> 32));
+                                    }
+                                    ++nnz;
+                                    start = f + 1;
+                                }
+                            }
+                            NGP_TICK(17);
+                            if (lane == 0) {
+                                st_relaxed_u64(llw, seqhi | (unsigned long long)(uint32_t)nnz);
+                                ml.nnz = nnz;
+                            }
+                            __syncwarp();
+                            if (lane == 0) {
+                                mbar_arrive(&nzc_full[gidx & (kNzRing - 1)]);
+                                mbar_arrive(&rb_free[rs]);
+                            }
+                            NGP_TICK(18);
+                            // outputs of the block (plain coalesced stores, fire and forget)
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) {
+                                const int q = b * 32 + lane;
+                                const int64_t j = (int64_t)m * B + q;
+                                if (live[b]) {
+                                    acc_bb = fma(bnew[b], bnew[b], acc_bb);
+                                    if (method != 0) acc_n += inc[b] ? 1.0 : 0.0;
+                                    if (j < p_real) {
+                                        beta_g[j] = bnew[b];
+                                        if (method != 0) delta_g[j] = inc[b] ? 1 : 0;
+                                        if (method == 1)                                    // functions.jl:182,186
+                                            vb_g[j] = inc[b] ? (sdf + bnew[b] * bnew[b]) / cst[F_CHI * B + q] : 0.0;
+                                    }
+                                }
+                            }
+                            if constexpr (PROF) pf[6] += nnz;
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&rec_free[rcs]);     // the record (Gram rows, constants) is no longer needed
+                            NGP_TICK(19);
+                        }
+                    } else if (warp == 1) {
+                        // ------------------------------------------------------------------ TMA producer of the block records
+                        if (lane == 0) {
+                            fence_proxy_async();     // consts were written through the generic proxy by other CTAs
+                            const uint32_t gbytes = (uint32_t)((1 + DN) * gram_bytes(B)), cbytes = (uint32_t)consts_bytes(B);
+                            for (int m = 0; m < nblk; ++m) {
+                                if (recs_issued >= (unsigned)NR) mbar_wait(&rec_free[r_rec.s], r_rec.ph ^ 1u);
+                                unsigned char* dst = recs + r_rec.s * L.rec_bytes;
+                                mbar_expect_tx(&rec_full[r_rec.s], gbytes + cbytes);
+                                bulk_g2s(dst, gx_g + (size_t)m * gx_blk, gbytes, &rec_full[r_rec.s]);
+                                bulk_g2s(dst + gbytes, S.consts + (size_t)m * kNF * B, cbytes, &rec_full[r_rec.s]);
+                                r_rec.adv(NR); ++recs_issued;
+                            }
+                        }
+                    } else if (warp < kFirstPrepWarp + kPrepWarps) {
+                        // ------------------------------------------------------------------ prep warps
+                        const int pw = warp - kFirstPrepWarp;
+                        int m0 = (int)((unsigned)(pw - (int)(gblk & (kPrepWarps - 1))) & (kPrepWarps - 1));   // first m with (gblk+m) % kPrepWarps == pw
+                        for (int m = m0; m < nblk; m += kPrepWarps) {
+                            const unsigned gidx = gblk + (unsigned)m;
+                            if (warp == kFirstPrepWarp) if constexpr (PROF) tc = clock64();
+                            double far[NB], cs[NB], mean[NB];
+                            bool live[NB];
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) {
+                                const int q = b * 32 + lane;
+                                live[b] = q < B;
+                                const int64_t j = (int64_t)m * B + (live[b] ? q : 0);
+                                cs[b] = (double)__ldg(&S.colsum[j]);
+                                mean[b] = __ldg(&S.mean[j]);
+                                far[b] = 0.0;
+                            }
+                            // poll the accumulators of block m until all Tw worker CTAs have added their partial sums
+                            const int slot = (int)(gidx & (kSlots - 1));
+                            const long long* acc = sy->acc + slot * kMaxB;
+                            long long cur[NB];
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) cur[b] = 0;
+                            if (!(dbg & 2)) {
+                                bool done;
+                                do {
+                                    done = true;
+#pragma unroll
+                                    for (int b = 0; b < NB; ++b) {
+                                        const int q = b * 32 + lane;
+                                        if (live[b]) {
+                                            cur[b] = ld_relaxed_s64(acc + q);
+                                            done = done && (((cur[b] - prev[slot * B + q]) & 0xFF) == (long long)Tw);
+                                        }
+                                    }
+                                } while (!__all_sync(0xffffffffu, done));
+                            }
+                            if (warp == kFirstPrepWarp) NGP_TICK(13);
+                            // cross-Gram corrections of distance >= 2, oldest block first:
+                            //   blocks m-D .. m-DN-1: rows fetched on demand from HBM/L2;  blocks m-DN .. m-2: rows from the block record
+                            bool have_rec = false;
+                            const unsigned rcs = gidx & (unsigned)(NR - 1);
+                            const uint32_t rcp = (gidx / (unsigned)NR) & 1u;
+                            const int32_t* gram = reinterpret_cast<const int32_t*>(recs + rcs * L.rec_bytes);
+                            for (int sblk = max(0, m - D); sblk <= m - 2; ++sblk) {
+                                const unsigned gs_ = gblk + (unsigned)sblk;
+                                mbar_wait(&nzc_full[gs_ & (kNzRing - 1)], (gs_ / kNzRing) & 1u);
+                                const NzList& pl = cnz[gs_ & (kNzRing - 1)];
+                                const int np = pl.nnz;
+                                if (np == 0) continue;
+                                const int d = m - sblk;
+                                if (d > DN) {
+                                    const int32_t* gd = gx_g + (size_t)m * gx_blk + (size_t)d * B * B;
+                                    for (int i0 = 0; i0 < np; i0 += 4) {
+                                        int gv[4][NB];
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                            for (int b = 0; b < NB; ++b)
+                                                gv[u][b] = (i0 + u < np && live[b]) ? __ldg(gd + pl.idx[i0 + u] * B + b * 32 + lane) : 0;
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u)
+                                            if (i0 + u < np) {
+                                                const double dbf = pl.db[i0 + u], csf = pl.aux[i0 + u];
+#pragma unroll
+                                                for (int b = 0; b < NB; ++b) far[b] = fma(-((double)gv[u][b] - csf * cs[b] * inv_n), dbf, far[b]);
+                                            }
+                                    }
+                                } else {
+                                    if (!have_rec) { mbar_wait(&rec_full[rcs], rcp); have_rec = true; }
+                                    const int32_t* gd = gram + d * B * B;
+                                    for (int i = 0; i < np; ++i) {
+                                        const int a = pl.idx[i];
+                                        const double dbf = pl.db[i], csf = pl.aux[i];
+#pragma unroll
+                                        for (int b = 0; b < NB; ++b)
+                                            if (live[b]) far[b] = fma(-((double)gd[a * B + b * 32 + lane] - csf * cs[b] * inv_n), dbf, far[b]);
+                                    }
+                                }
+                            }
+                            if (!have_rec) mbar_wait(&rec_full[rcs], rcp);     // the chain warp relies on it
+                            if (warp == kFirstPrepWarp) NGP_TICK(12);
+                            if (rb_uses > 0) mbar_wait(&rb_free[pw], (rb_uses - 1) & 1u);
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) {
+                                const int q = b * 32 + lane;
+                                if (live[b]) {
+                                    long long* pv = prev + slot * B + q;
+                                    const double A = (double)((cur[b] - *pv - (long long)Tw) >> kCntBits) * fx_inv;
+                                    if (!(dbg & 2)) *pv = cur[b];
+                                    rbase[pw * B + q] = (A - mean[b] * Stot) + far[b];       // x_q'e as the dots saw it + corrections of distance >= 2
+                                }
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&rb_full[pw]);
+                            ++rb_uses;
+                        }
+                    }
                 }
-                // ---- epilogue: apply the last block
-                if (warp >= 1 && warp <= kWorkerWarps) worker_axpy(nblk - 1);
-                if (warp == kProducerWarp && t == 0) write_out(nblk - 1);
                 __syncthreads();
-                gk = (gk + (unsigned)nblk) % (2u * (unsigned)S_);
-                rk += (unsigned)nblk;
+                gblk += (unsigned)nblk;
             } else {
                 // ============================ literal per-marker sweep ============================
-                const int ngrp = R >> 3;
+                // every CTA (the chain CTA owns no rows) evaluates the scalar update redundantly; CTA Tw writes the outputs
+                long long* lprev = reinterpret_cast<long long*>(misc + 48);
+                const int nwords = R >> 2;
                 for (int64_t j = 0; j < S.p; ++j, ++rk) {
-                    const uint8_t* col = S.geno + ((int64_t)t * S.p_pad + j) * R;
+                    const int k = (int)(j / B), q = (int)(j % B);
+                    const uint8_t* tile = S.geno + ((int64_t)t * nblk + k) * L.tile_bytes;
                     const int slot = (int)(rk & (kSlots - 1));
-                    long long* acc = sy->acc + (int64_t)slot * (kMaxB + 1) * kAccStride;
-                    uint2 w0 = make_uint2(0xF0F0F0F0u, 0xF0F0F0F0u);
+                    long long* acc = sy->acc + slot * kMaxB;
+                    uint32_t w0 = 0;
                     double a = 0.0, dummy = 0.0;
-                    for (int g = tid; g < ngrp; g += kThreads) {
-                        const uint2 w = __ldg(reinterpret_cast<const uint2*>(col + 8 * g));
-                        if (g == tid) w0 = w;
-                        const double* ep = e_s + 8 * g;
-                        a = fma(dec_byte(w.x, 0), ep[0], a); a = fma(dec_byte(w.x, 1), ep[1], a);
-                        a = fma(dec_byte(w.x, 2), ep[2], a); a = fma(dec_byte(w.x, 3), ep[3], a);
-                        a = fma(dec_byte(w.y, 0), ep[4], a); a = fma(dec_byte(w.y, 1), ep[5], a);
-                        a = fma(dec_byte(w.y, 2), ep[6], a); a = fma(dec_byte(w.y, 3), ep[7], a);
+                    if (!is_chain) {
+                        for (int wr = tid; wr < nwords; wr += kThreads) {
+                            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(tile) + word_off(B, q, wr));
+                            if (wr == tid) w0 = w;
+                            const double* ep = e_s + 4 * wr;
+                            a = fma((double)(w & 0xff), ep[0], a); a = fma((double)((w >> 8) & 0xff), ep[1], a);
+                            a = fma((double)((w >> 16) & 0xff), ep[2], a); a = fma((double)(w >> 24), ep[3], a);
+                        }
                     }
                     block_sum2(a, dummy, misc);
-                    if (tid == 0) {
+                    if (tid == 0 && !is_chain) {
                         const double xs = a * fx_scale;
                         if (!(fabs(xs) < 9007199254740992.0)) atomicOr(&sy->err, 1);
-                        red_add_u64(acc, (__double2ll_rn(xs) << kCntBits) + 1);
+                        red_add_u64(acc, (long long)((unsigned long long)__double2ll_rn(xs) << kCntBits) + 1);
                     }
                     if (warp == 0) {
-                        const double* c = reinterpret_cast<const double*>(S.blk + (j / B) * (int64_t)blk_bytes(B) + B * B * 4) + (j % B);
+                        const double* c = S.consts + (int64_t)k * (kNF * B) + q;
                         const double cA = __ldcg(c + F_A * B), cB = __ldcg(c + F_B * B), cT = __ldcg(c + F_T * B);
                         const double cC = __ldcg(c + F_C * B), cQ = __ldcg(c + F_QSZ * B), d = __ldcg(c + F_D * B);
                         const double bold = __ldcg(c + F_BOLD * B), mean = __ldcg(c + F_MEAN * B), chi = __ldcg(c + F_CHI * B);
-                        long long* pv = prev + slot * (kMaxB + 1);
+                        long long* pv = lprev + slot;
                         long long cur;
-                        do { cur = ld_relaxed_s64(acc); } while (((cur - *pv) & 0xFF) != (long long)P.T);
-                        const double A = (double)((cur - *pv - (long long)P.T) >> kCntBits) * fx_inv;
+                        do { cur = ld_relaxed_s64(acc); } while (((cur - *pv) & 0xFF) != (long long)Tw);
+                        const double A = (double)((cur - *pv - (long long)Tw) >> kCntBits) * fx_inv;
                         __syncwarp();
                         if (lane == 0) *pv = cur;
-                        const double r = 4.0 * (A - Stot) - mean * Stot;
+                        const double r = A - mean * Stot;
                         const double rr = fma(d, bold, r);
                         const double dl = fma(cB, rr * rr, cA);
                         const bool in = dl < cT;
@@ -584,7 +873,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             misc[40] = bn - bold; misc[41] = mean;
                             acc_bb = fma(bn, bn, acc_bb);
                             if (S.method != 0) acc_n += in ? 1.0 : 0.0;
-                            if (t == 0) {
+                            if (is_chain) {
                                 S.beta[j] = bn;
                                 if (S.method != 0) S.delta[j] = in ? 1 : 0;
                                 if (S.method == 1) S.varBeta[j] = in ? (S.scale * S.df + bn * bn) / chi : 0.0;
@@ -593,34 +882,30 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     }
                     __syncthreads();
                     const double db = misc[40];
-                    if (db != 0.0) {
-                        const double db4 = 4.0 * db, K = db4 * (1.0 + 0.25 * misc[41]);
-                        for (int g = tid; g < ngrp; g += kThreads) {
-                            const uint2 w = (g == tid) ? w0 : __ldg(reinterpret_cast<const uint2*>(col + 8 * g));   // first pass from registers
-                            double* ep = e_s + 8 * g;
-                            const int lim = nrow - 8 * g;
-                            if (lim > 0) ep[0] -= fma(db4, dec_byte(w.x, 0), -K);
-                            if (lim > 1) ep[1] -= fma(db4, dec_byte(w.x, 1), -K);
-                            if (lim > 2) ep[2] -= fma(db4, dec_byte(w.x, 2), -K);
-                            if (lim > 3) ep[3] -= fma(db4, dec_byte(w.x, 3), -K);
-                            if (lim > 4) ep[4] -= fma(db4, dec_byte(w.y, 0), -K);
-                            if (lim > 5) ep[5] -= fma(db4, dec_byte(w.y, 1), -K);
-                            if (lim > 6) ep[6] -= fma(db4, dec_byte(w.y, 2), -K);
-                            if (lim > 7) ep[7] -= fma(db4, dec_byte(w.y, 3), -K);
+                    if (db != 0.0 && !is_chain) {
+                        const double K = db * misc[41];
+                        for (int wr = tid; wr < nwords; wr += kThreads) {
+                            const uint32_t w = (wr == tid) ? w0 : __ldg(reinterpret_cast<const uint32_t*>(tile) + word_off(B, q, wr));   // first pass from registers
+                            double* ep = e_s + 4 * wr;
+                            const int lim = nrow - 4 * wr;
+                            if (lim > 0) ep[0] -= fma(db, (double)(w & 0xff), -K);
+                            if (lim > 1) ep[1] -= fma(db, (double)((w >> 8) & 0xff), -K);
+                            if (lim > 2) ep[2] -= fma(db, (double)((w >> 16) & 0xff), -K);
+                            if (lim > 3) ep[3] -= fma(db, (double)(w >> 24), -K);
                         }
                     }
                     __syncthreads();
                 }
                 // (only lane 0 accumulated acc_bb / acc_n in the literal path; the other lanes hold 0)
             }
-            if (tid == 0) { tc = clock64(); }
+            if constexpr (PROF) tc = clock64();
 
-            // ------------------------------------------------------------------ phase 3
+            // ------------------------------------------------------------------ phase 3 (chain CTA)
             const bool regional = (S.method == 0 && S.n_regions > 1);
-            if (warp == 0 && !regional) {
+            if (is_chain && warp == 0 && !regional) {
                 const double bb = warp_sum(acc_bb);
                 const double nl = warp_sum(acc_n);
-                if (t == 0 && lane == 0) {
+                if (lane == 0) {
                     Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)s};
                     if (S.method == 0) {            // one region: functions.jl:135
                         const double chi2 = P.replay ? S.rp_chi2b[rp_row * S.nvar] : stream_chisq(st, P_CHI2_B, 0, 0, S.df + (double)S.p);
@@ -637,8 +922,8 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                 }
             }
             if (regional || P.accumulate) {
-                // beta / delta of this sweep were written by CTA 0 (plain stores, off the critical path): one grid
-                // barrier, then the posterior sums and the region variances are spread over the whole grid
+                // beta / delta of this sweep were written by the chain CTA (plain stores): one grid barrier, then the
+                // posterior sums and the region variances are spread over the whole grid
                 __syncthreads();
                 gs.nbar++;
                 if (tid == 0) gs.arrive();
@@ -646,7 +931,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                 __syncthreads();
             }
             if (P.accumulate) {
-                for (int64_t j = (int64_t)t * kThreads + tid; j < S.p; j += (int64_t)P.T * kThreads) {
+                for (int64_t j = (int64_t)t * kThreads + tid; j < S.p; j += (int64_t)(Tw + 1) * kThreads) {
                     const double bj = __ldcg(&S.beta[j]);
                     S.sum_beta[j] += bj;
                     S.sum_beta2[j] = fma(bj, bj, S.sum_beta2[j]);
@@ -655,7 +940,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
             }
             if (regional) {
                 Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)s};
-                for (int64_t rg = (int64_t)t * kWarps + warp; rg < S.n_regions; rg += (int64_t)P.T * kWarps) {
+                for (int64_t rg = (int64_t)t * kWarps + warp; rg < S.n_regions; rg += (int64_t)(Tw + 1) * kWarps) {
                     const int64_t j0 = S.region_off[rg], j1 = S.region_off[rg + 1];
                     double bb = 0.0;
                     for (int64_t j = j0 + lane; j < j1; j += 32) { const double bj = __ldcg(&S.beta[j]); bb = fma(bj, bj, bb); }
@@ -670,7 +955,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
             if (tid == 0) NGP_TICK(11);
         }   // sets
 
-        if (t == 0 && tid == 0) {
+        if (is_chain && tid == 0) {
             P.sc->mu = mu; P.sc->varE = varE; P.sc->iter = iter0 + it + 1;
             if (P.accumulate) P.sc->n_post += 1;
         }
@@ -678,13 +963,16 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 
     __syncthreads();
     for (int r = tid; r < nrow; r += kThreads) P.e[row0 + r] = e_s[r];
-    if (tid == 0) {
-        const int own[] = {0, 3, 4, 5, 6, 7, 8, 9, 11};
-        for (int i : own) sy->prof[t * kProf + i] = pf[i];
-    }
-    if (tid == 32) {
-        const int own[] = {1, 2, 10, 12, 13, 14};
-        for (int i : own) sy->prof[t * kProf + i] = pf[i];
+    // profile: thread 0 of every CTA (worker warp 0 / chain warp), plus the first prep warp of the chain CTA
+    if constexpr (PROF) {
+        // thread 0 = updater (worker CTA) / chain warp (chain CTA); first dot warp; first prep warp
+        const bool dotlane = !is_chain && tid == kFirstDotWarp * 32, preplane = is_chain && tid == kFirstPrepWarp * 32;
+        for (int i = 0; i < kProf; ++i) {
+            const bool dot_i = (i == 1 || i == 14 || i == 15 || i == 20), prep_i = (i == 12 || i == 13);
+            if (tid == 0 && !(dot_i && !is_chain) && !(prep_i && is_chain)) sy->prof[t * kProf + i] = pf[i];
+            if (dotlane && dot_i) sy->prof[t * kProf + i] = pf[i];
+            if (preplane && prep_i) sy->prof[t * kProf + i] = pf[i];
+        }
     }
 #undef NGP_TICK
 }

@@ -12,8 +12,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nextgp.jl_b200 as ngp  # noqa: E402
 from bench import CONFIGS, SEED0  # noqa: E402
 
-NAMES = ["tile_wait", "w_dot_red", "w_axpy", "acc_poll", "chain", "chain_waits_workers", "changed_effects", "spec_evals",
-         "phase0", "phase1", "w_waits_chain", "phase3", "w_tile_wait", "w_dot_loop", "w_dot_bar", "x15"]
+NAMES = ["c_rec_wait", "w_dot", "w_axpy_quant", "c_rbase_wait", "c_load", "x5", "changed_effects", "spec_evals",
+         "phase0", "phase1", "w_list_wait", "phase3", "p_far_corr", "p_acc_poll", "w_tile_wait", "w_combine_red",
+         "c_near_corr", "c_spec_loop", "c_publish", "c_outputs", "x20", "x21", "x22", "x23"]
 
 
 def main():
@@ -23,6 +24,9 @@ def main():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--warm", type=int, default=20)
     ap.add_argument("--model", default="")
+    ap.add_argument("--lookahead", type=int, default=0)
+    ap.add_argument("--tiles", type=int, default=0)
+    ap.add_argument("--near", type=int, default=0)
     a = ap.parse_args()
     n, p, model = CONFIGS[a.config]
     model = a.model or model
@@ -30,7 +34,8 @@ def main():
     prob = ngp.synth.problem(n, p, seed)
     v_e, v, pi = ngp.synth.priors(prob, model)
     method = 0 if model in ("BayesRR", "BayesPR") else (1 if model == "BayesB" else 2)
-    s = ngp.Sampler(0, kernel=a.kernel, block=a.block)
+    s = ngp.Sampler(0, kernel=a.kernel, block=a.block, lookahead=a.lookahead, tile_stages=a.tiles, near=a.near)
+    s.configure(ngp._lib.CFG_PROFILE, 1)
     s.synth_genotypes(0, n, p, seed, prob["thr0"], prob["thr1"])
     s.set_prior(0, method, 4.0, v * 0.5, v, pi_in=pi, est_pi=(method == 2))
     s.set_phenotype(prob["y"]); s.set_residual_prior(4.0, v_e * 0.5); s.set_intercept(True); s.set_rng(seed, 0)
@@ -44,10 +49,11 @@ def main():
             st = s.state(want_e=False)
             rec["included"] = int(st["sets"][0]["delta"].sum()) if method else p
             rec["varE"] = st["varE"]
-            rec["phases_mean_cycles"] = {k: float(pr[:, i].mean()) for i, k in enumerate(NAMES)}
-            rec["phases_max_cycles"] = {k: float(pr[:, i].max()) for i, k in enumerate(NAMES)}
             nblk = (p + t["block"] - 1) // t["block"]
-            rec["per_block_mean_cycles"] = {k: float(pr[:, i].mean()) / nblk for i, k in enumerate(NAMES)}
+            w, c = pr[:-1], pr[-1]           # worker CTAs, chain CTA
+            rec["worker_per_block_mean_cycles"] = {k: float(w[:, i].mean()) / nblk for i, k in enumerate(NAMES) if k.startswith("w_") or k.startswith("phase")}
+            rec["worker_per_block_max_cycles"] = {k: float(w[:, i].max()) / nblk for i, k in enumerate(NAMES) if k.startswith("w_")}
+            rec["chain_cta_per_block_cycles"] = {k: float(c[i]) / nblk for i, k in enumerate(NAMES) if k[0] in "cp" or k in ("changed_effects", "spec_evals")}
         out["iters"].append(rec)
     out["geometry"] = s.timing()
     print(json.dumps(out, indent=1))
