@@ -70,6 +70,9 @@ enum ngp_config_key {
     NGP_CFG_NEAR = 6,          /* cross-Gram distances kept in the chain CTA's block record (0 = auto) */
                                /* keys 1..6 must be set before the first upload             */
     NGP_CFG_PROFILE = 7,       /* 1 = launch the instrumented kernel (cycle counters for ngp_get_profile) */
+    NGP_CFG_REFETCH = 9,       /* 1 = release a genotype tile right after its dots and re-read the (few) changed columns from L2 for
+                                  the residual update: the tile ring no longer limits the look-ahead (set before the first upload) */
+    NGP_CFG_VERSIONS = 10,     /* versions of the fixed-point residual kept per worker CTA (0 = auto; before the first upload) */
     NGP_CFG_DEBUG = 8          /* timing experiments that decouple the kernel's roles; RESULTS ARE INVALID when non-zero */
 };
 
@@ -185,7 +188,7 @@ int ngp_reset_posterior(ngp_handle* h);
 int ngp_get_posterior(ngp_handle* h, int set_id, int64_t* n_samples, double* sum_beta, double* sum_beta2, double* sum_delta);
 int ngp_get_timing(ngp_handle* h, ngp_timing* out);
 
-/* per-CTA cycle counters of the last launch, 24 int64 per CTA (clock64; blocked kernel).  The last CTA is the
+/* per-CTA cycle counters of the last launch, 32 int64 per CTA (clock64; blocked kernel).  The last CTA is the
  * chain CTA, the others are worker CTAs.
  * worker CTA (thread 0):  [1] IMMA dots + limb combine [2] axpy + re-quantise [10] wait for the changed-effect list
  *                         [14] wait for the TMA tile [15] CTA combine + RED
@@ -195,6 +198,9 @@ int ngp_get_timing(ngp_handle* h, ngp_timing* out);
  * every CTA  (thread 0):  [8] phase 0 (varE, intercept) [9] phase 1 (marker constants) [11] phase 3
  * Returns the number of CTAs written. */
 int ngp_get_profile(ngp_handle* h, int64_t* out, int32_t max_ctas);
+
+/* instrumented kernel only: (start clock, cycles waited for the dots) of the chain warp's first 2048 steps of the last sweep */
+int ngp_get_trace(ngp_handle* h, int64_t* out, int32_t n);
 
 /* stream self-test: fills out[0..n) with the handle's variates of one purpose
  * (purpose: 2=uniform 3=normal 4=chisq(df)) for iteration iter, set set_id.   */

@@ -400,12 +400,20 @@ class Sampler:
         return {k: getattr(t, k) for k, _ in L.Timing._fields_}
 
     def profile(self) -> np.ndarray:
-        """(ctas, 24) int64 cycle counters of the last launch, see ngp_get_profile."""
-        out = np.zeros((160, 24), dtype=np.int64)
+        """(ctas, 32) int64 cycle counters of the last launch, see ngp_get_profile."""
+        out = np.zeros((160, 32), dtype=np.int64)
         nc = self._lib.ngp_get_profile(self._h, _p(out), 160)
         if nc < 0:
             self._ck(nc)
         return out[:nc]
+
+    def trace(self) -> np.ndarray:
+        """(steps, 2) int64: start clock and cycles waited for r_base of the chain warp's first 2048 steps (instrumented kernel)."""
+        out = np.zeros((2048, 2), dtype=np.int64)
+        nc = self._lib.ngp_get_trace(self._h, _p(out), 4096)
+        if nc < 0:
+            self._ck(nc)
+        return out
 
     def debug_variates(self, set_id: int, it: int, purpose: int, df: float, n: int) -> np.ndarray:
         out = np.empty(n)

@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <string.h>
 #include <math.h>
 #include <string>
@@ -18,6 +19,8 @@
 #include "ngp_sweep.cuh"
 
 using namespace ngp;
+
+static_assert(kSyncHeadBytes == offsetof(SyncArea, acc), "the per-launch memset covers exactly the head of SyncArea");
 
 // ============================================================================= set-up kernels
 namespace {
@@ -200,8 +203,8 @@ struct ngp_handle {
     std::string err;
     // geometry
     int64_t n = 0;
-    int Tw = 0, R = 0, B = 0, D = 0, DN = 0, NT = 0, NR = 0;      // worker CTAs (grid = Tw + 1), rows per panel, block, look-ahead, near depth, tile stages
-    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0;
+    int Tw = 0, R = 0, B = 0, D = 0, DN = 0, NT = 0, NR = 0, NV = 0;      // worker CTAs (grid = Tw + 1), rows per panel, block, look-ahead, near depth, tile stages
+    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0, cfg_refetch = 0, cfg_versions = 0;
     SmemLayout L{};
     // model
     SetHost sets[NGP_MAX_SETS];
@@ -223,6 +226,7 @@ struct ngp_handle {
     double *rp_chi2_e = nullptr, *rp_z_mu = nullptr;
     // stats
     int64_t launches = 0;
+    uint64_t gblk = 0;          // blocks swept so far by the blocked kernel (numbers the list words and accumulator slots)
     bool timed = false;
 };
 
@@ -355,6 +359,13 @@ int ngp_configure(ngp_handle* h, int key, int64_t value)
         if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: max CTAs must be set before the first upload");
         if (value < 0 || value == 1) return fail(h, NGP_EINVAL, "ngp_configure: max CTAs must be 0 (one per SM) or >= 2 (workers + the chain CTA)");
         h->cfg_max_ctas = (int)value; return NGP_OK;
+    case NGP_CFG_VERSIONS:
+        if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: residual versions must be set before the first upload");
+        if (value < 0 || value > kLimbVers || value == 1) return fail(h, NGP_EINVAL, "ngp_configure: residual versions must be 0 (auto) or in [2,%d]", kLimbVers);
+        h->cfg_versions = (int)value; return NGP_OK;
+    case NGP_CFG_REFETCH:
+        if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: refetch mode must be set before the first upload");
+        h->cfg_refetch = value ? 1 : 0; return NGP_OK;
     case NGP_CFG_DEBUG:
         h->cfg_debug = (int)value; return NGP_OK;
     case NGP_CFG_PROFILE:
@@ -401,25 +412,29 @@ static int choose_geometry(ngp_handle* h, int64_t n)
     if (R > maxR)
         return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA; block %d supports at most %lld (use block 16 for up to %d)",
                     (long long)n, (long long)R, B, (long long)maxR, 4 * kUpdThreads * kUpdGroups);
-    int DN = h->cfg_near ? h->cfg_near : (B == 64 ? 1 : B == 32 ? 3 : 6);
-    int D = h->cfg_lookahead ? h->cfg_lookahead : (B == 64 ? 6 : B == 32 ? 12 : 20);
+    const int dn_min = 2 * (64 / B) - 1;           // the chain warp steps over 64 markers: distances inside two steps come from the records
+    int DN = std::max(dn_min, h->cfg_near ? h->cfg_near : 0);
+    int D = h->cfg_lookahead ? h->cfg_lookahead : h->cfg_refetch ? (B == 64 ? 10 : B == 32 ? 20 : kMaxD) : (B == 64 ? 6 : B == 32 ? 13 : 20);
     D = std::min(D, kNzRing - 2);
     for (;; ) {
-        DN = std::max(1, std::min(DN, D));
-        int NT = h->cfg_tile_stages ? std::max(h->cfg_tile_stages, D + 2) : D + 4;
+        if (D < dn_min) break;
+        DN = std::max(dn_min, std::min(DN, D));
+        const int nt_min = h->cfg_refetch ? 2 : D + 2;     // resident mode: a tile stays in smem until its block has been applied to e
+        int NT = h->cfg_tile_stages ? std::max(h->cfg_tile_stages, nt_min) : h->cfg_refetch ? kDotWarps + 6 : D + 4;     // a tile stays resident until its block has been applied to e
         // shrink the record ring of the chain CTA, the tile ring, then the look-ahead, until both CTA roles fit
         for (;;) {
             for (int NR = kRecStages; NR >= 2; NR >>= 1) {
-                SmemLayout L = smem_layout((int)R, B, NT, DN, NR);
+                const int NV = h->cfg_versions ? h->cfg_versions : std::max(4, std::min(kLimbVers, D / 2 + 3));
+                SmemLayout L = smem_layout((int)R, B, NT, DN, NR, NV);
                 if ((size_t)L.total + 1024 <= cap) {
-                    h->n = n; h->Tw = Tw; h->R = (int)R; h->B = B; h->D = D; h->DN = DN; h->NT = NT; h->NR = NR; h->L = L;
+                    h->n = n; h->Tw = Tw; h->R = (int)R; h->B = B; h->D = D; h->DN = DN; h->NT = NT; h->NR = NR; h->NV = NV; h->L = L;
                     return NGP_OK;
                 }
             }
-            if (NT > D + 2) --NT; else break;
+            if (NT > nt_min) --NT; else break;
         }
-        if (DN > 1) { --DN; continue; }
-        if (D > 1) { --D; continue; }
+        if (DN > dn_min) { --DN; continue; }
+        if (D > dn_min) { --D; continue; }
         break;
     }
     return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA: the panel tiles (block %d) do not fit in %zu bytes of shared memory",
@@ -791,13 +806,13 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     if (rc) return rc;
     Params P{};
     P.n = h->n; P.Tw = h->Tw; P.R = h->R; P.B = h->B; P.n_sets = h->n_sets; P.kernel = h->cfg_kernel;
-    P.D = h->D; P.DN = h->DN; P.NT = h->NT; P.NR = h->NR;
+    P.D = h->D; P.DN = h->DN; P.NT = h->NT; P.NR = h->NR; P.NV = h->NV;
     P.e = h->e; P.sets = h->sets_dev; P.sc = h->sc; P.sync = h->sync;
     P.df_e = h->df_e; P.scale_e = h->scale_e; P.has_mu = h->has_mu; P.do_varE = do_varE; P.do_mu = do_mu; P.set_mask = set_mask;
     P.mu_lhs0 = h->mu_lhs0; P.mu_rhs0 = h->mu_rhs0; P.varE_in = varE_in; P.n_iter = n_iter; P.replay = h->replay;
     P.replay_base = h->replay_base; P.rp_chi2_e = h->rp_chi2_e; P.rp_z_mu = h->rp_z_mu;
     P.key0 = (uint32_t)(h->seed & 0xffffffffu); P.key1 = (uint32_t)(h->seed >> 32); P.chain = h->chain; P.accumulate = accumulate;
-    P.debug = h->cfg_debug;
+    P.debug = h->cfg_debug; P.refetch = h->cfg_refetch;
 #define NGP_PICK(PROF, DBG) ((h->B == 64) ? (const void*)gibbs_kernel<64, PROF, DBG> : (h->B == 32) ? (const void*)gibbs_kernel<32, PROF, DBG> : (const void*)gibbs_kernel<16, PROF, DBG>)
     const void* kfn = h->cfg_debug ? NGP_PICK(false, true) : h->cfg_profile ? NGP_PICK(true, false) : NGP_PICK(false, false);
 #undef NGP_PICK
@@ -806,7 +821,16 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, h->L.total));
     if (per_sm * h->prop.multiProcessorCount < h->Tw + 1)
         return fail(h, NGP_EUNSUPPORTED, "cooperative grid of %d CTAs does not fit (%d per SM x %d SMs)", h->Tw + 1, per_sm, h->prop.multiProcessorCount);
-    CU(cudaMemsetAsync(h->sync, 0, sizeof(SyncArea), h->stream));
+    uint64_t blocks = 0;
+    for (int s = 0; s < h->n_sets; ++s) if ((set_mask >> s) & 1) blocks += (uint64_t)(h->sets[s].p_pad / h->B);
+    blocks *= (uint64_t)n_iter;
+    if (h->gblk + blocks >= 0xffff0000ull) {          // 32-bit sequence numbers: start over with clean rings
+        CU(cudaMemsetAsync(h->sync, 0, sizeof(SyncArea), h->stream));
+        h->gblk = 0;
+    }
+    P.gblk0 = (uint32_t)h->gblk;
+    h->gblk += blocks;
+    CU(cudaMemsetAsync(h->sync, 0, kSyncHeadBytes, h->stream));
     void* args[] = {&P};
     CU(cudaEventRecord(h->ev0, h->stream));
     CU(cudaLaunchCooperativeKernel(kfn, dim3(h->Tw + 1), dim3(kThreads), args, (size_t)h->L.total, h->stream));
@@ -970,6 +994,15 @@ int ngp_get_profile(ngp_handle* h, int64_t* out, int32_t max_ctas)
     const int nc = std::min<int>(max_ctas, h->Tw + 1);
     CU(cpy(h, out, h->sync->prof, sizeof(long long) * kProf * nc, cudaMemcpyDeviceToHost));
     return nc;
+}
+
+int ngp_get_trace(ngp_handle* h, int64_t* out, int32_t n)
+{
+    if (!h || !out || n <= 0) return fail(h, NGP_EINVAL, "ngp_get_trace: bad argument");
+    CU(cudaSetDevice(h->device));
+    const int m = std::min<int>(n, 2 * 2048);
+    CU(cpy(h, out, h->sync->trace, sizeof(long long) * m, cudaMemcpyDeviceToHost));
+    return m;
 }
 
 int ngp_debug_variates(ngp_handle* h, int set_id, uint32_t iter, int purpose, double df, int64_t n, double* out)

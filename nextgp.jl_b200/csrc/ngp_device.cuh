@@ -29,18 +29,22 @@ constexpr int kWarps = 14;
 constexpr int kThreads = kWarps * 32;  // chain CTA: warp 0 chain, warp 1 TMA producer of the block records, warps 2..9 "prep" warps
 constexpr int kPrepWarps = 8;          //            (poll accumulators, cross-Gram corrections of distance >= 2 -> r_base)
 constexpr int kFirstPrepWarp = 2;
-constexpr int kLimbVers = 4;           // versions of the fixed-point residual kept per worker CTA
+constexpr int kLimbVers = 16;          // maximum number of versions of the fixed-point residual kept per worker CTA
 
-constexpr int kProf = 24;              // cycle counters per CTA (ngp_get_profile)
+constexpr int kProf = 32;              // cycle counters per CTA (ngp_get_profile)
 constexpr int kMaxB = 64;              // markers per block: 16, 32 or 64
 constexpr int kNF = 10;                // per-marker constant fields
 constexpr int kMaxD = 24;              // maximum look-ahead depth (blocks)
 constexpr int kSlots = 32;             // accumulator ring (blocks in flight <= D+1), multiple of kPrepWarps
 constexpr int kMaxCtas = 160;          // < 256: the low byte of an accumulator counts arrivals
 constexpr int kCntBits = 8;
+constexpr int kAccStride = 1;          // int64 units between two accumulators (contiguous measured no slower than 256 B apart)
+constexpr int kLLCopies = 8;           // replicas of the changed-effect list ring (worker CTA t polls replica t % 8): no L2 hot spot
 constexpr int kNzRing = 32;            // rings indexed by the global block number (lists, versions, dot-done flags): >= D+2
-constexpr int kNzSmem = 4;             // worker-CTA smem ring of received lists
+constexpr int kNzSmem = 8;             // worker-CTA smem ring of received lists
 constexpr int kRecStages = 8;          // chain CTA: maximum stages of the block-record ring (TMA)
+constexpr int kPollPipe = 1;           // polling loops (lists, accumulators): probes kept in flight
+constexpr int kPollGap = 0;            //                                          cycles between two probes
 constexpr int kLLEntryWords = 5;       // idx, dbeta lo/hi, K lo/hi
 constexpr int kLLSlotWords = 1 + kLLEntryWords * kMaxB + 3;   // header + entries, padded to a multiple of 4 words
 
@@ -75,15 +79,21 @@ struct SetDev {
     double* sum_delta;
 };
 
-struct SyncArea {              // zeroed before every launch
+struct SyncArea {
+    // ---- head: zeroed before every launch
     unsigned long long counter;                 // grid-barrier arrivals, monotonic within a launch
     unsigned long long pad0[15];
-    long long acc[kSlots * kMaxB];              // fixed-point reduction accumulators (monotonic; low byte counts arrivals)
-    unsigned long long ll[kNzRing * kLLSlotWords];   // changed-effect lists chain CTA -> worker CTAs; every 8-byte word = {payload32, seq32}
     double part[kMaxCtas * 2];                  // phase-0 partials (e'e, sum e) per CTA
-    long long prof[kMaxCtas * kProf];           // per-CTA cycle counters of the last launch: see ngp_get_profile
     int err;
+    int pad1[31];
+    // ---- body: persists across launches (monotonic accumulators, sequence-numbered list words)
+    long long acc[kSlots * kMaxB * kAccStride]; // fixed-point reduction accumulators (monotonic; low byte counts arrivals)
+    unsigned long long ll[kLLCopies][kNzRing * kLLSlotWords];   // changed-effect lists chain CTA -> worker CTAs (copy = CTA % kLLCopies);
+                                                // every 8-byte word = {payload32, seq32}, seq = global block number + 1
+    long long prof[kMaxCtas * kProf];           // per-CTA cycle counters of the last launch: see ngp_get_profile
+    long long trace[2 * 2048];                  // instrumented kernel: (start clock, cycles waited for r_base) of the chain warp's first 2048 steps
 };
+constexpr size_t kSyncHeadBytes = 16 * 8 + kMaxCtas * 2 * 8 + 32 * 4;
 
 struct Scalars {          // device-resident chain scalars
     double mu, varE;
@@ -95,6 +105,7 @@ struct Params {
     int64_t n;
     int32_t Tw;                // worker CTAs (row panels); the grid has Tw + 1 CTAs
     int32_t R, B, n_sets, kernel;
+    int32_t NV;                // versions of the fixed-point residual per worker CTA (<= kLimbVers)
     int32_t D, DN, NT, NR;     // look-ahead depth (blocks), near depth (cross-Grams kept in the block record), tile ring stages,
                                // block-record ring stages of the chain CTA (power of two <= kRecStages)
     double* e;                 // [Tw*R]
@@ -111,7 +122,9 @@ struct Params {
     const double* rp_z_mu;
     uint32_t key0, key1, chain;
     int32_t accumulate;        // add to posterior sums
+    uint32_t gblk0;            // global number of the first block of this launch (lists and accumulator slots are numbered globally)
     int32_t debug;             // timing experiments (NGP_CFG_DEBUG), see ngp_sweep.cuh
+    int32_t refetch;           // 1: tiles leave smem after their dots, changed columns are re-read from L2 for the axpy
 };
 
 // ----------------------------------------------------------------------------- tile layout
@@ -155,6 +168,7 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)

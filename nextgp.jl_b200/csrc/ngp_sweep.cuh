@@ -45,12 +45,12 @@ struct SmemLayout {
     // worker CTA
     int w_e, w_limb, w_tile, w_nz, w_vbuf, w_bar;
     // chain CTA
-    int c_rec, c_rbase, c_nz, c_prev, c_bar;
+    int c_rec, c_rbase, c_nz, c_prev, c_bar, c_outb, c_outi;
     int misc, total;
     int tile_bytes, rec_bytes, limb_bytes, nz_bytes;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int R, int B, int NT, int DN, int NR)
+__host__ __device__ inline SmemLayout smem_layout(int R, int B, int NT, int DN, int NR, int NV)
 {
     SmemLayout L;
     L.tile_bytes = B * R;
@@ -62,7 +62,7 @@ __host__ __device__ inline SmemLayout smem_layout(int R, int B, int NT, int DN, 
     const int base = o;
     // worker
     L.w_e = o;     o += R * 8;
-    L.w_limb = o;  o += kLimbVers * L.limb_bytes;
+    L.w_limb = o;  o += NV * L.limb_bytes;
     L.w_nz = o;    o += kNzSmem * L.nz_bytes;
     L.w_vbuf = o;  o += kNzRing * 4;
     L.w_bar = o;   o += (2 * NT + 2 * kNzSmem + 2 * kNzRing) * 8;
@@ -71,7 +71,9 @@ __host__ __device__ inline SmemLayout smem_layout(int R, int B, int NT, int DN, 
     const int wtot = o;
     // chain
     o = base;
-    L.c_bar = o;   o += (2 * kRecStages + 2 * kPrepWarps + kNzRing) * 8;
+    L.c_bar = o;   o += (2 * kRecStages + 3 * kPrepWarps + kNzRing) * 8;
+    L.c_outb = o;  o += kPrepWarps * 64 * 8;
+    L.c_outi = o;  o += kPrepWarps * 64 * 4;
     L.c_rbase = o; o += kPrepWarps * B * 8;
     L.c_prev = o;  o += kSlots * B * 8;
     L.c_nz = o;    o += kNzRing * L.nz_bytes;
@@ -202,7 +204,11 @@ template <int B, bool PROF, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int NB = (B + 31) / 32;      // markers per lane of a chain / prep warp (lane <-> marker b*32 + lane)
+    constexpr int NB = (B + 31) / 32;      // markers per lane of a prep warp (lane <-> marker b*32 + lane)
+    constexpr int SB = 64 / B;             // blocks per step of the chain warp (a step = 64 markers, 2 per lane)
+    constexpr int SBS = (SB == 1) ? 0 : (SB == 2) ? 1 : 2;
+    constexpr int RBS = kPrepWarps / SB;   // super-block slots of the r_base ring
+    constexpr int kHelperWarp = kFirstPrepWarp + kPrepWarps;     // chain CTA: publishes the lists and writes the outputs
     constexpr int MG = B / 16;             // 16-marker MMA groups per block
     constexpr int UG = (B == 16) ? kUpdGroups : 1;   // 4-row groups per updater thread (B = 32 / 64 are chosen for R <= 512)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -210,17 +216,20 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     const int Tw = P.Tw;
     const bool is_chain = (t == Tw);
     const int R = P.R, D = P.D, DN = P.DN, NT = P.NT, NR = P.NR;
-    const SmemLayout L = smem_layout(R, B, NT, DN, NR);
+    const int NV = P.NV;
+    const SmemLayout L = smem_layout(R, B, NT, DN, NR, NV);
     // timing experiments only (results are garbage): 1 workers ignore the lists, 2 prep warps skip the accumulator poll,
     // 4 chain warp skips corrections + scalar updates, 8 workers skip the dots and the RED
     const int dbg = DBG ? P.debug : 0;
-    double* misc = reinterpret_cast<double*>(smem + L.misc);     // [0..27] block_sum scratch, [32..] scalars, [48..] literal-kernel prev
+    const bool refetch = P.refetch != 0;
+    double* misc = reinterpret_cast<double*>(smem + L.misc);     // [0..27] block_sum scratch, [32..] scalars, [44] chain progress, [48..] literal-kernel prev
+    volatile unsigned* cprog = reinterpret_cast<volatile unsigned*>(misc + 44);     // chain CTA: global number of blocks whose lists are complete
     SyncArea* sy = P.sync;
 
     typedef NzListT<B> NzList;
     // worker views
     double* e_s = reinterpret_cast<double*>(smem + L.w_e);
-    uint32_t* limb = reinterpret_cast<uint32_t*>(smem + L.w_limb);                          // [kLimbVers][R*2] words
+    uint32_t* limb = reinterpret_cast<uint32_t*>(smem + L.w_limb);                          // [NV][R*2] words
     NzList* wnz = reinterpret_cast<NzList*>(smem + L.w_nz);
     int* vbuf = reinterpret_cast<int*>(smem + L.w_vbuf);                                    // [kNzRing] limb version holding the state after block g
     uint64_t* tile_full = reinterpret_cast<uint64_t*>(smem + L.w_bar);
@@ -235,6 +244,9 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     uint64_t* rb_full = rec_free + kRecStages;
     uint64_t* rb_free = rb_full + kPrepWarps;
     uint64_t* nzc_full = rb_free + kPrepWarps;
+    uint64_t* step_done = nzc_full + kNzRing;                                               // [kPrepWarps] a 64-marker step of the chain warp
+    double* out_b = reinterpret_cast<double*>(smem + L.c_outb);                             // [kPrepWarps][64] new effects of a step
+    int* out_i = reinterpret_cast<int*>(smem + L.c_outi);                                   // [kPrepWarps][64] inclusion indicators
     double* rbase = reinterpret_cast<double*>(smem + L.c_rbase);                            // [kPrepWarps][B]
     long long* prev = reinterpret_cast<long long*>(smem + L.c_prev);                        // [kSlots][B]
     NzList* cnz = reinterpret_cast<NzList*>(smem + L.c_nz);
@@ -247,23 +259,27 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     if (!is_chain) {
         for (int r = tid; r < R; r += kThreads) e_s[r] = (r < nrow) ? P.e[row0 + r] : 0.0;
     } else {
-        for (int q = tid; q < kSlots * B; q += kThreads) prev[q] = 0;
+        // the accumulators are monotonic across launches: start from their current values
+        for (int q = tid; q < kSlots * B; q += kThreads) prev[q] = sy->acc[((size_t)(q / B) * kMaxB + (q % B)) * kAccStride];
     }
-    if (tid < kSlots) reinterpret_cast<long long*>(misc + 48)[tid] = 0;      // literal kernel: previous accumulator values
+    if (tid < kSlots) reinterpret_cast<long long*>(misc + 48)[tid] = sy->acc[(size_t)tid * kMaxB * kAccStride];      // literal kernel: previous accumulator values
+    if (tid == 0) *cprog = 0u;
     if (tid == 0) {
         if (!is_chain) {
-            for (int s = 0; s < NT; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_free[s], kUpdWarps); }
+            for (int s = 0; s < NT; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_free[s], P.refetch ? 1 : kUpdWarps); }
             for (int s = 0; s < kNzSmem; ++s) { mbar_init(&nz_full[s], 1); mbar_init(&nz_free[s], kUpdWarps); }
             for (int s = 0; s < kNzRing; ++s) { mbar_init(&ver_full[s], kUpdWarps); mbar_init(&dot_done[s], 1); }
         } else {
             for (int s = 0; s < kRecStages; ++s) { mbar_init(&rec_full[s], 1); mbar_init(&rec_free[s], 1); }
-            for (int s = 0; s < kPrepWarps; ++s) { mbar_init(&rb_full[s], 1); mbar_init(&rb_free[s], 1); }
+            for (int s = 0; s < kPrepWarps; ++s) { mbar_init(&rb_full[s], 64 / B); mbar_init(&rb_free[s], 1); mbar_init(&step_done[s], 1); }
             for (int s = 0; s < kNzRing; ++s) mbar_init(&nzc_full[s], 1);
         }
         fence_mbar_init();
     }
     __syncthreads();
 
+    __shared__ long long step_end_clk[64];
+    __shared__ unsigned long long pub_ns[kNzRing];   // instrumented kernel: global time at which a list was published (worker CTA copy / chain CTA copy)        // instrumented kernel: clock at which the chain warp finished a step
     // cycle counters, see ngp_get_profile
     long long pf[kProf];
 #pragma unroll
@@ -275,8 +291,9 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     Ring r_ta{0, 0}, r_tp{0, 0};                  // tile ring: updater (release), TMA producer
     Ring r_nzw{0, 0}, r_nzp{0, 0};                // worker nz list ring: consumer (updaters), producer (poll warp)
     Ring r_rec{0, 0};                             // chain CTA record ring (TMA producer cursor)
-    unsigned tiles_issued = 0, recs_issued = 0, nz_recv = 0, rb_uses = 0;
-    unsigned gblk = 0;       // blocks processed before the current sweep (all sets, all iterations of this launch)
+    unsigned tiles_issued = 0, recs_issued = 0, nz_recv = 0;
+    unsigned gblk = 0;       // blocks processed before the current sweep (all sets, all iterations of this launch): indexes every ring
+    const uint32_t seq0 = P.gblk0;     // blocks swept by earlier launches: sequence number of a list word = seq0 + block number + 1
     unsigned rk = 0;         // literal kernel: running reduction count
     double mu = P.sc->mu;
     const long long iter0 = P.sc->iter;
@@ -395,12 +412,13 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         for (int ja = 0; ja < nblk; ++ja) {
                             const unsigned gidx = gblk + (unsigned)ja;
                             if (!(dbg & 1)) mbar_wait(&nz_full[r_nzw.s], r_nzw.ph);
+                            else mbar_wait(&dot_done[gidx & (kNzRing - 1)], (gidx / kNzRing) & 1u);     // stay behind the dots like the real protocol
                             if (tid == 0) NGP_TICK(10);
                             const NzList& nl = wnz[r_nzw.s];
                             const int nnz = (dbg & 1) ? 0 : nl.nnz;
                             if (nnz > 0) {
                                 // e -= sum_q dbeta_q (g_q - mean_q): one tile word = the 4 codes of this thread's rows
-                                const int nv = (cur + 1 == kLimbVers) ? 0 : cur + 1;
+                                const int nv = (cur + 1 == NV) ? 0 : cur + 1;
                                 int sv = -1;
 #pragma unroll
                                 for (int v = 0; v < kLimbVers; ++v) if (v == nv) sv = sup[v];
@@ -412,19 +430,30 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                     }
                                 }
                                 if (tid == 0) NGP_TICK(5);
-                                const uint32_t* tw = reinterpret_cast<const uint32_t*>(tiles + r_ta.s * L.tile_bytes);
+                                // one 32-bit word = the 4 codes of this thread's rows.  Resident mode: the tile is still in shared memory.
+                                // Refetch mode: the stage was released right after the dots and the words of the changed columns come
+                                // back from L2 (the tile was streamed D+1 blocks ago) - the tile ring is then independent of D.
+                                const uint32_t* tw = refetch ? reinterpret_cast<const uint32_t*>(gbase + (int64_t)ja * L.tile_bytes)
+                                                             : reinterpret_cast<const uint32_t*>(tiles + r_ta.s * L.tile_bytes);
 #pragma unroll
                                 for (int k = 0; k < UG; ++k) {
                                     const int rg = tid + k * kUpdThreads;
                                     if (4 * rg < R) {
                                         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                                        for (int i = 0; i < nnz; ++i) {
-                                            const uint32_t w = tw[word_off(B, nl.idx[i], rg)];
-                                            const double db = nl.db[i], kk = nl.aux[i];
-                                            s0 += fma(db, (double)(w & 0xff), -kk);
-                                            s1 += fma(db, (double)((w >> 8) & 0xff), -kk);
-                                            s2 += fma(db, (double)((w >> 16) & 0xff), -kk);
-                                            s3 += fma(db, (double)(w >> 24), -kk);
+                                        for (int i0 = 0; i0 < nnz; i0 += 4) {
+                                            uint32_t w4[4];
+#pragma unroll
+                                            for (int u = 0; u < 4; ++u) w4[u] = (i0 + u < nnz) ? tw[word_off(B, nl.idx[i0 + u], rg)] : 0u;      // generic load: smem or global
+#pragma unroll
+                                            for (int u = 0; u < 4; ++u)
+                                                if (i0 + u < nnz) {
+                                                    const uint32_t w = w4[u];
+                                                    const double db = nl.db[i0 + u], kk = nl.aux[i0 + u];
+                                                    s0 += fma(db, (double)(w & 0xff), -kk);
+                                                    s1 += fma(db, (double)((w >> 8) & 0xff), -kk);
+                                                    s2 += fma(db, (double)((w >> 16) & 0xff), -kk);
+                                                    s3 += fma(db, (double)(w >> 24), -kk);
+                                                }
                                         }
                                         const int r0 = 4 * rg;
                                         if (r0 < nrow) er[k][0] -= s0;
@@ -439,10 +468,11 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                 cur = nv;
                             }
                             if (tid == 0) vbuf[gidx & (kNzRing - 1)] = cur;
+                            if constexpr (PROF) { if (tid == 0) { pf[26] += (long long)(global_ns() - pub_ns[gidx & (kNzRing - 1)]); pf[27] += 1; } }
                             __syncwarp();
                             if (lane == 0) {
                                 mbar_arrive(&ver_full[gidx & (kNzRing - 1)]);
-                                mbar_arrive(&tile_free[r_ta.s]);
+                                if (!refetch) mbar_arrive(&tile_free[r_ta.s]);
                                 if (!(dbg & 1)) mbar_arrive(&nz_free[r_nzw.s]);
                             }
                             r_ta.adv(NT); r_nzw.adv(kNzSmem);
@@ -500,8 +530,12 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                         }
                                     }
                                 }
+                                if (refetch) {
+                                    __syncwarp();
+                                    if (lane == 0) mbar_arrive(&tile_free[tslot]);      // all fragments are in registers: the stage can be refilled
+                                }
                                 if (tid == kFirstDotWarp * 32) NGP_TICK(1);
-                                long long* accg = sy->acc + (gidx & (kSlots - 1)) * kMaxB;
+                                long long* accg = sy->acc + (size_t)(gidx & (kSlots - 1)) * kMaxB * kAccStride;
 #pragma unroll
                                 for (int mg = 0; mg < MG; ++mg) {
                                     int c4[4];
@@ -520,12 +554,16 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                     if (tt < 2) {
                                         const long long sa = (long long)(tt ? v1 : v0);
                                         if (sa >= plim || sa <= -plim) atomicOr(&sy->err, 1);
-                                        red_add_u64(accg + mg * 16 + g + 8 * tt, (long long)((unsigned long long)sa << kCntBits) + 1);
+                                        red_add_u64(accg + (mg * 16 + g + 8 * tt) * kAccStride, (long long)((unsigned long long)sa << kCntBits) + 1);
                                     }
                                 }
                             }
+                            if constexpr (PROF) { if (tid == kFirstDotWarp * 32 && ja >= 0) { pf[28] += (long long)(global_ns() - pub_ns[(gblk + (unsigned)ja) & (kNzRing - 1)]); pf[29] += 1; } }
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&dot_done[gidx & (kNzRing - 1)]);
+                            if (lane == 0) {
+                                if (refetch && (dbg & 8)) mbar_arrive(&tile_free[tslot]);
+                                mbar_arrive(&dot_done[gidx & (kNzRing - 1)]);
+                            }
                             tslot += kDotWarps;
                             while (tslot >= NT) { tslot -= NT; tph ^= 1u; }
                             if (tid == kFirstDotWarp * 32) NGP_TICK(15);
@@ -542,39 +580,100 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         }
                     } else {
                         // ------------------------------------------------------------------ poll warp: changed-effect lists
-                        for (int ja = 0; ja < ((dbg & 1) ? 0 : nblk); ++ja) {
-                            const unsigned gidx = gblk + (unsigned)ja;
-                            const uint32_t seq = gidx + 1u;
-                            const unsigned long long* sw = sy->ll + (size_t)(gidx & (kNzRing - 1)) * kLLSlotWords;
+                        // one L2 round trip probes the first 8 words (header + one entry) of 4 consecutive slots
+                        int ja_cur = 0;
+                        const unsigned long long* llc = sy->ll[t % kLLCopies];      // this CTA's replica of the list ring
+                        auto deliver_begin = [&]() -> NzList& {
                             if (nz_recv >= (unsigned)kNzSmem) mbar_wait(&nz_free[r_nzp.s], r_nzp.ph ^ 1u);
-                            NzList& nl = wnz[r_nzp.s];
-                            int need = 1 << 30, nnz = 0;
-                            for (int base = 0; base < need; base += 32) {
-                                unsigned long long w;
-                                for (;;) {
-                                    w = ld_relaxed_u64(sw + base + lane);
-                                    const bool ok = (uint32_t)(w >> 32) == seq;
-                                    if (base == 0) {
-                                        const unsigned long long hdr = __shfl_sync(0xffffffffu, w, 0);
-                                        if ((uint32_t)(hdr >> 32) != seq) continue;
-                                        nnz = (int)(uint32_t)hdr;
-                                        need = 1 + kLLEntryWords * nnz;
-                                    }
-                                    if (__all_sync(0xffffffffu, ok || (base + lane >= need))) break;
-                                }
-                                const int wi = base + lane;
-                                if (wi >= 1 && wi < need) {
-                                    const int en = (wi - 1) / kLLEntryWords, f = (wi - 1) - en * kLLEntryWords;
-                                    const uint32_t pay = (uint32_t)w;
-                                    if (f == 0) nl.idx[en] = (int)pay;
-                                    else if (f <= 2) reinterpret_cast<uint32_t*>(&nl.db[en])[f - 1] = pay;
-                                    else reinterpret_cast<uint32_t*>(&nl.aux[en])[f - 3] = pay;
+                            return wnz[r_nzp.s];
+                        };
+                        auto deliver_end = [&](NzList& nl, int nnz) {
+                            if constexpr (PROF) {
+                                if (lane == 0) {
+                                    const unsigned gq = gblk + (unsigned)ja_cur;
+                                    unsigned long long w;
+                                    do { w = ld_relaxed_u64(llc + (size_t)(gq & (kNzRing - 1)) * kLLSlotWords + kLLSlotWords - 1); } while ((uint32_t)(w >> 32) != seq0 + gq + 1u);
+                                    const unsigned long long tn = global_ns();
+                                    const unsigned long long tp = (tn & ~0xffffffffull) | (w & 0xffffffffull);
+                                    pub_ns[gq & (kNzRing - 1)] = tp;
+                                    pf[24] += (long long)(tn - tp); pf[25] += 1;
                                 }
                             }
                             if (lane == 0) nl.nnz = nnz;
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&nz_full[r_nzp.s]);
                             r_nzp.adv(kNzSmem); ++nz_recv;
+                        };
+                        const int g4 = lane >> 3, wi8 = lane & 7;
+                        int ja = (dbg & 1) ? nblk : 0;
+                        // kPollPipe probes are kept in flight, one issued every kPollGap cycles: a list is seen about half a gap
+                        // (not half an L2 round trip, which is > 1 us under the streaming load) after it lands in L2
+                        auto probe = [&](int tag) -> unsigned long long {
+                            const unsigned gme = gblk + (unsigned)(tag + g4);
+                            return (tag + g4 < nblk) ? ld_relaxed_u64(llc + (size_t)(gme & (kNzRing - 1)) * kLLSlotWords + wi8) : 0ull;
+                        };
+                        unsigned long long pwv[kPollPipe];
+                        int ptag[kPollPipe];
+#pragma unroll
+                        for (int i = 0; i < kPollPipe; ++i) { pwv[i] = 0ull; ptag[i] = -1000; }     // tag -1000: an empty pipeline slot
+                        long long t_issue = clock64() - kPollGap;
+                        while (ja < nblk) {
+                            ja_cur = ja;
+                            // oldest probe out, new probe in (issued before the old one is looked at)
+                            const unsigned long long w = pwv[0];
+                            const int tag = ptag[0];
+#pragma unroll
+                            for (int i = 0; i + 1 < kPollPipe; ++i) { pwv[i] = pwv[i + 1]; ptag[i] = ptag[i + 1]; }
+                            while (clock64() - t_issue < kPollGap) { }
+                            t_issue = clock64();
+                            pwv[kPollPipe - 1] = probe(ja); ptag[kPollPipe - 1] = ja;
+                            if (tag + 4 <= ja) continue;                                   // empty slot, or everything it probed was delivered meanwhile
+                            const bool ok = (tag + g4 < nblk) && ((uint32_t)(w >> 32) == seq0 + gblk + (unsigned)(tag + g4) + 1u);
+                            const unsigned okm_all = __ballot_sync(0xffffffffu, ok);
+                            const int skip = ja - tag;                                     // lane groups whose list was delivered by an earlier probe
+                            const unsigned okm = okm_all >> (8 * skip);
+                            for (int k = 0; k + skip < 4 && ja < nblk; ++k) {
+                                if (!((okm >> (8 * k)) & 1u)) break;                       // header of the next list not there yet: next probe
+                                const int nnz = (int)(uint32_t)__shfl_sync(0xffffffffu, w, 8 * (k + skip));
+                                if (nnz == 0) {
+                                    NzList& nl = deliver_begin();
+                                    deliver_end(nl, 0);
+                                } else if (nnz == 1) {
+                                    if (((okm >> (8 * k)) & 0x3Eu) != 0x3Eu) break;         // its entry is still in flight
+                                    NzList& nl = deliver_begin();
+                                    if (g4 == k + skip && wi8 >= 1 && wi8 <= kLLEntryWords) {
+                                        const uint32_t pay = (uint32_t)w;
+                                        if (wi8 == 1) nl.idx[0] = (int)pay;
+                                        else if (wi8 <= 3) reinterpret_cast<uint32_t*>(&nl.db[0])[wi8 - 2] = pay;
+                                        else reinterpret_cast<uint32_t*>(&nl.aux[0])[wi8 - 4] = pay;
+                                    }
+                                    deliver_end(nl, 1);
+                                } else {
+                                    // long list: read the whole slot, 32 words per round trip
+                                    const unsigned gidx = gblk + (unsigned)ja;
+                                    const uint32_t seq = seq0 + gidx + 1u;
+                                    const unsigned long long* sw = llc + (size_t)(gidx & (kNzRing - 1)) * kLLSlotWords;
+                                    NzList& nl = deliver_begin();
+                                    const int need = 1 + kLLEntryWords * nnz;
+                                    for (int base = 0; base < need; base += 32) {
+                                        unsigned long long w2;
+                                        for (;;) {
+                                            w2 = ld_relaxed_u64(sw + base + lane);
+                                            if (__all_sync(0xffffffffu, ((uint32_t)(w2 >> 32) == seq) || (base + lane >= need))) break;
+                                        }
+                                        const int wi = base + lane;
+                                        if (wi >= 1 && wi < need) {
+                                            const int en = (wi - 1) / kLLEntryWords, f = (wi - 1) - en * kLLEntryWords;
+                                            const uint32_t pay = (uint32_t)w2;
+                                            if (f == 0) nl.idx[en] = (int)pay;
+                                            else if (f <= 2) reinterpret_cast<uint32_t*>(&nl.db[en])[f - 1] = pay;
+                                            else reinterpret_cast<uint32_t*>(&nl.aux[en])[f - 3] = pay;
+                                        }
+                                    }
+                                    deliver_end(nl, nnz);
+                                }
+                                ++ja; ja_cur = ja;
+                            }
                         }
                     }
                 } else {
@@ -582,139 +681,141 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     unsigned char* recs = smem + L.c_rec;
                     const int32_t* const gx_g = S.gx;
                     const size_t gx_blk = (size_t)(D + 1) * B * B;
+                    const int gofs = (1 + DN) * gram_bytes(B);          // constants follow the Gram matrices in a record
                     if (warp == 0) {
-                        // ------------------------------------------------------------------ chain warp
-                        double* const beta_g = S.beta;
-                        int32_t* const delta_g = S.delta;
-                        double* const vb_g = S.varBeta;
-                        const double sdf = S.scale * S.df;
-                        for (int m = 0; m < nblk; ++m) {
-                            const unsigned gidx = gblk + (unsigned)m;
-                            if constexpr (PROF) tc = clock64();
-                            const int rs = (int)(gidx & (kPrepWarps - 1));
-                            // r_base of block m is published after its record has landed (the prep warp waited for it)
-                            mbar_wait(&rb_full[rs], (gidx / kPrepWarps) & 1u);
-                            NGP_TICK(3);
-                            const unsigned rcs = gidx & (unsigned)(NR - 1);      // record ring stage
-                            const unsigned char* rec = recs + rcs * L.rec_bytes;
-                            const int32_t* gram = reinterpret_cast<const int32_t*>(rec);
-                            const double* cst = reinterpret_cast<const double*>(rec + (1 + DN) * gram_bytes(B));
-                            double r[NB], bold[NB], dd[NB], cs[NB], bnew[NB];
-                            bool inc[NB], live[NB];
+                        // ------------------------------------------------------------------ chain warp: 64 markers per step
+                        // slot i of a lane = marker mi = 32 i + lane of the step: block kb = mi / B of the step, column qb = mi % B
+                        int kb[2], qb[2];
 #pragma unroll
-                            for (int b = 0; b < NB; ++b) {
-                                const int q = b * 32 + lane;
-                                live[b] = q < B;
-                                const int qq = live[b] ? q : 0;
-                                r[b] = rbase[rs * B + qq];
-                                cs[b] = cst[F_CS * B + qq];
-                                bold[b] = live[b] ? cst[F_BOLD * B + qq] : 0.0;
-                                dd[b] = cst[F_D * B + qq];
-                                bnew[b] = 0.0; inc[b] = false;
+                        for (int i = 0; i < 2; ++i) { kb[i] = (32 * i + lane) / B; qb[i] = (32 * i + lane) % B; }
+                        int nn[SB];                                         // changed effects per block of the step
+#pragma unroll
+                        for (int k = 0; k < SB; ++k) nn[k] = 0;
+                        for (int s0 = 0; s0 < nblk; s0 += SB) {
+                            const unsigned g0 = gblk + (unsigned)s0;            // global number of the first block of the step
+                            const unsigned sg = g0 >> SBS;                      // global step number
+                            const int ss = (int)(sg & (RBS - 1));
+                            if constexpr (PROF) tc = clock64();
+                            // r_base of the step's blocks is published after their records have landed (the prep warps waited for them)
+                            mbar_wait(&rb_full[ss], (sg / RBS) & 1u);
+                            if constexpr (PROF) {
+                                const long long now_ = clock64();
+                                if (lane == 0 && (s0 >> SBS) < 2048) { sy->trace[2 * (s0 >> SBS)] = tc; sy->trace[2 * (s0 >> SBS) + 1] = now_ - tc; }
+                            }
+                            NGP_TICK(3);
+                            const int32_t* gram[2];
+                            const double* cst[2];
+                            // rr = x'e + d*beta_old (add-back fused: x'(e + x b) = x'e + d b) is the running quantity; bnz = (beta_old != 0)
+                            double rr[2], bold[2], cs[2], bnew[2], cA[2], cB[2], cT[2], cC[2], cQ[2];
+                            bool inc[2], bnz[2];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const unsigned gk = g0 + (unsigned)kb[i];
+                                const unsigned char* rec = recs + (gk & (unsigned)(NR - 1)) * L.rec_bytes;
+                                gram[i] = reinterpret_cast<const int32_t*>(rec);
+                                cst[i] = reinterpret_cast<const double*>(rec + gofs) + qb[i];
+                                const double r0 = rbase[(gk & (kPrepWarps - 1)) * B + qb[i]];
+                                cs[i] = cst[i][F_CS * B]; bold[i] = cst[i][F_BOLD * B];
+                                rr[i] = fma(cst[i][F_D * B], bold[i], r0);
+                                cA[i] = cst[i][F_A * B]; cB[i] = cst[i][F_B * B]; cT[i] = cst[i][F_T * B];
+                                cC[i] = cst[i][F_C * B]; cQ[i] = cst[i][F_QSZ * B];
+                                bnew[i] = 0.0; inc[i] = false; bnz[i] = bold[i] != 0.0;
                             }
                             NGP_TICK(4);
-                            // cross-Gram correction of distance 1 (block m-1), rows from the block record
-                            if (m >= 1 && DN >= 1 && !(dbg & 4)) {
-                                const NzList& pl = cnz[(gidx - 1u) & (kNzRing - 1)];
-                                const int np = pl.nnz;
-                                const int32_t* gd = gram + B * B;
-                                for (int i = 0; i < np; ++i) {
-                                    const int a = pl.idx[i];
-                                    const double dbf = pl.db[i], csf = pl.aux[i];
+                            // cross-Gram corrections from the blocks of the previous step (distances 1 .. 2 SB - 1 <= DN), oldest first
+                            if (s0 > 0 && !(dbg & 4)) {
 #pragma unroll
-                                    for (int b = 0; b < NB; ++b)
-                                        if (live[b]) r[b] = fma(-((double)gd[a * B + b * 32 + lane] - csf * cs[b] * inv_n), dbf, r[b]);
+                                for (int kk = SB; kk >= 1; --kk) {
+                                    const int np = nn[SB - kk];                 // list sizes of the previous step are still in registers
+                                    if (np == 0) continue;
+                                    const NzList& pl = cnz[(g0 - (unsigned)kk) & (kNzRing - 1)];
+                                    for (int e = 0; e < np; ++e) {
+                                        const int a = pl.idx[e];
+                                        const double dbf = pl.db[e], csf = pl.aux[e];
+#pragma unroll
+                                        for (int i = 0; i < 2; ++i)
+                                            rr[i] = fma(-((double)gram[i][(kb[i] + kk) * B * B + a * B + qb[i]] - csf * cs[i] * inv_n), dbf, rr[i]);
+                                    }
                                 }
                             }
                             NGP_TICK(16);
-                            NzList& ml = cnz[gidx & (kNzRing - 1)];
-                            unsigned long long* llw = sy->ll + (size_t)(gidx & (kNzRing - 1)) * kLLSlotWords;
-                            const unsigned long long seqhi = (unsigned long long)(gidx + 1u) << 32;
-                            int nnz = 0;
 #pragma unroll
-                            for (int b = 0; b < NB; ++b) {
-                                const int q = b * 32 + lane, qq = live[b] ? q : 0;
-                                const double cA = cst[F_A * B + qq], cB = cst[F_B * B + qq];
-                                const double cT = live[b] ? cst[F_T * B + qq] : -INFINITY;
-                                const double cC = cst[F_C * B + qq], cQ = cst[F_QSZ * B + qq];
-                                const double mq = cst[F_MEAN * B + qq];
-                                int start = (dbg & 4) ? 32 : 0;
-                                while (start < 32) {
-                                    if constexpr (PROF) pf[7]++;
-                                    const double rr = fma(dd[b], bold[b], r[b]);        // add-back fused: x'(e + x b) = x'e + d b
-                                    const double dl = fma(cB, rr * rr, cA);
-                                    const bool in = dl < cT;                            // NaN -> excluded, like rand() < NaN
-                                    const double bn = in ? fma(rr, cC, cQ) : 0.0;
-                                    const double db = bn - bold[b];
-                                    const bool act = lane >= start;
-                                    const unsigned mk = __ballot_sync(0xffffffffu, act && (db != 0.0));
-                                    const int f = mk ? (__ffs(mk) - 1) : 32;
-                                    if (act && lane <= f) { bnew[b] = bn; inc[b] = in; }
-                                    if (f == 32) break;
-                                    const double dbf = __shfl_sync(0xffffffffu, db, f);
-                                    const double csf = __shfl_sync(0xffffffffu, cs[b], f);
-                                    const double mf = __shfl_sync(0xffffffffu, mq, f);
-                                    const int32_t* grow = gram + (b * 32 + f) * B;
+                            for (int k = 0; k < SB; ++k) nn[k] = 0;
+                            int pos = (dbg & 4) ? 64 : 0;                       // markers [0, pos) of the step are committed
+                            while (pos < 64) {
+                                if constexpr (PROF) pf[7]++;
+                                double bnv[2];
+                                bool inv[2];
+                                unsigned mk[2];
 #pragma unroll
-                                    for (int bb = 0; bb < NB; ++bb) {
-                                        if (bb >= b && live[bb]) {
-                                            const double gc = (double)grow[bb * 32 + lane] - csf * cs[bb] * inv_n;
-                                            if (bb > b || lane > f) r[bb] = fma(-gc, dbf, r[bb]);
-                                        }
-                                    }
-                                    if (lane == 0) {
-                                        ml.idx[nnz] = b * 32 + f; ml.db[nnz] = dbf; ml.aux[nnz] = csf;
-                                        // publish to the worker CTAs: {payload32, seq32} words, any order, no fence
-                                        const unsigned long long dbb = (unsigned long long)__double_as_longlong(dbf);
-                                        const unsigned long long kkb = (unsigned long long)__double_as_longlong(dbf * mf);
-                                        unsigned long long* ew = llw + 1 + kLLEntryWords * nnz;
-                                        st_relaxed_u64(ew + 0, seqhi | (unsigned long long)(uint32_t)(b * 32 + f));
-                                        st_relaxed_u64(ew + 1, seqhi | (dbb & 0xffffffffull));
-                                        st_relaxed_u64(ew + 2, seqhi | (dbb >> 32));
-                                        st_relaxed_u64(ew + 3, seqhi | (kkb & 0xffffffffull));
-                                        st_relaxed_u64(ew + 4, seqhi | (kkb >> 32));
-                                    }
-                                    ++nnz;
-                                    start = f + 1;
+                                for (int i = 0; i < 2; ++i) {
+                                    const double dl = fma(cB[i], rr[i] * rr[i], cA[i]);
+                                    bnv[i] = fma(rr[i], cC[i], cQ[i]);                  // evaluated alongside the inclusion test
+                                    inv[i] = dl < cT[i];                                // NaN -> excluded, like rand() < NaN
+                                    const bool ch = inv[i] ? (bnv[i] != bold[i]) : bnz[i];      // effect changes <=> beta_new - beta_old != 0
+                                    mk[i] = __ballot_sync(0xffffffffu, (32 * i + lane >= pos) && ch);
                                 }
+                                const int ci = mk[0] ? 0 : 1;                           // slot of the first marker whose effect changes
+                                const unsigned mm = mk[0] ? mk[0] : mk[1];
+                                const int f = mm ? (__ffs(mm) - 1) : 32;
+                                const int last = mm ? 32 * ci + f : 63;                 // commit markers [pos, last]
+#pragma unroll
+                                for (int i = 0; i < 2; ++i) {
+                                    const int mi = 32 * i + lane;
+                                    if (mi >= pos && mi <= last) { bnew[i] = inv[i] ? bnv[i] : 0.0; inc[i] = inv[i]; }
+                                }
+                                if (!mm) break;
+                                const double mydb = ci ? ((inv[1] ? bnv[1] : 0.0) - bold[1]) : ((inv[0] ? bnv[0] : 0.0) - bold[0]);
+                                const double dbf = __shfl_sync(0xffffffffu, mydb, f);
+                                const double csf = __shfl_sync(0xffffffffu, ci ? cs[1] : cs[0], f);
+                                const int ka = (32 * ci + f) / B, qa = (32 * ci + f) % B;
+                                // restore the later markers of the step: Gram row of (block ka, column qa) against their block
+#pragma unroll
+                                for (int i = 0; i < 2; ++i) {
+                                    if (32 * i + lane > last) {
+                                        const double gc = (double)gram[i][(kb[i] - ka) * B * B + qa * B + qb[i]] - csf * cs[i] * inv_n;
+                                        rr[i] = fma(-gc, dbf, rr[i]);
+                                    }
+                                }
+                                if (lane == 0) {
+                                    NzList& ml = cnz[(g0 + (unsigned)ka) & (kNzRing - 1)];
+                                    int at = 0;
+#pragma unroll
+                                    for (int k = 0; k < SB; ++k) if (k == ka) at = nn[k];
+                                    ml.idx[at] = qa; ml.db[at] = dbf; ml.aux[at] = csf;
+                                }
+#pragma unroll
+                                for (int k = 0; k < SB; ++k) if (k == ka) nn[k]++;
+                                pos = last + 1;
                             }
                             NGP_TICK(17);
+                            // hand the step over: lists (prep warps, helper warp), new effects and indicators (helper warp)
+                            const int os = (int)(sg & (kPrepWarps - 1));
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) { out_b[os * 64 + 32 * i + lane] = bnew[i]; out_i[os * 64 + 32 * i + lane] = inc[i] ? 1 : 0; }
                             if (lane == 0) {
-                                st_relaxed_u64(llw, seqhi | (unsigned long long)(uint32_t)nnz);
-                                ml.nnz = nnz;
+#pragma unroll
+                                for (int k = 0; k < SB; ++k) cnz[(g0 + (unsigned)k) & (kNzRing - 1)].nnz = nn[k];
                             }
                             __syncwarp();
                             if (lane == 0) {
-                                mbar_arrive(&nzc_full[gidx & (kNzRing - 1)]);
-                                mbar_arrive(&rb_free[rs]);
+                                *cprog = g0 + (unsigned)SB;                     // prep warps skip the barriers of lists known to be complete
+                                mbar_arrive(&step_done[os]);
+#pragma unroll
+                                for (int k = 0; k < SB; ++k) mbar_arrive(&nzc_full[(g0 + (unsigned)k) & (kNzRing - 1)]);
+                            }
+                            if constexpr (PROF) {
+#pragma unroll
+                                for (int k = 0; k < SB; ++k) pf[6] += nn[k];
+                                if (lane == 0) step_end_clk[sg & 63u] = clock64();
                             }
                             NGP_TICK(18);
-                            // outputs of the block (plain coalesced stores, fire and forget)
-#pragma unroll
-                            for (int b = 0; b < NB; ++b) {
-                                const int q = b * 32 + lane;
-                                const int64_t j = (int64_t)m * B + q;
-                                if (live[b]) {
-                                    acc_bb = fma(bnew[b], bnew[b], acc_bb);
-                                    if (method != 0) acc_n += inc[b] ? 1.0 : 0.0;
-                                    if (j < p_real) {
-                                        beta_g[j] = bnew[b];
-                                        if (method != 0) delta_g[j] = inc[b] ? 1 : 0;
-                                        if (method == 1)                                    // functions.jl:182,186
-                                            vb_g[j] = inc[b] ? (sdf + bnew[b] * bnew[b]) / cst[F_CHI * B + q] : 0.0;
-                                    }
-                                }
-                            }
-                            if constexpr (PROF) pf[6] += nnz;
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&rec_free[rcs]);     // the record (Gram rows, constants) is no longer needed
-                            NGP_TICK(19);
                         }
                     } else if (warp == 1) {
                         // ------------------------------------------------------------------ TMA producer of the block records
                         if (lane == 0) {
                             fence_proxy_async();     // consts were written through the generic proxy by other CTAs
-                            const uint32_t gbytes = (uint32_t)((1 + DN) * gram_bytes(B)), cbytes = (uint32_t)consts_bytes(B);
+                            const uint32_t gbytes = (uint32_t)gofs, cbytes = (uint32_t)consts_bytes(B);
                             for (int m = 0; m < nblk; ++m) {
                                 if (recs_issued >= (unsigned)NR) mbar_wait(&rec_free[r_rec.s], r_rec.ph ^ 1u);
                                 unsigned char* dst = recs + r_rec.s * L.rec_bytes;
@@ -730,6 +831,8 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         int m0 = (int)((unsigned)(pw - (int)(gblk & (kPrepWarps - 1))) & (kPrepWarps - 1));   // first m with (gblk+m) % kPrepWarps == pw
                         for (int m = m0; m < nblk; m += kPrepWarps) {
                             const unsigned gidx = gblk + (unsigned)m;
+                            const unsigned sg = gidx >> SBS;
+                            const int ss = (int)(sg & (RBS - 1));
                             if (warp == kFirstPrepWarp) if constexpr (PROF) tc = clock64();
                             double far[NB], cs[NB], mean[NB];
                             bool live[NB];
@@ -742,39 +845,15 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                 mean[b] = __ldg(&S.mean[j]);
                                 far[b] = 0.0;
                             }
-                            // poll the accumulators of block m until all Tw worker CTAs have added their partial sums
-                            const int slot = (int)(gidx & (kSlots - 1));
-                            const long long* acc = sy->acc + slot * kMaxB;
-                            long long cur[NB];
-#pragma unroll
-                            for (int b = 0; b < NB; ++b) cur[b] = 0;
-                            if (!(dbg & 2)) {
-                                bool done;
-                                do {
-                                    done = true;
-#pragma unroll
-                                    for (int b = 0; b < NB; ++b) {
-                                        const int q = b * 32 + lane;
-                                        if (live[b]) {
-                                            cur[b] = ld_relaxed_s64(acc + q);
-                                            done = done && (((cur[b] - prev[slot * B + q]) & 0xFF) == (long long)Tw);
-                                        }
-                                    }
-                                } while (!__all_sync(0xffffffffu, done));
-                            }
-                            if (warp == kFirstPrepWarp) NGP_TICK(13);
-                            // cross-Gram corrections of distance >= 2, oldest block first:
-                            //   blocks m-D .. m-DN-1: rows fetched on demand from HBM/L2;  blocks m-DN .. m-2: rows from the block record
+                            // cross-Gram corrections from the blocks before the previous step, oldest block first:
+                            //   distances > DN: rows fetched on demand from HBM/L2;  distances <= DN: rows from the block record
                             bool have_rec = false;
                             const unsigned rcs = gidx & (unsigned)(NR - 1);
                             const uint32_t rcp = (gidx / (unsigned)NR) & 1u;
                             const int32_t* gram = reinterpret_cast<const int32_t*>(recs + rcs * L.rec_bytes);
-                            for (int sblk = max(0, m - D); sblk <= m - 2; ++sblk) {
-                                const unsigned gs_ = gblk + (unsigned)sblk;
-                                mbar_wait(&nzc_full[gs_ & (kNzRing - 1)], (gs_ / kNzRing) & 1u);
-                                const NzList& pl = cnz[gs_ & (kNzRing - 1)];
+                            auto apply_list = [&](int sblk) {
+                                const NzList& pl = cnz[(gblk + (unsigned)sblk) & (kNzRing - 1)];
                                 const int np = pl.nnz;
-                                if (np == 0) continue;
                                 const int d = m - sblk;
                                 if (d > DN) {
                                     const int32_t* gd = gx_g + (size_t)m * gx_blk + (size_t)d * B * B;
@@ -804,10 +883,87 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                             if (live[b]) far[b] = fma(-((double)gd[a * B + b * 32 + lane] - csf * cs[b] * inv_n), dbf, far[b]);
                                     }
                                 }
+                            };
+                            const int s_first = max(0, m - D);
+                            const int s_last = (m & ~(SB - 1)) - SB - 1;          // last block whose list is not the chain warp's business
+                            // pass 1, without blocking: the lists the chain warp has already completed (one ballot finds the non-empty ones)
+                            int s_next = s_first;
+                            {
+                                const int done = (int)(*cprog - gblk);              // blocks of this sweep with complete lists
+                                const int avail = min(s_last, done - 1);
+                                const int sb_ = s_first + lane;
+                                const bool has = (sb_ <= avail) && (cnz[(gblk + (unsigned)sb_) & (kNzRing - 1)].nnz > 0);
+                                unsigned msk = __ballot_sync(0xffffffffu, has);
+                                // the far rows of all these lists are prefetched together (one 128-byte line per changed marker and
+                                // 32 columns), so that the in-order accumulation below does not pay one L2 round trip per list
+                                for (unsigned mp = msk; mp; mp &= mp - 1) {
+                                    const int sb2 = s_first + __ffs(mp) - 1, d2 = m - sb2;
+                                    if (d2 > DN) {
+                                        const NzList& pl = cnz[(gblk + (unsigned)sb2) & (kNzRing - 1)];
+                                        const int32_t* gd = gx_g + (size_t)m * gx_blk + (size_t)d2 * B * B;
+                                        const int np = pl.nnz;
+                                        for (int e = 0; e < np; ++e)
+#pragma unroll
+                                            for (int b = 0; b < NB; ++b)
+                                                if (live[b]) asm volatile("prefetch.global.L1 [%0];" ::"l"(gd + pl.idx[e] * B + b * 32 + lane));
+                                    }
+                                }
+                                while (msk) { const int l = __ffs(msk) - 1; msk &= msk - 1; apply_list(s_first + l); }
+                                if (avail >= s_first) s_next = avail + 1;
+                            }
+                            // poll the accumulators of block m until all Tw worker CTAs have added their partial sums
+                            const int slot = (int)(gidx & (kSlots - 1));
+                            const long long* acc = sy->acc + (size_t)slot * kMaxB * kAccStride;
+                            long long cur[NB];
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) cur[b] = 0;
+                            if (!(dbg & 2)) {
+                                // pipelined like the list polling of the worker CTAs: kPollPipe probes in flight, kPollGap cycles apart
+                                long long pv_[kPollPipe][NB];
+                                bool pvalid[kPollPipe];
+#pragma unroll
+                                for (int i = 0; i < kPollPipe; ++i) pvalid[i] = false;
+                                long long t_issue = clock64() - kPollGap;
+                                for (;;) {
+                                    bool done = pvalid[0];
+#pragma unroll
+                                    for (int b = 0; b < NB; ++b) {
+                                        cur[b] = pv_[0][b];
+                                        if (live[b] && pvalid[0]) done = done && (((cur[b] - prev[slot * B + b * 32 + lane]) & 0xFF) == (long long)Tw);
+                                    }
+                                    const bool valid0 = pvalid[0];
+#pragma unroll
+                                    for (int i = 0; i + 1 < kPollPipe; ++i) {
+                                        pvalid[i] = pvalid[i + 1];
+#pragma unroll
+                                        for (int b = 0; b < NB; ++b) pv_[i][b] = pv_[i + 1][b];
+                                    }
+                                    if (valid0 && __all_sync(0xffffffffu, done)) break;
+                                    while (clock64() - t_issue < kPollGap) { }
+                                    t_issue = clock64();
+#pragma unroll
+                                    for (int b = 0; b < NB; ++b) pv_[kPollPipe - 1][b] = live[b] ? ld_relaxed_s64(acc + (b * 32 + lane) * kAccStride) : 0;
+                                    pvalid[kPollPipe - 1] = true;
+                                }
+                            }
+                            if (warp == kFirstPrepWarp) NGP_TICK(13);
+                            if constexpr (PROF) {
+                                // loop latency: end of the chain step that released the dots of block m -> their sums are complete
+                                if (warp == kFirstPrepWarp && m - D - 1 >= 0) {
+                                    const long long lat = clock64() - step_end_clk[((gblk + (unsigned)(m - D - 1)) >> SBS) & 63u];
+                                    pf[21] += lat; pf[22] += 1; if (lat > pf[23]) pf[23] = lat;
+                                    pf[30] += (long long)(global_ns() - pub_ns[(gblk + (unsigned)(m - D - 1)) & (kNzRing - 1)]); pf[31] += 1;
+                                }
+                            }
+                            // pass 2: the remaining lists, as the chain warp completes them
+                            for (int sblk = s_next; sblk <= s_last; ++sblk) {
+                                const unsigned gs_ = gblk + (unsigned)sblk;
+                                mbar_wait(&nzc_full[gs_ & (kNzRing - 1)], (gs_ / kNzRing) & 1u);
+                                if (cnz[gs_ & (kNzRing - 1)].nnz > 0) apply_list(sblk);
                             }
                             if (!have_rec) mbar_wait(&rec_full[rcs], rcp);     // the chain warp relies on it
                             if (warp == kFirstPrepWarp) NGP_TICK(12);
-                            if (rb_uses > 0) mbar_wait(&rb_free[pw], (rb_uses - 1) & 1u);
+                            if (sg >= (unsigned)RBS) mbar_wait(&rb_free[ss], ((sg / RBS) - 1u) & 1u);      // the helper warp is done with the slot
 #pragma unroll
                             for (int b = 0; b < NB; ++b) {
                                 const int q = b * 32 + lane;
@@ -815,12 +971,80 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                     long long* pv = prev + slot * B + q;
                                     const double A = (double)((cur[b] - *pv - (long long)Tw) >> kCntBits) * fx_inv;
                                     if (!(dbg & 2)) *pv = cur[b];
-                                    rbase[pw * B + q] = (A - mean[b] * Stot) + far[b];       // x_q'e as the dots saw it + corrections of distance >= 2
+                                    rbase[pw * B + q] = (A - mean[b] * Stot) + far[b];       // x_q'e as the dots saw it + the corrections above
                                 }
                             }
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&rb_full[pw]);
-                            ++rb_uses;
+                            if (lane == 0) mbar_arrive(&rb_full[ss]);
+                        }
+                    } else if (warp == kHelperWarp) {
+                        // ------------------------------------------------------------------ helper warp: publish the lists, write the outputs
+                        double* const beta_g = S.beta;
+                        int32_t* const delta_g = S.delta;
+                        double* const vb_g = S.varBeta;
+                        const double sdf = S.scale * S.df;
+                        int kb[2], qb[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) { kb[i] = (32 * i + lane) / B; qb[i] = (32 * i + lane) % B; }
+                        for (int s0 = 0; s0 < nblk; s0 += SB) {
+                            const unsigned g0 = gblk + (unsigned)s0;
+                            const unsigned sg = g0 >> SBS;
+                            const int os = (int)(sg & (kPrepWarps - 1));
+                            mbar_wait(&step_done[os], (sg / kPrepWarps) & 1u);
+                            // changed effects -> worker CTAs: {payload32, seq32} words, any order, no fence
+#pragma unroll
+                            for (int k = 0; k < SB; ++k) {
+                                const unsigned gk = g0 + (unsigned)k;
+                                const NzList& ml = cnz[gk & (kNzRing - 1)];
+                                const int nnz = ml.nnz;
+                                const size_t lofs = (size_t)(gk & (kNzRing - 1)) * kLLSlotWords;
+                                const unsigned long long seqhi = (unsigned long long)(seq0 + gk + 1u) << 32;
+                                const double* cm = reinterpret_cast<const double*>(recs + (gk & (unsigned)(NR - 1)) * L.rec_bytes + gofs) + F_MEAN * B;
+                                // (entry, replica) pairs are spread over the lanes; the header of a replica goes last (any order is fine)
+                                for (int x = lane; x < nnz * kLLCopies; x += 32) {
+                                    const int e = x / kLLCopies, cpy_ = x % kLLCopies;
+                                    const int q = ml.idx[e];
+                                    const double dbf = ml.db[e];
+                                    const unsigned long long dbb = (unsigned long long)__double_as_longlong(dbf);
+                                    const unsigned long long kkb = (unsigned long long)__double_as_longlong(dbf * cm[q]);
+                                    unsigned long long* ew = sy->ll[cpy_] + lofs + 1 + kLLEntryWords * e;
+                                    st_relaxed_u64(ew + 0, seqhi | (unsigned long long)(uint32_t)q);
+                                    st_relaxed_u64(ew + 1, seqhi | (dbb & 0xffffffffull));
+                                    st_relaxed_u64(ew + 2, seqhi | (dbb >> 32));
+                                    st_relaxed_u64(ew + 3, seqhi | (kkb & 0xffffffffull));
+                                    st_relaxed_u64(ew + 4, seqhi | (kkb >> 32));
+                                }
+                                if (lane < kLLCopies) st_relaxed_u64(sy->ll[lane] + lofs, seqhi | (unsigned long long)(uint32_t)nnz);
+                                if constexpr (PROF) {
+                                    const unsigned long long tn = global_ns();
+                                    if (lane == 0) pub_ns[gk & (kNzRing - 1)] = tn;
+                                    if (lane < kLLCopies) st_relaxed_u64(sy->ll[lane] + lofs + kLLSlotWords - 1, seqhi | (tn & 0xffffffffull));
+                                }
+                            }
+                            // outputs of the step (plain coalesced stores)
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const unsigned gk = g0 + (unsigned)kb[i];
+                                const int64_t j = (int64_t)(s0 + kb[i]) * B + qb[i];
+                                const double bn = out_b[os * 64 + 32 * i + lane];
+                                const bool in = out_i[os * 64 + 32 * i + lane] != 0;
+                                acc_bb = fma(bn, bn, acc_bb);
+                                if (method != 0) acc_n += in ? 1.0 : 0.0;
+                                if (j < p_real) {
+                                    beta_g[j] = bn;
+                                    if (method != 0) delta_g[j] = in ? 1 : 0;
+                                    if (method == 1) {                                      // functions.jl:182,186
+                                        const double chi = reinterpret_cast<const double*>(recs + (gk & (unsigned)(NR - 1)) * L.rec_bytes + gofs)[F_CHI * B + qb[i]];
+                                        vb_g[j] = in ? (sdf + bn * bn) / chi : 0.0;
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                            if (lane == 0) {
+#pragma unroll
+                                for (int k = 0; k < SB; ++k) mbar_arrive(&rec_free[(g0 + (unsigned)k) & (unsigned)(NR - 1)]);
+                                mbar_arrive(&rb_free[(int)(sg & (RBS - 1))]);
+                            }
                         }
                     }
                 }
@@ -835,7 +1059,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     const int k = (int)(j / B), q = (int)(j % B);
                     const uint8_t* tile = S.geno + ((int64_t)t * nblk + k) * L.tile_bytes;
                     const int slot = (int)(rk & (kSlots - 1));
-                    long long* acc = sy->acc + slot * kMaxB;
+                    long long* acc = sy->acc + (size_t)slot * kMaxB * kAccStride;
                     uint32_t w0 = 0;
                     double a = 0.0, dummy = 0.0;
                     if (!is_chain) {
@@ -902,7 +1126,8 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 
             // ------------------------------------------------------------------ phase 3 (chain CTA)
             const bool regional = (S.method == 0 && S.n_regions > 1);
-            if (is_chain && warp == 0 && !regional) {
+            const int p3warp = (P.kernel == 0) ? kHelperWarp : 0;     // the warp that accumulated beta'beta and nLoci
+            if (is_chain && warp == p3warp && !regional) {
                 const double bb = warp_sum(acc_bb);
                 const double nl = warp_sum(acc_n);
                 if (lane == 0) {
@@ -968,8 +1193,9 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         // thread 0 = updater (worker CTA) / chain warp (chain CTA); first dot warp; first prep warp
         const bool dotlane = !is_chain && tid == kFirstDotWarp * 32, preplane = is_chain && tid == kFirstPrepWarp * 32;
         for (int i = 0; i < kProf; ++i) {
-            const bool dot_i = (i == 1 || i == 14 || i == 15 || i == 20), prep_i = (i == 12 || i == 13);
-            if (tid == 0 && !(dot_i && !is_chain) && !(prep_i && is_chain)) sy->prof[t * kProf + i] = pf[i];
+            const bool dot_i = (i == 1 || i == 14 || i == 15 || i == 20 || i == 28 || i == 29), poll_i = (i == 24 || i == 25), prep_i = (i == 12 || i == 13 || (i >= 21 && i <= 23) || i >= 30);
+            if (tid == 0 && !((dot_i || poll_i) && !is_chain) && !(prep_i && is_chain)) sy->prof[t * kProf + i] = pf[i];
+            if (!is_chain && tid == kPollWarp * 32 && poll_i) sy->prof[t * kProf + i] = pf[i];
             if (dotlane && dot_i) sy->prof[t * kProf + i] = pf[i];
             if (preplane && prep_i) sy->prof[t * kProf + i] = pf[i];
         }

@@ -12,9 +12,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nextgp.jl_b200 as ngp  # noqa: E402
 from bench import CONFIGS, SEED0  # noqa: E402
 
-NAMES = ["c_rec_wait", "w_dot", "w_axpy_quant", "c_rbase_wait", "c_load", "x5", "changed_effects", "spec_evals",
-         "phase0", "phase1", "w_list_wait", "phase3", "p_far_corr", "p_acc_poll", "w_tile_wait", "w_combine_red",
-         "c_near_corr", "c_spec_loop", "c_publish", "c_outputs", "x20", "x21", "x22", "x23"]
+NAMES = ["x0", "d_imma", "u_axpy_quant", "c_rbase_wait", "c_load", "u_dotdone_wait", "changed_effects", "spec_evals",
+         "phase0", "phase1", "u_list_wait", "phase3", "p_corrections", "p_acc_poll", "d_version_wait", "d_reduce_red",
+         "c_near1", "c_spec_loop", "c_publish", "c_outputs", "d_tile_wait", "p_looplat_sum", "p_looplat_n", "p_looplat_max",
+         "l_poll_ns", "l_poll_n", "l_upd_ns", "l_upd_n", "l_dot_ns", "l_dot_n", "l_acc_ns", "l_acc_n"]
+# u_* updater warp 0, d_* first dot warp (handles every 8th block) of a worker CTA; c_* chain warp, p_* first prep warp (every 8th block)
 
 
 def main():
@@ -51,10 +53,18 @@ def main():
             rec["varE"] = st["varE"]
             nblk = (p + t["block"] - 1) // t["block"]
             w, c = pr[:-1], pr[-1]           # worker CTAs, chain CTA
-            rec["worker_per_block_mean_cycles"] = {k: float(w[:, i].mean()) / nblk for i, k in enumerate(NAMES) if k.startswith("w_") or k.startswith("phase")}
-            rec["worker_per_block_max_cycles"] = {k: float(w[:, i].max()) / nblk for i, k in enumerate(NAMES) if k.startswith("w_")}
+            rec["worker_per_block_mean_cycles"] = {k: float(w[:, i].mean()) / nblk for i, k in enumerate(NAMES) if k[:2] in ("u_", "d_") or k.startswith("phase")}
+            rec["worker_per_block_max_cycles"] = {k: float(w[:, i].max()) / nblk for i, k in enumerate(NAMES) if k[:2] in ("u_", "d_")}
+            rec["loop_latency_cycles"] = {"mean": float(c[21] / max(c[22], 1)), "max": float(c[23]), "samples": int(c[22])}
+            rec["ns_since_list_published"] = {"list_received_by_poll_warp": float(w[:, 24].sum() / max(w[:, 25].sum(), 1)),
+                                              "residual_version_ready": float(w[:, 26].sum() / max(w[:, 27].sum(), 1)),
+                                              "dots_of_block_plus_D_plus_1_red": float(w[:, 28].sum() / max(w[:, 29].sum(), 1)),
+                                              "their_sums_complete_in_chain_cta": float(c[30] / max(c[31], 1))}
             rec["chain_cta_per_block_cycles"] = {k: float(c[i]) / nblk for i, k in enumerate(NAMES) if k[0] in "cp" or k in ("changed_effects", "spec_evals")}
         out["iters"].append(rec)
+    tr = s.trace()
+    nst = min(2048, (p + 63) // 64)
+    out["chain_trace"] = {"step_start_delta": np.diff(tr[:nst, 0]).tolist(), "wait": tr[:nst, 1].tolist()}
     out["geometry"] = s.timing()
     print(json.dumps(out, indent=1))
 
