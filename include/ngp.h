@@ -70,9 +70,7 @@ enum ngp_config_key {
     NGP_CFG_NEAR = 6,          /* cross-Gram distances kept in the chain CTA's block record (0 = auto) */
                                /* keys 1..6 must be set before the first upload             */
     NGP_CFG_PROFILE = 7,       /* 1 = launch the instrumented kernel (cycle counters for ngp_get_profile) */
-    NGP_CFG_REFETCH = 9,       /* 1 = release a genotype tile right after its dots and re-read the (few) changed columns from L2 for
-                                  the residual update: the tile ring no longer limits the look-ahead (set before the first upload) */
-    NGP_CFG_VERSIONS = 10,     /* versions of the fixed-point residual kept per worker CTA (0 = auto; before the first upload) */
+    NGP_CFG_VERSIONS = 9,      /* versions of the fixed-point residual kept per worker CTA (0 = auto; before the first upload) */
     NGP_CFG_DEBUG = 8          /* timing experiments that decouple the kernel's roles; RESULTS ARE INVALID when non-zero */
 };
 

@@ -204,7 +204,7 @@ struct ngp_handle {
     // geometry
     int64_t n = 0;
     int Tw = 0, R = 0, B = 0, D = 0, DN = 0, NT = 0, NR = 0, NV = 0;      // worker CTAs (grid = Tw + 1), rows per panel, block, look-ahead, near depth, tile stages
-    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0, cfg_refetch = 0, cfg_versions = 0;
+    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0, cfg_versions = 0;
     SmemLayout L{};
     // model
     SetHost sets[NGP_MAX_SETS];
@@ -363,9 +363,6 @@ int ngp_configure(ngp_handle* h, int key, int64_t value)
         if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: residual versions must be set before the first upload");
         if (value < 0 || value > kLimbVers || value == 1) return fail(h, NGP_EINVAL, "ngp_configure: residual versions must be 0 (auto) or in [2,%d]", kLimbVers);
         h->cfg_versions = (int)value; return NGP_OK;
-    case NGP_CFG_REFETCH:
-        if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: refetch mode must be set before the first upload");
-        h->cfg_refetch = value ? 1 : 0; return NGP_OK;
     case NGP_CFG_DEBUG:
         h->cfg_debug = (int)value; return NGP_OK;
     case NGP_CFG_PROFILE:
@@ -412,15 +409,15 @@ static int choose_geometry(ngp_handle* h, int64_t n)
     if (R > maxR)
         return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA; block %d supports at most %lld (use block 16 for up to %d)",
                     (long long)n, (long long)R, B, (long long)maxR, 4 * kUpdThreads * kUpdGroups);
-    const int dn_min = 2 * (64 / B) - 1;           // the chain warp steps over 64 markers: distances inside two steps come from the records
+    const int dn_min = 2 * ((B == 16 ? 32 : 64) / B) - 1;    // the chain warp steps over 64 markers (32 for blocks of 16): distances inside two steps come from the records
     int DN = std::max(dn_min, h->cfg_near ? h->cfg_near : 0);
-    int D = h->cfg_lookahead ? h->cfg_lookahead : h->cfg_refetch ? (B == 64 ? 10 : B == 32 ? 20 : kMaxD) : (B == 64 ? 6 : B == 32 ? 13 : 20);
+    int D = h->cfg_lookahead ? h->cfg_lookahead : (B == 64 ? 6 : B == 32 ? 13 : 20);
     D = std::min(D, kNzRing - 2);
     for (;; ) {
         if (D < dn_min) break;
         DN = std::max(dn_min, std::min(DN, D));
-        const int nt_min = h->cfg_refetch ? 2 : D + 2;     // resident mode: a tile stays in smem until its block has been applied to e
-        int NT = h->cfg_tile_stages ? std::max(h->cfg_tile_stages, nt_min) : h->cfg_refetch ? kDotWarps + 6 : D + 4;     // a tile stays resident until its block has been applied to e
+        const int nt_min = D + 2;     // a tile stays in smem until its block has been applied to e
+        int NT = h->cfg_tile_stages ? std::max(h->cfg_tile_stages, nt_min) : D + 4;     // a tile stays resident until its block has been applied to e
         // shrink the record ring of the chain CTA, the tile ring, then the look-ahead, until both CTA roles fit
         for (;;) {
             for (int NR = kRecStages; NR >= 2; NR >>= 1) {
@@ -812,7 +809,7 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     P.mu_lhs0 = h->mu_lhs0; P.mu_rhs0 = h->mu_rhs0; P.varE_in = varE_in; P.n_iter = n_iter; P.replay = h->replay;
     P.replay_base = h->replay_base; P.rp_chi2_e = h->rp_chi2_e; P.rp_z_mu = h->rp_z_mu;
     P.key0 = (uint32_t)(h->seed & 0xffffffffu); P.key1 = (uint32_t)(h->seed >> 32); P.chain = h->chain; P.accumulate = accumulate;
-    P.debug = h->cfg_debug; P.refetch = h->cfg_refetch;
+    P.debug = h->cfg_debug;
 #define NGP_PICK(PROF, DBG) ((h->B == 64) ? (const void*)gibbs_kernel<64, PROF, DBG> : (h->B == 32) ? (const void*)gibbs_kernel<32, PROF, DBG> : (const void*)gibbs_kernel<16, PROF, DBG>)
     const void* kfn = h->cfg_debug ? NGP_PICK(false, true) : h->cfg_profile ? NGP_PICK(true, false) : NGP_PICK(false, false);
 #undef NGP_PICK

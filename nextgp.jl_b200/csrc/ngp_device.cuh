@@ -124,7 +124,6 @@ struct Params {
     int32_t accumulate;        // add to posterior sums
     uint32_t gblk0;            // global number of the first block of this launch (lists and accumulator slots are numbered globally)
     int32_t debug;             // timing experiments (NGP_CFG_DEBUG), see ngp_sweep.cuh
-    int32_t refetch;           // 1: tiles leave smem after their dots, changed columns are re-read from L2 for the axpy
 };
 
 // ----------------------------------------------------------------------------- tile layout

@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NB = (B + 31) / 32;      // markers per lane of a prep warp (lane <-> marker b*32 + lane)
-    constexpr int SB = 64 / B;             // blocks per step of the chain warp (a step = 64 markers, 2 per lane)
+    constexpr int NS = (B == 16) ? 1 : 2;  // markers per lane of a chain step: a step covers SM = 32 NS markers (32 for blocks of 16, else 64)
+    constexpr int SM = 32 * NS;
+    constexpr int SB = SM / B;             // blocks per step of the chain warp (B = 16, 32: 2; B = 64: 1)
     constexpr int SBS = (SB == 1) ? 0 : (SB == 2) ? 1 : 2;
     constexpr int RBS = kPrepWarps / SB;   // super-block slots of the r_base ring
     constexpr int kHelperWarp = kFirstPrepWarp + kPrepWarps;     // chain CTA: publishes the lists and writes the outputs
@@ -221,7 +223,6 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     // timing experiments only (results are garbage): 1 workers ignore the lists, 2 prep warps skip the accumulator poll,
     // 4 chain warp skips corrections + scalar updates, 8 workers skip the dots and the RED
     const int dbg = DBG ? P.debug : 0;
-    const bool refetch = P.refetch != 0;
     double* misc = reinterpret_cast<double*>(smem + L.misc);     // [0..27] block_sum scratch, [32..] scalars, [44] chain progress, [48..] literal-kernel prev
     volatile unsigned* cprog = reinterpret_cast<volatile unsigned*>(misc + 44);     // chain CTA: global number of blocks whose lists are complete
     SyncArea* sy = P.sync;
@@ -266,12 +267,12 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     if (tid == 0) *cprog = 0u;
     if (tid == 0) {
         if (!is_chain) {
-            for (int s = 0; s < NT; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_free[s], P.refetch ? 1 : kUpdWarps); }
+            for (int s = 0; s < NT; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_free[s], kUpdWarps); }
             for (int s = 0; s < kNzSmem; ++s) { mbar_init(&nz_full[s], 1); mbar_init(&nz_free[s], kUpdWarps); }
             for (int s = 0; s < kNzRing; ++s) { mbar_init(&ver_full[s], kUpdWarps); mbar_init(&dot_done[s], 1); }
         } else {
             for (int s = 0; s < kRecStages; ++s) { mbar_init(&rec_full[s], 1); mbar_init(&rec_free[s], 1); }
-            for (int s = 0; s < kPrepWarps; ++s) { mbar_init(&rb_full[s], 64 / B); mbar_init(&rb_free[s], 1); mbar_init(&step_done[s], 1); }
+            for (int s = 0; s < kPrepWarps; ++s) { mbar_init(&rb_full[s], ((B == 16) ? 32 : 64) / B); mbar_init(&rb_free[s], 1); mbar_init(&step_done[s], 1); }
             for (int s = 0; s < kNzRing; ++s) mbar_init(&nzc_full[s], 1);
         }
         fence_mbar_init();
@@ -430,11 +431,8 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                     }
                                 }
                                 if (tid == 0) NGP_TICK(5);
-                                // one 32-bit word = the 4 codes of this thread's rows.  Resident mode: the tile is still in shared memory.
-                                // Refetch mode: the stage was released right after the dots and the words of the changed columns come
-                                // back from L2 (the tile was streamed D+1 blocks ago) - the tile ring is then independent of D.
-                                const uint32_t* tw = refetch ? reinterpret_cast<const uint32_t*>(gbase + (int64_t)ja * L.tile_bytes)
-                                                             : reinterpret_cast<const uint32_t*>(tiles + r_ta.s * L.tile_bytes);
+                                // the tile is still resident in shared memory: one 32-bit word = the 4 codes of this thread's rows
+                                const uint32_t* tw = reinterpret_cast<const uint32_t*>(tiles + r_ta.s * L.tile_bytes);
 #pragma unroll
                                 for (int k = 0; k < UG; ++k) {
                                     const int rg = tid + k * kUpdThreads;
@@ -443,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                         for (int i0 = 0; i0 < nnz; i0 += 4) {
                                             uint32_t w4[4];
 #pragma unroll
-                                            for (int u = 0; u < 4; ++u) w4[u] = (i0 + u < nnz) ? tw[word_off(B, nl.idx[i0 + u], rg)] : 0u;      // generic load: smem or global
+                                            for (int u = 0; u < 4; ++u) w4[u] = (i0 + u < nnz) ? tw[word_off(B, nl.idx[i0 + u], rg)] : 0u;
 #pragma unroll
                                             for (int u = 0; u < 4; ++u)
                                                 if (i0 + u < nnz) {
@@ -472,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             __syncwarp();
                             if (lane == 0) {
                                 mbar_arrive(&ver_full[gidx & (kNzRing - 1)]);
-                                if (!refetch) mbar_arrive(&tile_free[r_ta.s]);
+                                mbar_arrive(&tile_free[r_ta.s]);
                                 if (!(dbg & 1)) mbar_arrive(&nz_free[r_nzw.s]);
                             }
                             r_ta.adv(NT); r_nzw.adv(kNzSmem);
@@ -530,10 +528,6 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                         }
                                     }
                                 }
-                                if (refetch) {
-                                    __syncwarp();
-                                    if (lane == 0) mbar_arrive(&tile_free[tslot]);      // all fragments are in registers: the stage can be refilled
-                                }
                                 if (tid == kFirstDotWarp * 32) NGP_TICK(1);
                                 long long* accg = sy->acc + (size_t)(gidx & (kSlots - 1)) * kMaxB * kAccStride;
 #pragma unroll
@@ -560,10 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             }
                             if constexpr (PROF) { if (tid == kFirstDotWarp * 32 && ja >= 0) { pf[28] += (long long)(global_ns() - pub_ns[(gblk + (unsigned)ja) & (kNzRing - 1)]); pf[29] += 1; } }
                             __syncwarp();
-                            if (lane == 0) {
-                                if (refetch && (dbg & 8)) mbar_arrive(&tile_free[tslot]);
-                                mbar_arrive(&dot_done[gidx & (kNzRing - 1)]);
-                            }
+                            if (lane == 0) mbar_arrive(&dot_done[gidx & (kNzRing - 1)]);
                             tslot += kDotWarps;
                             while (tslot >= NT) { tslot -= NT; tph ^= 1u; }
                             if (tid == kFirstDotWarp * 32) NGP_TICK(15);
@@ -683,11 +674,11 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     const size_t gx_blk = (size_t)(D + 1) * B * B;
                     const int gofs = (1 + DN) * gram_bytes(B);          // constants follow the Gram matrices in a record
                     if (warp == 0) {
-                        // ------------------------------------------------------------------ chain warp: 64 markers per step
+                        // ------------------------------------------------------------------ chain warp: SM = 32 NS markers per step
                         // slot i of a lane = marker mi = 32 i + lane of the step: block kb = mi / B of the step, column qb = mi % B
-                        int kb[2], qb[2];
+                        int kb[NS], qb[NS];
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) { kb[i] = (32 * i + lane) / B; qb[i] = (32 * i + lane) % B; }
+                        for (int i = 0; i < NS; ++i) { kb[i] = (32 * i + lane) / B; qb[i] = (32 * i + lane) % B; }
                         int nn[SB];                                         // changed effects per block of the step
 #pragma unroll
                         for (int k = 0; k < SB; ++k) nn[k] = 0;
@@ -703,13 +694,13 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                 if (lane == 0 && (s0 >> SBS) < 2048) { sy->trace[2 * (s0 >> SBS)] = tc; sy->trace[2 * (s0 >> SBS) + 1] = now_ - tc; }
                             }
                             NGP_TICK(3);
-                            const int32_t* gram[2];
-                            const double* cst[2];
+                            const int32_t* gram[NS];
+                            const double* cst[NS];
                             // rr = x'e + d*beta_old (add-back fused: x'(e + x b) = x'e + d b) is the running quantity; bnz = (beta_old != 0)
-                            double rr[2], bold[2], cs[2], bnew[2], cA[2], cB[2], cT[2], cC[2], cQ[2];
-                            bool inc[2], bnz[2];
+                            double rr[NS], bold[NS], cs[NS], bnew[NS], cA[NS], cB[NS], cT[NS], cC[NS], cQ[NS];
+                            bool inc[NS], bnz[NS];
 #pragma unroll
-                            for (int i = 0; i < 2; ++i) {
+                            for (int i = 0; i < NS; ++i) {
                                 const unsigned gk = g0 + (unsigned)kb[i];
                                 const unsigned char* rec = recs + (gk & (unsigned)(NR - 1)) * L.rec_bytes;
                                 gram[i] = reinterpret_cast<const int32_t*>(rec);
@@ -733,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                         const int a = pl.idx[e];
                                         const double dbf = pl.db[e], csf = pl.aux[e];
 #pragma unroll
-                                        for (int i = 0; i < 2; ++i)
+                                        for (int i = 0; i < NS; ++i)
                                             rr[i] = fma(-((double)gram[i][(kb[i] + kk) * B * B + a * B + qb[i]] - csf * cs[i] * inv_n), dbf, rr[i]);
                                     }
                                 }
@@ -741,37 +732,37 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             NGP_TICK(16);
 #pragma unroll
                             for (int k = 0; k < SB; ++k) nn[k] = 0;
-                            int pos = (dbg & 4) ? 64 : 0;                       // markers [0, pos) of the step are committed
-                            while (pos < 64) {
+                            int pos = (dbg & 4) ? SM : 0;                       // markers [0, pos) of the step are committed
+                            while (pos < SM) {
                                 if constexpr (PROF) pf[7]++;
-                                double bnv[2];
-                                bool inv[2];
-                                unsigned mk[2];
+                                double bnv[NS];
+                                bool inv[NS];
+                                unsigned mk[NS];
 #pragma unroll
-                                for (int i = 0; i < 2; ++i) {
+                                for (int i = 0; i < NS; ++i) {
                                     const double dl = fma(cB[i], rr[i] * rr[i], cA[i]);
                                     bnv[i] = fma(rr[i], cC[i], cQ[i]);                  // evaluated alongside the inclusion test
                                     inv[i] = dl < cT[i];                                // NaN -> excluded, like rand() < NaN
                                     const bool ch = inv[i] ? (bnv[i] != bold[i]) : bnz[i];      // effect changes <=> beta_new - beta_old != 0
                                     mk[i] = __ballot_sync(0xffffffffu, (32 * i + lane >= pos) && ch);
                                 }
-                                const int ci = mk[0] ? 0 : 1;                           // slot of the first marker whose effect changes
-                                const unsigned mm = mk[0] ? mk[0] : mk[1];
+                                const int ci = (NS == 1 || mk[0]) ? 0 : 1;              // slot of the first marker whose effect changes
+                                const unsigned mm = (NS == 1 || mk[0]) ? mk[0] : mk[NS - 1];
                                 const int f = mm ? (__ffs(mm) - 1) : 32;
-                                const int last = mm ? 32 * ci + f : 63;                 // commit markers [pos, last]
+                                const int last = mm ? 32 * ci + f : SM - 1;                 // commit markers [pos, last]
 #pragma unroll
-                                for (int i = 0; i < 2; ++i) {
+                                for (int i = 0; i < NS; ++i) {
                                     const int mi = 32 * i + lane;
                                     if (mi >= pos && mi <= last) { bnew[i] = inv[i] ? bnv[i] : 0.0; inc[i] = inv[i]; }
                                 }
                                 if (!mm) break;
-                                const double mydb = ci ? ((inv[1] ? bnv[1] : 0.0) - bold[1]) : ((inv[0] ? bnv[0] : 0.0) - bold[0]);
+                                const double mydb = ci ? ((inv[NS - 1] ? bnv[NS - 1] : 0.0) - bold[NS - 1]) : ((inv[0] ? bnv[0] : 0.0) - bold[0]);
                                 const double dbf = __shfl_sync(0xffffffffu, mydb, f);
-                                const double csf = __shfl_sync(0xffffffffu, ci ? cs[1] : cs[0], f);
+                                const double csf = __shfl_sync(0xffffffffu, ci ? cs[NS - 1] : cs[0], f);
                                 const int ka = (32 * ci + f) / B, qa = (32 * ci + f) % B;
                                 // restore the later markers of the step: Gram row of (block ka, column qa) against their block
 #pragma unroll
-                                for (int i = 0; i < 2; ++i) {
+                                for (int i = 0; i < NS; ++i) {
                                     if (32 * i + lane > last) {
                                         const double gc = (double)gram[i][(kb[i] - ka) * B * B + qa * B + qb[i]] - csf * cs[i] * inv_n;
                                         rr[i] = fma(-gc, dbf, rr[i]);
@@ -792,7 +783,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             // hand the step over: lists (prep warps, helper warp), new effects and indicators (helper warp)
                             const int os = (int)(sg & (kPrepWarps - 1));
 #pragma unroll
-                            for (int i = 0; i < 2; ++i) { out_b[os * 64 + 32 * i + lane] = bnew[i]; out_i[os * 64 + 32 * i + lane] = inc[i] ? 1 : 0; }
+                            for (int i = 0; i < NS; ++i) { out_b[os * 64 + 32 * i + lane] = bnew[i]; out_i[os * 64 + 32 * i + lane] = inc[i] ? 1 : 0; }
                             if (lane == 0) {
 #pragma unroll
                                 for (int k = 0; k < SB; ++k) cnz[(g0 + (unsigned)k) & (kNzRing - 1)].nnz = nn[k];
@@ -851,6 +842,15 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             const unsigned rcs = gidx & (unsigned)(NR - 1);
                             const uint32_t rcp = (gidx / (unsigned)NR) & 1u;
                             const int32_t* gram = reinterpret_cast<const int32_t*>(recs + rcs * L.rec_bytes);
+                            // An mbarrier wait only tells the parity of the last completed phase: before waiting for the record of block m
+                            // make sure the previous occupant of its stage (block m - NR) is gone, i.e. that block has been through the chain warp
+                            auto wait_record = [&]() {
+                                if (m >= NR) {
+                                    const unsigned gp = gidx - (unsigned)NR;
+                                    mbar_wait(&nzc_full[gp & (kNzRing - 1)], (gp / kNzRing) & 1u);
+                                }
+                                mbar_wait(&rec_full[rcs], rcp);
+                            };
                             auto apply_list = [&](int sblk) {
                                 const NzList& pl = cnz[(gblk + (unsigned)sblk) & (kNzRing - 1)];
                                 const int np = pl.nnz;
@@ -873,7 +873,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                             }
                                     }
                                 } else {
-                                    if (!have_rec) { mbar_wait(&rec_full[rcs], rcp); have_rec = true; }
+                                    if (!have_rec) { wait_record(); have_rec = true; }
                                     const int32_t* gd = gram + d * B * B;
                                     for (int i = 0; i < np; ++i) {
                                         const int a = pl.idx[i];
@@ -961,7 +961,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                 mbar_wait(&nzc_full[gs_ & (kNzRing - 1)], (gs_ / kNzRing) & 1u);
                                 if (cnz[gs_ & (kNzRing - 1)].nnz > 0) apply_list(sblk);
                             }
-                            if (!have_rec) mbar_wait(&rec_full[rcs], rcp);     // the chain warp relies on it
+                            if (!have_rec) wait_record();     // the chain warp relies on it
                             if (warp == kFirstPrepWarp) NGP_TICK(12);
                             if (sg >= (unsigned)RBS) mbar_wait(&rb_free[ss], ((sg / RBS) - 1u) & 1u);      // the helper warp is done with the slot
 #pragma unroll
@@ -983,9 +983,9 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         int32_t* const delta_g = S.delta;
                         double* const vb_g = S.varBeta;
                         const double sdf = S.scale * S.df;
-                        int kb[2], qb[2];
+                        int kb[NS], qb[NS];
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) { kb[i] = (32 * i + lane) / B; qb[i] = (32 * i + lane) % B; }
+                        for (int i = 0; i < NS; ++i) { kb[i] = (32 * i + lane) / B; qb[i] = (32 * i + lane) % B; }
                         for (int s0 = 0; s0 < nblk; s0 += SB) {
                             const unsigned g0 = gblk + (unsigned)s0;
                             const unsigned sg = g0 >> SBS;
@@ -1023,7 +1023,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             }
                             // outputs of the step (plain coalesced stores)
 #pragma unroll
-                            for (int i = 0; i < 2; ++i) {
+                            for (int i = 0; i < NS; ++i) {
                                 const unsigned gk = g0 + (unsigned)kb[i];
                                 const int64_t j = (int64_t)(s0 + kb[i]) * B + qb[i];
                                 const double bn = out_b[os * 64 + 32 * i + lane];

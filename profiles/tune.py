@@ -29,14 +29,12 @@ def main():
     v_e, v, pi = ngp.synth.priors(prob, model)
     method = 0 if model in ("BayesRR", "BayesPR") else (1 if model == "BayesB" else 2)
     for combo in a.combos.split(","):
-        b, d, nt, dn, dbg, rf, nv = (list(int(x) for x in combo.split(":")) + [0, 0, 0])[:7]
+        b, d, nt, dn, dbg, nv = (list(int(x) for x in combo.split(":")) + [0, 0])[:6]
         t0 = time.time()
         try:
             s = ngp.Sampler(0, block=b, lookahead=d, tile_stages=nt, near=dn, max_ctas=a.max_ctas)
             if nv:
                 s.configure(ngp._lib.CFG_VERSIONS, nv)
-            if rf:
-                s.configure(ngp._lib.CFG_REFETCH, 1)
             if dbg:
                 s.configure(ngp._lib.CFG_DEBUG, dbg)
             s.synth_genotypes(0, n, p, seed, prob["thr0"], prob["thr1"])

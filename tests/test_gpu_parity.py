@@ -92,7 +92,7 @@ CASES = [
 ]
 
 
-def _run_replay(prob, method, kw, kernel, iters, block=0, min_rows=0, intercept=True, lhs0=None, rhs0=None):
+def _run_replay(prob, method, kw, kernel, iters, block=0, min_rows=0, intercept=True, lhs0=None, rhs0=None, max_ctas=0, **geom):
     kw = dict(kw)
     p = prob["codes"].shape[1]
     ro = kw.pop("region_off", None)
@@ -106,7 +106,7 @@ def _run_replay(prob, method, kw, kernel, iters, block=0, min_rows=0, intercept=
         logs.append(ch.iteration(seed=42, chain=1))
         snaps.append(ch.snapshot())
     g = gpu_sampler(prob, method, region_off=ro, kernel=kernel, block=block, min_rows=min_rows, intercept=intercept,
-                    lhs0=lhs0, rhs0=rhs0, **kw)
+                    lhs0=lhs0, rhs0=rhs0, max_ctas=max_ctas, **geom, **kw)
     g.set_replay(logs)
     worst = 0.0
     for it in range(iters):
@@ -138,6 +138,45 @@ def test_replay_parity_ragged_shapes(gpu, n, p, block, min_rows):
     prob = make_problem(n, p, 5 + n)
     _run_replay(prob, 2, dict(v=0.05, pi=0.3, est_pi=True), "blocked", iters=6, block=block, min_rows=min_rows)
     _run_replay(prob, 0, dict(v=0.02), "blocked", iters=4, block=block, min_rows=min_rows)
+
+
+@pytest.mark.parametrize("geom", [dict(lookahead=1, near=1, block=64), dict(lookahead=3, tile_stages=5, versions=2), dict(lookahead=24, block=16),
+                                  dict(lookahead=9, versions=3, near=6), dict(lookahead=6, near=5, block=64),
+                                  dict(profile=True)],
+                         ids=["D1-B64", "D3-2versions", "D24-B16", "D9-near6", "D6-near5-B64", "instrumented"])
+def test_replay_parity_over_pipeline_geometries(gpu, geom):
+    """The look-ahead depth, ring sizes (incl. a 2- or 4-stage record ring), residual-version count and the instrumented variant change the schedule, never the result."""
+    prob = make_problem(1300, 700, 77)
+    geom = dict(geom)
+    block = geom.pop("block", 0)
+    _run_replay(prob, 2, dict(v=0.05, pi=0.2, est_pi=True), "blocked", iters=5, block=block, min_rows=8, **geom)
+    _run_replay(prob, 0, dict(v=0.02), "blocked", iters=3, block=block, min_rows=8, **geom)
+
+
+def test_replay_parity_many_rows_per_cta(gpu):
+    """Few CTAs => > 512 rows per worker CTA => blocks of 16 markers with 4 row groups per updater thread (the C5 / C3 geometry)."""
+    prob = make_problem(3001, 150, 78)
+    for method, kw in ((2, dict(v=0.05, pi=0.3, est_pi=True)), (1, dict(v=0.05, pi=0.3, est_pi=True)), (0, dict(v=0.02))):
+        _run_replay(prob, method, kw, "blocked", iters=4, max_ctas=3)
+    g = gpu_sampler(prob, 2, 0.05, pi=0.3, est_pi=True, max_ctas=3)
+    t = g.timing()
+    assert t["block"] == 16 and t["rows_per_cta"] > 512 and t["ctas"] == 3
+    g.close()
+    with pytest.raises(ngp.NgpError) as ei:        # rows do not fit the register-resident residual of a 32-marker-block CTA
+        gpu_sampler(prob, 2, 0.05, pi=0.3, est_pi=True, max_ctas=3, block=32)
+    assert ei.value.code == L.EUNSUPPORTED
+
+
+def test_profile_and_trace_of_instrumented_kernel(gpu):
+    prob = make_problem(900, 640, 79)
+    g = gpu_sampler(prob, 2, 0.05, pi=0.1, est_pi=True, profile=True)
+    g.set_rng(3, 0)
+    g.run(2)
+    pr, tr = g.profile(), g.trace()
+    t = g.timing()
+    assert pr.shape == (t["ctas"], 32) and (pr[-1, 4] > 0) and (pr[:-1, 2] > 0).all()      # chain warp and every updater warp ticked
+    assert (tr[: 640 // 64, 1] > 0).all() and t["lookahead"] >= 1 and t["record_stages"] in (2, 4, 8)
+    g.close()
 
 
 def test_replay_parity_no_intercept_and_summary_stat_priors(gpu):
