@@ -33,7 +33,8 @@ enum ngp_status {
                        /* the reference drops such columns, prepMatVec.jl:118)*/
     NGP_ERANGE = -4,   /* fixed-point reduction overflow guard tripped       */
     NGP_ENOMEM = -5,
-    NGP_EUNSUPPORTED = -6
+    NGP_EUNSUPPORTED = -6,
+    NGP_ENUMERIC = -7  /* a covariance matrix of the tuple sampler lost positive definiteness */
 };
 
 /* priorVCV[pSet].name dispatch of mme.jl:331,350,362 */
@@ -90,6 +91,24 @@ typedef struct ngp_prior {
     const double* lhs0;          /* p or NULL: M[pSet][:lhs] summary-stat precision (mme.jl:314-322) */
     const double* rhs0;          /* p or NULL: M[pSet][:rhs]                                   */
 } ngp_prior;
+
+/* -------------------------------------------------------------------------
+ * Prior of a TUPLE of marker sets (multi-breed / correlated effects): what
+ * mme.getMME! derives for `(:M1,:M2) => BayesPR(r, V)` (mme.jl:448-489 layout,
+ * :493 df = 3 + k, :501 scale = V .* (df - k - 1), :516 initial varBeta = V).
+ * The member sets share n, p and the region structure; per locus their k effects
+ * are drawn jointly (functions.jl:140-154).  Row-major k x k matrices.
+ * ------------------------------------------------------------------------- */
+typedef struct ngp_joint_prior {
+    int32_t k;                       /* 2..8 member sets                                         */
+    int32_t set_id[NGP_MAX_SETS];    /* uploaded marker sets; breed b = set_id[b] (the tuple replaces them, mme.jl:459) */
+    int32_t pad_;
+    double df;                       /* 3 + k                                                    */
+    const double* scale;             /* [k*k]                                                    */
+    const double* var_init;          /* [k*k] V: initial value of every region's covariance      */
+    int64_t n_regions;               /* length(regionArray) (mme.jl:470-487)                     */
+    const int64_t* region_off;       /* n_regions+1 offsets, 0-based half-open; NULL = one region */
+} ngp_joint_prior;
 
 /* Variate log of n_iter iterations for replay parity: the sampler
  * consumes these instead of its Philox stream.  Layout is row-major
@@ -166,10 +185,17 @@ int ngp_set_residual_prior(ngp_handle* h, double df_e, double scale_e);      /* 
 /* single-column fixed effect of ones (functions.jl:39-47); lhs0/rhs0 = X[xSet][:lhs/:rhs] */
 int ngp_set_intercept(ngp_handle* h, int enabled, double lhs0, double rhs0);
 int ngp_set_prior(ngp_handle* h, int set_id, const ngp_prior* prior);
+/* tuple of marker sets with jointly drawn effects (mme.jl:448-489); at most one tuple per handle, and every
+ * uploaded set of the handle must be a member                                                            */
+int ngp_set_joint_prior(ngp_handle* h, const ngp_joint_prior* prior);
 
 /* ---- variates --------------------------------------------------------------- */
 int ngp_set_rng(ngp_handle* h, uint64_t seed, uint32_t chain_id);            /* Philox4x32-10 key / stream */
 int ngp_set_replay(ngp_handle* h, const ngp_replay* log);                    /* NULL = back to Philox */
+/* variate log of the tuple: z [n_iter][p][k] (MvNormal = mean + chol(C) z, functions.jl:149), Bartlett variates of the
+ * inverse-Wishart draw (functions.jl:515) iw_chi2 [n_iter][n_regions][k], iw_z [n_iter][n_regions][k][k] (strict lower
+ * triangle).  Call after ngp_set_replay (which carries chi2_e / z_mu; its per-set members are ignored for tuple members). */
+int ngp_set_joint_replay(ngp_handle* h, int32_t n_iter, const double* z, const double* iw_chi2, const double* iw_z);
 
 /* ---- sampling ---------------------------------------------------------------
  * ngp_run replaces n_iter trips of the loop body of samplers.runSampler!
@@ -179,6 +205,11 @@ int ngp_run(ngp_handle* h, int32_t n_iter);
  * (samplers.jl:52; functions.jl:118,157,197): host buffers in, mutated in place. */
 int ngp_sweep(ngp_handle* h, int set_id, double* ycorr, double varE,
               double* beta, int64_t* delta, double* varBeta, double* piHat);
+/* ngp_joint_sweep replaces ONE call sampleBayesPR!(mSet::Tuple, M, beta, delta, ycorr, varE, varBeta)
+ * (functions.jl:140-154): beta is k x p row-major (row b = breed b), varBeta is n_regions x k x k.          */
+int ngp_joint_sweep(ngp_handle* h, double* ycorr, double varE, double* beta, double* varBeta);
+/* effects (k x p row-major) and region covariances (n_regions x k x k) of the tuple; NULL members are skipped */
+int ngp_get_joint_state(ngp_handle* h, double* beta, double* varBeta);
 int ngp_get_state(ngp_handle* h, ngp_state* out);
 int ngp_set_state(ngp_handle* h, const ngp_state* in);
 /* running posterior sums since the last reset: sum(beta), sum(beta^2), sum(delta) per marker */

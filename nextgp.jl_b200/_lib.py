@@ -19,7 +19,7 @@ GENO_I8, GENO_F64, GENO_PACKED2 = 0, 1, 2
 STORE_I8, STORE_2BIT = 0, 1
 KERNEL_BLOCKED, KERNEL_LITERAL = 0, 1
 CFG_KERNEL, CFG_BLOCK, CFG_MIN_ROWS, CFG_MAX_CTAS, CFG_LOOKAHEAD, CFG_TILE_STAGES, CFG_NEAR, CFG_PROFILE, CFG_DEBUG, CFG_VERSIONS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
-OK, EINVAL, ECUDA, EDATA, ERANGE, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+OK, EINVAL, ECUDA, EDATA, ERANGE, ENOMEM, EUNSUPPORTED, ENUMERIC = 0, -1, -2, -3, -4, -5, -6, -7
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -35,6 +35,11 @@ class Prior(C.Structure):
     _fields_ = [("method", C.c_int32), ("est_pi", C.c_int32), ("df", C.c_double), ("scale", C.c_double),
                 ("var_init", C.c_double), ("pi_in", C.c_double), ("n_regions", C.c_int64),
                 ("region_off", C.c_void_p), ("lhs0", C.c_void_p), ("rhs0", C.c_void_p)]
+
+
+class JointPrior(C.Structure):
+    _fields_ = [("k", C.c_int32), ("set_id", C.c_int32 * NGP_MAX_SETS), ("pad_", C.c_int32), ("df", C.c_double),
+                ("scale", C.c_void_p), ("var_init", C.c_void_p), ("n_regions", C.c_int64), ("region_off", C.c_void_p)]
 
 
 class Replay(C.Structure):
@@ -100,6 +105,10 @@ _SIGS = {
     "ngp_set_residual_prior": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "ngp_set_intercept": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     "ngp_set_prior": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Prior)]),
+    "ngp_set_joint_prior": (C.c_int, [C.c_void_p, C.POINTER(JointPrior)]),
+    "ngp_set_joint_replay": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ngp_joint_sweep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "ngp_get_joint_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ngp_set_rng": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32]),
     "ngp_set_replay": (C.c_int, [C.c_void_p, C.POINTER(Replay)]),
     "ngp_run": (C.c_int, [C.c_void_p, C.c_int32]),

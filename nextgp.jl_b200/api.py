@@ -320,6 +320,44 @@ class Sampler:
         nvar = (len(region_off) - 1 if region_off is not None else 1) if method == L.BAYESPR else (p if method == L.BAYESB else 1)
         self.sets[set_id].update(method=method, nvar=nvar, est_pi=bool(est_pi))
 
+    def set_joint_prior(self, set_ids: list[int], df: float, scale: np.ndarray, var_init: np.ndarray,
+                        region_off: np.ndarray | None = None) -> None:
+        """(:M1,:M2,...) => BayesPR(r, V): the member sets' effects are drawn jointly per locus (mme.jl:448-489)."""
+        k = len(set_ids)
+        pr = L.JointPrior()
+        pr.k, pr.df = k, df
+        for b, sid in enumerate(set_ids):
+            pr.set_id[b] = sid
+        scale = np.ascontiguousarray(scale, dtype=np.float64).reshape(k, k)
+        var_init = np.ascontiguousarray(var_init, dtype=np.float64).reshape(k, k)
+        pr.scale, pr.var_init = _p(scale), _p(var_init)
+        if region_off is not None:
+            region_off = np.ascontiguousarray(region_off, dtype=np.int64)
+            pr.n_regions, pr.region_off = len(region_off) - 1, _p(region_off)
+        self._ck(self._lib.ngp_set_joint_prior(self._h, C.byref(pr)))
+        self.joint = {"k": k, "sets": list(set_ids), "p": self.sets[set_ids[0]]["p"],
+                      "n_regions": len(region_off) - 1 if region_off is not None else 1}
+
+    def set_joint_replay(self, logs: list[dict]) -> None:
+        """logs: per iteration the oracle's tuple variate log {z [p,k], iw_chi2 [R,k], iw_z [R,k,k]}."""
+        z = np.ascontiguousarray(np.stack([g["z"] for g in logs]), dtype=np.float64)
+        c2 = np.ascontiguousarray(np.stack([g["iw_chi2"] for g in logs]), dtype=np.float64)
+        zl = np.ascontiguousarray(np.stack([g["iw_z"] for g in logs]), dtype=np.float64)
+        self._ck(self._lib.ngp_set_joint_replay(self._h, len(logs), _p(z), _p(c2), _p(zl)))
+
+    def joint_sweep(self, ycorr: np.ndarray, varE: float, beta: np.ndarray, varBeta: np.ndarray) -> None:
+        """sampleBayesPR!(mSet::Tuple, M, beta, delta, ycorr, varE, varBeta): host arrays, mutated in place."""
+        for a in (ycorr, beta, varBeta):
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+        self._ck(self._lib.ngp_joint_sweep(self._h, _p(ycorr), varE, _p(beta), _p(varBeta)))
+
+    def joint_state(self) -> dict:
+        j = self.joint
+        beta = np.empty((j["k"], j["p"]))
+        vb = np.empty((j["n_regions"], j["k"], j["k"]))
+        self._ck(self._lib.ngp_get_joint_state(self._h, _p(beta), _p(vb)))
+        return {"beta": beta, "varBeta": vb}
+
     def set_rng(self, seed: int, chain_id: int = 0) -> None:
         self._ck(self._lib.ngp_set_rng(self._h, C.c_uint64(seed), chain_id))
 

@@ -17,6 +17,7 @@
 
 #include "../../include/ngp.h"
 #include "ngp_sweep.cuh"
+#include "ngp_joint.cuh"
 
 using namespace ngp;
 
@@ -182,7 +183,7 @@ __global__ void debug_variates_kernel(uint32_t key0, uint32_t key1, uint32_t cha
 
 // ============================================================================= handle
 struct SetHost {
-    bool have_geno = false, have_prior = false;
+    bool have_geno = false, have_prior = false, joint_member = false;
     int64_t p = 0, p_pad = 0, nvar = 0, n_regions = 0;
     int method = 0, est_pi = 0, storage = 0;
     double df = 4.0, scale = 0.0, var_init = 0.0, pi_in = 0.0;
@@ -193,6 +194,17 @@ struct SetHost {
     double *lhs0 = nullptr, *rhs0 = nullptr, *sum_beta = nullptr, *sum_beta2 = nullptr, *sum_delta = nullptr;
     int64_t* region_off = nullptr;
     double *rp_u = nullptr, *rp_z = nullptr, *rp_chi2b = nullptr, *rp_betapi = nullptr;
+};
+
+struct JointHost {      // tuple of marker sets with jointly drawn effects (mme.jl:448-489)
+    bool active = false;
+    int k = 0, set[kMaxK] = {0};
+    int64_t p = 0, n_regions = 0;
+    double df = 0.0, scale[kMaxK * kMaxK] = {0.0};
+    double *varBeta = nullptr, *mtm = nullptr;
+    int64_t* region_off = nullptr;
+    double *rp_z = nullptr, *rp_iw_chi2 = nullptr, *rp_iw_z = nullptr;
+    int replay_iters = 0;
 };
 
 struct ngp_handle {
@@ -208,6 +220,7 @@ struct ngp_handle {
     SmemLayout L{};
     // model
     SetHost sets[NGP_MAX_SETS];
+    JointHost joint;
     int n_sets = 0;
     double* e = nullptr;
     bool have_y = false;
@@ -264,6 +277,12 @@ static cudaError_t dalloc(Tp** p, size_t count)
 {
     if (*p) { cudaFree(*p); *p = nullptr; }
     return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(Tp));
+}
+
+static void free_joint(JointHost& j)
+{
+    cudaFree(j.varBeta); cudaFree(j.mtm); cudaFree(j.region_off); cudaFree(j.rp_z); cudaFree(j.rp_iw_chi2); cudaFree(j.rp_iw_z);
+    j = JointHost();
 }
 
 static void free_set(SetHost& s)
@@ -331,6 +350,7 @@ int ngp_destroy(ngp_handle* h)
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (auto& s : h->sets) free_set(s);
+    free_joint(h->joint);
     cudaFree(h->e); cudaFree(h->sc); cudaFree(h->sync); cudaFree(h->sets_dev);
     cudaFree(h->rp_chi2_e); cudaFree(h->rp_z_mu);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -482,6 +502,10 @@ static int begin_upload(ngp_handle* h, int set_id, int64_t n, int64_t p, int sto
         return fail(h, NGP_EINVAL, "all marker sets of a handle must have n = %lld individuals (got %lld)", (long long)h->n, (long long)n);
     }
     SetHost& S = h->sets[set_id];
+    if (S.joint_member) {                       // re-uploading a member dissolves the tuple
+        for (int b = 0; b < h->joint.k; ++b) { h->sets[h->joint.set[b]].joint_member = false; h->sets[h->joint.set[b]].have_prior = false; }
+        free_joint(h->joint);
+    }
     free_set(S);
     S.p = p;
     S.p_pad = ((p + kMaxB - 1) / kMaxB) * kMaxB;
@@ -664,6 +688,8 @@ int ngp_set_prior(ngp_handle* h, int set_id, const ngp_prior* pr)
     if (!h || !pr) return fail(h, NGP_EINVAL, "ngp_set_prior: NULL argument");
     if (set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_geno) return fail(h, NGP_EINVAL, "ngp_set_prior: upload genotypes of set %d first", set_id);
     SetHost& S = h->sets[set_id];
+    if (S.joint_member) return fail(h, NGP_EINVAL, "ngp_set_prior: set %d is a member of a tuple (ngp_set_joint_prior)", set_id);
+    if (h->joint.active) return fail(h, NGP_EUNSUPPORTED, "ngp_set_prior: a handle with a tuple of marker sets samples only the tuple");
     if (pr->method != NGP_BAYESPR && pr->method != NGP_BAYESB && pr->method != NGP_BAYESC) return fail(h, NGP_EINVAL, "ngp_set_prior: unknown method %d", pr->method);
     if (!(pr->df > 0.0) || !(pr->var_init >= 0.0)) return fail(h, NGP_EINVAL, "ngp_set_prior: df must be > 0 and var_init >= 0");
     if (pr->method != NGP_BAYESPR && !(pr->pi_in > 0.0 && pr->pi_in < 1.0)) return fail(h, NGP_EINVAL, "ngp_set_prior: pi_in must be inside (0,1)");
@@ -735,7 +761,7 @@ int ngp_set_replay(ngp_handle* h, const ngp_replay* log)
     else if (h->has_mu) return fail(h, NGP_EINVAL, "ngp_set_replay: z_mu is required when the intercept is enabled");
     for (int s = 0; s < h->n_sets; ++s) {
         SetHost& S = h->sets[s];
-        if (!S.have_geno) continue;
+        if (!S.have_geno || S.joint_member) continue;
         if (!S.have_prior) return fail(h, NGP_EINVAL, "ngp_set_replay: set the prior of set %d first", s);
         if (s >= log->n_sets || !log->z[s] || !log->chi2_b[s]) return fail(h, NGP_EINVAL, "ngp_set_replay: z / chi2_b missing for set %d", s);
         CU(dalloc(&S.rp_z, (size_t)ni * S.p));
@@ -783,9 +809,71 @@ static int sync_sets(ngp_handle* h)
     return NGP_OK;
 }
 
+static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int do_varE, int do_mu, double varE_in, int accumulate)
+{
+    P.n = h->n; P.Tw = h->Tw; P.R = h->R; P.B = h->B; P.n_sets = h->n_sets; P.kernel = h->cfg_kernel;
+    P.D = h->D; P.DN = h->DN; P.NT = h->NT; P.NR = h->NR; P.NV = h->NV;
+    P.e = h->e; P.sets = h->sets_dev; P.sc = h->sc; P.sync = h->sync;
+    P.df_e = h->df_e; P.scale_e = h->scale_e; P.has_mu = h->has_mu; P.do_varE = do_varE; P.do_mu = do_mu; P.set_mask = set_mask;
+    P.mu_lhs0 = h->mu_lhs0; P.mu_rhs0 = h->mu_rhs0; P.varE_in = varE_in; P.n_iter = n_iter; P.replay = h->replay;
+    P.replay_base = h->replay_base; P.rp_chi2_e = h->rp_chi2_e; P.rp_z_mu = h->rp_z_mu;
+    P.key0 = (uint32_t)(h->seed & 0xffffffffu); P.key1 = (uint32_t)(h->seed >> 32); P.chain = h->chain; P.accumulate = accumulate;
+    P.debug = h->cfg_debug;
+}
+
+static int check_kernel_error(ngp_handle* h)
+{
+    int kerr = 0;
+    CU(cpy(h, &kerr, &h->sync->err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (kerr & 2) return fail(h, NGP_ENUMERIC, "a covariance matrix of the tuple sampler is not positive definite");
+    if (kerr) return fail(h, NGP_ERANGE, "fixed-point reduction range exceeded (residual grew by more than 2^4 within an iteration)");
+    return NGP_OK;
+}
+
+// whole iterations (or one sweep) of the tuple sampler: ngp_joint.cuh
+static int launch_joint(ngp_handle* h, int n_iter, int do_varE, int do_mu, double varE_in, int accumulate)
+{
+    CU(cudaSetDevice(h->device));
+    JointHost& Jh = h->joint;
+    if (!Jh.active) return fail(h, NGP_EINVAL, "no tuple of marker sets (ngp_set_joint_prior)");
+    if (!h->have_y) return fail(h, NGP_EINVAL, "no phenotype / residual on the device (ngp_set_phenotype or ngp_joint_sweep)");
+    if (h->replay) {
+        Scalars sc;
+        CU(cpy(h, &sc, h->sc, sizeof sc, cudaMemcpyDeviceToHost));
+        if (sc.iter - h->replay_base + n_iter > h->replay_iters || !Jh.rp_z || Jh.replay_iters != h->replay_iters)
+            return fail(h, NGP_EINVAL, "replay log of the tuple missing or exhausted (ngp_set_joint_replay after ngp_set_replay)");
+    }
+    int rc = sync_sets(h);
+    if (rc) return rc;
+    Params P{};
+    fill_params(h, P, n_iter, 0, do_varE, do_mu, varE_in, accumulate);
+    JointDev J{};
+    J.k = Jh.k; J.stream_set = Jh.set[0]; J.p = Jh.p; J.n_regions = Jh.n_regions; J.df = Jh.df;
+    for (int b = 0; b < Jh.k; ++b) J.set[b] = Jh.set[b];
+    memcpy(J.scale, Jh.scale, sizeof J.scale);
+    J.varBeta = Jh.varBeta; J.region_off = Jh.region_off; J.mtm = Jh.mtm;
+    J.rp_z = Jh.rp_z; J.rp_iw_chi2 = Jh.rp_iw_chi2; J.rp_iw_z = Jh.rp_iw_z;
+    const size_t smem = sizeof(double) * (size_t)(160 + kSlots * kMaxK + h->R);
+    CU(cudaFuncSetAttribute((const void*)joint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)joint_kernel, kThreads, smem));
+    if (per_sm * h->prop.multiProcessorCount < h->Tw + 1)
+        return fail(h, NGP_EUNSUPPORTED, "cooperative grid of %d CTAs does not fit (%d per SM x %d SMs)", h->Tw + 1, per_sm, h->prop.multiProcessorCount);
+    CU(cudaMemsetAsync(h->sync, 0, kSyncHeadBytes, h->stream));
+    void* args[] = {&P, &J};
+    CU(cudaEventRecord(h->ev0, h->stream));
+    CU(cudaLaunchCooperativeKernel((const void*)joint_kernel, dim3(h->Tw + 1), dim3(kThreads), args, smem, h->stream));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    h->launches += 1;
+    h->timed = true;
+    CU(cudaStreamSynchronize(h->stream));
+    return check_kernel_error(h);
+}
+
 static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_mu, double varE_in, int accumulate)
 {
     CU(cudaSetDevice(h->device));
+    if (h->joint.active) return fail(h, NGP_EINVAL, "this handle samples a tuple of marker sets: use ngp_run / ngp_joint_sweep");
     if (!h->have_y) return fail(h, NGP_EINVAL, "no phenotype / residual on the device (ngp_set_phenotype or ngp_sweep)");
     int active = 0;
     for (int s = 0; s < h->n_sets; ++s)
@@ -802,14 +890,7 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     int rc = sync_sets(h);
     if (rc) return rc;
     Params P{};
-    P.n = h->n; P.Tw = h->Tw; P.R = h->R; P.B = h->B; P.n_sets = h->n_sets; P.kernel = h->cfg_kernel;
-    P.D = h->D; P.DN = h->DN; P.NT = h->NT; P.NR = h->NR; P.NV = h->NV;
-    P.e = h->e; P.sets = h->sets_dev; P.sc = h->sc; P.sync = h->sync;
-    P.df_e = h->df_e; P.scale_e = h->scale_e; P.has_mu = h->has_mu; P.do_varE = do_varE; P.do_mu = do_mu; P.set_mask = set_mask;
-    P.mu_lhs0 = h->mu_lhs0; P.mu_rhs0 = h->mu_rhs0; P.varE_in = varE_in; P.n_iter = n_iter; P.replay = h->replay;
-    P.replay_base = h->replay_base; P.rp_chi2_e = h->rp_chi2_e; P.rp_z_mu = h->rp_z_mu;
-    P.key0 = (uint32_t)(h->seed & 0xffffffffu); P.key1 = (uint32_t)(h->seed >> 32); P.chain = h->chain; P.accumulate = accumulate;
-    P.debug = h->cfg_debug;
+    fill_params(h, P, n_iter, set_mask, do_varE, do_mu, varE_in, accumulate);
 #define NGP_PICK(PROF, DBG) ((h->B == 64) ? (const void*)gibbs_kernel<64, PROF, DBG> : (h->B == 32) ? (const void*)gibbs_kernel<32, PROF, DBG> : (const void*)gibbs_kernel<16, PROF, DBG>)
     const void* kfn = h->cfg_debug ? NGP_PICK(false, true) : h->cfg_profile ? NGP_PICK(true, false) : NGP_PICK(false, false);
 #undef NGP_PICK
@@ -835,16 +916,14 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     h->launches += 1;
     h->timed = true;
     CU(cudaStreamSynchronize(h->stream));
-    int kerr = 0;
-    CU(cpy(h, &kerr, &h->sync->err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (kerr) return fail(h, NGP_ERANGE, "fixed-point reduction range exceeded (residual grew by more than 2^4 within an iteration)");
-    return NGP_OK;
+    return check_kernel_error(h);
 }
 
 int ngp_run(ngp_handle* h, int32_t n_iter)
 {
     if (!h) return NGP_EINVAL;
     if (n_iter <= 0) return fail(h, NGP_EINVAL, "ngp_run: n_iter must be positive");
+    if (h->joint.active) return launch_joint(h, n_iter, 1, 1, 0.0, 1);
     int mask = 0;
     for (int s = 0; s < h->n_sets; ++s) if (h->sets[s].have_geno) mask |= 1 << s;
     return launch(h, n_iter, mask, 1, 1, 0.0, 1);
@@ -859,7 +938,7 @@ static int push_set_state(ngp_handle* h, int s, const double* beta, const int64_
         for (int64_t j = 0; j < S.p; ++j) d32[(size_t)j] = (int32_t)delta[j];
         CU(cpy(h, S.delta, d32.data(), sizeof(int32_t) * S.p, cudaMemcpyHostToDevice));
     }
-    if (varBeta) CU(cpy(h, S.varBeta, varBeta, sizeof(double) * S.nvar, cudaMemcpyHostToDevice));
+    if (varBeta && S.varBeta) CU(cpy(h, S.varBeta, varBeta, sizeof(double) * S.nvar, cudaMemcpyHostToDevice));
     if (piHat && S.method != NGP_BAYESPR) {
         double pi4[4] = {piHat[0], piHat[1], log(piHat[0]), log(piHat[1])};
         CU(cpy(h, S.pi, pi4, sizeof pi4, cudaMemcpyHostToDevice));
@@ -876,8 +955,8 @@ static int pull_set_state(ngp_handle* h, int s, double* beta, int64_t* delta, do
         CU(cpy(h, d32.data(), S.delta, sizeof(int32_t) * S.p, cudaMemcpyDeviceToHost));
         for (int64_t j = 0; j < S.p; ++j) delta[j] = d32[(size_t)j];
     }
-    if (varBeta) CU(cpy(h, varBeta, S.varBeta, sizeof(double) * S.nvar, cudaMemcpyDeviceToHost));
-    if (piHat) {
+    if (varBeta && S.varBeta) CU(cpy(h, varBeta, S.varBeta, sizeof(double) * S.nvar, cudaMemcpyDeviceToHost));
+    if (piHat && S.pi) {
         double pi4[4];
         CU(cpy(h, pi4, S.pi, sizeof pi4, cudaMemcpyDeviceToHost));
         piHat[0] = pi4[0]; piHat[1] = pi4[1];
@@ -901,6 +980,112 @@ int ngp_sweep(ngp_handle* h, int set_id, double* ycorr, double varE, double* bet
     if (rc) return rc;
     CU(cpy(h, ycorr, h->e, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
     return pull_set_state(h, set_id, beta, delta, varBeta, piHat);
+}
+
+int ngp_set_joint_prior(ngp_handle* h, const ngp_joint_prior* pr)
+{
+    if (!h || !pr) return fail(h, NGP_EINVAL, "ngp_set_joint_prior: NULL argument");
+    const int k = pr->k;
+    if (k < 2 || k > kMaxK) return fail(h, NGP_EINVAL, "ngp_set_joint_prior: k must be in [2,%d]", kMaxK);
+    if (!pr->scale || !pr->var_init || !(pr->df > 0.0)) return fail(h, NGP_EINVAL, "ngp_set_joint_prior: scale / var_init / df missing");
+    int64_t p = 0;
+    unsigned member_mask = 0;
+    for (int b = 0; b < k; ++b) {
+        const int s = pr->set_id[b];
+        if (s < 0 || s >= NGP_MAX_SETS || !h->sets[s].have_geno) return fail(h, NGP_EINVAL, "ngp_set_joint_prior: upload genotypes of set %d first", s);
+        if ((member_mask >> s) & 1u) return fail(h, NGP_EINVAL, "ngp_set_joint_prior: set %d listed twice", s);
+        member_mask |= 1u << s;
+        if (b == 0) p = h->sets[s].p;
+        else if (h->sets[s].p != p) return fail(h, NGP_EINVAL, "ngp_set_joint_prior: member sets must have the same number of loci (mme.jl:453)");
+    }
+    for (int s = 0; s < h->n_sets; ++s)
+        if (h->sets[s].have_geno && !((member_mask >> s) & 1u))
+            return fail(h, NGP_EUNSUPPORTED, "ngp_set_joint_prior: every marker set of the handle must be a member of the tuple (set %d is not)", s);
+    int64_t R = 1;
+    std::vector<int64_t> ro;
+    if (pr->region_off && pr->n_regions >= 1) {
+        R = pr->n_regions;
+        if (pr->region_off[0] != 0 || pr->region_off[R] != p) return fail(h, NGP_EINVAL, "ngp_set_joint_prior: region offsets must start at 0 and end at p");
+        for (int64_t r = 0; r < R; ++r)
+            if (pr->region_off[r + 1] <= pr->region_off[r]) return fail(h, NGP_EINVAL, "ngp_set_joint_prior: empty or unordered region %lld", (long long)r);
+        ro.assign(pr->region_off, pr->region_off + R + 1);
+    } else ro = {0, p};
+    CU(cudaSetDevice(h->device));
+    for (int b = 0; b < h->joint.k; ++b) h->sets[h->joint.set[b]].joint_member = false;
+    free_joint(h->joint);
+    JointHost& J = h->joint;
+    J.k = k; J.p = p; J.n_regions = R; J.df = pr->df;
+    for (int b = 0; b < k; ++b) J.set[b] = pr->set_id[b];
+    for (int i = 0; i < k * k; ++i) J.scale[i] = pr->scale[i];
+    CU(dalloc(&J.region_off, (size_t)R + 1));
+    CU(cpy(h, J.region_off, ro.data(), sizeof(int64_t) * (R + 1), cudaMemcpyHostToDevice));
+    std::vector<double> vb((size_t)R * k * k);
+    for (int64_t r = 0; r < R; ++r) for (int i = 0; i < k * k; ++i) vb[(size_t)r * k * k + i] = pr->var_init[i];      // mme.jl:516
+    CU(dalloc(&J.varBeta, vb.size()));
+    CU(cpy(h, J.varBeta, vb.data(), sizeof(double) * vb.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&J.mtm, (size_t)p * k * k));
+    JointGeno G{};
+    for (int b = 0; b < k; ++b) { G.geno[b] = h->sets[J.set[b]].geno; G.colsum[b] = h->sets[J.set[b]].colsum; }
+    joint_mtm_kernel<<<(unsigned)((p + 7) / 8), 256, 0, h->stream>>>(G, k, h->Tw, h->R, h->B, h->sets[J.set[0]].p_pad / h->B, h->n, p, J.mtm);
+    CU(cudaGetLastError());
+    for (int b = 0; b < k; ++b) {
+        SetHost& S = h->sets[J.set[b]];
+        S.method = NGP_BAYESPR; S.est_pi = 0; S.nvar = 0; S.n_regions = R; S.df = pr->df; S.scale = 0.0;
+        CU(dalloc(&S.sum_beta, S.p_pad)); CU(dalloc(&S.sum_beta2, S.p_pad)); CU(dalloc(&S.sum_delta, S.p_pad));
+        CU(cudaMemsetAsync(S.sum_beta, 0, sizeof(double) * S.p_pad, h->stream));
+        CU(cudaMemsetAsync(S.sum_beta2, 0, sizeof(double) * S.p_pad, h->stream));
+        CU(cudaMemsetAsync(S.sum_delta, 0, sizeof(double) * S.p_pad, h->stream));
+        CU(cudaMemsetAsync(S.beta, 0, sizeof(double) * S.p_pad, h->stream));                                      // mme.jl:458
+        S.have_prior = true; S.joint_member = true;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    J.active = true;
+    h->sets_dirty = true;
+    return NGP_OK;
+}
+
+int ngp_set_joint_replay(ngp_handle* h, int32_t n_iter, const double* z, const double* iw_chi2, const double* iw_z)
+{
+    if (!h) return NGP_EINVAL;
+    JointHost& J = h->joint;
+    if (!J.active) return fail(h, NGP_EINVAL, "ngp_set_joint_replay: no tuple of marker sets");
+    if (n_iter <= 0 || !z || !iw_chi2 || !iw_z) return fail(h, NGP_EINVAL, "ngp_set_joint_replay: n_iter must be > 0 and the logs non-NULL");
+    CU(cudaSetDevice(h->device));
+    const size_t k = (size_t)J.k, nz = (size_t)n_iter * J.p * k, nc = (size_t)n_iter * J.n_regions * k, nl = nc * k;
+    CU(dalloc(&J.rp_z, nz)); CU(cpy(h, J.rp_z, z, sizeof(double) * nz, cudaMemcpyHostToDevice));
+    CU(dalloc(&J.rp_iw_chi2, nc)); CU(cpy(h, J.rp_iw_chi2, iw_chi2, sizeof(double) * nc, cudaMemcpyHostToDevice));
+    CU(dalloc(&J.rp_iw_z, nl)); CU(cpy(h, J.rp_iw_z, iw_z, sizeof(double) * nl, cudaMemcpyHostToDevice));
+    J.replay_iters = n_iter;
+    return NGP_OK;
+}
+
+int ngp_get_joint_state(ngp_handle* h, double* beta, double* varBeta)
+{
+    if (!h) return NGP_EINVAL;
+    JointHost& J = h->joint;
+    if (!J.active) return fail(h, NGP_EINVAL, "ngp_get_joint_state: no tuple of marker sets");
+    CU(cudaSetDevice(h->device));
+    if (beta) for (int b = 0; b < J.k; ++b) CU(cpy(h, beta + (size_t)b * J.p, h->sets[J.set[b]].beta, sizeof(double) * J.p, cudaMemcpyDeviceToHost));
+    if (varBeta) CU(cpy(h, varBeta, J.varBeta, sizeof(double) * (size_t)J.n_regions * J.k * J.k, cudaMemcpyDeviceToHost));
+    return NGP_OK;
+}
+
+int ngp_joint_sweep(ngp_handle* h, double* ycorr, double varE, double* beta, double* varBeta)
+{
+    if (!h) return NGP_EINVAL;
+    JointHost& J = h->joint;
+    if (!J.active) return fail(h, NGP_EINVAL, "ngp_joint_sweep: no tuple of marker sets");
+    if (!ycorr || !(varE > 0.0)) return fail(h, NGP_EINVAL, "ngp_joint_sweep: ycorr must be non-NULL and varE > 0");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->e, ycorr, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+    if (beta) for (int b = 0; b < J.k; ++b) CU(cudaMemcpyAsync(h->sets[J.set[b]].beta, beta + (size_t)b * J.p, sizeof(double) * J.p, cudaMemcpyHostToDevice, h->stream));
+    if (varBeta) CU(cudaMemcpyAsync(J.varBeta, varBeta, sizeof(double) * (size_t)J.n_regions * J.k * J.k, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_y = true;
+    int rc = launch_joint(h, 1, 0, 0, varE, 0);
+    if (rc) return rc;
+    CU(cpy(h, ycorr, h->e, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
+    return ngp_get_joint_state(h, beta, varBeta);
 }
 
 int ngp_get_state(ngp_handle* h, ngp_state* out)
