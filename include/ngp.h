@@ -110,6 +110,23 @@ typedef struct ngp_joint_prior {
     const int64_t* region_off;       /* n_regions+1 offsets, 0-based half-open; NULL = one region */
 } ngp_joint_prior;
 
+/* -------------------------------------------------------------------------
+ * Row-sharded single chain (BASELINE config 5): rank r of `world`
+ * holds a contiguous slice of the individuals (rows of X, y, e).  Per marker the
+ * partial dots of all ranks are reduced through NVLink peer memory inside the
+ * persistent kernel; every rank draws the same effect from the same counter.
+ * What a rank publishes to its peers (exchange the structs with any transport,
+ * e.g. an all-gather over NCCL/gloo, or pass them by hand within one process):
+ * ------------------------------------------------------------------------- */
+typedef struct ngp_shard_info {
+    unsigned char ipc[64];   /* cudaIpcMemHandle_t of the rank's synchronisation area            */
+    int64_t n_local;         /* rows held by the rank                                            */
+    int32_t worker_ctas;     /* row panels (worker CTAs) of the rank                             */
+    int32_t device;
+    int64_t pid;             /* same pid => same-process attach through local_ptr (+ peer access) */
+    uint64_t local_ptr;
+} ngp_shard_info;
+
 /* Variate log of n_iter iterations for replay parity: the sampler
  * consumes these instead of its Philox stream.  Layout is row-major
  * [iteration][index].  Set s uses u[s], z[s], chi2_b[s], beta_pi[s].           */
@@ -170,10 +187,23 @@ int ngp_upload_genotypes(ngp_handle* h, int set_id, int64_t n, int64_t p,
  * ctr=(i>>2, j, 0, 0x47454e4f)).  Bit-identical to oracle ngo_synth_codes.  */
 int ngp_synth_genotypes(ngp_handle* h, int set_id, int64_t n, int64_t p, uint64_t seed,
                         const uint32_t* thr0, const uint32_t* thr1, int storage);
+/* rows [row0, row0 + n) of the same synthetic matrix (row0 a multiple of 4): the slice of one rank of a row-sharded chain */
+int ngp_synth_genotypes_rows(ngp_handle* h, int set_id, int64_t row0, int64_t n, int64_t p, uint64_t seed,
+                             const uint32_t* thr0, const uint32_t* thr1, int storage);
 /* unpack device storage back to int8 column-major (bit-exact round-trip tests) */
 int ngp_download_genotypes(ngp_handle* h, int set_id, int64_t j0, int64_t j1, int8_t* out);
 /* mean_j (prepMatVec.jl:129) and mpm_j = X_j'X_j of the centred column (mme.jl:305-307) */
 int ngp_get_column_stats(ngp_handle* h, int set_id, double* mean, double* mpm);
+
+/* ---- row-sharded chain: call order  ngp_shard_init -> uploads (local rows) -> ngp_shard_export -> [exchange] ->
+ *      ngp_shard_attach -> ngp_get_column_sums -> [all-reduce] -> ngp_set_column_sums -> priors, phenotype (local rows) ->
+ *      ngp_run with identical arguments on every rank, concurrently.  mean_j and mpm_j (prepMatVec.jl:129, mme.jl:305-307)
+ *      are those of the whole column.  Only the per-marker kernel (NGP_KERNEL_LITERAL) runs sharded.                   */
+int ngp_shard_init(ngp_handle* h, int rank, int world);
+int ngp_shard_export(ngp_handle* h, ngp_shard_info* out);
+int ngp_shard_attach(ngp_handle* h, const ngp_shard_info* all_ranks);
+int ngp_get_column_sums(ngp_handle* h, int set_id, int64_t* colsum, int64_t* colsumsq);
+int ngp_set_column_sums(ngp_handle* h, int set_id, int64_t n_total, const int64_t* colsum, const int64_t* colsumsq);
 
 /* host 2-bit codec (format NGP_GENO_PACKED2); returns NGP_EDATA on a code outside 0..2 */
 int ngp_pack2(const int8_t* codes, int64_t n, int64_t p, int64_t ld_in, uint8_t* out, int64_t ld_out);

@@ -42,6 +42,11 @@ class JointPrior(C.Structure):
                 ("scale", C.c_void_p), ("var_init", C.c_void_p), ("n_regions", C.c_int64), ("region_off", C.c_void_p)]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [("ipc", C.c_ubyte * 64), ("n_local", C.c_int64), ("worker_ctas", C.c_int32), ("device", C.c_int32),
+                ("pid", C.c_int64), ("local_ptr", C.c_uint64)]
+
+
 class Replay(C.Structure):
     _fields_ = [("n_iter", C.c_int32), ("n_sets", C.c_int32), ("chi2_e", C.c_void_p), ("z_mu", C.c_void_p),
                 ("u", C.c_void_p * NGP_MAX_SETS), ("z", C.c_void_p * NGP_MAX_SETS),
@@ -97,6 +102,12 @@ _SIGS = {
     "ngp_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ngp_upload_genotypes": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int]),
     "ngp_synth_genotypes": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]),
+    "ngp_synth_genotypes_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]),
+    "ngp_shard_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ngp_shard_export": (C.c_int, [C.c_void_p, C.POINTER(ShardInfo)]),
+    "ngp_shard_attach": (C.c_int, [C.c_void_p, C.POINTER(ShardInfo)]),
+    "ngp_get_column_sums": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ngp_set_column_sums": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "ngp_download_genotypes": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
     "ngp_get_column_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ngp_pack2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),

@@ -32,7 +32,7 @@ from . import _lib as L
 @dataclass
 class BayesPRType:
     r: int
-    v: float
+    v: Any                       # Float64, or a k x k matrix for a tuple of correlated marker sets
     name: str = "BayesPR"
 
 
@@ -65,9 +65,9 @@ class SummaryStatistics:
     v: Any
 
 
-def BayesPR(r: int, v: float, name: str = "BayesPR") -> BayesPRType:
+def BayesPR(r: int, v, name: str = "BayesPR") -> BayesPRType:
     """runTime.jl:36-45 — r: 1 per-SNP variance, 99 per chromosome, 9999 one common variance, else window size."""
-    return BayesPRType(int(r), float(v), name)
+    return BayesPRType(int(r), float(v) if np.ndim(v) == 0 else np.asarray(v, dtype=np.float64), name)
 
 
 def BayesB(pi: float, v: float, name: str = "BayesB", estimatePi: bool = False) -> BayesBType:
@@ -277,6 +277,37 @@ class Sampler:
         self.n = n
         self.sets[set_id] = {"p": p}
 
+    def synth_genotypes_rows(self, set_id: int, row0: int, n: int, p: int, seed: int, thr0: np.ndarray, thr1: np.ndarray) -> None:
+        thr0 = np.ascontiguousarray(thr0, dtype=np.uint32)
+        thr1 = np.ascontiguousarray(thr1, dtype=np.uint32)
+        self._ck(self._lib.ngp_synth_genotypes_rows(self._h, set_id, row0, n, p, C.c_uint64(seed), _p(thr0), _p(thr1), L.STORE_I8))
+        self.n = n
+        self.sets[set_id] = {"p": p}
+
+    # -- row-sharded chain (include/ngp.h: ngp_shard_*)
+    def shard_init(self, rank: int, world: int) -> None:
+        self._ck(self._lib.ngp_shard_init(self._h, rank, world))
+
+    def shard_export(self) -> bytes:
+        info = L.ShardInfo()
+        self._ck(self._lib.ngp_shard_export(self._h, C.byref(info)))
+        return bytes(info)
+
+    def shard_attach(self, infos: list[bytes]) -> None:
+        arr = (L.ShardInfo * len(infos))(*[L.ShardInfo.from_buffer_copy(b) for b in infos])
+        self._ck(self._lib.ngp_shard_attach(self._h, arr))
+
+    def column_sums(self, set_id: int):
+        p = self.sets[set_id]["p"]
+        a, b = np.empty(p, dtype=np.int64), np.empty(p, dtype=np.int64)
+        self._ck(self._lib.ngp_get_column_sums(self._h, set_id, _p(a), _p(b)))
+        return a, b
+
+    def set_column_sums(self, set_id: int, n_total: int, colsum: np.ndarray, colsumsq: np.ndarray) -> None:
+        a = np.ascontiguousarray(colsum, dtype=np.int64)
+        b = np.ascontiguousarray(colsumsq, dtype=np.int64)
+        self._ck(self._lib.ngp_set_column_sums(self._h, set_id, n_total, _p(a), _p(b)))
+
     def download_genotypes(self, set_id: int, j0: int = 0, j1: int | None = None) -> np.ndarray:
         p = self.sets[set_id]["p"]
         j1 = p if j1 is None else j1
@@ -463,6 +494,80 @@ class Sampler:
         return out
 
 
+class ShardedChain:
+    """One chain whose individuals are row-sharded over several handles of THIS process (one per device, or several on one
+    device for testing).  Each handle runs the same persistent per-marker kernel; the kernels of all shards must be
+    co-resident, so every ngp_run is issued from one host thread per shard.  With one process per GPU use the Sampler
+    methods directly and exchange shard_export() blobs / column sums with torch.distributed (bench.py --sharded)."""
+
+    def __init__(self, devices: list[int], max_ctas: int = 0, min_rows: int = 0):
+        self.world = len(devices)
+        self.shards = [Sampler(d, kernel="literal", max_ctas=max_ctas, min_rows=min_rows) for d in devices]
+        for r, s in enumerate(self.shards):
+            s.shard_init(r, self.world)
+        self.rows: list[tuple[int, int]] = []
+
+    def split_rows(self, n: int) -> list[tuple[int, int]]:
+        per = -(-n // self.world)
+        per = -(-per // 4) * 4                                   # shard boundaries on multiples of 4 rows
+        self.rows = [(min(n, r * per), min(n, (r + 1) * per)) for r in range(self.world)]
+        return self.rows
+
+    def upload_genotypes(self, set_id: int, codes: np.ndarray) -> None:
+        n = codes.shape[0]
+        if not self.rows:
+            self.split_rows(n)
+        for s, (a, b) in zip(self.shards, self.rows):
+            s.upload_genotypes(set_id, np.asfortranarray(codes[a:b]))
+        self._finish(set_id, n)
+
+    def _finish(self, set_id: int, n: int) -> None:
+        if not self.shards[0].__dict__.get("_attached"):
+            infos = [s.shard_export() for s in self.shards]
+            for s in self.shards:
+                s.shard_attach(infos)
+                s._attached = True
+        sums = [s.column_sums(set_id) for s in self.shards]
+        cs, css = sum(x[0] for x in sums), sum(x[1] for x in sums)
+        for s in self.shards:
+            s.set_column_sums(set_id, n, cs, css)
+
+    def each(self, fn) -> list:
+        return [fn(s, r) for r, s in enumerate(self.shards)]
+
+    def set_phenotype(self, y: np.ndarray) -> None:
+        for s, (a, b) in zip(self.shards, self.rows):
+            s.set_phenotype(y[a:b])
+
+    def run(self, n_iter: int = 1) -> None:
+        import threading
+        errs: list = []
+
+        def work(s):
+            try:
+                s.run(n_iter)
+            except Exception as ex:  # noqa: BLE001
+                errs.append(ex)
+        th = [threading.Thread(target=work, args=(s,)) for s in self.shards]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def state(self) -> dict:
+        sts = [s.state() for s in self.shards]
+        out = sts[0]
+        out["e"] = np.concatenate([st["e"] for st in sts])
+        out["shards"] = sts
+        return out
+
+    def close(self) -> None:
+        for s in self.shards:
+            s.close()
+
+
 # ----------------------------------------------------------------------------- getMME / runSampler / runLMEM
 @dataclass
 class MarkerTerm:
@@ -484,6 +589,9 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
         raise NotImplementedError("weighted residuals (E.str == \"D\") stay in Julia: SURVEY §8(f3)")
     df_e = 4.0
     scale_e = 0.0005 if e_prior.v == 0.0 else e_prior.v * (df_e - 2.0) / df_e  # mme.jl:87-94
+    tuples = [k for k in priorVCV if isinstance(k, tuple)]
+    if tuples:                                                                  # (:M1,:M2) => BayesPR(r, V): mme.jl:448-489
+        return _getMME_tuple(sampler, Y, M, priorVCV, tuples, outPut, intercept, df_e, scale_e)
     info = []
     for sid, term in enumerate(M):
         sampler.upload_genotypes(sid, term.codes)
@@ -544,6 +652,49 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
     return {"df_e": df_e, "scale_e": scale_e, "sets": info}
 
 
+def _getMME_tuple(sampler, Y, M, priorVCV, tuples, outPut, intercept, df_e, scale_e):
+    """Correlated (multi-breed) marker sets: one tuple whose members are all marker terms of the model."""
+    if len(tuples) != 1 or sorted(tuples[0]) != sorted(t.name for t in M):
+        raise NotImplementedError("one tuple covering every marker set of the model is supported on device")
+    names = list(tuples[0])
+    pr = priorVCV[tuples[0]]
+    if pr.name != "BayesPR":
+        raise NotImplementedError("correlated marker sets are sampled with BayesPR (functions.jl:140)")
+    by_name = {t.name: t for t in M}
+    maps = [by_name[nm].map for nm in names]
+    if any(m != maps[0] for m in maps):
+        raise ValueError("correlated marker sets must have the same map file!")      # mme.jl:453
+    k = len(names)
+    V = np.asarray(pr.v, dtype=np.float64).reshape(k, k)
+    for sid, nm in enumerate(names):
+        sampler.upload_genotypes(sid, by_name[nm].codes)
+    p = by_name[names[0]].codes.shape[1]
+    if maps[0] is None or maps[0] == "":                                          # mme.jl:470-481
+        if pr.r == 1:
+            region_off = np.arange(p + 1, dtype=np.int64)
+        elif pr.r == 9999:
+            region_off = None
+        else:
+            raise ValueError("Please enter a valid region size (1 or 9999)")
+    else:
+        region_off = prep2RegionData(outPut, "_".join(names), maps[0], pr.r)        # mme.jl:483-484
+    df = 3.0 + k                                                                  # mme.jl:493
+    sampler.set_joint_prior(list(range(k)), df, V * (df - k - 1.0), V, region_off=region_off)   # mme.jl:501,516
+    sampler.set_phenotype(Y)
+    sampler.set_residual_prior(df_e, scale_e)
+    sampler.set_intercept(intercept)
+    R = sampler.joint["n_regions"]
+    tname = "_".join(names)
+    if outPut is not None:
+        outMCMC(outPut, "b", [["(Intercept)"]] if intercept else [[]])
+        for nm in names:
+            levels = by_name[nm].levels or [f"M{i}" for i in range(1, p + 1)]
+            outMCMC(outPut, f"beta{nm}", [levels])
+        outMCMC(outPut, f"var{tname}", [[f"reg_{r}_{a}_{b}" for r in range(1, R + 1) for a in names for b in names]])
+        outMCMC(outPut, "varE", [["e"]])
+    return {"df_e": df_e, "scale_e": scale_e, "sets": [], "tuple": {"names": names, "name": tname, "k": k, "p": p, "df": df}}
+
+
 def runSampler(sampler: Sampler, M: list[MarkerTerm], info: dict, chainLength: int, burnIn: int, outputFreq: int, outPut: str | None,
                intercept: bool = True, on_sample=None) -> None:
     """samplers.runSampler! (samplers.jl:23-106): iterations run on device in batches that end on a kept iteration;
@@ -567,7 +718,14 @@ def runSampler(sampler: Sampler, M: list[MarkerTerm], info: dict, chainLength: i
                 if inf["method"] in ("BayesB", "BayesC"):
                     outMCMC(outPut, f"pi{term.name}", st["sets"][sid]["piHat"])
             for sid, term in enumerate(M):
-                outMCMC(outPut, f"var{term.name}", st["sets"][sid]["varBeta"])
+                if not info.get("tuple"):
+                    outMCMC(outPut, f"var{term.name}", st["sets"][sid]["varBeta"])
+            if info.get("tuple"):
+                js = sampler.joint_state()
+                st["joint"] = js
+                for b, nm in enumerate(info["tuple"]["names"]):
+                    outMCMC(outPut, f"beta{nm}", js["beta"][b])
+                outMCMC(outPut, f"var{info['tuple']['name']}", js["varBeta"].ravel())
         if on_sample is not None:
             on_sample(it, st)
     if done < chainLength:

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <unistd.h>
 
 #include "../../include/ngp.h"
 #include "ngp_sweep.cuh"
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const uint8_t* __restrict__ g
     }
 }
 
-__global__ void synth_kernel(uint32_t key0, uint32_t key1, int64_t n, int64_t j0, int64_t ncols,
+__global__ void synth_kernel(uint32_t key0, uint32_t key1, int64_t n, int64_t row0, int64_t j0, int64_t ncols,
                              const uint32_t* __restrict__ thr0, const uint32_t* __restrict__ thr1, int8_t* __restrict__ out)
 {
     const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -131,7 +132,7 @@ __global__ void synth_kernel(uint32_t key0, uint32_t key1, int64_t n, int64_t j0
     if (i4 >= n || jc >= ncols) return;
     const int64_t j = j0 + jc;
     uint32_t w[4];
-    philox4x32_10((uint32_t)(i4 >> 2), (uint32_t)j, 0u, 0x47454e4fu, key0, key1, w);
+    philox4x32_10((uint32_t)((row0 + i4) >> 2), (uint32_t)j, 0u, 0x47454e4fu, key0, key1, w);     // row0 is a multiple of 4
     const uint32_t a = thr0[j], b = thr1[j];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -237,6 +238,14 @@ struct ngp_handle {
     int replay = 0, replay_iters = 0;
     int64_t replay_base = 0;
     double *rp_chi2_e = nullptr, *rp_z_mu = nullptr;
+    // row-sharded chain
+    int shard_rank = 0, shard_world = 1;
+    bool shard_attached = false;
+    SyncArea* peer[kMaxRanks] = {nullptr};
+    bool peer_ipc[kMaxRanks] = {false};
+    int shard_Tw[kMaxRanks] = {0};
+    int64_t n_total = 0;
+    uint64_t bar_count = 0;     // grid-barrier rounds so far (the sharded counter is monotonic across launches)
     // stats
     int64_t launches = 0;
     uint64_t gblk = 0;          // blocks swept so far by the blocked kernel (numbers the list words and accumulator slots)
@@ -351,6 +360,7 @@ int ngp_destroy(ngp_handle* h)
     cudaDeviceSynchronize();
     for (auto& s : h->sets) free_set(s);
     free_joint(h->joint);
+    for (int r = 0; r < h->shard_world; ++r) if (h->peer_ipc[r] && h->peer[r]) cudaIpcCloseMemHandle(h->peer[r]);
     cudaFree(h->e); cudaFree(h->sc); cudaFree(h->sync); cudaFree(h->sets_dev);
     cudaFree(h->rp_chi2_e); cudaFree(h->rp_z_mu);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -415,7 +425,7 @@ static int choose_geometry(ngp_handle* h, int64_t n)
 {
     const int sms = h->prop.multiProcessorCount;
     int maxc = h->cfg_max_ctas ? std::min(h->cfg_max_ctas, sms) : sms;
-    maxc = std::min(maxc, kMaxCtas);
+    maxc = std::min(maxc, kMaxCtas / h->shard_world);      // phase-0 partials of all ranks share one array; arrivals per accumulator < 256
     if (maxc < 2) return fail(h, NGP_EUNSUPPORTED, "the sweep kernel needs at least 2 co-resident CTAs (device has %d SMs)", sms);
     const int maxw = maxc - 1;                     // one CTA runs the scalar chain
     const int64_t want = (n + h->cfg_min_rows - 1) / h->cfg_min_rows;
@@ -558,8 +568,14 @@ int ngp_upload_genotypes(ngp_handle* h, int set_id, int64_t n, int64_t p, const 
 
 int ngp_synth_genotypes(ngp_handle* h, int set_id, int64_t n, int64_t p, uint64_t seed, const uint32_t* thr0, const uint32_t* thr1, int storage)
 {
+    return ngp_synth_genotypes_rows(h, set_id, 0, n, p, seed, thr0, thr1, storage);
+}
+
+int ngp_synth_genotypes_rows(ngp_handle* h, int set_id, int64_t row0, int64_t n, int64_t p, uint64_t seed, const uint32_t* thr0, const uint32_t* thr1, int storage)
+{
     if (!h) return NGP_EINVAL;
     if (!thr0 || !thr1) return fail(h, NGP_EINVAL, "ngp_synth_genotypes: thresholds are NULL");
+    if (row0 < 0 || (row0 & 3)) return fail(h, NGP_EINVAL, "ngp_synth_genotypes_rows: row0 must be a non-negative multiple of 4");
     int rc = begin_upload(h, set_id, n, p, storage);
     if (rc) return rc;
     SetHost& S = h->sets[set_id];
@@ -578,7 +594,7 @@ int ngp_synth_genotypes(ngp_handle* h, int set_id, int64_t n, int64_t p, uint64_
     for (int64_t j0 = 0; j0 < p; j0 += chunk) {
         const int64_t nc = std::min(chunk, p - j0);
         dim3 grid((unsigned)(((n + 3) / 4 + 255) / 256), (unsigned)nc);
-        synth_kernel<<<grid, 256, 0, h->stream>>>((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), n, j0, nc, d0, d1, stage);
+        synth_kernel<<<grid, 256, 0, h->stream>>>((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), n, row0, j0, nc, d0, d1, stage);
         CU(cudaGetLastError());
         pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, n, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr);
         CU(cudaGetLastError());
@@ -819,6 +835,18 @@ static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int 
     P.replay_base = h->replay_base; P.rp_chi2_e = h->rp_chi2_e; P.rp_z_mu = h->rp_z_mu;
     P.key0 = (uint32_t)(h->seed & 0xffffffffu); P.key1 = (uint32_t)(h->seed >> 32); P.chain = h->chain; P.accumulate = accumulate;
     P.debug = h->cfg_debug;
+    P.n_ranks = h->shard_world; P.rank = h->shard_rank; P.n_total = h->shard_world > 1 ? h->n_total : h->n;
+    P.cta_off = 0; P.T_all = h->Tw + 1; P.Tw_all = h->Tw; P.bar_base = 0;
+    P.peer[0] = h->sync;
+    if (h->shard_world > 1) {
+        P.T_all = 0; P.Tw_all = 0;
+        for (int r = 0; r < h->shard_world; ++r) {
+            if (r == h->shard_rank) P.cta_off = P.T_all;
+            P.T_all += h->shard_Tw[r] + 1; P.Tw_all += h->shard_Tw[r];
+            P.peer[r] = h->peer[r];
+        }
+        P.bar_base = h->bar_count * (unsigned long long)P.T_all;
+    }
 }
 
 static int check_kernel_error(ngp_handle* h)
@@ -874,6 +902,10 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
 {
     CU(cudaSetDevice(h->device));
     if (h->joint.active) return fail(h, NGP_EINVAL, "this handle samples a tuple of marker sets: use ngp_run / ngp_joint_sweep");
+    const bool sharded = h->shard_world > 1;
+    if (sharded && !h->shard_attached) return fail(h, NGP_EINVAL, "row-sharded handle: call ngp_shard_attach before sampling");
+    if (sharded && h->cfg_kernel != NGP_KERNEL_LITERAL)
+        return fail(h, NGP_EUNSUPPORTED, "the row-sharded chain runs the per-marker kernel (NGP_CFG_KERNEL = NGP_KERNEL_LITERAL)");
     if (!h->have_y) return fail(h, NGP_EINVAL, "no phenotype / residual on the device (ngp_set_phenotype or ngp_sweep)");
     int active = 0;
     for (int s = 0; s < h->n_sets; ++s)
@@ -908,7 +940,14 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     }
     P.gblk0 = (uint32_t)h->gblk;
     h->gblk += blocks;
-    CU(cudaMemsetAsync(h->sync, 0, kSyncHeadBytes, h->stream));
+    if (sharded) {
+        // peers may already be arriving on this rank's counter: never reset it; account for the barrier rounds of this launch
+        CU(cudaMemsetAsync(&h->sync->err, 0, sizeof(int), h->stream));
+        uint64_t rounds = 2;
+        for (int s = 0; s < h->n_sets; ++s)
+            if ((set_mask >> s) & 1) rounds += ((h->sets[s].method == NGP_BAYESPR && h->sets[s].n_regions > 1) || accumulate) ? 1 : 0;
+        h->bar_count += rounds * (uint64_t)n_iter;
+    } else CU(cudaMemsetAsync(h->sync, 0, kSyncHeadBytes, h->stream));
     void* args[] = {&P};
     CU(cudaEventRecord(h->ev0, h->stream));
     CU(cudaLaunchCooperativeKernel(kfn, dim3(h->Tw + 1), dim3(kThreads), args, (size_t)h->L.total, h->stream));
@@ -980,6 +1019,100 @@ int ngp_sweep(ngp_handle* h, int set_id, double* ycorr, double varE, double* bet
     if (rc) return rc;
     CU(cpy(h, ycorr, h->e, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
     return pull_set_state(h, set_id, beta, delta, varBeta, piHat);
+}
+
+// ----------------------------------------------------------------------------- row-sharded chain
+int ngp_shard_init(ngp_handle* h, int rank, int world)
+{
+    if (!h) return NGP_EINVAL;
+    if (h->Tw) return fail(h, NGP_EINVAL, "ngp_shard_init: must be called before the first upload");
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(h, NGP_EINVAL, "ngp_shard_init: rank %d / world %d out of range (<= %d)", rank, world, kMaxRanks);
+    h->shard_rank = rank; h->shard_world = world; h->shard_attached = false;
+    return NGP_OK;
+}
+
+int ngp_shard_export(ngp_handle* h, ngp_shard_info* out)
+{
+    if (!h || !out) return fail(h, NGP_EINVAL, "ngp_shard_export: NULL argument");
+    if (!h->Tw) return fail(h, NGP_EINVAL, "ngp_shard_export: upload the rank's rows first (fixes its CTA geometry)");
+    CU(cudaSetDevice(h->device));
+    memset(out, 0, sizeof *out);
+    cudaIpcMemHandle_t ih;
+    CU(cudaIpcGetMemHandle(&ih, h->sync));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ngp_shard_info.ipc holds a cudaIpcMemHandle_t");
+    memcpy(out->ipc, &ih, 64);
+    out->n_local = h->n; out->worker_ctas = h->Tw; out->device = h->device; out->pid = (int64_t)getpid();
+    out->local_ptr = (uint64_t)(uintptr_t)h->sync;
+    return NGP_OK;
+}
+
+int ngp_shard_attach(ngp_handle* h, const ngp_shard_info* all)
+{
+    if (!h || !all) return fail(h, NGP_EINVAL, "ngp_shard_attach: NULL argument");
+    if (h->shard_world < 2) return fail(h, NGP_EINVAL, "ngp_shard_attach: the handle is not sharded (ngp_shard_init)");
+    if (!h->Tw) return fail(h, NGP_EINVAL, "ngp_shard_attach: upload the rank's rows first");
+    CU(cudaSetDevice(h->device));
+    int64_t ntot = 0, ctas = 0;
+    for (int r = 0; r < h->shard_world; ++r) {
+        const ngp_shard_info& I = all[r];
+        if (I.worker_ctas <= 0 || I.n_local <= 0) return fail(h, NGP_EINVAL, "ngp_shard_attach: rank %d published no geometry", r);
+        ntot += I.n_local; ctas += I.worker_ctas + 1;
+        h->shard_Tw[r] = I.worker_ctas;
+        if (r == h->shard_rank) { h->peer[r] = h->sync; h->peer_ipc[r] = false; continue; }
+        if (I.pid == (int64_t)getpid()) {                       // same process: the pointer is valid here; map the peer device if needed
+            if (I.device != h->device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, h->device, I.device));
+                if (!can) return fail(h, NGP_EUNSUPPORTED, "device %d cannot access device %d (no NVLink / P2P)", h->device, I.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(I.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+                cudaGetLastError();
+            }
+            h->peer[r] = (SyncArea*)(uintptr_t)I.local_ptr; h->peer_ipc[r] = false;
+        } else {                                               // one process per GPU: CUDA IPC mapping over NVLink
+            cudaIpcMemHandle_t ih;
+            memcpy(&ih, I.ipc, 64);
+            void* ptr = nullptr;
+            CU(cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+            h->peer[r] = (SyncArea*)ptr; h->peer_ipc[r] = true;
+        }
+    }
+    if (ctas > kMaxCtas) return fail(h, NGP_EUNSUPPORTED, "%lld CTAs over all ranks exceed %d", (long long)ctas, kMaxCtas);
+    h->n_total = ntot;
+    h->shard_attached = true;
+    return NGP_OK;
+}
+
+int ngp_get_column_sums(ngp_handle* h, int set_id, int64_t* colsum, int64_t* colsumsq)
+{
+    if (!h || set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_geno) return fail(h, NGP_EINVAL, "ngp_get_column_sums: no such set");
+    SetHost& S = h->sets[set_id];
+    CU(cudaSetDevice(h->device));
+    std::vector<int32_t> a((size_t)S.p), b((size_t)S.p);
+    CU(cpy(h, a.data(), S.colsum, sizeof(int32_t) * S.p, cudaMemcpyDeviceToHost));
+    CU(cpy(h, b.data(), S.colsumsq, sizeof(int32_t) * S.p, cudaMemcpyDeviceToHost));
+    for (int64_t j = 0; j < S.p; ++j) { if (colsum) colsum[j] = a[(size_t)j]; if (colsumsq) colsumsq[j] = b[(size_t)j]; }
+    return NGP_OK;
+}
+
+int ngp_set_column_sums(ngp_handle* h, int set_id, int64_t n_total, const int64_t* colsum, const int64_t* colsumsq)
+{
+    if (!h || set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_geno) return fail(h, NGP_EINVAL, "ngp_set_column_sums: no such set");
+    if (!colsum || !colsumsq || n_total < h->n) return fail(h, NGP_EINVAL, "ngp_set_column_sums: bad argument");
+    SetHost& S = h->sets[set_id];
+    CU(cudaSetDevice(h->device));
+    std::vector<int32_t> a((size_t)S.p), b((size_t)S.p);
+    for (int64_t j = 0; j < S.p; ++j) {
+        if (colsum[j] < 0 || colsum[j] > 0x7fffffffLL || colsumsq[j] < 0 || colsumsq[j] > 0x7fffffffLL) return fail(h, NGP_EINVAL, "ngp_set_column_sums: sum out of range at column %lld", (long long)j);
+        a[(size_t)j] = (int32_t)colsum[j]; b[(size_t)j] = (int32_t)colsumsq[j];
+    }
+    CU(cpy(h, S.colsum, a.data(), sizeof(int32_t) * S.p, cudaMemcpyHostToDevice));
+    CU(cpy(h, S.colsumsq, b.data(), sizeof(int32_t) * S.p, cudaMemcpyHostToDevice));
+    // mean and mpm of the WHOLE column (all ranks' rows): prepMatVec.jl:129, mme.jl:305-307
+    colstats_kernel<<<(unsigned)((S.p_pad + 255) / 256), 256, 0, h->stream>>>(n_total, S.p, S.p_pad, S.colsum, S.colsumsq, S.mean, S.d);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    return NGP_OK;
 }
 
 int ngp_set_joint_prior(ngp_handle* h, const ngp_joint_prior* pr)

@@ -31,6 +31,7 @@ constexpr int kPrepWarps = 8;          //            (poll accumulators, cross-G
 constexpr int kFirstPrepWarp = 2;
 constexpr int kLimbVers = 16;          // maximum number of versions of the fixed-point residual kept per worker CTA
 
+constexpr int kMaxRanks = 8;           // row shards of one chain (GPUs of one NVSwitch box)
 constexpr int kProf = 32;              // cycle counters per CTA (ngp_get_profile)
 constexpr int kMaxB = 64;              // markers per block: 16, 32 or 64
 constexpr int kNF = 10;                // per-marker constant fields
@@ -124,6 +125,15 @@ struct Params {
     int32_t accumulate;        // add to posterior sums
     uint32_t gblk0;            // global number of the first block of this launch (lists and accumulator slots are numbered globally)
     int32_t debug;             // timing experiments (NGP_CFG_DEBUG), see ngp_sweep.cuh
+    // ---- row-sharded chain: rank r holds rows [row_0(r), row_0(r) + n) of X and e; every grid-wide quantity
+    //      (barrier arrivals, phase-0 partials, per-marker fixed-point sums) is PUSHED into the SyncArea of every rank over
+    //      NVLink peer memory, and every poll is local.  n_ranks == 1: not sharded (peer[0] == sync).
+    int32_t n_ranks, rank;
+    int32_t cta_off, T_all;    // index of this rank's first CTA in the all-rank CTA numbering; CTAs of all ranks
+    int32_t Tw_all, pad_sh;    // worker CTAs of all ranks (arrivals per accumulator)
+    int64_t n_total;           // individuals over all ranks (n is the local row count)
+    unsigned long long bar_base;   // barrier arrivals counted before this launch (sharded: the counter is never reset)
+    SyncArea* peer[kMaxRanks];
 };
 
 // ----------------------------------------------------------------------------- tile layout
@@ -150,6 +160,21 @@ __device__ __forceinline__ void red_add_u64(long long* addr, long long v)
 __device__ __forceinline__ void arrive_release(unsigned long long* c)
 {
     asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(c) : "memory");
+}
+// system-scope variants for peer memory over NVLink (row-sharded chain)
+__device__ __forceinline__ void red_add_u64_sys(long long* addr, long long v)
+{
+    asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void arrive_release_sys(unsigned long long* c)
+{
+    asm volatile("red.release.sys.global.add.u64 [%0], 1;" ::"l"(c) : "memory");
+}
+__device__ __forceinline__ long long ld_relaxed_s64_sys(const long long* p)
+{
+    long long v;
+    asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ long long ld_relaxed_s64(const long long* p)     // LDG.STRONG.GPU, no L1, no fence
 {

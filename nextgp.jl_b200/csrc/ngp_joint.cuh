@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) joint_kernel(const Params P, cons
     long long* lprev = reinterpret_cast<long long*>(misc + 160);             // [kSlots][kMaxK] previous accumulator values
     double* e_s = misc + 160 + kSlots * kMaxK;
     SyncArea* sy = P.sync;
-    GridSync gs{&sy->counter, 0ull, (unsigned)(Tw + 1)};
+    GridSync gs{&sy->counter, 0ull, (unsigned)(Tw + 1), 0ull, 1};
     const int64_t row0 = (int64_t)t * R;
     const int nrow = is_chain ? 0 : (int)max((int64_t)0, min((int64_t)R, P.n - row0));
     const int nwords = R >> 2;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) joint_kernel(const Params P, cons
         block_sum2(ee, se, misc);
         if (tid == 0) {
             sy->part[2 * t] = ee; sy->part[2 * t + 1] = se;
-            gs.nbar++; gs.arrive();
+            gs.nbar++; gs.arrive(P);
         } else gs.nbar++;
         if (warp == 0) {
             gs.wait_warp();
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) joint_kernel(const Params P, cons
         // ------------------------------------------------------------------ phase 3: Sigma_r (functions.jl:152, 513-516), posterior sums
         __syncthreads();
         gs.nbar++;
-        if (tid == 0) gs.arrive();
+        if (tid == 0) gs.arrive(P);
         if (warp == 0) gs.wait_warp();
         __syncthreads();
         if (P.accumulate) {

@@ -106,19 +106,30 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch
     a = sa; b = sb;
 }
 
+// Grid barrier.  Sharded chain (n_ranks > 1): an arrival is pushed to the counter of every rank (release at system scope
+// covers this CTA's earlier peer stores), every rank polls its own counter; the counter is monotonic across launches.
 struct GridSync {
     unsigned long long* counter;
-    unsigned long long nbar;     // barriers this CTA has taken part in
-    unsigned int T;
-    __device__ __forceinline__ void arrive()        // one thread, after a __syncthreads
+    unsigned long long nbar;     // barriers this CTA has taken part in (this launch)
+    unsigned int T;              // CTAs of all ranks
+    unsigned long long base;     // arrivals before this launch
+    int n_ranks;
+    __device__ __forceinline__ void arrive(const Params& P)        // one thread, after a __syncthreads
     {
-        arrive_release(counter);
+        if (n_ranks > 1) {
+            for (int r = 0; r < n_ranks; ++r) arrive_release_sys(&P.peer[r]->counter);
+        } else arrive_release(counter);
     }
     __device__ __forceinline__ void wait_warp()     // whole warp polls
     {
-        const unsigned long long target = nbar * (unsigned long long)T;
-        while ((unsigned long long)ld_relaxed_s64(reinterpret_cast<const long long*>(counter)) < target) { }
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");      // acquire once, not one CCTL.IVALL per poll
+        const unsigned long long target = base + nbar * (unsigned long long)T;
+        if (n_ranks > 1) {
+            while ((unsigned long long)ld_relaxed_s64_sys(reinterpret_cast<const long long*>(counter)) < target) { }
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+        } else {
+            while ((unsigned long long)ld_relaxed_s64(reinterpret_cast<const long long*>(counter)) < target) { }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");      // acquire once, not one CCTL.IVALL per poll
+        }
     }
 };
 
@@ -252,7 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     long long* prev = reinterpret_cast<long long*>(smem + L.c_prev);                        // [kSlots][B]
     NzList* cnz = reinterpret_cast<NzList*>(smem + L.c_nz);
 
-    GridSync gs{&sy->counter, 0ull, (unsigned)(Tw + 1)};
+    const bool sharded = P.n_ranks > 1;
+    GridSync gs{&sy->counter, 0ull, (unsigned)P.T_all, P.bar_base, P.n_ranks};
     const int64_t row0 = (int64_t)t * R;
     const int nrow = is_chain ? 0 : (int)max((int64_t)0, min((int64_t)R, P.n - row0));    // real rows of this panel
     const int nchunk = R >> 5;
@@ -309,19 +321,22 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         if (!is_chain) for (int r = tid; r < R; r += kThreads) { const double x = e_s[r]; ee = fma(x, x, ee); se += x; }
         block_sum2(ee, se, misc);
         if (tid == 0) {
-            sy->part[2 * t] = ee; sy->part[2 * t + 1] = se;
-            gs.nbar++; gs.arrive();
+            if (sharded) {
+                for (int r = 0; r < P.n_ranks; ++r) { P.peer[r]->part[2 * (P.cta_off + t)] = ee; P.peer[r]->part[2 * (P.cta_off + t) + 1] = se; }
+            } else { sy->part[2 * t] = ee; sy->part[2 * t + 1] = se; }
+            gs.nbar++; gs.arrive(P);
         } else gs.nbar++;
         if (warp == 0) {
             gs.wait_warp();
             double a = 0.0, b = 0.0;
-            for (int c = lane; c < Tw; c += 32) { a += __ldcg(&sy->part[2 * c]); b += __ldcg(&sy->part[2 * c + 1]); }
+            const int nparts = sharded ? P.T_all : Tw;     // same order on every rank: identical sums, identical draws
+            for (int c = lane; c < nparts; c += 32) { a += __ldcg(&sy->part[2 * c]); b += __ldcg(&sy->part[2 * c + 1]); }
             a = warp_sum(a); b = warp_sum(b);
             if (lane == 0) {
                 double varE = P.varE_in;
                 if (P.do_varE) {
                     Stream st{P.key0, P.key1, P.chain, iter, 0u};
-                    const double chi2 = P.replay ? P.rp_chi2_e[rp_row] : stream_chisq(st, P_CHI2_E, 0, 0, P.df_e + (double)P.n);
+                    const double chi2 = P.replay ? P.rp_chi2_e[rp_row] : stream_chisq(st, P_CHI2_E, 0, 0, P.df_e + (double)P.n_total);
                     varE = (P.df_e * P.scale_e + a) / chi2;                       // functions.jl:524
                 }
                 double dmu = 0.0;
@@ -329,15 +344,15 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     Stream st{P.key0, P.key1, P.chain, iter, 0u};
                     const double zmu = P.replay ? P.rp_z_mu[rp_row] : stream_normal(st, P_Z_MU, 0);
                     const double iVarE = 1.0 / varE;
-                    const double rhs = (b + (double)P.n * mu) * iVarE + P.mu_rhs0;
-                    const double lhs = (double)P.n * iVarE + P.mu_lhs0;
+                    const double rhs = (b + (double)P.n_total * mu) * iVarE + P.mu_rhs0;
+                    const double lhs = (double)P.n_total * iVarE + P.mu_lhs0;
                     const double mu_new = rhs / lhs + sqrt(1.0 / lhs) * zmu;
                     dmu = mu - mu_new;
                     mu = mu_new;
                 }
                 // fixed-point scale of the sweep reductions: |sum_i g_i e_i| <= 2 sqrt(n) ||e|| (Cauchy-Schwarz), 2^4 headroom
                 // for growth of ||e|| inside the iteration, 8 count bits: the grid total stays below 2^55
-                const double nn = (double)P.n;
+                const double nn = (double)P.n_total;
                 double M = 2.0 * sqrt(nn) * (sqrt(a) + sqrt(nn) * fabs(dmu));
                 if (!(M > 1e-300)) M = 1e-300;
                 int ex; (void)frexp(M, &ex);
@@ -365,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         }
         __syncthreads();
         gs.nbar++;
-        if (tid == 0) gs.arrive();
+        if (tid == 0) gs.arrive(P);
         if (warp == 0) gs.wait_warp();
         __syncthreads();
         if (tid == 0) NGP_TICK(9);
@@ -375,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
             if (!((P.set_mask >> s) & 1)) continue;
             const SetDev& S = P.sets[s];
             const int nblk = (int)(S.p_pad / B);
-            const double inv_n = 1.0 / (double)P.n;
+            const double inv_n = 1.0 / (double)P.n_total;
             const int method = S.method;
             const int64_t p_real = S.p;
             double acc_bb = 0.0, acc_n = 0.0;          // chain warp: per-lane partials of beta'beta and nLoci
@@ -1055,6 +1070,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                 // every CTA (the chain CTA owns no rows) evaluates the scalar update redundantly; CTA Tw writes the outputs
                 long long* lprev = reinterpret_cast<long long*>(misc + 48);
                 const int nwords = R >> 2;
+                const long long arrivals = (long long)P.Tw_all;       // worker CTAs of all ranks add into every rank's accumulators
                 for (int64_t j = 0; j < S.p; ++j, ++rk) {
                     const int k = (int)(j / B), q = (int)(j % B);
                     const uint8_t* tile = S.geno + ((int64_t)t * nblk + k) * L.tile_bytes;
@@ -1075,7 +1091,11 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     if (tid == 0 && !is_chain) {
                         const double xs = a * fx_scale;
                         if (!(fabs(xs) < 9007199254740992.0)) atomicOr(&sy->err, 1);
-                        red_add_u64(acc, (long long)((unsigned long long)__double2ll_rn(xs) << kCntBits) + 1);
+                        const long long v = (long long)((unsigned long long)__double2ll_rn(xs) << kCntBits) + 1;
+                        if (sharded) {
+                            // the per-marker scalar reduction over NVLink peer memory: one RED into every rank's accumulator
+                            for (int r = 0; r < P.n_ranks; ++r) red_add_u64_sys(P.peer[r]->acc + (size_t)slot * kMaxB * kAccStride, v);
+                        } else red_add_u64(acc, v);
                     }
                     if (warp == 0) {
                         const double* c = S.consts + (int64_t)k * (kNF * B) + q;
@@ -1084,8 +1104,9 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         const double bold = __ldcg(c + F_BOLD * B), mean = __ldcg(c + F_MEAN * B), chi = __ldcg(c + F_CHI * B);
                         long long* pv = lprev + slot;
                         long long cur;
-                        do { cur = ld_relaxed_s64(acc); } while (((cur - *pv) & 0xFF) != (long long)Tw);
-                        const double A = (double)((cur - *pv - (long long)Tw) >> kCntBits) * fx_inv;
+                        if (sharded) { do { cur = ld_relaxed_s64_sys(acc); } while (((cur - *pv) & 0xFF) != arrivals); }
+                        else { do { cur = ld_relaxed_s64(acc); } while (((cur - *pv) & 0xFF) != arrivals); }
+                        const double A = (double)((cur - *pv - arrivals) >> kCntBits) * fx_inv;
                         __syncwarp();
                         if (lane == 0) *pv = cur;
                         const double r = A - mean * Stot;
@@ -1151,7 +1172,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                 // posterior sums and the region variances are spread over the whole grid
                 __syncthreads();
                 gs.nbar++;
-                if (tid == 0) gs.arrive();
+                if (tid == 0) gs.arrive(P);
                 if (warp == 0) gs.wait_warp();
                 __syncthreads();
             }

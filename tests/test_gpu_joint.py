@@ -115,3 +115,23 @@ def test_joint_prior_argument_checks(gpu):
     with pytest.raises(ngp.NgpError):
         s.set_prior(0, 0, 4.0, 0.01, 0.02)                  # members have no prior of their own
     s.close()
+
+
+def test_runLMEM_with_a_tuple_of_marker_sets(gpu, tmp_path):
+    """`(:M1,:M2) => BayesPR(9999, V)` through the reference-shaped driver: per-member beta files + one covariance file."""
+    import os
+    probs, y = _breeds(150, 30, 2, 21)
+    out = str(tmp_path / "outMCMC")
+    VCV = {("M1", "M2"): ngp.BayesPR(9999, V2), "e": ngp.Random("I", float(np.var(y)) / 2)}
+    s = ngp.runLMEM("y ~ 1 + SNP(M1,a) + SNP(M2,b)", {"y": y}, 30, 10, 10, outFolder=out, VCV=VCV, seed=9,
+                    matrices={"M1": probs[0]["codes"], "M2": probs[1]["codes"]})
+    assert sorted(os.listdir(out)) == ["bOut", "betaM1Out", "betaM2Out", "varEOut", "varM1_M2Out"]
+    b2 = np.loadtxt(os.path.join(out, "betaM2Out"), delimiter="\t", skiprows=1)
+    vv = np.loadtxt(os.path.join(out, "varM1_M2Out"), delimiter="\t", skiprows=1)
+    assert b2.shape == (2, 30) and vv.shape == (2, 4)             # kept iterations 20, 30
+    ch, mb = _oracle(probs, y, V2, None, float(np.var(y)) / 2)
+    for _ in range(30):
+        ch.iteration(seed=9, chain=0)
+        mb.sweep(ch.e, ch.varE, it=ch.iter, seed=9, chain=0)
+    assert rel(b2[-1], mb.beta[1]) < 1e-7 and rel(vv[-1], mb.varBeta.ravel()) < 1e-7
+    s.close()
