@@ -28,6 +28,8 @@ CONFIGS = {
     # name: (n, p, model)    — BASELINE.json configs
     "c1": (1000, 5000, "BayesRR"),
     "c2": (50000, 50000, "BayesC"),
+    "c3": (100000, 600000, "BayesB"),
+    "c4": (30000, 50000, "MultiBreed2"),
     "c5": (200000, 50000, "BayesC"),
     "tiny": (2000, 4096, "BayesC"),
 }
@@ -36,6 +38,8 @@ METRIC = "marker-updates/sec"
 
 
 def workload_name(cfg, n, p, model):
+    if model.startswith("MultiBreed"):
+        return f"{cfg}: {n} individuals x {p} SNPs, {model[10:]}-breed tuple BayesPR (joint effects per locus) + intercept, int8 genotypes in HBM"
     return f"{cfg}: {n} individuals x {p} SNPs single-trait {model}{'pi' if model == 'BayesC' else ''} + intercept, int8 genotypes in HBM"
 
 
@@ -166,6 +170,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-cols", type=int, default=2000)
+    ap.add_argument("--sharded", action="store_true",
+                    help="ONE chain whose individuals are row-sharded over the N GPUs (per-marker reduction over NVLink peer memory); strong scaling")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -191,19 +197,50 @@ def main():
     n, p, model = CONFIGS[args.config] if not args.n else (args.n, args.p, args.model)
     seed = SEED0 + 2
     prob = ngp.synth.problem(n, p, seed)
-    v_e, v, pi = ngp.synth.priors(prob, model)
+    v_e, v, pi = ngp.synth.priors(prob, "BayesRR" if model.startswith("MultiBreed") else model)
     method = 0 if model in ("BayesRR", "BayesPR") else (1 if model == "BayesB" else 2)
 
+    sharded = args.sharded and world > 1
+    kbreeds = int(model[10:]) if model.startswith("MultiBreed") else 0
+    if sharded:
+        args.kernel = "literal"
+        args.no_e2e = True
     s = ngp.Sampler(local, kernel=args.kernel, block=args.block)
     stream = torch.cuda.current_stream()
     s.set_stream(stream.cuda_stream)
-    s.synth_genotypes(0, n, p, seed, prob["thr0"], prob["thr1"])       # every rank: same X, generated on device
     df, scale = 4.0, v * 0.5
-    s.set_prior(0, method, df, scale, v, pi_in=pi, est_pi=(method == 2))
-    s.set_phenotype(prob["y"])
+    y = prob["y"]
+    if sharded:
+        # one chain, rows [a, b) on this rank; NCCL only for set-up (handles, column sums) and the timing barrier
+        per = -(-(-(-n // world)) // 4) * 4
+        a, b = min(n, rank * per), min(n, (rank + 1) * per)
+        s.shard_init(rank, world)
+        s.synth_genotypes_rows(0, a, b - a, p, seed, prob["thr0"], prob["thr1"])
+        infos = [None] * world
+        dist.all_gather_object(infos, s.shard_export())
+        s.shard_attach(infos)
+        cs, css = s.column_sums(0)
+        tcs = torch.from_numpy(np.stack([cs, css])).cuda()
+        dist.all_reduce(tcs)
+        tcs = tcs.cpu().numpy()
+        s.set_column_sums(0, n, tcs[0], tcs[1])
+        y = prob["y"][a:b]
+    elif kbreeds:
+        for bset in range(kbreeds):
+            pb = ngp.synth.problem(n, p, seed + 101 * bset)
+            s.synth_genotypes(bset, n, p, seed + 101 * bset, pb["thr0"], pb["thr1"])
+        V = np.eye(kbreeds) * v + (np.ones((kbreeds, kbreeds)) - np.eye(kbreeds)) * 0.3 * v
+        dfk = 3.0 + kbreeds
+        s.set_joint_prior(list(range(kbreeds)), dfk, V * (dfk - kbreeds - 1.0), V)
+        args.no_e2e = True
+    else:
+        s.synth_genotypes(0, n, p, seed, prob["thr0"], prob["thr1"])       # every rank: same X, generated on device
+    if not kbreeds:
+        s.set_prior(0, method, df, scale, v, pi_in=pi, est_pi=(method == 2))
+    s.set_phenotype(y)
     s.set_residual_prior(4.0, v_e * 0.5)
     s.set_intercept(True)
-    s.set_rng(seed, rank)                                              # independent chains: chain id = rank
+    s.set_rng(seed, 0 if sharded else rank)                            # independent chains: chain id = rank
 
     for _ in range(args.warmup):
         s.run(1)
@@ -219,9 +256,14 @@ def main():
     kern_ms = []
     torch.cuda.synchronize()
     ev0.record(stream)
-    for _ in range(args.steps):
-        s.run(1)
-        kern_ms.append(s.timing()["last_run_ms"])
+    if sharded:
+        # one launch runs all K iterations (ngp_run(h, K)): the shards' persistent kernels stay co-resident, no host in the loop
+        s.run(args.steps)
+        kern_ms.append(s.timing()["last_run_ms"] / args.steps)
+    else:
+        for _ in range(args.steps):
+            s.run(1)
+            kern_ms.append(s.timing()["last_run_ms"])
     ev1.record(stream)
     torch.cuda.synchronize()
     if dist:
@@ -234,7 +276,8 @@ def main():
     if dist:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_all = float(tms.item())
-    value = world * p * args.steps / (ms_all * 1e-3)
+    nchains = 1 if sharded else world
+    value = nchains * p * args.steps / (ms_all * 1e-3)
 
     # ---- e2e: the plugin call with host buffers (pinned), H2D + sweep + D2H inside the timed region
     e2e = None
@@ -266,7 +309,9 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         tm = s.timing()
-        alg_bytes = p * (n * 1.0 + 40.0)                       # n*g + 40 B of per-marker scalars, g = 1 B
+        alg_bytes = p * (n * 1.0 + 40.0) * max(1, kbreeds)     # n*g + 40 B of per-marker scalars, g = 1 B (per breed column)
+        if sharded:
+            alg_bytes /= world                                 # bytes streamed by ONE GPU (its row slice)
         k_ms = float(np.mean(kern_ms))
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         traffic = None
@@ -277,19 +322,24 @@ def main():
             except Exception:
                 traffic = None
         line = {"metric": METRIC, "value": value, "unit": "marker-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": workload_name(args.config, n, p, model), "kernel": args.kernel, "chains": world,
-                           "parallelism": f"{world} independent chain(s), one per GPU, no data-path collective",
+                "config": {"workload": workload_name(args.config, n, p, model), "kernel": "joint (per locus)" if kbreeds else args.kernel, "chains": nchains,
+                           "parallelism": (f"ONE chain row-sharded over {world} GPUs: per-marker fixed-point reduction pushed into every rank's "
+                                           f"accumulators over NVLink peer memory (CUDA IPC), identical draw on every rank")
+                                          if sharded else f"{world} independent chain(s), one per GPU, no data-path collective",
                            "l2": f"genotype matrix {n * p / 1e9:.2f} GB per sweep vs 126 MB L2 (inputs larger than L2, no flush needed)"
                                  if n * p > 4e8 else "inputs fit in L2 (cache-resident workload; HBM roofline not meaningful)",
-                           "gibbs_iters_per_s": world * args.steps / (ms_all * 1e-3),
+                           "gibbs_iters_per_s": nchains * args.steps / (ms_all * 1e-3),
                            "geometry": {k: tm[k] for k in ("ctas", "threads", "block", "rows_per_cta", "smem_bytes", "lookahead", "near_depth", "tile_stages", "record_stages")}},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "kernel": "ngp::gibbs_kernel (one launch = one Gibbs iteration)", "kernel_ms": k_ms,
+                             "kernel": "ngp::joint_kernel (one launch = one Gibbs iteration)" if kbreeds else
+                                       "ngp::gibbs_kernel (one launch = one Gibbs iteration)", "kernel_ms": k_ms,
                              "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": summarize_clocks(lines)}
-        if not args.no_cpu:
+        if sharded:
+            line["per_marker_us"] = 1e3 * ms_all / args.steps / p
+        if not args.no_cpu and not kbreeds:
             line["cpu_baseline"] = cpu_baseline(n, p, model, seed)
         print(json.dumps(line), flush=True)
     s.close()

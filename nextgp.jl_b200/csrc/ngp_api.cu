@@ -882,15 +882,25 @@ static int launch_joint(ngp_handle* h, int n_iter, int do_varE, int do_mu, doubl
     J.varBeta = Jh.varBeta; J.region_off = Jh.region_off; J.mtm = Jh.mtm;
     J.rp_z = Jh.rp_z; J.rp_iw_chi2 = Jh.rp_iw_chi2; J.rp_iw_z = Jh.rp_iw_z;
     const size_t smem = sizeof(double) * (size_t)(160 + kSlots * kMaxK + h->R);
-    CU(cudaFuncSetAttribute((const void*)joint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const void* kfn = nullptr;
+    switch (Jh.k) {
+    case 2: kfn = (const void*)joint_kernel<2>; break;
+    case 3: kfn = (const void*)joint_kernel<3>; break;
+    case 4: kfn = (const void*)joint_kernel<4>; break;
+    case 5: kfn = (const void*)joint_kernel<5>; break;
+    case 6: kfn = (const void*)joint_kernel<6>; break;
+    case 7: kfn = (const void*)joint_kernel<7>; break;
+    default: kfn = (const void*)joint_kernel<8>; break;
+    }
+    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)joint_kernel, kThreads, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, smem));
     if (per_sm * h->prop.multiProcessorCount < h->Tw + 1)
         return fail(h, NGP_EUNSUPPORTED, "cooperative grid of %d CTAs does not fit (%d per SM x %d SMs)", h->Tw + 1, per_sm, h->prop.multiProcessorCount);
     CU(cudaMemsetAsync(h->sync, 0, kSyncHeadBytes, h->stream));
     void* args[] = {&P, &J};
     CU(cudaEventRecord(h->ev0, h->stream));
-    CU(cudaLaunchCooperativeKernel((const void*)joint_kernel, dim3(h->Tw + 1), dim3(kThreads), args, smem, h->stream));
+    CU(cudaLaunchCooperativeKernel(kfn, dim3(h->Tw + 1), dim3(kThreads), args, smem, h->stream));
     CU(cudaEventRecord(h->ev1, h->stream));
     h->launches += 1;
     h->timed = true;

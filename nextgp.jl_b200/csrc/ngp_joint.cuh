@@ -36,7 +36,8 @@ struct JointDev {
 };
 
 // ---- small dense algebra, k <= 8, row-major, one thread
-__device__ __forceinline__ bool jt_chol(int k, const double* A, double* L)
+template <int k>
+__device__ __forceinline__ bool jt_chol(const double* A, double* L)
 {
     for (int i = 0; i < k * k; ++i) L[i] = 0.0;
     for (int i = 0; i < k; ++i)
@@ -50,10 +51,11 @@ __device__ __forceinline__ bool jt_chol(int k, const double* A, double* L)
 }
 
 // inverse of an SPD matrix through its Cholesky factor: A^-1 = L^-T L^-1
-__device__ __forceinline__ bool jt_inv_spd(int k, const double* A, double* Ainv)
+template <int k>
+__device__ __forceinline__ bool jt_inv_spd(const double* A, double* Ainv)
 {
-    double L[kMaxK * kMaxK], Li[kMaxK * kMaxK];
-    if (!jt_chol(k, A, L)) return false;
+    double L[k * k], Li[k * k];
+    if (!jt_chol<k>(A, L)) return false;
     for (int i = 0; i < k * k; ++i) Li[i] = 0.0;
     for (int c = 0; c < k; ++c) {
         Li[c * k + c] = 1.0 / L[c * k + c];
@@ -73,10 +75,11 @@ __device__ __forceinline__ bool jt_inv_spd(int k, const double* A, double* Ainv)
 }
 
 // Sigma ~ InvWishart(df, Psi) by Bartlett: W = (L A)(L A)' with L = chol(Psi^-1), A lower, A_ii = sqrt(chi2_i), A_ij = z_ij
-__device__ __forceinline__ bool jt_inv_wishart(int k, const double* Psi, const double* chi2, const double* zl, double* Sigma)
+template <int k>
+__device__ __forceinline__ bool jt_inv_wishart(const double* Psi, const double* chi2, const double* zl, double* Sigma)
 {
-    double Pinv[kMaxK * kMaxK], L[kMaxK * kMaxK], LA[kMaxK * kMaxK], W[kMaxK * kMaxK];
-    if (!jt_inv_spd(k, Psi, Pinv) || !jt_chol(k, Pinv, L)) return false;
+    double Pinv[k * k], L[k * k], LA[k * k], W[k * k];
+    if (!jt_inv_spd<k>(Psi, Pinv) || !jt_chol<k>(Pinv, L)) return false;
     for (int i = 0; i < k; ++i)
         for (int j = 0; j < k; ++j) {
             double s = 0.0;
@@ -89,7 +92,7 @@ __device__ __forceinline__ bool jt_inv_wishart(int k, const double* Psi, const d
             for (int t = 0; t < k; ++t) s += LA[i * k + t] * LA[j * k + t];
             W[i * k + j] = s;
         }
-    return jt_inv_spd(k, W, Sigma);
+    return jt_inv_spd<k>(W, Sigma);
 }
 
 // centred cross-products of the k columns of every locus: mtm[j][a][b] = sum_i g_a g_b - cs_a cs_b / n   (one warp per locus)
@@ -134,12 +137,14 @@ __global__ void joint_mtm_kernel(const JointGeno G, int k, int Tw, int R, int B,
 }
 
 // ----------------------------------------------------------------------------- the kernel
+template <int KK>
 __global__ void __launch_bounds__(kThreads, 1) joint_kernel(const Params P, const JointDev J)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = blockIdx.x;
-    const int Tw = P.Tw, R = P.R, B = P.B, k = J.k;
+    const int Tw = P.Tw, R = P.R, B = P.B;
+    constexpr int k = KK;                            // components (J.k == KK)
     const bool is_chain = (t == Tw);                 // owns no rows; writes the outputs
     double* misc = reinterpret_cast<double*>(smem);                          // [0..27] block_sum scratch, [32..] scalars, [40..] dbeta / K
     double* invB = misc + 96;                                                // [64] inv(Sigma_r)
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) joint_kernel(const Params P, cons
             if (tid == 0) {                                                       // invB = inv(varBeta[mSet][r]), functions.jl:143
                 double Sg[kMaxK * kMaxK], Iv[kMaxK * kMaxK];
                 for (int i = 0; i < k * k; ++i) Sg[i] = __ldcg(&J.varBeta[rg * k * k + i]);
-                if (!jt_inv_spd(k, Sg, Iv)) { atomicOr(&sy->err, 2); for (int i = 0; i < k * k; ++i) Iv[i] = 0.0; }
+                if (!jt_inv_spd<k>(Sg, Iv)) { atomicOr(&sy->err, 2); for (int i = 0; i < k * k; ++i) Iv[i] = 0.0; }
                 for (int i = 0; i < k * k; ++i) invB[i] = Iv[i];
             }
             __syncthreads();
@@ -272,7 +277,18 @@ __global__ void __launch_bounds__(kThreads, 1) joint_kernel(const Params P, cons
                         }
                 }
                 if (warp == 0) {
-                    // lane b waits for the k-th accumulator to hold all Tw partial sums
+                    // everything that does not depend on the sums is fetched / drawn while they are in flight: lane b draws z_b
+                    Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)J.stream_set};
+                    double zb = 0.0, meanb = 0.0, boldb = 0.0;
+                    if (lane < k) {
+                        zb = P.replay ? J.rp_z[(rp_row * J.p + j) * k + lane] : stream_normal(st, P_Z, (uint32_t)j, 0, (uint32_t)lane);
+                        meanb = s_mean[lane][j];
+                        boldb = __ldcg(&s_beta[lane][j]);
+                    }
+                    double MtM[k * k];
+#pragma unroll
+                    for (int i = 0; i < k * k; ++i) MtM[i] = __ldg(&J.mtm[j * k * k + i]);
+                    // lane b waits for accumulator b to hold all Tw partial sums
                     double rb = 0.0;
                     if (lane < k) {
                         long long* pv = lprev + slot * kMaxK + lane;
@@ -280,41 +296,45 @@ __global__ void __launch_bounds__(kThreads, 1) joint_kernel(const Params P, cons
                         do { cur = ld_relaxed_s64(acc + lane * kAccStride); } while (((cur - *pv) & 0xFF) != (long long)Tw);
                         const double A = (double)((cur - *pv - (long long)Tw) >> kCntBits) * fx_inv;
                         *pv = cur;
-                        rb = A - s_mean[lane][j] * Stot;              // x_b'e of the centred column
+                        rb = A - meanb * Stot;                                    // x_b'e of the centred column
                     }
-                    double r[kMaxK];
+                    double r[k], z[k], bold[k], mean[k];
 #pragma unroll
-                    for (int b = 0; b < kMaxK; ++b) r[b] = __shfl_sync(0xffffffffu, rb, b);
+                    for (int b = 0; b < k; ++b) {
+                        r[b] = __shfl_sync(0xffffffffu, rb, b); z[b] = __shfl_sync(0xffffffffu, zb, b);
+                        bold[b] = __shfl_sync(0xffffffffu, boldb, b); mean[b] = __shfl_sync(0xffffffffu, meanb, b);
+                    }
                     if (lane == 0) {
-                        double bold[kMaxK], MtM[kMaxK * kMaxK], LHS[kMaxK * kMaxK], C[kMaxK * kMaxK], Lc[kMaxK * kMaxK], bn[kMaxK];
-                        for (int b = 0; b < k; ++b) bold[b] = __ldcg(&s_beta[b][j]);
-                        for (int i = 0; i < k * k; ++i) MtM[i] = __ldg(&J.mtm[j * k * k + i]);
-                        bool ok = true;
+                        double LHS[k * k], C[k * k], Lc[k * k], bn[k], rhs[k];
+#pragma unroll
                         for (int a = 0; a < k; ++a)
+#pragma unroll
                             for (int b = 0; b < k; ++b) LHS[a * k + b] = MtM[a * k + b] * iVarE + invB[a * k + b];
-                        ok = jt_inv_spd(k, LHS, C) && jt_chol(k, C, Lc);          // functions.jl:147
+                        const bool ok = jt_inv_spd<k>(LHS, C) && jt_chol<k>(C, Lc);   // functions.jl:147
                         if (!ok) atomicOr(&sy->err, 2);
-                        Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)J.stream_set};
-                        double z[kMaxK], rhs[kMaxK];
+#pragma unroll
                         for (int b = 0; b < k; ++b) {
                             double rr = r[b];
+#pragma unroll
                             for (int a = 0; a < k; ++a) rr = fma(MtM[b * k + a], bold[a], rr);       // add-back fused (functions.jl:145)
                             rhs[b] = rr * iVarE;                                                    // functions.jl:146
-                            z[b] = P.replay ? J.rp_z[(rp_row * J.p + j) * k + b] : stream_normal(st, P_Z, (uint32_t)j, 0, (uint32_t)b);
                         }
-                        double K = 0.0;
+                        double Kc = 0.0;
+#pragma unroll
                         for (int a = 0; a < k; ++a) {
                             double m = 0.0;
+#pragma unroll
                             for (int b = 0; b < k; ++b) m += C[a * k + b] * rhs[b];                  // functions.jl:148
-                            double s = m;
-                            for (int b = 0; b <= a; ++b) s += Lc[a * k + b] * z[b];                  // functions.jl:149: MvNormal(mean, C)
-                            bn[a] = ok ? s : bold[a];
+                            double sdraw = m;
+#pragma unroll
+                            for (int b = 0; b <= a; ++b) sdraw += Lc[a * k + b] * z[b];              // functions.jl:149: MvNormal(mean, C)
+                            bn[a] = ok ? sdraw : bold[a];
                             const double db = bn[a] - bold[a];
                             misc[40 + a] = db;
-                            K = fma(db, s_mean[a][j], K);
+                            Kc = fma(db, mean[a], Kc);
                             if (is_chain) s_beta[a][j] = bn[a];
                         }
-                        misc[40 + kMaxK] = K;
+                        misc[40 + kMaxK] = Kc;
                     }
                 }
                 __syncthreads();
@@ -390,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) joint_kernel(const Params P, cons
                             zl[i * k + jj] = P.replay ? J.rp_iw_z[((rp_row * J.n_regions + rg) * k + i) * k + jj]
                                                       : stream_normal(st, P_IW, (uint32_t)rg, 0, (uint32_t)(i * k + jj));
                     }
-                    if (jt_inv_wishart(k, Psi, chi2, zl, Sg)) { for (int i = 0; i < k * k; ++i) J.varBeta[rg * k * k + i] = Sg[i]; }
+                    if (jt_inv_wishart<k>(Psi, chi2, zl, Sg)) { for (int i = 0; i < k * k; ++i) J.varBeta[rg * k * k + i] = Sg[i]; }
                     else atomicOr(&sy->err, 2);
                 }
             }
