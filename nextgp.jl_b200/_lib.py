@@ -18,7 +18,7 @@ BAYESPR, BAYESB, BAYESC = 0, 1, 2
 GENO_I8, GENO_F64, GENO_PACKED2 = 0, 1, 2
 STORE_I8, STORE_2BIT = 0, 1
 KERNEL_BLOCKED, KERNEL_LITERAL = 0, 1
-CFG_KERNEL, CFG_BLOCK, CFG_MIN_ROWS, CFG_MAX_CTAS, CFG_LOOKAHEAD, CFG_TILE_STAGES, CFG_NEAR, CFG_PROFILE, CFG_DEBUG, CFG_VERSIONS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+CFG_KERNEL, CFG_BLOCK, CFG_MIN_ROWS, CFG_MAX_CTAS, CFG_LOOKAHEAD, CFG_TILE_STAGES, CFG_NEAR, CFG_PROFILE, CFG_DEBUG, CFG_VERSIONS, CFG_REFETCH = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 OK, EINVAL, ECUDA, EDATA, ERANGE, ENOMEM, EUNSUPPORTED, ENUMERIC = 0, -1, -2, -3, -4, -5, -6, -7
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -201,7 +201,8 @@ class Sampler:
     """One chain on one GPU.  Thin, explicit wrapper over the C ABI (include/ngp.h)."""
 
     def __init__(self, device: int = 0, kernel: str = "blocked", block: int = 0, min_rows: int = 0, max_ctas: int = 0,
-                 lookahead: int = 0, tile_stages: int = 0, near: int = 0, versions: int = 0, profile: bool = False):
+                 lookahead: int = 0, tile_stages: int = 0, near: int = 0, versions: int = 0, profile: bool = False,
+                 refetch: int = -1):
         self._lib = L.lib()
         hp = C.c_void_p()
         rc = self._lib.ngp_create(device, C.byref(hp))
@@ -228,6 +229,8 @@ class Sampler:
             self.configure(L.CFG_VERSIONS, versions)
         if profile:
             self.configure(L.CFG_PROFILE, 1)
+        if refetch != -1:
+            self.configure(L.CFG_REFETCH, refetch)
 
     # -- plumbing
     def _ck(self, rc: int) -> None:

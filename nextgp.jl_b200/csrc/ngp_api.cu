@@ -216,8 +216,9 @@ struct ngp_handle {
     std::string err;
     // geometry
     int64_t n = 0;
+    int refetch = 0;
     int Tw = 0, R = 0, B = 0, D = 0, DN = 0, NT = 0, NR = 0, NV = 0;      // worker CTAs (grid = Tw + 1), rows per panel, block, look-ahead, near depth, tile stages
-    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0, cfg_versions = 0;
+    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0, cfg_versions = 0, cfg_refetch = -1;
     SmemLayout L{};
     // model
     SetHost sets[NGP_MAX_SETS];
@@ -395,6 +396,10 @@ int ngp_configure(ngp_handle* h, int key, int64_t value)
         h->cfg_versions = (int)value; return NGP_OK;
     case NGP_CFG_DEBUG:
         h->cfg_debug = (int)value; return NGP_OK;
+    case NGP_CFG_REFETCH:
+        if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: the tile-ring mode must be set before the first upload");
+        if (value < -1 || value > 1) return fail(h, NGP_EINVAL, "ngp_configure: refetch must be -1 (auto), 0 or 1");
+        h->cfg_refetch = (int)value; return NGP_OK;
     case NGP_CFG_PROFILE:
         h->cfg_profile = value ? 1 : 0; return NGP_OK;
     case NGP_CFG_LOOKAHEAD:
@@ -440,29 +445,47 @@ static int choose_geometry(ngp_handle* h, int64_t n)
         return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA; block %d supports at most %lld (use block 16 for up to %d)",
                     (long long)n, (long long)R, B, (long long)maxR, 4 * kUpdThreads * kUpdGroups);
     const int dn_min = 2 * ((B == 16 ? 32 : 64) / B) - 1;    // the chain warp steps over 64 markers (32 for blocks of 16): distances inside two steps come from the records
-    int DN = std::max(dn_min, h->cfg_near ? h->cfg_near : 0);
-    int D = h->cfg_lookahead ? h->cfg_lookahead : (B == 64 ? 6 : B == 32 ? 13 : 20);
-    D = std::min(D, kNzRing - 2);
-    for (;; ) {
-        if (D < dn_min) break;
-        DN = std::max(dn_min, std::min(DN, D));
-        const int nt_min = D + 2;     // a tile stays in smem until its block has been applied to e
-        int NT = h->cfg_tile_stages ? std::max(h->cfg_tile_stages, nt_min) : D + 4;     // a tile stays resident until its block has been applied to e
-        // shrink the record ring of the chain CTA, the tile ring, then the look-ahead, until both CTA roles fit
-        for (;;) {
-            for (int NR = kRecStages; NR >= 2; NR >>= 1) {
-                const int NV = h->cfg_versions ? h->cfg_versions : std::max(4, std::min(kLimbVers, D / 2 + 3));
-                SmemLayout L = smem_layout((int)R, B, NT, DN, NR, NV);
-                if ((size_t)L.total + 1024 <= cap) {
-                    h->n = n; h->Tw = Tw; h->R = (int)R; h->B = B; h->D = D; h->DN = DN; h->NT = NT; h->NR = NR; h->NV = NV; h->L = L;
-                    return NGP_OK;
+    // Two tile-ring modes.  resident: a tile stays in shared memory until its block has been applied to e (NT >= D + 2), so the rare
+    // residual update reads it there.  refetch: a tile stays only until its dots are formed (NT = 8 / 4 / 2 / 1 stages, consumed by as many
+    // dot warps) and the columns of changed effects are re-read from L2 / HBM: the look-ahead is no longer bounded by shared memory.
+    // Small panels use resident; refetch is chosen when resident would leave fewer than kMinResidentD blocks of look-ahead.
+    const int want_D = h->cfg_lookahead ? h->cfg_lookahead : (B == 64 ? 6 : B == 32 ? 13 : 20);
+    constexpr int kMinResidentD = 10;
+    auto search = [&](int refetch) -> bool {
+        int DN = std::max(dn_min, h->cfg_near ? h->cfg_near : 0);
+        int D = std::min(refetch ? std::min(want_D, 13) : want_D, kNzRing - 2);
+        if (refetch && h->cfg_lookahead) D = std::min(h->cfg_lookahead, kNzRing - 2);
+        auto legal_nt = [](int v) { return v >= 8 ? 8 : v >= 4 ? 4 : v >= 2 ? 2 : 1; };
+        for (;; ) {
+            if (D < dn_min) break;
+            DN = std::max(dn_min, std::min(DN, D));
+            const int nt_min = refetch ? 1 : D + 2;
+            int NT = refetch ? legal_nt(h->cfg_tile_stages ? h->cfg_tile_stages : 8) : (h->cfg_tile_stages ? std::max(h->cfg_tile_stages, nt_min) : D + 4);
+            // shrink the record ring of the chain CTA, the tile ring, then the look-ahead, until both CTA roles fit
+            for (;;) {
+                for (int NR = kRecStages; NR >= 2; NR >>= 1) {
+                    const int NV = h->cfg_versions ? h->cfg_versions : std::max(4, std::min(kLimbVers, D / 2 + 3));
+                    SmemLayout L = smem_layout((int)R, B, NT, DN, NR, NV);
+                    if ((size_t)L.total + 1024 <= cap) {
+                        h->n = n; h->Tw = Tw; h->R = (int)R; h->B = B; h->D = D; h->DN = DN; h->NT = NT; h->NR = NR; h->NV = NV; h->L = L;
+                        h->refetch = refetch;
+                        return true;
+                    }
                 }
+                if (NT > nt_min) NT = refetch ? legal_nt(NT - 1) : NT - 1; else break;
             }
-            if (NT > nt_min) --NT; else break;
+            if (DN > dn_min) { --DN; continue; }
+            if (D > dn_min) { --D; continue; }
+            break;
         }
-        if (DN > dn_min) { --DN; continue; }
-        if (D > dn_min) { --D; continue; }
-        break;
+        return false;
+    };
+    if (h->cfg_refetch == 0) { if (search(0)) return NGP_OK; }
+    else if (h->cfg_refetch == 1) { if (search(1)) return NGP_OK; }
+    else {
+        if (search(0) && h->D >= std::min(want_D, kMinResidentD)) return NGP_OK;
+        if (search(1)) return NGP_OK;
+        if (search(0)) return NGP_OK;
     }
     return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA: the panel tiles (block %d) do not fit in %zu bytes of shared memory",
                 (long long)n, (long long)R, B, cap);
@@ -828,7 +851,7 @@ static int sync_sets(ngp_handle* h)
 static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int do_varE, int do_mu, double varE_in, int accumulate)
 {
     P.n = h->n; P.Tw = h->Tw; P.R = h->R; P.B = h->B; P.n_sets = h->n_sets; P.kernel = h->cfg_kernel;
-    P.D = h->D; P.DN = h->DN; P.NT = h->NT; P.NR = h->NR; P.NV = h->NV;
+    P.D = h->D; P.DN = h->DN; P.NT = h->NT; P.NR = h->NR; P.NV = h->NV; P.refetch = h->refetch;
     P.e = h->e; P.sets = h->sets_dev; P.sc = h->sc; P.sync = h->sync;
     P.df_e = h->df_e; P.scale_e = h->scale_e; P.has_mu = h->has_mu; P.do_varE = do_varE; P.do_mu = do_mu; P.set_mask = set_mask;
     P.mu_lhs0 = h->mu_lhs0; P.mu_rhs0 = h->mu_rhs0; P.varE_in = varE_in; P.n_iter = n_iter; P.replay = h->replay;

@@ -130,7 +130,8 @@ struct Params {
     //      NVLink peer memory, and every poll is local.  n_ranks == 1: not sharded (peer[0] == sync).
     int32_t n_ranks, rank;
     int32_t cta_off, T_all;    // index of this rank's first CTA in the all-rank CTA numbering; CTAs of all ranks
-    int32_t Tw_all, pad_sh;    // worker CTAs of all ranks (arrivals per accumulator)
+    int32_t Tw_all;            // worker CTAs of all ranks (arrivals per accumulator)
+    int32_t refetch;           // 1: tiles leave shared memory once their dots are formed; the columns of changed effects are re-read from L2/HBM
     int64_t n_total;           // individuals over all ranks (n is the local row count)
     unsigned long long bar_base;   // barrier arrivals counted before this launch (sharded: the counter is never reset)
     SyncArea* peer[kMaxRanks];

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     if (tid == 0) *cprog = 0u;
     if (tid == 0) {
         if (!is_chain) {
-            for (int s = 0; s < NT; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_free[s], kUpdWarps); }
+            for (int s = 0; s < NT; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_free[s], P.refetch ? 1 : kUpdWarps); }
             for (int s = 0; s < kNzSmem; ++s) { mbar_init(&nz_full[s], 1); mbar_init(&nz_free[s], kUpdWarps); }
             for (int s = 0; s < kNzRing; ++s) { mbar_init(&ver_full[s], kUpdWarps); mbar_init(&dot_done[s], 1); }
         } else {
@@ -446,8 +446,10 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                     }
                                 }
                                 if (tid == 0) NGP_TICK(5);
-                                // the tile is still resident in shared memory: one 32-bit word = the 4 codes of this thread's rows
-                                const uint32_t* tw = reinterpret_cast<const uint32_t*>(tiles + r_ta.s * L.tile_bytes);
+                                // one 32-bit word = the 4 codes of this thread's rows: from the tile, still resident in shared memory, or (big
+                                // panels: the ring only covers the dots) re-read from L2 / HBM
+                                const uint32_t* tw = P.refetch ? reinterpret_cast<const uint32_t*>(gbase + (int64_t)ja * L.tile_bytes)
+                                                               : reinterpret_cast<const uint32_t*>(tiles + r_ta.s * L.tile_bytes);
 #pragma unroll
                                 for (int k = 0; k < UG; ++k) {
                                     const int rg = tid + k * kUpdThreads;
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             __syncwarp();
                             if (lane == 0) {
                                 mbar_arrive(&ver_full[gidx & (kNzRing - 1)]);
-                                mbar_arrive(&tile_free[r_ta.s]);
+                                if (!P.refetch) mbar_arrive(&tile_free[r_ta.s]);
                                 if (!(dbg & 1)) mbar_arrive(&nz_free[r_nzw.s]);
                             }
                             r_ta.adv(NT); r_nzw.adv(kNzSmem);
@@ -505,11 +507,14 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         const int dw = warp - kFirstDotWarp;
                         const int g = lane >> 2, tt = lane & 3;
                         const long long plim = (1LL << 55) / Tw;
-                        const int j0 = (int)((unsigned)(dw - (int)(gblk & (kDotWarps - 1))) & (kDotWarps - 1));    // first j with (gblk+j) % kDotWarps == dw
+                        // refetch mode: a stage is always consumed by the same warp (the dot warps taking part divide NT), so an mbarrier
+                        // waiter is never more than one fill behind
+                        const int ND = !P.refetch ? kDotWarps : (NT >= 8) ? 8 : (NT >= 4) ? 4 : (NT >= 2) ? 2 : 1;
+                        const int j0 = (dw < ND) ? (int)((unsigned)(dw - (int)(gblk & (unsigned)(ND - 1))) & (unsigned)(ND - 1)) : nblk;    // first j with (gblk+j) % ND == dw
                         int tslot = (int)((gblk + (unsigned)j0) % (unsigned)NT);
                         uint32_t tph = ((gblk + (unsigned)j0) / (unsigned)NT) & 1u;
                         constexpr int CH = (MG >= 4) ? 1 : 4 / MG;          // independent accumulator chains per marker group
-                        for (int j = j0; j < nblk; j += kDotWarps) {
+                        for (int j = j0; j < nblk; j += ND) {
                             const unsigned gidx = gblk + (unsigned)j;
                             const int ja = j - D - 1;
                             int ver = 0;
@@ -569,8 +574,8 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             }
                             if constexpr (PROF) { if (tid == kFirstDotWarp * 32 && ja >= 0) { pf[28] += (long long)(global_ns() - pub_ns[(gblk + (unsigned)ja) & (kNzRing - 1)]); pf[29] += 1; } }
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&dot_done[gidx & (kNzRing - 1)]);
-                            tslot += kDotWarps;
+                            if (lane == 0) { mbar_arrive(&dot_done[gidx & (kNzRing - 1)]); if (P.refetch) mbar_arrive(&tile_free[tslot]); }
+                            tslot += ND;
                             while (tslot >= NT) { tslot -= NT; tph ^= 1u; }
                             if (tid == kFirstDotWarp * 32) NGP_TICK(15);
                         }

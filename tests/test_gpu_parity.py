@@ -142,8 +142,10 @@ def test_replay_parity_ragged_shapes(gpu, n, p, block, min_rows):
 
 @pytest.mark.parametrize("geom", [dict(lookahead=1, near=1, block=64), dict(lookahead=3, tile_stages=5, versions=2), dict(lookahead=24, block=16),
                                   dict(lookahead=9, versions=3, near=6), dict(lookahead=6, near=5, block=64),
-                                  dict(profile=True)],
-                         ids=["D1-B64", "D3-2versions", "D24-B16", "D9-near6", "D6-near5-B64", "instrumented"])
+                                  dict(profile=True), dict(refetch=1, lookahead=13), dict(refetch=1, lookahead=20, tile_stages=4, block=16),
+                                  dict(refetch=1, lookahead=5, tile_stages=1, block=64)],
+                         ids=["D1-B64", "D3-2versions", "D24-B16", "D9-near6", "D6-near5-B64", "instrumented", "refetch-D13", "refetch-D20-4stages-B16",
+                              "refetch-1stage-B64"])
 def test_replay_parity_over_pipeline_geometries(gpu, geom):
     """The look-ahead depth, ring sizes (incl. a 2- or 4-stage record ring), residual-version count and the instrumented variant change the schedule, never the result."""
     prob = make_problem(1300, 700, 77)
