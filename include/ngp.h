@@ -210,6 +210,16 @@ int ngp_set_column_sums(ngp_handle* h, int set_id, int64_t n_total, const int64_
 int ngp_pack2(const int8_t* codes, int64_t n, int64_t p, int64_t ld_in, uint8_t* out, int64_t ld_out);
 int ngp_unpack2(const uint8_t* packed, int64_t n, int64_t p, int64_t ld_in, int8_t* out, int64_t ld_out);
 
+/* ---- ingest straight to 2-bit codes (never through the Matrix{Float64} of prepMatVec.jl:116-120).  Host-only.
+ * Text: the reference's format — one row per individual, fields separated by ONE space, no header; a column with a missing
+ * field ("", NA, NaN, missing) is dropped like prepMatVec.jl:118 does; any value other than 0/1/2 -> NGP_EDATA.
+ * Call once with packed == NULL to learn n and p_total, allocate ld * p_total bytes (ld >= ceil(n/4)) and keep[p_total], call again:
+ * the kept columns are compacted to the front (NGP_GENO_PACKED2 layout), keep[j] tells which survived, *p_kept how many.        */
+int ngp_read_text_genotypes(const char* path, int64_t* n, int64_t* p_total, uint8_t* packed, int64_t ld, uint8_t* keep, int64_t* p_kept);
+/* PLINK .bed (SNP-major): n samples, p variants; code = copies of allele A1 (count_a1 != 0) or A2.  Variants with a missing
+ * genotype are dropped the same way.                                                                                          */
+int ngp_read_bed_genotypes(const char* path, int64_t n, int64_t p, int count_a1, uint8_t* packed, int64_t ld, uint8_t* keep, int64_t* p_kept);
+
 /* ---- model: replaces the state getMME! allocates (mme.jl:57,87-94,443-444,492-520) */
 int ngp_set_phenotype(ngp_handle* h, const double* y, int64_t n);            /* ycorr = deepcopy(Y) */
 int ngp_set_residual_prior(ngp_handle* h, double df_e, double scale_e);      /* E[:df], E[:scale]  */

@@ -67,7 +67,7 @@ class Timing(C.Structure):
 
 
 def sources() -> list[str]:
-    return [os.path.join(CSRC, "ngp_api.cu")]
+    return [os.path.join(CSRC, "ngp_api.cu"), os.path.join(CSRC, "ngp_ingest.cpp")]
 
 
 def _stale() -> bool:
@@ -112,6 +112,8 @@ _SIGS = {
     "ngp_get_column_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ngp_pack2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
     "ngp_unpack2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
+    "ngp_read_text_genotypes": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]),
+    "ngp_read_bed_genotypes": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]),
     "ngp_set_phenotype": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "ngp_set_residual_prior": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "ngp_set_intercept": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),

@@ -127,18 +127,56 @@ def prep_snp(path_or_matrix) -> np.ndarray:
     if isinstance(path_or_matrix, np.ndarray):
         raw = np.asarray(path_or_matrix, dtype=np.float64)
     else:
-        rows = []
-        with open(path_or_matrix) as f:
-            for line in f:
-                toks = line.rstrip("\n").split(" ")
-                rows.append([_tok(t) for t in toks])
-        raw = np.array(rows, dtype=np.float64)
+        packed, n, _ = read_text_packed(str(path_or_matrix))      # native reader: text -> 2-bit codes, no Float64 matrix
+        return unpack2(packed, n)
     keep = ~np.isnan(raw).any(axis=0)
     raw = raw[:, keep]
     ok = np.isin(raw, (0.0, 1.0, 2.0)).all(axis=0)
     if not ok.all():
         raise ValueError("genotype codes must be 0/1/2 for packed storage; columns %s are not" % np.where(~ok)[0][:10])
     return np.asfortranarray(raw.astype(np.int8))
+
+
+def read_text_packed(path: str):
+    """Native reader of the reference's genotype text format (prepMatVec.jl:116-118) straight to 2-bit codes:
+    returns (packed uint8 [ceil(n/4), p_kept] Fortran order, n, keep mask over the file's columns)."""
+    lib = L.lib()
+    n, p = C.c_int64(), C.c_int64()
+    rc = lib.ngp_read_text_genotypes(path.encode(), C.byref(n), C.byref(p), None, 0, None, None)
+    if rc != 0:
+        raise L.NgpError(rc, f"cannot read {path}")
+    ld = (n.value + 3) // 4
+    packed = np.zeros((ld, p.value), dtype=np.uint8, order="F")
+    keep = np.zeros(p.value, dtype=np.uint8)
+    pk = C.c_int64()
+    rc = lib.ngp_read_text_genotypes(path.encode(), C.byref(n), C.byref(p), _p(packed), ld, _p(keep), C.byref(pk))
+    if rc == L.EDATA:
+        raise ValueError(f"{path}: genotype codes must be 0/1/2 (packed storage) in rows of equal length")
+    if rc != 0:
+        raise L.NgpError(rc, f"cannot read {path}")
+    return np.asfortranarray(packed[:, :pk.value]), n.value, keep.astype(bool)
+
+
+def read_bed_packed(path: str, n: int, p: int, count_a1: bool = True):
+    """PLINK .bed (SNP-major) -> 2-bit codes; variants with missing calls are dropped like columns with missing values."""
+    lib = L.lib()
+    ld = (n + 3) // 4
+    packed = np.zeros((ld, p), dtype=np.uint8, order="F")
+    keep = np.zeros(p, dtype=np.uint8)
+    pk = C.c_int64()
+    rc = lib.ngp_read_bed_genotypes(path.encode(), n, p, int(count_a1), _p(packed), ld, _p(keep), C.byref(pk))
+    if rc != 0:
+        raise L.NgpError(rc, f"cannot read {path} as a SNP-major PLINK .bed of {n} samples x {p} variants")
+    return np.asfortranarray(packed[:, :pk.value]), keep.astype(bool)
+
+
+def unpack2(packed: np.ndarray, n: int) -> np.ndarray:
+    ld, p = packed.shape
+    out = np.empty((n, p), dtype=np.int8, order="F")
+    rc = L.lib().ngp_unpack2(_p(np.asfortranarray(packed)), n, p, ld, _p(out), n)
+    if rc != 0:
+        raise L.NgpError(rc, "ngp_unpack2")
+    return out
 
 
 def _tok(t: str) -> float:
@@ -575,9 +613,21 @@ class ShardedChain:
 @dataclass
 class MarkerTerm:
     name: str
-    codes: np.ndarray            # int8 (n,p)
+    codes: Any                   # int8 (n,p), or None when `packed` is given
     map: Any = None              # map file path / dict or None
     levels: list = field(default_factory=list)
+    packed: Any = None           # uint8 (ceil(n/4), p) 2-bit codes from the native readers (NGP_GENO_PACKED2)
+    n: int = 0                   # individuals (needed with `packed`)
+
+    @property
+    def p(self) -> int:
+        return self.packed.shape[1] if self.packed is not None else self.codes.shape[1]
+
+    def upload(self, sampler: "Sampler", sid: int) -> None:
+        if self.packed is not None:
+            sampler.upload_genotypes(sid, self.packed, fmt=L.GENO_PACKED2, n=self.n)
+        else:
+            sampler.upload_genotypes(sid, self.codes)
 
 
 def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict, summaryStat: dict | None, outPut: str | None,
@@ -597,8 +647,8 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
         return _getMME_tuple(sampler, Y, M, priorVCV, tuples, outPut, intercept, df_e, scale_e)
     info = []
     for sid, term in enumerate(M):
-        sampler.upload_genotypes(sid, term.codes)
-        p = term.codes.shape[1]
+        term.upload(sampler, sid)
+        p = term.p
         pr = priorVCV.get(term.name)
         lhs0 = rhs0 = None
         if term.name in summaryStat:                                           # mme.jl:314-322
@@ -670,8 +720,8 @@ def _getMME_tuple(sampler, Y, M, priorVCV, tuples, outPut, intercept, df_e, scal
     k = len(names)
     V = np.asarray(pr.v, dtype=np.float64).reshape(k, k)
     for sid, nm in enumerate(names):
-        sampler.upload_genotypes(sid, by_name[nm].codes)
-    p = by_name[names[0]].codes.shape[1]
+        by_name[nm].upload(sampler, sid)
+    p = by_name[names[0]].p
     if maps[0] is None or maps[0] == "":                                          # mme.jl:470-481
         if pr.r == 1:
             region_off = np.arange(p + 1, dtype=np.int64)
@@ -759,8 +809,18 @@ def runLMEM(formula: str, userData, nChain: int, nBurn: int, nThin: int, outFold
             if not m:
                 raise NotImplementedError(f"term '{t}' is outside the B200 hot path (stays in Julia)")
             name, path, mp = m.group(1), m.group(2).strip("\"'"), (m.group(3) or "").strip("\"'")
-            codes = prep_snp(matrices[name]) if (matrices and name in matrices) else prep_snp(path)
-            M.append(MarkerTerm(name, codes, mp or None))
+            if matrices and name in matrices:
+                M.append(MarkerTerm(name, prep_snp(matrices[name]), mp or None))
+            elif path.lower().endswith(".bed"):
+                # PLINK triple: sample / variant counts from the .fam / .bim files next to the .bed
+                stem = path[:-4]
+                n_s = sum(1 for ln in open(stem + ".fam") if ln.strip())
+                p_v = sum(1 for ln in open(stem + ".bim") if ln.strip())
+                packed, _ = read_bed_packed(path, n_s, p_v)
+                M.append(MarkerTerm(name, None, mp or None, packed=packed, n=n_s))
+            else:
+                packed, n_s, _ = read_text_packed(path)      # text -> 2-bit codes -> device, never a Float64 matrix (prepMatVec.jl:116-120)
+                M.append(MarkerTerm(name, None, mp or None, packed=packed, n=n_s))
     Y = np.asarray(userData[lhs], dtype=np.float64)
     folderHandler(outFolder)
     sampler = sampler or Sampler(device)

@@ -64,3 +64,81 @@ def test_synth_codes_match_oracle_generator():
     b = O.synth_codes(12, 203, 0, 40, pr["thr0"], pr["thr1"])
     assert np.array_equal(a, b)
     assert set(np.unique(a)) <= {0, 1, 2}
+
+
+# ----------------------------------------------------------------------------- native ingest, host-only code of libngp
+def _py_parse(path):
+    """The reference's rule restated in Python: split on ONE space, "" / NA / NaN / missing are missing, a column with a missing
+    value is dropped (prepMatVec.jl:116-118)."""
+    rows = []
+    with open(path, newline="") as f:
+        for line in f.read().split("\n"):
+            line = line.rstrip("\r")
+            if line == "":
+                continue
+            rows.append([np.nan if t.strip() == "" or t.strip().upper() in ("NA", "NAN", "MISSING") else float(t) for t in line.split(" ")])
+    raw = np.array(rows)
+    keep = ~np.isnan(raw).any(axis=0)
+    return raw[:, keep].astype(np.int8), keep
+
+
+@pytest.mark.parametrize("n,p,eol", [(7, 5, "\n"), (64, 33, "\n"), (101, 17, "\r\n")])
+def test_native_text_reader_is_bit_exact_and_drops_columns_with_missing(tmp_path, n, p, eol):
+    from nextgp.jl_b200 import api
+    rng = np.random.default_rng(n)
+    codes = rng.integers(0, 3, size=(n, p))
+    toks = codes.astype(str).astype(object)
+    toks[rng.integers(0, n), 1] = "NA"
+    toks[rng.integers(0, n), p - 1] = ""
+    toks[0, 3] = "missing"
+    toks[n - 1, 0] = "2.0"
+    codes[n - 1, 0] = 2
+    f = tmp_path / "geno.txt"
+    f.write_bytes((eol.join(" ".join(r) for r in toks) + eol).encode())
+    packed, n_read, keep = api.read_text_packed(str(f))
+    ref, keep_ref = _py_parse(str(f))
+    assert n_read == n and np.array_equal(keep, keep_ref) and keep.sum() == p - 3
+    assert np.array_equal(api.unpack2(packed, n), ref)
+    assert np.array_equal(ngp.prep_snp(str(f)), ref)
+    # the padding bits of the last byte of every column are zero (device packing relies on it)
+    if n % 4:
+        assert not (packed[-1] >> (2 * (n % 4))).any()
+
+
+def test_native_text_reader_rejects_dosages_and_ragged_rows(tmp_path):
+    from nextgp.jl_b200 import api
+    f = tmp_path / "g.txt"
+    f.write_text("0 1 2\n1 0.5 2\n")
+    with pytest.raises(ValueError):
+        api.read_text_packed(str(f))
+    f.write_text("0 1 2\n1 0\n")
+    with pytest.raises(ValueError):
+        api.read_text_packed(str(f))
+
+
+@pytest.mark.parametrize("n,p", [(8, 3), (13, 40), (1001, 7)])
+def test_plink_bed_reader_is_bit_exact(tmp_path, n, p):
+    from nextgp.jl_b200 import api
+    rng = np.random.default_rng(p)
+    a1 = rng.integers(0, 3, size=(n, p))                 # copies of allele A1
+    miss = np.zeros((n, p), dtype=bool)
+    miss[rng.integers(0, n), 2] = True
+    enc = np.where(a1 == 2, 0b00, np.where(a1 == 1, 0b10, 0b11))
+    enc = np.where(miss, 0b01, enc)
+    bpc = (n + 3) // 4
+    bed = bytearray([0x6c, 0x1b, 0x01])
+    for j in range(p):
+        col = np.zeros(bpc * 4, dtype=np.uint8)
+        col[:n] = enc[:, j]
+        b = col[0::4] | (col[1::4] << 2) | (col[2::4] << 4) | (col[3::4] << 6)
+        bed += bytes(b.astype(np.uint8))
+    f = tmp_path / "x.bed"
+    f.write_bytes(bytes(bed))
+    for count_a1 in (True, False):
+        packed, keep = api.read_bed_packed(str(f), n, p, count_a1=count_a1)
+        assert keep.sum() == p - 1 and not keep[2]
+        want = (a1 if count_a1 else 2 - a1)[:, keep].astype(np.int8)
+        assert np.array_equal(api.unpack2(packed, n), want)
+    f.write_bytes(bytes([0x6c, 0x1b, 0x00]) + bytes(bed[3:]))
+    with pytest.raises(ngp.NgpError):
+        api.read_bed_packed(str(f), n, p)               # individual-major files are not supported
