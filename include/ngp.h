@@ -38,7 +38,9 @@ enum ngp_status {
 };
 
 /* priorVCV[pSet].name dispatch of mme.jl:331,350,362 */
-enum ngp_method { NGP_BAYESPR = 0, NGP_BAYESB = 1, NGP_BAYESC = 2 };
+enum ngp_method { NGP_BAYESPR = 0, NGP_BAYESB = 1, NGP_BAYESC = 2,
+                  NGP_BAYESR = 3 /* mme.jl:374-383; sampled by the per-marker kernel */ };
+#define NGP_MAX_CLASSES 8
 
 /* host input formats for ngp_upload_genotypes */
 enum ngp_geno_format {
@@ -91,6 +93,11 @@ typedef struct ngp_prior {
     const int64_t* region_off;   /* BayesPR: n_regions+1 offsets, 0-based half-open; NULL = one region */
     const double* lhs0;          /* p or NULL: M[pSet][:lhs] summary-stat precision (mme.jl:314-322) */
     const double* rhs0;          /* p or NULL: M[pSet][:rhs]                                   */
+    /* BayesR only (runTime.jl:78-93, mme.jl:374-383)                                            */
+    int32_t n_class;             /* length(class) <= NGP_MAX_CLASSES                           */
+    int32_t pad_;
+    const double* v_class;       /* [n_class] M[pSet][:vClass], e.g. 0, 1e-4, 1e-3, 1e-2        */
+    const double* pi_class;      /* [n_class] starting / fixed class proportions (est_pi: Dirichlet update, functions.jl:284-288) */
 } ngp_prior;
 
 /* -------------------------------------------------------------------------
@@ -136,10 +143,10 @@ typedef struct ngp_replay {
     int32_t n_sets;
     const double* chi2_e;                  /* [n_iter]       functions.jl:524               */
     const double* z_mu;                    /* [n_iter]       functions.jl:45                */
-    const double* u[NGP_MAX_SETS];         /* [n_iter][p]    functions.jl:174,216 (B/C)     */
+    const double* u[NGP_MAX_SETS];         /* [n_iter][p]    functions.jl:174,216 (B/C); BayesR: [n_iter][p][n_class], one per comparison (functions.jl:261) */
     const double* z[NGP_MAX_SETS];         /* [n_iter][p]    functions.jl:494               */
     const double* chi2_b[NGP_MAX_SETS];    /* [n_iter][nvar] functions.jl:510 (nvar: PR=n_regions, B=p, C=1) */
-    const double* beta_pi[NGP_MAX_SETS];   /* [n_iter]       functions.jl:532               */
+    const double* beta_pi[NGP_MAX_SETS];   /* [n_iter]       functions.jl:532; BayesR: [n_iter][n_class] the Dirichlet draw (functions.jl:537) */
 } ngp_replay;
 
 /* Chain state, the arguments M[mSet].funct mutates (functions.jl:118,157,197)
@@ -245,12 +252,14 @@ int ngp_run(ngp_handle* h, int32_t n_iter);
 /* ngp_sweep replaces ONE call M[mSet].funct(mSet,M,beta,delta,ycorr,varE,varBeta)
  * (samplers.jl:52; functions.jl:118,157,197): host buffers in, mutated in place. */
 int ngp_sweep(ngp_handle* h, int set_id, double* ycorr, double varE,
-              double* beta, int64_t* delta, double* varBeta, double* piHat);
+              double* beta, int64_t* delta, double* varBeta, double* piHat);   /* piHat: 2 values (B/C) or n_class (BayesR) */
 /* ngp_joint_sweep replaces ONE call sampleBayesPR!(mSet::Tuple, M, beta, delta, ycorr, varE, varBeta)
  * (functions.jl:140-154): beta is k x p row-major (row b = breed b), varBeta is n_regions x k x k.          */
 int ngp_joint_sweep(ngp_handle* h, double* ycorr, double varE, double* beta, double* varBeta);
 /* effects (k x p row-major) and region covariances (n_regions x k x k) of the tuple; NULL members are skipped */
 int ngp_get_joint_state(ngp_handle* h, double* beta, double* varBeta);
+/* BayesR: class proportions M[pSet][:piHat] (n_class values); ngp_state.delta holds the 1-based class of every locus */
+int ngp_get_class_pi(ngp_handle* h, int set_id, double* piHat);
 int ngp_get_state(ngp_handle* h, ngp_state* out);
 int ngp_set_state(ngp_handle* h, const ngp_state* in);
 /* running posterior sums since the last reset: sum(beta), sum(beta^2), sum(delta) per marker */

@@ -53,6 +53,15 @@ class BayesCType:
 
 
 @dataclass
+class BayesRType:
+    pi: Any                      # vector of class proportions (runTime.jl:78-84)
+    class_: Any                  # vector of class scales, increasing, e.g. [0.0, 0.0001, 0.001, 0.01]
+    v: float
+    name: str = "BayesR"
+    estimatePi: bool = False
+
+
+@dataclass
 class RandomEffectType:
     str: Any
     v: float
@@ -78,6 +87,11 @@ def BayesB(pi: float, v: float, name: str = "BayesB", estimatePi: bool = False) 
 def BayesC(pi: float, v: float, name: str = "BayesC", estimatePi: bool = False) -> BayesCType:
     """runTime.jl:70-76"""
     return BayesCType(float(pi), float(v), name, bool(estimatePi))
+
+
+def BayesR(pi, class_, v: float, name: str = "BayesR", estimatePi: bool = False) -> BayesRType:
+    """runTime.jl:87-93."""
+    return BayesRType(np.asarray(pi, dtype=np.float64), np.asarray(class_, dtype=np.float64), float(v), name, bool(estimatePi))
 
 
 def Random(str_: Any, v: float, type: int = 1) -> RandomEffectType:
@@ -375,8 +389,12 @@ class Sampler:
 
     def set_prior(self, set_id: int, method: int, df: float, scale: float, var_init: float, pi_in: float = 0.0,
                   est_pi: bool = False, region_off: np.ndarray | None = None, lhs0: np.ndarray | None = None,
-                  rhs0: np.ndarray | None = None) -> None:
+                  rhs0: np.ndarray | None = None, v_class: np.ndarray | None = None, pi_class: np.ndarray | None = None) -> None:
         pr = L.Prior()
+        if method == L.BAYESR:
+            v_class = np.ascontiguousarray(v_class, dtype=np.float64)
+            pi_class = np.ascontiguousarray(pi_class, dtype=np.float64)
+            pr.n_class, pr.v_class, pr.pi_class = len(v_class), _p(v_class), _p(pi_class)
         pr.method, pr.est_pi, pr.df, pr.scale, pr.var_init, pr.pi_in = method, int(est_pi), df, scale, var_init, pi_in
         p = self.sets[set_id]["p"]
         if region_off is not None:
@@ -390,7 +408,7 @@ class Sampler:
             pr.rhs0 = _p(rhs0)
         self._ck(self._lib.ngp_set_prior(self._h, set_id, C.byref(pr)))
         nvar = (len(region_off) - 1 if region_off is not None else 1) if method == L.BAYESPR else (p if method == L.BAYESB else 1)
-        self.sets[set_id].update(method=method, nvar=nvar, est_pi=bool(est_pi))
+        self.sets[set_id].update(method=method, nvar=nvar, est_pi=bool(est_pi), n_class=(len(v_class) if method == L.BAYESR else 0))
 
     def set_joint_prior(self, set_ids: list[int], df: float, scale: np.ndarray, var_init: np.ndarray,
                         region_off: np.ndarray | None = None) -> None:
@@ -448,10 +466,13 @@ class Sampler:
         keep += [chi2_e, z_mu]
         rp.chi2_e, rp.z_mu = _p(chi2_e), _p(z_mu)
         for s in range(rp.n_sets):
+            if "dir_pi" in logs[0]["sets"][s]:                      # BayesR log: u [p, n_class], the Dirichlet draw instead of the Beta draw
+                for g in logs:
+                    g["sets"][s].setdefault("beta_pi", g["sets"][s]["dir_pi"])
             u = np.ascontiguousarray(np.stack([g["sets"][s]["u"] for g in logs]), dtype=np.float64)
             z = np.ascontiguousarray(np.stack([g["sets"][s]["z"] for g in logs]), dtype=np.float64)
             cb = np.ascontiguousarray(np.stack([g["sets"][s]["chi2_b"] for g in logs]), dtype=np.float64)
-            bp = np.array([g["sets"][s]["beta_pi"] for g in logs], dtype=np.float64)
+            bp = np.ascontiguousarray(np.array([g["sets"][s]["beta_pi"] for g in logs], dtype=np.float64))
             keep += [u, z, cb, bp]
             rp.u[s], rp.z[s], rp.chi2_b[s], rp.beta_pi[s] = _p(u), _p(z), _p(cb), _p(bp)
         self._ck(self._lib.ngp_set_replay(self._h, C.byref(rp)))
@@ -479,9 +500,16 @@ class Sampler:
             bufs[s] = (b, d, v)
             st.beta[s], st.delta[s], st.varBeta[s] = _p(b), _p(d), _p(v)
         self._ck(self._lib.ngp_get_state(self._h, C.byref(st)))
-        return {"e": e, "mu": st.mu, "varE": st.varE, "iter": st.iter,
-                "sets": {s: {"beta": b, "delta": d, "varBeta": v, "piHat": np.array([st.pi[s][0], st.pi[s][1]])}
-                         for s, (b, d, v) in bufs.items()}}
+        out = {"e": e, "mu": st.mu, "varE": st.varE, "iter": st.iter,
+               "sets": {s: {"beta": b, "delta": d, "varBeta": v, "piHat": np.array([st.pi[s][0], st.pi[s][1]])}
+                        for s, (b, d, v) in bufs.items()}}
+        for s in bufs:
+            nc = self.sets[s].get("n_class", 0)
+            if nc:
+                ph = np.empty(nc)
+                self._ck(self._lib.ngp_get_class_pi(self._h, s, _p(ph)))
+                out["sets"][s]["piHat"] = ph
+        return out
 
     def set_state(self, e=None, mu=0.0, varE=0.0, iter=0, sets: dict | None = None) -> None:
         st = L.State()
@@ -681,13 +709,17 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
                 method, region_off = L.BAYESB, None
             elif name == "BayesC":
                 method, region_off = L.BAYESC, None
+            elif name == "BayesR":                                              # mme.jl:374-383
+                method, region_off, pi = L.BAYESR, None, 0.0
             else:
                 raise NotImplementedError(f"{name} stays in Julia: SURVEY §8(f2)")
         df = 3.0 + 1.0                                                          # mme.jl:493 (scalar v)
         scale = v * (df - 2.0) / df                                             # mme.jl:501
-        sampler.set_prior(sid, method, df, scale, v, pi_in=pi, est_pi=est, region_off=region_off, lhs0=lhs0, rhs0=rhs0)
+        extra = dict(v_class=pr.class_, pi_class=pr.pi) if name == "BayesR" else {}
+        sampler.set_prior(sid, method, df, scale, v, pi_in=pi, est_pi=est, region_off=region_off, lhs0=lhs0, rhs0=rhs0, **extra)
         nvar = sampler.sets[sid]["nvar"]
-        info.append({"name": term.name, "method": name, "p": p, "nvar": nvar, "df": df, "scale": scale})
+        info.append({"name": term.name, "method": name, "p": p, "nvar": nvar, "df": df, "scale": scale,
+                     "n_pi": len(pr.class_) if name == "BayesR" else 2})
     sampler.set_phenotype(Y)
     sampler.set_residual_prior(df_e, scale_e)
     sampler.set_intercept(intercept)
@@ -697,8 +729,8 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
             levels = term.levels or [f"M{i}" for i in range(1, inf["p"] + 1)]
             outMCMC(outPut, f"beta{term.name}", [levels])
             outMCMC(outPut, f"delta{term.name}", [levels])
-            if inf["method"] in ("BayesB", "BayesC"):
-                outMCMC(outPut, f"pi{term.name}", [["pi1", "pi2"]])
+            if inf["method"] in ("BayesB", "BayesC", "BayesR"):                  # mme.jl:571-572
+                outMCMC(outPut, f"pi{term.name}", [[f"pi{v}" for v in range(1, inf["n_pi"] + 1)]])
         for term, inf in zip(M, info):
             outMCMC(outPut, f"var{term.name}", [[f"reg_{r}" for r in range(1, inf["nvar"] + 1)]])
         outMCMC(outPut, "varE", [["e"]])
@@ -768,7 +800,7 @@ def runSampler(sampler: Sampler, M: list[MarkerTerm], info: dict, chainLength: i
             for sid, (term, inf) in enumerate(zip(M, info["sets"])):
                 outMCMC(outPut, f"beta{term.name}", st["sets"][sid]["beta"])
                 outMCMC(outPut, f"delta{term.name}", st["sets"][sid]["delta"])
-                if inf["method"] in ("BayesB", "BayesC"):
+                if inf["method"] in ("BayesB", "BayesC", "BayesR"):              # samplers.jl:82
                     outMCMC(outPut, f"pi{term.name}", st["sets"][sid]["piHat"])
             for sid, term in enumerate(M):
                 if not info.get("tuple"):

@@ -191,7 +191,9 @@ struct SetHost {
     uint8_t* geno = nullptr;
     double* consts = nullptr;
     int32_t *gx = nullptr, *colsum = nullptr, *colsumsq = nullptr, *delta = nullptr, *region_of = nullptr;
-    double *d = nullptr, *mean = nullptr, *beta = nullptr, *varBeta = nullptr, *pi = nullptr;
+    double *d = nullptr, *mean = nullptr, *beta = nullptr, *varBeta = nullptr, *pi = nullptr, *pi_class = nullptr;
+    int n_class = 0;
+    double v_class[kMaxClass] = {0.0};
     double *lhs0 = nullptr, *rhs0 = nullptr, *sum_beta = nullptr, *sum_beta2 = nullptr, *sum_delta = nullptr;
     int64_t* region_off = nullptr;
     double *rp_u = nullptr, *rp_z = nullptr, *rp_chi2b = nullptr, *rp_betapi = nullptr;
@@ -298,7 +300,7 @@ static void free_joint(JointHost& j)
 static void free_set(SetHost& s)
 {
     cudaFree(s.geno); cudaFree(s.consts); cudaFree(s.gx); cudaFree(s.colsum); cudaFree(s.colsumsq); cudaFree(s.delta); cudaFree(s.region_of);
-    cudaFree(s.d); cudaFree(s.mean); cudaFree(s.beta); cudaFree(s.varBeta); cudaFree(s.pi);
+    cudaFree(s.d); cudaFree(s.mean); cudaFree(s.beta); cudaFree(s.varBeta); cudaFree(s.pi); cudaFree(s.pi_class);
     cudaFree(s.lhs0); cudaFree(s.rhs0); cudaFree(s.sum_beta); cudaFree(s.sum_beta2); cudaFree(s.sum_delta);
     cudaFree(s.region_off); cudaFree(s.rp_u); cudaFree(s.rp_z); cudaFree(s.rp_chi2b); cudaFree(s.rp_betapi);
     s = SetHost();
@@ -729,9 +731,14 @@ int ngp_set_prior(ngp_handle* h, int set_id, const ngp_prior* pr)
     SetHost& S = h->sets[set_id];
     if (S.joint_member) return fail(h, NGP_EINVAL, "ngp_set_prior: set %d is a member of a tuple (ngp_set_joint_prior)", set_id);
     if (h->joint.active) return fail(h, NGP_EUNSUPPORTED, "ngp_set_prior: a handle with a tuple of marker sets samples only the tuple");
-    if (pr->method != NGP_BAYESPR && pr->method != NGP_BAYESB && pr->method != NGP_BAYESC) return fail(h, NGP_EINVAL, "ngp_set_prior: unknown method %d", pr->method);
+    if (pr->method != NGP_BAYESPR && pr->method != NGP_BAYESB && pr->method != NGP_BAYESC && pr->method != NGP_BAYESR) return fail(h, NGP_EINVAL, "ngp_set_prior: unknown method %d", pr->method);
     if (!(pr->df > 0.0) || !(pr->var_init >= 0.0)) return fail(h, NGP_EINVAL, "ngp_set_prior: df must be > 0 and var_init >= 0");
-    if (pr->method != NGP_BAYESPR && !(pr->pi_in > 0.0 && pr->pi_in < 1.0)) return fail(h, NGP_EINVAL, "ngp_set_prior: pi_in must be inside (0,1)");
+    if ((pr->method == NGP_BAYESB || pr->method == NGP_BAYESC) && !(pr->pi_in > 0.0 && pr->pi_in < 1.0)) return fail(h, NGP_EINVAL, "ngp_set_prior: pi_in must be inside (0,1)");
+    if (pr->method == NGP_BAYESR) {
+        if (pr->n_class < 1 || pr->n_class > kMaxClass || !pr->v_class || !pr->pi_class) return fail(h, NGP_EINVAL, "ngp_set_prior: BayesR needs 1..%d classes with v_class and pi_class", kMaxClass);
+        for (int v = 0; v < pr->n_class; ++v)
+            if (!(pr->v_class[v] >= 0.0) || !(pr->pi_class[v] > 0.0)) return fail(h, NGP_EINVAL, "ngp_set_prior: BayesR class %d: scale must be >= 0 and proportion > 0", v);
+    }
     CU(cudaSetDevice(h->device));
     S.method = pr->method; S.est_pi = pr->est_pi ? 1 : 0; S.df = pr->df; S.scale = pr->scale; S.var_init = pr->var_init; S.pi_in = pr->pi_in;
     cudaFree(S.region_off); S.region_off = nullptr;
@@ -755,12 +762,21 @@ int ngp_set_prior(ngp_handle* h, int set_id, const ngp_prior* pr)
         }
     } else if (pr->method == NGP_BAYESB) S.nvar = S.p;
     else S.nvar = 1;
+    S.n_class = 0;
+    if (pr->method == NGP_BAYESR) {
+        S.n_class = pr->n_class;
+        double pc[2 * kMaxClass];
+        for (int v = 0; v < S.n_class; ++v) { S.v_class[v] = pr->v_class[v]; pc[v] = pr->pi_class[v]; pc[S.n_class + v] = log(pr->pi_class[v]); }   // mme.jl:375,383
+        CU(dalloc(&S.pi_class, 2 * kMaxClass));
+        CU(cudaMemcpyAsync(S.pi_class, pc, sizeof(double) * 2 * S.n_class, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
     CU(dalloc(&S.varBeta, S.nvar));
     fill_kernel<<<(unsigned)((S.nvar + 255) / 256), 256, 0, h->stream>>>(S.varBeta, S.nvar, pr->var_init);     // mme.jl:516
     CU(cudaGetLastError());
     CU(dalloc(&S.pi, 4));
     double pi4[4] = {0.0, 1.0, -INFINITY, 0.0};
-    if (pr->method != NGP_BAYESPR) { pi4[0] = 1.0 - pr->pi_in; pi4[1] = pr->pi_in; pi4[2] = log(1.0 - pr->pi_in); pi4[3] = log(pr->pi_in); }   // mme.jl:351,359
+    if (pr->method == NGP_BAYESB || pr->method == NGP_BAYESC) { pi4[0] = 1.0 - pr->pi_in; pi4[1] = pr->pi_in; pi4[2] = log(1.0 - pr->pi_in); pi4[3] = log(pr->pi_in); }   // mme.jl:351,359
     CU(cudaMemcpyAsync(S.pi, pi4, sizeof pi4, cudaMemcpyHostToDevice, h->stream));
     cudaFree(S.lhs0); S.lhs0 = nullptr; cudaFree(S.rhs0); S.rhs0 = nullptr;
     if (pr->lhs0) { CU(dalloc(&S.lhs0, S.p)); CU(cudaMemcpyAsync(S.lhs0, pr->lhs0, sizeof(double) * S.p, cudaMemcpyHostToDevice, h->stream)); }
@@ -809,12 +825,13 @@ int ngp_set_replay(ngp_handle* h, const ngp_replay* log)
         CU(cpy(h, S.rp_chi2b, log->chi2_b[s], sizeof(double) * (size_t)ni * S.nvar, cudaMemcpyHostToDevice));
         if (S.method != NGP_BAYESPR) {
             if (!log->u[s]) return fail(h, NGP_EINVAL, "ngp_set_replay: u missing for set %d", s);
-            CU(dalloc(&S.rp_u, (size_t)ni * S.p));
-            CU(cpy(h, S.rp_u, log->u[s], sizeof(double) * (size_t)ni * S.p, cudaMemcpyHostToDevice));
+            const size_t per_u = (S.method == NGP_BAYESR) ? (size_t)S.n_class : 1, per_pi = per_u;
+            CU(dalloc(&S.rp_u, (size_t)ni * S.p * per_u));
+            CU(cpy(h, S.rp_u, log->u[s], sizeof(double) * (size_t)ni * S.p * per_u, cudaMemcpyHostToDevice));
             if (S.est_pi) {
                 if (!log->beta_pi[s]) return fail(h, NGP_EINVAL, "ngp_set_replay: beta_pi missing for set %d", s);
-                CU(dalloc(&S.rp_betapi, ni));
-                CU(cpy(h, S.rp_betapi, log->beta_pi[s], sizeof(double) * ni, cudaMemcpyHostToDevice));
+                CU(dalloc(&S.rp_betapi, ni * per_pi));
+                CU(cpy(h, S.rp_betapi, log->beta_pi[s], sizeof(double) * ni * per_pi, cudaMemcpyHostToDevice));
             }
         }
     }
@@ -836,7 +853,8 @@ static int sync_sets(ngp_handle* h)
         if (!S.have_geno || !S.have_prior) continue;
         SetDev& D = sd[s];
         D.p = S.p; D.p_pad = S.p_pad; D.method = S.method; D.est_pi = S.est_pi; D.n_regions = S.n_regions; D.nvar = S.nvar;
-        D.df = S.df; D.scale = S.scale; D.geno = S.geno; D.gx = S.gx; D.consts = S.consts; D.colsum = S.colsum; D.d = S.d; D.mean = S.mean;
+        D.df = S.df; D.scale = S.scale; D.n_class = S.n_class; D.pi_class = S.pi_class; memcpy(D.v_class, S.v_class, sizeof D.v_class);
+        D.geno = S.geno; D.gx = S.gx; D.consts = S.consts; D.colsum = S.colsum; D.d = S.d; D.mean = S.mean;
         D.beta = S.beta; D.delta = S.delta; D.varBeta = S.varBeta; D.pi = S.pi; D.region_of = S.region_of; D.region_off = S.region_off;
         D.lhs0 = S.lhs0; D.rhs0 = S.rhs0;
         D.rp_u = S.rp_u; D.rp_z = S.rp_z; D.rp_chi2b = S.rp_chi2b; D.rp_betapi = S.rp_betapi;
@@ -877,6 +895,7 @@ static int check_kernel_error(ngp_handle* h)
     int kerr = 0;
     CU(cpy(h, &kerr, &h->sync->err, sizeof(int), cudaMemcpyDeviceToHost));
     if (kerr & 2) return fail(h, NGP_ENUMERIC, "a covariance matrix of the tuple sampler is not positive definite");
+    if (kerr & 4) return fail(h, NGP_ENUMERIC, "BayesR: no class reached its uniform (the reference's findfirst returns nothing here)");
     if (kerr) return fail(h, NGP_ERANGE, "fixed-point reduction range exceeded (residual grew by more than 2^4 within an iteration)");
     return NGP_OK;
 }
@@ -956,6 +975,8 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     if (rc) return rc;
     Params P{};
     fill_params(h, P, n_iter, set_mask, do_varE, do_mu, varE_in, accumulate);
+    for (int s = 0; s < h->n_sets; ++s)
+        if (((set_mask >> s) & 1) && h->sets[s].method == NGP_BAYESR) P.kernel = NGP_KERNEL_LITERAL;     // the class algebra lives in the per-marker sweep
 #define NGP_PICK(PROF, DBG) ((h->B == 64) ? (const void*)gibbs_kernel<64, PROF, DBG> : (h->B == 32) ? (const void*)gibbs_kernel<32, PROF, DBG> : (const void*)gibbs_kernel<16, PROF, DBG>)
     const void* kfn = h->cfg_debug ? NGP_PICK(false, true) : h->cfg_profile ? NGP_PICK(true, false) : NGP_PICK(false, false);
 #undef NGP_PICK
@@ -1011,7 +1032,11 @@ static int push_set_state(ngp_handle* h, int s, const double* beta, const int64_
         CU(cpy(h, S.delta, d32.data(), sizeof(int32_t) * S.p, cudaMemcpyHostToDevice));
     }
     if (varBeta && S.varBeta) CU(cpy(h, S.varBeta, varBeta, sizeof(double) * S.nvar, cudaMemcpyHostToDevice));
-    if (piHat && S.method != NGP_BAYESPR) {
+    if (piHat && S.method == NGP_BAYESR) {
+        double pc[2 * kMaxClass];
+        for (int v = 0; v < S.n_class; ++v) { pc[v] = piHat[v]; pc[S.n_class + v] = log(piHat[v]); }
+        CU(cpy(h, S.pi_class, pc, sizeof(double) * 2 * S.n_class, cudaMemcpyHostToDevice));
+    } else if (piHat && S.method != NGP_BAYESPR) {
         double pi4[4] = {piHat[0], piHat[1], log(piHat[0]), log(piHat[1])};
         CU(cpy(h, S.pi, pi4, sizeof pi4, cudaMemcpyHostToDevice));
     }
@@ -1028,7 +1053,9 @@ static int pull_set_state(ngp_handle* h, int s, double* beta, int64_t* delta, do
         for (int64_t j = 0; j < S.p; ++j) delta[j] = d32[(size_t)j];
     }
     if (varBeta && S.varBeta) CU(cpy(h, varBeta, S.varBeta, sizeof(double) * S.nvar, cudaMemcpyDeviceToHost));
-    if (piHat && S.pi) {
+    if (piHat && S.method == NGP_BAYESR && S.pi_class) {
+        CU(cpy(h, piHat, S.pi_class, sizeof(double) * S.n_class, cudaMemcpyDeviceToHost));
+    } else if (piHat && S.pi) {
         double pi4[4];
         CU(cpy(h, pi4, S.pi, sizeof pi4, cudaMemcpyDeviceToHost));
         piHat[0] = pi4[0]; piHat[1] = pi4[1];
@@ -1254,6 +1281,15 @@ int ngp_joint_sweep(ngp_handle* h, double* ycorr, double varE, double* beta, dou
     return ngp_get_joint_state(h, beta, varBeta);
 }
 
+int ngp_get_class_pi(ngp_handle* h, int set_id, double* piHat)
+{
+    if (!h || !piHat || set_id < 0 || set_id >= NGP_MAX_SETS || h->sets[set_id].method != NGP_BAYESR || !h->sets[set_id].pi_class)
+        return fail(h, NGP_EINVAL, "ngp_get_class_pi: set %d is not a BayesR set", set_id);
+    CU(cudaSetDevice(h->device));
+    CU(cpy(h, piHat, h->sets[set_id].pi_class, sizeof(double) * h->sets[set_id].n_class, cudaMemcpyDeviceToHost));
+    return NGP_OK;
+}
+
 int ngp_get_state(ngp_handle* h, ngp_state* out)
 {
     if (!h || !out) return fail(h, NGP_EINVAL, "ngp_get_state: NULL argument");
@@ -1264,7 +1300,7 @@ int ngp_get_state(ngp_handle* h, ngp_state* out)
     if (out->e && h->e) CU(cpy(h, out->e, h->e, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
     for (int s = 0; s < h->n_sets; ++s) {
         if (!h->sets[s].have_geno || !h->sets[s].have_prior) continue;
-        int rc = pull_set_state(h, s, out->beta[s], out->delta[s], out->varBeta[s], out->pi[s]);
+        int rc = pull_set_state(h, s, out->beta[s], out->delta[s], out->varBeta[s], h->sets[s].method == NGP_BAYESR ? nullptr : out->pi[s]);   // class proportions: ngp_get_class_pi
         if (rc) return rc;
     }
     return NGP_OK;
@@ -1282,7 +1318,7 @@ int ngp_set_state(ngp_handle* h, const ngp_state* in)
     if (in->e) { CU(cpy(h, h->e, in->e, sizeof(double) * h->n, cudaMemcpyHostToDevice)); h->have_y = true; }
     for (int s = 0; s < h->n_sets; ++s) {
         if (!h->sets[s].have_geno || !h->sets[s].have_prior) continue;
-        int rc = push_set_state(h, s, in->beta[s], in->delta[s], in->varBeta[s], in->pi[s]);
+        int rc = push_set_state(h, s, in->beta[s], in->delta[s], in->varBeta[s], h->sets[s].method == NGP_BAYESR ? nullptr : in->pi[s]);
         if (rc) return rc;
     }
     return NGP_OK;

@@ -31,6 +31,7 @@ constexpr int kPrepWarps = 8;          //            (poll accumulators, cross-G
 constexpr int kFirstPrepWarp = 2;
 constexpr int kLimbVers = 16;          // maximum number of versions of the fixed-point residual kept per worker CTA
 
+constexpr int kMaxClass = 8;           // BayesR variance classes
 constexpr int kMaxRanks = 8;           // row shards of one chain (GPUs of one NVSwitch box)
 constexpr int kProf = 32;              // cycle counters per CTA (ngp_get_profile)
 constexpr int kMaxB = 64;              // markers per block: 16, 32 or 64
@@ -75,6 +76,9 @@ struct SetDev {
     const double* rp_z;
     const double* rp_chi2b;
     const double* rp_betapi;
+    int32_t n_class, pad_cls;  // BayesR (method 3): variance classes (functions.jl:241)
+    double v_class[kMaxClass]; //   M.vClass
+    double* pi_class;          //   [2 * n_class] piHat, logPi (mme.jl:375,383)
     double* sum_beta;          // posterior sums [p_pad]
     double* sum_beta2;
     double* sum_delta;

@@ -165,7 +165,7 @@ __device__ __forceinline__ void prep_marker(const Params& P, const SetDev& S, in
         fC = iVarE * ilhs;
         fQSZ = sqrt(ilhs) * z + ((S.method == 2) ? 0.0 : r0 * ilhs);
         fD = d; fBOLD = bold; fMEAN = S.mean[j]; fCS = (double)S.colsum[j];
-        if (S.method != 0) {
+        if (S.method == 1 || S.method == 2) {
             const double u = P.replay ? S.rp_u[rp_row * S.p + j] : stream_uniform(st, P_U, (uint32_t)j);
             const double v0 = d * varE;
             const double v1 = (d * d) * vb + v0;
@@ -174,8 +174,10 @@ __device__ __forceinline__ void prep_marker(const Params& P, const SetDev& S, in
             fT = log(1.0 / u - 1.0);
             if (S.method == 1)
                 fCHI = P.replay ? S.rp_chi2b[rp_row * S.nvar + j] : stream_chisq(st, P_CHI2_B, (uint32_t)j, 0, S.df + 1.0);
-        } else {
+        } else if (S.method == 0) {
             fT = INFINITY;   // BayesPR: always "included"
+        } else {
+            fC = 0.0; fQSZ = z;   // BayesR (per-marker kernel only): F_QSZ carries the normal variate, the class algebra runs in the sweep
         }
     }
     c[F_A * B] = fA; c[F_B * B] = fB; c[F_T * B] = fT; c[F_C * B] = fC; c[F_QSZ * B] = fQSZ;
@@ -394,6 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
             const int method = S.method;
             const int64_t p_real = S.p;
             double acc_bb = 0.0, acc_n = 0.0;          // chain warp: per-lane partials of beta'beta and nLoci
+            double acc_cls = 0.0;                      // BayesR: loci assigned to class `lane`
             if constexpr (PROF) tc = clock64();
 
             if (P.kernel == 0) {
@@ -1076,6 +1079,14 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                 long long* lprev = reinterpret_cast<long long*>(misc + 48);
                 const int nwords = R >> 2;
                 const long long arrivals = (long long)P.Tw_all;       // worker CTAs of all ranks add into every rank's accumulators
+                // BayesR (functions.jl:238-289): lane v of warp 0 owns variance class v
+                const int nc = (S.method == 3) ? S.n_class : 0;
+                double varc_v = 0.0, logpi_v = 0.0, vcls_v = 0.0;
+                if (nc && lane < nc) {
+                    vcls_v = S.v_class[lane];
+                    varc_v = __ldcg(&S.varBeta[0]) * vcls_v;                            // functions.jl:244
+                    logpi_v = __ldcg(&S.pi_class[nc + lane]);
+                }
                 for (int64_t j = 0; j < S.p; ++j, ++rk) {
                     const int k = (int)(j / B), q = (int)(j % B);
                     const uint8_t* tile = S.geno + ((int64_t)t * nblk + k) * L.tile_bytes;
@@ -1107,6 +1118,11 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         const double cA = __ldcg(c + F_A * B), cB = __ldcg(c + F_B * B), cT = __ldcg(c + F_T * B);
                         const double cC = __ldcg(c + F_C * B), cQ = __ldcg(c + F_QSZ * B), d = __ldcg(c + F_D * B);
                         const double bold = __ldcg(c + F_BOLD * B), mean = __ldcg(c + F_MEAN * B), chi = __ldcg(c + F_CHI * B);
+                        double u_v = 0.0;                                               // BayesR: a fresh uniform per comparison (functions.jl:261)
+                        if (nc && lane < nc) {
+                            Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)s};
+                            u_v = P.replay ? S.rp_u[(rp_row * S.p + j) * nc + lane] : stream_uniform(st, P_U, (uint32_t)j, 0, (uint32_t)lane);
+                        }
                         long long* pv = lprev + slot;
                         long long cur;
                         if (sharded) { do { cur = ld_relaxed_s64_sys(acc); } while (((cur - *pv) & 0xFF) != arrivals); }
@@ -1116,6 +1132,33 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         if (lane == 0) *pv = cur;
                         const double r = A - mean * Stot;
                         const double rr = fma(d, bold, r);
+                        if (nc) {
+                            // class likelihoods (functions.jl:250-258), one class per lane
+                            const double iVarE = 1.0 / varE;
+                            const double l0 = S.lhs0 ? S.lhs0[j] : 0.0, r0 = S.rhs0 ? S.rhs0[j] : 0.0;
+                            const double rhs = fma(rr, iVarE, r0);
+                            const double lhs_v = (varc_v == 0.0) ? 0.0 : d * iVarE + l0 + 1.0 / varc_v;
+                            double ex = 0.0;
+                            if (lane < nc) ex = exp((varc_v == 0.0) ? logpi_v : -0.5 * (log(varc_v * lhs_v) - (rhs * rhs) / lhs_v) + logpi_v);
+                            double tot = 0.0;                                           // sum in class order, like sum(ExpLogL)
+                            for (int v = 0; v < nc; ++v) tot += __shfl_sync(0xffffffffu, ex, v);
+                            const double pr = ex / tot;
+                            double cum = 0.0;                                           // cumsum(probs)
+                            for (int v = 0; v < nc; ++v) { const double pv_ = __shfl_sync(0xffffffffu, pr, v); if (v <= lane) cum += pv_; }
+                            const unsigned hit = __ballot_sync(0xffffffffu, lane < nc && cum >= u_v);
+                            if (!hit) atomicOr(&sy->err, 4);                            // findfirst found nothing: the reference throws here
+                            const int cls = hit ? (__ffs(hit) - 1) : 0;
+                            const double varc_c = __shfl_sync(0xffffffffu, varc_v, cls);
+                            const double lhs_c = __shfl_sync(0xffffffffu, lhs_v, cls);
+                            const double vcls_c = __shfl_sync(0xffffffffu, vcls_v, cls);
+                            const double bn = (varc_c != 0.0) ? rhs / lhs_c + sqrt(1.0 / lhs_c) * cQ : 0.0;      // functions.jl:266-268, :275
+                            if (lane == cls) acc_cls += 1.0;                            // nLoci[classSNP] += 1
+                            if (lane == 0) {
+                                misc[40] = bn - bold; misc[41] = mean;
+                                if (varc_c != 0.0) { acc_bb += (bn * bn) / vcls_c; acc_n += 1.0; }               // sumS, nNonZero
+                                if (is_chain) { S.beta[j] = bn; S.delta[j] = cls + 1; }
+                            }
+                        } else {
                         const double dl = fma(cB, rr * rr, cA);
                         const bool in = dl < cT;
                         const double bn = in ? fma(rr, cC, cQ) : 0.0;
@@ -1128,6 +1171,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                 if (S.method != 0) S.delta[j] = in ? 1 : 0;
                                 if (S.method == 1) S.varBeta[j] = in ? (S.scale * S.df + bn * bn) / chi : 0.0;
                             }
+                        }
                         }
                     }
                     __syncthreads();
@@ -1153,7 +1197,26 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
             // ------------------------------------------------------------------ phase 3 (chain CTA)
             const bool regional = (S.method == 0 && S.n_regions > 1);
             const int p3warp = (P.kernel == 0) ? kHelperWarp : 0;     // the warp that accumulated beta'beta and nLoci
-            if (is_chain && warp == p3warp && !regional) {
+            if (is_chain && warp == p3warp && S.method == 3) {
+                const double sumS = warp_sum(acc_bb);
+                const double nnz = warp_sum(acc_n);
+                const int nc = S.n_class;
+                Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)s};
+                if (lane == 0) {                    // functions.jl:281, 518-520
+                    const double chi2 = P.replay ? S.rp_chi2b[rp_row * S.nvar] : stream_chisq(st, P_CHI2_B, 0, 0, S.df + nnz);
+                    S.varBeta[0] = (S.scale * S.df + sumS) / chi2;
+                }
+                if (S.est_pi) {                     // functions.jl:284-288, 536-538: Dirichlet(nLoci .+ 1) = normalised gammas
+                    double gv = 0.0;
+                    if (lane < nc) gv = P.replay ? S.rp_betapi[rp_row * nc + lane] : stream_gamma(st, P_PI_A, 0, (uint32_t)lane, acc_cls + 1.0);
+                    double tg = 0.0;
+                    for (int v = 0; v < nc; ++v) tg += __shfl_sync(0xffffffffu, gv, v);
+                    if (lane < nc) {
+                        const double ph = P.replay ? gv : gv / tg;
+                        S.pi_class[lane] = ph; S.pi_class[nc + lane] = log(ph);
+                    }
+                }
+            } else if (is_chain && warp == p3warp && !regional) {
                 const double bb = warp_sum(acc_bb);
                 const double nl = warp_sum(acc_n);
                 if (lane == 0) {

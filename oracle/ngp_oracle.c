@@ -673,6 +673,111 @@ int ngo_mb_sweep(const ngo_mb_set* S, double* beta /* k x p */, double* varBeta 
 }
 
 /* ------------------------------------------------------------------------- */
+/* BayesR: functions.jl:238-289 (sampleBayesR!), :518-520 (sampleVarBetaR),     */
+/* :536-538 (samplePi(::Vector) = Dirichlet(nLoci .+ 1)); wiring mme.jl:374-383 */
+/* nc variance classes with scales v_class (first is usually 0).  Quirk 11     */
+/* (SURVEY App. D): findfirst(x -> x >= rand(), cumProbs) draws a FRESH uniform */
+/* for every comparison, so the variate log holds nc uniforms per locus.       */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    int64_t n, p;
+    const double* X;          /* n x p column-major, centred                      */
+    const double* mpm;        /* p                                                */
+    const double* lhs0;       /* p or NULL                                        */
+    const double* rhs0;       /* p or NULL                                        */
+    int32_t n_class, est_pi;
+    const double* v_class;    /* n_class (M.vClass)                               */
+    double df, scale;
+    int32_t set_id, pad_;
+} ngo_r_set;
+
+typedef struct {
+    double* beta;             /* p                                                */
+    int64_t* delta;           /* p: class of the locus, 1-based (functions.jl:261) */
+    double* varBeta;          /* 1                                                */
+    double* piHat;            /* n_class                                          */
+    double* logPi;            /* n_class                                          */
+} ngo_r_state;
+
+typedef struct {
+    int32_t replay, pad_;
+    uint64_t seed;
+    uint32_t chain, iter;
+    double* u;                /* p x n_class (row j = the uniforms of locus j)    */
+    double* z;                /* p                                                */
+    double* chi2_b;           /* 1                                                */
+    double* dir_pi;           /* n_class: the Dirichlet draw itself               */
+} ngo_r_variates;
+
+void ngo_r_fill_variates(const ngo_r_set* S, ngo_r_variates* V)
+{
+    ngo_stream s = {V->seed, V->chain, V->iter, (uint32_t)S->set_id};
+    const int nc = S->n_class;
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < S->p; ++j) {
+        for (int v = 0; v < nc; ++v) V->u[j * nc + v] = stream_uniform(&s, NGO_P_U, (uint32_t)j, 0, (uint32_t)v);
+        V->z[j] = stream_normal(&s, NGO_P_Z, (uint32_t)j, 0, 0);
+    }
+}
+
+int ngo_r_sweep(const ngo_r_set* S, ngo_r_state* T, double* e, double varE, ngo_r_variates* V)
+{
+    const int64_t n = S->n, p = S->p;
+    const int nc = S->n_class;
+    if (nc < 1 || nc > 16) return -1;
+    double varc[16], lhs[16], ExpLogL[16];
+    int64_t nLoci[16];
+    int64_t nNonZero = 0;
+    double sumS = 0.0;
+    const double iVarE = 1.0 / varE;
+    for (int v = 0; v < nc; ++v) { varc[v] = T->varBeta[0] * S->v_class[v]; nLoci[v] = 0; }          /* :244 */
+    for (int64_t j = 0; j < p; ++j) {
+        const double* x = S->X + j * n;
+        daxpy(n, T->beta[j], x, e);                                                              /* :249 */
+        const double rhs = ddot(n, x, e) * iVarE + (S->rhs0 ? S->rhs0[j] : 0.0);                  /* :250 */
+        double tot = 0.0;
+        for (int v = 0; v < nc; ++v) {                                                           /* :253-257 */
+            lhs[v] = varc[v] == 0.0 ? 0.0 : S->mpm[j] * iVarE + (S->lhs0 ? S->lhs0[j] : 0.0) + 1.0 / varc[v];
+            const double logLc = varc[v] == 0.0 ? T->logPi[v]
+                                                : -0.5 * (log(varc[v] * lhs[v]) - ((rhs * rhs) / lhs[v])) + T->logPi[v];
+            ExpLogL[v] = exp(logLc);
+            tot += ExpLogL[v];
+        }
+        int cls = -1;
+        double cum = 0.0;
+        for (int v = 0; v < nc; ++v) {                                                           /* :259-261 */
+            cum += ExpLogL[v] / tot;
+            if (cum >= V->u[j * nc + v]) { cls = v; break; }
+        }
+        if (cls < 0) return -2;                                    /* findfirst returned nothing: the reference errors */
+        T->delta[j] = cls + 1;
+        nLoci[cls] += 1;
+        if (varc[cls] != 0.0) {                                                                  /* :265-274 */
+            nNonZero += 1;
+            const double meanBeta = rhs / lhs[cls];
+            const double b = meanBeta + sqrt(1.0 / lhs[cls]) * V->z[j];
+            T->beta[j] = b;
+            daxpy(n, -1.0 * b, x, e);
+            sumS += (b * b) / S->v_class[cls];
+        } else {
+            T->beta[j] = 0.0;                                                                    /* :275 */
+        }
+    }
+    ngo_stream s = {V->seed, V->chain, V->iter, (uint32_t)S->set_id};
+    if (!V->replay) V->chi2_b[0] = stream_chisq(&s, NGO_P_CHI2_B, 0, 0, S->df + (double)nNonZero);
+    T->varBeta[0] = (S->scale * S->df + sumS) / V->chi2_b[0];                                     /* :281, :518-520 */
+    if (S->est_pi) {                                                                             /* :284-288 */
+        if (!V->replay) {
+            double g[16], tg = 0.0;
+            for (int v = 0; v < nc; ++v) { g[v] = stream_gamma(&s, NGO_P_PI_A, 0, (uint32_t)v, (double)nLoci[v] + 1.0); tg += g[v]; }
+            for (int v = 0; v < nc; ++v) V->dir_pi[v] = g[v] / tg;
+        }
+        for (int v = 0; v < nc; ++v) { T->piHat[v] = V->dir_pi[v]; T->logPi[v] = log(V->dir_pi[v]); }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
 /* synthetic genotype generator (SURVEY Appendix C / DESIGN.md §synthetic):    */
 /* code(i,j) from Philox word (i&3) of counter (i>>2, j, 0, 0x47454e4f) under  */
 /* key = seed, compared with per-column 32-bit thresholds.                    */

@@ -60,6 +60,21 @@ class _MbSet(C.Structure):
                 ("df", C.c_double), ("scale", C.c_void_p)]
 
 
+class _RSet(C.Structure):
+    _fields_ = [("n", C.c_int64), ("p", C.c_int64), ("X", C.c_void_p), ("mpm", C.c_void_p), ("lhs0", C.c_void_p),
+                ("rhs0", C.c_void_p), ("n_class", C.c_int32), ("est_pi", C.c_int32), ("v_class", C.c_void_p),
+                ("df", C.c_double), ("scale", C.c_double), ("set_id", C.c_int32), ("pad_", C.c_int32)]
+
+
+class _RState(C.Structure):
+    _fields_ = [("beta", C.c_void_p), ("delta", C.c_void_p), ("varBeta", C.c_void_p), ("piHat", C.c_void_p), ("logPi", C.c_void_p)]
+
+
+class _RVariates(C.Structure):
+    _fields_ = [("replay", C.c_int32), ("pad_", C.c_int32), ("seed", C.c_uint64), ("chain", C.c_uint32), ("iter", C.c_uint32),
+                ("u", C.c_void_p), ("z", C.c_void_p), ("chi2_b", C.c_void_p), ("dir_pi", C.c_void_p)]
+
+
 class _MbVariates(C.Structure):
     _fields_ = [("replay", C.c_int32), ("pad_", C.c_int32), ("seed", C.c_uint64),
                 ("chain", C.c_uint32), ("iter", C.c_uint32), ("z", C.c_void_p),
@@ -102,6 +117,10 @@ def lib():
         L.ngo_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ngo_set_threads.argtypes = [C.c_int]
         L.ngo_max_threads.restype = C.c_int
+        L.ngo_r_sweep.restype = C.c_int
+        L.ngo_r_sweep.argtypes = [C.POINTER(_RSet), C.POINTER(_RState), C.c_void_p, C.c_double, C.POINTER(_RVariates)]
+        L.ngo_r_fill_variates.restype = None
+        L.ngo_r_fill_variates.argtypes = [C.POINTER(_RSet), C.POINTER(_RVariates)]
         L.ngo_mb_sweep.restype = C.c_int
         L.ngo_mb_sweep.argtypes = [C.POINTER(_MbSet), C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(_MbVariates)]
         L.ngo_mb_fill_variates.restype = None
@@ -318,6 +337,53 @@ class OracleChain:
         return {"varE": self.varE, "mu": self.mu, "e": self.e.copy(),
                 "sets": [{"beta": S.beta.copy(), "delta": S.delta.copy(), "varBeta": S.varBeta.copy(),
                           "piHat": S.piHat.copy()} for S in self.sets]}
+
+
+# --------------------------------------------------------------------------- BayesR
+class BayesROracle:
+    """functions.jl:238-289 with the wiring of mme.jl:374-383: variance classes v_class, class proportions pi (Dirichlet update
+    when est_pi), one common variance.  delta holds the 1-based class of every locus."""
+
+    def __init__(self, X: np.ndarray, mpm: np.ndarray, pi: np.ndarray, v_class: np.ndarray, v: float, est_pi: bool = False,
+                 lhs0=None, rhs0=None, set_id: int = 0):
+        self.X = np.asfortranarray(X, dtype=np.float64)
+        self.mpm = np.ascontiguousarray(mpm, dtype=np.float64)
+        self.n, self.p = self.X.shape
+        self.v_class = np.ascontiguousarray(v_class, dtype=np.float64)
+        self.nc = len(self.v_class)
+        self.piHat = np.ascontiguousarray(pi, dtype=np.float64).copy()
+        self.logPi = np.log(self.piHat)                                   # mme.jl:375
+        self.df, self.scale = marker_hyper(v)
+        self.est_pi = est_pi
+        self.lhs0 = None if lhs0 is None else np.ascontiguousarray(lhs0, dtype=np.float64)
+        self.rhs0 = None if rhs0 is None else np.ascontiguousarray(rhs0, dtype=np.float64)
+        self.beta = np.zeros(self.p)
+        self.delta = np.ones(self.p, dtype=np.int64)
+        self.varBeta = np.array([float(v)])
+        self.set_id = set_id
+
+    def sweep(self, e: np.ndarray, varE: float, it: int, seed: int = 0, chain: int = 0, replay: dict | None = None) -> dict:
+        L = lib()
+        S = _RSet()
+        S.n, S.p, S.X, S.mpm = self.n, self.p, _ptr(self.X), _ptr(self.mpm)
+        S.lhs0 = _ptr(self.lhs0) if self.lhs0 is not None else None
+        S.rhs0 = _ptr(self.rhs0) if self.rhs0 is not None else None
+        S.n_class, S.est_pi, S.v_class, S.df, S.scale, S.set_id = self.nc, int(self.est_pi), _ptr(self.v_class), self.df, self.scale, self.set_id
+        T = _RState()
+        T.beta, T.delta, T.varBeta, T.piHat, T.logPi = _ptr(self.beta), _ptr(self.delta), _ptr(self.varBeta), _ptr(self.piHat), _ptr(self.logPi)
+        if replay is None:
+            u, z, c2, dp = np.zeros((self.p, self.nc)), np.zeros(self.p), np.zeros(1), np.zeros(self.nc)
+        else:
+            u = np.ascontiguousarray(replay["u"], dtype=np.float64).copy(); z = np.ascontiguousarray(replay["z"], dtype=np.float64).copy()
+            c2 = np.ascontiguousarray(replay["chi2_b"], dtype=np.float64).copy(); dp = np.ascontiguousarray(replay["dir_pi"], dtype=np.float64).copy()
+        V = _RVariates()
+        V.replay, V.seed, V.chain, V.iter = int(replay is not None), seed, chain, it
+        V.u, V.z, V.chi2_b, V.dir_pi = _ptr(u), _ptr(z), _ptr(c2), _ptr(dp)
+        if replay is None:
+            L.ngo_r_fill_variates(C.byref(S), C.byref(V))
+        rc = L.ngo_r_sweep(C.byref(S), C.byref(T), _ptr(e), varE, C.byref(V))
+        assert rc == 0, rc
+        return {"u": u, "z": z, "chi2_b": c2, "dir_pi": dp}
 
 
 # --------------------------------------------------------------------------- multi-breed (Tuple) BayesPR

@@ -138,3 +138,43 @@ def test_region_builder_matches_reference_rules():
     assert O.regions_from_map(chr_id, 9999).tolist() == [0, 15]
     assert O.regions_from_map(chr_id, 99).tolist() == [0, 7, 12, 15]
     assert O.regions_from_map(chr_id, 3).tolist() == [0, 3, 6, 7, 10, 12, 15]      # ceil windows inside each chromosome
+
+
+def test_bayesr_oracle_matches_a_literal_numpy_restatement():
+    """functions.jl:238-289 line by line in numpy (fresh uniform per cumulative comparison, class 1 = zero variance)."""
+    rng = np.random.default_rng(11)
+    n, p = 120, 25
+    X = np.asfortranarray(rng.binomial(2, 0.3, size=(n, p)).astype(float)); X -= X.mean(0)
+    mpm = (X * X).sum(0)
+    vclass = np.array([0.0, 0.0001, 0.001, 0.01]); pi = np.array([0.7, 0.15, 0.1, 0.05])
+    R = O.BayesROracle(X, mpm, pi, vclass, v=0.8, est_pi=True)
+    e = rng.normal(size=n) * 2; e0 = e.copy(); varE = 1.7
+    log = R.sweep(e, varE, it=1, seed=5, chain=0)
+    beta = np.zeros(p); ee = e0.copy(); varc = 0.8 * vclass; logPi = np.log(pi)
+    nLoci = np.zeros(4, dtype=int); nnz = 0; sumS = 0.0
+    for j in range(p):
+        ee += X[:, j] * beta[j]
+        rhs = X[:, j] @ ee / varE
+        lhs = np.where(varc == 0, 0.0, mpm[j] / varE + 1.0 / np.where(varc == 0, 1.0, varc))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            logL = np.where(varc == 0, logPi, -0.5 * (np.log(varc * lhs) - rhs * rhs / lhs) + logPi)
+        cum = np.cumsum(np.exp(logL) / np.exp(logL).sum())
+        cls = next(v for v in range(4) if cum[v] >= log["u"][j, v])
+        nLoci[cls] += 1
+        if varc[cls] != 0:
+            nnz += 1
+            beta[j] = rhs / lhs[cls] + np.sqrt(1 / lhs[cls]) * log["z"][j]
+            ee -= X[:, j] * beta[j]
+            sumS += beta[j] ** 2 / vclass[cls]
+        else:
+            beta[j] = 0.0
+        assert R.delta[j] == cls + 1
+    assert np.allclose(beta, R.beta, rtol=1e-10, atol=1e-13) and np.allclose(ee, e, rtol=1e-10, atol=1e-11)
+    df, scale = O.marker_hyper(0.8)
+    assert np.isclose(R.varBeta[0], (scale * df + sumS) / log["chi2_b"][0], rtol=1e-12)
+    assert np.isclose(R.piHat.sum(), 1.0) and np.allclose(R.logPi, np.log(R.piHat)) and np.array_equal(R.piHat, log["dir_pi"])
+    # replaying the log reproduces the sweep bit for bit
+    R2 = O.BayesROracle(X, mpm, pi, vclass, v=0.8, est_pi=True)
+    e2 = e0.copy()
+    R2.sweep(e2, varE, it=1, seed=999, chain=3, replay=log)
+    assert np.array_equal(R2.beta, R.beta) and np.array_equal(e2, e) and np.array_equal(R2.piHat, R.piHat)
