@@ -13,7 +13,7 @@ using NextGP, DelimitedFiles
 
 const libngp = get(ENV, "LIBNGP", joinpath(@__DIR__, "..", "nextgp.jl_b200", "libngp.so"))
 
-const NGP_BAYESPR, NGP_BAYESB, NGP_BAYESC = Cint(0), Cint(1), Cint(2)
+const NGP_BAYESPR, NGP_BAYESB, NGP_BAYESC, NGP_BAYESR = Cint(0), Cint(1), Cint(2), Cint(3)
 const NGP_GENO_F64, NGP_STORE_I8 = Cint(1), Cint(0)
 const NGP_MAX_SETS = 8
 
@@ -22,6 +22,18 @@ struct NgpPrior            # mirrors struct ngp_prior
     df::Cdouble; scale::Cdouble; var_init::Cdouble; pi_in::Cdouble
     n_regions::Int64
     region_off::Ptr{Int64}; lhs0::Ptr{Cdouble}; rhs0::Ptr{Cdouble}
+    n_class::Cint; pad::Cint                         # BayesR only (mme.jl:374-383)
+    v_class::Ptr{Cdouble}; pi_class::Ptr{Cdouble}
+end
+
+struct NgpJointPrior       # mirrors struct ngp_joint_prior: (:M1,:M2) => BayesPR(r, V), mme.jl:448-489
+    k::Cint
+    set_id::NTuple{NGP_MAX_SETS,Cint}
+    pad::Cint
+    df::Cdouble
+    scale::Ptr{Cdouble}; var_init::Ptr{Cdouble}
+    n_regions::Int64
+    region_off::Ptr{Int64}
 end
 
 mutable struct NgpState    # mirrors struct ngp_state
@@ -60,6 +72,7 @@ function method_id(name::String)
     name == "BayesPR" && return NGP_BAYESPR
     name == "BayesB" && return NGP_BAYESB
     name == "BayesC" && return NGP_BAYESC
+    name == "BayesR" && return NGP_BAYESR
     error("$name is not on the B200 hot path (stays in Julia)")
 end
 
@@ -67,10 +80,14 @@ end
 function set_prior!(h, set::Integer, Mset, v0::Float64)
     offs = Int64[first(r) - 1 for r in Mset.regionArray]; push!(offs, last(Mset.regionArray[end]))
     isPR = Mset.method == "BayesPR"
-    pi_in = isPR ? 0.0 : Mset.piHat[2]
-    GC.@preserve offs begin
+    isR = Mset.method == "BayesR"
+    pi_in = (isPR || isR) ? 0.0 : Mset.piHat[2]
+    vclass = isR ? Vector{Float64}(Mset.vClass) : Float64[]
+    piclass = isR ? Vector{Float64}(Mset.piHat) : Float64[]
+    GC.@preserve offs vclass piclass begin
         pr = NgpPrior(method_id(Mset.method), isPR ? 0 : Cint(Mset.estPi), Mset.df, Mset.scale, v0, pi_in,
-                      isPR ? length(offs) - 1 : 0, isPR ? pointer(offs) : C_NULL, pointer(Mset.lhs), pointer(Mset.rhs))
+                      isPR ? length(offs) - 1 : 0, isPR ? pointer(offs) : C_NULL, pointer(Mset.lhs), pointer(Mset.rhs),
+                      Cint(length(vclass)), Cint(0), isR ? pointer(vclass) : C_NULL, isR ? pointer(piclass) : C_NULL)
         check(h, ccall((:ngp_set_prior, libngp), Cint, (Ptr{Cvoid}, Cint, Ref{NgpPrior}), h, set, pr))
     end
 end
@@ -85,6 +102,37 @@ function b200_funct(h, set::Integer)
                        (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Int64}, Ptr{Cdouble}, Ptr{Cdouble}),
                        h, set, ycorr, varE, b, d, vb, piHat))
         haskey(M[mSet], :logPi) && (M[mSet].logPi .= log.(M[mSet].piHat))
+        nothing
+    end
+end
+
+"""Tuple of correlated marker sets (multi-breed): sets 0..k-1 of the handle are the members, in the order of the tuple key.
+`Mt` is M[(:M1,:M2,...)] of getMME! (mme.jl:448-489), `V0` the k x k prior covariance (priorVCV[pSet].v)."""
+function set_joint_prior!(h, Mt, V0::Matrix{Float64})
+    k = size(V0, 1)
+    offs = Int64[first(r) - 1 for r in Mt.regionArray]; push!(offs, last(Mt.regionArray[end]))
+    sc = Matrix{Float64}(permutedims(Mt.scale)); v0 = Matrix{Float64}(permutedims(V0))       # row-major for the C side
+    GC.@preserve offs sc v0 begin
+        pr = NgpJointPrior(Cint(k), ntuple(i -> Cint(i <= k ? i - 1 : 0), NGP_MAX_SETS), Cint(0), Mt.df, pointer(sc), pointer(v0),
+                           length(offs) - 1, pointer(offs))
+        check(h, ccall((:ngp_set_joint_prior, libngp), Cint, (Ptr{Cvoid}, Ref{NgpJointPrior}), h, pr))
+    end
+end
+
+"""Sweep-level drop-in for sampleBayesPR!(mSet::Tuple, ...) (functions.jl:140-154): same 7 arguments."""
+function b200_joint_funct(h)
+    return function (mSet, M, beta, delta, ycorr, varE, varBeta)
+        pos = M[mSet].pos
+        k = length(pos); p = length(beta[pos[1]])
+        B = Matrix{Float64}(undef, p, k)                       # column b = breed b  ==  k x p row-major on the C side
+        for (b, ps) in enumerate(pos); B[:, b] .= vec(beta[ps]); end
+        R = length(varBeta[mSet])
+        VB = Array{Float64}(undef, k, k, R)
+        for r in 1:R; VB[:, :, r] .= permutedims(varBeta[mSet][r]); end
+        check(h, ccall((:ngp_joint_sweep, libngp), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}),
+                       h, ycorr, varE, B, VB))
+        for (b, ps) in enumerate(pos); beta[ps] .= reshape(B[:, b], size(beta[ps])); end
+        for r in 1:R; varBeta[mSet][r] = permutedims(VB[:, :, r]); end
         nothing
     end
 end
