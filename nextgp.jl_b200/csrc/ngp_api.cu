@@ -397,6 +397,9 @@ int ngp_configure(ngp_handle* h, int key, int64_t value)
         if (value < 0 || value > kLimbVers || value == 1) return fail(h, NGP_EINVAL, "ngp_configure: residual versions must be 0 (auto) or in [2,%d]", kLimbVers);
         h->cfg_versions = (int)value; return NGP_OK;
     case NGP_CFG_DEBUG:
+        // only the decoupling experiments that keep every ring protocol alive are accepted (2: prep warps skip the accumulator poll,
+        // 4: the chain warp skips corrections + scalar updates); the others stall the pipeline they were written for
+        if (value != 0 && value != 2 && value != 4 && value != 6) return fail(h, NGP_EINVAL, "ngp_configure: debug must be 0, 2, 4 or 6");
         h->cfg_debug = (int)value; return NGP_OK;
     case NGP_CFG_REFETCH:
         if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: the tile-ring mode must be set before the first upload");
