@@ -756,6 +756,41 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 #pragma unroll
                             for (int k = 0; k < SB; ++k) nn[k] = 0;
                             int pos = (dbg & 4) ? SM : 0;                       // markers [0, pos) of the step are committed
+                            if (method == 0 && pos < SM) {
+                                // BayesPR: every effect is redrawn, so there is nothing to speculate on and the positions of the changes are
+                                // known: the dependent chain per marker is  beta_new = rr*C + QSZ -> dbeta -> shuffle -> rr of the later markers;
+                                // the Gram values of marker m against the later ones do not depend on dbeta and are fetched ahead of it.
+                                double mydb[NS];
+#pragma unroll
+                                for (int i = 0; i < NS; ++i) {
+#pragma unroll 4
+                                    for (int f = 0; f < 32; ++f) {
+                                        const int m = 32 * i + f;
+                                        const int ka = m / B, qa = m % B;
+                                        const double bn = fma(rr[i], cC[i], cQ[i]);
+                                        const double dbl = bn - bold[i];
+                                        const double dbf = __shfl_sync(0xffffffffu, dbl, f);
+                                        const double csf = __shfl_sync(0xffffffffu, cs[i], f);
+                                        if (lane == f) { bnew[i] = bn; inc[i] = true; mydb[i] = dbl; }
+#pragma unroll
+                                        for (int i2 = i; i2 < NS; ++i2)
+                                            if (32 * i2 + lane > m) {
+                                                const double gc = (double)gram[i2][(kb[i2] - ka) * B * B + qa * B + qb[i2]] - csf * cs[i2] * inv_n;
+                                                rr[i2] = fma(-gc, dbf, rr[i2]);
+                                            }
+                                    }
+                                }
+                                // every marker of the step is a list entry, in marker order: each lane writes its own
+#pragma unroll
+                                for (int i = 0; i < NS; ++i) {
+                                    NzList& ml = cnz[(g0 + (unsigned)kb[i]) & (kNzRing - 1)];
+                                    ml.idx[qb[i]] = qb[i]; ml.db[qb[i]] = mydb[i]; ml.aux[qb[i]] = cs[i];
+                                }
+#pragma unroll
+                                for (int k = 0; k < SB; ++k) nn[k] = B;
+                                if constexpr (PROF) pf[7] += SM;
+                                pos = SM;
+                            }
                             while (pos < SM) {
                                 if constexpr (PROF) pf[7]++;
                                 double bnv[NS];

@@ -398,3 +398,59 @@ def test_large_shape_properties(gpu):
         g.close()
     assert rel(sts[0]["sets"][0]["beta"], sts[1]["sets"][0]["beta"]) < 1e-8
     assert np.array_equal(sts[0]["sets"][0]["delta"], sts[1]["sets"][0]["delta"])
+
+
+# ----------------------------------------------------------------------------- edge cases the reference's arithmetic defines
+@pytest.mark.parametrize("method,kw", [(2, dict(v=0.05, pi=0.3, est_pi=True)), (1, dict(v=0.05, pi=0.3)), (0, dict(v=0.02))])
+def test_monomorphic_columns_follow_the_reference_arithmetic(gpu, method, kw):
+    """A column without variation centres to zero: mpm = 0, so BayesB/C get log(0) and 0/0 in the inclusion probability (NaN ->
+    `rand() < NaN` is false -> never included, functions.jl:169-174, 209-216) and BayesPR draws from the prior (lhs = 1/varBeta)."""
+    prob = make_problem(300, 70, 13)
+    codes = prob["codes"].copy()
+    codes[:, 5] = 2; codes[:, 40] = 0; codes[:, 69] = 1
+    prob = dict(prob, codes=np.asfortranarray(codes))
+    with np.errstate(all="ignore"):
+        ch, S = oracle_chain(prob, method, **kw)
+        g = gpu_sampler(prob, method, **kw)
+        g.set_rng(21, 0)
+        for _ in range(5):
+            ch.iteration(seed=21, chain=0)
+    g.run(5)
+    st = g.state()
+    assert np.array_equal(st["sets"][0]["delta"], S.delta)
+    assert rel(st["sets"][0]["beta"], S.beta) < 1e-8 and rel(st["e"], ch.e) < 1e-8
+    if method:
+        assert not st["sets"][0]["delta"][[5, 40, 69]].any() and not st["sets"][0]["beta"][[5, 40, 69]].any()
+    g.close()
+
+
+@pytest.mark.parametrize("n,p", [(5, 3), (31, 1), (33, 65)])
+def test_tiny_shapes(gpu, n, p):
+    """Fewer rows than one MMA chunk, a single marker, one marker more than a padded block."""
+    prob = make_problem(n, p, 3 + n)
+    for method, kw in ((2, dict(v=0.05, pi=0.4, est_pi=True)), (0, dict(v=0.02))):
+        for kernel in ("blocked", "literal"):
+            _run_replay(prob, method, kw, kernel, iters=3)
+
+
+def test_call_order_and_argument_errors(gpu):
+    s = ngp.Sampler(0)
+    with pytest.raises(ngp.NgpError):
+        s.set_phenotype(np.zeros(10))                       # no marker set yet
+    prob = make_problem(100, 20, 1)
+    s.upload_genotypes(0, prob["codes"])
+    with pytest.raises(ngp.NgpError):
+        s.run(1)                                            # no prior / phenotype
+    with pytest.raises(ngp.NgpError):
+        s.set_phenotype(np.zeros(99))                       # wrong n
+    s.set_prior(0, 2, 4.0, 0.01, 0.02, pi_in=0.1)
+    s.set_phenotype(prob["y"]); s.set_residual_prior(4.0, 1.0)
+    with pytest.raises(ngp.NgpError):
+        s.run(0)                                            # n_iter must be positive
+    with pytest.raises(ngp.NgpError):
+        s.upload_genotypes(1, prob["codes"][:50])           # all sets of a handle share n
+    with pytest.raises(ngp.NgpError):
+        s.configure(L.CFG_DEBUG, 1)                         # only the terminating experiments are accepted
+    s.run(2)
+    assert s.state()["iter"] == 2
+    s.close()
