@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--model", default="")
     ap.add_argument("--max_ctas", type=int, default=0)
     ap.add_argument("--refetch", type=int, default=-1)
+    ap.add_argument("--min_rows", type=int, default=0)
     a = ap.parse_args()
     n, p, model = CONFIGS[a.config]
     model = a.model or model
@@ -33,7 +34,7 @@ def main():
         b, d, nt, dn, dbg, nv = (list(int(x) for x in combo.split(":")) + [0, 0])[:6]
         t0 = time.time()
         try:
-            s = ngp.Sampler(0, block=b, lookahead=d, tile_stages=nt, near=dn, max_ctas=a.max_ctas, refetch=a.refetch)
+            s = ngp.Sampler(0, block=b, lookahead=d, tile_stages=nt, near=dn, max_ctas=a.max_ctas, refetch=a.refetch, min_rows=a.min_rows)
             if nv:
                 s.configure(ngp._lib.CFG_VERSIONS, nv)
             if dbg:

@@ -75,3 +75,66 @@ def test_streams_of_different_chains_do_not_collide():
     a = [L.ngo_stream_uniform(5, 0, 1, 0, O.P_U, i) for i in range(256)]
     b = [L.ngo_stream_uniform(5, 1, 1, 0, O.P_U, i) for i in range(256)]
     assert len(set(a) & set(b)) == 0
+
+
+# ----------------------------------------------------------------------------- row-sharded single chain, host-side logic on gloo
+def _shard_worker(rank, world, port, q):
+    """What bench.py --sharded does around the device calls, with numpy standing in for the kernel: rows split on multiples of 4,
+    integer column sums all-reduced -> the mean / mpm of the WHOLE column on every rank, and per marker ONE all-reduced scalar
+    (the partial dot of the rank's rows); every rank then draws the identical effect and updates only its own rows of e."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from common import make_problem
+    n, p = 203, 30
+    prob = make_problem(n, p, 9)
+    per = -(-(-(-n // world)) // 4) * 4
+    a, b = min(n, rank * per), min(n, (rank + 1) * per)
+    g = prob["codes"][a:b].astype(np.int64)
+    sums = torch.from_numpy(np.stack([g.sum(0), (g * g).sum(0)]))
+    dist.all_reduce(sums)
+    cs, css = sums[0].numpy().astype(np.float64), sums[1].numpy().astype(np.float64)
+    mean, mpm = cs / n, (n * css - cs * cs) / n                   # colstats_kernel of csrc/ngp_api.cu with n_total
+    x = g - mean
+    e = (prob["y"] - prob["y"].mean())[a:b].copy()
+    rng = np.random.default_rng(5)                                # the same variates on every rank (same Philox counter on device)
+    beta = np.zeros(p); varE, vb = 1.3, 0.02
+    for j in range(p):
+        part = torch.tensor([x[:, j] @ e])
+        dist.all_reduce(part)                                     # the per-marker scalar reduction
+        rr = part.item() + mpm[j] * beta[j]
+        lhs = mpm[j] / varE + 1.0 / vb
+        bn = (rr / varE) / lhs + rng.standard_normal() / np.sqrt(lhs)
+        e -= x[:, j] * (bn - beta[j])
+        beta[j] = bn
+    parts = [None] * world
+    dist.all_gather_object(parts, (a, b, e))
+    if rank == 0:
+        q.put((mean, mpm, beta, parts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_chain_logic_over_two_ranks_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    mean, mpm, beta, parts = q.get(timeout=120)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    from common import make_problem
+    prob = make_problem(203, 30, 9)
+    X, mean_o, mpm_o = O.center_codes(prob["codes"])
+    assert np.allclose(mean, mean_o, rtol=1e-14) and np.allclose(mpm, mpm_o, rtol=1e-12)
+    assert parts[0][0] == 0 and parts[0][1] % 4 == 0 and parts[0][1] == parts[1][0] and parts[1][1] == 203      # slices tile the rows
+    # single-process restatement of the same sweep on all rows
+    e = prob["y"] - prob["y"].mean(); rng = np.random.default_rng(5); b1 = np.zeros(30)
+    for j in range(30):
+        rr = X[:, j] @ e + mpm_o[j] * b1[j]
+        lhs = mpm_o[j] / 1.3 + 1.0 / 0.02
+        bn = (rr / 1.3) / lhs + rng.standard_normal() / np.sqrt(lhs)
+        e -= X[:, j] * (bn - b1[j]); b1[j] = bn
+    assert np.allclose(beta, b1, rtol=1e-9) and np.allclose(np.concatenate([pt[2] for pt in parts]), e, rtol=1e-8, atol=1e-10)
