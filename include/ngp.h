@@ -135,6 +135,21 @@ typedef struct ngp_shard_info {
     uint64_t local_ptr;
 } ngp_shard_info;
 
+/* -------------------------------------------------------------------------
+ * One fixed-effect term besides the intercept: X[xSet] of getMME! (covariate,
+ * or the level columns of a factor).  Sampled after the intercept, in the order
+ * given, by sampleX! (functions.jl:39-54): a single column like the intercept,
+ * several columns with "Wang's trick" (sampleb!, functions.jl:22-36).
+ * ------------------------------------------------------------------------- */
+typedef struct ngp_fixed_set {
+    int32_t n_cols;              /* columns of X[xSet].data                                   */
+    int32_t pad_;
+    const double* data;          /* [n x n_cols] column-major                                  */
+    double lhs0, rhs0;           /* single-column sets: X[xSet].lhs / .rhs (else ignored)      */
+} ngp_fixed_set;
+#define NGP_MAX_FIXED_SETS 4
+#define NGP_MAX_FIXED_COLS 32
+
 /* Variate log of n_iter iterations for replay parity: the sampler
  * consumes these instead of its Philox stream.  Layout is row-major
  * [iteration][index].  Set s uses u[s], z[s], chi2_b[s], beta_pi[s].           */
@@ -232,6 +247,12 @@ int ngp_set_phenotype(ngp_handle* h, const double* y, int64_t n);            /* 
 int ngp_set_residual_prior(ngp_handle* h, double df_e, double scale_e);      /* E[:df], E[:scale]  */
 /* single-column fixed effect of ones (functions.jl:39-47); lhs0/rhs0 = X[xSet][:lhs/:rhs] */
 int ngp_set_intercept(ngp_handle* h, int enabled, double lhs0, double rhs0);
+/* fixed effects besides the intercept (at most NGP_MAX_FIXED_SETS sets, NGP_MAX_FIXED_COLS columns in all); call after the first
+ * upload; n_sets = 0 removes them.  Sampled inside ngp_run right after the intercept (samplers.jl:37-39).           */
+int ngp_set_fixed_effects(ngp_handle* h, int n_sets, const ngp_fixed_set* sets);
+int ngp_get_fixed_effects(ngp_handle* h, double* b);                          /* all columns, set after set */
+/* replay: one standard normal per column and iteration, z[n_iter][n_cols] (functions.jl:34,45); after ngp_set_replay */
+int ngp_set_fixed_replay(ngp_handle* h, int32_t n_iter, const double* z);
 int ngp_set_prior(ngp_handle* h, int set_id, const ngp_prior* prior);
 /* tuple of marker sets with jointly drawn effects (mme.jl:448-489); at most one tuple per handle, and every
  * uploaded set of the handle must be a member                                                            */

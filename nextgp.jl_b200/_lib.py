@@ -43,6 +43,10 @@ class JointPrior(C.Structure):
                 ("scale", C.c_void_p), ("var_init", C.c_void_p), ("n_regions", C.c_int64), ("region_off", C.c_void_p)]
 
 
+class FixedSet(C.Structure):
+    _fields_ = [("n_cols", C.c_int32), ("pad_", C.c_int32), ("data", C.c_void_p), ("lhs0", C.c_double), ("rhs0", C.c_double)]
+
+
 class ShardInfo(C.Structure):
     _fields_ = [("ipc", C.c_ubyte * 64), ("n_local", C.c_int64), ("worker_ctas", C.c_int32), ("device", C.c_int32),
                 ("pid", C.c_int64), ("local_ptr", C.c_uint64)]
@@ -118,6 +122,9 @@ _SIGS = {
     "ngp_set_phenotype": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "ngp_set_residual_prior": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "ngp_set_intercept": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
+    "ngp_set_fixed_effects": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(FixedSet)]),
+    "ngp_get_fixed_effects": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ngp_set_fixed_replay": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "ngp_set_prior": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Prior)]),
     "ngp_set_joint_prior": (C.c_int, [C.c_void_p, C.POINTER(JointPrior)]),
     "ngp_set_joint_replay": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

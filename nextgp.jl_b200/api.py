@@ -387,6 +387,32 @@ class Sampler:
     def set_intercept(self, enabled: bool = True, lhs0: float = 0.0, rhs0: float = 0.0) -> None:
         self._ck(self._lib.ngp_set_intercept(self._h, int(enabled), lhs0, rhs0))
 
+    def set_fixed_effects(self, sets: list) -> None:
+        """Fixed-effect terms besides the intercept, sampled after it in this order (functions.jl:22-54).
+        sets: arrays (n,) / (n, c), or (array, lhs0, rhs0) for a single column with prior information."""
+        arr = (L.FixedSet * max(len(sets), 1))()
+        keep = []
+        self.fixed_cols = 0
+        for i, s in enumerate(sets):
+            data, l0, r0 = (s if isinstance(s, tuple) else (s, 0.0, 0.0))
+            data = np.asfortranarray(data, dtype=np.float64)
+            if data.ndim == 1:
+                data = np.asfortranarray(data[:, None])
+            keep.append(data)
+            arr[i].n_cols, arr[i].data, arr[i].lhs0, arr[i].rhs0 = data.shape[1], _p(data), l0, r0
+            self.fixed_cols += data.shape[1]
+        self._ck(self._lib.ngp_set_fixed_effects(self._h, len(sets), arr))
+
+    def fixed_effects(self) -> np.ndarray:
+        b = np.empty(self.fixed_cols)
+        self._ck(self._lib.ngp_get_fixed_effects(self._h, _p(b)))
+        return b
+
+    def set_fixed_replay(self, logs: list[dict]) -> None:
+        """logs: the oracle's per-iteration logs; their "z_fx" entries (one array per fixed set) are concatenated per iteration."""
+        z = np.ascontiguousarray(np.stack([np.concatenate([np.atleast_1d(v) for v in g["z_fx"]]) for g in logs]), dtype=np.float64)
+        self._ck(self._lib.ngp_set_fixed_replay(self._h, len(logs), _p(z)))
+
     def set_prior(self, set_id: int, method: int, df: float, scale: float, var_init: float, pi_in: float = 0.0,
                   est_pi: bool = False, region_off: np.ndarray | None = None, lhs0: np.ndarray | None = None,
                   rhs0: np.ndarray | None = None, v_class: np.ndarray | None = None, pi_class: np.ndarray | None = None) -> None:
@@ -659,7 +685,7 @@ class MarkerTerm:
 
 
 def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict, summaryStat: dict | None, outPut: str | None,
-           intercept: bool = True):
+           intercept: bool = True, fixed: list | None = None):
     """mme.getMME! for intercept + marker sets: derives df/scale/regions (mme.jl:87-94, 324-373, 492-520), uploads
     everything through the C ABI and writes the header rows of the output files (mme.jl:543-595)."""
     summaryStat = summaryStat or {}
@@ -720,11 +746,15 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
         nvar = sampler.sets[sid]["nvar"]
         info.append({"name": term.name, "method": name, "p": p, "nvar": nvar, "df": df, "scale": scale,
                      "n_pi": len(pr.class_) if name == "BayesR" else 2})
+    fixed = fixed or []                                                          # [(name, data (n,c), level names)]
+    if fixed:
+        sampler.set_fixed_effects([d for _, d, _ in fixed])                      # X[xSet] besides the intercept (functions.jl:22-54)
     sampler.set_phenotype(Y)
     sampler.set_residual_prior(df_e, scale_e)
     sampler.set_intercept(intercept)
+    fx_names = [lv for _, _, lvs in fixed for lv in lvs]
     if outPut is not None:                                                       # header rows, mme.jl:543-595
-        outMCMC(outPut, "b", [["(Intercept)"]] if intercept else [[]])
+        outMCMC(outPut, "b", [(["(Intercept)"] if intercept else []) + fx_names])
         for term, inf in zip(M, info):
             levels = term.levels or [f"M{i}" for i in range(1, inf["p"] + 1)]
             outMCMC(outPut, f"beta{term.name}", [levels])
@@ -734,7 +764,7 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
         for term, inf in zip(M, info):
             outMCMC(outPut, f"var{term.name}", [[f"reg_{r}" for r in range(1, inf["nvar"] + 1)]])
         outMCMC(outPut, "varE", [["e"]])
-    return {"df_e": df_e, "scale_e": scale_e, "sets": info}
+    return {"df_e": df_e, "scale_e": scale_e, "sets": info, "n_fixed": len(fx_names)}
 
 
 def _getMME_tuple(sampler, Y, M, priorVCV, tuples, outPut, intercept, df_e, scale_e):
@@ -795,7 +825,9 @@ def runSampler(sampler: Sampler, M: list[MarkerTerm], info: dict, chainLength: i
         done = it
         st = sampler.state(want_e=False)
         if outPut is not None:
-            outMCMC(outPut, "b", [[st["mu"]]] if intercept else [[]])
+            bfx = list(sampler.fixed_effects()) if info.get("n_fixed") else []
+            st["b_fixed"] = np.array(bfx)
+            outMCMC(outPut, "b", [([st["mu"]] if intercept else []) + bfx])
             outMCMC(outPut, "varE", st["varE"])
             for sid, (term, inf) in enumerate(zip(M, info["sets"])):
                 outMCMC(outPut, f"beta{term.name}", st["sets"][sid]["beta"])
@@ -831,6 +863,7 @@ def runLMEM(formula: str, userData, nChain: int, nBurn: int, nThin: int, outFold
     terms = [t.strip() for t in re.split(r"\+(?![^(]*\))", rhs)]
     intercept = False
     M: list[MarkerTerm] = []
+    fixed: list = []
     for t in terms:
         if t == "1":
             intercept = True
@@ -838,6 +871,16 @@ def runLMEM(formula: str, userData, nChain: int, nBurn: int, nThin: int, outFold
             intercept = False
         else:
             m = _SNP_RE.fullmatch(t)
+            if not m and re.fullmatch(r"[A-Za-z_]\w*", t) and t in userData:
+                # a covariate (numeric column) or a factor (anything else: one column per level, first level dropped like
+                # StatsModels' DummyCoding); sampled on device right after the intercept (functions.jl:39-54)
+                col = np.asarray(userData[t])
+                if np.issubdtype(col.dtype, np.number):
+                    fixed.append((t, col.astype(np.float64)[:, None], [t]))
+                else:
+                    lv = sorted(set(col.tolist()))
+                    fixed.append((t, np.column_stack([(col == v).astype(np.float64) for v in lv[1:]]), [f"{t}: {v}" for v in lv[1:]]))
+                continue
             if not m:
                 raise NotImplementedError(f"term '{t}' is outside the B200 hot path (stays in Julia)")
             name, path, mp = m.group(1), m.group(2).strip("\"'"), (m.group(3) or "").strip("\"'")
@@ -857,6 +900,6 @@ def runLMEM(formula: str, userData, nChain: int, nBurn: int, nThin: int, outFold
     folderHandler(outFolder)
     sampler = sampler or Sampler(device)
     sampler.set_rng(seed, chain_id)
-    info = getMME(sampler, Y, M, VCV, summaryStat, outFolder, intercept=intercept)
+    info = getMME(sampler, Y, M, VCV, summaryStat, outFolder, intercept=intercept, fixed=fixed)
     runSampler(sampler, M, info, nChain, nBurn, nThin, outFolder, intercept=intercept)
     return sampler

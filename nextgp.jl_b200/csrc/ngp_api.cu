@@ -241,6 +241,10 @@ struct ngp_handle {
     int replay = 0, replay_iters = 0;
     int64_t replay_base = 0;
     double *rp_chi2_e = nullptr, *rp_z_mu = nullptr;
+    // fixed effects besides the intercept
+    FxDev fx{};
+    double *fx_data = nullptr, *fx_xpx = nullptr, *fx_colsum = nullptr, *fx_b = nullptr, *fx_rp_z = nullptr;
+    int fx_replay_iters = 0;
     // row-sharded chain
     int shard_rank = 0, shard_world = 1;
     bool shard_attached = false;
@@ -366,6 +370,7 @@ int ngp_destroy(ngp_handle* h)
     for (int r = 0; r < h->shard_world; ++r) if (h->peer_ipc[r] && h->peer[r]) cudaIpcCloseMemHandle(h->peer[r]);
     cudaFree(h->e); cudaFree(h->sc); cudaFree(h->sync); cudaFree(h->sets_dev);
     cudaFree(h->rp_chi2_e); cudaFree(h->rp_z_mu);
+    cudaFree(h->fx_data); cudaFree(h->fx_xpx); cudaFree(h->fx_colsum); cudaFree(h->fx_b); cudaFree(h->fx_rp_z);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -471,7 +476,7 @@ static int choose_geometry(ngp_handle* h, int64_t n)
                 for (int NR = kRecStages; NR >= 2; NR >>= 1) {
                     const int NV = h->cfg_versions ? h->cfg_versions : std::max(4, std::min(kLimbVers, D / 2 + 3));
                     SmemLayout L = smem_layout((int)R, B, NT, DN, NR, NV);
-                    if ((size_t)L.total + 1024 <= cap) {
+                    if ((size_t)L.total + 2048 <= cap) {
                         h->n = n; h->Tw = Tw; h->R = (int)R; h->B = B; h->D = D; h->DN = DN; h->NT = NT; h->NR = NR; h->NV = NV; h->L = L;
                         h->refetch = refetch;
                         return true;
@@ -708,6 +713,7 @@ int ngp_set_phenotype(ngp_handle* h, const double* y, int64_t n)
     CU(cpy(h, h->e, y, sizeof(double) * n, cudaMemcpyHostToDevice));     // ycorr = deepcopy(Y), mme.jl:57
     Scalars z{};
     CU(cpy(h, h->sc, &z, sizeof z, cudaMemcpyHostToDevice));
+    if (h->fx_b) CU(zero(h, h->fx_b, 0, sizeof(double) * kMaxFxCols));       // b = zeros, like every effect getMME! allocates
     h->have_y = true;
     return NGP_OK;
 }
@@ -724,6 +730,77 @@ int ngp_set_intercept(ngp_handle* h, int enabled, double lhs0, double rhs0)
 {
     if (!h) return NGP_EINVAL;
     h->has_mu = enabled ? 1 : 0; h->mu_lhs0 = lhs0; h->mu_rhs0 = rhs0;
+    return NGP_OK;
+}
+
+int ngp_set_fixed_effects(ngp_handle* h, int n_sets, const ngp_fixed_set* sets)
+{
+    if (!h) return NGP_EINVAL;
+    if (h->Tw == 0) return fail(h, NGP_EINVAL, "ngp_set_fixed_effects: upload a marker set first (it fixes n and the row panels)");
+    if (h->joint.active) return fail(h, NGP_EUNSUPPORTED, "ngp_set_fixed_effects: not available together with a tuple of marker sets");
+    if (n_sets < 0 || n_sets > kMaxFxSets || (n_sets > 0 && !sets)) return fail(h, NGP_EINVAL, "ngp_set_fixed_effects: 0..%d sets", kMaxFxSets);
+    CU(cudaSetDevice(h->device));
+    cudaFree(h->fx_data); cudaFree(h->fx_xpx); cudaFree(h->fx_colsum); cudaFree(h->fx_b); cudaFree(h->fx_rp_z);
+    h->fx_data = h->fx_xpx = h->fx_colsum = h->fx_b = h->fx_rp_z = nullptr;
+    h->fx = FxDev{};
+    h->fx_replay_iters = 0;
+    if (n_sets == 0) return NGP_OK;
+    FxDev F{};
+    int cols = 0, xsz = 0;
+    for (int s = 0; s < n_sets; ++s) {
+        if (sets[s].n_cols < 1 || !sets[s].data) return fail(h, NGP_EINVAL, "ngp_set_fixed_effects: set %d has no columns", s);
+        F.first[s] = cols; F.xoff[s] = xsz; F.lhs0[s] = sets[s].n_cols == 1 ? sets[s].lhs0 : 0.0; F.rhs0[s] = sets[s].n_cols == 1 ? sets[s].rhs0 : 0.0;
+        cols += sets[s].n_cols; xsz += sets[s].n_cols * sets[s].n_cols;
+    }
+    if (cols > kMaxFxCols) return fail(h, NGP_EUNSUPPORTED, "ngp_set_fixed_effects: %d columns exceed %d", cols, kMaxFxCols);
+    for (int s = n_sets; s <= kMaxFxSets; ++s) F.first[s] = cols;
+    F.n_sets = n_sets; F.n_cols = cols;
+    const int64_t n = h->n, ldx = (int64_t)h->Tw * h->R;
+    std::vector<double> data((size_t)cols * ldx, 0.0), xpx((size_t)xsz, 0.0), cs((size_t)cols, 0.0);
+    for (int s = 0; s < n_sets; ++s) {
+        const int nc = sets[s].n_cols;
+        for (int c = 0; c < nc; ++c) {
+            const double* src = sets[s].data + (int64_t)c * n;
+            double* dst = data.data() + (size_t)(F.first[s] + c) * ldx;
+            double sum = 0.0;
+            for (int64_t i = 0; i < n; ++i) { dst[i] = src[i]; sum += src[i]; }
+            cs[(size_t)(F.first[s] + c)] = sum;
+        }
+        for (int a = 0; a < nc; ++a)                                                  // X[xSet].xpx = X'X
+            for (int b = a; b < nc; ++b) {
+                const double *xa = sets[s].data + (int64_t)a * n, *xb = sets[s].data + (int64_t)b * n;
+                double d = 0.0;
+                for (int64_t i = 0; i < n; ++i) d += xa[i] * xb[i];
+                xpx[(size_t)F.xoff[s] + a * nc + b] = d; xpx[(size_t)F.xoff[s] + b * nc + a] = d;
+            }
+    }
+    CU(dalloc(&h->fx_data, data.size())); CU(cpy(h, h->fx_data, data.data(), sizeof(double) * data.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&h->fx_xpx, xpx.size())); CU(cpy(h, h->fx_xpx, xpx.data(), sizeof(double) * xpx.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&h->fx_colsum, cs.size())); CU(cpy(h, h->fx_colsum, cs.data(), sizeof(double) * cs.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&h->fx_b, (size_t)kMaxFxCols)); CU(zero(h, h->fx_b, 0, sizeof(double) * kMaxFxCols));
+    CU(cudaStreamSynchronize(h->stream));
+    F.data = h->fx_data; F.xpx = h->fx_xpx; F.colsum = h->fx_colsum; F.b = h->fx_b;
+    h->fx = F;
+    return NGP_OK;
+}
+
+int ngp_get_fixed_effects(ngp_handle* h, double* b)
+{
+    if (!h || !b) return fail(h, NGP_EINVAL, "ngp_get_fixed_effects: NULL argument");
+    if (!h->fx.n_cols) return fail(h, NGP_EINVAL, "ngp_get_fixed_effects: the handle has no fixed effects besides the intercept");
+    CU(cudaSetDevice(h->device));
+    CU(cpy(h, b, h->fx_b, sizeof(double) * h->fx.n_cols, cudaMemcpyDeviceToHost));
+    return NGP_OK;
+}
+
+int ngp_set_fixed_replay(ngp_handle* h, int32_t n_iter, const double* z)
+{
+    if (!h) return NGP_EINVAL;
+    if (!h->fx.n_cols || n_iter <= 0 || !z) return fail(h, NGP_EINVAL, "ngp_set_fixed_replay: no fixed effects, or empty log");
+    CU(cudaSetDevice(h->device));
+    CU(dalloc(&h->fx_rp_z, (size_t)n_iter * h->fx.n_cols));
+    CU(cpy(h, h->fx_rp_z, z, sizeof(double) * (size_t)n_iter * h->fx.n_cols, cudaMemcpyHostToDevice));
+    h->fx_replay_iters = n_iter;
     return NGP_OK;
 }
 
@@ -879,6 +956,7 @@ static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int 
     P.replay_base = h->replay_base; P.rp_chi2_e = h->rp_chi2_e; P.rp_z_mu = h->rp_z_mu;
     P.key0 = (uint32_t)(h->seed & 0xffffffffu); P.key1 = (uint32_t)(h->seed >> 32); P.chain = h->chain; P.accumulate = accumulate;
     P.debug = h->cfg_debug;
+    P.fx = h->fx; P.fx.rp_z = h->fx_rp_z;
     P.n_ranks = h->shard_world; P.rank = h->shard_rank; P.n_total = h->shard_world > 1 ? h->n_total : h->n;
     P.cta_off = 0; P.T_all = h->Tw + 1; P.Tw_all = h->Tw; P.bar_base = 0;
     P.peer[0] = h->sync;
@@ -959,6 +1037,9 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     if (h->joint.active) return fail(h, NGP_EINVAL, "this handle samples a tuple of marker sets: use ngp_run / ngp_joint_sweep");
     const bool sharded = h->shard_world > 1;
     if (sharded && !h->shard_attached) return fail(h, NGP_EINVAL, "row-sharded handle: call ngp_shard_attach before sampling");
+    if (sharded && h->fx.n_cols) return fail(h, NGP_EUNSUPPORTED, "fixed effects besides the intercept are not available on a row-sharded handle");
+    if (h->replay && h->fx.n_cols && do_mu && (!h->fx_rp_z || h->fx_replay_iters != h->replay_iters))
+        return fail(h, NGP_EINVAL, "replay log of the fixed effects missing (ngp_set_fixed_replay after ngp_set_replay)");
     if (sharded && h->cfg_kernel != NGP_KERNEL_LITERAL)
         return fail(h, NGP_EUNSUPPORTED, "the row-sharded chain runs the per-marker kernel (NGP_CFG_KERNEL = NGP_KERNEL_LITERAL)");
     if (!h->have_y) return fail(h, NGP_EINVAL, "no phenotype / residual on the device (ngp_set_phenotype or ngp_sweep)");

@@ -32,6 +32,8 @@ constexpr int kFirstPrepWarp = 2;
 constexpr int kLimbVers = 16;          // maximum number of versions of the fixed-point residual kept per worker CTA
 
 constexpr int kMaxClass = 8;           // BayesR variance classes
+constexpr int kMaxFxCols = 32;         // columns of all fixed-effect sets besides the intercept
+constexpr int kMaxFxSets = 4;
 constexpr int kMaxRanks = 8;           // row shards of one chain (GPUs of one NVSwitch box)
 constexpr int kProf = 32;              // cycle counters per CTA (ngp_get_profile)
 constexpr int kMaxB = 64;              // markers per block: 16, 32 or 64
@@ -84,6 +86,20 @@ struct SetDev {
     double* sum_delta;
 };
 
+// fixed effects with one or several columns (covariates, factor levels): X[xSet] of getMME!, sampled after the intercept
+// (samplers.jl:37-39, functions.jl:22-54)
+struct FxDev {
+    int32_t n_sets, n_cols;              // sets, columns of all sets
+    int32_t first[kMaxFxSets + 1];       // columns [first[s], first[s+1]) belong to set s
+    int32_t xoff[kMaxFxSets];            // offset of the set's c x c block in xpx
+    const double* data;                  // [n_cols][Tw*R] column-major, pad rows zero
+    const double* xpx;                   // X'X per set (X[xSet].xpx)
+    const double* colsum;                // [n_cols] 1'x_c: keeps 1'e current
+    double* b;                           // [n_cols] the effects
+    double lhs0[kMaxFxSets], rhs0[kMaxFxSets];   // single-column sets: X[xSet].lhs / .rhs
+    const double* rp_z;                  // replay [iter][n_cols]
+};
+
 struct SyncArea {
     // ---- head: zeroed before every launch
     unsigned long long counter;                 // grid-barrier arrivals, monotonic within a launch
@@ -97,6 +113,7 @@ struct SyncArea {
                                                 // every 8-byte word = {payload32, seq32}, seq = global block number + 1
     long long prof[kMaxCtas * kProf];           // per-CTA cycle counters of the last launch: see ngp_get_profile
     long long trace[2 * 2048];                  // instrumented kernel: (start clock, cycles waited for r_base) of the chain warp's first 2048 steps
+    double part_fx[kMaxCtas * kMaxFxCols];      // per-CTA partial dots x_c'e of the fixed-effect columns
 };
 constexpr size_t kSyncHeadBytes = 16 * 8 + kMaxCtas * 2 * 8 + 32 * 4;
 
@@ -139,6 +156,7 @@ struct Params {
     int64_t n_total;           // individuals over all ranks (n is the local row count)
     unsigned long long bar_base;   // barrier arrivals counted before this launch (sharded: the counter is never reset)
     SyncArea* peer[kMaxRanks];
+    FxDev fx;
 };
 
 // ----------------------------------------------------------------------------- tile layout

@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     }
     __syncthreads();
 
+    __shared__ double fx_s[2 * kMaxFxCols];          // fixed effects: [0..32) the effects, [32..64) Yi of the set being sampled
     __shared__ long long step_end_clk[64];
     __shared__ unsigned long long pub_ns[kNzRing];   // instrumented kernel: global time at which a list was published (worker CTA copy / chain CTA copy)        // instrumented kernel: clock at which the chain warp finished a step
     // cycle counters, see ngp_get_profile
@@ -366,11 +367,91 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         __syncthreads();
         const double varE = misc[32];
         const double dmu = misc[33];
-        const double Stot = misc[34];                 // 1'e after the intercept update; invariant under marker updates
+        double Stot = misc[34];                       // 1'e after the intercept update; invariant under marker updates
         const int sh = (int)misc[35];
         mu = misc[36];
         const double fx_scale = ldexp(1.0, sh), fx_inv = ldexp(1.0, -sh);
         if (dmu != 0.0) for (int r = tid; r < nrow; r += kThreads) e_s[r] += dmu;
+        // ------------------------------------------------------------------ fixed effects besides the intercept (functions.jl:22-54)
+        if (P.fx.n_cols > 0 && P.do_mu) {
+            const FxDev& X = P.fx;
+            const int64_t ldx = (int64_t)Tw * R;
+            const double iVarE = 1.0 / varE;
+            __syncthreads();
+            if (tid < X.n_cols) fx_s[tid] = __ldcg(&X.b[tid]);
+            __syncthreads();
+            for (int xs = 0; xs < X.n_sets; ++xs) {
+                const int c0 = X.first[xs], c1 = X.first[xs + 1];
+                // ycorr += X b (functions.jl:42, :49)
+                if (!is_chain)
+                    for (int r = tid; r < nrow; r += kThreads) {
+                        double a = 0.0;
+                        for (int c = c0; c < c1; ++c) a = fma(X.data[(int64_t)c * ldx + row0 + r], fx_s[c], a);
+                        e_s[r] += a;
+                    }
+                __syncthreads();
+                // Xp * ycorr: per-CTA partials, one grid barrier, summed in CTA order by everybody
+                for (int c = c0; c < c1; c += 2) {
+                    double a0 = 0.0, a1 = 0.0;
+                    if (!is_chain)
+                        for (int r = tid; r < nrow; r += kThreads) {
+                            const double ev = e_s[r];
+                            a0 = fma(X.data[(int64_t)c * ldx + row0 + r], ev, a0);
+                            if (c + 1 < c1) a1 = fma(X.data[(int64_t)(c + 1) * ldx + row0 + r], ev, a1);
+                        }
+                    block_sum2(a0, a1, misc);
+                    if (tid == 0) { sy->part_fx[t * kMaxFxCols + c] = a0; if (c + 1 < c1) sy->part_fx[t * kMaxFxCols + c + 1] = a1; }
+                }
+                __syncthreads();
+                gs.nbar++;
+                if (tid == 0) gs.arrive(P);
+                if (warp == 0) {
+                    gs.wait_warp();
+                    double yi = 0.0;
+                    if (c0 + lane < c1) { for (int cta = 0; cta < Tw; ++cta) yi += __ldcg(&sy->part_fx[cta * kMaxFxCols + c0 + lane]); }
+                    fx_s[kMaxFxCols + (lane & (kMaxFxCols - 1))] = yi * iVarE;                       // Yi (functions.jl:25)
+                    __syncwarp();
+                    if (lane == 0) {
+                        Stream st{P.key0, P.key1, P.chain, iter, 0u};
+                        const int nc = c1 - c0;
+                        const double* xpx = X.xpx + X.xoff[xs];
+                        double dS = 0.0;
+                        for (int i = 0; i < nc; ++i) {
+                            const double z = P.replay ? X.rp_z[rp_row * X.n_cols + c0 + i] : stream_normal(st, P_Z_MU, (uint32_t)(1 + c0 + i));
+                            const double bold_i = fx_s[c0 + i];
+                            double bn;
+                            if (nc == 1) {                                                            // functions.jl:43-46
+                                const double rhs = fx_s[kMaxFxCols] + X.rhs0[xs];
+                                const double lhs = xpx[0] * iVarE + X.lhs0[xs];
+                                bn = rhs / lhs + sqrt(1.0 / lhs) * z;
+                            } else {                                                                  // Wang's trick, functions.jl:27-34
+                                fx_s[c0 + i] = 0.0;
+                                double dt = 0.0;
+                                for (int kk = 0; kk < nc; ++kk) dt += xpx[i * nc + kk] * fx_s[c0 + kk];
+                                const double rhsb = fx_s[kMaxFxCols + i] - dt * iVarE;
+                                const double invLhsb = 1.0 / (xpx[i * nc + i] * iVarE);
+                                bn = invLhsb * rhsb + sqrt(invLhsb) * z;
+                            }
+                            fx_s[c0 + i] = bn;
+                            dS = fma(X.colsum[c0 + i], bn - bold_i, dS);
+                            if (is_chain) X.b[c0 + i] = bn;
+                        }
+                        // e was restored to e + X b_old before the dots: 1'e of the final e = 1'e_before - sum_c colsum_c (b_new - b_old)
+                        misc[34] -= dS;
+                    }
+                }
+                __syncthreads();
+                // ycorr -= X b (functions.jl:47, :51)
+                if (!is_chain)
+                    for (int r = tid; r < nrow; r += kThreads) {
+                        double a = 0.0;
+                        for (int c = c0; c < c1; ++c) a = fma(X.data[(int64_t)c * ldx + row0 + r], fx_s[c], a);
+                        e_s[r] -= a;
+                    }
+                __syncthreads();
+            }
+            Stot = misc[34];
+        }
         if (tid == 0) NGP_TICK(8);
 
         // ------------------------------------------------------------------ phase 1

@@ -673,6 +673,49 @@ int ngo_mb_sweep(const ngo_mb_set* S, double* beta /* k x p */, double* varBeta 
 }
 
 /* ------------------------------------------------------------------------- */
+/* fixed effects with one or several columns: functions.jl:22-36 (sampleb!,    */
+/* "Wang's trick") and :39-54 (sampleX!); X[xSet].xpx = X'X, Xp = X' (mme.jl).  */
+/* z: one standard normal per column (stream purpose Z_MU, index col0 + c).    */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    int64_t n;
+    int32_t n_cols, col0;     /* col0: index of the set's first column among all fixed columns (0 is the intercept) */
+    const double* data;       /* n x n_cols column-major                          */
+    const double* xpx;        /* n_cols x n_cols                                  */
+    double lhs0, rhs0;        /* single-column sets only (X[xSet].lhs / .rhs)     */
+} ngo_fx_set;
+
+void ngo_sample_fixed(const ngo_fx_set* F, double* b, double* e, double varE,
+                      int replay, uint64_t seed, uint32_t chain, uint32_t iter, double* z)
+{
+    const int64_t n = F->n;
+    const int c = F->n_cols;
+    const double iVarE = 1.0 / varE;
+    ngo_stream s = {seed, chain, iter, 0};
+    if (!replay) for (int k = 0; k < c; ++k) z[k] = stream_normal(&s, NGO_P_Z_MU, (uint32_t)(F->col0 + k), 0, 0);
+    for (int k = 0; k < c; ++k) daxpy(n, b[k], F->data + (int64_t)k * n, e);                       /* :42 / :49 */
+    if (c == 1) {
+        const double rhs = ddot(n, F->data, e) * iVarE + F->rhs0;                                 /* :43 */
+        const double lhs = F->xpx[0] * iVarE + F->lhs0;                                           /* :44 */
+        b[0] = rhs / lhs + sqrt(1.0 / lhs) * z[0];                                               /* :45-46 */
+    } else {
+        double Yi[64], bVec[64];
+        for (int k = 0; k < c; ++k) { Yi[k] = ddot(n, F->data + (int64_t)k * n, e) * iVarE; bVec[k] = b[k]; }   /* :25 */
+        for (int i = 0; i < c; ++i) {                                                            /* :27-34 */
+            bVec[i] = 0.0;
+            double dt = 0.0;
+            for (int k = 0; k < c; ++k) dt += F->xpx[i * c + k] * bVec[k];
+            const double rhsb = Yi[i] - dt * iVarE;
+            const double lhsb = F->xpx[i * c + i] * iVarE;
+            const double invLhsb = 1.0 / lhsb;
+            bVec[i] = invLhsb * rhsb + sqrt(invLhsb) * z[i];
+        }
+        for (int k = 0; k < c; ++k) b[k] = bVec[k];
+    }
+    for (int k = 0; k < c; ++k) daxpy(n, -b[k], F->data + (int64_t)k * n, e);                      /* :47 / :51 */
+}
+
+/* ------------------------------------------------------------------------- */
 /* BayesR: functions.jl:238-289 (sampleBayesR!), :518-520 (sampleVarBetaR),     */
 /* :536-538 (samplePi(::Vector) = Dirichlet(nLoci .+ 1)); wiring mme.jl:374-383 */
 /* nc variance classes with scales v_class (first is usually 0).  Quirk 11     */

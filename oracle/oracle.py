@@ -60,6 +60,11 @@ class _MbSet(C.Structure):
                 ("df", C.c_double), ("scale", C.c_void_p)]
 
 
+class _FxSet(C.Structure):
+    _fields_ = [("n", C.c_int64), ("n_cols", C.c_int32), ("col0", C.c_int32), ("data", C.c_void_p), ("xpx", C.c_void_p),
+                ("lhs0", C.c_double), ("rhs0", C.c_double)]
+
+
 class _RSet(C.Structure):
     _fields_ = [("n", C.c_int64), ("p", C.c_int64), ("X", C.c_void_p), ("mpm", C.c_void_p), ("lhs0", C.c_void_p),
                 ("rhs0", C.c_void_p), ("n_class", C.c_int32), ("est_pi", C.c_int32), ("v_class", C.c_void_p),
@@ -117,6 +122,8 @@ def lib():
         L.ngo_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ngo_set_threads.argtypes = [C.c_int]
         L.ngo_max_threads.restype = C.c_int
+        L.ngo_sample_fixed.restype = None
+        L.ngo_sample_fixed.argtypes = [C.POINTER(_FxSet), C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
         L.ngo_r_sweep.restype = C.c_int
         L.ngo_r_sweep.argtypes = [C.POINTER(_RSet), C.POINTER(_RState), C.c_void_p, C.c_double, C.POINTER(_RVariates)]
         L.ngo_r_fill_variates.restype = None
@@ -280,7 +287,8 @@ class OracleChain:
     """One chain: intercept (optional) + marker sets, iteration order of samplers.jl:32-53."""
 
     def __init__(self, y: np.ndarray, sets: list[MarkerSet], v_e: float, intercept: bool = True,
-                 mu_lhs0: float = 0.0, mu_rhs0: float = 0.0):
+                 mu_lhs0: float = 0.0, mu_rhs0: float = 0.0, fixed: list | None = None):
+        self.fixed = fixed or []          # FixedSet objects, sampled after the intercept in this order (samplers.jl:37-39)
         self.y = np.asarray(y, dtype=np.float64)
         self.n = len(self.y)
         self.sets = sets
@@ -307,6 +315,9 @@ class OracleChain:
             self.mu = L.ngo_sample_intercept(self.n, _ptr(self.e), self.mu, self.varE, self.mu_lhs0, self.mu_rhs0,
                                              int(rep), seed, chain, it, C.byref(z_mu))
             log["z_mu"] = z_mu.value
+        log["z_fx"] = []
+        for fi, F in enumerate(self.fixed):
+            log["z_fx"].append(F.sample(self.e, self.varE, it, seed=seed, chain=chain, replay_z=(replay["z_fx"][fi] if rep else None)))
         log["sets"] = []
         for si, S in enumerate(self.sets):
             p = S.X.shape[1]
@@ -337,6 +348,28 @@ class OracleChain:
         return {"varE": self.varE, "mu": self.mu, "e": self.e.copy(),
                 "sets": [{"beta": S.beta.copy(), "delta": S.delta.copy(), "varBeta": S.varBeta.copy(),
                           "piHat": S.piHat.copy()} for S in self.sets]}
+
+
+# --------------------------------------------------------------------------- fixed effects with several columns
+class FixedSet:
+    """One X[xSet] of getMME! (covariates / factor levels): functions.jl:22-54.  col0 = index of its first column among all fixed
+    columns of the model (0 is the intercept), which addresses the variate stream."""
+
+    def __init__(self, data: np.ndarray, col0: int, lhs0: float = 0.0, rhs0: float = 0.0):
+        self.data = np.asfortranarray(data, dtype=np.float64)
+        if self.data.ndim == 1:
+            self.data = np.asfortranarray(self.data[:, None])
+        self.n, self.c = self.data.shape
+        self.xpx = np.ascontiguousarray(self.data.T @ self.data)
+        self.col0, self.lhs0, self.rhs0 = col0, lhs0, rhs0
+        self.b = np.zeros(self.c)
+
+    def sample(self, e: np.ndarray, varE: float, it: int, seed: int = 0, chain: int = 0, replay_z=None) -> np.ndarray:
+        F = _FxSet()
+        F.n, F.n_cols, F.col0, F.data, F.xpx, F.lhs0, F.rhs0 = self.n, self.c, self.col0, _ptr(self.data), _ptr(self.xpx), self.lhs0, self.rhs0
+        z = np.zeros(self.c) if replay_z is None else np.ascontiguousarray(replay_z, dtype=np.float64).copy()
+        lib().ngo_sample_fixed(C.byref(F), _ptr(self.b), _ptr(e), varE, int(replay_z is not None), seed, chain, it, _ptr(z))
+        return z
 
 
 # --------------------------------------------------------------------------- BayesR

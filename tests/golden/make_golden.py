@@ -21,7 +21,58 @@ CASES = {
 }
 
 
+EXTRA = {
+    "bayesr": dict(n=280, p=120, seed=105, v=0.5, est_pi=True, iters=20, v_class=[0.0, 0.0001, 0.001, 0.01], pi=[0.8, 0.1, 0.07, 0.03]),
+    "tuple2": dict(n=260, p=90, seed=106, iters=15, V=[[0.02, 0.005], [0.005, 0.03]], region_off=[0, 30, 90]),
+}
+
+
+def breeds(n, p, k, seed):
+    probs = [make_problem(n, p, seed + 17 * b) for b in range(k)]
+    y = probs[0]["y"].copy()
+    for b in range(1, k):
+        y += probs[b]["y"] - probs[b]["y"].mean()
+    return probs, y
+
+
+def main_extra():
+    from oracle import oracle as O
+    c = EXTRA["bayesr"]
+    prob = make_problem(c["n"], c["p"], c["seed"])
+    X, mean, mpm = O.center_codes(prob["codes"])
+    R = O.BayesROracle(X, mpm, np.array(c["pi"]), np.array(c["v_class"]), v=c["v"], est_pi=c["est_pi"])
+    ch = O.OracleChain(prob["y"], [], v_e=prob["var_y"] / 2)
+    out = {k: [] for k in ("chi2_e", "z_mu", "u", "z", "chi2_b", "dir_pi", "beta", "delta", "varBeta", "varE", "mu", "pi")}
+    for _ in range(c["iters"]):
+        log = ch.iteration(seed=c["seed"], chain=3)
+        s = R.sweep(ch.e, ch.varE, it=ch.iter, seed=c["seed"], chain=3)
+        out["chi2_e"].append(log["chi2_e"]); out["z_mu"].append(log["z_mu"])
+        for k in ("u", "z", "chi2_b", "dir_pi"):
+            out[k].append(np.array(s[k]))
+        out["beta"].append(R.beta.copy()); out["delta"].append(R.delta.copy()); out["varBeta"].append(R.varBeta.copy())
+        out["varE"].append(ch.varE); out["mu"].append(ch.mu); out["pi"].append(R.piHat.copy())
+    np.savez_compressed(os.path.join(HERE, "bayesr.npz"), e_final=ch.e, **{k: np.array(v) for k, v in out.items()})
+    print("bayesr varE", ch.varE, "classes", np.bincount(R.delta, minlength=5)[1:])
+    c = EXTRA["tuple2"]
+    probs, y = breeds(c["n"], c["p"], 2, c["seed"])
+    Xk = [O.center_codes(pr["codes"])[0] for pr in probs]
+    mb = O.MultiBreedOracle(Xk, np.array(c["V"]), region_off=np.array(c["region_off"], dtype=np.int64))
+    ch = O.OracleChain(y, [], v_e=float(np.var(y)) / 2)
+    out = {k: [] for k in ("chi2_e", "z_mu", "z", "iw_chi2", "iw_z", "beta", "varBeta", "varE", "mu")}
+    for _ in range(c["iters"]):
+        log = ch.iteration(seed=c["seed"], chain=3)
+        s = mb.sweep(ch.e, ch.varE, it=ch.iter, seed=c["seed"], chain=3)
+        out["chi2_e"].append(log["chi2_e"]); out["z_mu"].append(log["z_mu"])
+        for k in ("z", "iw_chi2", "iw_z"):
+            out[k].append(np.array(s[k]))
+        out["beta"].append(mb.beta.copy()); out["varBeta"].append(mb.varBeta.copy()); out["varE"].append(ch.varE); out["mu"].append(ch.mu)
+    np.savez_compressed(os.path.join(HERE, "tuple2.npz"), e_final=ch.e, **{k: np.array(v) for k, v in out.items()})
+    print("tuple2 varE", ch.varE)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        return main_extra()
     for name, c in CASES.items():
         prob = make_problem(c["n"], c["p"], c["seed"])
         ro = np.array(c["region_off"], dtype=np.int64) if "region_off" in c else None

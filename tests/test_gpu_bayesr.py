@@ -99,3 +99,43 @@ def test_runLMEM_bayesr_writes_class_proportions(gpu, tmp_path):
     dl = np.loadtxt(os.path.join(out, "deltaMOut"), delimiter="\t", skiprows=1)
     assert pis.shape == (2, 4) and np.allclose(pis.sum(1), 1.0) and set(np.unique(dl)) <= {1, 2, 3, 4}
     s.close()
+
+
+def test_bayesr_and_tuple_replay_against_committed_golden(gpu):
+    """The device consumes the committed variate logs (tests/golden/bayesr.npz, tuple2.npz) and must land on the committed states —
+    no oracle code runs in this test."""
+    import importlib.util
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(gold, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    c = mg.EXTRA["bayesr"]; g = np.load(os.path.join(gold, "bayesr.npz"))
+    prob = make_problem(c["n"], c["p"], c["seed"])
+    s = ngp.Sampler(0)
+    s.upload_genotypes(0, prob["codes"])
+    v = c["v"]
+    s.set_prior(0, L.BAYESR, 4.0, v * 0.5, v, est_pi=True, v_class=np.array(c["v_class"]), pi_class=np.array(c["pi"]))
+    s.set_phenotype(prob["y"]); s.set_residual_prior(4.0, prob["var_y"] / 2 * 0.5); s.set_intercept(True)
+    ni = c["iters"]
+    s.set_replay([{"chi2_e": g["chi2_e"][i], "z_mu": g["z_mu"][i],
+                   "sets": [{"u": g["u"][i], "z": g["z"][i], "chi2_b": g["chi2_b"][i], "dir_pi": g["dir_pi"][i]}]} for i in range(ni)])
+    s.run(ni)
+    st = s.state()
+    assert np.array_equal(st["sets"][0]["delta"], g["delta"][-1]) and rel(st["sets"][0]["beta"], g["beta"][-1]) < 1e-8
+    assert rel(st["sets"][0]["piHat"], g["pi"][-1]) < 1e-12 and rel(st["e"], g["e_final"]) < 1e-8
+    s.close()
+    c = mg.EXTRA["tuple2"]; g = np.load(os.path.join(gold, "tuple2.npz"))
+    probs, y = mg.breeds(c["n"], c["p"], 2, c["seed"])
+    V = np.array(c["V"])
+    s = ngp.Sampler(0)
+    for b, pr in enumerate(probs):
+        s.upload_genotypes(b, pr["codes"])
+    s.set_joint_prior([0, 1], 5.0, V * 2.0, V, region_off=np.array(c["region_off"], dtype=np.int64))
+    s.set_phenotype(y); s.set_residual_prior(4.0, float(np.var(y)) / 2 * 0.5); s.set_intercept(True)
+    ni = c["iters"]
+    s.set_replay([{"chi2_e": g["chi2_e"][i], "z_mu": g["z_mu"][i], "sets": []} for i in range(ni)])
+    s.set_joint_replay([{"z": g["z"][i], "iw_chi2": g["iw_chi2"][i], "iw_z": g["iw_z"][i]} for i in range(ni)])
+    s.run(ni)
+    js = s.joint_state()
+    assert rel(js["beta"], g["beta"][-1]) < 1e-8 and rel(js["varBeta"], g["varBeta"][-1]) < 1e-8 and rel(s.state()["e"], g["e_final"]) < 1e-8
+    s.close()

@@ -178,3 +178,60 @@ def test_bayesr_oracle_matches_a_literal_numpy_restatement():
     e2 = e0.copy()
     R2.sweep(e2, varE, it=1, seed=999, chain=3, replay=log)
     assert np.array_equal(R2.beta, R.beta) and np.array_equal(e2, e) and np.array_equal(R2.piHat, R.piHat)
+
+
+def _golden_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    return mg
+
+
+def test_bayesr_and_tuple_oracles_reproduce_their_committed_golden_chains():
+    mg = _golden_module()
+    c = mg.EXTRA["bayesr"]; g = np.load(os.path.join(GOLD, "bayesr.npz"))
+    prob = make_problem(c["n"], c["p"], c["seed"])
+    X, mean, mpm = O.center_codes(prob["codes"])
+    R = O.BayesROracle(X, mpm, np.array(c["pi"]), np.array(c["v_class"]), v=c["v"], est_pi=c["est_pi"])
+    ch = O.OracleChain(prob["y"], [], v_e=prob["var_y"] / 2)
+    for it in range(c["iters"]):
+        ch.iteration(seed=c["seed"], chain=3)
+        R.sweep(ch.e, ch.varE, it=ch.iter, seed=c["seed"], chain=3)
+        assert np.array_equal(R.delta, g["delta"][it]) and np.allclose(R.beta, g["beta"][it], rtol=1e-9, atol=1e-13)
+        assert np.allclose(R.piHat, g["pi"][it], rtol=1e-12)
+    assert np.allclose(ch.e, g["e_final"], rtol=1e-8, atol=1e-10)
+    c = mg.EXTRA["tuple2"]; g = np.load(os.path.join(GOLD, "tuple2.npz"))
+    probs, y = mg.breeds(c["n"], c["p"], 2, c["seed"])
+    mb = O.MultiBreedOracle([O.center_codes(pr["codes"])[0] for pr in probs], np.array(c["V"]), region_off=np.array(c["region_off"], dtype=np.int64))
+    ch = O.OracleChain(y, [], v_e=float(np.var(y)) / 2)
+    for it in range(c["iters"]):
+        ch.iteration(seed=c["seed"], chain=3)
+        mb.sweep(ch.e, ch.varE, it=ch.iter, seed=c["seed"], chain=3)
+        assert np.allclose(mb.beta, g["beta"][it], rtol=1e-9, atol=1e-13) and np.allclose(mb.varBeta, g["varBeta"][it], rtol=1e-9)
+    assert np.allclose(ch.e, g["e_final"], rtol=1e-8, atol=1e-10)
+
+
+def test_fixed_effect_oracle_matches_numpy_restatement_of_wangs_trick():
+    """functions.jl:22-54: add-back, Yi = X'e/varE once, then the columns one by one against xpx."""
+    rng = np.random.default_rng(2)
+    n, c = 150, 4
+    Xf = np.asfortranarray(np.column_stack([rng.normal(size=n), rng.integers(0, 2, n), rng.normal(size=n) * 3, rng.uniform(size=n)]))
+    F = O.FixedSet(Xf, col0=1)
+    F.b[:] = rng.normal(size=c)
+    e = rng.normal(size=n); e0 = e.copy(); b0 = F.b.copy(); varE = 0.9
+    z = F.sample(e, varE, it=3, seed=8, chain=1)
+    ee = e0 + Xf @ b0
+    Yi = Xf.T @ ee / varE
+    xpx = Xf.T @ Xf
+    bv = b0.copy()
+    for i in range(c):
+        bv[i] = 0.0
+        rhs = Yi[i] - xpx[i] @ bv / varE
+        lhs = xpx[i, i] / varE
+        bv[i] = rhs / lhs + np.sqrt(1 / lhs) * z[i]
+    ee -= Xf @ bv
+    assert np.allclose(F.b, bv, rtol=1e-10) and np.allclose(e, ee, rtol=1e-10, atol=1e-12)
+    F1 = O.FixedSet(Xf[:, 0], col0=5, lhs0=0.3, rhs0=-0.2)
+    e = e0.copy(); z1 = F1.sample(e, varE, it=1, seed=8, chain=0)
+    rhs = Xf[:, 0] @ e0 / varE - 0.2; lhs = Xf[:, 0] @ Xf[:, 0] / varE + 0.3
+    assert np.isclose(F1.b[0], rhs / lhs + np.sqrt(1 / lhs) * z1[0], rtol=1e-12)
