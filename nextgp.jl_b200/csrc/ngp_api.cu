@@ -253,6 +253,10 @@ struct ngp_handle {
     int shard_Tw[kMaxRanks] = {0};
     int64_t n_total = 0;
     uint64_t bar_count = 0;     // grid-barrier rounds so far (the sharded counter is monotonic across launches)
+    // pinned staging of the sweep-level call (delta as int32, pi, error flag): one stream synchronisation per ngp_sweep
+    unsigned char* stage = nullptr;
+    size_t stage_bytes = 0;
+    const void* ready_kfn = nullptr;     // sweep-kernel variant whose launch attributes are set
     // stats
     int64_t launches = 0;
     uint64_t gblk = 0;          // blocks swept so far by the blocked kernel (numbers the list words and accumulator slots)
@@ -370,6 +374,7 @@ int ngp_destroy(ngp_handle* h)
     for (int r = 0; r < h->shard_world; ++r) if (h->peer_ipc[r] && h->peer[r]) cudaIpcCloseMemHandle(h->peer[r]);
     cudaFree(h->e); cudaFree(h->sc); cudaFree(h->sync); cudaFree(h->sets_dev);
     cudaFree(h->rp_chi2_e); cudaFree(h->rp_z_mu);
+    if (h->stage) cudaFreeHost(h->stage);
     cudaFree(h->fx_data); cudaFree(h->fx_xpx); cudaFree(h->fx_colsum); cudaFree(h->fx_b); cudaFree(h->fx_rp_z);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1031,7 +1036,7 @@ static int launch_joint(ngp_handle* h, int n_iter, int do_varE, int do_mu, doubl
     return check_kernel_error(h);
 }
 
-static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_mu, double varE_in, int accumulate)
+static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_mu, double varE_in, int accumulate, bool defer_sync = false)
 {
     CU(cudaSetDevice(h->device));
     if (h->joint.active) return fail(h, NGP_EINVAL, "this handle samples a tuple of marker sets: use ngp_run / ngp_joint_sweep");
@@ -1064,11 +1069,18 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
 #define NGP_PICK(PROF, DBG) ((h->B == 64) ? (const void*)gibbs_kernel<64, PROF, DBG> : (h->B == 32) ? (const void*)gibbs_kernel<32, PROF, DBG> : (const void*)gibbs_kernel<16, PROF, DBG>)
     const void* kfn = h->cfg_debug ? NGP_PICK(false, true) : h->cfg_profile ? NGP_PICK(true, false) : NGP_PICK(false, false);
 #undef NGP_PICK
-    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->L.total));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, h->L.total));
-    if (per_sm * h->prop.multiProcessorCount < h->Tw + 1)
-        return fail(h, NGP_EUNSUPPORTED, "cooperative grid of %d CTAs does not fit (%d per SM x %d SMs)", h->Tw + 1, per_sm, h->prop.multiProcessorCount);
+    if (h->ready_kfn != kfn) {                      // once per kernel variant: attribute + co-residency check of the cooperative grid
+        // the attribute belongs to the function, not to the handle: always the device maximum, so that handles with different
+        // geometries never lower it under each other
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, kfn));
+        CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->prop.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, h->L.total));
+        if (per_sm * h->prop.multiProcessorCount < h->Tw + 1)
+            return fail(h, NGP_EUNSUPPORTED, "cooperative grid of %d CTAs does not fit (%d per SM x %d SMs)", h->Tw + 1, per_sm, h->prop.multiProcessorCount);
+        h->ready_kfn = kfn;
+    }
     uint64_t blocks = 0;
     for (int s = 0; s < h->n_sets; ++s) if ((set_mask >> s) & 1) blocks += (uint64_t)(h->sets[s].p_pad / h->B);
     blocks *= (uint64_t)n_iter;
@@ -1092,6 +1104,7 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     CU(cudaEventRecord(h->ev1, h->stream));
     h->launches += 1;
     h->timed = true;
+    if (defer_sync) return NGP_OK;                 // the caller queues its device-to-host copies first and synchronises once
     CU(cudaStreamSynchronize(h->stream));
     return check_kernel_error(h);
 }
@@ -1154,15 +1167,50 @@ int ngp_sweep(ngp_handle* h, int set_id, double* ycorr, double varE, double* bet
         return fail(h, NGP_EINVAL, "ngp_sweep: marker set %d is not ready", set_id);
     if (!ycorr || !(varE > 0.0)) return fail(h, NGP_EINVAL, "ngp_sweep: ycorr must be non-NULL and varE > 0");
     CU(cudaSetDevice(h->device));
+    SetHost& S = h->sets[set_id];
+    // Everything is queued on the handle's stream — host-to-device copies, the sweep, device-to-host copies — and the stream is
+    // synchronised ONCE.  delta (Int64 on the Julia side, int32 on device), pi and the error flag go through a pinned staging buffer.
+    const size_t npi = (S.method == NGP_BAYESR) ? 2 * (size_t)S.n_class : 4;
+    const size_t need = sizeof(int32_t) * (size_t)S.p_pad + sizeof(double) * 2 * kMaxClass * 2 + 64;
+    if (h->stage_bytes < need) {
+        if (h->stage) cudaFreeHost(h->stage);
+        h->stage = nullptr; h->stage_bytes = 0;
+        CU(cudaMallocHost((void**)&h->stage, need));
+        h->stage_bytes = need;
+    }
+    int32_t* st_delta = reinterpret_cast<int32_t*>(h->stage);
+    double* st_pi_in = reinterpret_cast<double*>(h->stage + sizeof(int32_t) * (size_t)S.p_pad);
+    double* st_pi_out = st_pi_in + 2 * kMaxClass;
+    int* st_err = reinterpret_cast<int*>(st_pi_out + 2 * kMaxClass);
+    double* dev_pi = (S.method == NGP_BAYESR) ? S.pi_class : S.pi;
     CU(cudaMemcpyAsync(h->e, ycorr, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    if (beta) CU(cudaMemcpyAsync(S.beta, beta, sizeof(double) * S.p, cudaMemcpyHostToDevice, h->stream));
+    if (delta) {
+        for (int64_t j = 0; j < S.p; ++j) st_delta[j] = (int32_t)delta[j];
+        CU(cudaMemcpyAsync(S.delta, st_delta, sizeof(int32_t) * S.p, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (varBeta && S.varBeta) CU(cudaMemcpyAsync(S.varBeta, varBeta, sizeof(double) * S.nvar, cudaMemcpyHostToDevice, h->stream));
+    if (piHat && S.method != NGP_BAYESPR && dev_pi) {
+        const size_t half = npi / 2;
+        for (size_t v = 0; v < half; ++v) { st_pi_in[v] = piHat[v]; st_pi_in[half + v] = log(piHat[v]); }
+        CU(cudaMemcpyAsync(dev_pi, st_pi_in, sizeof(double) * npi, cudaMemcpyHostToDevice, h->stream));
+    }
     h->have_y = true;
-    int rc = push_set_state(h, set_id, beta, delta, varBeta, piHat);
+    int rc = launch(h, 1, 1 << set_id, 0, 0, varE, 0, /*defer_sync=*/true);
     if (rc) return rc;
-    rc = launch(h, 1, 1 << set_id, 0, 0, varE, 0);
-    if (rc) return rc;
-    CU(cpy(h, ycorr, h->e, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
-    return pull_set_state(h, set_id, beta, delta, varBeta, piHat);
+    CU(cudaMemcpyAsync(ycorr, h->e, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+    if (beta) CU(cudaMemcpyAsync(beta, S.beta, sizeof(double) * S.p, cudaMemcpyDeviceToHost, h->stream));
+    if (delta) CU(cudaMemcpyAsync(st_delta, S.delta, sizeof(int32_t) * S.p, cudaMemcpyDeviceToHost, h->stream));
+    if (varBeta && S.varBeta) CU(cudaMemcpyAsync(varBeta, S.varBeta, sizeof(double) * S.nvar, cudaMemcpyDeviceToHost, h->stream));
+    if (piHat && dev_pi) CU(cudaMemcpyAsync(st_pi_out, dev_pi, sizeof(double) * npi, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(st_err, &h->sync->err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (*st_err & 2) return fail(h, NGP_ENUMERIC, "a covariance matrix of the tuple sampler is not positive definite");
+    if (*st_err & 4) return fail(h, NGP_ENUMERIC, "BayesR: no class reached its uniform (the reference's findfirst returns nothing here)");
+    if (*st_err) return fail(h, NGP_ERANGE, "fixed-point reduction range exceeded (residual grew by more than 2^4 within an iteration)");
+    if (delta) for (int64_t j = 0; j < S.p; ++j) delta[j] = st_delta[j];
+    if (piHat && dev_pi) { const size_t half = npi / 2; for (size_t v = 0; v < half; ++v) piHat[v] = st_pi_out[v]; }
+    return NGP_OK;
 }
 
 // ----------------------------------------------------------------------------- row-sharded chain
