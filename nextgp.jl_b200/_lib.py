@@ -9,7 +9,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-SO_PATH = os.path.join(_HERE, "libngp.so")
+SO_PATH = os.environ.get("LIBNGP") or os.path.join(_HERE, "libngp.so")      # LIBNGP: another build of the same ABI (A/B timing)
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(_ROOT, "include", "ngp.h")
 
@@ -159,6 +159,8 @@ def lib() -> C.CDLL:
                                "(nvcc, sm_100a).  nextgp.jl_b200 has no CPU fallback.")
         L = C.CDLL(SO_PATH)
         for name, (res, args) in _SIGS.items():
+            if os.environ.get("LIBNGP") and not hasattr(L, name):
+                continue                     # an older build of the ABI loaded for A/B timing: its missing entry points stay unbound
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

@@ -1066,8 +1066,9 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     fill_params(h, P, n_iter, set_mask, do_varE, do_mu, varE_in, accumulate);
     for (int s = 0; s < h->n_sets; ++s)
         if (((set_mask >> s) & 1) && h->sets[s].method == NGP_BAYESR) P.kernel = NGP_KERNEL_LITERAL;     // the class algebra lives in the per-marker sweep
-#define NGP_PICK(PROF, DBG) ((h->B == 64) ? (const void*)gibbs_kernel<64, PROF, DBG> : (h->B == 32) ? (const void*)gibbs_kernel<32, PROF, DBG> : (const void*)gibbs_kernel<16, PROF, DBG>)
-    const void* kfn = h->cfg_debug ? NGP_PICK(false, true) : h->cfg_profile ? NGP_PICK(true, false) : NGP_PICK(false, false);
+#define NGP_PICK(PROF, DBG, LIT) ((h->B == 64) ? (const void*)gibbs_kernel<64, PROF, DBG, LIT> : (h->B == 32) ? (const void*)gibbs_kernel<32, PROF, DBG, LIT> : (const void*)gibbs_kernel<16, PROF, DBG, LIT>)
+    const void* kfn = (P.kernel == NGP_KERNEL_LITERAL) ? NGP_PICK(false, false, true)
+                    : h->cfg_debug ? NGP_PICK(false, true, false) : h->cfg_profile ? NGP_PICK(true, false, false) : NGP_PICK(false, false, false);
 #undef NGP_PICK
     if (h->ready_kfn != kfn) {                      // once per kernel variant: attribute + co-residency check of the cooperative grid
         // the attribute belongs to the function, not to the handle: always the device maximum, so that handles with different

@@ -213,7 +213,8 @@ __device__ __forceinline__ void quantise4(const double (&e)[4], uint32_t* limb, 
 }
 
 // ----------------------------------------------------------------------------- the kernel
-template <int B, bool PROF, bool DBG>
+// LIT: the per-marker ("literal") sweep instead of the blocked one — a separate instantiation, so that neither variant carries the other's code
+template <int B, bool PROF, bool DBG, bool LIT>
 __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
             double acc_cls = 0.0;                      // BayesR: loci assigned to class `lane`
             if constexpr (PROF) tc = clock64();
 
-            if (P.kernel == 0) {
+            if constexpr (!LIT) {
                 // ======================================================================================================
                 //                                  blocked exact sweep, look-ahead D
                 // ======================================================================================================
@@ -1312,7 +1313,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 
             // ------------------------------------------------------------------ phase 3 (chain CTA)
             const bool regional = (S.method == 0 && S.n_regions > 1);
-            const int p3warp = (P.kernel == 0) ? kHelperWarp : 0;     // the warp that accumulated beta'beta and nLoci
+            const int p3warp = LIT ? 0 : kHelperWarp;     // the warp that accumulated beta'beta and nLoci
             if (is_chain && warp == p3warp && S.method == 3) {
                 const double sumS = warp_sum(acc_bb);
                 const double nnz = warp_sum(acc_n);
