@@ -43,7 +43,7 @@ def test_product_never_imports_oracle():
     pat_c = re.compile(r"#include[^\n]*oracle|ngo_[a-z0-9_]+\s*\(|libngp_oracle")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            src = open(os.path.join(dirpath, f), errors="ignore").read() if f.endswith((".py", ".cu", ".cuh", ".h")) else ""
+            src = open(os.path.join(dirpath, f), errors="ignore").read() if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) else ""
             pat = pat_py if f.endswith(".py") else pat_c
             assert not pat.search(src), f"{f} uses the oracle"
 
