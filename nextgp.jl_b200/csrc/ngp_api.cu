@@ -43,10 +43,10 @@ __device__ __forceinline__ int block_sum_int(int v, int* scratch)
 template <int FMT>
 __global__ void pack_kernel(const void* __restrict__ src, int64_t ld, int64_t n, int64_t j0, int R, int B, int64_t nblk,
                             uint8_t* __restrict__ geno, int32_t* __restrict__ colsum, int32_t* __restrict__ colsumsq,
-                            int* __restrict__ err)
+                            int* __restrict__ err, int64_t jmul = 1, int64_t jadd = 0)
 {
     __shared__ int scratch[32];
-    const int64_t jc = blockIdx.x, j = j0 + jc;
+    const int64_t jc = blockIdx.x, j = (j0 + jc) * jmul + jadd;      // destination column (jmul, jadd: interleaving of a tuple's sets)
     const int64_t k = j / B;
     const int q = (int)(j - k * B);
     const int64_t tile_bytes = (int64_t)B * R;
@@ -155,6 +155,18 @@ __global__ void region_of_kernel(const int64_t* region_off, int64_t n_regions, i
         for (int64_t j = region_off[r] + threadIdx.x; j < region_off[r + 1]; j += blockDim.x) region_of[j] = (int32_t)r;
 }
 
+// effects of a tuple: member arrays beta_b[j]  <->  interleaved copy beta[j*k + b]
+struct TupleBeta { double* member[8]; };
+__global__ void tuple_beta_kernel(TupleBeta M, double* inter, int k, int64_t p, int to_inter)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    for (int b = 0; b < k; ++b) {
+        if (to_inter) inter[j * k + b] = M.member[b][j];
+        else M.member[b][j] = inter[j * k + b];
+    }
+}
+
 __global__ void fill_kernel(double* x, int64_t n, double v)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -191,7 +203,9 @@ struct SetHost {
     uint8_t* geno = nullptr;
     double* consts = nullptr;
     int32_t *gx = nullptr, *colsum = nullptr, *colsumsq = nullptr, *delta = nullptr, *region_of = nullptr;
-    double *d = nullptr, *mean = nullptr, *beta = nullptr, *varBeta = nullptr, *pi = nullptr, *pi_class = nullptr;
+    double *d = nullptr, *mean = nullptr, *beta = nullptr, *varBeta = nullptr, *pi = nullptr, *pi_class = nullptr, *jinvB = nullptr;
+    int group_k = 0, stream_set = 0;
+    bool joint_copy = false;           // the interleaved copy of a tuple's member sets
     int n_class = 0;
     double v_class[kMaxClass] = {0.0};
     double *lhs0 = nullptr, *rhs0 = nullptr, *sum_beta = nullptr, *sum_beta2 = nullptr, *sum_delta = nullptr;
@@ -208,6 +222,8 @@ struct JointHost {      // tuple of marker sets with jointly drawn effects (mme.
     int64_t* region_off = nullptr;
     double *rp_z = nullptr, *rp_iw_chi2 = nullptr, *rp_iw_z = nullptr;
     int replay_iters = 0;
+    int blocked_set = -1;     // slot of the interleaved copy swept by the blocked kernel (k = 2, 4, 8), or -1
+    bool state_in_copy = false;   // the current effects live in the interleaved copy (else in the member sets)
 };
 
 struct ngp_handle {
@@ -308,7 +324,7 @@ static void free_joint(JointHost& j)
 static void free_set(SetHost& s)
 {
     cudaFree(s.geno); cudaFree(s.consts); cudaFree(s.gx); cudaFree(s.colsum); cudaFree(s.colsumsq); cudaFree(s.delta); cudaFree(s.region_of);
-    cudaFree(s.d); cudaFree(s.mean); cudaFree(s.beta); cudaFree(s.varBeta); cudaFree(s.pi); cudaFree(s.pi_class);
+    cudaFree(s.d); cudaFree(s.mean); cudaFree(s.beta); cudaFree(s.varBeta); cudaFree(s.pi); cudaFree(s.pi_class); cudaFree(s.jinvB);
     cudaFree(s.lhs0); cudaFree(s.rhs0); cudaFree(s.sum_beta); cudaFree(s.sum_beta2); cudaFree(s.sum_delta);
     cudaFree(s.region_off); cudaFree(s.rp_u); cudaFree(s.rp_z); cudaFree(s.rp_chi2b); cudaFree(s.rp_betapi);
     s = SetHost();
@@ -901,7 +917,7 @@ int ngp_set_replay(ngp_handle* h, const ngp_replay* log)
     else if (h->has_mu) return fail(h, NGP_EINVAL, "ngp_set_replay: z_mu is required when the intercept is enabled");
     for (int s = 0; s < h->n_sets; ++s) {
         SetHost& S = h->sets[s];
-        if (!S.have_geno || S.joint_member) continue;
+        if (!S.have_geno || S.joint_member || S.joint_copy) continue;
         if (!S.have_prior) return fail(h, NGP_EINVAL, "ngp_set_replay: set the prior of set %d first", s);
         if (s >= log->n_sets || !log->z[s] || !log->chi2_b[s]) return fail(h, NGP_EINVAL, "ngp_set_replay: z / chi2_b missing for set %d", s);
         CU(dalloc(&S.rp_z, (size_t)ni * S.p));
@@ -938,11 +954,13 @@ static int sync_sets(ngp_handle* h)
         if (!S.have_geno || !S.have_prior) continue;
         SetDev& D = sd[s];
         D.p = S.p; D.p_pad = S.p_pad; D.method = S.method; D.est_pi = S.est_pi; D.n_regions = S.n_regions; D.nvar = S.nvar;
-        D.df = S.df; D.scale = S.scale; D.n_class = S.n_class; D.pi_class = S.pi_class; memcpy(D.v_class, S.v_class, sizeof D.v_class);
+        D.df = S.df; D.scale = S.scale; D.group_k = S.group_k; D.stream_set = S.stream_set; D.jinvB = S.jinvB;
+        if (S.group_k) { D.jvar = h->joint.varBeta; for (int a = 0; a < S.group_k * S.group_k; ++a) D.jscale[a] = h->joint.scale[a]; D.rp_iw_chi2 = h->joint.rp_iw_chi2; D.rp_iw_z = h->joint.rp_iw_z; D.rp_z = h->joint.rp_z; }
+        D.n_class = S.n_class; D.pi_class = S.pi_class; memcpy(D.v_class, S.v_class, sizeof D.v_class);
         D.geno = S.geno; D.gx = S.gx; D.consts = S.consts; D.colsum = S.colsum; D.d = S.d; D.mean = S.mean;
         D.beta = S.beta; D.delta = S.delta; D.varBeta = S.varBeta; D.pi = S.pi; D.region_of = S.region_of; D.region_off = S.region_off;
         D.lhs0 = S.lhs0; D.rhs0 = S.rhs0;
-        D.rp_u = S.rp_u; D.rp_z = S.rp_z; D.rp_chi2b = S.rp_chi2b; D.rp_betapi = S.rp_betapi;
+        D.rp_u = S.rp_u; D.rp_z = S.group_k ? h->joint.rp_z : S.rp_z; D.rp_chi2b = S.rp_chi2b; D.rp_betapi = S.rp_betapi;
         D.sum_beta = S.sum_beta; D.sum_beta2 = S.sum_beta2; D.sum_delta = S.sum_delta;
     }
     CU(cudaMemcpyAsync(h->sets_dev, sd, sizeof sd, cudaMemcpyHostToDevice, h->stream));
@@ -1039,7 +1057,8 @@ static int launch_joint(ngp_handle* h, int n_iter, int do_varE, int do_mu, doubl
 static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_mu, double varE_in, int accumulate, bool defer_sync = false)
 {
     CU(cudaSetDevice(h->device));
-    if (h->joint.active) return fail(h, NGP_EINVAL, "this handle samples a tuple of marker sets: use ngp_run / ngp_joint_sweep");
+    if (h->joint.active && !(h->joint.blocked_set >= 0 && set_mask == (1 << h->joint.blocked_set)))
+        return fail(h, NGP_EINVAL, "this handle samples a tuple of marker sets: use ngp_run / ngp_joint_sweep");
     const bool sharded = h->shard_world > 1;
     if (sharded && !h->shard_attached) return fail(h, NGP_EINVAL, "row-sharded handle: call ngp_shard_attach before sampling");
     if (sharded && h->fx.n_cols) return fail(h, NGP_EUNSUPPORTED, "fixed effects besides the intercept are not available on a row-sharded handle");
@@ -1066,9 +1085,12 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     fill_params(h, P, n_iter, set_mask, do_varE, do_mu, varE_in, accumulate);
     for (int s = 0; s < h->n_sets; ++s)
         if (((set_mask >> s) & 1) && h->sets[s].method == NGP_BAYESR) P.kernel = NGP_KERNEL_LITERAL;     // the class algebra lives in the per-marker sweep
-#define NGP_PICK(PROF, DBG, LIT) ((h->B == 64) ? (const void*)gibbs_kernel<64, PROF, DBG, LIT> : (h->B == 32) ? (const void*)gibbs_kernel<32, PROF, DBG, LIT> : (const void*)gibbs_kernel<16, PROF, DBG, LIT>)
-    const void* kfn = (P.kernel == NGP_KERNEL_LITERAL) ? NGP_PICK(false, false, true)
-                    : h->cfg_debug ? NGP_PICK(false, true, false) : h->cfg_profile ? NGP_PICK(true, false, false) : NGP_PICK(false, false, false);
+#define NGP_PICK(PROF, DBG, LIT, TUP) ((h->B == 64) ? (const void*)gibbs_kernel<64, PROF, DBG, LIT, TUP> : (h->B == 32) ? (const void*)gibbs_kernel<32, PROF, DBG, LIT, TUP> : (const void*)gibbs_kernel<16, PROF, DBG, LIT, TUP>)
+    bool tuple_mask = false;
+    for (int s = 0; s < h->n_sets; ++s) if (((set_mask >> s) & 1) && h->sets[s].group_k) tuple_mask = true;
+    const void* kfn = tuple_mask ? NGP_PICK(false, false, false, true)
+                    : (P.kernel == NGP_KERNEL_LITERAL) ? NGP_PICK(false, false, true, false)
+                    : h->cfg_debug ? NGP_PICK(false, true, false, false) : h->cfg_profile ? NGP_PICK(true, false, false, false) : NGP_PICK(false, false, false, false);
 #undef NGP_PICK
     if (h->ready_kfn != kfn) {                      // once per kernel variant: attribute + co-residency check of the cooperative grid
         // the attribute belongs to the function, not to the handle: always the device maximum, so that handles with different
@@ -1110,11 +1132,42 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     return check_kernel_error(h);
 }
 
+// the tuple's effects live either in the member sets (per-locus kernel) or in the interleaved copy (blocked kernel)
+static int tuple_sync_state(ngp_handle* h, bool want_copy)
+{
+    JointHost& J = h->joint;
+    if (J.blocked_set < 0 || J.state_in_copy == want_copy) return NGP_OK;
+    TupleBeta M{};
+    for (int b = 0; b < J.k; ++b) M.member[b] = h->sets[J.set[b]].beta;
+    tuple_beta_kernel<<<(unsigned)((J.p + 255) / 256), 256, 0, h->stream>>>(M, h->sets[J.blocked_set].beta, J.k, J.p, want_copy ? 1 : 0);
+    CU(cudaGetLastError());
+    J.state_in_copy = want_copy;
+    return NGP_OK;
+}
+
+static bool tuple_use_blocked(const ngp_handle* h) { return h->joint.blocked_set >= 0 && h->cfg_kernel == NGP_KERNEL_BLOCKED; }
+
+static int tuple_launch(ngp_handle* h, int n_iter, int do_varE, int do_mu, double varE_in, int accumulate)
+{
+    JointHost& J = h->joint;
+    if (tuple_use_blocked(h)) {
+        if (h->replay && (!J.rp_z || J.replay_iters != h->replay_iters))
+            return fail(h, NGP_EINVAL, "replay log of the tuple missing (ngp_set_joint_replay after ngp_set_replay)");
+        int rc = tuple_sync_state(h, true);
+        if (rc) return rc;
+        h->sets_dirty = true;                       // replay / covariance pointers of the copy follow the tuple's
+        return launch(h, n_iter, 1 << J.blocked_set, do_varE, do_mu, varE_in, accumulate);
+    }
+    int rc = tuple_sync_state(h, false);
+    if (rc) return rc;
+    return launch_joint(h, n_iter, do_varE, do_mu, varE_in, accumulate);
+}
+
 int ngp_run(ngp_handle* h, int32_t n_iter)
 {
     if (!h) return NGP_EINVAL;
     if (n_iter <= 0) return fail(h, NGP_EINVAL, "ngp_run: n_iter must be positive");
-    if (h->joint.active) return launch_joint(h, n_iter, 1, 1, 0.0, 1);
+    if (h->joint.active) return tuple_launch(h, n_iter, 1, 1, 0.0, 1);
     int mask = 0;
     for (int s = 0; s < h->n_sets; ++s) if (h->sets[s].have_geno) mask |= 1 << s;
     return launch(h, n_iter, mask, 1, 1, 0.0, 1);
@@ -1325,7 +1378,7 @@ int ngp_set_joint_prior(ngp_handle* h, const ngp_joint_prior* pr)
         else if (h->sets[s].p != p) return fail(h, NGP_EINVAL, "ngp_set_joint_prior: member sets must have the same number of loci (mme.jl:453)");
     }
     for (int s = 0; s < h->n_sets; ++s)
-        if (h->sets[s].have_geno && !((member_mask >> s) & 1u))
+        if (h->sets[s].have_geno && !h->sets[s].joint_copy && !((member_mask >> s) & 1u))
             return fail(h, NGP_EUNSUPPORTED, "ngp_set_joint_prior: every marker set of the handle must be a member of the tuple (set %d is not)", s);
     int64_t R = 1;
     std::vector<int64_t> ro;
@@ -1338,6 +1391,7 @@ int ngp_set_joint_prior(ngp_handle* h, const ngp_joint_prior* pr)
     } else ro = {0, p};
     CU(cudaSetDevice(h->device));
     for (int b = 0; b < h->joint.k; ++b) h->sets[h->joint.set[b]].joint_member = false;
+    if (h->joint.blocked_set >= 0) free_set(h->sets[h->joint.blocked_set]);
     free_joint(h->joint);
     JointHost& J = h->joint;
     J.k = k; J.p = p; J.n_regions = R; J.df = pr->df;
@@ -1367,6 +1421,70 @@ int ngp_set_joint_prior(ngp_handle* h, const ngp_joint_prior* pr)
     CU(cudaStreamSynchronize(h->stream));
     J.active = true;
     h->sets_dirty = true;
+    // Blocked path (k = 2 or 4, dividing the block size, a free set slot, one GPU): an INTERLEAVED copy of the members' codes, column
+    // j*k + b = breed b of locus j, is swept by the look-ahead kernel with the joint k x k draw in the chain warp (ngp_sweep.cuh: joint_step).
+    int slot = -1;
+    for (int s = 0; s < NGP_MAX_SETS; ++s) if (!h->sets[s].have_geno) { slot = s; break; }
+    if (slot >= 0 && (k == 2 || k == 4) && h->shard_world == 1 && p * k <= 0x7fffffffLL) {
+        // Every effect of a tuple changes in every sweep, so the look-ahead buys nothing but cross-Gram corrections (B changed columns per
+        // block and distance): a short look-ahead served entirely from the block records is the fast geometry (C1 / C4 measurements).
+        // Tw, R and B — the tile layout of the sets already uploaded — stay as they are; only the kernel's rings are re-sized.
+        if (!h->cfg_lookahead && !h->cfg_near) {
+            const int sv_l = h->cfg_lookahead, sv_n = h->cfg_near, sv_r = h->cfg_refetch, sv_b = h->cfg_block;
+            h->cfg_lookahead = 3; h->cfg_near = 3; h->cfg_refetch = 0; h->cfg_block = h->B;
+            const int Tw0 = h->Tw, R0 = h->R;
+            int rcg = choose_geometry(h, h->n);
+            h->cfg_lookahead = sv_l; h->cfg_near = sv_n; h->cfg_refetch = sv_r; h->cfg_block = sv_b;
+            if (rcg) return rcg;
+            if (h->Tw != Tw0 || h->R != R0) return fail(h, NGP_EINVAL, "internal: the tile layout changed while re-sizing the rings");
+            h->ready_kfn = nullptr;
+        }
+        int rc = begin_upload(h, slot, h->n, p * k, NGP_STORE_I8);
+        if (rc) return rc;
+        SetHost& T = h->sets[slot];
+        int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(p, (int64_t)((256u << 20) / (size_t)h->n)));
+        chunk = std::min<int64_t>(chunk, 65535);
+        int8_t* stage = nullptr;
+        int* derr = nullptr;
+        CU(cudaMalloc((void**)&stage, (size_t)h->n * chunk));
+        CU(cudaMalloc((void**)&derr, sizeof(int)));
+        CU(cudaMemsetAsync(derr, 0, sizeof(int), h->stream));
+        for (int b = 0; b < k; ++b) {
+            const SetHost& Mb = h->sets[J.set[b]];
+            for (int64_t c0 = 0; c0 < p; c0 += chunk) {
+                const int64_t nc = std::min(chunk, p - c0);
+                dim3 grid((unsigned)((h->n + 255) / 256), (unsigned)nc);
+                unpack_kernel<<<grid, 256, 0, h->stream>>>(Mb.geno, h->n, h->R, h->B, Mb.p_pad / h->B, c0, nc, stage);
+                CU(cudaGetLastError());
+                pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, h->n, h->n, c0, h->R, h->B, T.p_pad / h->B, T.geno, T.colsum, T.colsumsq, derr, (int64_t)k, (int64_t)b);
+                CU(cudaGetLastError());
+            }
+        }
+        CU(cudaStreamSynchronize(h->stream));
+        cudaFree(stage); cudaFree(derr);
+        rc = finish_upload(h, T);
+        if (rc) return rc;
+        T.method = 4; T.est_pi = 0; T.nvar = 0; T.n_regions = R; T.df = pr->df; T.scale = 0.0; T.group_k = k; T.stream_set = J.set[0]; T.joint_copy = true;
+        std::vector<int64_t> rok(ro);
+        for (auto& v : rok) v *= k;                                   // locus offsets -> column offsets of the interleaved copy
+        CU(dalloc(&T.region_off, (size_t)R + 1));
+        CU(cpy(h, T.region_off, rok.data(), sizeof(int64_t) * (R + 1), cudaMemcpyHostToDevice));
+        if (R > 1) {
+            CU(dalloc(&T.region_of, T.p_pad));
+            CU(zero(h, T.region_of, 0, sizeof(int32_t) * T.p_pad));
+            region_of_kernel<<<(unsigned)std::min<int64_t>(R, 4096), 128, 0, h->stream>>>(T.region_off, R, T.region_of);
+            CU(cudaGetLastError());
+        }
+        CU(dalloc(&T.jinvB, (size_t)R * k * k));
+        CU(dalloc(&T.sum_beta, T.p_pad)); CU(dalloc(&T.sum_beta2, T.p_pad)); CU(dalloc(&T.sum_delta, T.p_pad));
+        CU(cudaMemsetAsync(T.sum_beta, 0, sizeof(double) * T.p_pad, h->stream));
+        CU(cudaMemsetAsync(T.sum_beta2, 0, sizeof(double) * T.p_pad, h->stream));
+        CU(cudaMemsetAsync(T.sum_delta, 0, sizeof(double) * T.p_pad, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        T.have_prior = true;
+        J.blocked_set = slot; J.state_in_copy = false;
+        h->sets_dirty = true;
+    }
     return NGP_OK;
 }
 
@@ -1382,6 +1500,7 @@ int ngp_set_joint_replay(ngp_handle* h, int32_t n_iter, const double* z, const d
     CU(dalloc(&J.rp_iw_chi2, nc)); CU(cpy(h, J.rp_iw_chi2, iw_chi2, sizeof(double) * nc, cudaMemcpyHostToDevice));
     CU(dalloc(&J.rp_iw_z, nl)); CU(cpy(h, J.rp_iw_z, iw_z, sizeof(double) * nl, cudaMemcpyHostToDevice));
     J.replay_iters = n_iter;
+    h->sets_dirty = true;
     return NGP_OK;
 }
 
@@ -1391,7 +1510,11 @@ int ngp_get_joint_state(ngp_handle* h, double* beta, double* varBeta)
     JointHost& J = h->joint;
     if (!J.active) return fail(h, NGP_EINVAL, "ngp_get_joint_state: no tuple of marker sets");
     CU(cudaSetDevice(h->device));
-    if (beta) for (int b = 0; b < J.k; ++b) CU(cpy(h, beta + (size_t)b * J.p, h->sets[J.set[b]].beta, sizeof(double) * J.p, cudaMemcpyDeviceToHost));
+    if (beta) {
+        int rc = tuple_sync_state(h, false);          // effects back into the member sets if the blocked kernel ran last
+        if (rc) return rc;
+        for (int b = 0; b < J.k; ++b) CU(cpy(h, beta + (size_t)b * J.p, h->sets[J.set[b]].beta, sizeof(double) * J.p, cudaMemcpyDeviceToHost));
+    }
     if (varBeta) CU(cpy(h, varBeta, J.varBeta, sizeof(double) * (size_t)J.n_regions * J.k * J.k, cudaMemcpyDeviceToHost));
     return NGP_OK;
 }
@@ -1408,7 +1531,8 @@ int ngp_joint_sweep(ngp_handle* h, double* ycorr, double varE, double* beta, dou
     if (varBeta) CU(cudaMemcpyAsync(J.varBeta, varBeta, sizeof(double) * (size_t)J.n_regions * J.k * J.k, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->have_y = true;
-    int rc = launch_joint(h, 1, 0, 0, varE, 0);
+    if (beta) J.state_in_copy = false;                 // the caller's effects are in the member sets now
+    int rc = tuple_launch(h, 1, 0, 0, varE, 0);
     if (rc) return rc;
     CU(cpy(h, ycorr, h->e, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
     return ngp_get_joint_state(h, beta, varBeta);
@@ -1483,6 +1607,22 @@ int ngp_get_posterior(ngp_handle* h, int set_id, int64_t* n_samples, double* sum
     Scalars sc;
     CU(cpy(h, &sc, h->sc, sizeof sc, cudaMemcpyDeviceToHost));
     if (n_samples) *n_samples = sc.n_post;
+    if (S.joint_member && h->joint.blocked_set >= 0 && h->cfg_kernel == NGP_KERNEL_BLOCKED) {
+        // the blocked tuple sweep accumulates in the interleaved copy: column j*k + b
+        const JointHost& J = h->joint;
+        const SetHost& T = h->sets[J.blocked_set];
+        int b = 0;
+        for (int x = 0; x < J.k; ++x) if (J.set[x] == set_id) b = x;
+        std::vector<double> tmp((size_t)T.p);
+        double* outs[3] = {sum_beta, sum_beta2, sum_delta};
+        const double* srcs[3] = {T.sum_beta, T.sum_beta2, T.sum_delta};
+        for (int q = 0; q < 3; ++q)
+            if (outs[q]) {
+                CU(cpy(h, tmp.data(), srcs[q], sizeof(double) * T.p, cudaMemcpyDeviceToHost));
+                for (int64_t j = 0; j < J.p; ++j) outs[q][j] = tmp[(size_t)(j * J.k + b)];
+            }
+        return NGP_OK;
+    }
     if (sum_beta) CU(cpy(h, sum_beta, S.sum_beta, sizeof(double) * S.p, cudaMemcpyDeviceToHost));
     if (sum_beta2) CU(cpy(h, sum_beta2, S.sum_beta2, sizeof(double) * S.p, cudaMemcpyDeviceToHost));
     if (sum_delta) CU(cpy(h, sum_delta, S.sum_delta, sizeof(double) * S.p, cudaMemcpyDeviceToHost));

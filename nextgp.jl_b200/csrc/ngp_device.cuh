@@ -81,6 +81,14 @@ struct SetDev {
     int32_t n_class, pad_cls;  // BayesR (method 3): variance classes (functions.jl:241)
     double v_class[kMaxClass]; //   M.vClass
     double* pi_class;          //   [2 * n_class] piHat, logPi (mme.jl:375,383)
+    // tuple of k marker sets swept by the blocked kernel (method 4): the breeds' columns are INTERLEAVED, column j*k + b = breed b
+    // of locus j, and the k effects of a locus are drawn jointly (functions.jl:140-154)
+    int32_t group_k, stream_set;   // k (2 or 4; 0 = ordinary set); set id that addresses the variate stream (first member)
+    double jscale[16];             // k x k prior scale (mme.jl:501)
+    double* jvar;                  // [n_regions][k][k] covariances (varBeta of the tuple)
+    double* jinvB;                 // [n_regions][k][k] their inverses, refreshed in phase 1
+    const double* rp_iw_chi2;      // replay of the inverse-Wishart draw: [iter][n_regions][k]
+    const double* rp_iw_z;         //                                     [iter][n_regions][k][k]
     double* sum_beta;          // posterior sums [p_pad]
     double* sum_beta2;
     double* sum_delta;

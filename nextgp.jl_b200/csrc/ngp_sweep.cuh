@@ -30,6 +30,7 @@
 // north-star baseline whose sync cost we report).
 #pragma once
 #include "ngp_device.cuh"
+#include "ngp_small_la.cuh"
 
 namespace ngp {
 
@@ -154,10 +155,13 @@ __device__ __forceinline__ void prep_marker(const Params& P, const SetDev& S, in
         const double iVarE = 1.0 / varE;
         const double l0 = S.lhs0 ? S.lhs0[j] : 0.0;
         const double r0 = S.rhs0 ? S.rhs0[j] : 0.0;
-        Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)sidx};
-        const double z = P.replay ? S.rp_z[rp_row * S.p + j] : stream_normal(st, P_Z, (uint32_t)j);
+        Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)(S.group_k ? S.stream_set : sidx)};
+        // tuple (method 4): column j = locus j / k, breed j % k; the oracle addresses its normal as (locus, component)
+        const double z = P.replay ? S.rp_z[rp_row * S.p + j]
+                                  : (S.group_k ? stream_normal(st, P_Z, (uint32_t)(j / S.group_k), 0, (uint32_t)(j % S.group_k)) : stream_normal(st, P_Z, (uint32_t)j));
         double vb;
-        if (S.method == 0) vb = __ldcg(&S.varBeta[S.region_of ? S.region_of[j] : 0]);
+        if (S.method == 4) vb = 1.0;
+        else if (S.method == 0) vb = __ldcg(&S.varBeta[S.region_of ? S.region_of[j] : 0]);
         else if (S.method == 1) vb = __ldcg(&S.varBeta[j]);
         else vb = __ldcg(&S.varBeta[0]);
         const double lhs = d * iVarE + l0 + 1.0 / vb;          // 1/0 -> Inf (BayesB quirk, functions.jl:186)
@@ -176,6 +180,8 @@ __device__ __forceinline__ void prep_marker(const Params& P, const SetDev& S, in
                 fCHI = P.replay ? S.rp_chi2b[rp_row * S.nvar + j] : stream_chisq(st, P_CHI2_B, (uint32_t)j, 0, S.df + 1.0);
         } else if (S.method == 0) {
             fT = INFINITY;   // BayesPR: always "included"
+        } else if (S.method == 4) {
+            fC = 0.0; fQSZ = z; fT = (double)(S.region_of ? S.region_of[j] : 0);     // the joint solve runs in the chain warp: variate + region index
         } else {
             fC = 0.0; fQSZ = z;   // BayesR (per-marker kernel only): F_QSZ carries the normal variate, the class algebra runs in the sweep
         }
@@ -212,9 +218,122 @@ __device__ __forceinline__ void quantise4(const double (&e)[4], uint32_t* limb, 
     }
 }
 
+// ----------------------------------------------------------------------------- tuple step of the chain warp
+// One step (SM = 32 NS columns) of a tuple of K interleaved marker sets: the K lanes gl .. gl+K-1 of a slot hold the K breeds of one
+// locus.  Per locus: complete the add-back with the cross terms  sum_{a != b} Gc[a][b] beta_old_a  (rr already holds x'e + d beta_old),
+// gather the K values, solve  C = (M'M/varE + invB_r)^-1,  beta = C rhs + chol(C) z  in every lane (uniform inputs, no divergence),
+// then restore the later columns of the step from the Gram rows of the K changed columns.  Every column becomes a list entry.
+template <int B, int NS, int K, class NzList>
+__device__ __forceinline__ void joint_step(double (&rr)[NS], const double (&bold)[NS], const double (&cs)[NS], const double (&cQ)[NS],
+                                           const double (&cT)[NS], double (&bnew)[NS], bool (&inc)[NS], const int32_t* (&gram)[NS],
+                                           const int (&kb)[NS], const int (&qb)[NS], NzList* cnz, unsigned g0, int lane, double inv_n,
+                                           double iVarE, const double* jinvB, SyncArea* sy)
+{
+    const unsigned FULL = 0xffffffffu;
+    double mydb[NS];
+    int cur_rg = -1;
+    double invB[K * K];
+#pragma unroll
+    for (int x = 0; x < K * K; ++x) invB[x] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        mydb[i] = 0.0;
+#pragma unroll 1
+        for (int gl = 0; gl < 32; gl += K) {
+            const int m0 = 32 * i + gl;                      // first column of the locus within the step
+            const int ka = m0 / B, qa0 = m0 % B;             // its block of the step and column inside the block (K divides B: no straddling)
+            // region of the locus -> inverse covariance (uniform across the warp)
+            const double rgd = __shfl_sync(FULL, cT[i], gl);
+            if (!(rgd >= 0.0)) continue;                     // padding columns past the last locus (F_T = -inf): nothing to draw
+            const int rg = (int)rgd;
+            if (rg != cur_rg) {
+#pragma unroll
+                for (int x = 0; x < K * K; ++x) invB[x] = __ldcg(&jinvB[(size_t)rg * K * K + x]);
+                cur_rg = rg;
+            }
+            double bo[K], csg[K], zg[K], rhs[K];
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+                bo[a] = __shfl_sync(FULL, bold[i], gl + a);
+                csg[a] = __shfl_sync(FULL, cs[i], gl + a);
+                zg[a] = __shfl_sync(FULL, cQ[i], gl + a);
+            }
+            // centred Gram of the locus' K columns, M_j'M_j: the distance-0 Gram of their block, read through the record pointer of the
+            // lane that owns the locus' first column (the records of a step's blocks are different stages of the ring)
+            const unsigned long long owner_ptr = __shfl_sync(FULL, (unsigned long long)(uintptr_t)gram[i], gl);
+            const int32_t* gk = reinterpret_cast<const int32_t*>((uintptr_t)owner_ptr);
+            double MtM[K * K];
+#pragma unroll
+            for (int a = 0; a < K; ++a)
+#pragma unroll
+                for (int b = 0; b < K; ++b)
+                    MtM[a * K + b] = (double)gk[(qa0 + a) * B + (qa0 + b)] - csg[a] * csg[b] * inv_n;
+            // x_b'(e + M beta_old) = rr_b (own add-back included) + sum_{a != b} MtM[a][b] beta_old_a
+#pragma unroll
+            for (int b = 0; b < K; ++b) {
+                double v = __shfl_sync(FULL, rr[i], gl + b);
+#pragma unroll
+                for (int a = 0; a < K; ++a) if (a != b) v = fma(MtM[a * K + b], bo[a], v);
+                rhs[b] = v * iVarE;                                                        // RHS (functions.jl:146)
+            }
+            double LHS[K * K], C[K * K], Lc[K * K], bn[K], db[K];
+#pragma unroll
+            for (int x = 0; x < K * K; ++x) LHS[x] = MtM[x] * iVarE + invB[x];
+            bool ok;
+            if constexpr (K == 2) {
+                // 2 x 2 in closed form (the generic route costs eight fp64 divisions / square roots on the dependent path)
+                const double det = fma(LHS[0], LHS[3], -(LHS[1] * LHS[2]));
+                const double idet = 1.0 / det;
+                C[0] = LHS[3] * idet; C[1] = -LHS[1] * idet; C[2] = C[1]; C[3] = LHS[0] * idet;      // functions.jl:147
+                Lc[0] = sqrt(C[0]); Lc[1] = 0.0; Lc[2] = C[2] / Lc[0];
+                const double s22 = fma(-Lc[2], Lc[2], C[3]);
+                Lc[3] = sqrt(s22);
+                ok = (LHS[0] > 0.0) && (det > 0.0) && (s22 > 0.0);
+            } else {
+                ok = jt_inv_spd<K>(LHS, C) && jt_chol<K>(C, Lc);                           // functions.jl:147
+            }
+            if (!ok && lane == 0) atomicOr(&sy->err, 2);
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+                double mval = 0.0;
+#pragma unroll
+                for (int b = 0; b < K; ++b) mval += C[a * K + b] * rhs[b];                    // functions.jl:148
+                double sdraw = mval;
+#pragma unroll
+                for (int b = 0; b <= a; ++b) sdraw += Lc[a * K + b] * zg[b];                  // functions.jl:149
+                bn[a] = ok ? sdraw : bo[a];
+                db[a] = bn[a] - bo[a];
+            }
+#pragma unroll
+            for (int a = 0; a < K; ++a)
+                if (lane == gl + a) { bnew[i] = bn[a]; inc[i] = true; mydb[i] = db[a]; }
+            // restore the later columns of the step (everything after the locus)
+            const int mlast = m0 + K - 1;
+#pragma unroll
+            for (int i2 = i; i2 < NS; ++i2)
+                if (32 * i2 + lane > mlast) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int a = 0; a < K; ++a) {
+                        const double gc = (double)gram[i2][(kb[i2] - ka) * B * B + (qa0 + a) * B + qb[i2]] - csg[a] * cs[i2] * inv_n;
+                        acc = fma(gc, db[a], acc);
+                    }
+                    rr[i2] -= acc;
+                }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        NzList& ml = cnz[(g0 + (unsigned)kb[i]) & (kNzRing - 1)];
+        ml.idx[qb[i]] = qb[i]; ml.db[qb[i]] = mydb[i]; ml.aux[qb[i]] = cs[i];
+    }
+}
+
 // ----------------------------------------------------------------------------- the kernel
 // LIT: the per-marker ("literal") sweep instead of the blocked one — a separate instantiation, so that neither variant carries the other's code
-template <int B, bool PROF, bool DBG, bool LIT>
+// TUP: the instantiation that also sweeps a tuple of interleaved marker sets (method 4); kept apart so that the k x k algebra does not
+//      weigh on the register allocation of the single-trait sweep
+template <int B, bool PROF, bool DBG, bool LIT, bool TUP>
 __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -461,6 +580,16 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
             const SetDev& S = P.sets[s];
             for (int64_t j = (int64_t)t * kThreads + tid; j < S.p_pad; j += (int64_t)(Tw + 1) * kThreads)
                 prep_marker(P, S, s, j, varE, iter, rp_row);
+            if (TUP && S.method == 4) {                            // invB = inv(varBeta[mSet][r]) (functions.jl:143), one thread per region
+                const int k = S.group_k;
+                for (int64_t rg = (int64_t)t * kThreads + tid; rg < S.n_regions; rg += (int64_t)(Tw + 1) * kThreads) {
+                    double Sg[16], Iv[16];
+                    for (int i = 0; i < k * k; ++i) Sg[i] = __ldcg(&S.jvar[rg * k * k + i]);
+                    const bool ok = (k == 2) ? jt_inv_spd<2>(Sg, Iv) : jt_inv_spd<4>(Sg, Iv);
+                    if (!ok) { atomicOr(&sy->err, 2); for (int i = 0; i < k * k; ++i) Iv[i] = 0.0; }
+                    for (int i = 0; i < k * k; ++i) S.jinvB[rg * k * k + i] = Iv[i];
+                }
+            }
         }
         __syncthreads();
         gs.nbar++;
@@ -838,6 +967,16 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 #pragma unroll
                             for (int k = 0; k < SB; ++k) nn[k] = 0;
                             int pos = (dbg & 4) ? SM : 0;                       // markers [0, pos) of the step are committed
+                            if (TUP && method == 4 && pos < SM) {
+                                // Tuple of k interleaved marker sets (functions.jl:140-154): lanes g0 .. g0+k-1 of a slot hold the k breeds of one locus.
+                                // Strictly sequential over the loci; per locus the k x k solve is evaluated by every lane (uniform inputs).
+                                if (S.group_k == 2) joint_step<B, NS, 2>(rr, bold, cs, cQ, cT, bnew, inc, gram, kb, qb, cnz, g0, lane, inv_n, 1.0 / varE, S.jinvB, sy);
+                                else joint_step<B, NS, 4>(rr, bold, cs, cQ, cT, bnew, inc, gram, kb, qb, cnz, g0, lane, inv_n, 1.0 / varE, S.jinvB, sy);
+#pragma unroll
+                                for (int k = 0; k < SB; ++k) nn[k] = B;
+                                if constexpr (PROF) pf[7] += SM;
+                                pos = SM;
+                            }
                             if (method == 0 && pos < SM) {
                                 // BayesPR: every effect is redrawn, so there is nothing to speculate on and the positions of the changes are
                                 // known: the dependent chain per marker is  beta_new = rr*C + QSZ -> dbeta -> shuffle -> rr of the later markers;
@@ -1312,7 +1451,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
             if constexpr (PROF) tc = clock64();
 
             // ------------------------------------------------------------------ phase 3 (chain CTA)
-            const bool regional = (S.method == 0 && S.n_regions > 1);
+            const bool regional = (S.method == 0 && S.n_regions > 1) || S.method == 4;
             const int p3warp = LIT ? 0 : kHelperWarp;     // the warp that accumulated beta'beta and nLoci
             if (is_chain && warp == p3warp && S.method == 3) {
                 const double sumS = warp_sum(acc_bb);
@@ -1369,7 +1508,39 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     S.sum_delta[j] += (S.method == 0) ? 1.0 : (double)__ldcg(&S.delta[j]);
                 }
             }
-            if (regional) {
+            if (TUP && S.method == 4) {
+                // Sigma_r ~ InvWishart(df + |r|, scale + B_r'B_r) (functions.jl:152, 513-516), one warp per region; effects are interleaved
+                const int k = S.group_k;
+                Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)S.stream_set};
+                for (int64_t rg = (int64_t)t * kWarps + warp; rg < S.n_regions; rg += (int64_t)(Tw + 1) * kWarps) {
+                    const int64_t c0 = S.region_off[rg], c1 = S.region_off[rg + 1];          // column offsets = locus offsets * k
+                    double Sb[16];
+                    for (int x = 0; x < k * k; ++x) Sb[x] = 0.0;
+                    for (int64_t c = c0 + (int64_t)lane * k; c < c1; c += 32 * k) {
+                        double bj[4];
+                        for (int b = 0; b < k; ++b) bj[b] = __ldcg(&S.beta[c + b]);
+                        for (int a = 0; a < k; ++a)
+                            for (int b = a; b < k; ++b) Sb[a * k + b] = fma(bj[a], bj[b], Sb[a * k + b]);
+                    }
+                    for (int a = 0; a < k; ++a)
+                        for (int b = a; b < k; ++b) { const double v = warp_sum(Sb[a * k + b]); Sb[a * k + b] = v; Sb[b * k + a] = v; }
+                    if (lane == 0) {
+                        double Psi[16], chi2[4], zl[16], Sg[16];
+                        const double dfr = S.df + (double)((c1 - c0) / k);
+                        for (int x = 0; x < k * k; ++x) { Psi[x] = S.jscale[x] + Sb[x]; zl[x] = 0.0; }
+                        for (int i = 0; i < k; ++i) {
+                            chi2[i] = P.replay ? S.rp_iw_chi2[(rp_row * S.n_regions + rg) * k + i]
+                                               : stream_chisq(st, P_IW, (uint32_t)rg, (uint32_t)(i * k + i), dfr - (double)i);
+                            for (int jj = 0; jj < i; ++jj)
+                                zl[i * k + jj] = P.replay ? S.rp_iw_z[((rp_row * S.n_regions + rg) * k + i) * k + jj]
+                                                          : stream_normal(st, P_IW, (uint32_t)rg, 0, (uint32_t)(i * k + jj));
+                        }
+                        const bool ok = (k == 2) ? jt_inv_wishart<2>(Psi, chi2, zl, Sg) : jt_inv_wishart<4>(Psi, chi2, zl, Sg);
+                        if (ok) { for (int x = 0; x < k * k; ++x) S.jvar[rg * k * k + x] = Sg[x]; }
+                        else atomicOr(&sy->err, 2);
+                    }
+                }
+            } else if (regional) {
                 Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)s};
                 for (int64_t rg = (int64_t)t * kWarps + warp; rg < S.n_regions; rg += (int64_t)(Tw + 1) * kWarps) {
                     const int64_t j0 = S.region_off[rg], j1 = S.region_off[rg + 1];

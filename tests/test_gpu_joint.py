@@ -44,9 +44,12 @@ V3 = np.array([[0.02, 0.004, 0.002], [0.004, 0.03, -0.003], [0.002, -0.003, 0.02
 
 
 @pytest.mark.parametrize("n,p,k,v,regions,kw", [
-    (700, 96, 2, V2, None, {}),
-    (1203, 150, 3, V3, [0, 40, 41, 150], dict(min_rows=64)),
+    (700, 96, 2, V2, None, {}),                                          # blocked tuple sweep (interleaved copy, joint draw in the chain warp)
+    (700, 96, 2, V2, None, dict(kernel="literal")),                      # per-locus kernel
+    (1203, 150, 3, V3, [0, 40, 41, 150], dict(min_rows=64)),             # k = 3 does not divide the block: per-locus kernel
     (333, 70, 2, V2, [0, 10, 70], dict(block=16, max_ctas=5)),
+    (900, 200, 2, V2, [0, 64, 65, 130, 200], dict(block=64, lookahead=3)),
+    (500, 48, 4, np.eye(4) * 0.02 + 0.004, [0, 20, 48], dict(min_rows=32)),
 ])
 def test_joint_native_chain_matches_oracle(gpu, n, p, k, v, regions, kw):
     probs, y = _breeds(n, p, k, 11)
@@ -79,14 +82,15 @@ def test_joint_replay_and_sweep_level_call(gpu):
         logs.append(ch.iteration(seed=901, chain=0))
         jlogs.append(mb.sweep(ch.e, ch.varE, it=ch.iter, seed=901, chain=0))
     # replay: the device consumes the logged variates instead of its own stream (different seed on purpose)
-    g = _gpu(probs, y, V2, ro, v_e)
-    g.set_rng(1, 0)
-    g.set_replay(logs)
-    g.set_joint_replay(jlogs)
-    g.run(3)
-    st, js = g.state(), g.joint_state()
-    assert rel(js["beta"], mb.beta) < 1e-8 and rel(js["varBeta"], mb.varBeta) < 1e-8 and rel(st["e"], ch.e) < 1e-8
-    g.close()
+    for kern in ("blocked", "literal"):
+        g = _gpu(probs, y, V2, ro, v_e, kernel=kern)
+        g.set_rng(1, 0)
+        g.set_replay(logs)
+        g.set_joint_replay(jlogs)
+        g.run(3)
+        st, js = g.state(), g.joint_state()
+        assert rel(js["beta"], mb.beta) < 1e-8 and rel(js["varBeta"], mb.varBeta) < 1e-8 and rel(st["e"], ch.e) < 1e-8
+        g.close()
     # sweep level: host buffers in, mutated in place, like the reference's M[mSet].funct call
     ch2, mb2 = _oracle(probs, y, V2, ro, v_e)
     g = _gpu(probs, y, V2, ro, v_e)
