@@ -32,6 +32,7 @@ CONFIGS = {
     "c4": (30000, 50000, "MultiBreed2"),
     "c5": (200000, 50000, "BayesC"),
     "tiny": (2000, 4096, "BayesC"),
+    "c4rr": (30000, 100000, "BayesRR"),     # diagnostic: dense updates at the size of the interleaved C4 tuple
 }
 SEED0 = 20261018
 METRIC = "marker-updates/sec"
@@ -324,7 +325,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "marker-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": workload_name(args.config, n, p, model), "kernel": "joint (per locus)" if kbreeds else args.kernel, "chains": nchains,
+                "config": {"workload": workload_name(args.config, n, p, model), "kernel": ("blocked tuple sweep (interleaved copy, joint draw in the chain warp)" if args.kernel == "blocked" and kbreeds in (2, 4) else "joint (per locus)") if kbreeds else args.kernel, "chains": nchains,
                            "parallelism": (f"ONE chain row-sharded over {world} GPUs: per-marker fixed-point reduction pushed into every rank's "
                                            f"accumulators over NVLink peer memory (CUDA IPC), identical draw on every rank")
                                           if sharded else f"{world} independent chain(s), one per GPU, no data-path collective",
@@ -333,7 +334,8 @@ def main():
                            "gibbs_iters_per_s": nchains * args.steps / (ms_all * 1e-3),
                            "geometry": {k: tm[k] for k in ("ctas", "threads", "block", "rows_per_cta", "smem_bytes", "lookahead", "near_depth", "tile_stages", "record_stages")}},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "kernel": "ngp::joint_kernel (one launch = one Gibbs iteration)" if kbreeds else
+                             "kernel": ("ngp::gibbs_kernel<TUP> (one launch = one Gibbs iteration)" if args.kernel == "blocked" and kbreeds in (2, 4)
+                                        else "ngp::joint_kernel (one launch = one Gibbs iteration)") if kbreeds else
                                        "ngp::gibbs_kernel (one launch = one Gibbs iteration)", "kernel_ms": k_ms,
                              "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": summarize_clocks(lines)}
