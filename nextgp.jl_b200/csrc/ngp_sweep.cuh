@@ -954,12 +954,24 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                     const int np = nn[SB - kk];                 // list sizes of the previous step are still in registers
                                     if (np == 0) continue;
                                     const NzList& pl = cnz[(g0 - (unsigned)kk) & (kNzRing - 1)];
-                                    for (int e = 0; e < np; ++e) {
-                                        const int a = pl.idx[e];
-                                        const double dbf = pl.db[e], csf = pl.aux[e];
+                                    // four entries at a time: the list reads and the Gram loads of a group are issued together (a dense
+                                    // list — BayesPR, tuple — has B entries; one entry at a time costs a full LDS -> LDS -> I2F -> DFMA chain each)
+                                    for (int e0 = 0; e0 < np; e0 += 4) {
+                                        int a4[4]; double db4[4], cs4[4]; int g4_[4][NS];
 #pragma unroll
-                                        for (int i = 0; i < NS; ++i)
-                                            rr[i] = fma(-((double)gram[i][(kb[i] + kk) * B * B + a * B + qb[i]] - csf * cs[i] * inv_n), dbf, rr[i]);
+                                        for (int u = 0; u < 4; ++u) {
+                                            const bool on = e0 + u < np;
+                                            a4[u] = on ? pl.idx[e0 + u] : 0; db4[u] = on ? pl.db[e0 + u] : 0.0; cs4[u] = on ? pl.aux[e0 + u] : 0.0;
+                                        }
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                            for (int i = 0; i < NS; ++i) g4_[u][i] = gram[i][(kb[i] + kk) * B * B + a4[u] * B + qb[i]];
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                            for (int i = 0; i < NS; ++i)
+                                                rr[i] = fma(-((double)g4_[u][i] - cs4[u] * cs[i] * inv_n), db4[u], rr[i]);
                                     }
                                 }
                             }
