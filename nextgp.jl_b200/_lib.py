@@ -121,6 +121,7 @@ _SIGS = {
     "ngp_read_bed_genotypes": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]),
     "ngp_set_phenotype": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "ngp_set_residual_prior": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "ngp_set_residual_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "ngp_set_intercept": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     "ngp_set_fixed_effects": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(FixedSet)]),
     "ngp_get_fixed_effects": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -384,6 +384,14 @@ class Sampler:
     def set_residual_prior(self, df_e: float, scale_e: float) -> None:
         self._ck(self._lib.ngp_set_residual_prior(self._h, df_e, scale_e))
 
+    def set_residual_weights(self, w) -> None:
+        """E.iVarStr of a "D" residual structure (mme.jl:70-73): one positive weight per individual; None returns to "I"."""
+        if w is None:
+            self._ck(self._lib.ngp_set_residual_weights(self._h, None, 0))
+            return
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        self._ck(self._lib.ngp_set_residual_weights(self._h, _p(w), len(w)))
+
     def set_intercept(self, enabled: bool = True, lhs0: float = 0.0, rhs0: float = 0.0) -> None:
         self._ck(self._lib.ngp_set_intercept(self._h, int(enabled), lhs0, rhs0))
 
@@ -692,8 +700,16 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
     if "e" not in priorVCV:
         priorVCV = dict(priorVCV, e=Random("I", 100.0))                       # mme.jl:79-84
     e_prior = priorVCV["e"]
-    if not (e_prior.str in ("I", [], None, "")):
-        raise NotImplementedError("weighted residuals (E.str == \"D\") stay in Julia: SURVEY §8(f3)")
+    weights = None
+    if isinstance(e_prior.str, (list, tuple, np.ndarray)) and len(e_prior.str) > 0:      # "D": mme.jl:70-73, iVarStr = inv.(D)
+        dvec = np.asarray(e_prior.str, dtype=np.float64)
+        if dvec.shape != (len(Y),):
+            raise ValueError("the \"D\" vector of priorVCV[:e] needs one entry per record")
+        weights = 1.0 / dvec
+        if fixed or any(isinstance(k, tuple) for k in priorVCV):
+            raise NotImplementedError("weighted residuals: intercept + marker-set models only (further fixed effects and tuples stay in Julia)")
+    elif not (isinstance(e_prior.str, str) and e_prior.str in ("I", "")) and not (e_prior.str is None or len(e_prior.str) == 0):
+        raise ValueError("provide a valid prior var-cov structure (\"I\", \"D\" or leave it empty \"[]\") for \"e\" ")   # mme.jl:76
     df_e = 4.0
     scale_e = 0.0005 if e_prior.v == 0.0 else e_prior.v * (df_e - 2.0) / df_e  # mme.jl:87-94
     tuples = [k for k in priorVCV if isinstance(k, tuple)]
@@ -751,6 +767,7 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
         sampler.set_fixed_effects([d for _, d, _ in fixed])                      # X[xSet] besides the intercept (functions.jl:22-54)
     sampler.set_phenotype(Y)
     sampler.set_residual_prior(df_e, scale_e)
+    sampler.set_residual_weights(weights)
     sampler.set_intercept(intercept)
     fx_names = [lv for _, _, lvs in fixed for lv in lvs]
     if outPut is not None:                                                       # header rows, mme.jl:543-595

@@ -11,6 +11,7 @@
 #include <stddef.h>
 #include <string.h>
 #include <math.h>
+#include <cmath>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -149,6 +150,34 @@ __global__ void unpack_kernel(const uint8_t* __restrict__ geno, int64_t n, int R
     out[jc * n + i] = (int8_t)geno[(t * nblk + k) * ((int64_t)B * R) + byte_off(B, (int)(j - k * B), (int)(i - t * R))];
 }
 
+// weighted residuals (E.str == "D"): mpm_j = sum_i w_i x_ij^2 with x = g - mean (mme.jl:299-301) and sum_i w_i x_ij; one CTA per marker
+__global__ void __launch_bounds__(256) weighted_moments_kernel(const uint8_t* __restrict__ geno, int64_t n, int R, int B, int64_t nblk, int64_t p,
+                                                                const double* __restrict__ mean, const double* __restrict__ w,
+                                                                double* __restrict__ dw, double* __restrict__ wcs)
+{
+    const int64_t j = blockIdx.x;
+    if (j >= p) return;
+    const int64_t k = j / B;
+    const int q = (int)(j - k * B);
+    const double m = mean[j];
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int64_t t = i / R;
+        const double x = (double)geno[(t * nblk + k) * ((int64_t)B * R) + byte_off(B, q, (int)(i - t * R))] - m;
+        const double wx = w[i] * x;
+        s1 += wx; s2 = fma(wx, x, s2);
+    }
+    __shared__ double sh[2 * 8];
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { sh[2 * (threadIdx.x >> 5)] = s1; sh[2 * (threadIdx.x >> 5) + 1] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int v = 0; v < 8; ++v) { a += sh[2 * v]; b += sh[2 * v + 1]; }
+        wcs[j] = a; dw[j] = b;
+    }
+}
+
 __global__ void region_of_kernel(const int64_t* region_off, int64_t n_regions, int32_t* region_of)
 {
     for (int64_t r = blockIdx.x; r < n_regions; r += gridDim.x)
@@ -211,6 +240,8 @@ struct SetHost {
     double *lhs0 = nullptr, *rhs0 = nullptr, *sum_beta = nullptr, *sum_beta2 = nullptr, *sum_delta = nullptr;
     int64_t* region_off = nullptr;
     double *rp_u = nullptr, *rp_z = nullptr, *rp_chi2b = nullptr, *rp_betapi = nullptr;
+    double *dw = nullptr, *wcs = nullptr;      // weighted residuals: weighted mpm, weighted centred column sums
+    bool w_ready = false;
 };
 
 struct JointHost {      // tuple of marker sets with jointly drawn effects (mme.jl:448-489)
@@ -243,6 +274,8 @@ struct ngp_handle {
     JointHost joint;
     int n_sets = 0;
     double* e = nullptr;
+    double* w = nullptr;           // residual weights E.iVarStr (mme.jl:73), [Tw*R], or null
+    double w_sum = 0.0, w_min = 0.0, w_max = 0.0;
     bool have_y = false;
     double df_e = 4.0, scale_e = 0.0;
     int has_mu = 0;
@@ -327,6 +360,7 @@ static void free_set(SetHost& s)
     cudaFree(s.d); cudaFree(s.mean); cudaFree(s.beta); cudaFree(s.varBeta); cudaFree(s.pi); cudaFree(s.pi_class); cudaFree(s.jinvB);
     cudaFree(s.lhs0); cudaFree(s.rhs0); cudaFree(s.sum_beta); cudaFree(s.sum_beta2); cudaFree(s.sum_delta);
     cudaFree(s.region_off); cudaFree(s.rp_u); cudaFree(s.rp_z); cudaFree(s.rp_chi2b); cudaFree(s.rp_betapi);
+    cudaFree(s.dw); cudaFree(s.wcs);
     s = SetHost();
 }
 
@@ -388,7 +422,7 @@ int ngp_destroy(ngp_handle* h)
     for (auto& s : h->sets) free_set(s);
     free_joint(h->joint);
     for (int r = 0; r < h->shard_world; ++r) if (h->peer_ipc[r] && h->peer[r]) cudaIpcCloseMemHandle(h->peer[r]);
-    cudaFree(h->e); cudaFree(h->sc); cudaFree(h->sync); cudaFree(h->sets_dev);
+    cudaFree(h->e); cudaFree(h->w); cudaFree(h->sc); cudaFree(h->sync); cudaFree(h->sets_dev);
     cudaFree(h->rp_chi2_e); cudaFree(h->rp_z_mu);
     if (h->stage) cudaFreeHost(h->stage);
     cudaFree(h->fx_data); cudaFree(h->fx_xpx); cudaFree(h->fx_colsum); cudaFree(h->fx_b); cudaFree(h->fx_rp_z);
@@ -687,7 +721,7 @@ int ngp_get_column_stats(ngp_handle* h, int set_id, double* mean, double* mpm)
     SetHost& S = h->sets[set_id];
     CU(cudaSetDevice(h->device));
     if (mean) CU(cpy(h, mean, S.mean, sizeof(double) * S.p, cudaMemcpyDeviceToHost));
-    if (mpm) CU(cpy(h, mpm, S.d, sizeof(double) * S.p, cudaMemcpyDeviceToHost));
+    if (mpm) CU(cpy(h, mpm, (h->w && S.w_ready) ? S.dw : S.d, sizeof(double) * S.p, cudaMemcpyDeviceToHost));   // weighted once sampled with weights
     return NGP_OK;
 }
 
@@ -744,6 +778,30 @@ int ngp_set_residual_prior(ngp_handle* h, double df_e, double scale_e)
     if (!h) return NGP_EINVAL;
     if (!(df_e > 0.0) || !(scale_e >= 0.0)) return fail(h, NGP_EINVAL, "ngp_set_residual_prior: df must be > 0 and scale >= 0");
     h->df_e = df_e; h->scale_e = scale_e;
+    return NGP_OK;
+}
+
+// E.str == "D" (mme.jl:70-73): w = E.iVarStr = inv.(priorVCV[:e].str), one positive weight per individual; NULL returns to "I".
+// Replaces sum(e.^2) by sum(w.*e.^2) in sampleVarE (functions.jl:526-528), xpx / Xp of the intercept (mme.jl:135-136) and
+// mpm / Mp of every marker set (mme.jl:299-303).  Sampled by the per-marker kernel (the weighted dots are not integer sums of codes).
+int ngp_set_residual_weights(ngp_handle* h, const double* w, int64_t n)
+{
+    if (!h) return NGP_EINVAL;
+    CU(cudaSetDevice(h->device));
+    for (auto& S : h->sets) S.w_ready = false;
+    h->sets_dirty = true;
+    if (!w) { cudaFree(h->w); h->w = nullptr; return NGP_OK; }
+    if (h->Tw == 0) return fail(h, NGP_EINVAL, "ngp_set_residual_weights: upload a marker set first (it fixes n)");
+    if (n != h->n) return fail(h, NGP_EINVAL, "ngp_set_residual_weights: n = %lld but the genotypes have %lld rows", (long long)n, (long long)h->n);
+    double sum = 0.0, lo = INFINITY, hi = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (!(w[i] > 0.0) || !std::isfinite(w[i])) return fail(h, NGP_EINVAL, "ngp_set_residual_weights: weight %lld is not a positive finite number", (long long)i);
+        sum += w[i]; lo = std::min(lo, w[i]); hi = std::max(hi, w[i]);
+    }
+    if (!h->w) CU(dalloc(&h->w, (size_t)h->Tw * h->R));
+    CU(zero(h, h->w, 0, sizeof(double) * (size_t)h->Tw * h->R));
+    CU(cpy(h, h->w, w, sizeof(double) * n, cudaMemcpyHostToDevice));
+    h->w_sum = sum; h->w_min = lo; h->w_max = hi;
     return NGP_OK;
 }
 
@@ -958,6 +1016,7 @@ static int sync_sets(ngp_handle* h)
         if (S.group_k) { D.jvar = h->joint.varBeta; for (int a = 0; a < S.group_k * S.group_k; ++a) D.jscale[a] = h->joint.scale[a]; D.rp_iw_chi2 = h->joint.rp_iw_chi2; D.rp_iw_z = h->joint.rp_iw_z; D.rp_z = h->joint.rp_z; }
         D.n_class = S.n_class; D.pi_class = S.pi_class; memcpy(D.v_class, S.v_class, sizeof D.v_class);
         D.geno = S.geno; D.gx = S.gx; D.consts = S.consts; D.colsum = S.colsum; D.d = S.d; D.mean = S.mean;
+        if (h->w && S.w_ready) { D.d = S.dw; D.d_unw = S.d; D.wcs = S.wcs; }
         D.beta = S.beta; D.delta = S.delta; D.varBeta = S.varBeta; D.pi = S.pi; D.region_of = S.region_of; D.region_off = S.region_off;
         D.lhs0 = S.lhs0; D.rhs0 = S.rhs0;
         D.rp_u = S.rp_u; D.rp_z = S.group_k ? h->joint.rp_z : S.rp_z; D.rp_chi2b = S.rp_chi2b; D.rp_betapi = S.rp_betapi;
@@ -980,6 +1039,7 @@ static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int 
     P.key0 = (uint32_t)(h->seed & 0xffffffffu); P.key1 = (uint32_t)(h->seed >> 32); P.chain = h->chain; P.accumulate = accumulate;
     P.debug = h->cfg_debug;
     P.fx = h->fx; P.fx.rp_z = h->fx_rp_z;
+    P.w = h->w; P.w_sum = h->w_sum; P.w_min = h->w_min; P.w_max = h->w_max;
     P.n_ranks = h->shard_world; P.rank = h->shard_rank; P.n_total = h->shard_world > 1 ? h->n_total : h->n;
     P.cta_off = 0; P.T_all = h->Tw + 1; P.Tw_all = h->Tw; P.bar_base = 0;
     P.peer[0] = h->sync;
@@ -1079,10 +1139,28 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
         CU(cpy(h, &sc, h->sc, sizeof sc, cudaMemcpyDeviceToHost));
         if (sc.iter - h->replay_base + n_iter > h->replay_iters) return fail(h, NGP_EINVAL, "replay log exhausted (%d iterations)", h->replay_iters);
     }
+    if (h->w) {
+        if (sharded || h->fx.n_cols || h->joint.active)
+            return fail(h, NGP_EUNSUPPORTED, "weighted residuals: available for intercept + marker-set models on one GPU (no tuple, no further fixed effects, no row sharding)");
+        for (int s = 0; s < h->n_sets; ++s) {
+            SetHost& S = h->sets[s];
+            if (!((set_mask >> s) & 1)) continue;
+            if (S.method == NGP_BAYESR) return fail(h, NGP_EUNSUPPORTED, "weighted residuals are not available for BayesR");
+            if (S.w_ready) continue;
+            if (!S.dw) { CU(dalloc(&S.dw, S.p_pad)); CU(dalloc(&S.wcs, S.p_pad)); }
+            CU(zero(h, S.dw, 0, sizeof(double) * S.p_pad));
+            CU(zero(h, S.wcs, 0, sizeof(double) * S.p_pad));
+            weighted_moments_kernel<<<(unsigned)S.p, 256, 0, h->stream>>>(S.geno, h->n, h->R, h->B, S.p_pad / h->B, S.p, S.mean, h->w, S.dw, S.wcs);
+            CU(cudaGetLastError());
+            S.w_ready = true;
+            h->sets_dirty = true;
+        }
+    }
     int rc = sync_sets(h);
     if (rc) return rc;
     Params P{};
     fill_params(h, P, n_iter, set_mask, do_varE, do_mu, varE_in, accumulate);
+    if (h->w) P.kernel = NGP_KERNEL_LITERAL;            // weighted dots are not integer sums of codes: per-marker sweep
     for (int s = 0; s < h->n_sets; ++s)
         if (((set_mask >> s) & 1) && h->sets[s].method == NGP_BAYESR) P.kernel = NGP_KERNEL_LITERAL;     // the class algebra lives in the per-marker sweep
 #define NGP_PICK(PROF, DBG, LIT, TUP) ((h->B == 64) ? (const void*)gibbs_kernel<64, PROF, DBG, LIT, TUP> : (h->B == 32) ? (const void*)gibbs_kernel<32, PROF, DBG, LIT, TUP> : (const void*)gibbs_kernel<16, PROF, DBG, LIT, TUP>)
@@ -1149,6 +1227,7 @@ static bool tuple_use_blocked(const ngp_handle* h) { return h->joint.blocked_set
 
 static int tuple_launch(ngp_handle* h, int n_iter, int do_varE, int do_mu, double varE_in, int accumulate)
 {
+    if (h->w) return fail(h, NGP_EUNSUPPORTED, "weighted residuals are not available for a tuple of marker sets");
     JointHost& J = h->joint;
     if (tuple_use_blocked(h)) {
         if (h->replay && (!J.rp_z || J.replay_iters != h->replay_iters))

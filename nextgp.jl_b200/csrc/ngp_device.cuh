@@ -89,6 +89,9 @@ struct SetDev {
     double* jinvB;                 // [n_regions][k][k] their inverses, refreshed in phase 1
     const double* rp_iw_chi2;      // replay of the inverse-Wishart draw: [iter][n_regions][k]
     const double* rp_iw_z;         //                                     [iter][n_regions][k][k]
+    // weighted residuals (E.str == "D", mme.jl:299-303; per-marker kernel only): d then points at the WEIGHTED mpm
+    const double* d_unw;       // [p_pad] unweighted mpm x_j'x_j (the BayesB/C inclusion dot is unweighted: functions.jl:168, :208) or null
+    const double* wcs;         // [p_pad] sum_i w_i (g_ij - mean_j): change of sum_i w_i e_i per unit change of the effect
     double* sum_beta;          // posterior sums [p_pad]
     double* sum_beta2;
     double* sum_delta;
@@ -165,6 +168,9 @@ struct Params {
     unsigned long long bar_base;   // barrier arrivals counted before this launch (sharded: the counter is never reset)
     SyncArea* peer[kMaxRanks];
     FxDev fx;
+    // weighted residuals: w = E.iVarStr = inv.(D) (mme.jl:73), zero beyond row n; null = "I"
+    const double* w;           // [Tw*R]
+    double w_sum, w_min, w_max;
 };
 
 // ----------------------------------------------------------------------------- tile layout

@@ -398,6 +398,11 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         for (int q = tid; q < kSlots * B; q += kThreads) prev[q] = sy->acc[((size_t)(q / B) * kMaxB + (q % B)) * kAccStride];
     }
     if (tid < kSlots) reinterpret_cast<long long*>(misc + 48)[tid] = sy->acc[(size_t)tid * kMaxB * kAccStride];      // literal kernel: previous accumulator values
+    // weighted residuals (per-marker kernel): the second accumulator of a slot carries the UNWEIGHTED dot; lane l of warp 0 keeps
+    // its previous value for slot l (kSlots == 32)
+    const bool wt = LIT && P.w != nullptr;
+    long long prev_u = 0;
+    if (LIT && warp == 0) prev_u = sy->acc[((size_t)lane * kMaxB + 1) * kAccStride];
     if (tid == 0) *cprog = 0u;
     if (tid == 0) {
         if (!is_chain) {
@@ -441,7 +446,14 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 
         // ------------------------------------------------------------------ phase 0
         double ee = 0.0, se = 0.0;
-        if (!is_chain) for (int r = tid; r < R; r += kThreads) { const double x = e_s[r]; ee = fma(x, x, ee); se += x; }
+        if (wt) {
+            // E.str == "D": e'We (functions.jl:526-528) and 1'We (Xp of the intercept, mme.jl:136); the plain 1'e goes along for the
+            // unweighted inclusion dots of BayesB/C
+            double su = 0.0, dm = 0.0;
+            if (!is_chain) for (int r = tid; r < R; r += kThreads) { const double x = e_s[r], wv = __ldg(&P.w[row0 + r]); ee = fma(wv * x, x, ee); se = fma(wv, x, se); su += x; }
+            block_sum2(su, dm, misc);
+            if (tid == 0) sy->part_fx[t * kMaxFxCols] = su;
+        } else if (!is_chain) for (int r = tid; r < R; r += kThreads) { const double x = e_s[r]; ee = fma(x, x, ee); se += x; }
         block_sum2(ee, se, misc);
         if (tid == 0) {
             if (sharded) {
@@ -451,10 +463,11 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         } else gs.nbar++;
         if (warp == 0) {
             gs.wait_warp();
-            double a = 0.0, b = 0.0;
+            double a = 0.0, b = 0.0, bu = 0.0;
             const int nparts = sharded ? P.T_all : Tw;     // same order on every rank: identical sums, identical draws
-            for (int c = lane; c < nparts; c += 32) { a += __ldcg(&sy->part[2 * c]); b += __ldcg(&sy->part[2 * c + 1]); }
+            for (int c = lane; c < nparts; c += 32) { a += __ldcg(&sy->part[2 * c]); b += __ldcg(&sy->part[2 * c + 1]); if (wt) bu += __ldcg(&sy->part_fx[c * kMaxFxCols]); }
             a = warp_sum(a); b = warp_sum(b);
+            if (wt) bu = warp_sum(bu);
             if (lane == 0) {
                 double varE = P.varE_in;
                 if (P.do_varE) {
@@ -467,8 +480,9 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     Stream st{P.key0, P.key1, P.chain, iter, 0u};
                     const double zmu = P.replay ? P.rp_z_mu[rp_row] : stream_normal(st, P_Z_MU, 0);
                     const double iVarE = 1.0 / varE;
-                    const double rhs = (b + (double)P.n_total * mu) * iVarE + P.mu_rhs0;
-                    const double lhs = (double)P.n_total * iVarE + P.mu_lhs0;
+                    const double xpx = wt ? P.w_sum : (double)P.n_total;               // mme.jl:135 / :138
+                    const double rhs = (b + xpx * mu) * iVarE + P.mu_rhs0;
+                    const double lhs = xpx * iVarE + P.mu_lhs0;
                     const double mu_new = rhs / lhs + sqrt(1.0 / lhs) * zmu;
                     dmu = mu - mu_new;
                     mu = mu_new;
@@ -477,17 +491,21 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                 // for growth of ||e|| inside the iteration, 8 count bits: the grid total stays below 2^55
                 const double nn = (double)P.n_total;
                 double M = 2.0 * sqrt(nn) * (sqrt(a) + sqrt(nn) * fabs(dmu));
+                if (wt) M = 2.0 * sqrt(nn) * (sqrt(a / P.w_min) + sqrt(nn) * fabs(dmu)) * fmax(1.0, P.w_max);    // |sum g w e| <= 2 sqrt(n) max(w) ||e||
                 if (!(M > 1e-300)) M = 1e-300;
                 int ex; (void)frexp(M, &ex);
                 int sh = 62 - kCntBits - 4 - ex;
                 sh = max(-1000, min(1000, sh));
-                misc[32] = varE; misc[33] = dmu; misc[34] = b + nn * dmu; misc[35] = (double)sh; misc[36] = mu;
+                misc[32] = varE; misc[33] = dmu; misc[34] = b + (wt ? P.w_sum : nn) * dmu; misc[35] = (double)sh; misc[36] = mu;
+                if (wt) misc[37] = bu + nn * dmu;
             }
         }
         __syncthreads();
         const double varE = misc[32];
         const double dmu = misc[33];
         double Stot = misc[34];                       // 1'e after the intercept update; invariant under marker updates
+                                                      // (weighted residuals: 1'We, which every changed effect moves by wcs_j)
+        const double Stot_u = wt ? misc[37] : 0.0;    // weighted residuals: the plain 1'e (invariant)
         const int sh = (int)misc[35];
         mu = misc[36];
         const double fx_scale = ldexp(1.0, sh), fx_inv = ldexp(1.0, -sh);
@@ -1362,7 +1380,21 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     long long* acc = sy->acc + (size_t)slot * kMaxB * kAccStride;
                     uint32_t w0 = 0;
                     double a = 0.0, dummy = 0.0;
+                    const bool two = wt && (S.method == 1 || S.method == 2);      // BayesB/C: inclusion from the unweighted dot, mean from Mp_j'e
                     if (!is_chain) {
+                        if (wt) {
+                            // a = (x_j .* w)'e (Mp, mme.jl:303), dummy = x_j'e
+                            for (int wr = tid; wr < nwords; wr += kThreads) {
+                                const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(tile) + word_off(B, q, wr));
+                                if (wr == tid) w0 = w;
+                                const double* ep = e_s + 4 * wr;
+                                const double* wp = P.w + row0 + 4 * wr;
+                                const double c0 = (double)(w & 0xff), c1 = (double)((w >> 8) & 0xff), c2 = (double)((w >> 16) & 0xff), c3 = (double)(w >> 24);
+                                a = fma(c0 * __ldg(wp), ep[0], a); a = fma(c1 * __ldg(wp + 1), ep[1], a);
+                                a = fma(c2 * __ldg(wp + 2), ep[2], a); a = fma(c3 * __ldg(wp + 3), ep[3], a);
+                                dummy = fma(c0, ep[0], dummy); dummy = fma(c1, ep[1], dummy); dummy = fma(c2, ep[2], dummy); dummy = fma(c3, ep[3], dummy);
+                            }
+                        } else
                         for (int wr = tid; wr < nwords; wr += kThreads) {
                             const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(tile) + word_off(B, q, wr));
                             if (wr == tid) w0 = w;
@@ -1373,6 +1405,11 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     }
                     block_sum2(a, dummy, misc);
                     if (tid == 0 && !is_chain) {
+                        if (two) {
+                            const double xu = dummy * fx_scale;
+                            if (!(fabs(xu) < 9007199254740992.0)) atomicOr(&sy->err, 1);
+                            red_add_u64(acc + kAccStride, (long long)((unsigned long long)__double2ll_rn(xu) << kCntBits) + 1);
+                        }
                         const double xs = a * fx_scale;
                         if (!(fabs(xs) < 9007199254740992.0)) atomicOr(&sy->err, 1);
                         const long long v = (long long)((unsigned long long)__double2ll_rn(xs) << kCntBits) + 1;
@@ -1400,6 +1437,15 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         if (lane == 0) *pv = cur;
                         const double r = A - mean * Stot;
                         const double rr = fma(d, bold, r);
+                        double rq = rr;                                                 // the dot of the inclusion test
+                        if (two) {
+                            const long long pu = __shfl_sync(0xffffffffu, prev_u, slot);
+                            long long cu;
+                            do { cu = ld_relaxed_s64(acc + kAccStride); } while (((cu - pu) & 0xFF) != arrivals);
+                            if (lane == slot) prev_u = cu;
+                            const double Au = (double)((cu - pu - arrivals) >> kCntBits) * fx_inv;
+                            rq = fma(__ldg(&S.d_unw[j]), bold, Au - mean * Stot_u);       // functions.jl:168, :208: view(data,:,locus)'ycorr
+                        }
                         if (nc) {
                             // class likelihoods (functions.jl:250-258), one class per lane
                             const double iVarE = 1.0 / varE;
@@ -1427,9 +1473,10 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                 if (is_chain) { S.beta[j] = bn; S.delta[j] = cls + 1; }
                             }
                         } else {
-                        const double dl = fma(cB, rr * rr, cA);
+                        const double dl = fma(cB, rq * rq, cA);
                         const bool in = dl < cT;
                         const double bn = in ? fma(rr, cC, cQ) : 0.0;
+                        if (wt) Stot -= (bn - bold) * __ldg(&S.wcs[j]);                   // 1'We after e -= x_j (bn - bold)
                         if (lane == 0) {
                             misc[40] = bn - bold; misc[41] = mean;
                             acc_bb = fma(bn, bn, acc_bb);

@@ -354,6 +354,46 @@ double ngo_sample_intercept(int64_t n, double* e, double mu_old, double varE, do
     return mu;
 }
 
+/* ------------------------------------------------------------------------- */
+/* weighted residuals, E.str == "D" (mme.jl:70-73: iVarStr = inv.(D), w_i = 1/d_ii) */
+/*   residual variance  functions.jl:526-528 (called at samplers.jl:32-33):     */
+/*     (df*scale + sum(w .* e.^2)) / chi2(df + n)                               */
+/*   intercept          functions.jl:39-47 with xpx = 1'W1, Xp = (1 .* w)'       */
+/*     (mme.jl:133-136)                                                         */
+/*   the marker sweeps take Mp = (x_j .* w)' and mpm = sum(x_j .* w .* x_j)     */
+/*   (mme.jl:299-303) through ngo_set.Mp / ngo_set.mpm; the add-back and the    */
+/*   BayesB/C inclusion dot (functions.jl:168, :208) stay unweighted.           */
+/* ------------------------------------------------------------------------- */
+double ngo_sample_varE_w(int64_t n, const double* e, const double* w, double df_e, double scale_e,
+                         int replay, uint64_t seed, uint32_t chain, uint32_t iter, double* chi2_e)
+{
+    if (!replay) {
+        ngo_stream s = {seed, chain, iter, 0};
+        *chi2_e = stream_chisq(&s, NGO_P_CHI2_E, 0, 0, df_e + (double)n);
+    }
+    double ss = 0.0;
+    for (int64_t i = 0; i < n; ++i) ss += w[i] * (e[i] * e[i]);
+    return (df_e * scale_e + ss) / (*chi2_e);
+}
+
+double ngo_sample_intercept_w(int64_t n, double* e, const double* w, double mu_old, double varE, double lhs0, double rhs0,
+                              int replay, uint64_t seed, uint32_t chain, uint32_t iter, double* z_mu)
+{
+    const double iVarE = 1.0 / varE;
+    double sum = 0.0, xpx = 0.0;
+    for (int64_t i = 0; i < n; ++i) { e[i] += mu_old; sum += w[i] * e[i]; xpx += w[i]; }
+    const double rhs = sum * iVarE + rhs0;
+    const double lhs = xpx * iVarE + lhs0;
+    const double meanMu = rhs / lhs;
+    if (!replay) {
+        ngo_stream s = {seed, chain, iter, 0};
+        *z_mu = stream_normal(&s, NGO_P_Z_MU, 0, 0, 0);
+    }
+    const double mu = meanMu + sqrt(1.0 / lhs) * (*z_mu);
+    for (int64_t i = 0; i < n; ++i) e[i] -= mu;
+    return mu;
+}
+
 /* sampleVarBetaPR: functions.jl:509-511 */
 static double sample_var_beta(double scale, double df, const double* b, int64_t k, double regionSizeOrNLoci, double chi2)
 {

@@ -108,6 +108,12 @@ def lib():
         L.ngo_sample_intercept.restype = C.c_double
         L.ngo_sample_intercept.argtypes = [C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
                                            C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
+        L.ngo_sample_varE_w.restype = C.c_double
+        L.ngo_sample_varE_w.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_uint64,
+                                        C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
+        L.ngo_sample_intercept_w.restype = C.c_double
+        L.ngo_sample_intercept_w.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                             C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
         L.ngo_sweep.restype = C.c_int
         L.ngo_sweep.argtypes = [C.POINTER(_Set), C.POINTER(_SetState), C.c_void_p, C.c_double, C.POINTER(_Variates)]
         L.ngo_fill_marker_variates.restype = None
@@ -283,11 +289,22 @@ class MarkerSet:
         return t
 
 
+def weighted_marker_arrays(X: np.ndarray, w: np.ndarray):
+    """mme.jl:299-303 for E.str == "D": mpm_j = sum(x_j .* w .* x_j), Mp_j = (x_j .* w)'."""
+    w = np.asarray(w, dtype=np.float64)
+    Mp = np.asfortranarray(X * w[:, None])
+    mpm = np.ascontiguousarray(np.einsum("ij,ij->j", Mp, X))
+    return Mp, mpm
+
+
 class OracleChain:
     """One chain: intercept (optional) + marker sets, iteration order of samplers.jl:32-53."""
 
     def __init__(self, y: np.ndarray, sets: list[MarkerSet], v_e: float, intercept: bool = True,
-                 mu_lhs0: float = 0.0, mu_rhs0: float = 0.0, fixed: list | None = None):
+                 mu_lhs0: float = 0.0, mu_rhs0: float = 0.0, fixed: list | None = None, weights: np.ndarray | None = None):
+        # weights = E.iVarStr of a "D" residual structure (mme.jl:70-73); the marker sets must then carry Mp = X .* w and the
+        # weighted mpm (mme.jl:299-303): see weighted_marker_arrays
+        self.w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
         self.fixed = fixed or []          # FixedSet objects, sampled after the intercept in this order (samplers.jl:37-39)
         self.y = np.asarray(y, dtype=np.float64)
         self.n = len(self.y)
@@ -308,12 +325,19 @@ class OracleChain:
         rep = replay is not None
         log: dict = {"iter": it}
         chi2_e = C.c_double(replay["chi2_e"] if rep else 0.0)
-        self.varE = L.ngo_sample_varE(self.n, _ptr(self.e), self.df_e, self.scale_e, int(rep), seed, chain, it, C.byref(chi2_e))
+        if self.w is not None:      # samplers.jl:32-33
+            self.varE = L.ngo_sample_varE_w(self.n, _ptr(self.e), _ptr(self.w), self.df_e, self.scale_e, int(rep), seed, chain, it, C.byref(chi2_e))
+        else:
+            self.varE = L.ngo_sample_varE(self.n, _ptr(self.e), self.df_e, self.scale_e, int(rep), seed, chain, it, C.byref(chi2_e))
         log["chi2_e"] = chi2_e.value
         if self.intercept:
             z_mu = C.c_double(replay["z_mu"] if rep else 0.0)
-            self.mu = L.ngo_sample_intercept(self.n, _ptr(self.e), self.mu, self.varE, self.mu_lhs0, self.mu_rhs0,
-                                             int(rep), seed, chain, it, C.byref(z_mu))
+            if self.w is not None:
+                self.mu = L.ngo_sample_intercept_w(self.n, _ptr(self.e), _ptr(self.w), self.mu, self.varE, self.mu_lhs0, self.mu_rhs0,
+                                                   int(rep), seed, chain, it, C.byref(z_mu))
+            else:
+                self.mu = L.ngo_sample_intercept(self.n, _ptr(self.e), self.mu, self.varE, self.mu_lhs0, self.mu_rhs0,
+                                                 int(rep), seed, chain, it, C.byref(z_mu))
             log["z_mu"] = z_mu.value
         log["z_fx"] = []
         for fi, F in enumerate(self.fixed):

@@ -113,3 +113,74 @@ def bayes_c(X, mpm, lhs0, scale, df, est_pi, beta, delta, ycorr, varE, varBeta, 
         piHat[:] = [1.0 - beta_pi, beta_pi]
         logPi[:] = np.log(piHat)
     return nLoci
+
+
+# --------------------------------------------------------------------------- weighted residuals, E.str == "D"
+#   iVarStr = inv.(D)                          mme.jl:73
+#   sampleVarE(E, ycorr, n)                    functions.jl:526-528 (samplers.jl:32-33)
+#   xpx = X'(iVarStr .* X), Xp = (X .* iVarStr)'   mme.jl:133-136
+#   mpm_j = sum(c .* iVarStr .* c), Mp_j = (c .* iVarStr)'   mme.jl:299-303
+# The sweeps below spell out which dot takes Mp (weighted) and which takes view(data,:,locus) (unweighted).
+def sample_varE_w(df_e, S_e, iVarStr, ycorr, n, chi2):
+    return (df_e * S_e + np.sum(iVarStr * (ycorr ** 2))) / chi2
+
+
+def sample_intercept_w(ycorr, iVarStr, b, varE, z, lhs0=0.0, rhs0=0.0):
+    iVarE = 1.0 / varE
+    ones = np.ones_like(ycorr)
+    xpx = ones @ (iVarStr * ones)
+    Xp = ones * iVarStr
+    ycorr += ones * b
+    rhs = (Xp @ ycorr) * iVarE + rhs0
+    lhs = xpx * iVarE + lhs0
+    b = rhs / lhs + np.sqrt(1.0 / lhs) * z
+    ycorr -= ones * b
+    return b
+
+
+def weighted_setup(X, iVarStr):
+    mpm = np.array([np.sum(X[:, j] * iVarStr * X[:, j]) for j in range(X.shape[1])])
+    Mp = [X[:, j] * iVarStr for j in range(X.shape[1])]
+    return mpm, Mp
+
+
+def bayes_pr_w(X, Mp, mpm, lhs0, rhs0, regions, scale, df, beta, ycorr, varE, varBeta, z, chi2_b):
+    iVarE = 1.0 / varE
+    for r in range(len(regions) - 1):
+        iVarBeta = 1.0 / varBeta[r]
+        for j in range(regions[r], regions[r + 1]):
+            ycorr += beta[j] * X[:, j]                       # :128 data
+            rhs = (Mp[j] @ ycorr) * iVarE + rhs0[j]          # :129 Mp
+            lhs = mpm[j] * iVarE + lhs0[j] + iVarBeta
+            beta[j] = sample_beta(rhs / lhs, lhs, z[j])
+            ycorr += -1.0 * beta[j] * X[:, j]                # :133 data
+        varBeta[r] = sample_var_beta_pr(scale, df, beta[regions[r]:regions[r + 1]], chi2_b[r])
+
+
+def bayes_bc_w(method_b, X, Mp, mpm, lhs0, rhs0, scale, df, est_pi, beta, delta, ycorr, varE, varBeta, piHat, logPi, u, z, chi2_b, beta_pi):
+    p = X.shape[1]
+    iVarE = 1.0 / varE
+    for j in range(p):
+        vb = varBeta[j] if method_b else varBeta[0]
+        with np.errstate(divide="ignore"):
+            iVarBeta = np.float64(1.0) / np.float64(vb)
+        ycorr += beta[j] * X[:, j]                           # :167 / :207 data
+        rrr = X[:, j] @ ycorr                                # :168 / :208 data (unweighted), with the weighted mpm below
+        if u[j] < _prob_delta1(mpm[j], rrr, varE, vb, logPi):
+            delta[j] = 1
+            rhs = (Mp[j] @ ycorr) * iVarE + (rhs0[j] if method_b else 0.0)     # :177 / :219 Mp
+            lhs = mpm[j] * iVarE + lhs0[j] + iVarBeta
+            beta[j] = sample_beta(rhs / lhs, lhs, z[j])
+            ycorr += -1.0 * beta[j] * X[:, j]
+            if method_b:
+                varBeta[j] = sample_var_beta_pr(scale, df, beta[j:j + 1], chi2_b[j])
+        else:
+            beta[j] = 0.0
+            delta[j] = 0
+            if method_b:
+                varBeta[j] = 0.0
+    if not method_b:
+        varBeta[0] = sample_var_beta_pr(scale, df, beta, chi2_b[0])
+    if est_pi:
+        piHat[:] = [1.0 - beta_pi, beta_pi]
+        logPi[:] = np.log(piHat)

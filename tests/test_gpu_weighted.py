@@ -1,0 +1,162 @@
+"""GPU parity of weighted residuals, E.str == "D" (mme.jl:70-73, 133-136, 299-303; functions.jl:526-528), through the C ABI
+against the CPU oracle: the residual variance uses sum(w .* e.^2), the intercept xpx = 1'W1 and Xp = w', every marker Mp_j = (x_j .* w)'
+and mpm_j = sum(x_j .* w .* x_j) — while the add-back and the BayesB/C inclusion dot stay unweighted (functions.jl:168, :208), so those
+samplers form two dots per marker.  Sampled by the per-marker kernel whatever NGP_CFG_KERNEL says.
+Tolerance as in test_gpu_parity.py (BASELINE.json north_star): replayed draws reproduce effects and variances to 1e-9 relative."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import nextgp.jl_b200 as ngp
+from common import make_problem, gpu_sampler, rel
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+CASES = [
+    ("BayesPR-RR", 0, dict(v=0.01)),
+    ("BayesPR-regions", 0, dict(v=0.01, region_off=[0, 17, 18, 90, 200, 333])),
+    ("BayesB", 1, dict(v=0.05, pi=0.1, est_pi=True)),
+    ("BayesC-pi", 2, dict(v=0.05, pi=0.05, est_pi=True)),
+    ("BayesC-fixedpi", 2, dict(v=0.05, pi=0.5, est_pi=False)),
+]
+
+
+def _weights(n, seed):
+    return np.random.default_rng(seed).uniform(0.25, 4.0, n)
+
+
+def _oracle(prob, w, method, intercept=True, lhs0=None, rhs0=None, **kw):
+    X, mean, _ = O.center_codes(prob["codes"])
+    Mp, mpm = O.weighted_marker_arrays(X, w)
+    ro = kw.pop("region_off", None)
+    S = O.MarkerSet(X=X, mpm=mpm, method=method, region_off=None if ro is None else np.array(ro), lhs0=lhs0, rhs0=rhs0, **kw)
+    S.Mp = Mp
+    return O.OracleChain(prob["y"], [S], v_e=prob["var_y"] / 2, intercept=intercept, weights=w), S
+
+
+def _check(st, o, method, intercept=True):
+    worst = max(rel(st["sets"][0]["beta"], o["sets"][0]["beta"]), abs(st["varE"] / o["varE"] - 1),
+                abs(st["mu"] - o["mu"]) / max(abs(o["mu"]), 1e-300) if intercept else 0.0,
+                rel(st["sets"][0]["varBeta"], o["sets"][0]["varBeta"]), rel(st["e"], o["e"]))
+    assert np.array_equal(st["sets"][0]["delta"], o["sets"][0]["delta"])
+    if method:
+        worst = max(worst, rel(st["sets"][0]["piHat"], o["sets"][0]["piHat"]))
+    return worst
+
+
+@pytest.mark.parametrize("kernel", ["blocked", "literal"])
+@pytest.mark.parametrize("name,method,kw", CASES, ids=[c[0] for c in CASES])
+def test_weighted_replay_parity(gpu, kernel, name, method, kw):
+    prob = make_problem(640, 333, 23)
+    w = _weights(640, 5)
+    ch, S = _oracle(prob, w, method, **dict(kw))
+    logs, snaps = [], []
+    for _ in range(10):
+        logs.append(ch.iteration(seed=42, chain=1))
+        snaps.append(ch.snapshot())
+    kw2 = dict(kw)
+    ro = kw2.pop("region_off", None)
+    g = gpu_sampler(prob, method, region_off=None if ro is None else np.array(ro), kernel=kernel, **kw2)
+    g.set_residual_weights(w)
+    g.set_replay(logs)
+    for it in range(10):
+        g.run(1)
+        worst = _check(g.state(), snaps[it], method)
+        assert worst < TOL, f"iteration {it + 1}: rel diff {worst}"
+    mean, mpm = g.column_stats(0)
+    assert rel(mpm, S.mpm) < 1e-12                      # the weighted mpm of mme.jl:301
+    g.close()
+
+
+def test_weighted_ragged_shape_no_intercept_summary_priors(gpu):
+    n, p = 257, 71
+    prob = make_problem(n, p, 29)
+    w = _weights(n, 9)
+    rng = np.random.default_rng(3)
+    lhs0, rhs0 = rng.uniform(0.0, 2.0, p), rng.normal(0, 0.5, p)
+    for method, kw in [(0, dict(v=0.02)), (1, dict(v=0.05, pi=0.3, est_pi=True)), (2, dict(v=0.05, pi=0.3, est_pi=True))]:
+        ch, S = _oracle(prob, w, method, intercept=False, lhs0=lhs0, rhs0=rhs0, **kw)
+        logs, snaps = [], []
+        for _ in range(6):
+            logs.append(ch.iteration(seed=1, chain=0))
+            snaps.append(ch.snapshot())
+        g = gpu_sampler(prob, method, intercept=False, lhs0=lhs0, rhs0=rhs0, min_rows=8, **kw)
+        g.set_residual_weights(w)
+        g.set_replay(logs)
+        for it in range(6):
+            g.run(1)
+            assert _check(g.state(), snaps[it], method, intercept=False) < TOL
+        g.close()
+
+
+def test_unit_weights_equal_the_unweighted_chain(gpu):
+    """w = 1 is E.str == "I": the weighted path must reproduce the unweighted chain (same Philox draws)."""
+    prob = make_problem(500, 200, 31)
+    kw = dict(v=0.05, pi=0.1, est_pi=True)
+    a = gpu_sampler(prob, 2, kernel="literal", **kw)
+    b = gpu_sampler(prob, 2, kernel="literal", **kw)
+    b.set_residual_weights(np.ones(500))
+    for s in (a, b):
+        s.set_rng(77, 0)
+        s.run(15)
+    sa, sb = a.state(), b.state()
+    assert np.array_equal(sa["sets"][0]["delta"], sb["sets"][0]["delta"])
+    assert rel(sb["sets"][0]["beta"], sa["sets"][0]["beta"]) < 1e-9 and abs(sb["varE"] / sa["varE"] - 1) < 1e-9
+    # back to "I"
+    b.set_residual_weights(None)
+    a.run(3); b.run(3)
+    assert rel(b.state()["sets"][0]["beta"], a.state()["sets"][0]["beta"]) < 1e-9
+    a.close(); b.close()
+
+
+def test_weighted_native_chain_matches_oracle_native_chain(gpu):
+    prob = make_problem(400, 150, 37)
+    w = _weights(400, 11)
+    kw = dict(v=0.05, pi=0.2, est_pi=True)
+    ch, S = _oracle(prob, w, 2, **kw)
+    g = gpu_sampler(prob, 2, **kw)
+    g.set_residual_weights(w)
+    g.set_rng(123, 2)
+    for it in range(8):
+        ch.iteration(seed=123, chain=2)
+        g.run(1)
+        assert _check(g.state(), ch.snapshot(), 2) < 1e-8
+    g.close()
+
+
+def test_weighted_sweep_level_plugin_call(gpu):
+    """M[mSet].funct(...) with E.str == "D": Julia keeps varE and the intercept (weighted, here by the oracle's scalar routines)."""
+    prob = make_problem(450, 180, 41)
+    w = _weights(450, 13)
+    kw = dict(v=0.05, pi=0.1, est_pi=True)
+    ch, S = _oracle(prob, w, 2, **kw)
+    g = gpu_sampler(prob, 2, **kw)
+    g.set_residual_weights(w)
+    beta, delta = np.zeros(180), np.ones(180, dtype=np.int64)
+    varBeta, piHat = np.full(1, kw["v"]), np.array([1 - kw["pi"], kw["pi"]])
+    ycorr, mu = prob["y"].copy(), 0.0
+    Lo = O.lib()
+    for it in range(1, 6):
+        log = ch.iteration(seed=3, chain=0)
+        c2 = C.c_double(log["chi2_e"]); zm = C.c_double(log["z_mu"])
+        varE = Lo.ngo_sample_varE_w(len(ycorr), ycorr.ctypes.data, w.ctypes.data, 4.0, ch.scale_e, 1, 0, 0, it, C.byref(c2))
+        mu = Lo.ngo_sample_intercept_w(len(ycorr), ycorr.ctypes.data, w.ctypes.data, mu, varE, 0.0, 0.0, 1, 0, 0, it, C.byref(zm))
+        g.set_replay([log])
+        g.sweep(0, ycorr, varE, beta, delta, varBeta, piHat)
+        assert rel(beta, S.beta) < TOL and rel(ycorr, ch.e) < TOL and rel(varBeta, S.varBeta) < TOL
+        assert np.array_equal(delta, S.delta) and rel(piHat, S.piHat) < TOL
+    g.close()
+
+
+def test_weight_argument_errors(gpu):
+    prob = make_problem(128, 40, 43)
+    g = gpu_sampler(prob, 0, v=0.01)
+    with pytest.raises(ngp.NgpError):
+        g.set_residual_weights(np.ones(127))
+    bad = np.ones(128); bad[5] = 0.0
+    with pytest.raises(ngp.NgpError):
+        g.set_residual_weights(bad)
+    g.close()

@@ -72,6 +72,44 @@ def test_c_oracle_equals_numpy_restatement(method):
             assert (delta == S.delta).all()
 
 
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_weighted_residual_oracle_equals_numpy_restatement(method):
+    """E.str == "D" (mme.jl:70-73, 133-136, 299-303; functions.jl:526-528): the C oracle fed with Mp = X .* w and the weighted mpm
+    against the numpy restatement that spells out which dot is weighted."""
+    n, p = 160, 60
+    prob = make_problem(n, p, 8)
+    w = np.random.default_rng(4).uniform(0.25, 4.0, n)
+    rng = np.random.default_rng(0)
+    lhs0, rhs0 = rng.uniform(0, 2, p), rng.normal(size=p)
+    X, mean, _ = O.center_codes(prob["codes"])
+    Mp_c, mpm_c = O.weighted_marker_arrays(X, w)
+    ro = np.array([0, 10, 25, p]) if method == 0 else None
+    S = O.MarkerSet(X=X, mpm=mpm_c, method=method, v=0.02, pi=0.2, est_pi=True, region_off=ro, lhs0=lhs0, rhs0=rhs0)
+    S.Mp = Mp_c
+    ch = O.OracleChain(prob["y"], [S], v_e=1.0, weights=w)
+    mpm, Mp = R.weighted_setup(X, w)
+    assert np.allclose(mpm, mpm_c, rtol=1e-13)
+    e, mu, beta, delta = prob["y"].copy(), 0.0, np.zeros(p), np.ones(p, dtype=np.int64)
+    varBeta, piHat = np.full(S.nvar, 0.02), np.array([0.8, 0.2])
+    logPi = np.log(piHat)
+    for _ in range(15):
+        log = ch.iteration(seed=9, chain=2)
+        s = log["sets"][0]
+        varE = R.sample_varE_w(4.0, 0.5, w, e, n, log["chi2_e"])
+        mu = R.sample_intercept_w(e, w, mu, varE, log["z_mu"])
+        if method == 0:
+            R.bayes_pr_w(X, Mp, mpm, lhs0, rhs0, [0, 10, 25, p], S.scale, S.df, beta, e, varE, varBeta, s["z"], s["chi2_b"])
+        else:
+            R.bayes_bc_w(method == 1, X, Mp, mpm, lhs0, rhs0, S.scale, S.df, True, beta, delta, e, varE, varBeta, piHat, logPi,
+                         s["u"], s["z"], s["chi2_b"], s["beta_pi"])
+        assert np.isclose(varE, ch.varE, rtol=1e-11) and np.isclose(mu, ch.mu, rtol=1e-10)
+        assert np.allclose(beta, S.beta, rtol=1e-8, atol=1e-12)
+        assert np.allclose(varBeta, S.varBeta, rtol=1e-9)
+        assert np.allclose(e, ch.e, rtol=1e-8, atol=1e-10)
+        if method:
+            assert (delta == S.delta).all()
+
+
 def test_bayesb_zero_variance_quirk():
     """functions.jl:186 sets varBeta_j = 0.0 on exclusion; next iteration p1 == pi and an included locus draws beta == 0."""
     prob = make_problem(120, 40, 3)
