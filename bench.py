@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--p", type=int, default=0)
     ap.add_argument("--model", default="BayesC")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--weighted", action="store_true",
+                    help="diagnostic: residual weights w ~ U(0.5, 2) (E.str == \"D\", mme.jl:70-73); the set is swept by the per-marker kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-cols", type=int, default=2000)
     ap.add_argument("--sharded", action="store_true",
@@ -240,6 +242,9 @@ def main():
         s.set_prior(0, method, df, scale, v, pi_in=pi, est_pi=(method == 2))
     s.set_phenotype(y)
     s.set_residual_prior(4.0, v_e * 0.5)
+    if args.weighted:
+        s.set_residual_weights(np.random.default_rng(seed).uniform(0.5, 2.0, n))
+        args.kernel, args.no_e2e, args.no_cpu = "literal", True, True
     s.set_intercept(True)
     s.set_rng(seed, 0 if sharded else rank)                            # independent chains: chain id = rank
 
@@ -325,7 +330,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "marker-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": workload_name(args.config, n, p, model), "kernel": ("blocked tuple sweep (interleaved copy, joint draw in the chain warp)" if args.kernel == "blocked" and kbreeds in (2, 4) else "joint (per locus)") if kbreeds else args.kernel, "chains": nchains,
+                "config": {"workload": workload_name(args.config, n, p, model) + (" [diagnostic: weighted residuals E.str == \"D\", per-marker kernel]" if args.weighted else ""), "kernel": ("blocked tuple sweep (interleaved copy, joint draw in the chain warp)" if args.kernel == "blocked" and kbreeds in (2, 4) else "joint (per locus)") if kbreeds else args.kernel, "chains": nchains,
                            "parallelism": (f"ONE chain row-sharded over {world} GPUs: per-marker fixed-point reduction pushed into every rank's "
                                            f"accumulators over NVLink peer memory (CUDA IPC), identical draw on every rank")
                                           if sharded else f"{world} independent chain(s), one per GPU, no data-path collective",

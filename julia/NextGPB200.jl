@@ -148,6 +148,9 @@ function runSampler_b200!(h, ycorr, nData, E, X, b, Z, u, varU, M, beta, varBeta
     end
     check(h, ccall((:ngp_set_phenotype, libngp), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64), h, ycorr, nData))
     check(h, ccall((:ngp_set_residual_prior, libngp), Cint, (Ptr{Cvoid}, Cdouble, Cdouble), h, E.df, E.scale))
+    if E.str == "D"      # mme.jl:70-73: iVarStr = inv.(D)
+        check(h, ccall((:ngp_set_residual_weights, libngp), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64), h, Vector{Float64}(E.iVarStr), nData))
+    end
     check(h, ccall((:ngp_set_intercept, libngp), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cdouble), h, isempty(X) ? 0 : 1, 0.0, 0.0))
     check(h, ccall((:ngp_set_rng, libngp), Cint, (Ptr{Cvoid}, UInt64, UInt32), h, seed, chain))
     these2Keep = collect((burnIn + outputFreq):outputFreq:chainLength)

@@ -1145,7 +1145,6 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
         for (int s = 0; s < h->n_sets; ++s) {
             SetHost& S = h->sets[s];
             if (!((set_mask >> s) & 1)) continue;
-            if (S.method == NGP_BAYESR) return fail(h, NGP_EUNSUPPORTED, "weighted residuals are not available for BayesR");
             if (S.w_ready) continue;
             if (!S.dw) { CU(dalloc(&S.dw, S.p_pad)); CU(dalloc(&S.wcs, S.p_pad)); }
             CU(zero(h, S.dw, 0, sizeof(double) * S.p_pad));

@@ -1466,6 +1466,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             const double lhs_c = __shfl_sync(0xffffffffu, lhs_v, cls);
                             const double vcls_c = __shfl_sync(0xffffffffu, vcls_v, cls);
                             const double bn = (varc_c != 0.0) ? rhs / lhs_c + sqrt(1.0 / lhs_c) * cQ : 0.0;      // functions.jl:266-268, :275
+                            if (wt) Stot -= (bn - bold) * __ldg(&S.wcs[j]);               // 1'We after e -= x_j (bn - bold)
                             if (lane == cls) acc_cls += 1.0;                            // nLoci[classSNP] += 1
                             if (lane == 0) {
                                 misc[40] = bn - bold; misc[41] = mean;

@@ -772,6 +772,7 @@ typedef struct {
     const double* v_class;    /* n_class (M.vClass)                               */
     double df, scale;
     int32_t set_id, pad_;
+    const double* Mp;         /* (x_j .* w) columns for E.str == "D" (mme.jl:303) or NULL -> X */
 } ngo_r_set;
 
 typedef struct {
@@ -817,7 +818,7 @@ int ngo_r_sweep(const ngo_r_set* S, ngo_r_state* T, double* e, double varE, ngo_
     for (int64_t j = 0; j < p; ++j) {
         const double* x = S->X + j * n;
         daxpy(n, T->beta[j], x, e);                                                              /* :249 */
-        const double rhs = ddot(n, x, e) * iVarE + (S->rhs0 ? S->rhs0[j] : 0.0);                  /* :250 */
+        const double rhs = ddot(n, S->Mp ? S->Mp + j * n : x, e) * iVarE + (S->rhs0 ? S->rhs0[j] : 0.0);   /* :250 Mp */
         double tot = 0.0;
         for (int v = 0; v < nc; ++v) {                                                           /* :253-257 */
             lhs[v] = varc[v] == 0.0 ? 0.0 : S->mpm[j] * iVarE + (S->lhs0 ? S->lhs0[j] : 0.0) + 1.0 / varc[v];

@@ -68,7 +68,7 @@ class _FxSet(C.Structure):
 class _RSet(C.Structure):
     _fields_ = [("n", C.c_int64), ("p", C.c_int64), ("X", C.c_void_p), ("mpm", C.c_void_p), ("lhs0", C.c_void_p),
                 ("rhs0", C.c_void_p), ("n_class", C.c_int32), ("est_pi", C.c_int32), ("v_class", C.c_void_p),
-                ("df", C.c_double), ("scale", C.c_double), ("set_id", C.c_int32), ("pad_", C.c_int32)]
+                ("df", C.c_double), ("scale", C.c_double), ("set_id", C.c_int32), ("pad_", C.c_int32), ("Mp", C.c_void_p)]
 
 
 class _RState(C.Structure):
@@ -418,11 +418,13 @@ class BayesROracle:
         self.delta = np.ones(self.p, dtype=np.int64)
         self.varBeta = np.array([float(v)])
         self.set_id = set_id
+        self.Mp = None                    # E.str == "D": X .* w (mme.jl:303), with mpm the weighted one
 
     def sweep(self, e: np.ndarray, varE: float, it: int, seed: int = 0, chain: int = 0, replay: dict | None = None) -> dict:
         L = lib()
         S = _RSet()
         S.n, S.p, S.X, S.mpm = self.n, self.p, _ptr(self.X), _ptr(self.mpm)
+        S.Mp = _ptr(self.Mp) if self.Mp is not None else None
         S.lhs0 = _ptr(self.lhs0) if self.lhs0 is not None else None
         S.rhs0 = _ptr(self.rhs0) if self.rhs0 is not None else None
         S.n_class, S.est_pi, S.v_class, S.df, S.scale, S.set_id = self.nc, int(self.est_pi), _ptr(self.v_class), self.df, self.scale, self.set_id

@@ -160,3 +160,60 @@ def test_weight_argument_errors(gpu):
     with pytest.raises(ngp.NgpError):
         g.set_residual_weights(bad)
     g.close()
+
+
+def test_runLMEM_with_D_vector(gpu, tmp_path):
+    """priorVCV[:e] = Random(D, v) with a vector D (d_ii = 1/w_ii, mme.jl:70-73) through the runLMEM mirror; the final state equals an
+    oracle chain with iVarStr = inv.(D) on the same native stream."""
+    import os
+    n, p = 200, 50
+    prob = make_problem(n, p, 71)
+    dvec = np.random.default_rng(2).uniform(0.5, 3.0, n)
+    geno = tmp_path / "geno.txt"
+    np.savetxt(geno, prob["codes"], fmt="%d", delimiter=" ")
+    out = str(tmp_path / "outMCMC")
+    VCV = {"M": ngp.BayesC(0.2, 0.01, estimatePi=True), "e": ngp.Random(dvec, prob["var_y"] / 2)}
+    s = ngp.runLMEM(f'y ~ 1 + SNP(M,"{geno}")', {"y": prob["y"]}, 40, 20, 10, outFolder=out, VCV=VCV, seed=5)
+    beta = np.loadtxt(os.path.join(out, "betaMOut"), delimiter="\t", skiprows=1)
+    ch, S = _oracle(prob, 1.0 / dvec, 2, v=0.01, pi=0.2, est_pi=True)
+    for _ in range(40):
+        ch.iteration(seed=5, chain=0)
+    assert rel(beta[-1], S.beta) < 1e-7
+    s.close()
+    with pytest.raises(ValueError):
+        ngp.runLMEM(f'y ~ 1 + SNP(M,"{geno}")', {"y": prob["y"]}, 4, 2, 1, outFolder=str(tmp_path / "o2"),
+                    VCV={"M": ngp.BayesPR(9999, 0.01), "e": ngp.Random(np.ones(n - 1), 1.0)})
+
+
+@pytest.mark.parametrize("est_pi", [False, True])
+def test_weighted_bayesr_native_chain_matches_oracle(gpu, est_pi):
+    """BayesR (functions.jl:238-289) takes Mp and the weighted mpm only (rhs at :250; no unweighted dot)."""
+    from nextgp.jl_b200 import _lib as L
+    n, p = 600, 120
+    prob = make_problem(n, p, 31)
+    w = _weights(n, 17)
+    v_class, pi = np.array([0.0, 0.0001, 0.001, 0.01]), np.array([0.8, 0.1, 0.07, 0.03])
+    X, mean, _ = O.center_codes(prob["codes"])
+    Mp, mpm = O.weighted_marker_arrays(X, w)
+    R = O.BayesROracle(X, mpm, pi, v_class, v=0.5, est_pi=est_pi)
+    R.Mp = Mp
+    ch = O.OracleChain(prob["y"], [], v_e=prob["var_y"] / 2, intercept=True, weights=w)
+    g = ngp.Sampler(0)
+    g.upload_genotypes(0, prob["codes"])
+    df, scale = O.marker_hyper(0.5)
+    g.set_prior(0, L.BAYESR, df, scale, 0.5, est_pi=est_pi, v_class=v_class, pi_class=pi)
+    g.set_phenotype(prob["y"])
+    g.set_residual_prior(*O.residual_hyper(prob["var_y"] / 2))
+    g.set_residual_weights(w)
+    g.set_intercept(True)
+    g.set_rng(17, 1)
+    for _ in range(6):
+        ch.iteration(seed=17, chain=1)
+        R.sweep(ch.e, ch.varE, it=ch.iter, seed=17, chain=1)
+    g.run(6)
+    st = g.state()
+    assert np.array_equal(st["sets"][0]["delta"], R.delta)
+    assert rel(st["sets"][0]["beta"], R.beta) < 1e-8 and rel(st["sets"][0]["varBeta"], R.varBeta) < 1e-8
+    assert rel(st["sets"][0]["piHat"], R.piHat) < 1e-9 and rel(st["e"], ch.e) < 1e-8
+    assert abs(st["varE"] / ch.varE - 1) < 1e-9
+    g.close()
