@@ -246,7 +246,7 @@ int ngp_read_bed_genotypes(const char* path, int64_t n, int64_t p, int count_a1,
 int ngp_set_phenotype(ngp_handle* h, const double* y, int64_t n);            /* ycorr = deepcopy(Y) */
 int ngp_set_residual_prior(ngp_handle* h, double df_e, double scale_e);      /* E[:df], E[:scale]  */
 /* E.str == "D" (mme.jl:70-73, 133-136, 299-303; functions.jl:526-528): w = E.iVarStr = inv.(D), n positive weights; NULL = "I".
- * Intercept + marker-set models (BayesPR/B/C/R) on one GPU; sampled by the per-marker kernel.                                */
+ * Fixed effects + marker-set models (BayesPR/B/C/R) on one GPU; sampled by the per-marker kernel.                            */
 int ngp_set_residual_weights(ngp_handle* h, const double* w, int64_t n);
 /* single-column fixed effect of ones (functions.jl:39-47); lhs0/rhs0 = X[xSet][:lhs/:rhs] */
 int ngp_set_intercept(ngp_handle* h, int enabled, double lhs0, double rhs0);

@@ -706,8 +706,8 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
         if dvec.shape != (len(Y),):
             raise ValueError("the \"D\" vector of priorVCV[:e] needs one entry per record")
         weights = 1.0 / dvec
-        if fixed or any(isinstance(k, tuple) for k in priorVCV):
-            raise NotImplementedError("weighted residuals: intercept + marker-set models only (further fixed effects and tuples stay in Julia)")
+        if any(isinstance(k, tuple) for k in priorVCV):
+            raise NotImplementedError("weighted residuals: not with a tuple of marker sets (stays in Julia)")
     elif not (isinstance(e_prior.str, str) and e_prior.str in ("I", "")) and not (e_prior.str is None or len(e_prior.str) == 0):
         raise ValueError("provide a valid prior var-cov structure (\"I\", \"D\" or leave it empty \"[]\") for \"e\" ")   # mme.jl:76
     df_e = 4.0

@@ -293,6 +293,9 @@ struct ngp_handle {
     // fixed effects besides the intercept
     FxDev fx{};
     double *fx_data = nullptr, *fx_xpx = nullptr, *fx_colsum = nullptr, *fx_b = nullptr, *fx_rp_z = nullptr;
+    double *fx_xpx_w = nullptr, *fx_colsum_w = nullptr;      // weighted residuals: X'WX and w'x_c (mme.jl:135), built at the first launch
+    std::vector<double> fx_host, w_host;                      // host copies ([n_cols][n] columns, weights) to build them from
+    bool fx_w_ready = false;
     int fx_replay_iters = 0;
     // row-sharded chain
     int shard_rank = 0, shard_world = 1;
@@ -426,6 +429,7 @@ int ngp_destroy(ngp_handle* h)
     cudaFree(h->rp_chi2_e); cudaFree(h->rp_z_mu);
     if (h->stage) cudaFreeHost(h->stage);
     cudaFree(h->fx_data); cudaFree(h->fx_xpx); cudaFree(h->fx_colsum); cudaFree(h->fx_b); cudaFree(h->fx_rp_z);
+    cudaFree(h->fx_xpx_w); cudaFree(h->fx_colsum_w);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -790,7 +794,8 @@ int ngp_set_residual_weights(ngp_handle* h, const double* w, int64_t n)
     CU(cudaSetDevice(h->device));
     for (auto& S : h->sets) S.w_ready = false;
     h->sets_dirty = true;
-    if (!w) { cudaFree(h->w); h->w = nullptr; return NGP_OK; }
+    h->fx_w_ready = false;
+    if (!w) { cudaFree(h->w); h->w = nullptr; h->w_host.clear(); return NGP_OK; }
     if (h->Tw == 0) return fail(h, NGP_EINVAL, "ngp_set_residual_weights: upload a marker set first (it fixes n)");
     if (n != h->n) return fail(h, NGP_EINVAL, "ngp_set_residual_weights: n = %lld but the genotypes have %lld rows", (long long)n, (long long)h->n);
     double sum = 0.0, lo = INFINITY, hi = 0.0;
@@ -802,6 +807,7 @@ int ngp_set_residual_weights(ngp_handle* h, const double* w, int64_t n)
     CU(zero(h, h->w, 0, sizeof(double) * (size_t)h->Tw * h->R));
     CU(cpy(h, h->w, w, sizeof(double) * n, cudaMemcpyHostToDevice));
     h->w_sum = sum; h->w_min = lo; h->w_max = hi;
+    h->w_host.assign(w, w + n);
     return NGP_OK;
 }
 
@@ -820,7 +826,9 @@ int ngp_set_fixed_effects(ngp_handle* h, int n_sets, const ngp_fixed_set* sets)
     if (n_sets < 0 || n_sets > kMaxFxSets || (n_sets > 0 && !sets)) return fail(h, NGP_EINVAL, "ngp_set_fixed_effects: 0..%d sets", kMaxFxSets);
     CU(cudaSetDevice(h->device));
     cudaFree(h->fx_data); cudaFree(h->fx_xpx); cudaFree(h->fx_colsum); cudaFree(h->fx_b); cudaFree(h->fx_rp_z);
-    h->fx_data = h->fx_xpx = h->fx_colsum = h->fx_b = h->fx_rp_z = nullptr;
+    cudaFree(h->fx_xpx_w); cudaFree(h->fx_colsum_w);
+    h->fx_data = h->fx_xpx = h->fx_colsum = h->fx_b = h->fx_rp_z = h->fx_xpx_w = h->fx_colsum_w = nullptr;
+    h->fx_host.clear(); h->fx_w_ready = false;
     h->fx = FxDev{};
     h->fx_replay_iters = 0;
     if (n_sets == 0) return NGP_OK;
@@ -844,6 +852,7 @@ int ngp_set_fixed_effects(ngp_handle* h, int n_sets, const ngp_fixed_set* sets)
             double sum = 0.0;
             for (int64_t i = 0; i < n; ++i) { dst[i] = src[i]; sum += src[i]; }
             cs[(size_t)(F.first[s] + c)] = sum;
+            h->fx_host.insert(h->fx_host.end(), src, src + n);
         }
         for (int a = 0; a < nc; ++a)                                                  // X[xSet].xpx = X'X
             for (int b = a; b < nc; ++b) {
@@ -1040,6 +1049,7 @@ static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int 
     P.debug = h->cfg_debug;
     P.fx = h->fx; P.fx.rp_z = h->fx_rp_z;
     P.w = h->w; P.w_sum = h->w_sum; P.w_min = h->w_min; P.w_max = h->w_max;
+    if (h->w && h->fx.n_cols && h->fx_w_ready) { P.fx.xpx = h->fx_xpx_w; P.fx.colsum_w = h->fx_colsum_w; }
     P.n_ranks = h->shard_world; P.rank = h->shard_rank; P.n_total = h->shard_world > 1 ? h->n_total : h->n;
     P.cta_off = 0; P.T_all = h->Tw + 1; P.Tw_all = h->Tw; P.bar_base = 0;
     P.peer[0] = h->sync;
@@ -1140,8 +1150,33 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
         if (sc.iter - h->replay_base + n_iter > h->replay_iters) return fail(h, NGP_EINVAL, "replay log exhausted (%d iterations)", h->replay_iters);
     }
     if (h->w) {
-        if (sharded || h->fx.n_cols || h->joint.active)
-            return fail(h, NGP_EUNSUPPORTED, "weighted residuals: available for intercept + marker-set models on one GPU (no tuple, no further fixed effects, no row sharding)");
+        if (sharded || h->joint.active)
+            return fail(h, NGP_EUNSUPPORTED, "weighted residuals: available for fixed effects + marker-set models on one GPU (no tuple, no row sharding)");
+        if (h->fx.n_cols && !h->fx_w_ready) {              // X[xSet].xpx = X'(w .* X), and w'x_c for the running 1'We (mme.jl:135)
+            const FxDev& F = h->fx;
+            const int64_t n = h->n;
+            std::vector<double> xw((size_t)kMaxFxCols * kMaxFxCols, 0.0), cw((size_t)F.n_cols, 0.0);
+            for (int s = 0; s < F.n_sets; ++s) {
+                const int c0 = F.first[s], nc = F.first[s + 1] - c0;
+                for (int a = 0; a < nc; ++a) {
+                    const double* xa = h->fx_host.data() + (size_t)(c0 + a) * n;
+                    double sw = 0.0;
+                    for (int64_t i = 0; i < n; ++i) sw += h->w_host[i] * xa[i];
+                    cw[(size_t)(c0 + a)] = sw;
+                    for (int b = a; b < nc; ++b) {
+                        const double* xb = h->fx_host.data() + (size_t)(c0 + b) * n;
+                        double d = 0.0;
+                        for (int64_t i = 0; i < n; ++i) d += xa[i] * (h->w_host[i] * xb[i]);
+                        xw[(size_t)F.xoff[s] + a * nc + b] = d; xw[(size_t)F.xoff[s] + b * nc + a] = d;
+                    }
+                }
+            }
+            if (!h->fx_xpx_w) { CU(dalloc(&h->fx_xpx_w, xw.size())); CU(dalloc(&h->fx_colsum_w, (size_t)kMaxFxCols)); }
+            CU(cpy(h, h->fx_xpx_w, xw.data(), sizeof(double) * xw.size(), cudaMemcpyHostToDevice));
+            CU(cpy(h, h->fx_colsum_w, cw.data(), sizeof(double) * cw.size(), cudaMemcpyHostToDevice));
+            CU(cudaStreamSynchronize(h->stream));
+            h->fx_w_ready = true;
+        }
         for (int s = 0; s < h->n_sets; ++s) {
             SetHost& S = h->sets[s];
             if (!((set_mask >> s) & 1)) continue;

@@ -106,6 +106,7 @@ struct FxDev {
     const double* data;                  // [n_cols][Tw*R] column-major, pad rows zero
     const double* xpx;                   // X'X per set (X[xSet].xpx)
     const double* colsum;                // [n_cols] 1'x_c: keeps 1'e current
+    const double* colsum_w;              // [n_cols] w'x_c (weighted residuals: keeps 1'We current; xpx is then X'WX, mme.jl:135) or null
     double* b;                           // [n_cols] the effects
     double lhs0[kMaxFxSets], rhs0[kMaxFxSets];   // single-column sets: X[xSet].lhs / .rhs
     const double* rp_z;                  // replay [iter][n_cols]
@@ -125,6 +126,7 @@ struct SyncArea {
     long long prof[kMaxCtas * kProf];           // per-CTA cycle counters of the last launch: see ngp_get_profile
     long long trace[2 * 2048];                  // instrumented kernel: (start clock, cycles waited for r_base) of the chain warp's first 2048 steps
     double part_fx[kMaxCtas * kMaxFxCols];      // per-CTA partial dots x_c'e of the fixed-effect columns
+    double part_u[kMaxCtas];                    // weighted residuals: per-CTA partial of the plain 1'e (phase 0)
 };
 constexpr size_t kSyncHeadBytes = 16 * 8 + kMaxCtas * 2 * 8 + 32 * 4;
 

@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
             double su = 0.0, dm = 0.0;
             if (!is_chain) for (int r = tid; r < R; r += kThreads) { const double x = e_s[r], wv = __ldg(&P.w[row0 + r]); ee = fma(wv * x, x, ee); se = fma(wv, x, se); su += x; }
             block_sum2(su, dm, misc);
-            if (tid == 0) sy->part_fx[t * kMaxFxCols] = su;
+            if (tid == 0) sy->part_u[t] = su;
         } else if (!is_chain) for (int r = tid; r < R; r += kThreads) { const double x = e_s[r]; ee = fma(x, x, ee); se += x; }
         block_sum2(ee, se, misc);
         if (tid == 0) {
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
             gs.wait_warp();
             double a = 0.0, b = 0.0, bu = 0.0;
             const int nparts = sharded ? P.T_all : Tw;     // same order on every rank: identical sums, identical draws
-            for (int c = lane; c < nparts; c += 32) { a += __ldcg(&sy->part[2 * c]); b += __ldcg(&sy->part[2 * c + 1]); if (wt) bu += __ldcg(&sy->part_fx[c * kMaxFxCols]); }
+            for (int c = lane; c < nparts; c += 32) { a += __ldcg(&sy->part[2 * c]); b += __ldcg(&sy->part[2 * c + 1]); if (wt) bu += __ldcg(&sy->part_u[c]); }
             a = warp_sum(a); b = warp_sum(b);
             if (wt) bu = warp_sum(bu);
             if (lane == 0) {
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         const double dmu = misc[33];
         double Stot = misc[34];                       // 1'e after the intercept update; invariant under marker updates
                                                       // (weighted residuals: 1'We, which every changed effect moves by wcs_j)
-        const double Stot_u = wt ? misc[37] : 0.0;    // weighted residuals: the plain 1'e (invariant)
+        double Stot_u = wt ? misc[37] : 0.0;          // weighted residuals: the plain 1'e (invariant under marker updates)
         const int sh = (int)misc[35];
         mu = misc[36];
         const double fx_scale = ldexp(1.0, sh), fx_inv = ldexp(1.0, -sh);
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     double a0 = 0.0, a1 = 0.0;
                     if (!is_chain)
                         for (int r = tid; r < nrow; r += kThreads) {
-                            const double ev = e_s[r];
+                            const double ev = wt ? e_s[r] * __ldg(&P.w[row0 + r]) : e_s[r];       // Xp = (X .* w)' (mme.jl:136)
                             a0 = fma(X.data[(int64_t)c * ldx + row0 + r], ev, a0);
                             if (c + 1 < c1) a1 = fma(X.data[(int64_t)(c + 1) * ldx + row0 + r], ev, a1);
                         }
@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         Stream st{P.key0, P.key1, P.chain, iter, 0u};
                         const int nc = c1 - c0;
                         const double* xpx = X.xpx + X.xoff[xs];
-                        double dS = 0.0;
+                        double dS = 0.0, dSw = 0.0;
                         for (int i = 0; i < nc; ++i) {
                             const double z = P.replay ? X.rp_z[rp_row * X.n_cols + c0 + i] : stream_normal(st, P_Z_MU, (uint32_t)(1 + c0 + i));
                             const double bold_i = fx_s[c0 + i];
@@ -572,10 +572,12 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                             }
                             fx_s[c0 + i] = bn;
                             dS = fma(X.colsum[c0 + i], bn - bold_i, dS);
+                            if (wt) dSw = fma(X.colsum_w[c0 + i], bn - bold_i, dSw);
                             if (is_chain) X.b[c0 + i] = bn;
                         }
                         // e was restored to e + X b_old before the dots: 1'e of the final e = 1'e_before - sum_c colsum_c (b_new - b_old)
-                        misc[34] -= dS;
+                        misc[34] -= wt ? dSw : dS;
+                        if (wt) misc[37] -= dS;
                     }
                 }
                 __syncthreads();
@@ -589,6 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                 __syncthreads();
             }
             Stot = misc[34];
+            if (wt) Stot_u = misc[37];
         }
         if (tid == 0) NGP_TICK(8);
 

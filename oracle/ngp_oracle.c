@@ -723,6 +723,7 @@ typedef struct {
     const double* data;       /* n x n_cols column-major                          */
     const double* xpx;        /* n_cols x n_cols                                  */
     double lhs0, rhs0;        /* single-column sets only (X[xSet].lhs / .rhs)     */
+    const double* Xp;         /* E.str == "D": (X .* w) columns (mme.jl:136), xpx then X'(w .* X) (mme.jl:135); NULL -> data */
 } ngo_fx_set;
 
 void ngo_sample_fixed(const ngo_fx_set* F, double* b, double* e, double varE,
@@ -735,12 +736,12 @@ void ngo_sample_fixed(const ngo_fx_set* F, double* b, double* e, double varE,
     if (!replay) for (int k = 0; k < c; ++k) z[k] = stream_normal(&s, NGO_P_Z_MU, (uint32_t)(F->col0 + k), 0, 0);
     for (int k = 0; k < c; ++k) daxpy(n, b[k], F->data + (int64_t)k * n, e);                       /* :42 / :49 */
     if (c == 1) {
-        const double rhs = ddot(n, F->data, e) * iVarE + F->rhs0;                                 /* :43 */
+        const double rhs = ddot(n, F->Xp ? F->Xp : F->data, e) * iVarE + F->rhs0;                 /* :43 Xp */
         const double lhs = F->xpx[0] * iVarE + F->lhs0;                                           /* :44 */
         b[0] = rhs / lhs + sqrt(1.0 / lhs) * z[0];                                               /* :45-46 */
     } else {
         double Yi[64], bVec[64];
-        for (int k = 0; k < c; ++k) { Yi[k] = ddot(n, F->data + (int64_t)k * n, e) * iVarE; bVec[k] = b[k]; }   /* :25 */
+        for (int k = 0; k < c; ++k) { Yi[k] = ddot(n, (F->Xp ? F->Xp : F->data) + (int64_t)k * n, e) * iVarE; bVec[k] = b[k]; }   /* :25 Xp */
         for (int i = 0; i < c; ++i) {                                                            /* :27-34 */
             bVec[i] = 0.0;
             double dt = 0.0;

@@ -62,7 +62,7 @@ class _MbSet(C.Structure):
 
 class _FxSet(C.Structure):
     _fields_ = [("n", C.c_int64), ("n_cols", C.c_int32), ("col0", C.c_int32), ("data", C.c_void_p), ("xpx", C.c_void_p),
-                ("lhs0", C.c_double), ("rhs0", C.c_double)]
+                ("lhs0", C.c_double), ("rhs0", C.c_double), ("Xp", C.c_void_p)]
 
 
 class _RSet(C.Structure):
@@ -379,18 +379,24 @@ class FixedSet:
     """One X[xSet] of getMME! (covariates / factor levels): functions.jl:22-54.  col0 = index of its first column among all fixed
     columns of the model (0 is the intercept), which addresses the variate stream."""
 
-    def __init__(self, data: np.ndarray, col0: int, lhs0: float = 0.0, rhs0: float = 0.0):
+    def __init__(self, data: np.ndarray, col0: int, lhs0: float = 0.0, rhs0: float = 0.0, weights: np.ndarray | None = None):
         self.data = np.asfortranarray(data, dtype=np.float64)
         if self.data.ndim == 1:
             self.data = np.asfortranarray(self.data[:, None])
         self.n, self.c = self.data.shape
-        self.xpx = np.ascontiguousarray(self.data.T @ self.data)
+        self.Xp = None
+        if weights is not None:           # E.str == "D": xpx = X'(w .* X), Xp = (X .* w)' (mme.jl:133-136)
+            self.Xp = np.asfortranarray(self.data * np.asarray(weights, dtype=np.float64)[:, None])
+            self.xpx = np.ascontiguousarray(self.data.T @ self.Xp)
+        else:
+            self.xpx = np.ascontiguousarray(self.data.T @ self.data)
         self.col0, self.lhs0, self.rhs0 = col0, lhs0, rhs0
         self.b = np.zeros(self.c)
 
     def sample(self, e: np.ndarray, varE: float, it: int, seed: int = 0, chain: int = 0, replay_z=None) -> np.ndarray:
         F = _FxSet()
         F.n, F.n_cols, F.col0, F.data, F.xpx, F.lhs0, F.rhs0 = self.n, self.c, self.col0, _ptr(self.data), _ptr(self.xpx), self.lhs0, self.rhs0
+        F.Xp = _ptr(self.Xp)
         z = np.zeros(self.c) if replay_z is None else np.ascontiguousarray(replay_z, dtype=np.float64).copy()
         lib().ngo_sample_fixed(C.byref(F), _ptr(self.b), _ptr(e), varE, int(replay_z is not None), seed, chain, it, _ptr(z))
         return z

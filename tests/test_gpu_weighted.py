@@ -217,3 +217,47 @@ def test_weighted_bayesr_native_chain_matches_oracle(gpu, est_pi):
     assert rel(st["sets"][0]["piHat"], R.piHat) < 1e-9 and rel(st["e"], ch.e) < 1e-8
     assert abs(st["varE"] / ch.varE - 1) < 1e-9
     g.close()
+
+
+@pytest.mark.parametrize("method,kw", [(2, dict(v=0.05, pi=0.1, est_pi=True)), (0, dict(v=0.01)), (1, dict(v=0.05, pi=0.3, est_pi=True))])
+def test_weighted_fixed_effects_native_chain_matches_oracle(gpu, method, kw):
+    """Covariates and factor levels besides the intercept under E.str == "D": xpx = X'(w .* X), Xp = (X .* w)' (mme.jl:133-136) in
+    sampleX! / sampleb! (functions.jl:22-54); a single column with prior information and two multi-column sets."""
+    n, p = 777, 130
+    prob = make_problem(n, p, 41)
+    w = _weights(n, 19)
+    rng = np.random.default_rng(1)
+    age = rng.normal(size=n) * 2 + 5
+    herd = np.eye(3)[rng.integers(0, 3, n)][:, 1:]
+    cov2 = np.column_stack([rng.uniform(size=n), rng.normal(size=n), (rng.uniform(size=n) > 0.5).astype(float)])
+    specs = [(age, 0.7, -0.3), (herd, 0.0, 0.0), (cov2, 0.0, 0.0)]
+    y = prob["y"] + 0.8 * age
+    fixed_o, col = [], 1
+    for data, l0, r0 in specs:
+        F = O.FixedSet(data, col0=col, lhs0=l0, rhs0=r0, weights=w)
+        col += F.c
+        fixed_o.append(F)
+    X, mean, _ = O.center_codes(prob["codes"])
+    Mp, mpm = O.weighted_marker_arrays(X, w)
+    S = O.MarkerSet(X=X, mpm=mpm, method=method, **kw)
+    S.Mp = Mp
+    ch = O.OracleChain(y, [S], v_e=prob["var_y"] / 2, intercept=True, fixed=fixed_o, weights=w)
+    g = ngp.Sampler(0)
+    g.upload_genotypes(0, prob["codes"])
+    df, scale = O.marker_hyper(kw["v"])
+    g.set_prior(0, method, df, scale, kw["v"], pi_in=kw.get("pi", 0.0), est_pi=kw.get("est_pi", False))
+    g.set_fixed_effects(specs)
+    g.set_phenotype(y)
+    g.set_residual_prior(*O.residual_hyper(prob["var_y"] / 2))
+    g.set_residual_weights(w)
+    g.set_intercept(True)
+    g.set_rng(12, 2)
+    for _ in range(6):
+        ch.iteration(seed=12, chain=2)
+    g.run(4); g.run(2)
+    st = g.state()
+    assert rel(g.fixed_effects(), np.concatenate([F.b for F in fixed_o])) < 1e-8 and abs(st["mu"] - ch.mu) < 1e-8 * max(1.0, abs(ch.mu))
+    if method:
+        assert np.array_equal(st["sets"][0]["delta"], S.delta)
+    assert rel(st["sets"][0]["beta"], S.beta) < 1e-8 and rel(st["e"], ch.e) < 1e-8 and abs(st["varE"] / ch.varE - 1) < 1e-9
+    g.close()
