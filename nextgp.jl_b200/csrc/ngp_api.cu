@@ -518,10 +518,12 @@ static int choose_geometry(ngp_handle* h, int64_t n)
     // residual update reads it there.  refetch: a tile stays only until its dots are formed (NT = 8 / 4 / 2 / 1 stages, consumed by as many
     // dot warps) and the columns of changed effects are re-read from L2 / HBM: the look-ahead is no longer bounded by shared memory.
     // Small panels use resident; refetch is chosen when resident would leave fewer than kMinResidentD blocks of look-ahead.
-    const int want_D = h->cfg_lookahead ? h->cfg_lookahead : (B == 64 ? 6 : B == 32 ? 13 : 20);
+    // defaults from the sweeps in profiles/r1/tune_*_r1j.jsonl (C2: D 14 / near 4 = 0.971 ms against 0.994 at D 13 / near 3; near 5 falls off a
+    // cliff at 1.13 ms; C1 with blocks of 64: near 3 = 0.582 ms against 0.593 at near 1 in the sweep but no gain in bench.py, left at the minimum)
+    const int want_D = h->cfg_lookahead ? h->cfg_lookahead : (B == 64 ? 6 : B == 32 ? 14 : 20);
     constexpr int kMinResidentD = 10;
     auto search = [&](int refetch) -> bool {
-        int DN = std::max(dn_min, h->cfg_near ? h->cfg_near : 0);
+        int DN = std::max(dn_min, h->cfg_near ? h->cfg_near : (B == 32 ? 4 : 0));
         int D = std::min(refetch ? std::min(want_D, 13) : want_D, kNzRing - 2);
         if (refetch && h->cfg_lookahead) D = std::min(h->cfg_lookahead, kNzRing - 2);
         auto legal_nt = [](int v) { return v >= 8 ? 8 : v >= 4 ? 4 : v >= 2 ? 2 : 1; };

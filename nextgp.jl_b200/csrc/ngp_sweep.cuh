@@ -977,6 +977,17 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                     const NzList& pl = cnz[(g0 - (unsigned)kk) & (kNzRing - 1)];
                                     // four entries at a time: the list reads and the Gram loads of a group are issued together (a dense
                                     // list — BayesPR, tuple — has B entries; one entry at a time costs a full LDS -> LDS -> I2F -> DFMA chain each)
+                                    // (the tuple instantiation keeps one entry at a time: its chain warp is register-bound by the joint draw
+                                    //  and the grouped form cost C4 45.6 -> 57.4 ms/sweep)
+                                    if constexpr (TUP) {
+                                        for (int e = 0; e < np; ++e) {
+                                            const int a = pl.idx[e];
+                                            const double dbf = pl.db[e], csf = pl.aux[e];
+#pragma unroll
+                                            for (int i = 0; i < NS; ++i)
+                                                rr[i] = fma(-((double)gram[i][(kb[i] + kk) * B * B + a * B + qb[i]] - csf * cs[i] * inv_n), dbf, rr[i]);
+                                        }
+                                    } else
                                     for (int e0 = 0; e0 < np; e0 += 4) {
                                         int a4[4]; double db4[4], cs4[4]; int g4_[4][NS];
 #pragma unroll
