@@ -38,6 +38,16 @@ SEED0 = 20261018
 METRIC = "marker-updates/sec"
 
 
+
+def host_threads() -> int:
+    """All the host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently make the
+    CPU arm single-threaded at N > 1 (omp_get_max_threads() == 1): count the cores from the affinity mask instead."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def workload_name(cfg, n, p, model):
     if model.startswith("MultiBreed"):
         return f"{cfg}: {n} individuals x {p} SNPs, {model[10:]}-breed tuple BayesPR (joint effects per locus) + intercept, int8 genotypes in HBM"
@@ -99,7 +109,7 @@ def cpu_baseline(n, p, model, seed, budget_s=15.0, max_cols=2000):
     v_e, v, pi = ngp.synth.priors(prob, model)
     method = 0 if model in ("BayesRR", "BayesPR") else (1 if model == "BayesB" else 2)
     results = {}
-    for threads in sorted({1, O.max_threads()}):
+    for threads in sorted({1, host_threads()}):
         O.set_threads(threads)
         S = O.MarkerSet(X=X, mpm=mpm, method=method, v=v, pi=pi, est_pi=(method == 2))
         ch = O.OracleChain(prob["y"], [S], v_e=v_e)
@@ -134,10 +144,19 @@ def run_reference(args, rank):
     X, mean, mpm = O.center_codes(codes)
     v_e, v, pi = ngp.synth.priors(prob, model)
     method = 0 if model in ("BayesRR", "BayesPR") else (1 if model == "BayesB" else 2)
-    threads = O.max_threads()
-    O.set_threads(threads)
     S = O.MarkerSet(X=X, mpm=mpm, method=method, v=v, pi=pi, est_pi=(method == 2))
     ch = O.OracleChain(prob["y"], [S], v_e=v_e)
+    # the thread count that serves the CPU arm best: all host cores for long columns, one for short ones (the OpenMP fork/join of a
+    # level-1 call costs more than a 1000-row dot) — calibrated on two untimed iterations each
+    cal = {}
+    for threads in sorted({1, host_threads()}):
+        O.set_threads(threads)
+        ch.iteration(seed=seed, chain=0)
+        tc = time.perf_counter()
+        ch.iteration(seed=seed, chain=0)
+        cal[threads] = time.perf_counter() - tc
+    threads = min(cal, key=cal.get)
+    O.set_threads(threads)
     for _ in range(args.warmup):
         ch.iteration(seed=seed, chain=0)
     t0 = time.perf_counter()
@@ -150,7 +169,7 @@ def run_reference(args, rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.config, n, p, model), "sample": f"first {pc} of {p} markers, all rows; ms_per_step extrapolated linearly in p"},
             "cpu_baseline": {"value": val, "unit": "marker-updates/s", "cores": threads, "kind": "port",
-                             "sample": f"first {pc} of {p} markers x {n} rows, dense fp64, OpenMP over rows in dot/axpy; CPU restatement of NextGP.jl (no Julia on the box)"},
+                             "sample": f"first {pc} of {p} markers x {n} rows, dense fp64, OpenMP over rows in dot/axpy, {threads} of {host_threads()} host threads (the faster of 1 / all, calibrated); CPU restatement of NextGP.jl (no Julia on the box)"},
             "e2e": {"value": val, "unit": "marker-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
