@@ -92,6 +92,17 @@ function set_prior!(h, set::Integer, Mset, v0::Float64)
     end
 end
 
+"""E.str == "D" (mme.jl:70-73): hand E.iVarStr = inv.(D) to the device once, after the uploads; also needed for the sweep-level
+drop-in, whose Mp / mpm are the weighted ones of mme.jl:299-303.  `nothing` returns to "I"."""
+function set_residual_weights!(h, iVarStr)
+    if iVarStr === nothing || isempty(iVarStr)
+        check(h, ccall((:ngp_set_residual_weights, libngp), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64), h, C_NULL, 0))
+    else
+        w = Vector{Float64}(iVarStr)
+        check(h, ccall((:ngp_set_residual_weights, libngp), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64), h, w, length(w)))
+    end
+end
+
 """Sweep-level drop-in: returns a function with the signature of M[mSet].funct (samplers.jl:52)."""
 function b200_funct(h, set::Integer)
     return function (mSet, M, beta, delta, ycorr, varE, varBeta)
