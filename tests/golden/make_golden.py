@@ -2,7 +2,7 @@
 seed; the fixture stores the variate log and the per-iteration states).  The reference has no golden
 vectors of its own (test/runtests.jl is empty) and cannot run here (no Julia), so these pin the ORACLE
 against regressions and give the GPU tests a committed target that does not need the oracle .so.
-Run:  python tests/golden/make_golden.py"""
+Run:  python tests/golden/make_golden.py [extra | weighted]"""
 import os
 import sys
 
@@ -70,9 +70,51 @@ def main_extra():
     print("tuple2 varE", ch.varE)
 
 
+WEIGHTED = {
+    "bayesc_weighted": dict(n=290, p=140, seed=107, method=2, v=0.05, pi=0.1, est_pi=True, iters=20),
+    "bayesb_weighted": dict(n=270, p=110, seed=108, method=1, v=0.05, pi=0.2, est_pi=True, iters=20),
+}
+
+
+def weights_of(c):
+    """Residual weights w = E.iVarStr of the weighted cases (regenerated from the seed, like the genotypes)."""
+    return np.random.default_rng(c["seed"]).uniform(0.25, 4.0, c["n"])
+
+
+def weighted_chain(c):
+    from oracle import oracle as O
+    prob = make_problem(c["n"], c["p"], c["seed"])
+    w = weights_of(c)
+    X, mean, _ = O.center_codes(prob["codes"])
+    Mp, mpm = O.weighted_marker_arrays(X, w)                       # mme.jl:299-303
+    S = O.MarkerSet(X=X, mpm=mpm, method=c["method"], v=c["v"], pi=c["pi"], est_pi=c["est_pi"])
+    S.Mp = Mp
+    return prob, w, O.OracleChain(prob["y"], [S], v_e=prob["var_y"] / 2, weights=w), S
+
+
+def main_weighted():
+    """E.str == "D" (SURVEY §8 f3): oracle chains with residual weights."""
+    for name, c in WEIGHTED.items():
+        prob, w, ch, S = weighted_chain(c)
+        out = {k: [] for k in ("chi2_e", "z_mu", "u", "z", "chi2_b", "beta_pi", "beta", "delta", "varBeta", "varE", "mu", "pi")}
+        for _ in range(c["iters"]):
+            log = ch.iteration(seed=c["seed"], chain=3)
+            s = log["sets"][0]
+            for k in ("chi2_e", "z_mu"):
+                out[k].append(log[k])
+            for k in ("u", "z", "chi2_b", "beta_pi"):
+                out[k].append(np.array(s[k]))
+            out["beta"].append(S.beta.copy()); out["delta"].append(S.delta.copy()); out["varBeta"].append(S.varBeta.copy())
+            out["varE"].append(ch.varE); out["mu"].append(ch.mu); out["pi"].append(S.piHat.copy())
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), e_final=ch.e, **{k: np.array(v) for k, v in out.items()})
+        print(name, "varE", ch.varE, "nIn", int(S.delta.sum()))
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "extra":
         return main_extra()
+    if len(sys.argv) > 1 and sys.argv[1] == "weighted":
+        return main_weighted()
     for name, c in CASES.items():
         prob = make_problem(c["n"], c["p"], c["seed"])
         ro = np.array(c["region_off"], dtype=np.int64) if "region_off" in c else None

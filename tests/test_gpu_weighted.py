@@ -261,3 +261,29 @@ def test_weighted_fixed_effects_native_chain_matches_oracle(gpu, method, kw):
         assert np.array_equal(st["sets"][0]["delta"], S.delta)
     assert rel(st["sets"][0]["beta"], S.beta) < 1e-8 and rel(st["e"], ch.e) < 1e-8 and abs(st["varE"] / ch.varE - 1) < 1e-9
     g.close()
+
+
+@pytest.mark.parametrize("name", ["bayesc_weighted", "bayesb_weighted"])
+def test_weighted_replay_against_committed_golden(gpu, name):
+    """Same comparison against tests/golden (does not execute the oracle)."""
+    import importlib.util
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(gold, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    c = mg.WEIGHTED[name]
+    gd = np.load(os.path.join(gold, name + ".npz"))
+    prob = make_problem(c["n"], c["p"], c["seed"])
+    g = gpu_sampler(prob, c["method"], c["v"], pi=c["pi"], est_pi=c["est_pi"])
+    g.set_residual_weights(mg.weights_of(c))
+    logs = [{"chi2_e": gd["chi2_e"][i], "z_mu": gd["z_mu"][i],
+             "sets": [{"u": gd["u"][i], "z": gd["z"][i], "chi2_b": gd["chi2_b"][i], "beta_pi": gd["beta_pi"][i]}]}
+            for i in range(c["iters"])]
+    g.set_replay(logs)
+    for i in range(c["iters"]):
+        g.run(1)
+        st = g.state()
+        assert rel(st["sets"][0]["beta"], gd["beta"][i]) < TOL and abs(st["varE"] / gd["varE"][i] - 1) < TOL
+        assert rel(st["sets"][0]["varBeta"], gd["varBeta"][i]) < TOL and np.array_equal(st["sets"][0]["delta"], gd["delta"][i])
+    assert rel(g.state()["e"], gd["e_final"]) < TOL
+    g.close()

@@ -148,6 +148,21 @@ def test_oracle_against_golden(name):
     assert np.allclose(ch.e, g["e_final"], rtol=1e-8, atol=1e-10)
 
 
+@pytest.mark.parametrize("name", ["bayesc_weighted", "bayesb_weighted"])
+def test_weighted_oracle_against_golden(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    c = mg.WEIGHTED[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    prob, w, ch, S = mg.weighted_chain(c)
+    for it in range(c["iters"]):
+        ch.iteration(seed=c["seed"], chain=3)
+        assert np.allclose(S.beta, g["beta"][it], rtol=1e-9, atol=1e-13) and np.array_equal(S.delta, g["delta"][it])
+        assert np.isclose(ch.varE, g["varE"][it], rtol=1e-10)
+    assert np.allclose(ch.e, g["e_final"], rtol=1e-8, atol=1e-10)
+
+
 def test_multibreed_oracle_matches_dense_algebra():
     """functions.jl:140-154 with k=2: the per-locus draw equals mean + chol(C) z with C = (M'M/varE + inv(Sigma))^-1."""
     rng = np.random.default_rng(4)
