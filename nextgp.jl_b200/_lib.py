@@ -18,11 +18,12 @@ BAYESPR, BAYESB, BAYESC, BAYESR = 0, 1, 2, 3
 GENO_I8, GENO_F64, GENO_PACKED2 = 0, 1, 2
 STORE_I8, STORE_2BIT = 0, 1
 KERNEL_BLOCKED, KERNEL_LITERAL = 0, 1
-CFG_KERNEL, CFG_BLOCK, CFG_MIN_ROWS, CFG_MAX_CTAS, CFG_LOOKAHEAD, CFG_TILE_STAGES, CFG_NEAR, CFG_PROFILE, CFG_DEBUG, CFG_VERSIONS, CFG_REFETCH = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+CFG_KERNEL, CFG_BLOCK, CFG_MIN_ROWS, CFG_MAX_CTAS, CFG_LOOKAHEAD, CFG_TILE_STAGES, CFG_NEAR, CFG_PROFILE, CFG_DEBUG, CFG_VERSIONS, CFG_REFETCH, CFG_OPT = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
 OK, EINVAL, ECUDA, EDATA, ERANGE, ENOMEM, EUNSUPPORTED, ENUMERIC = 0, -1, -2, -3, -4, -5, -6, -7
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+BUILD_DIR = os.path.join(_HERE, "build")          # object files (git-ignored); the linked library is nextgp.jl_b200/libngp.so
+STAMP = SO_PATH + ".srchash"                      # hash of the sources + flags the library was linked from
 
 
 class NgpError(RuntimeError):
@@ -71,27 +72,73 @@ class Timing(C.Structure):
                 ("lookahead", C.c_int32), ("near_depth", C.c_int32), ("tile_stages", C.c_int32), ("record_stages", C.c_int32)]
 
 
+def translation_units() -> list[tuple[str, str, list[str]]]:
+    """(object name, source file, extra flags): one instantiation of the sweep kernels per unit (csrc/ngp_kernels.h)."""
+    tus = [("ngp_api", "ngp_api.cu", []), ("ngp_ingest", "ngp_ingest.cpp", [])]
+    for B in (16, 32, 64):
+        for v in range(5):
+            tus.append((f"ngp_k_gibbs_{B}_{v}", "ngp_k_gibbs.cu", [f"-DNGP_KB={B}", f"-DNGP_KV={v}"]))
+    for k in range(2, 9):
+        tus.append((f"ngp_k_joint_{k}", "ngp_k_joint.cu", [f"-DNGP_JK={k}"]))
+    return tus
+
+
 def sources() -> list[str]:
-    return [os.path.join(CSRC, "ngp_api.cu"), os.path.join(CSRC, "ngp_ingest.cpp")]
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [HEADER]
+
+
+def _hash(extra: list[str]) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for f in sources():
+        h.update(os.path.basename(f).encode()); h.update(open(f, "rb").read())
+    h.update(" ".join(NVCC_FLAGS + extra).encode())
+    return h.hexdigest()
+
+
+def source_hash() -> str:
+    return _hash([])
 
 
 def _stale() -> bool:
-    if not os.path.exists(SO_PATH):
+    """The library is rebuilt when the hash of its sources (not their mtime) differs from the one it was linked from."""
+    if not os.path.exists(SO_PATH) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(SO_PATH)
-    deps = [HEADER] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return open(STAMP).read().strip() != source_hash()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> nextgp.jl_b200/libngp.so (in-tree, travels to the GPU box)."""
-    if force or _stale():
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + sources()
+def build(force: bool = False, verbose: bool = False, jobs: int = 0) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> nextgp.jl_b200/libngp.so (in-tree, travels to the GPU box).
+    Units are compiled in parallel; an object is reused only if the hash of ALL sources + its flags is unchanged."""
+    if os.environ.get("LIBNGP"):
+        return SO_PATH
+    if not (force or _stale()):
+        return SO_PATH
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    tus = translation_units()
+
+    def compile_one(tu):
+        name, src, extra = tu
+        obj, stamp = os.path.join(BUILD_DIR, name + ".o"), os.path.join(BUILD_DIR, name + ".hash")
+        hh = _hash(extra)
+        if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == hh:
+            return obj, ""
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + extra + ["-c", "-o", obj, os.path.join(CSRC, src)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-        if verbose:
-            sys.stderr.write(r.stderr)
+            raise RuntimeError(f"nvcc failed on {name}:\n" + r.stdout + r.stderr)
+        open(stamp, "w").write(hh)
+        return obj, r.stderr
+    with ThreadPoolExecutor(max_workers=jobs or max(1, min(16, os.cpu_count() or 1))) as ex:
+        res = list(ex.map(compile_one, tus))
+    if verbose:
+        for _, err in res:
+            sys.stderr.write(err)
+    r = subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO_PATH] + [o for o, _ in res], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    open(STAMP, "w").write(source_hash())
     return SO_PATH
 
 

@@ -20,6 +20,7 @@
 #include "../../include/ngp.h"
 #include "ngp_sweep.cuh"
 #include "ngp_joint.cuh"
+#include "ngp_kernels.h"
 
 using namespace ngp;
 
@@ -267,7 +268,7 @@ struct ngp_handle {
     int64_t n = 0;
     int refetch = 0;
     int Tw = 0, R = 0, B = 0, D = 0, DN = 0, NT = 0, NR = 0, NV = 0;      // worker CTAs (grid = Tw + 1), rows per panel, block, look-ahead, near depth, tile stages
-    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0, cfg_versions = 0, cfg_refetch = -1;
+    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0, cfg_versions = 0, cfg_refetch = -1, cfg_opt = 0;
     SmemLayout L{};
     // model
     SetHost sets[NGP_MAX_SETS];
@@ -471,6 +472,9 @@ int ngp_configure(ngp_handle* h, int key, int64_t value)
         h->cfg_refetch = (int)value; return NGP_OK;
     case NGP_CFG_PROFILE:
         h->cfg_profile = value ? 1 : 0; return NGP_OK;
+    case NGP_CFG_OPT:
+        if (value < 0 || value > 0xffff) return fail(h, NGP_EINVAL, "ngp_configure: option mask out of range");
+        h->cfg_opt = (int)value; return NGP_OK;
     case NGP_CFG_LOOKAHEAD:
         if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: look-ahead must be set before the first upload");
         if (value < 0 || value > kMaxD) return fail(h, NGP_EINVAL, "ngp_configure: look-ahead must be in [0,%d] (0 = auto)", kMaxD);
@@ -1048,7 +1052,7 @@ static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int 
     P.mu_lhs0 = h->mu_lhs0; P.mu_rhs0 = h->mu_rhs0; P.varE_in = varE_in; P.n_iter = n_iter; P.replay = h->replay;
     P.replay_base = h->replay_base; P.rp_chi2_e = h->rp_chi2_e; P.rp_z_mu = h->rp_z_mu;
     P.key0 = (uint32_t)(h->seed & 0xffffffffu); P.key1 = (uint32_t)(h->seed >> 32); P.chain = h->chain; P.accumulate = accumulate;
-    P.debug = h->cfg_debug;
+    P.debug = h->cfg_debug; P.opt = h->cfg_opt;
     P.fx = h->fx; P.fx.rp_z = h->fx_rp_z;
     P.w = h->w; P.w_sum = h->w_sum; P.w_min = h->w_min; P.w_max = h->w_max;
     if (h->w && h->fx.n_cols && h->fx_w_ready) { P.fx.xpx = h->fx_xpx_w; P.fx.colsum_w = h->fx_colsum_w; }
@@ -1100,16 +1104,7 @@ static int launch_joint(ngp_handle* h, int n_iter, int do_varE, int do_mu, doubl
     J.varBeta = Jh.varBeta; J.region_off = Jh.region_off; J.mtm = Jh.mtm;
     J.rp_z = Jh.rp_z; J.rp_iw_chi2 = Jh.rp_iw_chi2; J.rp_iw_z = Jh.rp_iw_z;
     const size_t smem = sizeof(double) * (size_t)(160 + kSlots * kMaxK + h->R);
-    const void* kfn = nullptr;
-    switch (Jh.k) {
-    case 2: kfn = (const void*)joint_kernel<2>; break;
-    case 3: kfn = (const void*)joint_kernel<3>; break;
-    case 4: kfn = (const void*)joint_kernel<4>; break;
-    case 5: kfn = (const void*)joint_kernel<5>; break;
-    case 6: kfn = (const void*)joint_kernel<6>; break;
-    case 7: kfn = (const void*)joint_kernel<7>; break;
-    default: kfn = (const void*)joint_kernel<8>; break;
-    }
+    const void* kfn = ngp_joint_kernel(Jh.k);
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, smem));
@@ -1199,13 +1194,10 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     if (h->w) P.kernel = NGP_KERNEL_LITERAL;            // weighted dots are not integer sums of codes: per-marker sweep
     for (int s = 0; s < h->n_sets; ++s)
         if (((set_mask >> s) & 1) && h->sets[s].method == NGP_BAYESR) P.kernel = NGP_KERNEL_LITERAL;     // the class algebra lives in the per-marker sweep
-#define NGP_PICK(PROF, DBG, LIT, TUP) ((h->B == 64) ? (const void*)gibbs_kernel<64, PROF, DBG, LIT, TUP> : (h->B == 32) ? (const void*)gibbs_kernel<32, PROF, DBG, LIT, TUP> : (const void*)gibbs_kernel<16, PROF, DBG, LIT, TUP>)
     bool tuple_mask = false;
     for (int s = 0; s < h->n_sets; ++s) if (((set_mask >> s) & 1) && h->sets[s].group_k) tuple_mask = true;
-    const void* kfn = tuple_mask ? NGP_PICK(false, false, false, true)
-                    : (P.kernel == NGP_KERNEL_LITERAL) ? NGP_PICK(false, false, true, false)
-                    : h->cfg_debug ? NGP_PICK(false, true, false, false) : h->cfg_profile ? NGP_PICK(true, false, false, false) : NGP_PICK(false, false, false, false);
-#undef NGP_PICK
+    const int variant = tuple_mask ? NGP_KV_TUP : (P.kernel == NGP_KERNEL_LITERAL) ? NGP_KV_LIT : h->cfg_debug ? NGP_KV_DBG : h->cfg_profile ? NGP_KV_PROF : NGP_KV_PLAIN;
+    const void* kfn = ngp_gibbs_kernel(h->B, variant);
     if (h->ready_kfn != kfn) {                      // once per kernel variant: attribute + co-residency check of the cooperative grid
         // the attribute belongs to the function, not to the handle: always the device maximum, so that handles with different
         // geometries never lower it under each other

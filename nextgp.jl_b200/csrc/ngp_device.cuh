@@ -159,6 +159,7 @@ struct Params {
     int32_t accumulate;        // add to posterior sums
     uint32_t gblk0;            // global number of the first block of this launch (lists and accumulator slots are numbered globally)
     int32_t debug;             // timing experiments (NGP_CFG_DEBUG), see ngp_sweep.cuh
+    int32_t opt;               // schedule options (NGP_CFG_OPT): 1 tiles streamed evict-first, 2 far Gram rows prefetched at change time
     // ---- row-sharded chain: rank r holds rows [row_0(r), row_0(r) + n) of X and e; every grid-wide quantity
     //      (barrier arrivals, phase-0 partials, per-marker fixed-point sums) is PUSHED into the SyncArea of every rank over
     //      NVLink peer memory, and every poll is local.  n_ranks == 1: not sharded (peer[0] == sync).
@@ -263,6 +264,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the same with an L2 cache policy (the genotype stream is read once per sweep: evict-first keeps it from displacing the Gram band)
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 

@@ -38,7 +38,7 @@ struct JointGeno {
     const uint8_t* geno[kMaxK];
     const int32_t* colsum[kMaxK];
 };
-__global__ void joint_mtm_kernel(const JointGeno G, int k, int Tw, int R, int B, int64_t nblk, int64_t n, int64_t p, double* __restrict__ mtm)
+static __global__ void joint_mtm_kernel(const JointGeno G, int k, int Tw, int R, int B, int64_t nblk, int64_t n, int64_t p, double* __restrict__ mtm)
 {
     const int lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

@@ -817,10 +817,13 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                     } else if (warp == kTmaWarp) {
                         // ------------------------------------------------------------------ TMA producer of the tile ring
                         if (lane == 0) {
+                            const bool ef = (P.opt & 1) != 0;
+                            const uint64_t pol = policy_evict_first();
                             for (int i = 0; i < nblk; ++i) {
                                 if (tiles_issued >= (unsigned)NT) mbar_wait(&tile_free[r_tp.s], r_tp.ph ^ 1u);
                                 mbar_expect_tx(&tile_full[r_tp.s], (uint32_t)L.tile_bytes);
-                                bulk_g2s(tiles + r_tp.s * L.tile_bytes, gbase + (int64_t)i * L.tile_bytes, (uint32_t)L.tile_bytes, &tile_full[r_tp.s]);
+                                if (ef) bulk_g2s_hint(tiles + r_tp.s * L.tile_bytes, gbase + (int64_t)i * L.tile_bytes, (uint32_t)L.tile_bytes, &tile_full[r_tp.s], pol);
+                                else bulk_g2s(tiles + r_tp.s * L.tile_bytes, gbase + (int64_t)i * L.tile_bytes, (uint32_t)L.tile_bytes, &tile_full[r_tp.s]);
                                 r_tp.adv(NT); ++tiles_issued;
                             }
                         }
@@ -1338,6 +1341,21 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                                     st_relaxed_u64(ew + 4, seqhi | (kkb >> 32));
                                 }
                                 if (lane < kLLCopies) st_relaxed_u64(sy->ll[lane] + lofs, seqhi | (unsigned long long)(uint32_t)nnz);
+                                if (P.opt & 2) {
+                                    // the far cross-Gram rows of a changed effect (distances DN+1 .. D) will be wanted by the prep warps a few
+                                    // blocks from now: start them on their way from HBM into L2
+                                    const int nd = D - DN;
+                                    const int mblk = s0 + k;
+                                    for (int x = lane; x < nnz * nd; x += 32) {
+                                        const int e = x / nd, d = DN + 1 + x % nd;
+                                        const int m = mblk + d;
+                                        if (m < nblk) {
+                                            const int32_t* row = gx_g + (size_t)m * gx_blk + (size_t)d * B * B + ml.idx[e] * B;
+                                            prefetch_l2(row);
+                                            if (B == 64) prefetch_l2(row + 32);
+                                        }
+                                    }
+                                }
                                 if constexpr (PROF) {
                                     const unsigned long long tn = global_ns();
                                     if (lane == 0) pub_ns[gk & (kNzRing - 1)] = tn;

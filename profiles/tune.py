@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--max_ctas", type=int, default=0)
     ap.add_argument("--refetch", type=int, default=-1)
     ap.add_argument("--min_rows", type=int, default=0)
+    ap.add_argument("--opt", default="0", help="comma list of NGP_CFG_OPT masks, each run for every combo")
     a = ap.parse_args()
     n, p, model = CONFIGS[a.config]
     model = a.model or model
@@ -30,7 +31,7 @@ def main():
     prob = ngp.synth.problem(n, p, seed)
     v_e, v, pi = ngp.synth.priors(prob, model)
     method = 0 if model in ("BayesRR", "BayesPR") else (1 if model == "BayesB" else 2)
-    for combo in a.combos.split(","):
+    for combo, opt in [(c, int(o)) for c in a.combos.split(",") for o in a.opt.split(",")]:
         b, d, nt, dn, dbg, nv = (list(int(x) for x in combo.split(":")) + [0, 0])[:6]
         t0 = time.time()
         try:
@@ -39,6 +40,8 @@ def main():
                 s.configure(ngp._lib.CFG_VERSIONS, nv)
             if dbg:
                 s.configure(ngp._lib.CFG_DEBUG, dbg)
+            if opt:
+                s.configure(ngp._lib.CFG_OPT, opt)
             s.synth_genotypes(0, n, p, seed, prob["thr0"], prob["thr1"])
             t_up = time.time() - t0
             s.set_prior(0, method, 4.0, v * 0.5, v, pi_in=pi, est_pi=(method == 2))
@@ -49,7 +52,7 @@ def main():
                 ms.append(s.timing()["last_run_ms"])
             g = s.timing()
             st = s.state(want_e=False)
-            print(json.dumps({"combo": combo, "ms_last10_mean": float(np.mean(ms[-10:])), "ms_min": float(np.min(ms)), "ms_first": ms[0],
+            print(json.dumps({"combo": combo, "opt": opt, "ms_last10_mean": float(np.mean(ms[-10:])), "ms_min": float(np.min(ms)), "ms_first": ms[0],
                               "upload_s": round(t_up, 2), "included": int(st["sets"][0]["delta"].sum()),
                               "geom": {k: g[k] for k in ("ctas", "block", "rows_per_cta", "smem_bytes", "lookahead", "near_depth", "tile_stages", "record_stages")}}), flush=True)
             s.close()
