@@ -34,7 +34,8 @@ enum ngp_status {
     NGP_ERANGE = -4,   /* fixed-point reduction overflow guard tripped       */
     NGP_ENOMEM = -5,
     NGP_EUNSUPPORTED = -6,
-    NGP_ENUMERIC = -7  /* a covariance matrix of the tuple sampler lost positive definiteness */
+    NGP_ENUMERIC = -7, /* a covariance matrix of the tuple sampler lost positive definiteness */
+    NGP_ETIMEOUT = -8  /* row-sharded chain: another rank did not arrive within 4 s (its launch failed or it is not running); results invalid */
 };
 
 /* priorVCV[pSet].name dispatch of mme.jl:331,350,362 */
@@ -226,6 +227,12 @@ int ngp_get_column_stats(ngp_handle* h, int set_id, double* mean, double* mpm);
 int ngp_shard_init(ngp_handle* h, int rank, int world);
 int ngp_shard_export(ngp_handle* h, ngp_shard_info* out);
 int ngp_shard_attach(ngp_handle* h, const ngp_shard_info* all_ranks);
+/* All ranks of a chain whose shards live on ONE device (fewer GPUs than ranks: tests, small boxes): one cooperative grid over all
+ * ranks' row slices, handles[r] = rank r.  Kernels that wait for one another must never be separate launches on one GPU (they are
+ * not guaranteed to be co-resident), so ngp_run refuses such a handle and this call replaces it.  Same protocol and code path as
+ * between GPUs (system-scope REDs / polls on every rank's synchronisation area).  A rank that does not arrive within 4 s ends every
+ * wait: NGP_ETIMEOUT.                                                                                                          */
+int ngp_run_group(ngp_handle** handles, int n_handles, int32_t n_iter);
 int ngp_get_column_sums(ngp_handle* h, int set_id, int64_t* colsum, int64_t* colsumsq);
 int ngp_set_column_sums(ngp_handle* h, int set_id, int64_t n_total, const int64_t* colsum, const int64_t* colsumsq);
 

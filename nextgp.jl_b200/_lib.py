@@ -19,7 +19,7 @@ GENO_I8, GENO_F64, GENO_PACKED2 = 0, 1, 2
 STORE_I8, STORE_2BIT = 0, 1
 KERNEL_BLOCKED, KERNEL_LITERAL = 0, 1
 CFG_KERNEL, CFG_BLOCK, CFG_MIN_ROWS, CFG_MAX_CTAS, CFG_LOOKAHEAD, CFG_TILE_STAGES, CFG_NEAR, CFG_PROFILE, CFG_DEBUG, CFG_VERSIONS, CFG_REFETCH, CFG_OPT = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
-OK, EINVAL, ECUDA, EDATA, ERANGE, ENOMEM, EUNSUPPORTED, ENUMERIC = 0, -1, -2, -3, -4, -5, -6, -7
+OK, EINVAL, ECUDA, EDATA, ERANGE, ENOMEM, EUNSUPPORTED, ENUMERIC, ETIMEOUT = 0, -1, -2, -3, -4, -5, -6, -7, -8
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 BUILD_DIR = os.path.join(_HERE, "build")          # object files (git-ignored); the linked library is nextgp.jl_b200/libngp.so
@@ -76,7 +76,7 @@ def translation_units() -> list[tuple[str, str, list[str]]]:
     """(object name, source file, extra flags): one instantiation of the sweep kernels per unit (csrc/ngp_kernels.h)."""
     tus = [("ngp_api", "ngp_api.cu", []), ("ngp_ingest", "ngp_ingest.cpp", [])]
     for B in (16, 32, 64):
-        for v in range(5):
+        for v in range(6):
             tus.append((f"ngp_k_gibbs_{B}_{v}", "ngp_k_gibbs.cu", [f"-DNGP_KB={B}", f"-DNGP_KV={v}"]))
     for k in range(2, 9):
         tus.append((f"ngp_k_joint_{k}", "ngp_k_joint.cu", [f"-DNGP_JK={k}"]))
@@ -157,6 +157,7 @@ _SIGS = {
     "ngp_synth_genotypes_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]),
     "ngp_shard_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "ngp_shard_export": (C.c_int, [C.c_void_p, C.POINTER(ShardInfo)]),
+    "ngp_run_group": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32]),
     "ngp_shard_attach": (C.c_int, [C.c_void_p, C.POINTER(ShardInfo)]),
     "ngp_get_column_sums": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ngp_set_column_sums": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),

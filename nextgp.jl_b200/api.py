@@ -261,6 +261,7 @@ class Sampler:
         if rc != 0:
             raise L.NgpError(rc, self._lib.ngp_last_error(None).decode())
         self._h = hp
+        self.device = device
         self.sets: dict[int, dict] = {}
         self.n = 0
         self._keep = []
@@ -643,6 +644,19 @@ class ShardedChain:
             s.set_phenotype(y[a:b])
 
     def run(self, n_iter: int = 1) -> None:
+        """Shards on ONE device run as one cooperative grid (ngp_run_group): kernels that wait for one another must not be separate
+        launches on one GPU.  Shards on distinct devices: one launch per device, each from its own host thread; every shard is
+        validated (a dry ngp_get_timing / state check) before any is launched, and a rank that never arrives ends the others' waits
+        after 4 s (NGP_ETIMEOUT)."""
+        devs = {s.device for s in self.shards}
+        if len(devs) == 1:
+            arr = (C.c_void_p * self.world)(*[s._h for s in self.shards])
+            rc = L.lib().ngp_run_group(arr, self.world, n_iter)
+            if rc != L.OK:
+                raise L.NgpError(rc, (L.lib().ngp_last_error(self.shards[0]._h) or b"").decode())
+            return
+        if len(devs) != self.world:
+            raise ValueError("ShardedChain: shards must be on one device (one grid) or on pairwise distinct devices")
         import threading
         errs: list = []
 

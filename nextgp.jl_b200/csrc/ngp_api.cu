@@ -268,7 +268,7 @@ struct ngp_handle {
     int64_t n = 0;
     int refetch = 0;
     int Tw = 0, R = 0, B = 0, D = 0, DN = 0, NT = 0, NR = 0, NV = 0;      // worker CTAs (grid = Tw + 1), rows per panel, block, look-ahead, near depth, tile stages
-    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0, cfg_versions = 0, cfg_refetch = -1, cfg_opt = 0;
+    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0, cfg_versions = 0, cfg_refetch = -1, cfg_opt = 3;
     SmemLayout L{};
     // model
     SetHost sets[NGP_MAX_SETS];
@@ -300,7 +300,7 @@ struct ngp_handle {
     int fx_replay_iters = 0;
     // row-sharded chain
     int shard_rank = 0, shard_world = 1;
-    bool shard_attached = false;
+    bool shard_attached = false, shard_same_device = false;   // same_device: another rank of the chain lives on this device (one grid: ngp_run_group)
     SyncArea* peer[kMaxRanks] = {nullptr};
     bool peer_ipc[kMaxRanks] = {false};
     int shard_Tw[kMaxRanks] = {0};
@@ -1074,6 +1074,7 @@ static int check_kernel_error(ngp_handle* h)
 {
     int kerr = 0;
     CU(cpy(h, &kerr, &h->sync->err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (kerr & 8) return fail(h, NGP_ETIMEOUT, "row-sharded chain: a rank did not arrive within 4 s (results invalid)");
     if (kerr & 2) return fail(h, NGP_ENUMERIC, "a covariance matrix of the tuple sampler is not positive definite");
     if (kerr & 4) return fail(h, NGP_ENUMERIC, "BayesR: no class reached its uniform (the reference's findfirst returns nothing here)");
     if (kerr) return fail(h, NGP_ERANGE, "fixed-point reduction range exceeded (residual grew by more than 2^4 within an iteration)");
@@ -1121,7 +1122,8 @@ static int launch_joint(ngp_handle* h, int n_iter, int do_varE, int do_mu, doubl
     return check_kernel_error(h);
 }
 
-static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_mu, double varE_in, int accumulate, bool defer_sync = false)
+// everything up to the launch itself: checks, weighted set-up, Params, kernel variant, bookkeeping of the global block / barrier counters
+static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_mu, double varE_in, int accumulate, Params& P, const void*& kfn, bool group)
 {
     CU(cudaSetDevice(h->device));
     if (h->joint.active && !(h->joint.blocked_set >= 0 && set_mask == (1 << h->joint.blocked_set)))
@@ -1133,6 +1135,9 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
         return fail(h, NGP_EINVAL, "replay log of the fixed effects missing (ngp_set_fixed_replay after ngp_set_replay)");
     if (sharded && h->cfg_kernel != NGP_KERNEL_LITERAL)
         return fail(h, NGP_EUNSUPPORTED, "the row-sharded chain runs the per-marker kernel (NGP_CFG_KERNEL = NGP_KERNEL_LITERAL)");
+    if (sharded && h->shard_same_device && !group)
+        return fail(h, NGP_EUNSUPPORTED, "shards of one chain on the same device wait for one another: separate launches are not guaranteed to be "
+                                         "co-resident, run them as one grid with ngp_run_group");
     if (!h->have_y) return fail(h, NGP_EINVAL, "no phenotype / residual on the device (ngp_set_phenotype or ngp_sweep)");
     int active = 0;
     for (int s = 0; s < h->n_sets; ++s)
@@ -1189,7 +1194,7 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     }
     int rc = sync_sets(h);
     if (rc) return rc;
-    Params P{};
+    P = Params{};
     fill_params(h, P, n_iter, set_mask, do_varE, do_mu, varE_in, accumulate);
     if (h->w) P.kernel = NGP_KERNEL_LITERAL;            // weighted dots are not integer sums of codes: per-marker sweep
     for (int s = 0; s < h->n_sets; ++s)
@@ -1197,8 +1202,9 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     bool tuple_mask = false;
     for (int s = 0; s < h->n_sets; ++s) if (((set_mask >> s) & 1) && h->sets[s].group_k) tuple_mask = true;
     const int variant = tuple_mask ? NGP_KV_TUP : (P.kernel == NGP_KERNEL_LITERAL) ? NGP_KV_LIT : h->cfg_debug ? NGP_KV_DBG : h->cfg_profile ? NGP_KV_PROF : NGP_KV_PLAIN;
-    const void* kfn = ngp_gibbs_kernel(h->B, variant);
-    if (h->ready_kfn != kfn) {                      // once per kernel variant: attribute + co-residency check of the cooperative grid
+    kfn = ngp_gibbs_kernel(h->B, group ? NGP_KV_GROUP : variant);
+    if (group && variant != NGP_KV_LIT) return fail(h, NGP_EUNSUPPORTED, "ngp_run_group runs the per-marker kernel only");
+    if (!group && h->ready_kfn != kfn) {                      // once per kernel variant: attribute + co-residency check of the cooperative grid
         // the attribute belongs to the function, not to the handle: always the device maximum, so that handles with different
         // geometries never lower it under each other
         cudaFuncAttributes fa;
@@ -1227,6 +1233,15 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
             if ((set_mask >> s) & 1) rounds += ((h->sets[s].method == NGP_BAYESPR && h->sets[s].n_regions > 1) || accumulate) ? 1 : 0;
         h->bar_count += rounds * (uint64_t)n_iter;
     } else CU(cudaMemsetAsync(h->sync, 0, kSyncHeadBytes, h->stream));
+    return NGP_OK;
+}
+
+static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_mu, double varE_in, int accumulate, bool defer_sync = false)
+{
+    Params P{};
+    const void* kfn = nullptr;
+    int rc = launch_prepare(h, n_iter, set_mask, do_varE, do_mu, varE_in, accumulate, P, kfn, false);
+    if (rc) return rc;
     void* args[] = {&P};
     CU(cudaEventRecord(h->ev0, h->stream));
     CU(cudaLaunchCooperativeKernel(kfn, dim3(h->Tw + 1), dim3(kThreads), args, (size_t)h->L.total, h->stream));
@@ -1384,6 +1399,61 @@ int ngp_shard_init(ngp_handle* h, int rank, int world)
     return NGP_OK;
 }
 
+// All shards of a chain that live on ONE device: one cooperative grid over all ranks' row slices (ngp::gibbs_group_kernel).
+int ngp_run_group(ngp_handle** hs, int n_handles, int32_t n_iter)
+{
+    if (!hs || n_handles < 1 || !hs[0]) return NGP_EINVAL;
+    ngp_handle* h = hs[0];
+    if (n_iter <= 0) return fail(h, NGP_EINVAL, "ngp_run_group: n_iter must be positive");
+    if (n_handles != h->shard_world) return fail(h, NGP_EINVAL, "ngp_run_group: %d handles for a chain of %d shards", n_handles, h->shard_world);
+    int total = 0;
+    size_t smem = 0;
+    for (int r = 0; r < n_handles; ++r) {
+        ngp_handle* g = hs[r];
+        if (!g || g->device != h->device || g->shard_world != n_handles || g->shard_rank != r || g->B != h->B)
+            return fail(h, NGP_EINVAL, "ngp_run_group: handle %d is not rank %d of this chain on device %d (same block size)", r, r, h->device);
+        if (g->joint.active) return fail(h, NGP_EUNSUPPORTED, "ngp_run_group: no tuple sampler on a row-sharded chain");
+        total += g->Tw + 1;
+        smem = std::max(smem, (size_t)g->L.total);
+    }
+    CU(cudaSetDevice(h->device));
+    std::vector<Params> Ps((size_t)n_handles);
+    const void* kfn = nullptr;
+    // validate every shard before anything is launched
+    for (int r = 0; r < n_handles; ++r) {
+        ngp_handle* g = hs[r];
+        int mask = 0;
+        for (int s = 0; s < g->n_sets; ++s) if (g->sets[s].have_geno) mask |= 1 << s;
+        int rc = launch_prepare(g, n_iter, mask, 1, 1, 0.0, 1, Ps[(size_t)r], kfn, true);
+        if (rc) { if (g != h) h->err = g->err; return rc; }
+        if (g->stream != h->stream) CU(cudaStreamSynchronize(g->stream));      // its memsets / copies are ordered before the launch on hs[0]'s stream
+    }
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, kfn));
+    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->prop.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, smem));
+    if (per_sm * h->prop.multiProcessorCount < total)
+        return fail(h, NGP_EUNSUPPORTED, "cooperative grid of %d CTAs (all shards) does not fit (%d per SM x %d SMs)", total, per_sm, h->prop.multiProcessorCount);
+    Params* dPs = nullptr;
+    CU(cudaMalloc((void**)&dPs, sizeof(Params) * (size_t)n_handles));
+    CU(cudaMemcpyAsync(dPs, Ps.data(), sizeof(Params) * (size_t)n_handles, cudaMemcpyHostToDevice, h->stream));
+    GroupParams G{dPs, n_handles};
+    void* args[] = {&G};
+    CU(cudaEventRecord(h->ev0, h->stream));
+    CU(cudaLaunchCooperativeKernel(kfn, dim3((unsigned)total), dim3(kThreads), args, smem, h->stream));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(dPs);
+    for (int r = 0; r < n_handles; ++r) {
+        hs[r]->launches += 1;
+        hs[r]->timed = (r == 0);
+        int rc = check_kernel_error(hs[r]);
+        if (rc) { if (hs[r] != h) h->err = hs[r]->err; return rc; }
+    }
+    return NGP_OK;
+}
+
 int ngp_shard_export(ngp_handle* h, ngp_shard_info* out)
 {
     if (!h || !out) return fail(h, NGP_EINVAL, "ngp_shard_export: NULL argument");
@@ -1422,6 +1492,7 @@ int ngp_shard_attach(ngp_handle* h, const ngp_shard_info* all)
                 cudaGetLastError();
             }
             h->peer[r] = (SyncArea*)(uintptr_t)I.local_ptr; h->peer_ipc[r] = false;
+            if (I.device == h->device) h->shard_same_device = true;
         } else {                                               // one process per GPU: CUDA IPC mapping over NVLink
             cudaIpcMemHandle_t ih;
             memcpy(&ih, I.ipc, 64);

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) joint_kernel(const Params P, cons
     long long* lprev = reinterpret_cast<long long*>(misc + 160);             // [kSlots][kMaxK] previous accumulator values
     double* e_s = misc + 160 + kSlots * kMaxK;
     SyncArea* sy = P.sync;
-    GridSync gs{&sy->counter, 0ull, (unsigned)(Tw + 1), 0ull, 1};
+    GridSync gs{&sy->err, &sy->counter, 0ull, (unsigned)(Tw + 1), 0ull, 1};
     const int64_t row0 = (int64_t)t * R;
     const int nrow = is_chain ? 0 : (int)max((int64_t)0, min((int64_t)R, P.n - row0));
     const int nwords = R >> 2;

@@ -1,5 +1,5 @@
-// ngp_k_gibbs.cu — ONE instantiation of ngp::gibbs_kernel per translation unit: compile with -DNGP_KB={16,32,64} -DNGP_KV={0..4}
-// (block size; variant: 0 plain, 1 instrumented, 2 timing experiments, 3 per-marker "literal" sweep, 4 tuple sweep).  See ngp_kernels.h.
+// ngp_k_gibbs.cu — ONE instantiation of ngp::gibbs_kernel per translation unit: compile with -DNGP_KB={16,32,64} -DNGP_KV={0..5}
+// (block size; variant: 0 plain, 1 instrumented, 2 timing experiments, 3 per-marker "literal" sweep, 4 tuple sweep, 5 all ranks of a sharded chain on one device as one grid).  See ngp_kernels.h.
 #include "ngp_sweep.cuh"
 #include "ngp_kernels.h"
 
@@ -11,5 +11,9 @@
 
 extern "C" const void* NGP_CAT3(ngp_kptr_gibbs_, NGP_KB, NGP_KV)(void)
 {
+#if NGP_KV == 5
+    return (const void*)ngp::gibbs_group_kernel<NGP_KB>;
+#else
     return (const void*)ngp::gibbs_kernel<NGP_KB, NGP_KV == NGP_KV_PROF, NGP_KV == NGP_KV_DBG, NGP_KV == NGP_KV_LIT, NGP_KV == NGP_KV_TUP>;
+#endif
 }

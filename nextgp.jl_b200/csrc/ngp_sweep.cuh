@@ -109,7 +109,20 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch
 
 // Grid barrier.  Sharded chain (n_ranks > 1): an arrival is pushed to the counter of every rank (release at system scope
 // covers this CTA's earlier peer stores), every rank polls its own counter; the counter is monotonic across launches.
+// Row-sharded chain: every wait for another rank gives up after kShardTimeoutNs (or as soon as any wait of this rank has given up) and
+// raises bit 8 of the error word; the launch then runs to its end on garbage and the host reports NGP_ECUDA-free failure NGP_ETIMEOUT.
+constexpr unsigned long long kShardTimeoutNs = 4000000000ull;
+__device__ __forceinline__ bool shard_wait_expired(int* err, unsigned long long& t0)
+{
+    if (*reinterpret_cast<volatile int*>(err) & 8) return true;
+    const unsigned long long now = global_ns();
+    if (t0 == 0) { t0 = now; return false; }
+    if (now - t0 > kShardTimeoutNs) { atomicOr(err, 8); return true; }
+    return false;
+}
+
 struct GridSync {
+    int* err;
     unsigned long long* counter;
     unsigned long long nbar;     // barriers this CTA has taken part in (this launch)
     unsigned int T;              // CTAs of all ranks
@@ -125,7 +138,12 @@ struct GridSync {
     {
         const unsigned long long target = base + nbar * (unsigned long long)T;
         if (n_ranks > 1) {
-            while ((unsigned long long)ld_relaxed_s64_sys(reinterpret_cast<const long long*>(counter)) < target) { }
+            // bounded: a rank that never arrives (its launch failed, its GPU is gone) must not hang the others for ever
+            unsigned spins = 0;
+            unsigned long long t0 = 0;
+            while ((unsigned long long)ld_relaxed_s64_sys(reinterpret_cast<const long long*>(counter)) < target) {
+                if ((++spins & 0x3ffu) == 0u && shard_wait_expired(err, t0)) break;
+            }
             asm volatile("fence.acq_rel.sys;" ::: "memory");
         } else {
             while ((unsigned long long)ld_relaxed_s64(reinterpret_cast<const long long*>(counter)) < target) { }
@@ -334,7 +352,7 @@ __device__ __forceinline__ void joint_step(double (&rr)[NS], const double (&bold
 // TUP: the instantiation that also sweeps a tuple of interleaved marker sets (method 4); kept apart so that the k x k algebra does not
 //      weigh on the register allocation of the single-trait sweep
 template <int B, bool PROF, bool DBG, bool LIT, bool TUP>
-__global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
+__device__ __forceinline__ void gibbs_body(const Params& P, const int t)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NB = (B + 31) / 32;      // markers per lane of a prep warp (lane <-> marker b*32 + lane)
@@ -347,7 +365,6 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     constexpr int MG = B / 16;             // 16-marker MMA groups per block
     constexpr int UG = (B == 16) ? kUpdGroups : 1;   // 4-row groups per updater thread (B = 32 / 64 are chosen for R <= 512)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t = blockIdx.x;
     const int Tw = P.Tw;
     const bool is_chain = (t == Tw);
     const int R = P.R, D = P.D, DN = P.DN, NT = P.NT, NR = P.NR;
@@ -386,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
     NzList* cnz = reinterpret_cast<NzList*>(smem + L.c_nz);
 
     const bool sharded = P.n_ranks > 1;
-    GridSync gs{&sy->counter, 0ull, (unsigned)P.T_all, P.bar_base, P.n_ranks};
+    GridSync gs{&sy->err, &sy->counter, 0ull, (unsigned)P.T_all, P.bar_base, P.n_ranks};
     const int64_t row0 = (int64_t)t * R;
     const int nrow = is_chain ? 0 : (int)max((int64_t)0, min((int64_t)R, P.n - row0));    // real rows of this panel
     const int nchunk = R >> 5;
@@ -936,7 +953,10 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         // slot i of a lane = marker mi = 32 i + lane of the step: block kb = mi / B of the step, column qb = mi % B
                         int kb[NS], qb[NS];
 #pragma unroll
-                        for (int i = 0; i < NS; ++i) { kb[i] = (32 * i + lane) / B; qb[i] = (32 * i + lane) % B; }
+                        for (int i = 0; i < NS; ++i) {
+                            if constexpr (B >= 32) { kb[i] = (32 * i) / B; qb[i] = (32 * i) % B + lane; }      // the block of a slot is a compile-time constant
+                            else { kb[i] = (32 * i + lane) / B; qb[i] = (32 * i + lane) % B; }
+                        }
                         int nn[SB];                                         // changed effects per block of the step
 #pragma unroll
                         for (int k = 0; k < SB; ++k) nn[k] = 0;
@@ -1462,7 +1482,14 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
                         }
                         long long* pv = lprev + slot;
                         long long cur;
-                        if (sharded) { do { cur = ld_relaxed_s64_sys(acc); } while (((cur - *pv) & 0xFF) != arrivals); }
+                        if (sharded) {
+                            unsigned spins = 0;
+                            unsigned long long t0 = 0;
+                            do {
+                                cur = ld_relaxed_s64_sys(acc);
+                                if ((++spins & 0x3ffu) == 0u && shard_wait_expired(&sy->err, t0)) break;
+                            } while (((cur - *pv) & 0xFF) != arrivals);
+                        }
                         else { do { cur = ld_relaxed_s64(acc); } while (((cur - *pv) & 0xFF) != arrivals); }
                         const double A = (double)((cur - *pv - arrivals) >> kCntBits) * fx_inv;
                         __syncwarp();
@@ -1670,6 +1697,37 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
         }
     }
 #undef NGP_TICK
+}
+
+template <int B, bool PROF, bool DBG, bool LIT, bool TUP>
+__global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
+{
+    gibbs_body<B, PROF, DBG, LIT, TUP>(P, (int)blockIdx.x);
+}
+
+// All ranks of a row-sharded chain whose shards live on ONE device, as ONE cooperative grid (the only legal way to run kernels that wait
+// for one another on one GPU: separate launches are not guaranteed to be co-resident).  CTA b belongs to the rank r with
+// cta_off(r) <= b < cta_off(r) + Tw(r) + 1 and runs that rank's per-marker sweep on that rank's Params — the same code, the same
+// system-scope REDs and polls as between GPUs.
+struct GroupParams { const Params* ranks; int n_ranks; };
+template <int B>
+__global__ void __launch_bounds__(kThreads, 1) gibbs_group_kernel(const GroupParams G)
+{
+    __shared__ Params Ps;
+    __shared__ int rsel;
+    if (threadIdx.x == 0) {
+        int r = 0;
+        while (r + 1 < G.n_ranks && (int)blockIdx.x >= G.ranks[r + 1].cta_off) ++r;
+        rsel = r;
+    }
+    __syncthreads();
+    {
+        const int* src = reinterpret_cast<const int*>(&G.ranks[rsel]);
+        int* dst = reinterpret_cast<int*>(&Ps);
+        for (int i = threadIdx.x; i < (int)(sizeof(Params) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    gibbs_body<B, false, false, true, false>(Ps, (int)blockIdx.x - Ps.cta_off);
 }
 
 }  // namespace ngp

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import nextgp.jl_b200 as ngp
-from common import gpu_sampler, make_problem, oracle_chain, rel
+from common import METHODS, gpu_sampler, make_problem, oracle_chain, rel
 from nextgp.jl_b200 import _lib as L
 from oracle import oracle as O
 
@@ -454,3 +454,62 @@ def test_call_order_and_argument_errors(gpu):
     s.run(2)
     assert s.state()["iter"] == 2
     s.close()
+
+
+# ----------------------------------------------------------------------------- oracle parity AT the BASELINE row counts and kernel geometries
+def _native_vs_oracle_at_scale(n, p, model, iters, seed, expect=None, tol=1e-7, **geom):
+    """Device-generated genotypes (ngp_synth_genotypes) against the CPU oracle on the SAME codes (regenerated on the host by the
+    oracle's own Philox), native variate stream on both sides: per-iteration beta, delta, varE, mu, varBeta, pi and the residual."""
+    pr = ngp.synth.problem(n, p, seed)
+    v_e, v, pi = ngp.synth.priors(pr, model)
+    method = METHODS["BayesPR" if model == "BayesRR" else model]
+    codes = O.synth_codes(seed, n, 0, p, pr["thr0"], pr["thr1"])
+    X, _, mpm = O.center_codes(codes)
+    del codes
+    S = O.MarkerSet(X=X, mpm=mpm, method=method, v=v, pi=pi, est_pi=(method == 2))
+    ch = O.OracleChain(pr["y"], [S], v_e=v_e)
+    O.set_threads(max(1, len(os.sched_getaffinity(0))))
+    g = ngp.Sampler(0, **geom)
+    g.synth_genotypes(0, n, p, seed, pr["thr0"], pr["thr1"])
+    g.set_prior(0, method, *O.marker_hyper(v), v, pi_in=pi, est_pi=(method == 2))
+    g.set_phenotype(pr["y"]); g.set_residual_prior(*O.residual_hyper(v_e)); g.set_intercept(True)
+    g.set_rng(seed, 3)
+    t = g.timing()
+    if expect:
+        for k, val in expect.items():
+            assert t[k] == val if not callable(val) else val(t[k]), f"geometry {k} = {t[k]}"
+    worst = 0.0
+    try:
+        for it in range(iters):
+            ch.iteration(seed=seed, chain=3)
+            g.run(1)
+            st = g.state()
+            assert np.array_equal(st["sets"][0]["delta"], S.delta), f"indicator mismatch at iteration {it + 1}"
+            worst = max(worst, rel(st["sets"][0]["beta"], S.beta), abs(st["varE"] / ch.varE - 1), abs(st["mu"] / ch.mu - 1),
+                        rel(st["sets"][0]["varBeta"], S.varBeta), rel(st["e"], ch.e))
+            if method:
+                worst = max(worst, rel(st["sets"][0]["piHat"], S.piHat))
+            assert worst < tol, f"iteration {it + 1}: rel diff {worst}"
+    finally:
+        O.set_threads(1)
+        g.close()
+    return worst
+
+
+def test_oracle_parity_at_headline_rows_bayescpi(gpu):
+    """BASELINE config 2 rows: n = 50,000 x 2,000 markers BayesCpi (functions.jl:197-236), default geometry of the headline run
+    (blocks of 32, 352 rows per CTA, look-ahead 14), native stream, 3 iterations against the oracle to 1e-7."""
+    _native_vs_oracle_at_scale(50000, 2000, "BayesC", 3, 20261020,
+                               expect=dict(block=32, rows_per_cta=352, lookahead=14, ctas=lambda c: c >= 140))
+
+
+def test_oracle_parity_at_c5_geometry_refetch_ring(gpu):
+    """BASELINE config 5 rows: n = 200,000 x 512 markers BayesCpi: blocks of 16, 1,376+ rows per CTA (4 row groups per updater thread),
+    tiles leave shared memory after their dots (refetch ring) and changed columns are re-read from L2."""
+    _native_vs_oracle_at_scale(200000, 512, "BayesC", 3, 20261021,
+                               expect=dict(block=16, rows_per_cta=lambda r: r >= 1376, ctas=lambda c: c >= 140))
+
+
+def test_oracle_parity_at_c3_geometry_bayesb(gpu):
+    """BASELINE config 3 rows: n = 100,000 x 512 markers BayesB (functions.jl:157-195): blocks of 16, 704 rows per CTA."""
+    _native_vs_oracle_at_scale(100000, 512, "BayesB", 3, 20261022, expect=dict(block=16, rows_per_cta=704))

@@ -1,7 +1,9 @@
 """Row-sharded single chain (BASELINE config 5): the individuals are split over several handles whose
 persistent kernels reduce every marker's partial dots through each other's synchronisation areas (peer memory; NVLink
-between GPUs).  On a one-GPU box the shards are co-resident kernels on the same device — the same protocol, the same
-code path (`ld/red ...sys`), which is how SURVEY §8e asks the multi-rank logic to be tested when GPUs are scarce."""
+between GPUs).  On a one-GPU box all ranks run as ONE cooperative grid over all ranks' data (ngp_run_group,
+ngp::gibbs_group_kernel) — the same protocol, the same code path (`ld/red ...sys` on every rank's synchronisation area),
+which is how SURVEY §8e / §4(iv) ask the multi-rank logic to be tested when GPUs are scarce: kernels that wait for one
+another are never separate launches on one GPU."""
 import numpy as np
 import pytest
 
@@ -68,6 +70,17 @@ def test_sharded_chain_over_two_gpus(gpu):
     ch.run(5)
     st = ch.state()
     assert rel(st["sets"][0]["beta"], S.beta) < 1e-8 and rel(st["e"], ch_o.e) < 1e-8
+    ch.close()
+
+
+def test_same_device_shards_refuse_separate_launches(gpu):
+    """ngp_run on a handle whose peer lives on the same device would be a separate launch waiting for another: refused."""
+    prob = make_problem(400, 40, 3)
+    ch = _sharded(prob, [0, 0], 2, v=0.05, pi=0.1, est_pi=True)
+    with pytest.raises(ngp.NgpError) as ei:
+        ch.shards[0].run(1)
+    assert ei.value.code == ngp._lib.EUNSUPPORTED
+    ch.run(1)                                  # the group launch works
     ch.close()
 
 
