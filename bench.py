@@ -48,10 +48,11 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def workload_name(cfg, n, p, model):
+def workload_name(cfg, n, p, model, storage="i8"):
+    st = "2-bit packed" if storage == "2bit" else "int8"
     if model.startswith("MultiBreed"):
-        return f"{cfg}: {n} individuals x {p} SNPs, {model[10:]}-breed tuple BayesPR (joint effects per locus) + intercept, int8 genotypes in HBM"
-    return f"{cfg}: {n} individuals x {p} SNPs single-trait {model}{'pi' if model == 'BayesC' else ''} + intercept, int8 genotypes in HBM"
+        return f"{cfg}: {n} individuals x {p} SNPs, {model[10:]}-breed tuple BayesPR (joint effects per locus) + intercept, {st} genotypes in HBM"
+    return f"{cfg}: {n} individuals x {p} SNPs single-trait {model}{'pi' if model == 'BayesC' else ''} + intercept, {st} genotypes in HBM"
 
 
 def clocks_sampler(stop, out):
@@ -167,12 +168,70 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "marker-updates/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps * (p / pc), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, n, p, model), "sample": f"first {pc} of {p} markers, all rows; ms_per_step extrapolated linearly in p"},
+            "config": {"workload": workload_name(args.config, n, p, model), "sample": f"first {pc} of {p} markers, all rows; ms_per_step extrapolated linearly in p",
+                       "chains": 1, "note": "ONE CPU chain on rank 0's host cores whatever --gpus is: at N > 1 compare it with value / N of the GPU arm (N chains)"},
             "cpu_baseline": {"value": val, "unit": "marker-updates/s", "cores": threads, "kind": "port",
                              "sample": f"first {pc} of {p} markers x {n} rows, dense fp64, OpenMP over rows in dot/axpy, {threads} of {host_threads()} host threads (the faster of 1 / all, calibrated); CPU restatement of NextGP.jl (no Julia on the box)"},
             "e2e": {"value": val, "unit": "marker-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def sharded_leg(rank, world, local, dist, n, model, seed, p_s=2048, iters=3):
+    """Row-sharded single chain over the N GPUs of this run on a bounded slice of the workload (all n rows, the first p_s markers),
+    CHECKED: every rank must hold the bitwise identical chain, and it must agree with the unsharded chain that rank 0 runs on the
+    same data with the same variate stream.  Returns {per_marker_us, max_rel_err, ranks_identical} on rank 0."""
+    import torch
+    import nextgp.jl_b200 as ngp
+    prob = ngp.synth.problem(n, p_s, seed)
+    v_e, v, pi = ngp.synth.priors(prob, model)
+    method = 0 if model in ("BayesRR", "BayesPR") else (1 if model == "BayesB" else 2)
+    per = -(-(-(-n // world)) // 4) * 4
+    a, b = min(n, rank * per), min(n, (rank + 1) * per)
+    s = ngp.Sampler(local, kernel="literal")
+    s.shard_init(rank, world)
+    s.synth_genotypes_rows(0, a, b - a, p_s, seed, prob["thr0"], prob["thr1"])
+    infos = [None] * world
+    dist.all_gather_object(infos, s.shard_export())
+    s.shard_attach(infos)
+    cs, css = s.column_sums(0)
+    tcs = torch.from_numpy(np.stack([cs, css])).cuda()
+    dist.all_reduce(tcs)
+    tcs = tcs.cpu().numpy()
+    s.set_column_sums(0, n, tcs[0], tcs[1])
+    s.set_prior(0, method, 4.0, v * 0.5, v, pi_in=pi, est_pi=(method == 2))
+    s.set_phenotype(prob["y"][a:b]); s.set_residual_prior(4.0, v_e * 0.5); s.set_intercept(True); s.set_rng(seed, 0)
+    dist.barrier()
+    s.run(1)                                            # warm-up launch (also exercises the cross-launch barrier counter)
+    torch.cuda.synchronize(); dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(); s.run(iters - 1); ev1.record()
+    torch.cuda.synchronize()
+    tms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    st = s.state(want_e=False)
+    mine = torch.from_numpy(np.concatenate([st["sets"][0]["beta"], [st["varE"], st["mu"]]])).cuda()
+    allb = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allb, mine)
+    identical = all(bool(torch.equal(allb[0].view(torch.int64), x.view(torch.int64))) for x in allb)
+    s.close()
+    out = None
+    if rank == 0:
+        u = ngp.Sampler(local)                          # the same chain, unsharded, blocked kernel
+        u.synth_genotypes(0, n, p_s, seed, prob["thr0"], prob["thr1"])
+        u.set_prior(0, method, 4.0, v * 0.5, v, pi_in=pi, est_pi=(method == 2))
+        u.set_phenotype(prob["y"]); u.set_residual_prior(4.0, v_e * 0.5); u.set_intercept(True); u.set_rng(seed, 0)
+        u.run(iters)
+        su = u.state(want_e=False)
+        u.close()
+        ref = np.concatenate([su["sets"][0]["beta"], [su["varE"], su["mu"]]])
+        got = allb[0].cpu().numpy()
+        err = float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300))
+        out = {"per_marker_us": 1e3 * float(tms.item()) / (iters - 1) / p_s, "max_rel_err": err, "ranks_identical": bool(identical),
+               "checked_against": f"unsharded blocked chain of rank 0, {iters} iterations, beta / varE / mu",
+               "slice": f"all {n} rows x first {p_s} markers, per-marker kernel, one fixed-point RED per marker into every rank's accumulator over NVLink"}
+    dist.barrier()
+    return out
 
 
 def main():
@@ -187,10 +246,13 @@ def main():
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--p", type=int, default=0)
     ap.add_argument("--model", default="BayesC")
+    ap.add_argument("--storage", default="i8", choices=["i8", "2bit"], help="device storage of the genotype codes (2bit: NGP_STORE_2BIT, a quarter of the HBM bytes per sweep)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--weighted", action="store_true",
                     help="diagnostic: residual weights w ~ U(0.5, 2) (E.str == \"D\", mme.jl:70-73); the set is swept by the per-marker kernel")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sharded-leg", action="store_true", help="N > 1: skip the checked row-sharded leg")
+    ap.add_argument("--long-seconds", type=float, default=1.0, help="extra untimed-by-contract run of at least this many seconds after the K timed steps (0 = off)")
     ap.add_argument("--ref-cols", type=int, default=2000)
     ap.add_argument("--sharded", action="store_true",
                     help="ONE chain whose individuals are row-sharded over the N GPUs (per-marker reduction over NVLink peer memory); strong scaling")
@@ -227,7 +289,7 @@ def main():
     if sharded:
         args.kernel = "literal"
         args.no_e2e = True
-    s = ngp.Sampler(local, kernel=args.kernel, block=args.block)
+    s = ngp.Sampler(local, kernel=args.kernel, block=args.block, storage=args.storage)
     stream = torch.cuda.current_stream()
     s.set_stream(stream.cuda_stream)
     df, scale = 4.0, v * 0.5
@@ -304,6 +366,40 @@ def main():
     nchains = 1 if sharded else world
     value = nchains * p * args.steps / (ms_all * 1e-3)
 
+    # ---- a longer run (the contract's K steps last ~20 ms at C2): at least --long-seconds of back-to-back launches
+    long_run = None
+    if args.long_seconds > 0 and not sharded:
+        per = max(ms / max(args.steps, 1), 1e-3)
+        k2 = int(min(20000, max(args.steps, np.ceil(args.long_seconds * 1e3 / per))))
+        lms = []
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k2):
+            s.run(1)
+            lms.append(s.timing()["last_run_ms"])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        long_run = {"steps": k2, "ms_per_step": e0.elapsed_time(e1) / k2, "kernel_ms_mean": float(np.mean(lms)), "kernel_ms_p10_p90": [float(np.percentile(lms, 10)), float(np.percentile(lms, 90))]}
+    # ---- how many effects change per sweep (the cost of a sweep grows with it): three more iterations, counted on the host
+    changed = None
+    if not sharded and not kbreeds:
+        b_prev = s.state(want_e=False)["sets"][0]["beta"].copy()
+        cnt = []
+        for _ in range(3):
+            s.run(1)
+            b_new = s.state(want_e=False)["sets"][0]["beta"]
+            cnt.append(int(np.count_nonzero(b_new != b_prev)))
+            b_prev = b_new.copy()
+        changed = float(np.mean(cnt))
+    # ---- N > 1: the row-sharded single chain over the same GPUs, checked
+    shard_rec = None
+    if dist and not sharded and not kbreeds and not args.no_sharded_leg and not args.weighted and args.storage == "i8":
+        try:
+            shard_rec = sharded_leg(rank, world, local, dist, n, model, seed)
+        except Exception as ex:  # noqa: BLE001
+            shard_rec = {"error": str(ex)}
+
     # ---- e2e: the plugin call with host buffers (pinned), H2D + sweep + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -334,22 +430,28 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         tm = s.timing()
-        alg_bytes = p * (n * 1.0 + 40.0) * max(1, kbreeds)     # n*g + 40 B of per-marker scalars, g = 1 B (per breed column)
+        gbytes = 0.25 if args.storage == "2bit" else 1.0
+        alg_bytes = p * (n * gbytes + 40.0) * max(1, kbreeds)     # n*g + 40 B of per-marker scalars, g = 1 B int8 / 0.25 B 2-bit (per breed column)
         if sharded:
             alg_bytes /= world                                 # bytes streamed by ONE GPU (its row slice)
         k_ms = float(np.mean(kern_ms))
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_source = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(f"{args.config}:{args.kernel}")
+                tj = json.load(open(tp))
+                key = f"{args.config}:{args.kernel}" + (":2bit" if args.storage == "2bit" else "")
+                traffic = tj.get(key)
+                if traffic is not None:
+                    traffic_source = tj.get("_source", {}).get(key, "ncu --set full capture of this kernel at this config (dram__bytes_read.sum + dram__bytes_write.sum per launch), "
+                                                                     "recorded in profiles/traffic.json — NOT measured in this run")
             except Exception:
                 traffic = None
         line = {"metric": METRIC, "value": value, "unit": "marker-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": workload_name(args.config, n, p, model) + (" [diagnostic: weighted residuals E.str == \"D\", per-marker kernel]" if args.weighted else ""), "kernel": ("blocked tuple sweep (interleaved copy, joint draw in the chain warp)" if args.kernel == "blocked" and kbreeds in (2, 4) else "joint (per locus)") if kbreeds else args.kernel, "chains": nchains,
+                "config": {"workload": workload_name(args.config, n, p, model, args.storage) + (" [diagnostic: weighted residuals E.str == \"D\", per-marker kernel]" if args.weighted else ""), "kernel": ("blocked tuple sweep (interleaved copy, joint draw in the chain warp)" if args.kernel == "blocked" and kbreeds in (2, 4) else "joint (per locus)") if kbreeds else args.kernel, "chains": nchains,
                            "parallelism": (f"ONE chain row-sharded over {world} GPUs: per-marker fixed-point reduction pushed into every rank's "
                                            f"accumulators over NVLink peer memory (CUDA IPC), identical draw on every rank")
                                           if sharded else f"{world} independent chain(s), one per GPU, no data-path collective",
@@ -357,12 +459,16 @@ def main():
                                  if n * p > 4e8 else "inputs fit in L2 (cache-resident workload; HBM roofline not meaningful)",
                            "gibbs_iters_per_s": nchains * args.steps / (ms_all * 1e-3),
                            "geometry": {k: tm[k] for k in ("ctas", "threads", "block", "rows_per_cta", "smem_bytes", "lookahead", "near_depth", "tile_stages", "record_stages")}},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
                              "kernel": ("ngp::gibbs_kernel<TUP> (one launch = one Gibbs iteration)" if args.kernel == "blocked" and kbreeds in (2, 4)
                                         else "ngp::joint_kernel (one launch = one Gibbs iteration)") if kbreeds else
                                        "ngp::gibbs_kernel (one launch = one Gibbs iteration)", "kernel_ms": k_ms,
                              "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": summarize_clocks(lines)}
+        line["config"]["changed_effects_per_sweep"] = changed
+        line["long_run"] = long_run
+        if shard_rec is not None:
+            line["sharded"] = shard_rec
         if sharded:
             line["per_marker_us"] = 1e3 * ms_all / args.steps / p
         if not args.no_cpu and not kbreeds:

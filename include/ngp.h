@@ -55,7 +55,10 @@ enum ngp_geno_format {
 /* device storage of the genotype codes */
 enum ngp_storage {
     NGP_STORE_I8 = 0,     /* one byte per code, row panels x marker blocks, tiles in INT8-MMA operand order */
-    NGP_STORE_2BIT = 1    /* four codes per byte (capacity mode; not built yet: NGP_EUNSUPPORTED)            */
+    NGP_STORE_2BIT = 1    /* four codes per byte: the same tiles, every 32-bit word (4 rows of a marker) squeezed into one  */
+                          /* byte and expanded to the INT8 operands on chip; a quarter of the HBM bytes per sweep.  Blocked   */
+                          /* sweep of BayesPR / BayesB / BayesC sets on one GPU (per-marker kernel, tuple: NGP_EUNSUPPORTED); */
+                          /* all sets of a handle share the storage format                                                  */
 };
 
 /* kernel variants (ngp_configure key NGP_CFG_KERNEL) */

@@ -254,8 +254,9 @@ class Sampler:
 
     def __init__(self, device: int = 0, kernel: str = "blocked", block: int = 0, min_rows: int = 0, max_ctas: int = 0,
                  lookahead: int = 0, tile_stages: int = 0, near: int = 0, versions: int = 0, profile: bool = False,
-                 refetch: int = -1):
+                 refetch: int = -1, storage: str = "i8"):
         self._lib = L.lib()
+        self.storage = {"i8": L.STORE_I8, "2bit": L.STORE_2BIT}[storage]
         hp = C.c_void_p()
         rc = self._lib.ngp_create(device, C.byref(hp))
         if rc != 0:
@@ -322,21 +323,21 @@ class Sampler:
             data = np.asfortranarray(data, dtype=np.float64 if fmt == L.GENO_F64 else np.int8)
             n, p = data.shape
             ld = n
-        self._ck(self._lib.ngp_upload_genotypes(self._h, set_id, n, p, _p(data), fmt, ld, L.STORE_I8))
+        self._ck(self._lib.ngp_upload_genotypes(self._h, set_id, n, p, _p(data), fmt, ld, self.storage))
         self.n = n
         self.sets[set_id] = {"p": p}
 
     def synth_genotypes(self, set_id: int, n: int, p: int, seed: int, thr0: np.ndarray, thr1: np.ndarray) -> None:
         thr0 = np.ascontiguousarray(thr0, dtype=np.uint32)
         thr1 = np.ascontiguousarray(thr1, dtype=np.uint32)
-        self._ck(self._lib.ngp_synth_genotypes(self._h, set_id, n, p, C.c_uint64(seed), _p(thr0), _p(thr1), L.STORE_I8))
+        self._ck(self._lib.ngp_synth_genotypes(self._h, set_id, n, p, C.c_uint64(seed), _p(thr0), _p(thr1), self.storage))
         self.n = n
         self.sets[set_id] = {"p": p}
 
     def synth_genotypes_rows(self, set_id: int, row0: int, n: int, p: int, seed: int, thr0: np.ndarray, thr1: np.ndarray) -> None:
         thr0 = np.ascontiguousarray(thr0, dtype=np.uint32)
         thr1 = np.ascontiguousarray(thr1, dtype=np.uint32)
-        self._ck(self._lib.ngp_synth_genotypes_rows(self._h, set_id, row0, n, p, C.c_uint64(seed), _p(thr0), _p(thr1), L.STORE_I8))
+        self._ck(self._lib.ngp_synth_genotypes_rows(self._h, set_id, row0, n, p, C.c_uint64(seed), _p(thr0), _p(thr1), self.storage))
         self.n = n
         self.sets[set_id] = {"p": p}
 

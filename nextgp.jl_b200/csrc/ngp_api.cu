@@ -45,15 +45,15 @@ __device__ __forceinline__ int block_sum_int(int v, int* scratch)
 template <int FMT>
 __global__ void pack_kernel(const void* __restrict__ src, int64_t ld, int64_t n, int64_t j0, int R, int B, int64_t nblk,
                             uint8_t* __restrict__ geno, int32_t* __restrict__ colsum, int32_t* __restrict__ colsumsq,
-                            int* __restrict__ err, int64_t jmul = 1, int64_t jadd = 0)
+                            int* __restrict__ err, int64_t jmul = 1, int64_t jadd = 0, int store2 = 0)
 {
     __shared__ int scratch[32];
     const int64_t jc = blockIdx.x, j = (j0 + jc) * jmul + jadd;      // destination column (jmul, jadd: interleaving of a tuple's sets)
     const int64_t k = j / B;
     const int q = (int)(j - k * B);
-    const int64_t tile_bytes = (int64_t)B * R;
+    const int64_t tile_bytes = tile_bytes_of(B, R, store2);
     int s = 0, ss = 0, bad = 0;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    auto code_at = [&](int64_t i) -> int {
         int g;
         if (FMT == NGP_GENO_I8) {
             g = reinterpret_cast<const int8_t*>(src)[jc * ld + i];
@@ -65,9 +65,24 @@ __global__ void pack_kernel(const void* __restrict__ src, int64_t ld, int64_t n,
         }
         if (g < 0 || g > 2) { bad = 1; g = 0; }
         s += g; ss += g * g;
-        const int64_t t = i / R;
-        const int r = (int)(i - t * R);
-        geno[(t * nblk + k) * tile_bytes + byte_off(B, q, r)] = (uint8_t)g;
+        return g;
+    };
+    if (store2) {
+        // a thread owns the 4 consecutive rows of one stored byte (R is a multiple of 32: they lie in one panel)
+        for (int64_t i4 = (int64_t)threadIdx.x * 4; i4 < n; i4 += (int64_t)blockDim.x * 4) {
+            uint32_t byte = 0;
+            for (int u = 0; u < 4 && i4 + u < n; ++u) byte |= (uint32_t)code_at(i4 + u) << (2 * u);
+            const int64_t t = i4 / R;
+            const int r = (int)(i4 - t * R);
+            geno[(t * nblk + k) * tile_bytes + word_off(B, q, r >> 2)] = (uint8_t)byte;
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const int g = code_at(i);
+            const int64_t t = i / R;
+            const int r = (int)(i - t * R);
+            geno[(t * nblk + k) * tile_bytes + byte_off(B, q, r)] = (uint8_t)g;
+        }
     }
     s = block_sum_int(s, scratch);
     ss = block_sum_int(ss, scratch);
@@ -93,14 +108,14 @@ __global__ void colstats_kernel(int64_t n, int64_t p, int64_t p_pad, const int32
 // fragment-ordered tiles (the A atom is 512 contiguous bytes; a B register is one tile word of the other block).
 template <int B>
 __global__ void __launch_bounds__(256) gram_kernel(const uint8_t* __restrict__ geno, int Tw, int R, int64_t nblk, int D,
-                                                   int32_t* __restrict__ gx)
+                                                   int32_t* __restrict__ gx, int store2)
 {
     constexpr int MG = B / 16, NBG = B / 8;
     const int64_t k = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, tt = lane & 3;
     const int nchunk = R >> 5;
-    const int64_t tile_bytes = (int64_t)B * R;
+    const int64_t tile_bytes = tile_bytes_of(B, R, store2);
     const int items = (D + 1) * MG * NBG;
     for (int item = warp; item < items; item += 8) {
         const int d = item / (MG * NBG), rem = item - d * (MG * NBG), mg = rem / NBG, nb = rem - mg * NBG;
@@ -110,12 +125,23 @@ __global__ void __launch_bounds__(256) gram_kernel(const uint8_t* __restrict__ g
             for (int t = 0; t < Tw; ++t) {
                 const uint8_t* ta = geno + ((int64_t)t * nblk + (k - d)) * tile_bytes;
                 const uint32_t* tb = reinterpret_cast<const uint32_t*>(geno + ((int64_t)t * nblk + k) * tile_bytes);
+                if (store2) {
+                    const uint8_t* tb8 = reinterpret_cast<const uint8_t*>(tb);
+#pragma unroll 4
+                    for (int c = 0; c < nchunk; ++c) {
+                        const uint4 a = expand2_word(__ldg(reinterpret_cast<const uint32_t*>(ta) + (size_t)(c * MG + mg) * 32 + lane));
+                        const uint32_t b0 = expand2((uint32_t)__ldg(tb8 + word_off(B, qb, 8 * c + tt)));
+                        const uint32_t b1 = expand2((uint32_t)__ldg(tb8 + word_off(B, qb, 8 * c + 4 + tt)));
+                        imma16832(acc, a, b0, b1);
+                    }
+                } else {
 #pragma unroll 4
                 for (int c = 0; c < nchunk; ++c) {
                     const uint4 a = __ldg(reinterpret_cast<const uint4*>(ta + ((size_t)(c * MG + mg) * 32 + lane) * 16));
                     const uint32_t b0 = __ldg(tb + word_off(B, qb, 8 * c + tt));
                     const uint32_t b1 = __ldg(tb + word_off(B, qb, 8 * c + 4 + tt));
                     imma16832(acc, a, b0, b1);
+                }
                 }
             }
         }
@@ -142,13 +168,16 @@ __global__ void synth_kernel(uint32_t key0, uint32_t key1, int64_t n, int64_t ro
 }
 
 __global__ void unpack_kernel(const uint8_t* __restrict__ geno, int64_t n, int R, int B, int64_t nblk, int64_t j0, int64_t ncols,
-                              int8_t* __restrict__ out)
+                              int8_t* __restrict__ out, int store2)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t jc = blockIdx.y;
     if (i >= n || jc >= ncols) return;
     const int64_t j = j0 + jc, k = j / B, t = i / R;
-    out[jc * n + i] = (int8_t)geno[(t * nblk + k) * ((int64_t)B * R) + byte_off(B, (int)(j - k * B), (int)(i - t * R))];
+    const int r = (int)(i - t * R);
+    const uint8_t* tile = geno + (t * nblk + k) * tile_bytes_of(B, R, store2);
+    out[jc * n + i] = store2 ? (int8_t)((tile[word_off(B, (int)(j - k * B), r >> 2)] >> (2 * (r & 3))) & 3)
+                             : (int8_t)tile[byte_off(B, (int)(j - k * B), r)];
 }
 
 // weighted residuals (E.str == "D"): mpm_j = sum_i w_i x_ij^2 with x = g - mean (mme.jl:299-301) and sum_i w_i x_ij; one CTA per marker
@@ -266,7 +295,7 @@ struct ngp_handle {
     std::string err;
     // geometry
     int64_t n = 0;
-    int refetch = 0;
+    int refetch = 0, store2 = -1;      // store2: device storage of ALL marker sets of the handle (-1 until the first upload)
     int Tw = 0, R = 0, B = 0, D = 0, DN = 0, NT = 0, NR = 0, NV = 0;      // worker CTAs (grid = Tw + 1), rows per panel, block, look-ahead, near depth, tile stages
     int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0, cfg_versions = 0, cfg_refetch = -1, cfg_opt = 3;
     SmemLayout L{};
@@ -499,7 +528,7 @@ int ngp_set_stream(ngp_handle* h, void* cuda_stream)
 }
 
 // ----------------------------------------------------------------------------- geometry
-static int choose_geometry(ngp_handle* h, int64_t n)
+static int choose_geometry(ngp_handle* h, int64_t n, int store2)
 {
     const int sms = h->prop.multiProcessorCount;
     int maxc = h->cfg_max_ctas ? std::min(h->cfg_max_ctas, sms) : sms;
@@ -512,7 +541,7 @@ static int choose_geometry(ngp_handle* h, int64_t n)
     Tw = (int)((n + R - 1) / R);                                    // no empty panels
     const size_t cap = h->prop.sharedMemPerBlockOptin;
     int B = h->cfg_block;
-    if (!B) B = (64 * R <= 12288) ? 64 : (32 * R <= 16384) ? 32 : 16;
+    if (!B) B = (64 * R <= 12288) ? 64 : (32 * R <= 16384) ? 32 : 16;      // (2-bit storage: the same choice — the tiles are a quarter of the size)
     const int64_t maxR = 4LL * kUpdThreads * (B == 16 ? kUpdGroups : 1);     // residual rows an updater warp group holds in registers
     if (R > maxR)
         return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA; block %d supports at most %lld (use block 16 for up to %d)",
@@ -540,7 +569,7 @@ static int choose_geometry(ngp_handle* h, int64_t n)
             for (;;) {
                 for (int NR = kRecStages; NR >= 2; NR >>= 1) {
                     const int NV = h->cfg_versions ? h->cfg_versions : std::max(4, std::min(kLimbVers, D / 2 + 3));
-                    SmemLayout L = smem_layout((int)R, B, NT, DN, NR, NV);
+                    SmemLayout L = smem_layout((int)R, B, NT, DN, NR, NV, store2);
                     if ((size_t)L.total + 2048 <= cap) {
                         h->n = n; h->Tw = Tw; h->R = (int)R; h->B = B; h->D = D; h->DN = DN; h->NT = NT; h->NR = NR; h->NV = NV; h->L = L;
                         h->refetch = refetch;
@@ -577,9 +606,9 @@ static int finish_upload(ngp_handle* h, SetHost& S)
     CU(dalloc(&S.consts, (size_t)nblk * kNF * h->B));
     CU(zero(h, S.consts, 0, sizeof(double) * (size_t)nblk * kNF * h->B));
     CU(dalloc(&S.gx, (size_t)nblk * (h->D + 1) * h->B * h->B));
-    if (h->B == 64) gram_kernel<64><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx);
-    else if (h->B == 32) gram_kernel<32><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx);
-    else gram_kernel<16><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx);
+    if (h->B == 64) gram_kernel<64><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx, h->store2);
+    else if (h->B == 32) gram_kernel<32><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx, h->store2);
+    else gram_kernel<16><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx, h->store2);
     CU(cudaGetLastError());
     CU(dalloc(&S.beta, p_pad));
     CU(dalloc(&S.delta, p_pad));
@@ -599,11 +628,14 @@ static int begin_upload(ngp_handle* h, int set_id, int64_t n, int64_t p, int sto
     if (set_id < 0 || set_id >= NGP_MAX_SETS) return fail(h, NGP_EINVAL, "set_id %d out of range", set_id);
     if (n <= 0 || p <= 0) return fail(h, NGP_EINVAL, "n and p must be positive");
     if (p > 0x7fffffffLL || n > 0x7fffffffLL) return fail(h, NGP_EINVAL, "n and p must fit in 31 bits");
-    if (storage != NGP_STORE_I8) return fail(h, NGP_EUNSUPPORTED, "device storage %d is not available in this build (use NGP_STORE_I8)", storage);
+    if (storage != NGP_STORE_I8 && storage != NGP_STORE_2BIT) return fail(h, NGP_EINVAL, "unknown device storage %d", storage);
+    if (h->store2 >= 0 && h->store2 != (storage == NGP_STORE_2BIT)) return fail(h, NGP_EINVAL, "all marker sets of a handle share one device storage format");
+    if (storage == NGP_STORE_2BIT && h->shard_world > 1) return fail(h, NGP_EUNSUPPORTED, "2-bit device storage: blocked sweep on one GPU only (the row-sharded chain runs the per-marker kernel)");
     CU(cudaSetDevice(h->device));
     if (h->Tw == 0) {
-        int rc = choose_geometry(h, n);
+        int rc = choose_geometry(h, n, storage == NGP_STORE_2BIT);
         if (rc) return rc;
+        h->store2 = (storage == NGP_STORE_2BIT);
         CU(dalloc(&h->e, (size_t)h->Tw * h->R));
         CU(zero(h, h->e, 0, sizeof(double) * (size_t)h->Tw * h->R));
     } else if (n != h->n) {
@@ -618,7 +650,7 @@ static int begin_upload(ngp_handle* h, int set_id, int64_t n, int64_t p, int sto
     S.p = p;
     S.p_pad = ((p + kMaxB - 1) / kMaxB) * kMaxB;
     S.storage = storage;
-    const size_t gbytes = (size_t)h->Tw * S.p_pad * h->R;
+    const size_t gbytes = ((size_t)h->Tw * S.p_pad * h->R) >> (storage == NGP_STORE_2BIT ? 2 : 0);
     CU(dalloc(&S.geno, gbytes));
     CU(cudaMemsetAsync(S.geno, 0, gbytes, h->stream));             // code 0 everywhere (pad rows / pad markers)
     CU(dalloc(&S.colsum, S.p_pad));
@@ -651,9 +683,9 @@ int ngp_upload_genotypes(ngp_handle* h, int set_id, int64_t n, int64_t p, const 
     for (int64_t j0 = 0; j0 < p; j0 += chunk) {
         const int64_t nc = std::min(chunk, p - j0);
         CU(cudaMemcpyAsync(stage, (const char*)data + (size_t)j0 * colbytes, colbytes * nc, cudaMemcpyHostToDevice, h->stream));
-        if (fmt == NGP_GENO_I8) pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr);
-        else if (fmt == NGP_GENO_F64) pack_kernel<NGP_GENO_F64><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr);
-        else pack_kernel<NGP_GENO_PACKED2><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr);
+        if (fmt == NGP_GENO_I8) pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr, 1, 0, h->store2);
+        else if (fmt == NGP_GENO_F64) pack_kernel<NGP_GENO_F64><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr, 1, 0, h->store2);
+        else pack_kernel<NGP_GENO_PACKED2><<<(unsigned)nc, 256, 0, h->stream>>>(stage, ld, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr, 1, 0, h->store2);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(h->stream));     // the pageable source buffer is borrowed per chunk
     }
@@ -694,7 +726,7 @@ int ngp_synth_genotypes_rows(ngp_handle* h, int set_id, int64_t row0, int64_t n,
         dim3 grid((unsigned)(((n + 3) / 4 + 255) / 256), (unsigned)nc);
         synth_kernel<<<grid, 256, 0, h->stream>>>((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), n, row0, j0, nc, d0, d1, stage);
         CU(cudaGetLastError());
-        pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, n, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr);
+        pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, n, n, j0, h->R, h->B, S.p_pad / h->B, S.geno, S.colsum, S.colsumsq, derr, 1, 0, h->store2);
         CU(cudaGetLastError());
     }
     CU(cudaStreamSynchronize(h->stream));
@@ -716,7 +748,7 @@ int ngp_download_genotypes(ngp_handle* h, int set_id, int64_t j0, int64_t j1, in
     for (int64_t c0 = j0; c0 < j1; c0 += chunk) {
         const int64_t nc = std::min(chunk, j1 - c0);
         dim3 grid((unsigned)((n + 255) / 256), (unsigned)nc);
-        unpack_kernel<<<grid, 256, 0, h->stream>>>(S.geno, n, h->R, h->B, S.p_pad / h->B, c0, nc, stage);
+        unpack_kernel<<<grid, 256, 0, h->stream>>>(S.geno, n, h->R, h->B, S.p_pad / h->B, c0, nc, stage, h->store2);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out + (size_t)(c0 - j0) * n, stage, (size_t)n * nc, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -1046,7 +1078,7 @@ static int sync_sets(ngp_handle* h)
 static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int do_varE, int do_mu, double varE_in, int accumulate)
 {
     P.n = h->n; P.Tw = h->Tw; P.R = h->R; P.B = h->B; P.n_sets = h->n_sets; P.kernel = h->cfg_kernel;
-    P.D = h->D; P.DN = h->DN; P.NT = h->NT; P.NR = h->NR; P.NV = h->NV; P.refetch = h->refetch;
+    P.D = h->D; P.DN = h->DN; P.NT = h->NT; P.NR = h->NR; P.NV = h->NV; P.refetch = h->refetch; P.store2 = h->store2 > 0;
     P.e = h->e; P.sets = h->sets_dev; P.sc = h->sc; P.sync = h->sync;
     P.df_e = h->df_e; P.scale_e = h->scale_e; P.has_mu = h->has_mu; P.do_varE = do_varE; P.do_mu = do_mu; P.set_mask = set_mask;
     P.mu_lhs0 = h->mu_lhs0; P.mu_rhs0 = h->mu_rhs0; P.varE_in = varE_in; P.n_iter = n_iter; P.replay = h->replay;
@@ -1087,6 +1119,7 @@ static int launch_joint(ngp_handle* h, int n_iter, int do_varE, int do_mu, doubl
     CU(cudaSetDevice(h->device));
     JointHost& Jh = h->joint;
     if (!Jh.active) return fail(h, NGP_EINVAL, "no tuple of marker sets (ngp_set_joint_prior)");
+    if (h->store2 > 0) return fail(h, NGP_EUNSUPPORTED, "the tuple sampler reads int8 device storage (upload with NGP_STORE_I8)");
     if (!h->have_y) return fail(h, NGP_EINVAL, "no phenotype / residual on the device (ngp_set_phenotype or ngp_joint_sweep)");
     if (h->replay) {
         Scalars sc;
@@ -1202,6 +1235,9 @@ static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, 
     bool tuple_mask = false;
     for (int s = 0; s < h->n_sets; ++s) if (((set_mask >> s) & 1) && h->sets[s].group_k) tuple_mask = true;
     const int variant = tuple_mask ? NGP_KV_TUP : (P.kernel == NGP_KERNEL_LITERAL) ? NGP_KV_LIT : h->cfg_debug ? NGP_KV_DBG : h->cfg_profile ? NGP_KV_PROF : NGP_KV_PLAIN;
+    if (h->store2 > 0 && (variant == NGP_KV_LIT || variant == NGP_KV_TUP))
+        return fail(h, NGP_EUNSUPPORTED, "2-bit device storage serves the blocked sweep of BayesPR / BayesB / BayesC sets (not the per-marker kernel: "
+                                         "BayesR, weighted residuals, row sharding; not the tuple sampler): upload with NGP_STORE_I8");
     kfn = ngp_gibbs_kernel(h->B, group ? NGP_KV_GROUP : variant);
     if (group && variant != NGP_KV_LIT) return fail(h, NGP_EUNSUPPORTED, "ngp_run_group runs the per-marker kernel only");
     if (!group && h->ready_kfn != kfn) {                      // once per kernel variant: attribute + co-residency check of the cooperative grid
@@ -1544,6 +1580,7 @@ int ngp_set_joint_prior(ngp_handle* h, const ngp_joint_prior* pr)
     if (!h || !pr) return fail(h, NGP_EINVAL, "ngp_set_joint_prior: NULL argument");
     const int k = pr->k;
     if (k < 2 || k > kMaxK) return fail(h, NGP_EINVAL, "ngp_set_joint_prior: k must be in [2,%d]", kMaxK);
+    if (h->store2 > 0) return fail(h, NGP_EUNSUPPORTED, "the tuple sampler reads int8 device storage (upload with NGP_STORE_I8)");
     if (!pr->scale || !pr->var_init || !(pr->df > 0.0)) return fail(h, NGP_EINVAL, "ngp_set_joint_prior: scale / var_init / df missing");
     int64_t p = 0;
     unsigned member_mask = 0;
@@ -1611,7 +1648,7 @@ int ngp_set_joint_prior(ngp_handle* h, const ngp_joint_prior* pr)
             const int sv_l = h->cfg_lookahead, sv_n = h->cfg_near, sv_r = h->cfg_refetch, sv_b = h->cfg_block;
             h->cfg_lookahead = 3; h->cfg_near = 3; h->cfg_refetch = 0; h->cfg_block = h->B;
             const int Tw0 = h->Tw, R0 = h->R;
-            int rcg = choose_geometry(h, h->n);
+            int rcg = choose_geometry(h, h->n, 0);
             h->cfg_lookahead = sv_l; h->cfg_near = sv_n; h->cfg_refetch = sv_r; h->cfg_block = sv_b;
             if (rcg) return rcg;
             if (h->Tw != Tw0 || h->R != R0) return fail(h, NGP_EINVAL, "internal: the tile layout changed while re-sizing the rings");
@@ -1632,7 +1669,7 @@ int ngp_set_joint_prior(ngp_handle* h, const ngp_joint_prior* pr)
             for (int64_t c0 = 0; c0 < p; c0 += chunk) {
                 const int64_t nc = std::min(chunk, p - c0);
                 dim3 grid((unsigned)((h->n + 255) / 256), (unsigned)nc);
-                unpack_kernel<<<grid, 256, 0, h->stream>>>(Mb.geno, h->n, h->R, h->B, Mb.p_pad / h->B, c0, nc, stage);
+                unpack_kernel<<<grid, 256, 0, h->stream>>>(Mb.geno, h->n, h->R, h->B, Mb.p_pad / h->B, c0, nc, stage, h->store2);
                 CU(cudaGetLastError());
                 pack_kernel<NGP_GENO_I8><<<(unsigned)nc, 256, 0, h->stream>>>(stage, h->n, h->n, c0, h->R, h->B, T.p_pad / h->B, T.geno, T.colsum, T.colsumsq, derr, (int64_t)k, (int64_t)b);
                 CU(cudaGetLastError());

@@ -166,6 +166,7 @@ struct Params {
     int32_t n_ranks, rank;
     int32_t cta_off, T_all;    // index of this rank's first CTA in the all-rank CTA numbering; CTAs of all ranks
     int32_t Tw_all;            // worker CTAs of all ranks (arrivals per accumulator)
+    int32_t store2;            // 1: genotypes stored as 2-bit codes (NGP_STORE_2BIT), expanded to the INT8 operands on chip
     int32_t refetch;           // 1: tiles leave shared memory once their dots are formed; the columns of changed effects are re-read from L2/HBM
     int64_t n_total;           // individuals over all ranks (n is the local row count)
     unsigned long long bar_base;   // barrier arrivals counted before this launch (sharded: the counter is never reset)
@@ -188,6 +189,24 @@ __host__ __device__ __forceinline__ int word_off(int B, int q, int wr)
     return (((c * (B >> 4) + mg) * 32 + g * 4 + t) << 2) | a_idx;
 }
 __host__ __device__ __forceinline__ int byte_off(int B, int q, int r) { return (word_off(B, q, r >> 2) << 2) | (r & 3); }
+
+// 2-bit device storage (NGP_STORE_2BIT): the same tile with every 32-bit word (the codes of 4 consecutive rows of one marker) squeezed
+// into ONE byte, code of row 4w + i in bits 2i .. 2i+1.  The byte index of (marker q, rows 4 wr ..) is word_off(B, q, wr): a lane's four
+// A registers of an MMA atom become the four bytes of ONE 32-bit word, expanded on chip.
+//   expand2(x): byte of 4 codes -> 4 bytes (c0 | c1 << 8 | c2 << 16 | c3 << 24).  The low and the high nibble are moved 16 bits apart, so
+//   that the shifted copies of the multiplication by (1 + 2^6) neither overlap nor carry.
+__host__ __device__ __forceinline__ uint32_t expand2(uint32_t x)
+{
+    const uint32_t v = (x & 0x0Fu) | ((x & 0xF0u) << 12);
+    return (v * 0x41u) & 0x03030303u;
+}
+__host__ __device__ __forceinline__ uint4 expand2_word(uint32_t w)
+{
+    uint4 a;
+    a.x = expand2(w & 0xffu); a.y = expand2((w >> 8) & 0xffu); a.z = expand2((w >> 16) & 0xffu); a.w = expand2(w >> 24);
+    return a;
+}
+__host__ __device__ __forceinline__ int64_t tile_bytes_of(int B, int R, int store2) { return store2 ? ((int64_t)B * R) >> 2 : (int64_t)B * R; }
 
 __host__ __device__ __forceinline__ int consts_bytes(int B) { return kNF * B * 8; }
 __host__ __device__ __forceinline__ int gram_bytes(int B) { return B * B * 4; }

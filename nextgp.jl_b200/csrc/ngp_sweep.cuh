@@ -51,10 +51,10 @@ struct SmemLayout {
     int tile_bytes, rec_bytes, limb_bytes, nz_bytes;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int R, int B, int NT, int DN, int NR, int NV)
+__host__ __device__ inline SmemLayout smem_layout(int R, int B, int NT, int DN, int NR, int NV, int store2 = 0)
 {
     SmemLayout L;
-    L.tile_bytes = B * R;
+    L.tile_bytes = store2 ? (B * R) >> 2 : B * R;
     L.rec_bytes = (1 + DN) * gram_bytes(B) + consts_bytes(B);
     L.limb_bytes = R * 8;
     L.nz_bytes = 8 + 20 * B;
@@ -369,7 +369,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
     const bool is_chain = (t == Tw);
     const int R = P.R, D = P.D, DN = P.DN, NT = P.NT, NR = P.NR;
     const int NV = P.NV;
-    const SmemLayout L = smem_layout(R, B, NT, DN, NR, NV);
+    const SmemLayout L = smem_layout(R, B, NT, DN, NR, NV, P.store2);
     // timing experiments only (results are garbage): 1 workers ignore the lists, 2 prep warps skip the accumulator poll,
     // 4 chain warp skips corrections + scalar updates, 8 workers skip the dots and the RED
     const int dbg = DBG ? P.debug : 0;
@@ -710,7 +710,10 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                         for (int i0 = 0; i0 < nnz; i0 += 4) {
                                             uint32_t w4[4];
 #pragma unroll
-                                            for (int u = 0; u < 4; ++u) w4[u] = (i0 + u < nnz) ? tw[word_off(B, nl.idx[i0 + u], rg)] : 0u;
+                                            for (int u = 0; u < 4; ++u)
+                                                w4[u] = (i0 + u >= nnz) ? 0u
+                                                      : P.store2 ? expand2((uint32_t)reinterpret_cast<const uint8_t*>(tw)[word_off(B, nl.idx[i0 + u], rg)])
+                                                                 : tw[word_off(B, nl.idx[i0 + u], rg)];
 #pragma unroll
                                             for (int u = 0; u < 4; ++u)
                                                 if (i0 + u < nnz) {
@@ -786,6 +789,24 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                 for (int mg = 0; mg < MG; ++mg)
 #pragma unroll
                                     for (int ch = 0; ch < CH; ++ch) { acc[mg][ch][0] = acc[mg][ch][1] = acc[mg][ch][2] = acc[mg][ch][3] = 0; }
+                                if (P.store2) {
+                                    // 2-bit tiles: one 32-bit word per lane and MMA atom, expanded to the four A registers on chip
+                                    const uint32_t* tile2 = reinterpret_cast<const uint32_t*>(tile);
+                                    for (int c0 = 0; c0 < nchunk; c0 += CH) {
+#pragma unroll
+                                        for (int ch = 0; ch < CH; ++ch) {
+                                            const int c = c0 + ch;
+                                            if (c < nchunk) {
+                                                const uint32_t b0 = lv[c * 64 + lane], b1 = lv[c * 64 + 32 + (lane ^ 4)];
+#pragma unroll
+                                                for (int mg = 0; mg < MG; ++mg) {
+                                                    const uint4 a = expand2_word(tile2[(c * MG + mg) * 32 + lane]);
+                                                    imma16832(acc[mg][ch], a, b0, b1);
+                                                }
+                                            }
+                                        }
+                                    }
+                                } else
                                 for (int c0 = 0; c0 < nchunk; c0 += CH) {
 #pragma unroll
                                     for (int ch = 0; ch < CH; ++ch) {

@@ -28,8 +28,8 @@ def oracle_chain(prob, method, v, pi=0.0, est_pi=False, region_off=None, v_e=Non
 
 
 def gpu_sampler(prob, method, v, pi=0.0, est_pi=False, region_off=None, v_e=None, lhs0=None, rhs0=None,
-                intercept=True, kernel="blocked", block=0, min_rows=0, max_ctas=0, upload="i8", **geom):
-    s = ngp.Sampler(0, kernel=kernel, block=block, min_rows=min_rows, max_ctas=max_ctas, **geom)
+                intercept=True, kernel="blocked", block=0, min_rows=0, max_ctas=0, upload="i8", storage="i8", **geom):
+    s = ngp.Sampler(0, kernel=kernel, block=block, min_rows=min_rows, max_ctas=max_ctas, storage=storage, **geom)
     if upload == "f64":
         s.upload_genotypes(0, prob["codes"].astype(np.float64))
     else:
