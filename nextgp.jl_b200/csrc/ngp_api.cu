@@ -297,7 +297,7 @@ struct ngp_handle {
     int64_t n = 0;
     int refetch = 0, store2 = -1;      // store2: device storage of ALL marker sets of the handle (-1 until the first upload)
     int Tw = 0, R = 0, B = 0, D = 0, DN = 0, NT = 0, NR = 0, NV = 0;      // worker CTAs (grid = Tw + 1), rows per panel, block, look-ahead, near depth, tile stages
-    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0, cfg_versions = 0, cfg_refetch = -1, cfg_opt = 3;
+    int cfg_kernel = NGP_KERNEL_BLOCKED, cfg_block = 0, cfg_min_rows = 128, cfg_max_ctas = 0, cfg_lookahead = 0, cfg_tile_stages = 0, cfg_near = 0, cfg_profile = 0, cfg_debug = 0, cfg_versions = 0, cfg_refetch = -1, cfg_opt = -1;     // cfg_opt -1: by tile-ring mode (resident: 3, refetch: 2 — refetched columns should still be in L2)
     SmemLayout L{};
     // model
     SetHost sets[NGP_MAX_SETS];
@@ -502,7 +502,7 @@ int ngp_configure(ngp_handle* h, int key, int64_t value)
     case NGP_CFG_PROFILE:
         h->cfg_profile = value ? 1 : 0; return NGP_OK;
     case NGP_CFG_OPT:
-        if (value < 0 || value > 0xffff) return fail(h, NGP_EINVAL, "ngp_configure: option mask out of range");
+        if (value < -1 || value > 0xffff) return fail(h, NGP_EINVAL, "ngp_configure: option mask out of range (-1 = auto)");
         h->cfg_opt = (int)value; return NGP_OK;
     case NGP_CFG_LOOKAHEAD:
         if (h->Tw) return fail(h, NGP_EINVAL, "ngp_configure: look-ahead must be set before the first upload");
@@ -541,11 +541,14 @@ static int choose_geometry(ngp_handle* h, int64_t n, int store2)
     Tw = (int)((n + R - 1) / R);                                    // no empty panels
     const size_t cap = h->prop.sharedMemPerBlockOptin;
     int B = h->cfg_block;
-    if (!B) B = (64 * R <= 12288) ? 64 : (32 * R <= 16384) ? 32 : 16;      // (2-bit storage: the same choice — the tiles are a quarter of the size)
-    const int64_t maxR = 4LL * kUpdThreads * (B == 16 ? kUpdGroups : 1);     // residual rows an updater warp group holds in registers
+    // Blocks of 64 markers halve the number of trips round the feedback loop (list -> residual version -> dots -> sums) against blocks of
+    // 32, and the chain warp steps over 64 markers anyway.  Panels of up to 512 rows: 2-bit tiles of 64 markers (16 R bytes) stay
+    // resident with 12 blocks of look-ahead; int8 tiles (64 R bytes) use the refetch ring.  Larger panels: blocks of 64 for 2-bit tiles (refetch ring), blocks of 16 for int8
+    // (sweeps in profiles/r2/tune_*.jsonl).
+    if (!B) B = (R <= 512 || store2) ? 64 : 16;
+    const int64_t maxR = 4LL * kUpdThreads * kUpdGroups;     // residual rows the updater warps hold in registers
     if (R > maxR)
-        return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA; block %d supports at most %lld (use block 16 for up to %d)",
-                    (long long)n, (long long)R, B, (long long)maxR, 4 * kUpdThreads * kUpdGroups);
+        return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA; at most %lld are supported", (long long)n, (long long)R, (long long)maxR);
     const int dn_min = 2 * ((B == 16 ? 32 : 64) / B) - 1;    // the chain warp steps over 64 markers (32 for blocks of 16): distances inside two steps come from the records
     // Two tile-ring modes.  resident: a tile stays in shared memory until its block has been applied to e (NT >= D + 2), so the rare
     // residual update reads it there.  refetch: a tile stays only until its dots are formed (NT = 8 / 4 / 2 / 1 stages, consumed by as many
@@ -553,7 +556,7 @@ static int choose_geometry(ngp_handle* h, int64_t n, int store2)
     // Small panels use resident; refetch is chosen when resident would leave fewer than kMinResidentD blocks of look-ahead.
     // defaults from the sweeps in profiles/r1/tune_*_r1j.jsonl (C2: D 14 / near 4 = 0.971 ms against 0.994 at D 13 / near 3; near 5 falls off a
     // cliff at 1.13 ms; C1 with blocks of 64: near 3 = 0.582 ms against 0.593 at near 1 in the sweep but no gain in bench.py, left at the minimum)
-    const int want_D = h->cfg_lookahead ? h->cfg_lookahead : (B == 64 ? 6 : B == 32 ? 14 : 20);
+    const int want_D = h->cfg_lookahead ? h->cfg_lookahead : (B == 64 ? (n < 20000 ? 6 : 12) : B == 32 ? 14 : 20);     // (few rows: the loop is short, look-ahead only costs corrections)
     constexpr int kMinResidentD = 10;
     auto search = [&](int refetch) -> bool {
         int DN = std::max(dn_min, h->cfg_near ? h->cfg_near : (B == 32 ? 4 : 0));
@@ -564,7 +567,7 @@ static int choose_geometry(ngp_handle* h, int64_t n, int store2)
             if (D < dn_min) break;
             DN = std::max(dn_min, std::min(DN, D));
             const int nt_min = refetch ? 1 : D + 2;
-            int NT = refetch ? legal_nt(h->cfg_tile_stages ? h->cfg_tile_stages : 8) : (h->cfg_tile_stages ? std::max(h->cfg_tile_stages, nt_min) : D + 4);
+            int NT = refetch ? legal_nt(h->cfg_tile_stages ? h->cfg_tile_stages : (B == 64 ? 4 : 8)) : (h->cfg_tile_stages ? std::max(h->cfg_tile_stages, nt_min) : D + 4);
             // shrink the record ring of the chain CTA, the tile ring, then the look-ahead, until both CTA roles fit
             for (;;) {
                 for (int NR = kRecStages; NR >= 2; NR >>= 1) {
@@ -1084,7 +1087,7 @@ static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int 
     P.mu_lhs0 = h->mu_lhs0; P.mu_rhs0 = h->mu_rhs0; P.varE_in = varE_in; P.n_iter = n_iter; P.replay = h->replay;
     P.replay_base = h->replay_base; P.rp_chi2_e = h->rp_chi2_e; P.rp_z_mu = h->rp_z_mu;
     P.key0 = (uint32_t)(h->seed & 0xffffffffu); P.key1 = (uint32_t)(h->seed >> 32); P.chain = h->chain; P.accumulate = accumulate;
-    P.debug = h->cfg_debug; P.opt = h->cfg_opt;
+    P.debug = h->cfg_debug; P.opt = h->cfg_opt >= 0 ? h->cfg_opt : (h->refetch ? 2 : 3);
     P.fx = h->fx; P.fx.rp_z = h->fx_rp_z;
     P.w = h->w; P.w_sum = h->w_sum; P.w_min = h->w_min; P.w_max = h->w_max;
     if (h->w && h->fx.n_cols && h->fx_w_ready) { P.fx.xpx = h->fx_xpx_w; P.fx.colsum_w = h->fx_colsum_w; }
@@ -1234,7 +1237,11 @@ static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, 
         if (((set_mask >> s) & 1) && h->sets[s].method == NGP_BAYESR) P.kernel = NGP_KERNEL_LITERAL;     // the class algebra lives in the per-marker sweep
     bool tuple_mask = false;
     for (int s = 0; s < h->n_sets; ++s) if (((set_mask >> s) & 1) && h->sets[s].group_k) tuple_mask = true;
-    const int variant = tuple_mask ? NGP_KV_TUP : (P.kernel == NGP_KERNEL_LITERAL) ? NGP_KV_LIT : h->cfg_debug ? NGP_KV_DBG : h->cfg_profile ? NGP_KV_PROF : NGP_KV_PLAIN;
+    int variant = tuple_mask ? NGP_KV_TUP : (P.kernel == NGP_KERNEL_LITERAL) ? NGP_KV_LIT : h->cfg_debug ? NGP_KV_DBG : h->cfg_profile ? NGP_KV_PROF : NGP_KV_PLAIN;
+    if (h->R > 4 * kUpdThreads && h->B != 16) {          // more than 512 rows per CTA with blocks of 32 / 64: the instantiation with 4 row groups per updater thread
+        if (variant != NGP_KV_PLAIN) return fail(h, NGP_EUNSUPPORTED, "%d rows per CTA with blocks of %d: only the plain blocked sweep is built for this geometry (use blocks of 16)", h->R, h->B);
+        variant = NGP_KV_BIGR;
+    }
     if (h->store2 > 0 && (variant == NGP_KV_LIT || variant == NGP_KV_TUP))
         return fail(h, NGP_EUNSUPPORTED, "2-bit device storage serves the blocked sweep of BayesPR / BayesB / BayesC sets (not the per-marker kernel: "
                                          "BayesR, weighted residuals, row sharding; not the tuple sampler): upload with NGP_STORE_I8");

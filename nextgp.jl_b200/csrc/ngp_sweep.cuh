@@ -351,7 +351,7 @@ __device__ __forceinline__ void joint_step(double (&rr)[NS], const double (&bold
 // LIT: the per-marker ("literal") sweep instead of the blocked one — a separate instantiation, so that neither variant carries the other's code
 // TUP: the instantiation that also sweeps a tuple of interleaved marker sets (method 4); kept apart so that the k x k algebra does not
 //      weigh on the register allocation of the single-trait sweep
-template <int B, bool PROF, bool DBG, bool LIT, bool TUP>
+template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false>
 __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -363,7 +363,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
     constexpr int RBS = kPrepWarps / SB;   // super-block slots of the r_base ring
     constexpr int kHelperWarp = kFirstPrepWarp + kPrepWarps;     // chain CTA: publishes the lists and writes the outputs
     constexpr int MG = B / 16;             // 16-marker MMA groups per block
-    constexpr int UG = (B == 16) ? kUpdGroups : 1;   // 4-row groups per updater thread (B = 32 / 64 are chosen for R <= 512)
+    constexpr int UG = (B == 16 || BIGR) ? kUpdGroups : 1;   // 4-row groups per updater thread: panels of up to 512 rows, or (blocks of 16 / the BIGR instantiation) 2048
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Tw = P.Tw;
     const bool is_chain = (t == Tw);
@@ -1720,10 +1720,10 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
 #undef NGP_TICK
 }
 
-template <int B, bool PROF, bool DBG, bool LIT, bool TUP>
+template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false>
 __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 {
-    gibbs_body<B, PROF, DBG, LIT, TUP>(P, (int)blockIdx.x);
+    gibbs_body<B, PROF, DBG, LIT, TUP, BIGR>(P, (int)blockIdx.x);
 }
 
 // All ranks of a row-sharded chain whose shards live on ONE device, as ONE cooperative grid (the only legal way to run kernels that wait

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--max_ctas", type=int, default=0)
     ap.add_argument("--refetch", type=int, default=-1)
     ap.add_argument("--min_rows", type=int, default=0)
+    ap.add_argument("--storage", default="i8")
     ap.add_argument("--opt", default="0", help="comma list of NGP_CFG_OPT masks, each run for every combo")
     a = ap.parse_args()
     n, p, model = CONFIGS[a.config]
@@ -35,7 +36,7 @@ def main():
         b, d, nt, dn, dbg, nv = (list(int(x) for x in combo.split(":")) + [0, 0])[:6]
         t0 = time.time()
         try:
-            s = ngp.Sampler(0, block=b, lookahead=d, tile_stages=nt, near=dn, max_ctas=a.max_ctas, refetch=a.refetch, min_rows=a.min_rows)
+            s = ngp.Sampler(0, block=b, lookahead=d, tile_stages=nt, near=dn, max_ctas=a.max_ctas, refetch=a.refetch, min_rows=a.min_rows, storage=a.storage)
             if nv:
                 s.configure(ngp._lib.CFG_VERSIONS, nv)
             if dbg:

@@ -156,7 +156,7 @@ def test_replay_parity_over_pipeline_geometries(gpu, geom):
 
 
 def test_replay_parity_many_rows_per_cta(gpu):
-    """Few CTAs => > 512 rows per worker CTA => blocks of 16 markers with 4 row groups per updater thread (the C5 / C3 geometry)."""
+    """Few CTAs => > 512 rows per worker CTA => 4 row groups per updater thread (the C5 / C3 geometry), for every block size."""
     prob = make_problem(3001, 150, 78)
     for method, kw in ((2, dict(v=0.05, pi=0.3, est_pi=True)), (1, dict(v=0.05, pi=0.3, est_pi=True)), (0, dict(v=0.02))):
         _run_replay(prob, method, kw, "blocked", iters=4, max_ctas=3)
@@ -164,8 +164,12 @@ def test_replay_parity_many_rows_per_cta(gpu):
     t = g.timing()
     assert t["block"] == 16 and t["rows_per_cta"] > 512 and t["ctas"] == 3
     g.close()
-    with pytest.raises(ngp.NgpError) as ei:        # rows do not fit the register-resident residual of a 32-marker-block CTA
-        gpu_sampler(prob, 2, 0.05, pi=0.3, est_pi=True, max_ctas=3, block=32)
+    for block in (32, 64):
+        _run_replay(prob, 2, dict(v=0.05, pi=0.3, est_pi=True), "blocked", iters=4, max_ctas=3, block=block)
+        _run_replay(prob, 0, dict(v=0.02), "blocked", iters=3, max_ctas=3, block=block)
+    big = make_problem(8300, 40, 79)
+    with pytest.raises(ngp.NgpError) as ei:        # more rows than the updater warps hold in registers
+        gpu_sampler(big, 2, 0.05, pi=0.3, est_pi=True, max_ctas=3)
     assert ei.value.code == L.EUNSUPPORTED
 
 
@@ -498,9 +502,12 @@ def _native_vs_oracle_at_scale(n, p, model, iters, seed, expect=None, tol=1e-7, 
 
 def test_oracle_parity_at_headline_rows_bayescpi(gpu):
     """BASELINE config 2 rows: n = 50,000 x 2,000 markers BayesCpi (functions.jl:197-236), default geometry of the headline run
-    (blocks of 32, 352 rows per CTA, look-ahead 14), native stream, 3 iterations against the oracle to 1e-7."""
+    (blocks of 64, 352 rows per CTA, refetch ring, look-ahead 12), native stream, 3 iterations against the oracle to 1e-7; also with
+    the round-1 geometry (blocks of 32, resident tiles, look-ahead 14) and with 2-bit storage."""
     _native_vs_oracle_at_scale(50000, 2000, "BayesC", 3, 20261020,
-                               expect=dict(block=32, rows_per_cta=352, lookahead=14, ctas=lambda c: c >= 140))
+                               expect=dict(block=64, rows_per_cta=352, lookahead=12, ctas=lambda c: c >= 140))
+    _native_vs_oracle_at_scale(50000, 2000, "BayesC", 2, 20261020, block=32, expect=dict(block=32, lookahead=14))
+    _native_vs_oracle_at_scale(50000, 2000, "BayesC", 2, 20261020, storage="2bit", expect=dict(block=64, lookahead=12))
 
 
 def test_oracle_parity_at_c5_geometry_refetch_ring(gpu):
@@ -508,8 +515,12 @@ def test_oracle_parity_at_c5_geometry_refetch_ring(gpu):
     tiles leave shared memory after their dots (refetch ring) and changed columns are re-read from L2."""
     _native_vs_oracle_at_scale(200000, 512, "BayesC", 3, 20261021,
                                expect=dict(block=16, rows_per_cta=lambda r: r >= 1376, ctas=lambda c: c >= 140))
+    # the same rows as 2-bit tiles: blocks of 64, 4 row groups per updater thread (the BIGR instantiation), refetch ring
+    _native_vs_oracle_at_scale(200000, 512, "BayesC", 2, 20261021, storage="2bit",
+                               expect=dict(block=64, rows_per_cta=lambda r: r >= 1376))
 
 
 def test_oracle_parity_at_c3_geometry_bayesb(gpu):
     """BASELINE config 3 rows: n = 100,000 x 512 markers BayesB (functions.jl:157-195): blocks of 16, 704 rows per CTA."""
     _native_vs_oracle_at_scale(100000, 512, "BayesB", 3, 20261022, expect=dict(block=16, rows_per_cta=704))
+    _native_vs_oracle_at_scale(100000, 512, "BayesB", 2, 20261022, storage="2bit", expect=dict(block=64, rows_per_cta=704))
