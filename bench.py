@@ -48,8 +48,10 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def workload_name(cfg, n, p, model, storage="i8"):
+def workload_name(cfg, n, p, model, storage="i8", regions=0):
     st = "2-bit packed" if storage == "2bit" else "int8"
+    if regions and model in ("BayesPR", "BayesRR"):
+        model = f"BayesPR({regions}) region-wise variances"
     if model.startswith("MultiBreed"):
         return f"{cfg}: {n} individuals x {p} SNPs, {model[10:]}-breed tuple BayesPR (joint effects per locus) + intercept, {st} genotypes in HBM"
     return f"{cfg}: {n} individuals x {p} SNPs single-trait {model}{'pi' if model == 'BayesC' else ''} + intercept, {st} genotypes in HBM"
@@ -247,6 +249,7 @@ def main():
     ap.add_argument("--p", type=int, default=0)
     ap.add_argument("--model", default="BayesC")
     ap.add_argument("--storage", default="i8", choices=["i8", "2bit"], help="device storage of the genotype codes (2bit: NGP_STORE_2BIT, a quarter of the HBM bytes per sweep)")
+    ap.add_argument("--regions", type=int, default=0, help="BayesPR with one variance per window of this many SNPs (BayesPR(r, v): mme.jl:345-348, misc.jl:163-215) on 30 equal chromosomes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--weighted", action="store_true",
                     help="diagnostic: residual weights w ~ U(0.5, 2) (E.str == \"D\", mme.jl:70-73); the set is swept by the per-marker kernel")
@@ -319,8 +322,13 @@ def main():
         args.no_e2e = True
     else:
         s.synth_genotypes(0, n, p, seed, prob["thr0"], prob["thr1"])       # every rank: same X, generated on device
+    region_off = None
+    if args.regions and method == 0:
+        chrom = -(-p // 30)                         # 30 equal chromosomes; windows never span two chromosomes
+        edges = sorted({min(p, c0 + w) for c0 in range(0, p, chrom) for w in range(0, chrom + args.regions, args.regions)} | {0, p})
+        region_off = np.array(edges, dtype=np.int64)
     if not kbreeds:
-        s.set_prior(0, method, df, scale, v, pi_in=pi, est_pi=(method == 2))
+        s.set_prior(0, method, df, scale, v, pi_in=pi, est_pi=(method == 2), region_off=region_off)
     s.set_phenotype(y)
     s.set_residual_prior(4.0, v_e * 0.5)
     if args.weighted:
@@ -451,7 +459,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "marker-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": workload_name(args.config, n, p, model, args.storage) + (" [diagnostic: weighted residuals E.str == \"D\", per-marker kernel]" if args.weighted else ""), "kernel": ("blocked tuple sweep (interleaved copy, joint draw in the chain warp)" if args.kernel == "blocked" and kbreeds in (2, 4) else "joint (per locus)") if kbreeds else args.kernel, "chains": nchains,
+                "config": {"workload": workload_name(args.config, n, p, model, args.storage, args.regions) + (" [diagnostic: weighted residuals E.str == \"D\", per-marker kernel]" if args.weighted else ""), "kernel": ("blocked tuple sweep (interleaved copy, joint draw in the chain warp)" if args.kernel == "blocked" and kbreeds in (2, 4) else "joint (per locus)") if kbreeds else args.kernel, "chains": nchains,
                            "parallelism": (f"ONE chain row-sharded over {world} GPUs: per-marker fixed-point reduction pushed into every rank's "
                                            f"accumulators over NVLink peer memory (CUDA IPC), identical draw on every rank")
                                           if sharded else f"{world} independent chain(s), one per GPU, no data-path collective",

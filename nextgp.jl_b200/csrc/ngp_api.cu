@@ -1233,16 +1233,26 @@ static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, 
     P = Params{};
     fill_params(h, P, n_iter, set_mask, do_varE, do_mu, varE_in, accumulate);
     if (h->w) P.kernel = NGP_KERNEL_LITERAL;            // weighted dots are not integer sums of codes: per-marker sweep
+    // BayesR: the blocked sweep has its own instantiation (class algebra per lane in the chain warp) for <= 4 classes without summary-statistic
+    // priors, when every set of the launch is BayesR; anything else goes to the per-marker sweep
+    bool any_r = false, all_r = true, r_ok = true;
     for (int s = 0; s < h->n_sets; ++s)
-        if (((set_mask >> s) & 1) && h->sets[s].method == NGP_BAYESR) P.kernel = NGP_KERNEL_LITERAL;     // the class algebra lives in the per-marker sweep
+        if ((set_mask >> s) & 1) {
+            const SetHost& S = h->sets[s];
+            if (S.method == NGP_BAYESR) { any_r = true; if (S.n_class > 4 || S.lhs0 || S.rhs0) r_ok = false; } else all_r = false;
+        }
+    const bool r_blocked = any_r && all_r && r_ok && P.kernel == NGP_KERNEL_BLOCKED && !h->w && !sharded && !h->cfg_debug && !h->cfg_profile &&
+                           !(h->R > 4 * kUpdThreads && h->B != 16);
+    if (any_r && !r_blocked) P.kernel = NGP_KERNEL_LITERAL;
     bool tuple_mask = false;
     for (int s = 0; s < h->n_sets; ++s) if (((set_mask >> s) & 1) && h->sets[s].group_k) tuple_mask = true;
     int variant = tuple_mask ? NGP_KV_TUP : (P.kernel == NGP_KERNEL_LITERAL) ? NGP_KV_LIT : h->cfg_debug ? NGP_KV_DBG : h->cfg_profile ? NGP_KV_PROF : NGP_KV_PLAIN;
+    if (r_blocked) variant = NGP_KV_R;
     if (h->R > 4 * kUpdThreads && h->B != 16) {          // more than 512 rows per CTA with blocks of 32 / 64: the instantiation with 4 row groups per updater thread
         if (variant != NGP_KV_PLAIN) return fail(h, NGP_EUNSUPPORTED, "%d rows per CTA with blocks of %d: only the plain blocked sweep is built for this geometry (use blocks of 16)", h->R, h->B);
         variant = NGP_KV_BIGR;
     }
-    if (h->store2 > 0 && (variant == NGP_KV_LIT || variant == NGP_KV_TUP))
+    if (h->store2 > 0 && (variant == NGP_KV_LIT || variant == NGP_KV_TUP))   // (the blocked BayesR sweep reads 2-bit tiles like the plain one)
         return fail(h, NGP_EUNSUPPORTED, "2-bit device storage serves the blocked sweep of BayesPR / BayesB / BayesC sets (not the per-marker kernel: "
                                          "BayesR, weighted residuals, row sharding; not the tuple sampler): upload with NGP_STORE_I8");
     kfn = ngp_gibbs_kernel(h->B, group ? NGP_KV_GROUP : variant);

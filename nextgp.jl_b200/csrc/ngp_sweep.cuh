@@ -201,7 +201,15 @@ __device__ __forceinline__ void prep_marker(const Params& P, const SetDev& S, in
         } else if (S.method == 4) {
             fC = 0.0; fQSZ = z; fT = (double)(S.region_of ? S.region_of[j] : 0);     // the joint solve runs in the chain warp: variate + region index
         } else {
-            fC = 0.0; fQSZ = z;   // BayesR (per-marker kernel only): F_QSZ carries the normal variate, the class algebra runs in the sweep
+            // BayesR: F_QSZ carries the normal variate, the class algebra runs in the sweep.  The blocked sweep (<= 4 classes) also finds the
+            // uniforms of the cumulative comparisons (a fresh one per comparison, functions.jl:261) here: F_A, F_B, F_T, F_C = u_0 .. u_3
+            fC = 0.0; fQSZ = z;
+            if (S.n_class <= 4) {
+                double uv[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int v = 0; v < S.n_class; ++v)
+                    uv[v] = P.replay ? S.rp_u[(rp_row * S.p + j) * S.n_class + v] : stream_uniform(st, P_U, (uint32_t)j, 0, (uint32_t)v);
+                fA = uv[0]; fB = uv[1]; fT = uv[2]; fC = uv[3];
+            }
         }
     }
     c[F_A * B] = fA; c[F_B * B] = fB; c[F_T * B] = fT; c[F_C * B] = fC; c[F_QSZ * B] = fQSZ;
@@ -351,7 +359,7 @@ __device__ __forceinline__ void joint_step(double (&rr)[NS], const double (&bold
 // LIT: the per-marker ("literal") sweep instead of the blocked one — a separate instantiation, so that neither variant carries the other's code
 // TUP: the instantiation that also sweeps a tuple of interleaved marker sets (method 4); kept apart so that the k x k algebra does not
 //      weigh on the register allocation of the single-trait sweep
-template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false>
+template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false, bool BR = false>
 __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -643,6 +651,16 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
             const int nblk = (int)(S.p_pad / B);
             const double inv_n = 1.0 / (double)P.n_total;
             const int method = S.method;
+            // BayesR in the blocked sweep (the BR instantiation): class variances, log proportions (uniform)
+            double br_varc[4] = {0.0, 0.0, 0.0, 0.0}, br_logpi[4] = {0.0, 0.0, 0.0, 0.0}, br_vcls[4] = {1.0, 1.0, 1.0, 1.0};
+            const int br_nc = BR ? S.n_class : 0;
+            const double br_iVarE = 1.0 / varE;
+            bool br_bad = false;
+            if constexpr (BR) {
+                const double vb0 = __ldcg(&S.varBeta[0]);
+                for (int v = 0; v < 4; ++v)
+                    if (v < br_nc) { br_vcls[v] = S.v_class[v]; br_varc[v] = vb0 * S.v_class[v]; br_logpi[v] = __ldcg(&S.pi_class[br_nc + v]); }      // functions.jl:244
+            }
             const int64_t p_real = S.p;
             double acc_bb = 0.0, acc_n = 0.0;          // chain warp: per-lane partials of beta'beta and nLoci
             double acc_cls = 0.0;                      // BayesR: loci assigned to class `lane`
@@ -1011,6 +1029,25 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                 cC[i] = cst[i][F_C * B]; cQ[i] = cst[i][F_QSZ * B];
                                 bnew[i] = 0.0; inc[i] = false; bnz[i] = bold[i] != 0.0;
                             }
+                            // BayesR (functions.jl:238-289), classes v < nc <= 4: everything of the class likelihoods that does not depend on the running
+                            // dot, per marker:  1/lhs_v  and  A_v = -0.5 log(varc_v lhs_v) + logPi_v  (a class of variance 0: 1/lhs = 0, A = logPi)
+                            double r_il[BR ? NS : 1][4], r_A[BR ? NS : 1][4];
+                            int ocls[NS];
+                            if constexpr (BR) {
+#pragma unroll
+                                for (int i = 0; i < NS; ++i) {
+                                    const double dj = cst[i][F_D * B];
+#pragma unroll
+                                    for (int v = 0; v < 4; ++v) {
+                                        const double vc = br_varc[v];
+                                        const bool zero = !(v < br_nc) || vc == 0.0;
+                                        const double lhs_v = fma(dj, br_iVarE, 1.0 / vc);
+                                        r_il[i][v] = zero ? 0.0 : 1.0 / lhs_v;
+                                        r_A[i][v] = (v < br_nc) ? (zero ? br_logpi[v] : fma(-0.5, log(vc * lhs_v), br_logpi[v])) : -INFINITY;
+                                    }
+                                    ocls[i] = 0;
+                                }
+                            }
                             NGP_TICK(4);
                             // cross-Gram corrections from the blocks of the previous step (distances 1 .. 2 SB - 1 <= DN), oldest first
                             if (s0 > 0 && !(dbg & 4)) {
@@ -1106,10 +1143,34 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                 bool inv[NS];
                                 unsigned mk[NS];
 #pragma unroll
+                                int clsv[NS];
+#pragma unroll
                                 for (int i = 0; i < NS; ++i) {
+                                    clsv[i] = 0;
+                                    if constexpr (BR) {
+                                        // class likelihoods exp(A_v + rhs^2 / (2 lhs_v)), proportions in class order, first class whose cumulative
+                                        // probability reaches ITS uniform (functions.jl:250-262); beta from the class's lhs (functions.jl:266-275)
+                                        const double rhs = rr[i] * br_iVarE, hq = 0.5 * rhs * rhs;
+                                        const double uu[4] = {cA[i], cB[i], cT[i], cC[i]};
+                                        double ex[4], tot = 0.0;
+#pragma unroll
+                                        for (int v = 0; v < 4; ++v) { ex[v] = (v < br_nc) ? exp(fma(hq, r_il[i][v], r_A[i][v])) : 0.0; tot += ex[v]; }
+                                        double cum = 0.0, ilc = 0.0;
+                                        int cls = -1;
+#pragma unroll
+                                        for (int v = 0; v < 4; ++v) {
+                                            cum += ex[v] / tot;
+                                            if (cls < 0 && v < br_nc && cum >= uu[v]) { cls = v; ilc = r_il[i][v]; }
+                                        }
+                                        if (cls < 0) { if (32 * i + lane >= pos && bold[i] == bold[i]) br_bad = true; cls = 0; ilc = r_il[i][0]; }
+                                        clsv[i] = cls;
+                                        bnv[i] = (ilc != 0.0) ? fma(rhs, ilc, sqrt(ilc) * cQ[i]) : 0.0;
+                                        inv[i] = true;
+                                    } else {
                                     const double dl = fma(cB[i], rr[i] * rr[i], cA[i]);
                                     bnv[i] = fma(rr[i], cC[i], cQ[i]);                  // evaluated alongside the inclusion test
                                     inv[i] = dl < cT[i];                                // NaN -> excluded, like rand() < NaN
+                                    }
                                     const bool ch = inv[i] ? (bnv[i] != bold[i]) : bnz[i];      // effect changes <=> beta_new - beta_old != 0
                                     mk[i] = __ballot_sync(0xffffffffu, (32 * i + lane >= pos) && ch);
                                 }
@@ -1120,7 +1181,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
 #pragma unroll
                                 for (int i = 0; i < NS; ++i) {
                                     const int mi = 32 * i + lane;
-                                    if (mi >= pos && mi <= last) { bnew[i] = inv[i] ? bnv[i] : 0.0; inc[i] = inv[i]; }
+                                    if (mi >= pos && mi <= last) { bnew[i] = inv[i] ? bnv[i] : 0.0; inc[i] = inv[i]; if constexpr (BR) ocls[i] = clsv[i]; }
                                 }
                                 if (!mm) break;
                                 const double mydb = ci ? ((inv[NS - 1] ? bnv[NS - 1] : 0.0) - bold[NS - 1]) : ((inv[0] ? bnv[0] : 0.0) - bold[0]);
@@ -1147,10 +1208,11 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                 pos = last + 1;
                             }
                             NGP_TICK(17);
+                            if constexpr (BR) { if (br_bad) { atomicOr(&sy->err, 4); br_bad = false; } }       // findfirst found nothing: the reference throws here
                             // hand the step over: lists (prep warps, helper warp), new effects and indicators (helper warp)
                             const int os = (int)(sg & (kPrepWarps - 1));
 #pragma unroll
-                            for (int i = 0; i < NS; ++i) { out_b[os * 64 + 32 * i + lane] = bnew[i]; out_i[os * 64 + 32 * i + lane] = inc[i] ? 1 : 0; }
+                            for (int i = 0; i < NS; ++i) { out_b[os * 64 + 32 * i + lane] = bnew[i]; out_i[os * 64 + 32 * i + lane] = BR ? ocls[i] : (inc[i] ? 1 : 0); }
                             if (lane == 0) {
 #pragma unroll
                                 for (int k = 0; k < SB; ++k) cnz[(g0 + (unsigned)k) & (kNzRing - 1)].nnz = nn[k];
@@ -1409,6 +1471,25 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                 const unsigned gk = g0 + (unsigned)kb[i];
                                 const int64_t j = (int64_t)(s0 + kb[i]) * B + qb[i];
                                 const double bn = out_b[os * 64 + 32 * i + lane];
+                                if constexpr (BR) {
+                                    // BayesR: delta = class (1-based, functions.jl:263), nLoci per class, sumS = sum beta^2 / vClass and the
+                                    // number of loci in classes of non-zero variance (functions.jl:264-273)
+                                    const int cls = out_i[os * 64 + 32 * i + lane];
+                                    const bool real = j < p_real;
+#pragma unroll
+                                    for (int v = 0; v < 4; ++v) {
+                                        const unsigned mv = __ballot_sync(0xffffffffu, real && cls == v);
+                                        if (lane == v) acc_cls += (double)__popc(mv);
+                                    }
+                                    if (real) {
+                                        double vcl = br_vcls[0], vcc = br_varc[0];
+#pragma unroll
+                                        for (int v = 1; v < 4; ++v) if (cls == v) { vcl = br_vcls[v]; vcc = br_varc[v]; }
+                                        if (vcc != 0.0) { acc_bb += (bn * bn) / vcl; acc_n += 1.0; }
+                                        beta_g[j] = bn; delta_g[j] = cls + 1;
+                                    }
+                                    continue;
+                                }
                                 const bool in = out_i[os * 64 + 32 * i + lane] != 0;
                                 acc_bb = fma(bn, bn, acc_bb);
                                 if (method != 0) acc_n += in ? 1.0 : 0.0;
@@ -1720,10 +1801,10 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
 #undef NGP_TICK
 }
 
-template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false>
+template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false, bool BR = false>
 __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 {
-    gibbs_body<B, PROF, DBG, LIT, TUP, BIGR>(P, (int)blockIdx.x);
+    gibbs_body<B, PROF, DBG, LIT, TUP, BIGR, BR>(P, (int)blockIdx.x);
 }
 
 // All ranks of a row-sharded chain whose shards live on ONE device, as ONE cooperative grid (the only legal way to run kernels that wait
