@@ -33,6 +33,7 @@ CONFIGS = {
     "c5": (200000, 50000, "BayesC"),
     "tiny": (2000, 4096, "BayesC"),
     "c4rr": (30000, 100000, "BayesRR"),     # diagnostic: dense updates at the size of the interleaved C4 tuple
+    "c2r": (50000, 50000, "BayesR"),        # BayesR (4 variance classes, Dirichlet-updated proportions) at the headline shape
 }
 SEED0 = 20261018
 METRIC = "marker-updates/sec"
@@ -283,9 +284,14 @@ def main():
 
     n, p, model = CONFIGS[args.config] if not args.n else (args.n, args.p, args.model)
     seed = SEED0 + 2
-    prob = ngp.synth.problem(n, p, seed)
+    # (BayesR: a polygenic trait, p / 10 causal loci — the reference's class likelihoods overflow for a locus of chi-square > ~1400, functions.jl:255)
+    prob = ngp.synth.problem(n, p, seed, q=(p // 10 if model == "BayesR" else None))
     v_e, v, pi = ngp.synth.priors(prob, "BayesRR" if model.startswith("MultiBreed") else model)
-    method = 0 if model in ("BayesRR", "BayesPR") else (1 if model == "BayesB" else 2)
+    method = 0 if model in ("BayesRR", "BayesPR") else (1 if model == "BayesB" else 3 if model == "BayesR" else 2)
+    r_vclass, r_pi = np.array([0.0, 1e-4, 1e-3, 1e-2]), np.array([0.95, 0.02, 0.02, 0.01])
+    if method == 3:
+        v = prob["var_y"] / 2.0                   # BayesR: the class variances are fractions of the genetic variance
+        args.no_cpu = True                      # (the timed CPU port covers BayesPR / BayesB / BayesC)
 
     sharded = args.sharded and world > 1
     kbreeds = int(model[10:]) if model.startswith("MultiBreed") else 0
@@ -328,7 +334,10 @@ def main():
         edges = sorted({min(p, c0 + w) for c0 in range(0, p, chrom) for w in range(0, chrom + args.regions, args.regions)} | {0, p})
         region_off = np.array(edges, dtype=np.int64)
     if not kbreeds:
-        s.set_prior(0, method, df, scale, v, pi_in=pi, est_pi=(method == 2), region_off=region_off)
+        if method == 3:
+            s.set_prior(0, method, df, v * 0.5, v, est_pi=True, v_class=r_vclass, pi_class=r_pi)
+        else:
+            s.set_prior(0, method, df, scale, v, pi_in=pi, est_pi=(method == 2), region_off=region_off)
     s.set_phenotype(y)
     s.set_residual_prior(4.0, v_e * 0.5)
     if args.weighted:

@@ -193,6 +193,10 @@ typedef struct ngp_timing {
     int32_t block, rows_per_cta; /* markers per block, rows per CTA panel                        */
     int64_t smem_bytes;
     int32_t lookahead, near_depth, tile_stages, record_stages;
+    int32_t kernel_variant;      /* sweep kernel of the last launch: 0 blocked, 1 instrumented, 2 timing experiments, 3 per-marker (chosen by the library for */
+                                 /* weighted residuals, summary-statistic BayesR, > 4 BayesR classes, row sharding), 4 tuple, 5 shard group, 6 blocked     */
+                                 /* with > 512 rows per CTA, 7 blocked BayesR; -1 none yet                                                                */
+    int32_t refetch, storage_2bit, pad_;   /* tile-ring mode, device storage of the genotypes */
 } ngp_timing;
 
 /* ---- lifetime ------------------------------------------------------------ */

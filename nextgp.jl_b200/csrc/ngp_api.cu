@@ -341,6 +341,7 @@ struct ngp_handle {
     const void* ready_kfn = nullptr;     // sweep-kernel variant whose launch attributes are set
     // stats
     int64_t launches = 0;
+    int last_variant = -1;      // kernel variant of the last launch (ngp_timing.kernel_variant)
     uint64_t gblk = 0;          // blocks swept so far by the blocked kernel (numbers the list words and accumulator slots)
     bool timed = false;
 };
@@ -1256,6 +1257,7 @@ static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, 
         return fail(h, NGP_EUNSUPPORTED, "2-bit device storage serves the blocked sweep of BayesPR / BayesB / BayesC sets (not the per-marker kernel: "
                                          "BayesR, weighted residuals, row sharding; not the tuple sampler): upload with NGP_STORE_I8");
     kfn = ngp_gibbs_kernel(h->B, group ? NGP_KV_GROUP : variant);
+    h->last_variant = group ? NGP_KV_GROUP : variant;
     if (group && variant != NGP_KV_LIT) return fail(h, NGP_EUNSUPPORTED, "ngp_run_group runs the per-marker kernel only");
     if (!group && h->ready_kfn != kfn) {                      // once per kernel variant: attribute + co-residency check of the cooperative grid
         // the attribute belongs to the function, not to the handle: always the device maximum, so that handles with different
@@ -1867,6 +1869,7 @@ int ngp_get_timing(ngp_handle* h, ngp_timing* out)
     memset(out, 0, sizeof *out);
     out->launches = h->launches; out->ctas = h->Tw ? h->Tw + 1 : 0; out->threads = kThreads; out->block = h->B; out->rows_per_cta = h->R;
     out->smem_bytes = h->L.total; out->lookahead = h->D; out->near_depth = h->DN; out->tile_stages = h->NT; out->record_stages = h->NR;
+    out->kernel_variant = h->last_variant; out->refetch = h->refetch; out->storage_2bit = h->store2 > 0;
     if (h->timed) {
         float ms = 0.f;
         CU(cudaEventSynchronize(h->ev1));

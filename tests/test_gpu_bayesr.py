@@ -1,6 +1,7 @@
 """GPU parity of BayesR (functions.jl:238-289) through the C ABI against the CPU oracle (ngo_r_sweep): native Philox
 chains, replayed variates (one uniform per cumulative comparison), fixed and Dirichlet-updated class proportions, the sweep-level
-plugin call.  BayesR is sampled by the per-marker kernel whatever NGP_CFG_KERNEL says."""
+plugin call.  BayesR with <= 4 classes and no summary-statistic prior is swept by the blocked kernel's BayesR instantiation (class algebra
+per lane in the chain warp: ngp_timing.kernel_variant == 7); more classes, summary statistics or NGP_KERNEL_LITERAL: the per-marker kernel."""
 import numpy as np
 import pytest
 
@@ -45,7 +46,94 @@ def test_bayesr_native_chain_matches_oracle(gpu, n, p, kw, est_pi):
     assert rel(st["sets"][0]["beta"], R.beta) < 1e-8 and rel(st["sets"][0]["varBeta"], R.varBeta) < 1e-8
     assert rel(st["sets"][0]["piHat"], R.piHat) < 1e-9 and rel(st["e"], ch.e) < 1e-8
     assert abs(st["varE"] / ch.varE - 1) < 1e-9
+    assert g.timing()["kernel_variant"] == (3 if kw.get("kernel") == "literal" else 7)
     g.close()
+
+
+@pytest.mark.parametrize("storage,block", [("i8", 32), ("2bit", 0), ("i8", 16)])
+def test_bayesr_blocked_sweep_geometries_and_many_classes(gpu, storage, block):
+    """the blocked BayesR sweep over block sizes and 2-bit tiles; 5 classes fall back to the per-marker kernel with the same results"""
+    prob = make_problem(1300, 260, 35)
+    ch, R, g = _pair(prob, 0.5, True, storage=storage, block=block, min_rows=8)
+    g.set_rng(4, 2)
+    for _ in range(5):
+        ch.iteration(seed=4, chain=2)
+        R.sweep(ch.e, ch.varE, it=ch.iter, seed=4, chain=2)
+    g.run(5)
+    st = g.state()
+    assert g.timing()["kernel_variant"] == 7
+    assert np.array_equal(st["sets"][0]["delta"], R.delta) and rel(st["sets"][0]["beta"], R.beta) < 1e-8 and rel(st["e"], ch.e) < 1e-8
+    assert rel(st["sets"][0]["piHat"], R.piHat) < 1e-9 and rel(st["sets"][0]["varBeta"], R.varBeta) < 1e-8
+    g.close()
+    if storage == "i8" and block == 32:
+        v5, p5 = np.array([0.0, 1e-5, 1e-4, 1e-3, 1e-2]), np.array([0.7, 0.1, 0.1, 0.07, 0.03])
+        ch, R, g = _pair(prob, 0.5, True, v_class=v5, pi=p5)
+        g.set_rng(4, 2)
+        for _ in range(3):
+            ch.iteration(seed=4, chain=2)
+            R.sweep(ch.e, ch.varE, it=ch.iter, seed=4, chain=2)
+        g.run(3)
+        st = g.state()
+        assert g.timing()["kernel_variant"] == 3
+        assert np.array_equal(st["sets"][0]["delta"], R.delta) and rel(st["sets"][0]["beta"], R.beta) < 1e-8
+        g.close()
+
+
+def test_bayesr_at_headline_rows(gpu):
+    """n = 50,000 x 1,024 markers, device-generated genotypes, blocked BayesR sweep against the oracle (native stream, 3 iterations).
+    400 causal loci: the reference's class likelihoods exp(rhs^2 / 2 lhs) (functions.jl:255-256, no log-sum-exp) overflow for a locus whose
+    chi-square exceeds ~1400, which at n = 50,000 is any locus explaining > 3 % of the variance — oracle and GPU both report that case as
+    the error the reference would throw (test_bayesr_overflow_is_reported_like_the_reference)."""
+    n, p, seed = 50000, 1024, 20261024
+    pr = ngp.synth.problem(n, p, seed, q=400)
+    codes = O.synth_codes(seed, n, 0, p, pr["thr0"], pr["thr1"])
+    X, _, mpm = O.center_codes(codes)
+    del codes
+    v = pr["var_y"] / 2
+    R = O.BayesROracle(X, mpm, PI0, VCLASS, v=v, est_pi=True)
+    ch = O.OracleChain(pr["y"], [], v_e=pr["var_y"] / 2, intercept=True)
+    g = ngp.Sampler(0)
+    g.synth_genotypes(0, n, p, seed, pr["thr0"], pr["thr1"])
+    g.set_prior(0, L.BAYESR, *O.marker_hyper(v), v, est_pi=True, v_class=VCLASS, pi_class=PI0)
+    g.set_phenotype(pr["y"]); g.set_residual_prior(*O.residual_hyper(pr["var_y"] / 2)); g.set_intercept(True)
+    g.set_rng(seed, 1)
+    O.set_threads(max(1, len(__import__("os").sched_getaffinity(0))))
+    try:
+        for it in range(3):
+            ch.iteration(seed=seed, chain=1)
+            R.sweep(ch.e, ch.varE, it=ch.iter, seed=seed, chain=1)
+            g.run(1)
+            st = g.state()
+            assert np.array_equal(st["sets"][0]["delta"], R.delta), f"class mismatch at iteration {it + 1}"
+            assert rel(st["sets"][0]["beta"], R.beta) < 1e-7 and rel(st["e"], ch.e) < 1e-7 and abs(st["varE"] / ch.varE - 1) < 1e-8
+    finally:
+        O.set_threads(1)
+    assert g.timing()["kernel_variant"] == 7 and g.timing()["block"] == 64
+    g.close()
+
+
+def test_bayesr_overflow_is_reported_like_the_reference(gpu):
+    """a locus with a huge chi-square: every class likelihood is +Inf, the proportions are NaN and `findfirst` finds no class — the
+    reference throws (functions.jl:261-262); the oracle returns its error code and the library NGP_ENUMERIC, on both kernels"""
+    n, p, seed = 20000, 256, 20261025
+    pr = ngp.synth.problem(n, p, seed, q=3)
+    codes = O.synth_codes(seed, n, 0, p, pr["thr0"], pr["thr1"])
+    X, _, mpm = O.center_codes(codes)
+    y = pr["y"] - pr["y"].mean()
+    R = O.BayesROracle(X, mpm, PI0, VCLASS, v=pr["var_y"] / 2, est_pi=True)
+    ch = O.OracleChain(y, [], v_e=pr["var_y"] / 2, intercept=True)
+    ch.iteration(seed=1, chain=0)
+    with pytest.raises(AssertionError):
+        R.sweep(ch.e, ch.varE, it=1, seed=1, chain=0)
+    for kernel in ("blocked", "literal"):
+        g = ngp.Sampler(0, kernel=kernel)
+        g.upload_genotypes(0, codes)
+        g.set_prior(0, L.BAYESR, *O.marker_hyper(pr["var_y"] / 2), pr["var_y"] / 2, est_pi=True, v_class=VCLASS, pi_class=PI0)
+        g.set_phenotype(y); g.set_residual_prior(*O.residual_hyper(pr["var_y"] / 2)); g.set_intercept(True); g.set_rng(1, 0)
+        with pytest.raises(ngp.NgpError) as ei:
+            g.run(1)
+        assert ei.value.code == L.ENUMERIC
+        g.close()
 
 
 def test_bayesr_replay_and_sweep_level_call(gpu):
