@@ -166,6 +166,10 @@ function runSampler_b200!(h, ycorr, nData, E, X, b, Z, u, varU, M, beta, varBeta
     check(h, ccall((:ngp_set_rng, libngp), Cint, (Ptr{Cvoid}, UInt64, UInt32), h, seed, chain))
     these2Keep = collect((burnIn + outputFreq):outputFreq:chainLength)
     done = 0
+    if burnIn > 0     # the device's posterior sums (ngp_get_posterior) count EVERY iteration since the last reset: start them after burn-in
+        check(h, ccall((:ngp_run, libngp), Cint, (Ptr{Cvoid}, Int32), h, burnIn)); done = burnIn
+        check(h, ccall((:ngp_reset_posterior, libngp), Cint, (Ptr{Cvoid},), h))
+    end
     for it in these2Keep
         check(h, ccall((:ngp_run, libngp), Cint, (Ptr{Cvoid}, Int32), h, it - done)); done = it
         st = NgpState(nData, length(sets), 0, pointer(ycorr), 0.0, 0.0, 0,

@@ -341,6 +341,7 @@ struct ngp_handle {
     const void* ready_kfn = nullptr;     // sweep-kernel variant whose launch attributes are set
     // stats
     int64_t launches = 0;
+    int* err_pinned = nullptr;  // pinned landing place of the kernel's error word: copied on the stream right behind the launch, ONE synchronisation per run
     int last_variant = -1;      // kernel variant of the last launch (ngp_timing.kernel_variant)
     uint64_t gblk = 0;          // blocks swept so far by the blocked kernel (numbers the list words and accumulator slots)
     bool timed = false;
@@ -444,6 +445,7 @@ int ngp_create(int device, ngp_handle** out)
     CU(cudaMalloc((void**)&h->sync, sizeof(SyncArea)));
     CU(zero(h, h->sync, 0, sizeof(SyncArea)));
     CU(cudaMalloc((void**)&h->sets_dev, sizeof(SetDev) * NGP_MAX_SETS));
+    CU(cudaMallocHost((void**)&h->err_pinned, sizeof(int)));
     *out = h;
     return NGP_OK;
 }
@@ -459,6 +461,7 @@ int ngp_destroy(ngp_handle* h)
     cudaFree(h->e); cudaFree(h->w); cudaFree(h->sc); cudaFree(h->sync); cudaFree(h->sets_dev);
     cudaFree(h->rp_chi2_e); cudaFree(h->rp_z_mu);
     if (h->stage) cudaFreeHost(h->stage);
+    if (h->err_pinned) cudaFreeHost(h->err_pinned);
     cudaFree(h->fx_data); cudaFree(h->fx_xpx); cudaFree(h->fx_colsum); cudaFree(h->fx_b); cudaFree(h->fx_rp_z);
     cudaFree(h->fx_xpx_w); cudaFree(h->fx_colsum_w);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1106,10 +1109,15 @@ static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int 
     }
 }
 
+static int kernel_error_code(ngp_handle* h, int kerr);
 static int check_kernel_error(ngp_handle* h)
 {
     int kerr = 0;
     CU(cpy(h, &kerr, &h->sync->err, sizeof(int), cudaMemcpyDeviceToHost));
+    return kernel_error_code(h, kerr);
+}
+static int kernel_error_code(ngp_handle* h, int kerr)
+{
     if (kerr & 8) return fail(h, NGP_ETIMEOUT, "row-sharded chain: a rank did not arrive within 4 s (results invalid)");
     if (kerr & 2) return fail(h, NGP_ENUMERIC, "a covariance matrix of the tuple sampler is not positive definite");
     if (kerr & 4) return fail(h, NGP_ENUMERIC, "BayesR: no class reached its uniform (the reference's findfirst returns nothing here)");
@@ -1304,8 +1312,9 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     h->launches += 1;
     h->timed = true;
     if (defer_sync) return NGP_OK;                 // the caller queues its device-to-host copies first and synchronises once
+    CU(cudaMemcpyAsync(h->err_pinned, &h->sync->err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return check_kernel_error(h);
+    return kernel_error_code(h, *h->err_pinned);
 }
 
 // the tuple's effects live either in the member sets (per-locus kernel) or in the interleaved copy (blocked kernel)
@@ -1405,6 +1414,7 @@ int ngp_sweep(ngp_handle* h, int set_id, double* ycorr, double varE, double* bet
     const size_t need = sizeof(int32_t) * (size_t)S.p_pad + sizeof(double) * 2 * kMaxClass * 2 + 64;
     if (h->stage_bytes < need) {
         if (h->stage) cudaFreeHost(h->stage);
+    if (h->err_pinned) cudaFreeHost(h->err_pinned);
         h->stage = nullptr; h->stage_bytes = 0;
         CU(cudaMallocHost((void**)&h->stage, need));
         h->stage_bytes = need;
