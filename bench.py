@@ -180,7 +180,18 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def sharded_leg(rank, world, local, dist, n, model, seed, p_s=2048, iters=3):
+def allreduce_gram(s, set_id, dist):
+    """row-sharded chain on the blocked kernel: the banded Gram is a sum over individuals (NCCL all-reduce of the int32 band at set-up)"""
+    import torch
+    g = torch.from_numpy(s.gram(set_id)).cuda()
+    sizes = [None] * dist.get_world_size()
+    dist.all_gather_object(sizes, int(g.numel()))
+    assert len(set(sizes)) == 1, f"ranks chose different block sizes / look-aheads: {sizes}"
+    dist.all_reduce(g)
+    s.set_gram(set_id, g.cpu().numpy())
+
+
+def sharded_leg(rank, world, local, dist, n, model, seed, p_s=2048, iters=3, kernel="literal"):
     """Row-sharded single chain over the N GPUs of this run on a bounded slice of the workload (all n rows, the first p_s markers),
     CHECKED: every rank must hold the bitwise identical chain, and it must agree with the unsharded chain that rank 0 runs on the
     same data with the same variate stream.  Returns {per_marker_us, max_rel_err, ranks_identical} on rank 0."""
@@ -191,7 +202,7 @@ def sharded_leg(rank, world, local, dist, n, model, seed, p_s=2048, iters=3):
     method = 0 if model in ("BayesRR", "BayesPR") else (1 if model == "BayesB" else 2)
     per = -(-(-(-n // world)) // 4) * 4
     a, b = min(n, rank * per), min(n, (rank + 1) * per)
-    s = ngp.Sampler(local, kernel="literal")
+    s = ngp.Sampler(local, kernel=kernel)
     s.shard_init(rank, world)
     s.synth_genotypes_rows(0, a, b - a, p_s, seed, prob["thr0"], prob["thr1"])
     infos = [None] * world
@@ -202,6 +213,8 @@ def sharded_leg(rank, world, local, dist, n, model, seed, p_s=2048, iters=3):
     dist.all_reduce(tcs)
     tcs = tcs.cpu().numpy()
     s.set_column_sums(0, n, tcs[0], tcs[1])
+    if kernel == "blocked":
+        allreduce_gram(s, 0, dist)
     s.set_prior(0, method, 4.0, v * 0.5, v, pi_in=pi, est_pi=(method == 2))
     s.set_phenotype(prob["y"][a:b]); s.set_residual_prior(4.0, v_e * 0.5); s.set_intercept(True); s.set_rng(seed, 0)
     dist.barrier()
@@ -232,7 +245,9 @@ def sharded_leg(rank, world, local, dist, n, model, seed, p_s=2048, iters=3):
         err = float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300))
         out = {"per_marker_us": 1e3 * float(tms.item()) / (iters - 1) / p_s, "max_rel_err": err, "ranks_identical": bool(identical),
                "checked_against": f"unsharded blocked chain of rank 0, {iters} iterations, beta / varE / mu",
-               "slice": f"all {n} rows x first {p_s} markers, per-marker kernel, one fixed-point RED per marker into every rank's accumulator over NVLink"}
+               "slice": (f"all {n} rows x first {p_s} markers, per-marker kernel, one fixed-point RED per marker into every rank's accumulator over NVLink"
+                         if kernel == "literal" else
+                         f"all {n} rows x first {p_s} markers, blocked look-ahead kernel, the B partial sums of a block pushed into every rank's accumulator ring over NVLink")}
     dist.barrier()
     return out
 
@@ -258,6 +273,7 @@ def main():
     ap.add_argument("--no-sharded-leg", action="store_true", help="N > 1: skip the checked row-sharded leg")
     ap.add_argument("--long-seconds", type=float, default=1.0, help="extra untimed-by-contract run of at least this many seconds after the K timed steps (0 = off)")
     ap.add_argument("--ref-cols", type=int, default=2000)
+    ap.add_argument("--shard-kernel", default="blocked", choices=["blocked", "literal"], help="--sharded: kernel of the row-sharded chain")
     ap.add_argument("--sharded", action="store_true",
                     help="ONE chain whose individuals are row-sharded over the N GPUs (per-marker reduction over NVLink peer memory); strong scaling")
     args = ap.parse_args()
@@ -296,7 +312,7 @@ def main():
     sharded = args.sharded and world > 1
     kbreeds = int(model[10:]) if model.startswith("MultiBreed") else 0
     if sharded:
-        args.kernel = "literal"
+        args.kernel = args.shard_kernel
         args.no_e2e = True
     s = ngp.Sampler(local, kernel=args.kernel, block=args.block, storage=args.storage)
     stream = torch.cuda.current_stream()
@@ -317,6 +333,8 @@ def main():
         dist.all_reduce(tcs)
         tcs = tcs.cpu().numpy()
         s.set_column_sums(0, n, tcs[0], tcs[1])
+        if args.kernel == "blocked":
+            allreduce_gram(s, 0, dist)
         y = prob["y"][a:b]
     elif kbreeds:
         for bset in range(kbreeds):
@@ -358,6 +376,9 @@ def main():
     l0 = s.timing()["launches"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms = []
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()          # (rank 0 has just slept while its clock sampler started: a sharded chain's other ranks would wait for it inside their kernels)
     torch.cuda.synchronize()
     ev0.record(stream)
     if sharded:
@@ -413,7 +434,10 @@ def main():
     shard_rec = None
     if dist and not sharded and not kbreeds and not args.no_sharded_leg and not args.weighted and args.storage == "i8":
         try:
-            shard_rec = sharded_leg(rank, world, local, dist, n, model, seed)
+            shard_rec = sharded_leg(rank, world, local, dist, n, model, seed)                               # per-marker kernel
+            blk = sharded_leg(rank, world, local, dist, n, model, seed, p_s=8192, iters=6, kernel="blocked")        # blocked kernel
+            if shard_rec is not None:
+                shard_rec = dict(shard_rec, blocked=blk)
         except Exception as ex:  # noqa: BLE001
             shard_rec = {"error": str(ex)}
 
@@ -469,8 +493,8 @@ def main():
                 "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": workload_name(args.config, n, p, model, args.storage, args.regions) + (" [diagnostic: weighted residuals E.str == \"D\", per-marker kernel]" if args.weighted else ""), "kernel": ("blocked tuple sweep (interleaved copy, joint draw in the chain warp)" if args.kernel == "blocked" and kbreeds in (2, 4) else "joint (per locus)") if kbreeds else args.kernel, "chains": nchains,
-                           "parallelism": (f"ONE chain row-sharded over {world} GPUs: per-marker fixed-point reduction pushed into every rank's "
-                                           f"accumulators over NVLink peer memory (CUDA IPC), identical draw on every rank")
+                           "parallelism": (f"ONE chain row-sharded over {world} GPUs ({args.kernel} kernel): fixed-point partial sums pushed into every rank's "
+                                           f"accumulators over NVLink peer memory (CUDA IPC), identical draws on every rank")
                                           if sharded else f"{world} independent chain(s), one per GPU, no data-path collective",
                            "l2": f"genotype matrix {n * p / 1e9:.2f} GB per sweep vs 126 MB L2 (inputs larger than L2, no flush needed)"
                                  if n * p > 4e8 else "inputs fit in L2 (cache-resident workload; HBM roofline not meaningful)",

@@ -230,7 +230,7 @@ int ngp_get_column_stats(ngp_handle* h, int set_id, double* mean, double* mpm);
 /* ---- row-sharded chain: call order  ngp_shard_init -> uploads (local rows) -> ngp_shard_export -> [exchange] ->
  *      ngp_shard_attach -> ngp_get_column_sums -> [all-reduce] -> ngp_set_column_sums -> priors, phenotype (local rows) ->
  *      ngp_run with identical arguments on every rank, concurrently.  mean_j and mpm_j (prepMatVec.jl:129, mme.jl:305-307)
- *      are those of the whole column.  Only the per-marker kernel (NGP_KERNEL_LITERAL) runs sharded.                   */
+ *      are those of the whole column.  Per-marker kernel (NGP_KERNEL_LITERAL), or the blocked kernel after ngp_set_gram. */
 int ngp_shard_init(ngp_handle* h, int rank, int world);
 int ngp_shard_export(ngp_handle* h, ngp_shard_info* out);
 int ngp_shard_attach(ngp_handle* h, const ngp_shard_info* all_ranks);
@@ -242,6 +242,13 @@ int ngp_shard_attach(ngp_handle* h, const ngp_shard_info* all_ranks);
 int ngp_run_group(ngp_handle** handles, int n_handles, int32_t n_iter);
 int ngp_get_column_sums(ngp_handle* h, int set_id, int64_t* colsum, int64_t* colsumsq);
 int ngp_set_column_sums(ngp_handle* h, int set_id, int64_t n_total, const int64_t* colsum, const int64_t* colsumsq);
+/* Row-sharded chain on the BLOCKED kernel (NGP_KERNEL_BLOCKED; SURVEY 8e "B-many scalars blocked"): per block every worker CTA pushes its B
+ * partial sums into the accumulator ring of every rank, each rank's chain CTA computes the identical lists (identical sums, identical
+ * draws).  The banded Gram is a sum over individuals: read every rank's (ngp_get_gram), add them up, write the total back on every rank
+ * (ngp_set_gram) — all ranks must share the block size and the look-ahead.  count = (p_pad / B) (D + 1) B B int32 values.            */
+int ngp_gram_size(ngp_handle* h, int set_id, int64_t* count);
+int ngp_get_gram(ngp_handle* h, int set_id, int32_t* out);
+int ngp_set_gram(ngp_handle* h, int set_id, const int32_t* in);
 
 /* host 2-bit codec (format NGP_GENO_PACKED2); returns NGP_EDATA on a code outside 0..2 */
 int ngp_pack2(const int8_t* codes, int64_t n, int64_t p, int64_t ld_in, uint8_t* out, int64_t ld_out);

@@ -77,7 +77,7 @@ def translation_units() -> list[tuple[str, str, list[str]]]:
     """(object name, source file, extra flags): one instantiation of the sweep kernels per unit (csrc/ngp_kernels.h)."""
     tus = [("ngp_api", "ngp_api.cu", []), ("ngp_ingest", "ngp_ingest.cpp", [])]
     for B in (16, 32, 64):
-        for v in range(8):
+        for v in range(9):
             tus.append((f"ngp_k_gibbs_{B}_{v}", "ngp_k_gibbs.cu", [f"-DNGP_KB={B}", f"-DNGP_KV={v}"]))
     for k in range(2, 9):
         tus.append((f"ngp_k_joint_{k}", "ngp_k_joint.cu", [f"-DNGP_JK={k}"]))
@@ -162,6 +162,9 @@ _SIGS = {
     "ngp_shard_attach": (C.c_int, [C.c_void_p, C.POINTER(ShardInfo)]),
     "ngp_get_column_sums": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ngp_set_column_sums": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ngp_gram_size": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
+    "ngp_get_gram": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ngp_set_gram": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ngp_download_genotypes": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
     "ngp_get_column_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ngp_pack2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),

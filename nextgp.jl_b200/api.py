@@ -360,6 +360,21 @@ class Sampler:
         self._ck(self._lib.ngp_get_column_sums(self._h, set_id, _p(a), _p(b)))
         return a, b
 
+    def gram(self, set_id: int) -> np.ndarray:
+        """banded raw Gram of this handle's rows (int32): ngp_get_gram"""
+        cnt = C.c_int64()
+        self._ck(self._lib.ngp_gram_size(self._h, set_id, C.byref(cnt)))
+        out = np.empty(cnt.value, dtype=np.int32)
+        self._ck(self._lib.ngp_get_gram(self._h, set_id, _p(out)))
+        return out
+
+    def set_gram(self, set_id: int, gram: np.ndarray) -> None:
+        gram = np.ascontiguousarray(gram, dtype=np.int32)
+        cnt = C.c_int64()
+        self._ck(self._lib.ngp_gram_size(self._h, set_id, C.byref(cnt)))
+        assert gram.size == cnt.value
+        self._ck(self._lib.ngp_set_gram(self._h, set_id, _p(gram)))
+
     def set_column_sums(self, set_id: int, n_total: int, colsum: np.ndarray, colsumsq: np.ndarray) -> None:
         a = np.ascontiguousarray(colsum, dtype=np.int64)
         b = np.ascontiguousarray(colsumsq, dtype=np.int64)
@@ -605,9 +620,12 @@ class ShardedChain:
     co-resident, so every ngp_run is issued from one host thread per shard.  With one process per GPU use the Sampler
     methods directly and exchange shard_export() blobs / column sums with torch.distributed (bench.py --sharded)."""
 
-    def __init__(self, devices: list[int], max_ctas: int = 0, min_rows: int = 0):
+    def __init__(self, devices: list[int], max_ctas: int = 0, min_rows: int = 0, kernel: str = "literal", block: int = 0, lookahead: int = 0, **geom):
+        """kernel = "literal": one reduction per marker; "blocked": the look-ahead kernel, B partial sums per block pushed to every rank
+        (all ranks must share the block size and the look-ahead: pass them when the shards' row counts differ much)."""
         self.world = len(devices)
-        self.shards = [Sampler(d, kernel="literal", max_ctas=max_ctas, min_rows=min_rows) for d in devices]
+        self.kernel = kernel
+        self.shards = [Sampler(d, kernel=kernel, max_ctas=max_ctas, min_rows=min_rows, block=block, lookahead=lookahead, **geom) for d in devices]
         for r, s in enumerate(self.shards):
             s.shard_init(r, self.world)
         self.rows: list[tuple[int, int]] = []
@@ -636,6 +654,13 @@ class ShardedChain:
         cs, css = sum(x[0] for x in sums), sum(x[1] for x in sums)
         for s in self.shards:
             s.set_column_sums(set_id, n, cs, css)
+        if self.kernel == "blocked":                      # the banded Gram is a sum over individuals
+            grams = [s.gram(set_id) for s in self.shards]
+            if len({g.shape for g in grams}) != 1:
+                raise ValueError("ShardedChain: the shards chose different block sizes / look-aheads; pass block= and lookahead=")
+            total = np.sum(grams, axis=0, dtype=np.int64).astype(np.int32)
+            for s in self.shards:
+                s.set_gram(set_id, total)
 
     def each(self, fn) -> list:
         return [fn(s, r) for r, s in enumerate(self.shards)]

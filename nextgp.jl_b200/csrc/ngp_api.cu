@@ -24,7 +24,7 @@
 
 using namespace ngp;
 
-static_assert(kSyncHeadBytes == offsetof(SyncArea, acc), "the per-launch memset covers exactly the head of SyncArea");
+static_assert(kSyncHeadBytes == offsetof(SyncArea, acc) && kSyncHeadFixed == offsetof(SyncArea, part), "the per-launch memset covers the head of SyncArea: counter, error word, the partials of the CTAs in use");
 
 // ============================================================================= set-up kernels
 namespace {
@@ -256,6 +256,7 @@ __global__ void debug_variates_kernel(uint32_t key0, uint32_t key1, uint32_t cha
 // ============================================================================= handle
 struct SetHost {
     bool have_geno = false, have_prior = false, joint_member = false;
+    bool gram_global = false;          // row-sharded chain: the banded Gram has been summed over the ranks (ngp_set_gram)
     int64_t p = 0, p_pad = 0, nvar = 0, n_regions = 0;
     int method = 0, est_pi = 0, storage = 0;
     double df = 4.0, scale = 0.0, var_init = 0.0, pi_in = 0.0;
@@ -536,7 +537,7 @@ static int choose_geometry(ngp_handle* h, int64_t n, int store2)
 {
     const int sms = h->prop.multiProcessorCount;
     int maxc = h->cfg_max_ctas ? std::min(h->cfg_max_ctas, sms) : sms;
-    maxc = std::min(maxc, kMaxCtas / h->shard_world);      // phase-0 partials of all ranks share one array; arrivals per accumulator < 256
+    maxc = std::min(maxc, std::min(160, kMaxCtas / h->shard_world));      // phase-0 partials of all ranks share one array
     if (maxc < 2) return fail(h, NGP_EUNSUPPORTED, "the sweep kernel needs at least 2 co-resident CTAs (device has %d SMs)", sms);
     const int maxw = maxc - 1;                     // one CTA runs the scalar chain
     const int64_t want = (n + h->cfg_min_rows - 1) / h->cfg_min_rows;
@@ -1096,7 +1097,7 @@ static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int 
     P.w = h->w; P.w_sum = h->w_sum; P.w_min = h->w_min; P.w_max = h->w_max;
     if (h->w && h->fx.n_cols && h->fx_w_ready) { P.fx.xpx = h->fx_xpx_w; P.fx.colsum_w = h->fx_colsum_w; }
     P.n_ranks = h->shard_world; P.rank = h->shard_rank; P.n_total = h->shard_world > 1 ? h->n_total : h->n;
-    P.cta_off = 0; P.T_all = h->Tw + 1; P.Tw_all = h->Tw; P.bar_base = 0;
+    P.cta_off = 0; P.T_all = h->Tw + 1; P.Tw_all = h->Tw; P.bar_base = 0; P.cnt_bits = kCntBits;
     P.peer[0] = h->sync;
     if (h->shard_world > 1) {
         P.T_all = 0; P.Tw_all = 0;
@@ -1106,6 +1107,7 @@ static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int 
             P.peer[r] = h->peer[r];
         }
         P.bar_base = h->bar_count * (unsigned long long)P.T_all;
+        if (P.Tw_all > 255) P.cnt_bits = 11;              // up to 2047 arrivals per accumulator (three bits less of fixed-point resolution)
     }
 }
 
@@ -1156,7 +1158,7 @@ static int launch_joint(ngp_handle* h, int n_iter, int do_varE, int do_mu, doubl
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, smem));
     if (per_sm * h->prop.multiProcessorCount < h->Tw + 1)
         return fail(h, NGP_EUNSUPPORTED, "cooperative grid of %d CTAs does not fit (%d per SM x %d SMs)", h->Tw + 1, per_sm, h->prop.multiProcessorCount);
-    CU(cudaMemsetAsync(h->sync, 0, kSyncHeadBytes, h->stream));
+    CU(cudaMemsetAsync(h->sync, 0, kSyncHeadFixed + sizeof(double) * 2 * (size_t)(h->Tw + 1), h->stream));
     void* args[] = {&P, &J};
     CU(cudaEventRecord(h->ev0, h->stream));
     CU(cudaLaunchCooperativeKernel(kfn, dim3(h->Tw + 1), dim3(kThreads), args, smem, h->stream));
@@ -1179,7 +1181,10 @@ static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, 
     if (h->replay && h->fx.n_cols && do_mu && (!h->fx_rp_z || h->fx_replay_iters != h->replay_iters))
         return fail(h, NGP_EINVAL, "replay log of the fixed effects missing (ngp_set_fixed_replay after ngp_set_replay)");
     if (sharded && h->cfg_kernel != NGP_KERNEL_LITERAL)
-        return fail(h, NGP_EUNSUPPORTED, "the row-sharded chain runs the per-marker kernel (NGP_CFG_KERNEL = NGP_KERNEL_LITERAL)");
+        for (int s = 0; s < h->n_sets; ++s)
+            if (((set_mask >> s) & 1) && !h->sets[s].gram_global)
+                return fail(h, NGP_EINVAL, "row-sharded chain on the blocked kernel: the banded Gram of set %d holds this rank's rows only — sum it over "
+                                           "the ranks (ngp_get_gram -> all-reduce -> ngp_set_gram), or use NGP_KERNEL_LITERAL", s);
     if (sharded && h->shard_same_device && !group)
         return fail(h, NGP_EUNSUPPORTED, "shards of one chain on the same device wait for one another: separate launches are not guaranteed to be "
                                          "co-resident, run them as one grid with ngp_run_group");
@@ -1264,9 +1269,10 @@ static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, 
     if (h->store2 > 0 && (variant == NGP_KV_LIT || variant == NGP_KV_TUP))   // (the blocked BayesR sweep reads 2-bit tiles like the plain one)
         return fail(h, NGP_EUNSUPPORTED, "2-bit device storage serves the blocked sweep of BayesPR / BayesB / BayesC sets (not the per-marker kernel: "
                                          "BayesR, weighted residuals, row sharding; not the tuple sampler): upload with NGP_STORE_I8");
-    kfn = ngp_gibbs_kernel(h->B, group ? NGP_KV_GROUP : variant);
-    h->last_variant = group ? NGP_KV_GROUP : variant;
-    if (group && variant != NGP_KV_LIT) return fail(h, NGP_EUNSUPPORTED, "ngp_run_group runs the per-marker kernel only");
+    if (group && variant != NGP_KV_LIT && variant != NGP_KV_PLAIN) return fail(h, NGP_EUNSUPPORTED, "ngp_run_group runs the plain blocked or the per-marker sweep");
+    const int gvariant = group ? (variant == NGP_KV_LIT ? NGP_KV_GROUP : NGP_KV_GROUPB) : variant;
+    kfn = ngp_gibbs_kernel(h->B, gvariant);
+    h->last_variant = gvariant;
     if (!group && h->ready_kfn != kfn) {                      // once per kernel variant: attribute + co-residency check of the cooperative grid
         // the attribute belongs to the function, not to the handle: always the device maximum, so that handles with different
         // geometries never lower it under each other
@@ -1295,7 +1301,7 @@ static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, 
         for (int s = 0; s < h->n_sets; ++s)
             if ((set_mask >> s) & 1) rounds += ((h->sets[s].method == NGP_BAYESPR && h->sets[s].n_regions > 1) || accumulate) ? 1 : 0;
         h->bar_count += rounds * (uint64_t)n_iter;
-    } else CU(cudaMemsetAsync(h->sync, 0, kSyncHeadBytes, h->stream));
+    } else CU(cudaMemsetAsync(h->sync, 0, kSyncHeadFixed + sizeof(double) * 2 * (size_t)(h->Tw + 1), h->stream));
     return NGP_OK;
 }
 
@@ -1601,6 +1607,34 @@ int ngp_set_column_sums(ngp_handle* h, int set_id, int64_t n_total, const int64_
     colstats_kernel<<<(unsigned)((S.p_pad + 255) / 256), 256, 0, h->stream>>>(n_total, S.p, S.p_pad, S.colsum, S.colsumsq, S.mean, S.d);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
+    return NGP_OK;
+}
+
+// Row-sharded chain on the blocked kernel: the banded raw Gram gx[k][d][a][b] = sum_i g_a g_b is a sum over individuals, so every rank needs the
+// sum of all ranks' Grams (int32, (p_pad / B) * (D + 1) * B * B values; all ranks share B and D).  Host round trip at set-up.
+int ngp_gram_size(ngp_handle* h, int set_id, int64_t* count)
+{
+    if (!h || !count || set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_geno) return fail(h, NGP_EINVAL, "ngp_gram_size: bad argument");
+    *count = (h->sets[set_id].p_pad / h->B) * (int64_t)(h->D + 1) * h->B * h->B;
+    return NGP_OK;
+}
+int ngp_get_gram(ngp_handle* h, int set_id, int32_t* out)
+{
+    int64_t cnt = 0;
+    int rc = ngp_gram_size(h, set_id, &cnt);
+    if (rc || !out) return rc ? rc : fail(h, NGP_EINVAL, "ngp_get_gram: out is NULL");
+    CU(cudaSetDevice(h->device));
+    CU(cpy(h, out, h->sets[set_id].gx, sizeof(int32_t) * (size_t)cnt, cudaMemcpyDeviceToHost));
+    return NGP_OK;
+}
+int ngp_set_gram(ngp_handle* h, int set_id, const int32_t* in)
+{
+    int64_t cnt = 0;
+    int rc = ngp_gram_size(h, set_id, &cnt);
+    if (rc || !in) return rc ? rc : fail(h, NGP_EINVAL, "ngp_set_gram: in is NULL");
+    CU(cudaSetDevice(h->device));
+    CU(cpy(h, h->sets[set_id].gx, in, sizeof(int32_t) * (size_t)cnt, cudaMemcpyHostToDevice));
+    h->sets[set_id].gram_global = true;
     return NGP_OK;
 }
 

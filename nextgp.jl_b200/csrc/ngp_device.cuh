@@ -40,8 +40,8 @@ constexpr int kMaxB = 64;              // markers per block: 16, 32 or 64
 constexpr int kNF = 10;                // per-marker constant fields
 constexpr int kMaxD = 24;              // maximum look-ahead depth (blocks)
 constexpr int kSlots = 32;             // accumulator ring (blocks in flight <= D+1), multiple of kPrepWarps
-constexpr int kMaxCtas = 160;          // < 256: the low byte of an accumulator counts arrivals
-constexpr int kCntBits = 8;
+constexpr int kMaxCtas = 1280;         // CTAs of all ranks of a row-sharded chain (8 ranks x 160); one rank: <= 160
+constexpr int kCntBits = 8;            // low bits of an accumulator that count arrivals (Params::cnt_bits: 8, or 11 when more than 255 worker CTAs of all ranks add into it)
 constexpr int kAccStride = 1;          // int64 units between two accumulators (contiguous measured no slower than 256 B apart)
 constexpr int kLLCopies = 8;           // replicas of the changed-effect list ring (worker CTA t polls replica t % 8): no L2 hot spot
 constexpr int kNzRing = 32;            // rings indexed by the global block number (lists, versions, dot-done flags): >= D+2
@@ -113,22 +113,23 @@ struct FxDev {
 };
 
 struct SyncArea {
-    // ---- head: zeroed before every launch
+    // ---- head: zeroed before every launch (counter, error word, then the phase-0 partials of the CTAs in use)
     unsigned long long counter;                 // grid-barrier arrivals, monotonic within a launch
     unsigned long long pad0[15];
-    double part[kMaxCtas * 2];                  // phase-0 partials (e'e, sum e) per CTA
     int err;
     int pad1[31];
+    double part[kMaxCtas * 2];                  // phase-0 partials (e'e, sum e) per CTA
     // ---- body: persists across launches (monotonic accumulators, sequence-numbered list words)
-    long long acc[kSlots * kMaxB * kAccStride]; // fixed-point reduction accumulators (monotonic; low byte counts arrivals)
+    long long acc[kSlots * kMaxB * kAccStride]; // fixed-point reduction accumulators (monotonic; low bits count arrivals)
     unsigned long long ll[kLLCopies][kNzRing * kLLSlotWords];   // changed-effect lists chain CTA -> worker CTAs (copy = CTA % kLLCopies);
                                                 // every 8-byte word = {payload32, seq32}, seq = global block number + 1
-    long long prof[kMaxCtas * kProf];           // per-CTA cycle counters of the last launch: see ngp_get_profile
+    long long prof[160 * kProf];                // per-CTA cycle counters of the last launch (this rank's CTAs): see ngp_get_profile
     long long trace[2 * 2048];                  // instrumented kernel: (start clock, cycles waited for r_base) of the chain warp's first 2048 steps
-    double part_fx[kMaxCtas * kMaxFxCols];      // per-CTA partial dots x_c'e of the fixed-effect columns
-    double part_u[kMaxCtas];                    // weighted residuals: per-CTA partial of the plain 1'e (phase 0)
+    double part_fx[160 * kMaxFxCols];           // per-CTA partial dots x_c'e of the fixed-effect columns (not with row sharding)
+    double part_u[160];                         // weighted residuals: per-CTA partial of the plain 1'e (phase 0; not with row sharding)
 };
-constexpr size_t kSyncHeadBytes = 16 * 8 + kMaxCtas * 2 * 8 + 32 * 4;
+constexpr size_t kSyncHeadFixed = 16 * 8 + 32 * 4;                       // counter + error word; the launch also clears part[0 .. 2 T_all)
+constexpr size_t kSyncHeadBytes = kSyncHeadFixed + kMaxCtas * 2 * 8;
 
 struct Scalars {          // device-resident chain scalars
     double mu, varE;
@@ -166,6 +167,7 @@ struct Params {
     int32_t n_ranks, rank;
     int32_t cta_off, T_all;    // index of this rank's first CTA in the all-rank CTA numbering; CTAs of all ranks
     int32_t Tw_all;            // worker CTAs of all ranks (arrivals per accumulator)
+    int32_t cnt_bits;          // arrival-count bits of an accumulator: 8, or 11 when Tw_all > 255
     int32_t store2;            // 1: genotypes stored as 2-bit codes (NGP_STORE_2BIT), expanded to the INT8 operands on chip
     int32_t refetch;           // 1: tiles leave shared memory once their dots are formed; the columns of changed effects are re-read from L2/HBM
     int64_t n_total;           // individuals over all ranks (n is the local row count)

@@ -12,11 +12,13 @@
 extern "C" const void* NGP_CAT3(ngp_kptr_gibbs_, NGP_KB, NGP_KV)(void)
 {
 #if NGP_KV == 5
-    return (const void*)ngp::gibbs_group_kernel<NGP_KB>;
+    return (const void*)ngp::gibbs_group_kernel<NGP_KB, true>;
 #elif NGP_KV == 6
     return (const void*)ngp::gibbs_kernel<NGP_KB, false, false, false, false, true>;
 #elif NGP_KV == 7
     return (const void*)ngp::gibbs_kernel<NGP_KB, false, false, false, false, false, true>;
+#elif NGP_KV == 8
+    return (const void*)ngp::gibbs_group_kernel<NGP_KB, false>;
 #else
     return (const void*)ngp::gibbs_kernel<NGP_KB, NGP_KV == NGP_KV_PROF, NGP_KV == NGP_KV_DBG, NGP_KV == NGP_KV_LIT, NGP_KV == NGP_KV_TUP>;
 #endif

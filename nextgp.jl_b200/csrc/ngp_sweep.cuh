@@ -411,6 +411,9 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
     NzList* cnz = reinterpret_cast<NzList*>(smem + L.c_nz);
 
     const bool sharded = P.n_ranks > 1;
+    const int cb = P.cnt_bits;                               // arrival-count bits of the accumulators
+    const long long cmask = (1LL << cb) - 1;
+    const long long arr_all = (long long)P.Tw_all;           // worker CTAs of all ranks add into every rank's accumulators
     GridSync gs{&sy->err, &sy->counter, 0ull, (unsigned)P.T_all, P.bar_base, P.n_ranks};
     const int64_t row0 = (int64_t)t * R;
     const int nrow = is_chain ? 0 : (int)max((int64_t)0, min((int64_t)R, P.n - row0));    // real rows of this panel
@@ -519,7 +522,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                 if (wt) M = 2.0 * sqrt(nn) * (sqrt(a / P.w_min) + sqrt(nn) * fabs(dmu)) * fmax(1.0, P.w_max);    // |sum g w e| <= 2 sqrt(n) max(w) ||e||
                 if (!(M > 1e-300)) M = 1e-300;
                 int ex; (void)frexp(M, &ex);
-                int sh = 62 - kCntBits - 4 - ex;
+                int sh = 62 - P.cnt_bits - 4 - ex;
                 sh = max(-1000, min(1000, sh));
                 misc[32] = varE; misc[33] = dmu; misc[34] = b + (wt ? P.w_sum : nn) * dmu; misc[35] = (double)sh; misc[36] = mu;
                 if (wt) misc[37] = bu + nn * dmu;
@@ -779,7 +782,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                         // ------------------------------------------------------------------ dot warps: whole blocks, 8 in flight
                         const int dw = warp - kFirstDotWarp;
                         const int g = lane >> 2, tt = lane & 3;
-                        const long long plim = (1LL << 55) / Tw;
+                        const long long plim = (1LL << (63 - cb)) / P.Tw_all;
                         // refetch mode: a stage is always consumed by the same warp (the dot warps taking part divide NT), so an mbarrier
                         // waiter is never more than one fill behind
                         const int ND = !P.refetch ? kDotWarps : (NT >= 8) ? 8 : (NT >= 4) ? 4 : (NT >= 2) ? 2 : 1;
@@ -859,7 +862,12 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                     if (tt < 2) {
                                         const long long sa = (long long)(tt ? v1 : v0);
                                         if (sa >= plim || sa <= -plim) atomicOr(&sy->err, 1);
-                                        red_add_u64(accg + (mg * 16 + g + 8 * tt) * kAccStride, (long long)((unsigned long long)sa << kCntBits) + 1);
+                                        const long long rv = (long long)((unsigned long long)sa << cb) + 1;
+                                        if (sharded) {
+                                            // row-sharded chain: the partial sums of the block go into the accumulator ring of EVERY rank (NVLink peer memory)
+                                            const size_t aoff = (size_t)(gidx & (kSlots - 1)) * kMaxB * kAccStride + (size_t)(mg * 16 + g + 8 * tt) * kAccStride;
+                                            for (int r = 0; r < P.n_ranks; ++r) red_add_u64_sys(P.peer[r]->acc + aoff, rv);
+                                        } else red_add_u64(accg + (mg * 16 + g + 8 * tt) * kAccStride, rv);
                                     }
                                 }
                             }
@@ -1353,12 +1361,14 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
 #pragma unroll
                                 for (int i = 0; i < kPollPipe; ++i) pvalid[i] = false;
                                 long long t_issue = clock64() - kPollGap;
+                                unsigned sh_spins = 0;
+                                unsigned long long sh_t0 = 0;
                                 for (;;) {
                                     bool done = pvalid[0];
 #pragma unroll
                                     for (int b = 0; b < NB; ++b) {
                                         cur[b] = pv_[0][b];
-                                        if (live[b] && pvalid[0]) done = done && (((cur[b] - prev[slot * B + b * 32 + lane]) & 0xFF) == (long long)Tw);
+                                        if (live[b] && pvalid[0]) done = done && (((cur[b] - prev[slot * B + b * 32 + lane]) & cmask) == arr_all);
                                     }
                                     const bool valid0 = pvalid[0];
 #pragma unroll
@@ -1371,8 +1381,10 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                     while (clock64() - t_issue < kPollGap) { }
                                     t_issue = clock64();
 #pragma unroll
-                                    for (int b = 0; b < NB; ++b) pv_[kPollPipe - 1][b] = live[b] ? ld_relaxed_s64(acc + (b * 32 + lane) * kAccStride) : 0;
+                                    for (int b = 0; b < NB; ++b)
+                                        pv_[kPollPipe - 1][b] = !live[b] ? 0 : sharded ? ld_relaxed_s64_sys(acc + (b * 32 + lane) * kAccStride) : ld_relaxed_s64(acc + (b * 32 + lane) * kAccStride);
                                     pvalid[kPollPipe - 1] = true;
+                                    if (sharded && (++sh_spins & 0x3ffu) == 0u && shard_wait_expired(&sy->err, sh_t0)) break;      // a rank that never arrives
                                 }
                             }
                             if (warp == kFirstPrepWarp) NGP_TICK(13);
@@ -1398,7 +1410,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                 const int q = b * 32 + lane;
                                 if (live[b]) {
                                     long long* pv = prev + slot * B + q;
-                                    const double A = (double)((cur[b] - *pv - (long long)Tw) >> kCntBits) * fx_inv;
+                                    const double A = (double)((cur[b] - *pv - arr_all) >> cb) * fx_inv;
                                     if (!(dbg & 2)) *pv = cur[b];
                                     rbase[pw * B + q] = (A - mean[b] * Stot) + far[b];       // x_q'e as the dots saw it + the corrections above
                                 }
@@ -1518,7 +1530,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                 // every CTA (the chain CTA owns no rows) evaluates the scalar update redundantly; CTA Tw writes the outputs
                 long long* lprev = reinterpret_cast<long long*>(misc + 48);
                 const int nwords = R >> 2;
-                const long long arrivals = (long long)P.Tw_all;       // worker CTAs of all ranks add into every rank's accumulators
+                const long long arrivals = arr_all;
                 // BayesR (functions.jl:238-289): lane v of warp 0 owns variance class v
                 const int nc = (S.method == 3) ? S.n_class : 0;
                 double varc_v = 0.0, logpi_v = 0.0, vcls_v = 0.0;
@@ -1562,11 +1574,11 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                         if (two) {
                             const double xu = dummy * fx_scale;
                             if (!(fabs(xu) < 9007199254740992.0)) atomicOr(&sy->err, 1);
-                            red_add_u64(acc + kAccStride, (long long)((unsigned long long)__double2ll_rn(xu) << kCntBits) + 1);
+                            red_add_u64(acc + kAccStride, (long long)((unsigned long long)__double2ll_rn(xu) << cb) + 1);
                         }
                         const double xs = a * fx_scale;
                         if (!(fabs(xs) < 9007199254740992.0)) atomicOr(&sy->err, 1);
-                        const long long v = (long long)((unsigned long long)__double2ll_rn(xs) << kCntBits) + 1;
+                        const long long v = (long long)((unsigned long long)__double2ll_rn(xs) << cb) + 1;
                         if (sharded) {
                             // the per-marker scalar reduction over NVLink peer memory: one RED into every rank's accumulator
                             for (int r = 0; r < P.n_ranks; ++r) red_add_u64_sys(P.peer[r]->acc + (size_t)slot * kMaxB * kAccStride, v);
@@ -1590,10 +1602,10 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                             do {
                                 cur = ld_relaxed_s64_sys(acc);
                                 if ((++spins & 0x3ffu) == 0u && shard_wait_expired(&sy->err, t0)) break;
-                            } while (((cur - *pv) & 0xFF) != arrivals);
+                            } while (((cur - *pv) & cmask) != arrivals);
                         }
-                        else { do { cur = ld_relaxed_s64(acc); } while (((cur - *pv) & 0xFF) != arrivals); }
-                        const double A = (double)((cur - *pv - arrivals) >> kCntBits) * fx_inv;
+                        else { do { cur = ld_relaxed_s64(acc); } while (((cur - *pv) & cmask) != arrivals); }
+                        const double A = (double)((cur - *pv - arrivals) >> cb) * fx_inv;
                         __syncwarp();
                         if (lane == 0) *pv = cur;
                         const double r = A - mean * Stot;
@@ -1602,9 +1614,9 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                         if (two) {
                             const long long pu = __shfl_sync(0xffffffffu, prev_u, slot);
                             long long cu;
-                            do { cu = ld_relaxed_s64(acc + kAccStride); } while (((cu - pu) & 0xFF) != arrivals);
+                            do { cu = ld_relaxed_s64(acc + kAccStride); } while (((cu - pu) & cmask) != arrivals);
                             if (lane == slot) prev_u = cu;
-                            const double Au = (double)((cu - pu - arrivals) >> kCntBits) * fx_inv;
+                            const double Au = (double)((cu - pu - arrivals) >> cb) * fx_inv;
                             rq = fma(__ldg(&S.d_unw[j]), bold, Au - mean * Stot_u);       // functions.jl:168, :208: view(data,:,locus)'ycorr
                         }
                         if (nc) {
@@ -1812,7 +1824,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 // cta_off(r) <= b < cta_off(r) + Tw(r) + 1 and runs that rank's per-marker sweep on that rank's Params — the same code, the same
 // system-scope REDs and polls as between GPUs.
 struct GroupParams { const Params* ranks; int n_ranks; };
-template <int B>
+template <int B, bool LIT>
 __global__ void __launch_bounds__(kThreads, 1) gibbs_group_kernel(const GroupParams G)
 {
     __shared__ Params Ps;
@@ -1829,7 +1841,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_group_kernel(const GroupPar
         for (int i = threadIdx.x; i < (int)(sizeof(Params) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    gibbs_body<B, false, false, true, false>(Ps, (int)blockIdx.x - Ps.cta_off);
+    gibbs_body<B, false, false, LIT, false>(Ps, (int)blockIdx.x - Ps.cta_off);
 }
 
 }  // namespace ngp

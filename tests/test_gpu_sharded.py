@@ -14,8 +14,8 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _sharded(prob, devices, method, v, pi=0.0, est_pi=False, region_off=None, max_ctas=6):
-    ch = ngp.ShardedChain(devices, max_ctas=max_ctas)
+def _sharded(prob, devices, method, v, pi=0.0, est_pi=False, region_off=None, max_ctas=6, **kw):
+    ch = ngp.ShardedChain(devices, max_ctas=max_ctas, **kw)
     ch.upload_genotypes(0, prob["codes"])
     df, scale = O.marker_hyper(v)
     for s in ch.shards:
@@ -53,6 +53,69 @@ def test_sharded_chain_on_one_device_matches_oracle(gpu, world, method, kw):
     mean, mpm = ch.shards[-1].column_stats(0)
     _, mean_o, mpm_o = O.center_codes(prob["codes"])
     assert np.allclose(mean, mean_o, rtol=1e-14) and np.allclose(mpm, mpm_o, rtol=1e-12)
+    ch.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("block,method,kw", [(32, 2, dict(v=0.05, pi=0.1, est_pi=True)), (64, 1, dict(v=0.05, pi=0.2)),
+                                             (16, 0, dict(v=0.01, region_off=[0, 50, 51, 130])), (64, 2, dict(v=0.05, pi=0.3, est_pi=True))])
+def test_sharded_blocked_kernel_on_one_device_matches_oracle(gpu, world, block, method, kw):
+    """Row sharding of the BLOCKED kernel (SURVEY 8e "B-many scalars blocked"): every worker CTA pushes the B partial sums of a block into
+    the accumulator ring of every rank, every rank's chain CTA derives the identical lists; the banded Gram is summed over the ranks at
+    set-up.  All ranks as ONE cooperative grid (ngp_run_group)."""
+    prob = make_problem(1500, 200, 9)
+    kw = dict(kw)
+    if "region_off" in kw:
+        kw["region_off"] = np.array(kw["region_off"] + [200] if kw["region_off"][-1] != 200 else kw["region_off"], dtype=np.int64)
+    ch_o, S = oracle_chain(prob, method, **kw)
+    ch = _sharded(prob, [0] * world, method, kernel="blocked", block=block, lookahead=5, max_ctas=5, min_rows=8, **kw)
+    for s in ch.shards:
+        s.set_rng(31, 4)
+    for _ in range(5):
+        ch_o.iteration(seed=31, chain=4)
+    ch.run(3)
+    ch.run(2)
+    st = ch.state()
+    assert st["shards"][0]["sets"][0]["beta"].shape == S.beta.shape
+    assert rel(st["sets"][0]["beta"], S.beta) < 1e-8 and np.array_equal(st["sets"][0]["delta"], S.delta)
+    assert rel(st["sets"][0]["varBeta"], S.varBeta) < 1e-8 and abs(st["varE"] / ch_o.varE - 1) < 1e-9 and rel(st["e"], ch_o.e) < 1e-8
+    for other in st["shards"][1:]:
+        assert np.array_equal(other["sets"][0]["beta"], st["shards"][0]["sets"][0]["beta"]) and other["varE"] == st["shards"][0]["varE"]
+    assert ch.shards[0].timing()["kernel_variant"] == 8
+    ch.close()
+
+
+def test_sharded_blocked_needs_the_global_gram(gpu):
+    prob = make_problem(400, 64, 3)
+    ch = ngp.ShardedChain([0, 0], max_ctas=4, kernel="literal")
+    ch.upload_genotypes(0, prob["codes"])
+    df, scale = O.marker_hyper(0.05)
+    for s in ch.shards:
+        s.configure(ngp._lib.CFG_KERNEL, ngp._lib.KERNEL_BLOCKED)      # blocked kernel, but the Grams were never summed over the ranks
+        s.set_prior(0, 2, df, scale, 0.05, pi_in=0.1, est_pi=True)
+        s.set_residual_prior(*O.residual_hyper(1.0)); s.set_intercept(True)
+    ch.set_phenotype(prob["y"])
+    with pytest.raises(ngp.NgpError) as ei:
+        ch.run(1)
+    assert ei.value.code == ngp._lib.EINVAL
+    ch.close()
+
+
+def test_sharded_blocked_chain_over_two_gpus(gpu):
+    if ngp._lib.lib().ngp_device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    prob = make_problem(6000, 400, 12)
+    kw = dict(v=0.05, pi=0.1, est_pi=True)
+    ch_o, S = oracle_chain(prob, 2, **kw)
+    ch = _sharded(prob, [0, 1], 2, max_ctas=40, kernel="blocked", block=64, lookahead=8, **kw)
+    for s in ch.shards:
+        s.set_rng(5, 0)
+    for _ in range(5):
+        ch_o.iteration(seed=5, chain=0)
+    ch.run(5)
+    st = ch.state()
+    assert rel(st["sets"][0]["beta"], S.beta) < 1e-8 and rel(st["e"], ch_o.e) < 1e-8
+    assert np.array_equal(st["shards"][0]["sets"][0]["beta"], st["shards"][1]["sets"][0]["beta"])
     ch.close()
 
 
