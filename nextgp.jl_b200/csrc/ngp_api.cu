@@ -548,9 +548,9 @@ static int choose_geometry(ngp_handle* h, int64_t n, int store2)
     int B = h->cfg_block;
     // Blocks of 64 markers halve the number of trips round the feedback loop (list -> residual version -> dots -> sums) against blocks of
     // 32, and the chain warp steps over 64 markers anyway.  Panels of up to 512 rows: 2-bit tiles of 64 markers (16 R bytes) stay
-    // resident with 12 blocks of look-ahead; int8 tiles (64 R bytes) use the refetch ring.  Larger panels: blocks of 64 for 2-bit tiles (refetch ring), blocks of 16 for int8
-    // (sweeps in profiles/r2/tune_*.jsonl).
-    if (!B) B = (R <= 512 || store2) ? 64 : 16;
+    // resident with 12 blocks of look-ahead; int8 tiles (64 R bytes) use the refetch ring.  Larger panels (the BIGR instantiation): blocks of 64 for 2-bit tiles and for int8 panels of up to
+    // 1024 rows (refetch ring of 2 stages: C3 21.3 -> 15.3 ms/sweep), blocks of 16 beyond (sweeps in profiles/r2/tune_*.jsonl).
+    if (!B) B = (R <= 1024 || store2) ? 64 : 16;
     const int64_t maxR = 4LL * kUpdThreads * kUpdGroups;     // residual rows the updater warps hold in registers
     if (R > maxR)
         return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA; at most %lld are supported", (long long)n, (long long)R, (long long)maxR);
@@ -572,7 +572,7 @@ static int choose_geometry(ngp_handle* h, int64_t n, int store2)
             if (D < dn_min) break;
             DN = std::max(dn_min, std::min(DN, D));
             const int nt_min = refetch ? 1 : D + 2;
-            int NT = refetch ? legal_nt(h->cfg_tile_stages ? h->cfg_tile_stages : (B == 64 ? 4 : 8)) : (h->cfg_tile_stages ? std::max(h->cfg_tile_stages, nt_min) : D + 4);
+            int NT = refetch ? legal_nt(h->cfg_tile_stages ? h->cfg_tile_stages : (B == 64 ? (R <= 512 ? 4 : 2) : 8)) : (h->cfg_tile_stages ? std::max(h->cfg_tile_stages, nt_min) : D + 4);
             // shrink the record ring of the chain CTA, the tile ring, then the look-ahead, until both CTA roles fit
             for (;;) {
                 for (int NR = kRecStages; NR >= 2; NR >>= 1) {
@@ -1420,7 +1420,6 @@ int ngp_sweep(ngp_handle* h, int set_id, double* ycorr, double varE, double* bet
     const size_t need = sizeof(int32_t) * (size_t)S.p_pad + sizeof(double) * 2 * kMaxClass * 2 + 64;
     if (h->stage_bytes < need) {
         if (h->stage) cudaFreeHost(h->stage);
-    if (h->err_pinned) cudaFreeHost(h->err_pinned);
         h->stage = nullptr; h->stage_bytes = 0;
         CU(cudaMallocHost((void**)&h->stage, need));
         h->stage_bytes = need;

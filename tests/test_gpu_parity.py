@@ -478,10 +478,17 @@ def _native_vs_oracle_at_scale(n, p, model, iters, seed, expect=None, tol=1e-7, 
     g.set_prior(0, method, *O.marker_hyper(v), v, pi_in=pi, est_pi=(method == 2))
     g.set_phenotype(pr["y"]); g.set_residual_prior(*O.residual_hyper(v_e)); g.set_intercept(True)
     g.set_rng(seed, 3)
+    g.run(1)                                        # (an untimed, unchecked first launch: ngp_timing then names the kernel variant)
     t = g.timing()
     if expect:
         for k, val in expect.items():
             assert t[k] == val if not callable(val) else val(t[k]), f"geometry {k} = {t[k]}"
+    g.close()
+    g = ngp.Sampler(0, **geom)
+    g.synth_genotypes(0, n, p, seed, pr["thr0"], pr["thr1"])
+    g.set_prior(0, method, *O.marker_hyper(v), v, pi_in=pi, est_pi=(method == 2))
+    g.set_phenotype(pr["y"]); g.set_residual_prior(*O.residual_hyper(v_e)); g.set_intercept(True)
+    g.set_rng(seed, 3)
     worst = 0.0
     try:
         for it in range(iters):
@@ -521,6 +528,8 @@ def test_oracle_parity_at_c5_geometry_refetch_ring(gpu):
 
 
 def test_oracle_parity_at_c3_geometry_bayesb(gpu):
-    """BASELINE config 3 rows: n = 100,000 x 512 markers BayesB (functions.jl:157-195): blocks of 16, 704 rows per CTA."""
-    _native_vs_oracle_at_scale(100000, 512, "BayesB", 3, 20261022, expect=dict(block=16, rows_per_cta=704))
+    """BASELINE config 3 rows: n = 100,000 x 512 markers BayesB (functions.jl:157-195), 704 rows per CTA: blocks of 64 on the refetch ring
+    (the BIGR instantiation; default since round 2) and the round-1 geometry (blocks of 16, resident tiles)."""
+    _native_vs_oracle_at_scale(100000, 512, "BayesB", 3, 20261022, expect=dict(block=64, rows_per_cta=704, refetch=1, kernel_variant=6))
+    _native_vs_oracle_at_scale(100000, 512, "BayesB", 2, 20261022, block=16, expect=dict(block=16, rows_per_cta=704))
     _native_vs_oracle_at_scale(100000, 512, "BayesB", 2, 20261022, storage="2bit", expect=dict(block=64, rows_per_cta=704))
