@@ -1107,7 +1107,8 @@ static void fill_params(ngp_handle* h, Params& P, int n_iter, int set_mask, int 
             P.peer[r] = h->peer[r];
         }
         P.bar_base = h->bar_count * (unsigned long long)P.T_all;
-        if (P.Tw_all > 255) P.cnt_bits = 11;              // up to 2047 arrivals per accumulator (three bits less of fixed-point resolution)
+        if (P.Tw_all > 255) P.cnt_bits = 11;
+        P.hier = (h->shard_world >= 4 || (h->cfg_opt >= 0 && (h->cfg_opt & 256))) && !(h->cfg_opt >= 0 && (h->cfg_opt & 512));   // rank-local pre-reduction              // up to 2047 arrivals per accumulator (three bits less of fixed-point resolution)
     }
 }
 

@@ -121,6 +121,7 @@ struct SyncArea {
     double part[kMaxCtas * 2];                  // phase-0 partials (e'e, sum e) per CTA
     // ---- body: persists across launches (monotonic accumulators, sequence-numbered list words)
     long long acc[kSlots * kMaxB * kAccStride]; // fixed-point reduction accumulators (monotonic; low bits count arrivals)
+    long long acc2[kSlots * kMaxB];             // row-sharded chain, rank-local pre-reduction: this rank's worker CTAs add here, its prep warps forward the total
     unsigned long long ll[kLLCopies][kNzRing * kLLSlotWords];   // changed-effect lists chain CTA -> worker CTAs (copy = CTA % kLLCopies);
                                                 // every 8-byte word = {payload32, seq32}, seq = global block number + 1
     long long prof[160 * kProf];                // per-CTA cycle counters of the last launch (this rank's CTAs): see ngp_get_profile
@@ -168,6 +169,8 @@ struct Params {
     int32_t cta_off, T_all;    // index of this rank's first CTA in the all-rank CTA numbering; CTAs of all ranks
     int32_t Tw_all;            // worker CTAs of all ranks (arrivals per accumulator)
     int32_t cnt_bits;          // arrival-count bits of an accumulator: 8, or 11 when Tw_all > 255
+    int32_t hier;              // row-sharded blocked sweep: 1 = the worker CTAs of a rank reduce locally (acc2) and the rank's prep warps push ONE total per
+                               // marker to every rank (n_ranks arrivals per accumulator instead of Tw_all: many ranks are atomic-throughput-bound otherwise)
     int32_t store2;            // 1: genotypes stored as 2-bit codes (NGP_STORE_2BIT), expanded to the INT8 operands on chip
     int32_t refetch;           // 1: tiles leave shared memory once their dots are formed; the columns of changed effects are re-read from L2/HBM
     int64_t n_total;           // individuals over all ranks (n is the local row count)

@@ -863,7 +863,10 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                         const long long sa = (long long)(tt ? v1 : v0);
                                         if (sa >= plim || sa <= -plim) atomicOr(&sy->err, 1);
                                         const long long rv = (long long)((unsigned long long)sa << cb) + 1;
-                                        if (sharded) {
+                                        if (sharded && P.hier) {
+                                            // row-sharded chain, many ranks: reduce inside the rank first (its prep warps forward one total per marker)
+                                            red_add_u64(sy->acc2 + (size_t)(gidx & (kSlots - 1)) * kMaxB + (size_t)(mg * 16 + g + 8 * tt), rv);
+                                        } else if (sharded) {
                                             // row-sharded chain: the partial sums of the block go into the accumulator ring of EVERY rank (NVLink peer memory)
                                             const size_t aoff = (size_t)(gidx & (kSlots - 1)) * kMaxB * kAccStride + (size_t)(mg * 16 + g + 8 * tt) * kAccStride;
                                             for (int r = 0; r < P.n_ranks; ++r) red_add_u64_sys(P.peer[r]->acc + aoff, rv);
@@ -1257,6 +1260,8 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                         // ------------------------------------------------------------------ prep warps
                         const int pw = warp - kFirstPrepWarp;
                         int m0 = (int)((unsigned)(pw - (int)(gblk & (kPrepWarps - 1))) & (kPrepWarps - 1));   // first m with (gblk+m) % kPrepWarps == pw
+                        const bool hier = sharded && P.hier;
+                        const long long arr_exp = hier ? (long long)P.n_ranks : arr_all;      // arrivals per accumulator of this rank
                         for (int m = m0; m < nblk; m += kPrepWarps) {
                             const unsigned gidx = gblk + (unsigned)m;
                             const unsigned sg = gidx >> SBS;
@@ -1354,6 +1359,31 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                             long long cur[NB];
 #pragma unroll
                             for (int b = 0; b < NB; ++b) cur[b] = 0;
+                            if (hier) {
+                                // stage 1: wait for the Tw worker CTAs of THIS rank, forward the rank's total of every marker to every rank.  The staging
+                                // accumulators start from zero and are reset here: nobody adds to a slot again before its block has been consumed
+                                // (a worker is never kSlots blocks ahead of the chain)
+                                long long* a2 = sy->acc2 + (size_t)slot * kMaxB;
+                                long long c2[NB];
+                                for (;;) {
+                                    bool done = true;
+#pragma unroll
+                                    for (int b = 0; b < NB; ++b) {
+                                        c2[b] = live[b] ? ld_relaxed_s64(a2 + b * 32 + lane) : 0;
+                                        if (live[b]) done = done && ((c2[b] & cmask) == (long long)Tw);
+                                    }
+                                    if (__all_sync(0xffffffffu, done)) break;
+                                }
+#pragma unroll
+                                for (int b = 0; b < NB; ++b)
+                                    if (live[b]) {
+                                        st_relaxed_u64(reinterpret_cast<unsigned long long*>(a2 + b * 32 + lane), 0ull);
+                                        const long long v = (c2[b] - (long long)Tw) >> cb;                  // exact integer sum of this rank's rows
+                                        const long long rv = (long long)((unsigned long long)v << cb) + 1;
+                                        const size_t aoff = (size_t)slot * kMaxB * kAccStride + (size_t)(b * 32 + lane) * kAccStride;
+                                        for (int r = 0; r < P.n_ranks; ++r) red_add_u64_sys(P.peer[r]->acc + aoff, rv);
+                                    }
+                            }
                             if (!(dbg & 2)) {
                                 // pipelined like the list polling of the worker CTAs: kPollPipe probes in flight, kPollGap cycles apart
                                 long long pv_[kPollPipe][NB];
@@ -1368,7 +1398,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
 #pragma unroll
                                     for (int b = 0; b < NB; ++b) {
                                         cur[b] = pv_[0][b];
-                                        if (live[b] && pvalid[0]) done = done && (((cur[b] - prev[slot * B + b * 32 + lane]) & cmask) == arr_all);
+                                        if (live[b] && pvalid[0]) done = done && (((cur[b] - prev[slot * B + b * 32 + lane]) & cmask) == arr_exp);
                                     }
                                     const bool valid0 = pvalid[0];
 #pragma unroll
@@ -1410,7 +1440,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                 const int q = b * 32 + lane;
                                 if (live[b]) {
                                     long long* pv = prev + slot * B + q;
-                                    const double A = (double)((cur[b] - *pv - arr_all) >> cb) * fx_inv;
+                                    const double A = (double)((cur[b] - *pv - arr_exp) >> cb) * fx_inv;
                                     if (!(dbg & 2)) *pv = cur[b];
                                     rbase[pw * B + q] = (A - mean[b] * Stot) + far[b];       // x_q'e as the dots saw it + the corrections above
                                 }

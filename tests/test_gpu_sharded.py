@@ -56,13 +56,13 @@ def test_sharded_chain_on_one_device_matches_oracle(gpu, world, method, kw):
     ch.close()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world,hier", [(2, False), (3, False), (3, True), (4, None)])
 @pytest.mark.parametrize("block,method,kw", [(32, 2, dict(v=0.05, pi=0.1, est_pi=True)), (64, 1, dict(v=0.05, pi=0.2)),
                                              (16, 0, dict(v=0.01, region_off=[0, 50, 51, 130])), (64, 2, dict(v=0.05, pi=0.3, est_pi=True))])
-def test_sharded_blocked_kernel_on_one_device_matches_oracle(gpu, world, block, method, kw):
+def test_sharded_blocked_kernel_on_one_device_matches_oracle(gpu, world, hier, block, method, kw):
     """Row sharding of the BLOCKED kernel (SURVEY 8e "B-many scalars blocked"): every worker CTA pushes the B partial sums of a block into
-    the accumulator ring of every rank, every rank's chain CTA derives the identical lists; the banded Gram is summed over the ranks at
-    set-up.  All ranks as ONE cooperative grid (ngp_run_group)."""
+    the accumulator ring of every rank (or, with the rank-local pre-reduction, the rank's prep warps push one total per marker), every rank's
+    chain CTA derives the identical lists; the banded Gram is summed over the ranks at set-up.  All ranks as ONE cooperative grid (ngp_run_group)."""
     prob = make_problem(1500, 200, 9)
     kw = dict(kw)
     if "region_off" in kw:
@@ -71,6 +71,8 @@ def test_sharded_blocked_kernel_on_one_device_matches_oracle(gpu, world, block, 
     ch = _sharded(prob, [0] * world, method, kernel="blocked", block=block, lookahead=5, max_ctas=5, min_rows=8, **kw)
     for s in ch.shards:
         s.set_rng(31, 4)
+        if hier is not None:        # rank-local pre-reduction (one push per rank and marker): forced on / off; None = the default (on from 4 ranks)
+            s.configure(ngp._lib.CFG_OPT, 256 if hier else 512)
     for _ in range(5):
         ch_o.iteration(seed=31, chain=4)
     ch.run(3)
