@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--model", default="BayesC")
     ap.add_argument("--storage", default="i8", choices=["i8", "2bit"], help="device storage of the genotype codes (2bit: NGP_STORE_2BIT, a quarter of the HBM bytes per sweep)")
     ap.add_argument("--regions", type=int, default=0, help="BayesPR with one variance per window of this many SNPs (BayesPR(r, v): mme.jl:345-348, misc.jl:163-215) on 30 equal chromosomes")
+    ap.add_argument("--cfg-opt", type=int, default=-1, help="NGP_CFG_OPT mask (-1 = the library's defaults)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--weighted", action="store_true",
                     help="diagnostic: residual weights w ~ U(0.5, 2) (E.str == \"D\", mme.jl:70-73); the set is swept by the per-marker kernel")
@@ -315,6 +316,8 @@ def main():
         args.kernel = args.shard_kernel
         args.no_e2e = True
     s = ngp.Sampler(local, kernel=args.kernel, block=args.block, storage=args.storage)
+    if args.cfg_opt >= 0:
+        s.configure(L.CFG_OPT, args.cfg_opt)
     stream = torch.cuda.current_stream()
     s.set_stream(stream.cuda_stream)
     df, scale = 4.0, v * 0.5

@@ -79,7 +79,7 @@ enum ngp_config_key {
     NGP_CFG_PROFILE = 7,       /* 1 = launch the instrumented kernel (cycle counters for ngp_get_profile) */
     NGP_CFG_VERSIONS = 9,      /* versions of the fixed-point residual kept per worker CTA (0 = auto; before the first upload) */
     NGP_CFG_REFETCH = 10,      /* tile ring: 0 tiles stay resident until applied to e, 1 only until their dots are formed (changed columns re-read from L2), -1 auto; before the first upload */
-    NGP_CFG_OPT = 11,          /* bit mask of schedule options of the blocked sweep (results unchanged): 1 = genotype tiles streamed with an L2 evict-first policy, 2 = far cross-Gram rows prefetched into L2 when an effect changes; row-sharded blocked sweep: 256 = rank-local pre-reduction on (default from 4 ranks), 512 = off; -1 = auto */
+    NGP_CFG_OPT = 11,          /* bit mask of schedule options of the blocked sweep (results unchanged): 1 = genotype tiles streamed with an L2 evict-first policy, 2 = far cross-Gram rows prefetched into L2 when an effect changes; row-sharded blocked sweep: 512 = rank-local pre-reduction off (on by default); -1 = auto */
     NGP_CFG_DEBUG = 8          /* timing experiments that decouple the kernel's roles; RESULTS ARE INVALID when non-zero */
 };
 

@@ -71,8 +71,8 @@ def test_sharded_blocked_kernel_on_one_device_matches_oracle(gpu, world, hier, b
     ch = _sharded(prob, [0] * world, method, kernel="blocked", block=block, lookahead=5, max_ctas=5, min_rows=8, **kw)
     for s in ch.shards:
         s.set_rng(31, 4)
-        if hier is not None:        # rank-local pre-reduction (one push per rank and marker): forced on / off; None = the default (on from 4 ranks)
-            s.configure(ngp._lib.CFG_OPT, 256 if hier else 512)
+        if hier is False:           # rank-local pre-reduction (one push per rank and marker) is the default; 512 switches it off
+            s.configure(ngp._lib.CFG_OPT, 512)
     for _ in range(5):
         ch_o.iteration(seed=31, chain=4)
     ch.run(3)
