@@ -765,13 +765,15 @@ int ngp_download_genotypes(ngp_handle* h, int set_id, int64_t j0, int64_t j1, in
     return NGP_OK;
 }
 
+static int ensure_weighted_moments(ngp_handle* h, int s);
 int ngp_get_column_stats(ngp_handle* h, int set_id, double* mean, double* mpm)
 {
     if (!h || set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_geno) return fail(h, NGP_EINVAL, "ngp_get_column_stats: no such set");
     SetHost& S = h->sets[set_id];
     CU(cudaSetDevice(h->device));
     if (mean) CU(cpy(h, mean, S.mean, sizeof(double) * S.p, cudaMemcpyDeviceToHost));
-    if (mpm) CU(cpy(h, mpm, (h->w && S.w_ready) ? S.dw : S.d, sizeof(double) * S.p, cudaMemcpyDeviceToHost));   // weighted once sampled with weights
+    if (h->w) { int rcw = ensure_weighted_moments(h, set_id); if (rcw) return rcw; }      // weighted mpm as soon as weights are set, whatever the call order
+    if (mpm) CU(cpy(h, mpm, (h->w && S.w_ready) ? S.dw : S.d, sizeof(double) * S.p, cudaMemcpyDeviceToHost));
     return NGP_OK;
 }
 
@@ -1170,6 +1172,22 @@ static int launch_joint(ngp_handle* h, int n_iter, int do_varE, int do_mu, doubl
     return check_kernel_error(h);
 }
 
+// weighted residuals: mpm_j = sum_i w_i x_ij^2 and sum_i w_i x_ij of a marker set (mme.jl:299-303), once per weight vector
+static int ensure_weighted_moments(ngp_handle* h, int s)
+{
+    SetHost& S = h->sets[s];
+    if (!h->w || !S.have_geno || S.w_ready) return NGP_OK;
+    if (h->store2 > 0) return NGP_OK;                  // (2-bit tiles: the weighted path is refused at launch)
+    if (!S.dw) { CU(dalloc(&S.dw, S.p_pad)); CU(dalloc(&S.wcs, S.p_pad)); }
+    CU(zero(h, S.dw, 0, sizeof(double) * S.p_pad));
+    CU(zero(h, S.wcs, 0, sizeof(double) * S.p_pad));
+    weighted_moments_kernel<<<(unsigned)S.p, 256, 0, h->stream>>>(S.geno, h->n, h->R, h->B, S.p_pad / h->B, S.p, S.mean, h->w, S.dw, S.wcs);
+    CU(cudaGetLastError());
+    S.w_ready = true;
+    h->sets_dirty = true;
+    return NGP_OK;
+}
+
 // everything up to the launch itself: checks, weighted set-up, Params, kernel variant, bookkeeping of the global block / barrier counters
 static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_mu, double varE_in, int accumulate, Params& P, const void*& kfn, bool group)
 {
@@ -1230,18 +1248,8 @@ static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, 
             CU(cudaStreamSynchronize(h->stream));
             h->fx_w_ready = true;
         }
-        for (int s = 0; s < h->n_sets; ++s) {
-            SetHost& S = h->sets[s];
-            if (!((set_mask >> s) & 1)) continue;
-            if (S.w_ready) continue;
-            if (!S.dw) { CU(dalloc(&S.dw, S.p_pad)); CU(dalloc(&S.wcs, S.p_pad)); }
-            CU(zero(h, S.dw, 0, sizeof(double) * S.p_pad));
-            CU(zero(h, S.wcs, 0, sizeof(double) * S.p_pad));
-            weighted_moments_kernel<<<(unsigned)S.p, 256, 0, h->stream>>>(S.geno, h->n, h->R, h->B, S.p_pad / h->B, S.p, S.mean, h->w, S.dw, S.wcs);
-            CU(cudaGetLastError());
-            S.w_ready = true;
-            h->sets_dirty = true;
-        }
+        for (int s = 0; s < h->n_sets; ++s)
+            if ((set_mask >> s) & 1) { int rcw = ensure_weighted_moments(h, s); if (rcw) return rcw; }
     }
     int rc = sync_sets(h);
     if (rc) return rc;

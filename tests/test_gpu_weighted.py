@@ -61,6 +61,7 @@ def test_weighted_replay_parity(gpu, kernel, name, method, kw):
     ro = kw2.pop("region_off", None)
     g = gpu_sampler(prob, method, region_off=None if ro is None else np.array(ro), kernel=kernel, **kw2)
     g.set_residual_weights(w)
+    assert rel(g.column_stats(0)[1], S.mpm) < 1e-12     # weighted as soon as the weights are set, whatever the call order
     g.set_replay(logs)
     for it in range(10):
         g.run(1)
