@@ -197,6 +197,7 @@ typedef struct ngp_timing {
                                  /* weighted residuals, summary-statistic BayesR, > 4 BayesR classes, row sharding), 4 tuple, 5 shard group, 6 blocked     */
                                  /* with > 512 rows per CTA, 7 blocked BayesR; -1 none yet                                                                */
     int32_t refetch, storage_2bit, pad_;   /* tile-ring mode, device storage of the genotypes */
+    double sum_run_ms;           /* device time of ALL ngp_run / ngp_sweep kernels of this handle so far (sum of the per-launch event times) */
 } ngp_timing;
 
 /* ---- lifetime ------------------------------------------------------------ */

@@ -70,7 +70,8 @@ class Timing(C.Structure):
     _fields_ = [("last_run_ms", C.c_double), ("launches", C.c_int64), ("ctas", C.c_int32), ("threads", C.c_int32),
                 ("block", C.c_int32), ("rows_per_cta", C.c_int32), ("smem_bytes", C.c_int64),
                 ("lookahead", C.c_int32), ("near_depth", C.c_int32), ("tile_stages", C.c_int32), ("record_stages", C.c_int32),
-                ("kernel_variant", C.c_int32), ("refetch", C.c_int32), ("storage_2bit", C.c_int32), ("pad_", C.c_int32)]
+                ("kernel_variant", C.c_int32), ("refetch", C.c_int32), ("storage_2bit", C.c_int32), ("pad_", C.c_int32),
+                ("sum_run_ms", C.c_double)]
 
 
 def translation_units() -> list[tuple[str, str, list[str]]]:

@@ -343,6 +343,7 @@ struct ngp_handle {
     // stats
     int64_t launches = 0;
     int* err_pinned = nullptr;  // pinned landing place of the kernel's error word: copied on the stream right behind the launch, ONE synchronisation per run
+    double sum_run_ms = 0.0;    // device time of all sweep launches so far
     int last_variant = -1;      // kernel variant of the last launch (ngp_timing.kernel_variant)
     uint64_t gblk = 0;          // blocks swept so far by the blocked kernel (numbers the list words and accumulator slots)
     bool timed = false;
@@ -1329,6 +1330,7 @@ static int launch(ngp_handle* h, int n_iter, int set_mask, int do_varE, int do_m
     if (defer_sync) return NGP_OK;                 // the caller queues its device-to-host copies first and synchronises once
     CU(cudaMemcpyAsync(h->err_pinned, &h->sync->err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    { float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->sum_run_ms += ms; }
     return kernel_error_code(h, *h->err_pinned);
 }
 
@@ -1921,7 +1923,7 @@ int ngp_get_timing(ngp_handle* h, ngp_timing* out)
     memset(out, 0, sizeof *out);
     out->launches = h->launches; out->ctas = h->Tw ? h->Tw + 1 : 0; out->threads = kThreads; out->block = h->B; out->rows_per_cta = h->R;
     out->smem_bytes = h->L.total; out->lookahead = h->D; out->near_depth = h->DN; out->tile_stages = h->NT; out->record_stages = h->NR;
-    out->kernel_variant = h->last_variant; out->refetch = h->refetch; out->storage_2bit = h->store2 > 0;
+    out->kernel_variant = h->last_variant; out->refetch = h->refetch; out->storage_2bit = h->store2 > 0; out->sum_run_ms = h->sum_run_ms;
     if (h->timed) {
         float ms = 0.f;
         CU(cudaEventSynchronize(h->ev1));

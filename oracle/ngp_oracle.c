@@ -86,7 +86,8 @@ void ngo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  *   ctr3 = chain id                                                      */
 enum {
     NGO_P_CHI2_E = 0, NGO_P_Z_MU = 1, NGO_P_U = 2, NGO_P_Z = 3,
-    NGO_P_CHI2_B = 4, NGO_P_PI_A = 5, NGO_P_PI_B = 6, NGO_P_IW = 7
+    NGO_P_CHI2_B = 4, NGO_P_PI_A = 5, NGO_P_PI_B = 6, NGO_P_IW = 7,
+    NGO_P_U_ANNOT = 8, NGO_P_G_ANNOT = 9      /* BayesRCpi: the Categorical draw of the annotation, the gammas of sampleProb */
 };
 
 typedef struct { uint64_t seed; uint32_t chain; uint32_t iter; uint32_t set_id; } ngo_stream;
@@ -858,6 +859,181 @@ int ngo_r_sweep(const ngo_r_set* S, ngo_r_state* T, double* e, double varE, ngo_
             for (int v = 0; v < nc; ++v) V->dir_pi[v] = g[v] / tg;
         }
         for (int v = 0; v < nc; ++v) { T->piHat[v] = V->dir_pi[v]; T->logPi[v] = log(V->dir_pi[v]); }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* BayesRCpi (functions.jl:291-360) and BayesRCplus (functions.jl:362-419),   */
+/* wiring mme.jl:385-418: annotations (p x nAnnot integer matrix), one common  */
+/* variance and one vector of class proportions PER ANNOTATION.                */
+/* Variates (explicit, like everywhere in this oracle):                        */
+/*   RCpi  : u_annot[p] (Categorical: Distributions' sampler draws ONE uniform */
+/*           and walks the cumulative probabilities while cp <= u),            */
+/*           dirp[p][nA] (the RESULT of sampleProb = Dirichlet(annotInput +    */
+/*           e_chosen) on the non-zero annotations of the locus, 0 elsewhere), */
+/*           u[p][nc] (a fresh uniform per cumulative comparison, :327), z[p]  */
+/*   RCplus: u[p][nA][nc], z[p][nA]                                            */
+/*   both  : chi2_b[nA], dir_pi[nA][nc]                                        */
+/* ------------------------------------------------------------------------- */
+#define NGO_RC_MAXA 16
+#define NGO_RC_MAXC 16
+typedef struct {
+    int64_t n, p;
+    const double* X;          /* centred, n x p col-major */
+    const double* mpm;
+    const double* lhs0;       /* may be NULL */
+    const double* rhs0;       /* may be NULL */
+    int32_t n_class, n_annot, est_pi, plus;      /* plus: 0 = BayesRCpi, 1 = BayesRCplus */
+    const double* v_class;    /* [n_class] */
+    const int32_t* annot;     /* [p][n_annot] annotInput (mme.jl:394) */
+    double df, scale;
+    int32_t set_id, pad_;
+} ngo_rc_set;
+
+typedef struct {
+    double* beta;             /* [p] */
+    int64_t* delta;           /* [p] 1-based class */
+    int64_t* annot_cat;       /* [p] 1-based annotation (RCpi; mme.jl:403) */
+    double* varBeta;          /* [n_annot] */
+    double* piHat;            /* [n_annot][n_class] */
+    double* logPi;            /* [n_annot][n_class] */
+    double* annot_prob;       /* [p][n_annot] (RCpi; mme.jl:395) */
+} ngo_rc_state;
+
+typedef struct {
+    int32_t replay, pad_;
+    uint64_t seed;
+    uint32_t chain, iter;
+    double* u_annot;
+    double* dirp;
+    double* u;
+    double* z;
+    double* chi2_b;
+    double* dir_pi;
+} ngo_rc_variates;
+
+int ngo_rc_sweep(const ngo_rc_set* S, ngo_rc_state* T, double* e, double varE, ngo_rc_variates* V)
+{
+    const int64_t n = S->n, p = S->p;
+    const int nc = S->n_class, nA = S->n_annot;
+    if (nc < 1 || nc > NGO_RC_MAXC || nA < 1 || nA > NGO_RC_MAXA) return -1;
+    double varc[NGO_RC_MAXA][NGO_RC_MAXC], lhs[NGO_RC_MAXA][NGO_RC_MAXC], ExpLogL[NGO_RC_MAXA][NGO_RC_MAXC], sumS[NGO_RC_MAXA];
+    int64_t nLoci[NGO_RC_MAXA][NGO_RC_MAXC], nNonZero[NGO_RC_MAXA];
+    const double iVarE = 1.0 / varE;
+    ngo_stream s = {V->seed, V->chain, V->iter, (uint32_t)S->set_id};
+    for (int a = 0; a < nA; ++a) {
+        sumS[a] = 0.0; nNonZero[a] = 0;
+        for (int v = 0; v < nc; ++v) { varc[a][v] = T->varBeta[a] * S->v_class[v]; nLoci[a][v] = 0; }      /* :298 / :369 */
+    }
+    for (int64_t j = 0; j < p; ++j) {
+        const double* x = S->X + j * n;
+        const int32_t* an = S->annot + j * nA;
+        daxpy(n, T->beta[j], x, e);                                                              /* :303 / :374 */
+        if (!S->plus) {
+            const double rhs = ddot(n, x, e) * iVarE + (S->rhs0 ? S->rhs0[j] : 0.0);                /* :304 */
+            double Sa[NGO_RC_MAXA], pa[NGO_RC_MAXA], tot2 = 0.0;
+            for (int a = 0; a < nA; ++a) {
+                Sa[a] = 0.0;
+                for (int v = 0; v < nc; ++v) { lhs[a][v] = 0.0; ExpLogL[a][v] = 0.0; }               /* zeros(nAnnot,nVarClass) :305-306 */
+                if (an[a] == 0) continue;                                                        /* annotNonZeroPos :307 */
+                for (int v = 0; v < nc; ++v) {
+                    lhs[a][v] = varc[a][v] == 0.0 ? 0.0 : S->mpm[j] * iVarE + (S->lhs0 ? S->lhs0[j] : 0.0) + 1.0 / varc[a][v];
+                    const double logLv = varc[a][v] == 0.0 ? T->logPi[a * nc + v]
+                                                           : -0.5 * (log(varc[a][v] * lhs[a][v]) - ((rhs * rhs) / lhs[a][v])) + T->logPi[a * nc + v];
+                    ExpLogL[a][v] = exp(logLv);
+                    Sa[a] += ExpLogL[a][v];                                                      /* sum(ExpLogL,dims=2) :315 */
+                }
+            }
+            for (int a = 0; a < nA; ++a) { pa[a] = T->annot_prob[j * nA + a] * Sa[a]; tot2 += pa[a]; }    /* :315-316 */
+            for (int a = 0; a < nA; ++a) pa[a] /= tot2;                                           /* :317 */
+            if (!V->replay) V->u_annot[j] = stream_uniform(&s, NGO_P_U_ANNOT, (uint32_t)j, 0, 0);
+            /* rand(Categorical(probAnnot)) :319 — Distributions.jl: draw = rand(); cp = p[1]; i = 1; while cp <= draw && i < n: i += 1; cp += p[i] */
+            int A = 0;
+            { double cp = pa[0]; while (cp <= V->u_annot[j] && A < nA - 1) { ++A; cp += pa[A]; } }
+            if (!(tot2 == tot2) || an[A] == 0) return -3;             /* findfirst(isequal(A), annotNonZeroPos) finds nothing: the reference errors (:320) */
+            /* sampleProb (:322, :541-544): Dirichlet(annotInput[locus, nonzero] with +1 at the chosen annotation) */
+            if (!V->replay) {
+                double g[NGO_RC_MAXA], tg = 0.0;
+                for (int a = 0; a < nA; ++a) {
+                    g[a] = 0.0;
+                    if (an[a] == 0) continue;
+                    g[a] = stream_gamma(&s, NGO_P_G_ANNOT, (uint32_t)j, (uint32_t)a, (double)an[a] + (a == A ? 1.0 : 0.0));
+                    tg += g[a];
+                }
+                for (int a = 0; a < nA; ++a) V->dirp[j * nA + a] = an[a] == 0 ? 0.0 : g[a] / tg;
+            }
+            for (int a = 0; a < nA; ++a) if (an[a] != 0) T->annot_prob[j * nA + a] = V->dirp[j * nA + a];
+            if (!V->replay) for (int v = 0; v < nc; ++v) V->u[j * nc + v] = stream_uniform(&s, NGO_P_U, (uint32_t)j, 0, (uint32_t)v);
+            int cls = -1;
+            double cum = 0.0;
+            for (int v = 0; v < nc; ++v) {                                                       /* :325-327 */
+                cum += ExpLogL[A][v] / Sa[A];
+                if (cum >= V->u[j * nc + v]) { cls = v; break; }
+            }
+            if (cls < 0) return -2;
+            T->delta[j] = cls + 1;                                                               /* :329 */
+            T->annot_cat[j] = A + 1;                                                             /* :330 */
+            nLoci[A][cls] += 1;
+            if (varc[A][cls] != 0.0) {                                                           /* :333-341 */
+                nNonZero[A] += 1;
+                if (!V->replay) V->z[j] = stream_normal(&s, NGO_P_Z, (uint32_t)j, 0, 0);
+                const double b = rhs / lhs[A][cls] + sqrt(1.0 / lhs[A][cls]) * V->z[j];
+                T->beta[j] = b;
+                daxpy(n, -1.0 * b, x, e);
+                sumS[A] += (b * b) / S->v_class[cls];
+            } else {
+                T->beta[j] = 0.0;                                                                /* :342 */
+            }
+        } else {
+            double tempBeta = 0.0;                                                               /* :377 */
+            for (int a = 0; a < nA; ++a) {
+                if (an[a] == 0) continue;                                                        /* :378 */
+                const double rhs = ddot(n, x, e) * iVarE + (S->rhs0 ? S->rhs0[j] : 0.0);            /* :379 (ycorr already holds the earlier annotations' axpys) */
+                double tot = 0.0;
+                for (int v = 0; v < nc; ++v) {
+                    lhs[a][v] = varc[a][v] == 0.0 ? 0.0 : S->mpm[j] * iVarE + (S->lhs0 ? S->lhs0[j] : 0.0) + 1.0 / varc[a][v];
+                    const double logLv = varc[a][v] == 0.0 ? T->logPi[a * nc + v]
+                                                           : -0.5 * (log(varc[a][v] * lhs[a][v]) - ((rhs * rhs) / lhs[a][v])) + T->logPi[a * nc + v];
+                    ExpLogL[a][v] = exp(logLv);
+                    tot += ExpLogL[a][v];
+                }
+                if (!V->replay) for (int v = 0; v < nc; ++v) V->u[(j * nA + a) * nc + v] = stream_uniform(&s, NGO_P_U, (uint32_t)j, (uint32_t)a, (uint32_t)v);
+                int cls = -1;
+                double cum = 0.0;
+                for (int v = 0; v < nc; ++v) {                                                   /* :385-387 */
+                    cum += ExpLogL[a][v] / tot;
+                    if (cum >= V->u[(j * nA + a) * nc + v]) { cls = v; break; }
+                }
+                if (cls < 0) return -2;
+                T->delta[j] = cls + 1;                                                           /* :388 (the last annotation's class stays) */
+                nLoci[a][cls] += 1;
+                double b = 0.0;
+                if (varc[a][cls] != 0.0) {                                                       /* :391-397 */
+                    nNonZero[a] += 1;
+                    if (!V->replay) V->z[j * nA + a] = stream_normal(&s, NGO_P_Z, (uint32_t)j, (uint32_t)a, 0);
+                    b = rhs / lhs[a][cls] + sqrt(1.0 / lhs[a][cls]) * V->z[j * nA + a];
+                    sumS[a] += (b * b) / S->v_class[cls];
+                }
+                tempBeta += b;                                                                   /* :400 */
+                daxpy(n, -1.0 * b, x, e);                                                        /* :401 */
+            }
+            T->beta[j] = tempBeta;                                                               /* :403 */
+        }
+    }
+    for (int a = 0; a < nA; ++a) {                                                               /* :347-349 / :408-410 */
+        if (!V->replay) V->chi2_b[a] = stream_chisq(&s, NGO_P_CHI2_B, (uint32_t)a, 0, S->df + (double)nNonZero[a]);
+        T->varBeta[a] = (S->scale * S->df + sumS[a]) / V->chi2_b[a];
+    }
+    if (S->est_pi) {                                                                             /* :352-359 / :413-418 */
+        for (int a = 0; a < nA; ++a) {
+            if (!V->replay) {
+                double g[NGO_RC_MAXC], tg = 0.0;
+                for (int v = 0; v < nc; ++v) { g[v] = stream_gamma(&s, NGO_P_PI_A, (uint32_t)a, (uint32_t)v, (double)nLoci[a][v] + 1.0); tg += g[v]; }
+                for (int v = 0; v < nc; ++v) V->dir_pi[a * nc + v] = g[v] / tg;
+            }
+            for (int v = 0; v < nc; ++v) { T->piHat[a * nc + v] = V->dir_pi[a * nc + v]; T->logPi[a * nc + v] = log(V->dir_pi[a * nc + v]); }
+        }
     }
     return 0;
 }

@@ -80,6 +80,22 @@ class _RVariates(C.Structure):
                 ("u", C.c_void_p), ("z", C.c_void_p), ("chi2_b", C.c_void_p), ("dir_pi", C.c_void_p)]
 
 
+class _RCSet(C.Structure):
+    _fields_ = [("n", C.c_int64), ("p", C.c_int64), ("X", C.c_void_p), ("mpm", C.c_void_p), ("lhs0", C.c_void_p), ("rhs0", C.c_void_p),
+                ("n_class", C.c_int32), ("n_annot", C.c_int32), ("est_pi", C.c_int32), ("plus", C.c_int32), ("v_class", C.c_void_p),
+                ("annot", C.c_void_p), ("df", C.c_double), ("scale", C.c_double), ("set_id", C.c_int32), ("pad_", C.c_int32)]
+
+
+class _RCState(C.Structure):
+    _fields_ = [("beta", C.c_void_p), ("delta", C.c_void_p), ("annot_cat", C.c_void_p), ("varBeta", C.c_void_p), ("piHat", C.c_void_p),
+                ("logPi", C.c_void_p), ("annot_prob", C.c_void_p)]
+
+
+class _RCVariates(C.Structure):
+    _fields_ = [("replay", C.c_int32), ("pad_", C.c_int32), ("seed", C.c_uint64), ("chain", C.c_uint32), ("iter", C.c_uint32),
+                ("u_annot", C.c_void_p), ("dirp", C.c_void_p), ("u", C.c_void_p), ("z", C.c_void_p), ("chi2_b", C.c_void_p), ("dir_pi", C.c_void_p)]
+
+
 class _MbVariates(C.Structure):
     _fields_ = [("replay", C.c_int32), ("pad_", C.c_int32), ("seed", C.c_uint64),
                 ("chain", C.c_uint32), ("iter", C.c_uint32), ("z", C.c_void_p),
@@ -126,6 +142,8 @@ def lib():
         L.ngo_synth_codes.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ngo_philox4x32_10.restype = None
         L.ngo_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ngo_rc_sweep.restype = C.c_int
+        L.ngo_rc_sweep.argtypes = [C.POINTER(_RCSet), C.POINTER(_RCState), C.c_void_p, C.c_double, C.POINTER(_RCVariates)]
         L.ngo_set_threads.argtypes = [C.c_int]
         L.ngo_max_threads.restype = C.c_int
         L.ngo_sample_fixed.restype = None
@@ -489,3 +507,57 @@ class MultiBreedOracle:
         rc = L.ngo_mb_sweep(C.byref(S), _ptr(self.beta), _ptr(self.varBeta), _ptr(e), varE, C.byref(V))
         assert rc == 0, rc
         return {"z": z, "iw_chi2": iw_chi2, "iw_z": iw_z}
+
+
+class BayesRCOracle:
+    """BayesRCpi (functions.jl:291-360; plus=False) and BayesRCplus (functions.jl:362-419; plus=True) with the wiring of mme.jl:385-418:
+    annot (p x nAnnot integer matrix), variance classes v_class, class proportions pi shared by all annotations at the start, ONE variance
+    per annotation (varBeta = fill(v, nAnnot), mme.jl:516).  delta = 1-based class, annot_cat = 1-based annotation (RCpi)."""
+
+    def __init__(self, X, mpm, pi, v_class, v: float, annot, est_pi: bool = False, plus: bool = False, lhs0=None, rhs0=None, set_id: int = 0):
+        self.X = np.asfortranarray(X, dtype=np.float64)
+        self.mpm = np.ascontiguousarray(mpm, dtype=np.float64)
+        self.n, self.p = self.X.shape
+        self.v_class = np.ascontiguousarray(v_class, dtype=np.float64)
+        self.nc = len(self.v_class)
+        self.annot = np.ascontiguousarray(annot, dtype=np.int32)
+        assert self.annot.shape[0] == self.p
+        self.nA = self.annot.shape[1]
+        self.piHat = np.tile(np.asarray(pi, dtype=np.float64), (self.nA, 1)).copy()         # mme.jl:392
+        self.logPi = np.log(self.piHat)                                                      # mme.jl:390
+        with np.errstate(invalid="ignore", divide="ignore"):
+            self.annot_prob = np.ascontiguousarray(self.annot / self.annot.sum(1, keepdims=True), dtype=np.float64)   # mme.jl:395
+        self.df, self.scale = marker_hyper(v)
+        self.est_pi, self.plus = est_pi, plus
+        self.lhs0 = None if lhs0 is None else np.ascontiguousarray(lhs0, dtype=np.float64)
+        self.rhs0 = None if rhs0 is None else np.ascontiguousarray(rhs0, dtype=np.float64)
+        self.beta = np.zeros(self.p)
+        self.delta = np.ones(self.p, dtype=np.int64)
+        self.annot_cat = np.zeros(self.p, dtype=np.int64)                                    # mme.jl:403
+        self.varBeta = np.full(self.nA, float(v))
+        self.set_id = set_id
+
+    def sweep(self, e: np.ndarray, varE: float, it: int, seed: int = 0, chain: int = 0, replay: dict | None = None) -> dict:
+        L = lib()
+        S = _RCSet()
+        S.n, S.p, S.X, S.mpm = self.n, self.p, _ptr(self.X), _ptr(self.mpm)
+        S.lhs0 = _ptr(self.lhs0) if self.lhs0 is not None else None
+        S.rhs0 = _ptr(self.rhs0) if self.rhs0 is not None else None
+        S.n_class, S.n_annot, S.est_pi, S.plus = self.nc, self.nA, int(self.est_pi), int(self.plus)
+        S.v_class, S.annot, S.df, S.scale, S.set_id = _ptr(self.v_class), _ptr(self.annot), self.df, self.scale, self.set_id
+        T = _RCState()
+        T.beta, T.delta, T.annot_cat, T.varBeta = _ptr(self.beta), _ptr(self.delta), _ptr(self.annot_cat), _ptr(self.varBeta)
+        T.piHat, T.logPi, T.annot_prob = _ptr(self.piHat), _ptr(self.logPi), _ptr(self.annot_prob)
+        p, nA, nc = self.p, self.nA, self.nc
+        ushape, zshape = ((p, nA, nc), (p, nA)) if self.plus else ((p, nc), (p,))
+        if replay is None:
+            v = {"u_annot": np.zeros(p), "dirp": np.zeros((p, nA)), "u": np.zeros(ushape), "z": np.zeros(zshape), "chi2_b": np.zeros(nA),
+                 "dir_pi": np.zeros((nA, nc))}
+        else:
+            v = {k: np.ascontiguousarray(replay[k], dtype=np.float64).copy() for k in ("u_annot", "dirp", "u", "z", "chi2_b", "dir_pi")}
+        V = _RCVariates()
+        V.replay, V.seed, V.chain, V.iter = int(replay is not None), seed, chain, it
+        V.u_annot, V.dirp, V.u, V.z, V.chi2_b, V.dir_pi = (_ptr(v[k]) for k in ("u_annot", "dirp", "u", "z", "chi2_b", "dir_pi"))
+        rc = L.ngo_rc_sweep(C.byref(S), C.byref(T), _ptr(e), varE, C.byref(V))
+        assert rc == 0, rc
+        return v

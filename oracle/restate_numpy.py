@@ -184,3 +184,78 @@ def bayes_bc_w(method_b, X, Mp, mpm, lhs0, rhs0, scale, df, est_pi, beta, delta,
     if est_pi:
         piHat[:] = [1.0 - beta_pi, beta_pi]
         logPi[:] = np.log(piHat)
+
+
+def bayes_rc(X, mpm, e, varE, beta, delta, annot_cat, varBeta, piHat, logPi, annot, annot_prob, v_class, df, scale, est_pi, plus, v):
+    """Literal numpy restatement of sampleBayesRCpi! (functions.jl:291-360, plus=False) / sampleBayesRCplus! (functions.jl:362-419,
+    plus=True) with explicit variates v = {u_annot, dirp, u, z, chi2_b, dir_pi} (layouts of oracle/ngp_oracle.c: ngo_rc_sweep).
+    Mutates e, beta, delta, annot_cat, varBeta, piHat, logPi, annot_prob in place."""
+    p = X.shape[1]
+    nA, nc = annot.shape[1], len(v_class)
+    nLoci = np.zeros((nA, nc), dtype=np.int64)
+    nNonZero = np.zeros(nA, dtype=np.int64)
+    varc = [vb * np.asarray(v_class) for vb in varBeta]
+    sumS = np.zeros(nA)
+    iVarE = 1.0 / varE
+    for j in range(p):
+        x = X[:, j]
+        e += beta[j] * x
+        nz = [a for a in range(nA) if annot[j, a] != 0]
+        if not plus:
+            rhs = (x @ e) * iVarE
+            lhs = np.zeros((nA, nc)); Ex = np.zeros((nA, nc))
+            for a in nz:
+                for c in range(nc):
+                    lhs[a, c] = 0.0 if varc[a][c] == 0.0 else mpm[j] * iVarE + 1.0 / varc[a][c]
+                    ll = logPi[a, c] if varc[a][c] == 0.0 else -0.5 * (np.log(varc[a][c] * lhs[a, c]) - rhs ** 2 / lhs[a, c]) + logPi[a, c]
+                    Ex[a, c] = np.exp(ll)
+            pa1 = annot_prob[j, :] * Ex.sum(1)
+            pa = pa1 / pa1.sum()
+            A, cp = 0, pa[0]                                  # rand(Categorical(pa)) with the uniform u_annot[j]
+            while cp <= v["u_annot"][j] and A < nA - 1:
+                A += 1
+                cp += pa[A]
+            assert A in nz
+            annot_prob[j, nz] = v["dirp"][j, nz]              # sampleProb: the Dirichlet draw itself is the variate
+            pv = Ex[A, :] / Ex[A, :].sum()
+            cum = np.cumsum(pv)
+            cls = next(c for c in range(nc) if cum[c] >= v["u"][j, c])
+            delta[j] = cls + 1
+            annot_cat[j] = A + 1
+            nLoci[A, cls] += 1
+            if varc[A][cls] != 0.0:
+                nNonZero[A] += 1
+                b = rhs / lhs[A, cls] + np.sqrt(1.0 / lhs[A, cls]) * v["z"][j]
+                beta[j] = b
+                e -= b * x
+                sumS[A] += b * b / v_class[cls]
+            else:
+                beta[j] = 0.0
+        else:
+            temp = 0.0
+            for a in nz:
+                rhs = (x @ e) * iVarE
+                lhs = np.zeros(nc); Ex = np.zeros(nc)
+                for c in range(nc):
+                    lhs[c] = 0.0 if varc[a][c] == 0.0 else mpm[j] * iVarE + 1.0 / varc[a][c]
+                    ll = logPi[a, c] if varc[a][c] == 0.0 else -0.5 * (np.log(varc[a][c] * lhs[c]) - rhs ** 2 / lhs[c]) + logPi[a, c]
+                    Ex[c] = np.exp(ll)
+                cum = np.cumsum(Ex / Ex.sum())
+                cls = next(c for c in range(nc) if cum[c] >= v["u"][j, a, c])
+                delta[j] = cls + 1
+                nLoci[a, cls] += 1
+                b = 0.0
+                if varc[a][cls] != 0.0:
+                    nNonZero[a] += 1
+                    b = rhs / lhs[cls] + np.sqrt(1.0 / lhs[cls]) * v["z"][j, a]
+                    sumS[a] += b * b / v_class[cls]
+                temp += b
+                e -= b * x
+            beta[j] = temp
+    for a in range(nA):
+        varBeta[a] = (scale * df + sumS[a]) / v["chi2_b"][a]
+    if est_pi:
+        for a in range(nA):
+            piHat[a, :] = v["dir_pi"][a, :]
+            logPi[a, :] = np.log(v["dir_pi"][a, :])
+    return nLoci, nNonZero

@@ -288,3 +288,45 @@ def test_fixed_effect_oracle_matches_numpy_restatement_of_wangs_trick():
     e = e0.copy(); z1 = F1.sample(e, varE, it=1, seed=8, chain=0)
     rhs = Xf[:, 0] @ e0 / varE - 0.2; lhs = Xf[:, 0] @ Xf[:, 0] / varE + 0.3
     assert np.isclose(F1.b[0], rhs / lhs + np.sqrt(1 / lhs) * z1[0], rtol=1e-12)
+
+
+# ----------------------------------------------------------------------------- BayesRCpi / BayesRCplus (functions.jl:291-419)
+@pytest.mark.parametrize("plus", [False, True])
+@pytest.mark.parametrize("est_pi", [False, True])
+def test_bayesrc_oracle_matches_numpy_restatement(plus, est_pi):
+    """the C oracle (ngo_rc_sweep) against a literal numpy restatement of the reference's loops, same explicit variates; native variates
+    logged by the oracle in iteration k are replayed through both"""
+    from oracle import restate_numpy as RN
+    rng = np.random.default_rng(5)
+    n, p, nA = 300, 40, 3
+    codes = rng.integers(0, 3, size=(n, p)).astype(np.int8)
+    X, _, mpm = O.center_codes(np.asfortranarray(codes))
+    annot = rng.integers(0, 2, size=(p, nA)).astype(np.int32)
+    annot[annot.sum(1) == 0, 0] = 1                      # every locus has an annotation (mme.jl:396-399 leaves all-zero rows as NaN)
+    annot[3, :] = [2, 0, 1]                              # integer counts, not only 0/1
+    vclass, pi = np.array([0.0, 0.001, 0.01, 0.1]), np.array([0.7, 0.15, 0.1, 0.05])
+    y = rng.normal(size=n) + X[:, 2] * 0.8 - X[:, 11] * 0.5
+    R = O.BayesRCOracle(X, mpm, pi, vclass, v=0.6, annot=annot, est_pi=est_pi, plus=plus)
+    e_c = y - y.mean()
+    e_n = e_c.copy()
+    st = dict(beta=np.zeros(p), delta=np.ones(p, dtype=np.int64), annot_cat=np.zeros(p, dtype=np.int64), varBeta=np.full(nA, 0.6),
+              piHat=np.tile(pi, (nA, 1)), logPi=np.log(np.tile(pi, (nA, 1))), annot_prob=annot / annot.sum(1, keepdims=True))
+    for it in range(1, 5):
+        v = R.sweep(e_c, 1.3, it=it, seed=9, chain=2)                      # native stream, variates logged
+        RN.bayes_rc(X, mpm, e_n, 1.3, st["beta"], st["delta"], st["annot_cat"], st["varBeta"], st["piHat"], st["logPi"], annot,
+                    st["annot_prob"], vclass, R.df, R.scale, est_pi, plus, v)
+        assert np.array_equal(R.delta, st["delta"]) and np.allclose(R.beta, st["beta"], rtol=1e-10, atol=1e-14)
+        assert np.allclose(R.varBeta, st["varBeta"], rtol=1e-12) and np.allclose(R.piHat, st["piHat"], rtol=1e-14) and np.allclose(e_c, e_n, rtol=1e-9, atol=1e-11)
+        if not plus:
+            assert np.array_equal(R.annot_cat, st["annot_cat"]) and np.allclose(R.annot_prob, st["annot_prob"], rtol=1e-14)
+    assert (R.delta > 1).sum() > 0 and np.allclose(R.annot_prob.sum(1), 1.0)
+    if est_pi:
+        assert np.allclose(R.piHat.sum(1), 1.0)
+    # replaying the last iteration's log reproduces it
+    R2 = O.BayesRCOracle(X, mpm, pi, vclass, v=0.6, annot=annot, est_pi=est_pi, plus=plus)
+    e2 = y - y.mean()
+    v1 = R2.sweep(e2, 1.3, it=1, seed=9, chain=2)
+    R3 = O.BayesRCOracle(X, mpm, pi, vclass, v=0.6, annot=annot, est_pi=est_pi, plus=plus)
+    e3 = y - y.mean()
+    R3.sweep(e3, 1.3, it=1, seed=1234, chain=0, replay=v1)
+    assert np.array_equal(R2.beta, R3.beta) and np.array_equal(e2, e3) and np.array_equal(R2.varBeta, R3.varBeta)
