@@ -40,7 +40,8 @@ enum ngp_status {
 
 /* priorVCV[pSet].name dispatch of mme.jl:331,350,362 */
 enum ngp_method { NGP_BAYESPR = 0, NGP_BAYESB = 1, NGP_BAYESC = 2,
-                  NGP_BAYESR = 3 /* mme.jl:374-383; sampled by the per-marker kernel */ };
+                  NGP_BAYESR = 3 /* mme.jl:374-383 */,
+                  NGP_BAYESRCPI = 5 /* mme.jl:385-403, functions.jl:291-360 */, NGP_BAYESRCPLUS = 6 /* mme.jl:405-418, functions.jl:362-419 */ };
 #define NGP_MAX_CLASSES 8
 
 /* host input formats for ngp_upload_genotypes */
@@ -307,6 +308,27 @@ int ngp_joint_sweep(ngp_handle* h, double* ycorr, double varE, double* beta, dou
 int ngp_get_joint_state(ngp_handle* h, double* beta, double* varBeta);
 /* BayesR: class proportions M[pSet][:piHat] (n_class values); ngp_state.delta holds the 1-based class of every locus */
 int ngp_get_class_pi(ngp_handle* h, int set_id, double* piHat);
+/* ---- BayesRCpi / BayesRCplus: priorVCV[pSet] = BayesRCπ(pi, class, v, annot) / BayesRCplus(...) (runTime.jl:95-113); what getMME!
+ *      derives (mme.jl:385-418): one variance and one vector of class proportions PER ANNOTATION (varBeta has n_annot entries), annotProb =
+ *      annot ./ rowsums, annotCat.  Swept by the per-marker kernel; n_annot * n_class <= 32 (one lane per annotation and class).
+ *      ngp_state.delta = 1-based class of every locus, ngp_state.varBeta = the n_annot variances.                                          */
+typedef struct ngp_rc_prior {
+    int32_t plus;                /* 0 = BayesRCpi (sampleBayesRCπ!), 1 = BayesRCplus (sampleBayesRCplus!)                        */
+    int32_t est_pi;              /* estimatePi: Dirichlet update of every annotation's class proportions (functions.jl:352-359)  */
+    double df, scale, var_init;  /* as ngp_prior (mme.jl:493,501,516)                                                            */
+    int32_t n_class, n_annot;
+    const double* v_class;       /* [n_class]  M[pSet][:vClass]                                                                  */
+    const double* pi_class;      /* [n_class]  priorVCV[pSet].pi: the starting proportions of every annotation (mme.jl:390-392)  */
+    const int32_t* annot;        /* [p][n_annot] row-major: M[pSet][:annotInput] (mme.jl:394)                                    */
+} ngp_rc_prior;
+int ngp_set_rc_prior(ngp_handle* h, int set_id, const ngp_rc_prior* pr);
+/* annotCat (1-based, RCpi; p), annotProb (p x n_annot), piHat (n_annot x n_class); NULL members are skipped */
+int ngp_get_rc_state(ngp_handle* h, int set_id, int64_t* annot_cat, double* annot_prob, double* pi_hat);
+/* replay log of an RC set (after ngp_set_replay, which carries chi2_e / z_mu): u_annot [iter][p] and dirp [iter][p][n_annot] (RCpi: the
+ * uniform of the Categorical draw and the RESULT of sampleProb), u [iter][p][n_class] (RCpi) or [iter][p][n_annot][n_class] (RCplus),
+ * z [iter][p] or [iter][p][n_annot], chi2_b [iter][n_annot], dir_pi [iter][n_annot][n_class] (NULL unless est_pi)                     */
+int ngp_set_rc_replay(ngp_handle* h, int set_id, int32_t n_iter, const double* u_annot, const double* dirp, const double* u,
+                      const double* z, const double* chi2_b, const double* dir_pi);
 int ngp_get_state(ngp_handle* h, ngp_state* out);
 int ngp_set_state(ngp_handle* h, const ngp_state* in);
 /* running posterior sums since the last reset: sum(beta), sum(beta^2), sum(delta) per marker */

@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(_ROOT, "include", "ngp.h")
 
 NGP_MAX_SETS = 8
-BAYESPR, BAYESB, BAYESC, BAYESR = 0, 1, 2, 3
+BAYESPR, BAYESB, BAYESC, BAYESR, BAYESRCPI, BAYESRCPLUS = 0, 1, 2, 3, 5, 6
 GENO_I8, GENO_F64, GENO_PACKED2 = 0, 1, 2
 STORE_I8, STORE_2BIT = 0, 1
 KERNEL_BLOCKED, KERNEL_LITERAL = 0, 1
@@ -37,6 +37,11 @@ class Prior(C.Structure):
                 ("var_init", C.c_double), ("pi_in", C.c_double), ("n_regions", C.c_int64),
                 ("region_off", C.c_void_p), ("lhs0", C.c_void_p), ("rhs0", C.c_void_p),
                 ("n_class", C.c_int32), ("pad_", C.c_int32), ("v_class", C.c_void_p), ("pi_class", C.c_void_p)]
+
+
+class RCPrior(C.Structure):
+    _fields_ = [("plus", C.c_int32), ("est_pi", C.c_int32), ("df", C.c_double), ("scale", C.c_double), ("var_init", C.c_double),
+                ("n_class", C.c_int32), ("n_annot", C.c_int32), ("v_class", C.c_void_p), ("pi_class", C.c_void_p), ("annot", C.c_void_p)]
 
 
 class JointPrior(C.Structure):
@@ -189,6 +194,9 @@ _SIGS = {
     "ngp_run": (C.c_int, [C.c_void_p, C.c_int32]),
     "ngp_sweep": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ngp_get_class_pi": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ngp_set_rc_prior": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(RCPrior)]),
+    "ngp_get_rc_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ngp_set_rc_replay": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ngp_get_state": (C.c_int, [C.c_void_p, C.POINTER(State)]),
     "ngp_set_state": (C.c_int, [C.c_void_p, C.POINTER(State)]),
     "ngp_reset_posterior": (C.c_int, [C.c_void_p]),

@@ -62,6 +62,16 @@ class BayesRType:
 
 
 @dataclass
+class BayesRCType:
+    pi: Any                      # starting class proportions of every annotation (runTime.jl:95-102)
+    class_: Any
+    v: float
+    annot: Any                   # (p, n_annot) integer matrix
+    name: str = "BayesRCπ"
+    estimatePi: bool = False
+
+
+@dataclass
 class RandomEffectType:
     str: Any
     v: float
@@ -92,6 +102,16 @@ def BayesC(pi: float, v: float, name: str = "BayesC", estimatePi: bool = False) 
 def BayesR(pi, class_, v: float, name: str = "BayesR", estimatePi: bool = False) -> BayesRType:
     """runTime.jl:87-93."""
     return BayesRType(np.asarray(pi, dtype=np.float64), np.asarray(class_, dtype=np.float64), float(v), name, bool(estimatePi))
+
+
+def BayesRCpi(pi, class_, v: float, annot, name: str = "BayesRCπ", estimatePi: bool = False) -> BayesRCType:
+    """runTime.jl:112 (BayesRCπ)."""
+    return BayesRCType(np.asarray(pi, dtype=np.float64), np.asarray(class_, dtype=np.float64), float(v), np.asarray(annot, dtype=np.int32), name, bool(estimatePi))
+
+
+def BayesRCplus(pi, class_, v: float, annot, name: str = "BayesRCplus", estimatePi: bool = False) -> BayesRCType:
+    """runTime.jl:113."""
+    return BayesRCType(np.asarray(pi, dtype=np.float64), np.asarray(class_, dtype=np.float64), float(v), np.asarray(annot, dtype=np.int32), name, bool(estimatePi))
 
 
 def Random(str_: Any, v: float, type: int = 1) -> RandomEffectType:
@@ -499,6 +519,33 @@ class Sampler:
         self._ck(self._lib.ngp_get_joint_state(self._h, _p(beta), _p(vb)))
         return {"beta": beta, "varBeta": vb}
 
+    def set_rc_prior(self, set_id: int, plus: bool, df: float, scale: float, var_init: float, v_class, pi_class, annot, est_pi: bool = False) -> None:
+        """BayesRCpi (plus=False) / BayesRCplus (plus=True): annot = (p, n_annot) integer matrix (mme.jl:385-418)."""
+        v_class = np.ascontiguousarray(v_class, dtype=np.float64)
+        pi_class = np.ascontiguousarray(pi_class, dtype=np.float64)
+        annot = np.ascontiguousarray(annot, dtype=np.int32)
+        assert annot.shape[0] == self.sets[set_id]["p"] and len(pi_class) == len(v_class)
+        pr = L.RCPrior()
+        pr.plus, pr.est_pi, pr.df, pr.scale, pr.var_init = int(plus), int(est_pi), df, scale, var_init
+        pr.n_class, pr.n_annot, pr.v_class, pr.pi_class, pr.annot = len(v_class), annot.shape[1], _p(v_class), _p(pi_class), _p(annot)
+        self._ck(self._lib.ngp_set_rc_prior(self._h, set_id, C.byref(pr)))
+        self.sets[set_id].update(method=L.BAYESRCPLUS if plus else L.BAYESRCPI, nvar=annot.shape[1], est_pi=bool(est_pi), n_class=0,
+                                 rc=(annot.shape[1], len(v_class)))
+
+    def rc_state(self, set_id: int) -> dict:
+        nA, nc = self.sets[set_id]["rc"]
+        p = self.sets[set_id]["p"]
+        cat, prob, pi = np.zeros(p, dtype=np.int64), np.zeros((p, nA)), np.zeros((nA, nc))
+        self._ck(self._lib.ngp_get_rc_state(self._h, set_id, _p(cat), _p(prob), _p(pi)))
+        return {"annot_cat": cat, "annot_prob": prob, "piHat": pi}
+
+    def set_rc_replay(self, set_id: int, logs: list[dict]) -> None:
+        """logs: the oracle's BayesRCOracle.sweep() variate dicts, one per iteration (after set_replay with chi2_e / z_mu)"""
+        st = lambda k: np.ascontiguousarray(np.stack([g[k] for g in logs]), dtype=np.float64)
+        arrs = {k: st(k) for k in ("u_annot", "dirp", "u", "z", "chi2_b", "dir_pi")}
+        self._keep.append(arrs)
+        self._ck(self._lib.ngp_set_rc_replay(self._h, set_id, len(logs), *(_p(arrs[k]) for k in ("u_annot", "dirp", "u", "z", "chi2_b", "dir_pi"))))
+
     def set_rng(self, seed: int, chain_id: int = 0) -> None:
         self._ck(self._lib.ngp_set_rng(self._h, C.c_uint64(seed), chain_id))
 
@@ -793,15 +840,22 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
                 method, region_off = L.BAYESC, None
             elif name == "BayesR":                                              # mme.jl:374-383
                 method, region_off, pi = L.BAYESR, None, 0.0
+            elif name in ("BayesRCπ", "BayesRCplus"):                             # mme.jl:385-418
+                method, region_off, pi = (L.BAYESRCPI if name == "BayesRCπ" else L.BAYESRCPLUS), None, 0.0
             else:
                 raise NotImplementedError(f"{name} stays in Julia: SURVEY §8(f2)")
         df = 3.0 + 1.0                                                          # mme.jl:493 (scalar v)
         scale = v * (df - 2.0) / df                                             # mme.jl:501
         extra = dict(v_class=pr.class_, pi_class=pr.pi) if name == "BayesR" else {}
-        sampler.set_prior(sid, method, df, scale, v, pi_in=pi, est_pi=est, region_off=region_off, lhs0=lhs0, rhs0=rhs0, **extra)
+        if name in ("BayesRCπ", "BayesRCplus"):
+            if lhs0 is not None:
+                raise NotImplementedError("summary-statistic priors with BayesRCπ / BayesRCplus stay in Julia")
+            sampler.set_rc_prior(sid, name == "BayesRCplus", df, scale, v, pr.class_, pr.pi, pr.annot, est_pi=est)
+        else:
+            sampler.set_prior(sid, method, df, scale, v, pi_in=pi, est_pi=est, region_off=region_off, lhs0=lhs0, rhs0=rhs0, **extra)
         nvar = sampler.sets[sid]["nvar"]
         info.append({"name": term.name, "method": name, "p": p, "nvar": nvar, "df": df, "scale": scale,
-                     "n_pi": len(pr.class_) if name == "BayesR" else 2})
+                     "n_pi": (len(pr.class_) if name == "BayesR" else len(pr.class_) * nvar if name in ("BayesRCπ", "BayesRCplus") else 2)})
     fixed = fixed or []                                                          # [(name, data (n,c), level names)]
     if fixed:
         sampler.set_fixed_effects([d for _, d, _ in fixed])                      # X[xSet] besides the intercept (functions.jl:22-54)
@@ -816,8 +870,10 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
             levels = term.levels or [f"M{i}" for i in range(1, inf["p"] + 1)]
             outMCMC(outPut, f"beta{term.name}", [levels])
             outMCMC(outPut, f"delta{term.name}", [levels])
-            if inf["method"] in ("BayesB", "BayesC", "BayesR"):                  # mme.jl:571-572
+            if inf["method"] in ("BayesB", "BayesC", "BayesR", "BayesRCπ", "BayesRCplus"):                  # mme.jl:571-576
                 outMCMC(outPut, f"pi{term.name}", [[f"pi{v}" for v in range(1, inf["n_pi"] + 1)]])
+            if inf["method"] in ("BayesRCπ", "BayesRCplus"):
+                outMCMC(outPut, f"annot{term.name}", [levels])
         for term, inf in zip(M, info):
             outMCMC(outPut, f"var{term.name}", [[f"reg_{r}" for r in range(1, inf["nvar"] + 1)]])
         outMCMC(outPut, "varE", [["e"]])
@@ -891,6 +947,11 @@ def runSampler(sampler: Sampler, M: list[MarkerTerm], info: dict, chainLength: i
                 outMCMC(outPut, f"delta{term.name}", st["sets"][sid]["delta"])
                 if inf["method"] in ("BayesB", "BayesC", "BayesR"):              # samplers.jl:82
                     outMCMC(outPut, f"pi{term.name}", st["sets"][sid]["piHat"])
+                if inf["method"] in ("BayesRCπ", "BayesRCplus"):                   # samplers.jl:85-88: vcat(piHat...), annotCat
+                    rs = sampler.rc_state(sid)
+                    st["sets"][sid]["rc"] = rs
+                    outMCMC(outPut, f"pi{term.name}", rs["piHat"].ravel())
+                    outMCMC(outPut, f"annot{term.name}", rs["annot_cat"])
             for sid, term in enumerate(M):
                 if not info.get("tuple"):
                     outMCMC(outPut, f"var{term.name}", st["sets"][sid]["varBeta"])

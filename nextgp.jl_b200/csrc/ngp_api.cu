@@ -266,7 +266,9 @@ struct SetHost {
     double *d = nullptr, *mean = nullptr, *beta = nullptr, *varBeta = nullptr, *pi = nullptr, *pi_class = nullptr, *jinvB = nullptr;
     int group_k = 0, stream_set = 0;
     bool joint_copy = false;           // the interleaved copy of a tuple's member sets
-    int n_class = 0;
+    int n_class = 0, n_annot = 0;
+    int32_t *annot = nullptr, *annot_cat = nullptr;       // BayesRCpi / BayesRCplus
+    double *annot_prob = nullptr, *rp_u_annot = nullptr, *rp_dirp = nullptr;
     double v_class[kMaxClass] = {0.0};
     double *lhs0 = nullptr, *rhs0 = nullptr, *sum_beta = nullptr, *sum_beta2 = nullptr, *sum_delta = nullptr;
     int64_t* region_off = nullptr;
@@ -398,6 +400,7 @@ static void free_set(SetHost& s)
     cudaFree(s.lhs0); cudaFree(s.rhs0); cudaFree(s.sum_beta); cudaFree(s.sum_beta2); cudaFree(s.sum_delta);
     cudaFree(s.region_off); cudaFree(s.rp_u); cudaFree(s.rp_z); cudaFree(s.rp_chi2b); cudaFree(s.rp_betapi);
     cudaFree(s.dw); cudaFree(s.wcs);
+    cudaFree(s.annot); cudaFree(s.annot_cat); cudaFree(s.annot_prob); cudaFree(s.rp_u_annot); cudaFree(s.rp_dirp);
     s = SetHost();
 }
 
@@ -1034,6 +1037,7 @@ int ngp_set_replay(ngp_handle* h, const ngp_replay* log)
     for (int s = 0; s < h->n_sets; ++s) {
         SetHost& S = h->sets[s];
         if (!S.have_geno || S.joint_member || S.joint_copy) continue;
+        if (S.method == NGP_BAYESRCPI || S.method == NGP_BAYESRCPLUS) continue;        // their log comes through ngp_set_rc_replay
         if (!S.have_prior) return fail(h, NGP_EINVAL, "ngp_set_replay: set the prior of set %d first", s);
         if (s >= log->n_sets || !log->z[s] || !log->chi2_b[s]) return fail(h, NGP_EINVAL, "ngp_set_replay: z / chi2_b missing for set %d", s);
         CU(dalloc(&S.rp_z, (size_t)ni * S.p));
@@ -1073,6 +1077,7 @@ static int sync_sets(ngp_handle* h)
         D.df = S.df; D.scale = S.scale; D.group_k = S.group_k; D.stream_set = S.stream_set; D.jinvB = S.jinvB;
         if (S.group_k) { D.jvar = h->joint.varBeta; for (int a = 0; a < S.group_k * S.group_k; ++a) D.jscale[a] = h->joint.scale[a]; D.rp_iw_chi2 = h->joint.rp_iw_chi2; D.rp_iw_z = h->joint.rp_iw_z; D.rp_z = h->joint.rp_z; }
         D.n_class = S.n_class; D.pi_class = S.pi_class; memcpy(D.v_class, S.v_class, sizeof D.v_class);
+        D.n_annot = S.n_annot; D.annot = S.annot; D.annot_prob = S.annot_prob; D.annot_cat = S.annot_cat; D.rp_u_annot = S.rp_u_annot; D.rp_dirp = S.rp_dirp;
         D.geno = S.geno; D.gx = S.gx; D.consts = S.consts; D.colsum = S.colsum; D.d = S.d; D.mean = S.mean;
         if (h->w && S.w_ready) { D.d = S.dw; D.d_unw = S.d; D.wcs = S.wcs; }
         D.beta = S.beta; D.delta = S.delta; D.varBeta = S.varBeta; D.pi = S.pi; D.region_of = S.region_of; D.region_off = S.region_off;
@@ -1268,6 +1273,12 @@ static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, 
     const bool r_blocked = any_r && all_r && r_ok && P.kernel == NGP_KERNEL_BLOCKED && !h->w && !sharded && !h->cfg_debug && !h->cfg_profile &&
                            !(h->R > 4 * kUpdThreads && h->B != 16);
     if (any_r && !r_blocked) P.kernel = NGP_KERNEL_LITERAL;
+    for (int s = 0; s < h->n_sets; ++s)
+        if (((set_mask >> s) & 1) && (h->sets[s].method == NGP_BAYESRCPI || h->sets[s].method == NGP_BAYESRCPLUS)) {
+            if (h->w || sharded) return fail(h, NGP_EUNSUPPORTED, "BayesRCpi / BayesRCplus: no weighted residuals, no row sharding");
+            if (h->replay && (!h->sets[s].rp_u || !h->sets[s].rp_z)) return fail(h, NGP_EINVAL, "replay log of the RC set %d missing (ngp_set_rc_replay after ngp_set_replay)", s);
+            P.kernel = NGP_KERNEL_LITERAL;          // annotation algebra lives in the per-marker sweep
+        }
     bool tuple_mask = false;
     for (int s = 0; s < h->n_sets; ++s) if (((set_mask >> s) & 1) && h->sets[s].group_k) tuple_mask = true;
     int variant = tuple_mask ? NGP_KV_TUP : (P.kernel == NGP_KERNEL_LITERAL) ? NGP_KV_LIT : h->cfg_debug ? NGP_KV_DBG : h->cfg_profile ? NGP_KV_PROF : NGP_KV_PLAIN;
@@ -1423,6 +1434,8 @@ int ngp_sweep(ngp_handle* h, int set_id, double* ycorr, double varE, double* bet
     if (set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_geno || !h->sets[set_id].have_prior)
         return fail(h, NGP_EINVAL, "ngp_sweep: marker set %d is not ready", set_id);
     if (!ycorr || !(varE > 0.0)) return fail(h, NGP_EINVAL, "ngp_sweep: ycorr must be non-NULL and varE > 0");
+    if (h->sets[set_id].method == NGP_BAYESRCPI || h->sets[set_id].method == NGP_BAYESRCPLUS)
+        return fail(h, NGP_EUNSUPPORTED, "ngp_sweep: BayesRCpi / BayesRCplus sets are sampled at run level (ngp_run; state through ngp_get_state / ngp_get_rc_state)");
     CU(cudaSetDevice(h->device));
     SetHost& S = h->sets[set_id];
     // Everything is queued on the handle's stream — host-to-device copies, the sweep, device-to-host copies — and the stream is
@@ -1829,9 +1842,105 @@ int ngp_joint_sweep(ngp_handle* h, double* ycorr, double varE, double* beta, dou
 int ngp_get_class_pi(ngp_handle* h, int set_id, double* piHat)
 {
     if (!h || !piHat || set_id < 0 || set_id >= NGP_MAX_SETS || h->sets[set_id].method != NGP_BAYESR || !h->sets[set_id].pi_class)
-        return fail(h, NGP_EINVAL, "ngp_get_class_pi: set %d is not a BayesR set", set_id);
+        return fail(h, NGP_EINVAL, "ngp_get_class_pi: set %d is not a BayesR set (RC sets: ngp_get_rc_state)", set_id);
     CU(cudaSetDevice(h->device));
     CU(cpy(h, piHat, h->sets[set_id].pi_class, sizeof(double) * h->sets[set_id].n_class, cudaMemcpyDeviceToHost));
+    return NGP_OK;
+}
+
+int ngp_set_rc_prior(ngp_handle* h, int set_id, const ngp_rc_prior* pr)
+{
+    if (!h || !pr) return fail(h, NGP_EINVAL, "ngp_set_rc_prior: NULL argument");
+    if (set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_geno) return fail(h, NGP_EINVAL, "ngp_set_rc_prior: upload genotypes of set %d first", set_id);
+    if (pr->n_class < 1 || pr->n_class > kMaxClass || pr->n_annot < 1 || pr->n_annot * pr->n_class > 32 || !pr->v_class || !pr->pi_class || !pr->annot)
+        return fail(h, NGP_EINVAL, "ngp_set_rc_prior: 1..%d classes, n_annot * n_class <= 32, v_class / pi_class / annot non-NULL", kMaxClass);
+    for (int v = 0; v < pr->n_class; ++v)
+        if (!(pr->v_class[v] >= 0.0) || !(pr->pi_class[v] > 0.0)) return fail(h, NGP_EINVAL, "ngp_set_rc_prior: class %d: scale must be >= 0 and proportion > 0", v);
+    SetHost& S0 = h->sets[set_id];
+    const int64_t p = S0.p;
+    const int nA = pr->n_annot, nc = pr->n_class;
+    for (int64_t j = 0; j < p; ++j) {
+        int64_t rs = 0;
+        for (int a = 0; a < nA; ++a) { if (pr->annot[j * nA + a] < 0) return fail(h, NGP_EINVAL, "ngp_set_rc_prior: negative annotation count"); rs += pr->annot[j * nA + a]; }
+        if (rs == 0) return fail(h, NGP_EDATA, "ngp_set_rc_prior: locus %lld has no annotation (annotProb would be NaN, mme.jl:395-399)", (long long)j);
+    }
+    // the BayesR plumbing (classes, variances, state arrays), then the annotation arrays
+    ngp_prior q{};
+    q.method = NGP_BAYESR; q.est_pi = pr->est_pi; q.df = pr->df; q.scale = pr->scale; q.var_init = pr->var_init;
+    q.n_class = pr->n_class; q.v_class = pr->v_class; q.pi_class = pr->pi_class;
+    int rc = ngp_set_prior(h, set_id, &q);
+    if (rc) return rc;
+    SetHost& S = h->sets[set_id];
+    S.method = pr->plus ? NGP_BAYESRCPLUS : NGP_BAYESRCPI;
+    S.n_annot = nA;
+    S.nvar = nA;
+    CU(dalloc(&S.varBeta, S.nvar));
+    fill_kernel<<<1, 256, 0, h->stream>>>(S.varBeta, S.nvar, pr->var_init);                                  // mme.jl:516
+    CU(cudaGetLastError());
+    std::vector<double> pc((size_t)2 * nA * nc), ap((size_t)2 * p * nA);
+    for (int a = 0; a < nA; ++a)
+        for (int v = 0; v < nc; ++v) { pc[(size_t)a * nc + v] = pr->pi_class[v]; pc[(size_t)nA * nc + a * nc + v] = log(pr->pi_class[v]); }      // mme.jl:390-392
+    for (int64_t j = 0; j < p; ++j) {
+        double rs = 0.0;
+        for (int a = 0; a < nA; ++a) rs += (double)pr->annot[j * nA + a];
+        for (int a = 0; a < nA; ++a) ap[(size_t)j * nA + a] = ap[(size_t)(p + j) * nA + a] = (double)pr->annot[j * nA + a] / rs;                 // mme.jl:395
+    }
+    CU(dalloc(&S.pi_class, pc.size()));
+    CU(cpy(h, S.pi_class, pc.data(), sizeof(double) * pc.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&S.annot, (size_t)p * nA));
+    CU(cpy(h, S.annot, pr->annot, sizeof(int32_t) * (size_t)p * nA, cudaMemcpyHostToDevice));
+    CU(dalloc(&S.annot_prob, ap.size()));
+    CU(cpy(h, S.annot_prob, ap.data(), sizeof(double) * ap.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&S.annot_cat, (size_t)S.p_pad));
+    CU(zero(h, S.annot_cat, 0, sizeof(int32_t) * S.p_pad));                                                  // mme.jl:403
+    CU(cudaStreamSynchronize(h->stream));
+    h->sets_dirty = true;
+    return NGP_OK;
+}
+
+int ngp_get_rc_state(ngp_handle* h, int set_id, int64_t* annot_cat, double* annot_prob, double* pi_hat)
+{
+    if (!h || set_id < 0 || set_id >= NGP_MAX_SETS || (h->sets[set_id].method != NGP_BAYESRCPI && h->sets[set_id].method != NGP_BAYESRCPLUS))
+        return fail(h, NGP_EINVAL, "ngp_get_rc_state: set %d is not a BayesRCpi / BayesRCplus set", set_id);
+    SetHost& S = h->sets[set_id];
+    CU(cudaSetDevice(h->device));
+    if (annot_cat) {
+        std::vector<int32_t> t((size_t)S.p);
+        CU(cpy(h, t.data(), S.annot_cat, sizeof(int32_t) * S.p, cudaMemcpyDeviceToHost));
+        for (int64_t j = 0; j < S.p; ++j) annot_cat[j] = t[(size_t)j];
+    }
+    if (annot_prob) {
+        Scalars sc;
+        CU(cpy(h, &sc, h->sc, sizeof sc, cudaMemcpyDeviceToHost));
+        // iteration it reads buffer (it & 1) and writes buffer ((it + 1) & 1): after sc.iter iterations the current values are in buffer ((sc.iter + 1) & 1)
+        const size_t off = (size_t)((sc.iter + 1) & 1) * S.p * S.n_annot;
+        CU(cpy(h, annot_prob, S.annot_prob + off, sizeof(double) * (size_t)S.p * S.n_annot, cudaMemcpyDeviceToHost));
+    }
+    if (pi_hat) CU(cpy(h, pi_hat, S.pi_class, sizeof(double) * (size_t)S.n_annot * S.n_class, cudaMemcpyDeviceToHost));
+    return NGP_OK;
+}
+
+int ngp_set_rc_replay(ngp_handle* h, int set_id, int32_t n_iter, const double* u_annot, const double* dirp, const double* u,
+                      const double* z, const double* chi2_b, const double* dir_pi)
+{
+    if (!h || set_id < 0 || set_id >= NGP_MAX_SETS || (h->sets[set_id].method != NGP_BAYESRCPI && h->sets[set_id].method != NGP_BAYESRCPLUS))
+        return fail(h, NGP_EINVAL, "ngp_set_rc_replay: set %d is not a BayesRCpi / BayesRCplus set", set_id);
+    SetHost& S = h->sets[set_id];
+    if (!h->replay || n_iter != h->replay_iters) return fail(h, NGP_EINVAL, "ngp_set_rc_replay: call ngp_set_replay first, with the same number of iterations");
+    const bool plus = S.method == NGP_BAYESRCPLUS;
+    if (!u || !z || !chi2_b || (!plus && (!u_annot || !dirp)) || (S.est_pi && !dir_pi)) return fail(h, NGP_EINVAL, "ngp_set_rc_replay: missing arrays");
+    CU(cudaSetDevice(h->device));
+    const size_t ni = (size_t)n_iter, p = (size_t)S.p, nA = (size_t)S.n_annot, nc = (size_t)S.n_class;
+    const size_t nu = plus ? ni * p * nA * nc : ni * p * nc, nz = plus ? ni * p * nA : ni * p;
+    CU(dalloc(&S.rp_u, nu)); CU(cpy(h, S.rp_u, u, sizeof(double) * nu, cudaMemcpyHostToDevice));
+    CU(dalloc(&S.rp_z, nz)); CU(cpy(h, S.rp_z, z, sizeof(double) * nz, cudaMemcpyHostToDevice));
+    CU(dalloc(&S.rp_chi2b, ni * nA)); CU(cpy(h, S.rp_chi2b, chi2_b, sizeof(double) * ni * nA, cudaMemcpyHostToDevice));
+    if (!plus) {
+        CU(dalloc(&S.rp_u_annot, ni * p)); CU(cpy(h, S.rp_u_annot, u_annot, sizeof(double) * ni * p, cudaMemcpyHostToDevice));
+        CU(dalloc(&S.rp_dirp, ni * p * nA)); CU(cpy(h, S.rp_dirp, dirp, sizeof(double) * ni * p * nA, cudaMemcpyHostToDevice));
+    }
+    if (S.est_pi) { CU(dalloc(&S.rp_betapi, ni * nA * nc)); CU(cpy(h, S.rp_betapi, dir_pi, sizeof(double) * ni * nA * nc, cudaMemcpyHostToDevice)); }
+    h->sets_dirty = true;
     return NGP_OK;
 }
 

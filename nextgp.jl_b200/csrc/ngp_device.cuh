@@ -81,6 +81,14 @@ struct SetDev {
     int32_t n_class, pad_cls;  // BayesR (method 3): variance classes (functions.jl:241)
     double v_class[kMaxClass]; //   M.vClass
     double* pi_class;          //   [2 * n_class] piHat, logPi (mme.jl:375,383)
+    // BayesRCpi / BayesRCplus (methods 5, 6; per-marker kernel): annotations.  pi_class = [n_annot][n_class] piHat then [n_annot][n_class] logPi
+    int32_t n_annot, pad_an;
+    const int32_t* annot;      // [p][n_annot] annotInput (mme.jl:394)
+    double* annot_prob;        // [2][p][n_annot] annotProb (mme.jl:395), double-buffered by iteration parity: every CTA reads the values of the
+                               // previous iteration while the chain CTA writes this iteration's Dirichlet draws
+    int32_t* annot_cat;        // [p] annotCat (RCpi)
+    const double* rp_u_annot;  // replay [iter][p]
+    const double* rp_dirp;     // replay [iter][p][n_annot]
     // tuple of k marker sets swept by the blocked kernel (method 4): the breeds' columns are INTERLEAVED, column j*k + b = breed b
     // of locus j, and the k effects of a locus are drawn jointly (functions.jl:140-154)
     int32_t group_k, stream_set;   // k (2 or 4; 0 = ordinary set); set id that addresses the variate stream (first member)

@@ -20,7 +20,8 @@
 namespace ngp {
 
 enum Purpose : uint32_t {
-    P_CHI2_E = 0, P_Z_MU = 1, P_U = 2, P_Z = 3, P_CHI2_B = 4, P_PI_A = 5, P_PI_B = 6, P_IW = 7
+    P_CHI2_E = 0, P_Z_MU = 1, P_U = 2, P_Z = 3, P_CHI2_B = 4, P_PI_A = 5, P_PI_B = 6, P_IW = 7,
+    P_U_ANNOT = 8, P_G_ANNOT = 9       // BayesRCpi: the Categorical draw of the annotation, the gammas of sampleProb
 };
 
 struct Stream {

@@ -204,7 +204,7 @@ __device__ __forceinline__ void prep_marker(const Params& P, const SetDev& S, in
             // BayesR: F_QSZ carries the normal variate, the class algebra runs in the sweep.  The blocked sweep (<= 4 classes) also finds the
             // uniforms of the cumulative comparisons (a fresh one per comparison, functions.jl:261) here: F_A, F_B, F_T, F_C = u_0 .. u_3
             fC = 0.0; fQSZ = z;
-            if (S.n_class <= 4) {
+            if (S.n_class <= 4 && S.method == 3) {
                 double uv[4] = {0.0, 0.0, 0.0, 0.0};
                 for (int v = 0; v < S.n_class; ++v)
                     uv[v] = P.replay ? S.rp_u[(rp_row * S.p + j) * S.n_class + v] : stream_uniform(st, P_U, (uint32_t)j, 0, (uint32_t)v);
@@ -667,6 +667,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
             const int64_t p_real = S.p;
             double acc_bb = 0.0, acc_n = 0.0;          // chain warp: per-lane partials of beta'beta and nLoci
             double acc_cls = 0.0;                      // BayesR: loci assigned to class `lane`
+            double rc_nloci_keep = 0.0, rc_sumS_keep = 0.0, rc_nnz_keep = 0.0;      // BayesRCpi / BayesRCplus counters of warp 0 (per-marker kernel)
             if constexpr (PROF) tc = clock64();
 
             if constexpr (!LIT) {
@@ -1569,6 +1570,20 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                     varc_v = __ldcg(&S.varBeta[0]) * vcls_v;                            // functions.jl:244
                     logpi_v = __ldcg(&S.pi_class[nc + lane]);
                 }
+                // BayesRCpi / BayesRCplus (functions.jl:291-419): lane a * ncR + v of warp 0 owns (annotation a, class v)
+                const bool rc_pi = S.method == 5, rc_plus = S.method == 6;
+                const int nA = (rc_pi || rc_plus) ? S.n_annot : 0, ncR = (rc_pi || rc_plus) ? S.n_class : 1;
+                const int a_l = lane / ncR, v_l = lane % ncR;
+                const bool lane_on = nA && lane < nA * ncR;
+                double rc_varc = 0.0, rc_logpi = 0.0, rc_vcls = 1.0;
+                double rc_nloci = 0.0, rc_sumS = 0.0, rc_nnz = 0.0;          // nLoci[a][v] in lane (a,v); sumS[a], nNonZero[a] in lane (a,0)
+                if (lane_on) {
+                    rc_vcls = S.v_class[v_l];
+                    rc_varc = __ldcg(&S.varBeta[a_l]) * rc_vcls;                         // functions.jl:298 / :369
+                    rc_logpi = __ldcg(&S.pi_class[nA * ncR + lane]);
+                }
+                const double* ap_rd = nA ? S.annot_prob + (size_t)(iter & 1u) * S.p * nA : nullptr;         // annotProb as the previous iteration left it
+                double* ap_wr = nA ? S.annot_prob + (size_t)((iter + 1u) & 1u) * S.p * nA : nullptr;
                 for (int64_t j = 0; j < S.p; ++j, ++rk) {
                     const int k = (int)(j / B), q = (int)(j % B);
                     const uint8_t* tile = S.geno + ((int64_t)t * nblk + k) * L.tile_bytes;
@@ -1649,7 +1664,103 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                             const double Au = (double)((cu - pu - arrivals) >> cb) * fx_inv;
                             rq = fma(__ldg(&S.d_unw[j]), bold, Au - mean * Stot_u);       // functions.jl:168, :208: view(data,:,locus)'ycorr
                         }
-                        if (nc) {
+                        if (nA) {
+                            const unsigned FULL = 0xffffffffu;
+                            Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)s};
+                            const double iVarE = 1.0 / varE;
+                            const double l0 = S.lhs0 ? S.lhs0[j] : 0.0, r0 = S.rhs0 ? S.rhs0[j] : 0.0;
+                            const int an_l = lane_on ? __ldg(&S.annot[j * nA + a_l]) : 0;                    // annotInput of this lane's annotation
+                            const int an_a = (lane < nA) ? __ldg(&S.annot[j * nA + lane]) : 0;               // ... and of annotation `lane`
+                            const double lhs_l = (rc_varc == 0.0) ? 0.0 : d * iVarE + l0 + 1.0 / rc_varc;
+                            double bn = 0.0;
+                            int cls_out = 0;
+                            if (rc_pi) {
+                                const double rhs = fma(rr, iVarE, r0);                                                 // :304
+                                double ex = 0.0;                                                                       // ExpLogL[a][v], zero for annotations the locus does not have
+                                if (lane_on && an_l != 0) ex = exp((rc_varc == 0.0) ? rc_logpi : -0.5 * (log(rc_varc * lhs_l) - (rhs * rhs) / lhs_l) + rc_logpi);
+                                double Sa = 0.0;                                                                       // sum(ExpLogL, dims = 2)[a] in class order
+                                for (int v = 0; v < ncR; ++v) Sa += __shfl_sync(FULL, ex, (a_l * ncR + v) & 31);
+                                const double pa1 = lane_on ? __ldcg(&ap_rd[j * nA + a_l]) * Sa : 0.0;                  // :315
+                                double tot2 = 0.0;
+                                for (int a = 0; a < nA; ++a) tot2 += __shfl_sync(FULL, pa1, a * ncR);
+                                const double u_an = P.replay ? S.rp_u_annot[rp_row * S.p + j] : stream_uniform(st, P_U_ANNOT, (uint32_t)j);
+                                // rand(Categorical(probAnnot)) :319 — one uniform; cp = p[1]; while cp <= draw && i < n: i += 1; cp += p[i]
+                                int A = 0;
+                                double cp = __shfl_sync(FULL, pa1, 0) / tot2;
+                                for (int a = 1; a < nA; ++a) {
+                                    const double pa = __shfl_sync(FULL, pa1, a * ncR) / tot2;
+                                    if (A == a - 1 && cp <= u_an) { A = a; cp += pa; }
+                                }
+                                const int an_A = __shfl_sync(FULL, an_a, A);
+                                if (!(tot2 == tot2) || an_A == 0) atomicOr(&sy->err, 4);                              // findfirst(isequal(A), nonzero) finds nothing: the reference errors
+                                // sampleProb (:322, :541-544): Dirichlet(annotInput[nonzero] + e_A); lane a draws the gamma of annotation a
+                                double g = 0.0;
+                                if (!P.replay && lane < nA && an_a != 0) g = stream_gamma(st, P_G_ANNOT, (uint32_t)j, (uint32_t)lane, (double)an_a + (lane == A ? 1.0 : 0.0));
+                                double tg = 0.0;
+                                for (int a = 0; a < nA; ++a) tg += __shfl_sync(FULL, g, a);
+                                if (is_chain && lane < nA && an_a != 0) ap_wr[j * nA + lane] = P.replay ? S.rp_dirp[(rp_row * S.p + j) * nA + lane] : g / tg;
+                                // class inside the chosen annotation (:324-327): a fresh uniform per cumulative comparison
+                                const double u_v = (lane < ncR) ? (P.replay ? S.rp_u[(rp_row * S.p + j) * ncR + lane] : stream_uniform(st, P_U, (uint32_t)j, 0, (uint32_t)lane)) : 0.0;
+                                const double S_A = __shfl_sync(FULL, Sa, A * ncR);
+                                double cum = 0.0;
+                                int cls = -1;
+                                for (int v = 0; v < ncR; ++v) {
+                                    cum += __shfl_sync(FULL, ex, A * ncR + v) / S_A;
+                                    const double uv = __shfl_sync(FULL, u_v, v);
+                                    if (cls < 0 && cum >= uv) cls = v;
+                                }
+                                if (cls < 0) { atomicOr(&sy->err, 4); cls = 0; }
+                                const int lc = A * ncR + cls;
+                                const double varc_c = __shfl_sync(FULL, rc_varc, lc), lhs_c = __shfl_sync(FULL, lhs_l, lc), vcls_c = __shfl_sync(FULL, rc_vcls, lc);
+                                if (varc_c != 0.0) {                                                                   // :333-341
+                                    const double z = P.replay ? S.rp_z[rp_row * S.p + j] : stream_normal(st, P_Z, (uint32_t)j);
+                                    bn = rhs / lhs_c + sqrt(1.0 / lhs_c) * z;
+                                    if (lane == A * ncR) { rc_sumS += (bn * bn) / vcls_c; rc_nnz += 1.0; }
+                                }
+                                if (lane == lc) rc_nloci += 1.0;                                                       // nLoci[A, class] += 1
+                                cls_out = cls;
+                                if (is_chain && lane == 0) S.annot_cat[j] = A + 1;                                     // :330
+                            } else {
+                                // BayesRCplus: one effect per annotation of the locus, in annotation order; ycorr loses every one of them before the
+                                // next is drawn (:379, :401):  x'(e - x b) = x'e - (x'x) b
+                                double rr_run = rr, temp = 0.0;
+                                for (int a = 0; a < nA; ++a) {
+                                    if (__shfl_sync(FULL, an_a, a) == 0) continue;                                     // :378
+                                    const double rhs = fma(rr_run, iVarE, r0);
+                                    double ex = 0.0;
+                                    if (lane_on && a_l == a) ex = exp((rc_varc == 0.0) ? rc_logpi : -0.5 * (log(rc_varc * lhs_l) - (rhs * rhs) / lhs_l) + rc_logpi);
+                                    double tot = 0.0;
+                                    for (int v = 0; v < ncR; ++v) tot += __shfl_sync(FULL, ex, a * ncR + v);
+                                    const double u_v = (lane < ncR) ? (P.replay ? S.rp_u[((rp_row * S.p + j) * nA + a) * ncR + lane]
+                                                                                : stream_uniform(st, P_U, (uint32_t)j, (uint32_t)a, (uint32_t)lane)) : 0.0;
+                                    double cum = 0.0;
+                                    int cls = -1;
+                                    for (int v = 0; v < ncR; ++v) {
+                                        cum += __shfl_sync(FULL, ex, a * ncR + v) / tot;
+                                        const double uv = __shfl_sync(FULL, u_v, v);
+                                        if (cls < 0 && cum >= uv) cls = v;
+                                    }
+                                    if (cls < 0) { atomicOr(&sy->err, 4); cls = 0; }
+                                    const int lc = a * ncR + cls;
+                                    const double varc_c = __shfl_sync(FULL, rc_varc, lc), lhs_c = __shfl_sync(FULL, lhs_l, lc), vcls_c = __shfl_sync(FULL, rc_vcls, lc);
+                                    double b = 0.0;
+                                    if (varc_c != 0.0) {                                                               // :391-397
+                                        const double z = P.replay ? S.rp_z[(rp_row * S.p + j) * nA + a] : stream_normal(st, P_Z, (uint32_t)j, (uint32_t)a);
+                                        b = rhs / lhs_c + sqrt(1.0 / lhs_c) * z;
+                                        if (lane == a * ncR) { rc_sumS += (b * b) / vcls_c; rc_nnz += 1.0; }
+                                    }
+                                    if (lane == lc) rc_nloci += 1.0;
+                                    temp += b;                                                                         // :400
+                                    rr_run = fma(-d, b, rr_run);
+                                    cls_out = cls;                                                                     // :388: the last annotation's class stays in delta
+                                }
+                                bn = temp;                                                                             // :403
+                            }
+                            if (lane == 0) {
+                                misc[40] = bn - bold; misc[41] = mean;
+                                if (is_chain) { S.beta[j] = bn; S.delta[j] = cls_out + 1; }
+                            }
+                        } else if (nc) {
                             // class likelihoods (functions.jl:250-258), one class per lane
                             const double iVarE = 1.0 / varE;
                             const double l0 = S.lhs0 ? S.lhs0[j] : 0.0, r0 = S.rhs0 ? S.rhs0[j] : 0.0;
@@ -1710,13 +1821,34 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                     __syncthreads();
                 }
                 // (only lane 0 accumulated acc_bb / acc_n in the literal path; the other lanes hold 0)
+                rc_nloci_keep = rc_nloci; rc_sumS_keep = rc_sumS; rc_nnz_keep = rc_nnz;
             }
             if constexpr (PROF) tc = clock64();
 
             // ------------------------------------------------------------------ phase 3 (chain CTA)
             const bool regional = (S.method == 0 && S.n_regions > 1) || S.method == 4;
             const int p3warp = LIT ? 0 : kHelperWarp;     // the warp that accumulated beta'beta and nLoci
-            if (is_chain && warp == p3warp && S.method == 3) {
+            if (LIT && is_chain && warp == 0 && (S.method == 5 || S.method == 6)) {
+                // per annotation: variance (functions.jl:347-349 / :408-410) and, with estimatePi, Dirichlet(nLoci[a, :] + 1) (:352-359 / :413-418)
+                const int nA3 = S.n_annot, nc3 = S.n_class;
+                const int a3 = lane / nc3, v3 = lane % nc3;
+                const bool on3 = lane < nA3 * nc3;
+                Stream st{P.key0, P.key1, P.chain, iter, (uint32_t)s};
+                if (on3 && v3 == 0) {
+                    const double chi2 = P.replay ? S.rp_chi2b[rp_row * S.nvar + a3] : stream_chisq(st, P_CHI2_B, (uint32_t)a3, 0, S.df + rc_nnz_keep);
+                    S.varBeta[a3] = (S.scale * S.df + rc_sumS_keep) / chi2;
+                }
+                if (S.est_pi) {
+                    double gv = 0.0;
+                    if (on3) gv = P.replay ? S.rp_betapi[(rp_row * nA3 + a3) * nc3 + v3] : stream_gamma(st, P_PI_A, (uint32_t)a3, (uint32_t)v3, rc_nloci_keep + 1.0);
+                    double tg = 0.0;
+                    for (int v = 0; v < nc3; ++v) tg += __shfl_sync(0xffffffffu, gv, (a3 * nc3 + v) & 31);
+                    if (on3) {
+                        const double ph = P.replay ? gv : gv / tg;
+                        S.pi_class[lane] = ph; S.pi_class[nA3 * nc3 + lane] = log(ph);
+                    }
+                }
+            } else if (is_chain && warp == p3warp && S.method == 3) {
                 const double sumS = warp_sum(acc_bb);
                 const double nnz = warp_sum(acc_n);
                 const int nc = S.n_class;
