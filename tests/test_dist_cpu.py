@@ -138,3 +138,63 @@ def test_row_sharded_chain_logic_over_two_ranks_gloo():
         bn = (rr / 1.3) / lhs + rng.standard_normal() / np.sqrt(lhs)
         e -= X[:, j] * (bn - b1[j]); b1[j] = bn
     assert np.allclose(beta, b1, rtol=1e-9) and np.allclose(np.concatenate([pt[2] for pt in parts]), e, rtol=1e-8, atol=1e-10)
+
+
+# ----------------------------------------------------------------------------- row-sharded chain: the host-side exchange steps (round 2)
+def _exchange_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from common import make_problem
+    n, p, B, D = 203, 96, 32, 2
+    prob = make_problem(n, p, 5)
+    codes = prob["codes"].astype(np.int64)
+    per = -(-(-(-n // world)) // 4) * 4                      # bench.py / ShardedChain: shard boundaries on multiples of 4 rows
+    a, b = min(n, rank * per), min(n, (rank + 1) * per)
+    loc = codes[a:b]
+    # (i) whole-column statistics from the all-reduced integer column sums (ngp_get_column_sums -> all-reduce -> ngp_set_column_sums)
+    t = torch.from_numpy(np.stack([loc.sum(0), (loc * loc).sum(0)]))
+    dist.all_reduce(t)
+    cs, css = t[0].numpy().astype(np.float64), t[1].numpy().astype(np.float64)
+    mean, mpm = cs / n, (n * css - cs * cs) / n
+    # (ii) the banded raw Gram of the blocked kernel is a sum over individuals: gx[k][d][a][b] = sum_i g_{(k-d)B+a,i} g_{kB+b,i}
+    nblk = p // B
+    gx = np.zeros((nblk, D + 1, B, B), dtype=np.int64)
+    for k in range(nblk):
+        for d in range(D + 1):
+            if k - d >= 0:
+                gx[k, d] = loc[:, (k - d) * B:(k - d + 1) * B].T @ loc[:, k * B:(k + 1) * B]
+    g = torch.from_numpy(gx.astype(np.int32))
+    sizes = [None] * world
+    dist.all_gather_object(sizes, int(g.numel()))            # bench.allreduce_gram: all ranks must have chosen the same block size / look-ahead
+    dist.all_reduce(g)
+    # (iii) every rank must hold the bitwise identical chain: all-gather and compare as integers (bench.sharded_leg)
+    mine = torch.from_numpy(np.concatenate([mean, mpm]))
+    allb = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allb, mine)
+    identical = all(bool(torch.equal(allb[0].view(torch.int64), x.view(torch.int64))) for x in allb)
+    q.put((rank, a, b, mean, mpm, g.numpy(), sizes, identical))
+    dist.destroy_process_group()
+
+
+def test_row_sharding_exchange_steps_gloo_world2():
+    """the set-up collectives of the row-sharded chain on CPU (gloo, world size 2): row split, column-sum all-reduce, Gram all-reduce"""
+    from common import make_problem
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    prob = make_problem(203, 96, 5)
+    X, mean_o, mpm_o = O.center_codes(prob["codes"])
+    codes = prob["codes"].astype(np.int64)
+    assert res[0][1] == 0 and res[0][2] == res[1][1] == 104 and res[1][2] == 203 and res[0][2] % 4 == 0
+    for r in res:
+        assert np.allclose(r[3], mean_o, rtol=1e-14) and np.allclose(r[4], mpm_o, rtol=1e-12)
+        assert len(set(r[6])) == 1 and r[7]
+    full = codes[:, 0:32].T @ codes[:, 32:64]                 # gx[1][1]: block 0 against block 1, all rows
+    assert np.array_equal(res[0][5][1, 1], full) and np.array_equal(res[0][5], res[1][5])
