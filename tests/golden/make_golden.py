@@ -133,5 +133,45 @@ def main():
         print(name, "varE", ch.varE, "nIn", int(S.delta.sum()))
 
 
+RC = {
+    "bayesrc_pi": dict(n=240, p=80, seed=107, v=0.6, plus=False, iters=12, n_annot=3, v_class=[0.0, 0.001, 0.01, 0.1], pi=[0.7, 0.15, 0.1, 0.05]),
+    "bayesrc_plus": dict(n=240, p=80, seed=108, v=0.6, plus=True, iters=12, n_annot=3, v_class=[0.0, 0.001, 0.01, 0.1], pi=[0.7, 0.15, 0.1, 0.05]),
+}
+
+
+def rc_annot(p, nA, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 2, size=(p, nA)).astype(np.int32)
+    a[a.sum(1) == 0, 0] = 1
+    a[1, :] = np.arange(nA, 0, -1)
+    return a
+
+
+def main_rc():
+    """BayesRCpi / BayesRCplus (functions.jl:291-419): variate logs and per-iteration states of the oracle (python make_golden.py rc)"""
+    from oracle import oracle as O
+    for name, c in RC.items():
+        prob = make_problem(c["n"], c["p"], c["seed"])
+        X, _, mpm = O.center_codes(prob["codes"])
+        annot = rc_annot(c["p"], c["n_annot"], c["seed"])
+        R = O.BayesRCOracle(X, mpm, np.array(c["pi"]), np.array(c["v_class"]), v=c["v"], annot=annot, est_pi=True, plus=c["plus"])
+        ch = O.OracleChain(prob["y"], [], v_e=prob["var_y"] / 2)
+        keys = ("u_annot", "dirp", "u", "z", "chi2_b", "dir_pi")
+        out = {k: [] for k in ("chi2_e", "z_mu", "beta", "delta", "varBeta", "varE", "mu", "pi", "annot_cat") + keys}
+        for _ in range(c["iters"]):
+            log = ch.iteration(seed=c["seed"], chain=2)
+            s = R.sweep(ch.e, ch.varE, it=ch.iter, seed=c["seed"], chain=2)
+            out["chi2_e"].append(log["chi2_e"]); out["z_mu"].append(log["z_mu"])
+            for k in keys:
+                out[k].append(np.array(s[k]))
+            out["beta"].append(R.beta.copy()); out["delta"].append(R.delta.copy()); out["varBeta"].append(R.varBeta.copy())
+            out["varE"].append(ch.varE); out["mu"].append(ch.mu); out["pi"].append(R.piHat.copy()); out["annot_cat"].append(R.annot_cat.copy())
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), e_final=ch.e, annot_prob_final=R.annot_prob, **{k: np.array(v) for k, v in out.items()})
+        print(name, "varE", ch.varE, "classes", np.bincount(R.delta, minlength=5)[1:], "varBeta", R.varBeta)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "rc":
+        main_rc()
+    else:
+        main()

@@ -115,3 +115,31 @@ def test_runLMEM_bayesrc_writes_reference_output_files(gpu, tmp_path):
     pis = np.loadtxt(os.path.join(out, "piMOut"), delimiter="\t", skiprows=1)
     assert an.shape == (2, 40) and set(np.unique(an)) <= {1, 2} and pis.shape == (2, 8) and np.allclose(pis.reshape(2, 2, 4).sum(2), 1.0)
     s.close()
+
+
+@pytest.mark.parametrize("name", ["bayesrc_pi", "bayesrc_plus"])
+def test_bayesrc_replay_against_committed_golden(gpu, name):
+    """The device consumes the committed variate logs (tests/golden/bayesrc_*.npz) and must land on the committed states — no oracle
+    code runs in this test."""
+    import importlib.util
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(gold, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    c = mg.RC[name]; g = np.load(os.path.join(gold, name + ".npz"))
+    prob = make_problem(c["n"], c["p"], c["seed"])
+    s = ngp.Sampler(0)
+    s.upload_genotypes(0, prob["codes"])
+    v = c["v"]
+    s.set_rc_prior(0, c["plus"], 4.0, v * 0.5, v, np.array(c["v_class"]), np.array(c["pi"]), mg.rc_annot(c["p"], c["n_annot"], c["seed"]), est_pi=True)
+    s.set_phenotype(prob["y"]); s.set_residual_prior(4.0, prob["var_y"] / 2 * 0.5); s.set_intercept(True)
+    ni = c["iters"]
+    s.set_replay([{"chi2_e": g["chi2_e"][i], "z_mu": g["z_mu"][i], "sets": []} for i in range(ni)])
+    s.set_rc_replay(0, [{k: g[k][i] for k in ("u_annot", "dirp", "u", "z", "chi2_b", "dir_pi")} for i in range(ni)])
+    s.run(ni)
+    st, rs = s.state(), s.rc_state(0)
+    assert np.array_equal(st["sets"][0]["delta"], g["delta"][-1]) and rel(st["sets"][0]["beta"], g["beta"][-1]) < 1e-8
+    assert rel(st["sets"][0]["varBeta"], g["varBeta"][-1]) < 1e-8 and rel(rs["piHat"], g["pi"][-1]) < 1e-12 and rel(st["e"], g["e_final"]) < 1e-8
+    if not c["plus"]:
+        assert np.array_equal(rs["annot_cat"], g["annot_cat"][-1]) and rel(rs["annot_prob"], g["annot_prob_final"]) < 1e-12
+    s.close()

@@ -330,3 +330,22 @@ def test_bayesrc_oracle_matches_numpy_restatement(plus, est_pi):
     e3 = y - y.mean()
     R3.sweep(e3, 1.3, it=1, seed=1234, chain=0, replay=v1)
     assert np.array_equal(R2.beta, R3.beta) and np.array_equal(e2, e3) and np.array_equal(R2.varBeta, R3.varBeta)
+
+
+@pytest.mark.parametrize("name", ["bayesrc_pi", "bayesrc_plus"])
+def test_bayesrc_oracle_reproduces_its_committed_golden_chain(name):
+    """tests/golden/bayesrc_*.npz (python tests/golden/make_golden.py rc): the oracle, fed the committed variate log, lands on the committed states"""
+    mg = _golden_module()
+    c = mg.RC[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    prob = make_problem(c["n"], c["p"], c["seed"])
+    X, _, mpm = O.center_codes(prob["codes"])
+    R = O.BayesRCOracle(X, mpm, np.array(c["pi"]), np.array(c["v_class"]), v=c["v"], annot=mg.rc_annot(c["p"], c["n_annot"], c["seed"]),
+                        est_pi=True, plus=c["plus"])
+    ch = O.OracleChain(prob["y"], [], v_e=prob["var_y"] / 2)
+    for i in range(c["iters"]):
+        ch.iteration(replay={"chi2_e": float(g["chi2_e"][i]), "z_mu": float(g["z_mu"][i]), "z_fx": [], "sets": []})
+        R.sweep(ch.e, ch.varE, it=ch.iter, replay={k: g[k][i] for k in ("u_annot", "dirp", "u", "z", "chi2_b", "dir_pi")})
+        assert np.array_equal(R.delta, g["delta"][i]) and np.allclose(R.beta, g["beta"][i], rtol=1e-12, atol=1e-15)
+        assert np.allclose(R.varBeta, g["varBeta"][i], rtol=1e-12) and np.isclose(ch.varE, g["varE"][i], rtol=1e-12)
+    assert np.allclose(ch.e, g["e_final"], rtol=1e-10, atol=1e-12) and np.allclose(R.annot_prob, g["annot_prob_final"], rtol=1e-14)
