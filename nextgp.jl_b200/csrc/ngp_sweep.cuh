@@ -29,7 +29,6 @@
 // The "literal" variant does dot / reduce / draw / axpy per marker with one grid-wide reduction per marker (the
 // north-star baseline whose sync cost we report).
 #pragma once
-#include <type_traits>
 #include "ngp_device.cuh"
 #include "ngp_small_la.cuh"
 
@@ -1082,30 +1081,22 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                                 rr[i] = fma(-((double)gram[i][(kb[i] + kk) * B * B + a * B + qb[i]] - csf * cs[i] * inv_n), dbf, rr[i]);
                                         }
                                     } else
-                                    {
-                                        // groups of NG entries: the list reads and the Gram loads of a group are issued together.  Short lists (the
-                                        // mixture priors: 0.9 changed effects per step at C2) go two at a time — a group of four costs 78 instructions
-                                        // whatever it holds — dense lists (BayesPR: B entries) four at a time
-                                        auto near_group = [&](auto ng_tag, int e0) {
-                                            constexpr int NG = decltype(ng_tag)::value;
-                                            int a4[NG]; double db4[NG], cs4[NG]; int g4_[NG][NS];
+                                    for (int e0 = 0; e0 < np; e0 += 4) {
+                                        int a4[4]; double db4[4], cs4[4]; int g4_[4][NS];
 #pragma unroll
-                                            for (int u = 0; u < NG; ++u) {
-                                                const bool on = e0 + u < np;
-                                                a4[u] = on ? pl.idx[e0 + u] : 0; db4[u] = on ? pl.db[e0 + u] : 0.0; cs4[u] = on ? pl.aux[e0 + u] : 0.0;
-                                            }
+                                        for (int u = 0; u < 4; ++u) {
+                                            const bool on = e0 + u < np;
+                                            a4[u] = on ? pl.idx[e0 + u] : 0; db4[u] = on ? pl.db[e0 + u] : 0.0; cs4[u] = on ? pl.aux[e0 + u] : 0.0;
+                                        }
 #pragma unroll
-                                            for (int u = 0; u < NG; ++u)
+                                        for (int u = 0; u < 4; ++u)
 #pragma unroll
-                                                for (int i = 0; i < NS; ++i) g4_[u][i] = gram[i][(kb[i] + kk) * B * B + a4[u] * B + qb[i]];
+                                            for (int i = 0; i < NS; ++i) g4_[u][i] = gram[i][(kb[i] + kk) * B * B + a4[u] * B + qb[i]];
 #pragma unroll
-                                            for (int u = 0; u < NG; ++u)
+                                        for (int u = 0; u < 4; ++u)
 #pragma unroll
-                                                for (int i = 0; i < NS; ++i)
-                                                    rr[i] = fma(-((double)g4_[u][i] - cs4[u] * cs[i] * inv_n), db4[u], rr[i]);
-                                        };
-                                        if (np <= 4) { for (int e0 = 0; e0 < np; e0 += 2) near_group(std::integral_constant<int, 2>{}, e0); }
-                                        else { for (int e0 = 0; e0 < np; e0 += 4) near_group(std::integral_constant<int, 4>{}, e0); }
+                                            for (int i = 0; i < NS; ++i)
+                                                rr[i] = fma(-((double)g4_[u][i] - cs4[u] * cs[i] * inv_n), db4[u], rr[i]);
                                     }
                                 }
                             }
