@@ -281,6 +281,14 @@ int ngp_get_fixed_effects(ngp_handle* h, double* b);                          /*
 /* replay: one standard normal per column and iteration, z[n_iter][n_cols] (functions.jl:34,45); after ngp_set_replay */
 int ngp_set_fixed_replay(ngp_handle* h, int32_t n_iter, const double* z);
 int ngp_set_prior(ngp_handle* h, int set_id, const ngp_prior* prior);
+/* Replace only lhs0 / rhs0 (p doubles each, or NULL = none) of a set that already has a prior; coefficients, indicators and posterior
+ * sums are kept.  The GRN single-site loop (GRN.jl:150-164, sampleΛ2!) runs the same markers once per gene with the offset
+ * alpha*pMeans[g] on the right-hand side: see INTEGRATION.md "GRN". */
+int ngp_set_marker_summary(ngp_handle* h, int set_id, const double* lhs0, const double* rhs0);
+/* Overwrite varBeta (nvar doubles: regions for BayesPR, p for BayesB, 1 else) of one set, nothing else.  BayesLV (functions.jl:421-486)
+ * = the BayesPR sweep with one region per locus, followed by the caller's own model of the log-variances (functions.jl:446-485), which
+ * replaces the scaled-inverse-chi-square draw of the device: see INTEGRATION.md "BayesLV". */
+int ngp_set_var_beta(ngp_handle* h, int set_id, const double* varBeta);
 /* tuple of marker sets with jointly drawn effects (mme.jl:448-489); at most one tuple per handle, and every
  * uploaded set of the handle must be a member                                                            */
 int ngp_set_joint_prior(ngp_handle* h, const ngp_joint_prior* prior);

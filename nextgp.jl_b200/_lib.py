@@ -185,6 +185,8 @@ _SIGS = {
     "ngp_get_fixed_effects": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ngp_set_fixed_replay": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "ngp_set_prior": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Prior)]),
+    "ngp_set_marker_summary": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ngp_set_var_beta": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ngp_set_joint_prior": (C.c_int, [C.c_void_p, C.POINTER(JointPrior)]),
     "ngp_set_joint_replay": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ngp_joint_sweep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),

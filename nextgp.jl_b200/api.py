@@ -72,6 +72,16 @@ class BayesRCType:
 
 
 @dataclass
+class BayesLogVarType:
+    v: float
+    f: Any                       # None: `covariates` already is the (p, k) design matrix; else "1 + x1 + x2" over the columns of `covariates`
+    covariates: Any
+    varZeta: float
+    name: str = "BayesLV"
+    estimateVarZeta: Any = False  # False: fixed varZeta; True: var(residuals of the log-variances); a float: that share of var(logVar)
+
+
+@dataclass
 class RandomEffectType:
     str: Any
     v: float
@@ -112,6 +122,95 @@ def BayesRCpi(pi, class_, v: float, annot, name: str = "BayesRCπ", estimatePi: 
 def BayesRCplus(pi, class_, v: float, annot, name: str = "BayesRCplus", estimatePi: bool = False) -> BayesRCType:
     """runTime.jl:113."""
     return BayesRCType(np.asarray(pi, dtype=np.float64), np.asarray(class_, dtype=np.float64), float(v), np.asarray(annot, dtype=np.int32), name, bool(estimatePi))
+
+
+def BayesLV(v: float, f, covariates, varZeta: float, name: str = "BayesLV", estimateVarZeta=False) -> BayesLogVarType:
+    """runTime.jl:116-133: per-SNP variances with a log-linear model on SNP covariates."""
+    return BayesLogVarType(float(v), f, covariates, float(varZeta), name, estimateVarZeta)
+
+
+def _design_matrix(f, covariates) -> np.ndarray:
+    """modelmatrix(f, covariates) (mme.jl:426) for the terms this mirror knows: "1" and numeric columns, joined by "+"."""
+    if f is None:
+        X = np.asarray(covariates, dtype=np.float64)
+        return X[:, None] if X.ndim == 1 else X
+    cols = []
+    for t in [t.strip() for t in str(f).lstrip("~").split("+")]:
+        if t == "1":
+            cols.append(None)
+        elif t in ("0", "-1", ""):
+            continue
+        else:
+            cols.append(np.asarray(covariates[t], dtype=np.float64))
+    n = next(len(c) for c in cols if c is not None) if any(c is not None for c in cols) else len(next(iter(covariates.values())))
+    return np.column_stack([np.ones(n) if c is None else c for c in cols])
+
+
+class LogVarModel:
+    """Host-side state of a BayesLV marker set (mme.jl:418-440) and the model of the log-variances that follows the single-site loop in
+    sampleBayesLV! (functions.jl:446-485).  O(p k) work per iteration next to the O(n p) sweep on the device."""
+
+    def __init__(self, prior: BayesLogVarType, p: int, rng: np.random.Generator):
+        X = _design_matrix(prior.f, prior.covariates)
+        if X.shape[0] != p:
+            raise ValueError("BayesLV: one row of covariates per SNP")
+        self.covariates = X
+        self.logVar = np.full(p, np.log(prior.v))                               # mme.jl:425
+        self.c = rng.random(X.shape[1])                                         # mme.jl:429
+        self.SNPVARRESID = rng.random(p)                                        # mme.jl:430
+        CpC = X.T @ X
+        CpC = CpC + np.eye(X.shape[1]) * np.min(np.abs(np.diag(CpC) / 10000.0))  # mme.jl:432-434
+        self.iCpC = np.linalg.inv(CpC)                                          # mme.jl:437
+        self.varZeta = float(prior.varZeta)
+        self.estVarZeta = prior.estimateVarZeta
+        self.trapped = 0
+
+    def update(self, beta: np.ndarray, varBeta: np.ndarray, rng: np.random.Generator | None = None, u: np.ndarray | None = None,
+               z: np.ndarray | None = None) -> None:
+        """functions.jl:446-485 after the effects were sampled: slice-type update of every locus' variance (varBeta, in place), the
+        covariate coefficients c ~ MvNormal(iCpC C'logVar, iCpC varZeta), the residuals and varZeta.  u (p, 4) uniforms in the order the
+        reference calls rand() per locus, z (k) standard normals of the MvNormal draw; drawn from rng when not given."""
+        p, k = self.covariates.shape
+        u = rng.random((p, 4)) if u is None else u
+        z = rng.standard_normal(k) if z is None else z
+        vv = self.varZeta
+        bi2 = beta * beta
+        zeta = self.SNPVARRESID
+        var_mui = self.logVar - zeta
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            c1 = varBeta ** -1.5 * u[:, 0]
+            c2 = np.exp(-0.5 * bi2 / varBeta) * u[:, 1]
+            c3 = np.exp(-0.5 * zeta * zeta / vv) * u[:, 2]
+            temp = np.sqrt(-2.0 * vv * np.log(c3))
+            lbound, rbound = np.exp(var_mui - temp), np.exp(var_mui + temp)
+            r1 = np.exp((-2.0 / 3.0) * np.log(c1))
+            rbound = np.where(r1 < rbound, r1, rbound)
+            l1 = -0.5 * bi2 / np.log(c2)
+            lbound = np.where(l1 > lbound, l1, lbound)
+            ok = ~(lbound >= rbound)
+            vari = lbound + u[:, 3] * (rbound - lbound)
+        self.trapped = int(p - ok.sum())
+        varBeta[ok] = vari[ok]
+        self.logVar[ok] = np.log(vari[ok])
+        meanC = self.iCpC @ (self.covariates.T @ self.logVar)
+        cov = self.iCpC * vv
+        cov = np.triu(cov) + np.triu(cov, 1).T                                  # Symmetric(): the upper triangle
+        self.c[:] = meanC + np.linalg.cholesky(cov) @ z
+        self.SNPVARRESID[:] = self.logVar - self.covariates @ self.c
+        if isinstance(self.estVarZeta, float):
+            self.varZeta = self.estVarZeta * float(np.var(self.logVar, ddof=1))
+        elif self.estVarZeta is True:
+            self.varZeta = float(np.var(self.SNPVARRESID, ddof=1))
+
+
+def sampleBayesLV(sampler: "Sampler", set_id: int, model: LogVarModel, beta: np.ndarray, delta: np.ndarray, ycorr: np.ndarray, varE: float,
+                  varBeta: np.ndarray, rng: np.random.Generator | None = None, u=None, z=None) -> None:
+    """sampleBayesLV!(mSet,M,beta,delta,ycorr,varE,varBeta), functions.jl:421-486, host buffers mutated in place.  The single-site loop
+    (functions.jl:431-443) is the BayesPR sweep with one region per locus and runs on the device (ngp_sweep); the variance draw the device
+    appends to that sweep is discarded and the model of the log-variances (functions.jl:446-485) follows on the host."""
+    scratch = varBeta.copy()
+    sampler.sweep(set_id, ycorr, varE, beta, delta, scratch)
+    model.update(beta, varBeta, rng, u, z)
 
 
 def Random(str_: Any, v: float, type: int = 1) -> RandomEffectType:
@@ -548,6 +647,7 @@ class Sampler:
 
     def set_rng(self, seed: int, chain_id: int = 0) -> None:
         self._ck(self._lib.ngp_set_rng(self._h, C.c_uint64(seed), chain_id))
+        self.seed, self.chain_id = int(seed), int(chain_id)
 
     def set_replay(self, logs: list[dict] | None) -> None:
         """logs: list (one per iteration) of the oracle's variate-log dicts
@@ -578,6 +678,22 @@ class Sampler:
     # -- sampling
     def run(self, n_iter: int = 1) -> None:
         self._ck(self._lib.ngp_run(self._h, n_iter))
+
+    def set_var_beta(self, set_id: int, varBeta: np.ndarray) -> None:
+        """Overwrite the effect variances of one set (nvar values), nothing else."""
+        varBeta = np.ascontiguousarray(varBeta, dtype=np.float64)
+        assert varBeta.shape == (self.sets[set_id]["nvar"],)
+        self._ck(self._lib.ngp_set_var_beta(self._h, set_id, _p(varBeta)))
+
+    def set_marker_summary(self, set_id: int, lhs0: np.ndarray | None, rhs0: np.ndarray | None) -> None:
+        """Replace only the per-marker prior information (M[pSet][:lhs] / [:rhs], mme.jl:314-322) of a set; the chain state stays."""
+        if lhs0 is not None:
+            lhs0 = np.ascontiguousarray(lhs0, dtype=np.float64)
+            assert lhs0.shape == (self.sets[set_id]["p"],)
+        if rhs0 is not None:
+            rhs0 = np.ascontiguousarray(rhs0, dtype=np.float64)
+            assert rhs0.shape == (self.sets[set_id]["p"],)
+        self._ck(self._lib.ngp_set_marker_summary(self._h, set_id, _p(lhs0), _p(rhs0)))
 
     def sweep(self, set_id: int, ycorr: np.ndarray, varE: float, beta: np.ndarray, delta: np.ndarray,
               varBeta: np.ndarray, piHat: np.ndarray | None = None) -> None:
@@ -659,6 +775,27 @@ class Sampler:
         out = np.empty(n)
         self._ck(self._lib.ngp_debug_variates(self._h, set_id, it, purpose, df, n, _p(out)))
         return out
+
+
+def sampleLambda2(sampler: Sampler, set_id: int, Lambda2: np.ndarray, yCorr: np.ndarray, var_tau: np.ndarray, varE: float,
+                  pMeans: np.ndarray) -> None:
+    """sampleΛ2!(Λ2,Xc,yCorr,σ2τ,σ2ϵ,pMeans) of the gene-regulatory-network sampler (GRN.jl:150-164), in place: for every gene g one
+    single-site sweep over the SNPs of the uploaded (device-centred, GRN.jl:23) marker set with
+        beta_q ~ N((x_q'yCorr_g + alpha_g pMeans_g) / x_q'x_q, varE / x_q'x_q),   alpha_g = varE / var_tau[g].
+    That is the BayesPR sweep of ngp_sweep with an improper effect prior (varBeta = +Inf, so 1/varBeta = 0: the reference's LHS holds no
+    prior precision) and the right-hand-side offset rhs0 = alpha_g pMeans_g / varE = pMeans_g / var_tau[g] on every marker.
+    Lambda2 (genes, SNPs) and yCorr (genes, individuals) are C-contiguous float64 and are mutated row by row; the set needs a one-region
+    BayesPR prior (set_prior(set_id, BAYESPR, ...)).  Draws: the handle's counter stream, one iteration index per gene sweep."""
+    info = sampler.sets[set_id]
+    assert info.get("method") == L.BAYESPR and info["nvar"] == 1, "sampleLambda2 needs a one-region BayesPR set"
+    assert Lambda2.dtype == np.float64 and Lambda2.flags.c_contiguous and yCorr.dtype == np.float64 and yCorr.flags.c_contiguous
+    nGenes, nSNPs = Lambda2.shape
+    assert yCorr.shape == (nGenes, sampler.n) and nSNPs == info["p"]
+    delta = np.ones(nSNPs, dtype=np.int64)
+    for g in range(nGenes):
+        sampler.set_marker_summary(set_id, None, np.full(nSNPs, pMeans[g] / var_tau[g]))
+        vb = np.array([np.inf])
+        sampler.sweep(set_id, yCorr[g], varE, Lambda2[g], delta, vb)
 
 
 class ShardedChain:
@@ -842,6 +979,8 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
                 method, region_off, pi = L.BAYESR, None, 0.0
             elif name in ("BayesRCπ", "BayesRCplus"):                             # mme.jl:385-418
                 method, region_off, pi = (L.BAYESRCPI if name == "BayesRCπ" else L.BAYESRCPLUS), None, 0.0
+            elif name == "BayesLV":                                             # mme.jl:418-440: theseRegions = [r:r for r in 1:p]
+                method, region_off, pi = L.BAYESPR, np.arange(p + 1, dtype=np.int64), 0.0
             else:
                 raise NotImplementedError(f"{name} stays in Julia: SURVEY §8(f2)")
         df = 3.0 + 1.0                                                          # mme.jl:493 (scalar v)
@@ -856,6 +995,8 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
         nvar = sampler.sets[sid]["nvar"]
         info.append({"name": term.name, "method": name, "p": p, "nvar": nvar, "df": df, "scale": scale,
                      "n_pi": (len(pr.class_) if name == "BayesR" else len(pr.class_) * nvar if name in ("BayesRCπ", "BayesRCplus") else 2)})
+        if name == "BayesLV":
+            info[-1]["lv"] = LogVarModel(pr, p, np.random.default_rng([getattr(sampler, "seed", 0), getattr(sampler, "chain_id", 0), sid]))
     fixed = fixed or []                                                          # [(name, data (n,c), level names)]
     if fixed:
         sampler.set_fixed_effects([d for _, d, _ in fixed])                      # X[xSet] besides the intercept (functions.jl:22-54)
@@ -874,6 +1015,9 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
                 outMCMC(outPut, f"pi{term.name}", [[f"pi{v}" for v in range(1, inf["n_pi"] + 1)]])
             if inf["method"] in ("BayesRCπ", "BayesRCplus"):
                 outMCMC(outPut, f"annot{term.name}", [levels])
+            if inf["method"] == "BayesLV":                                      # mme.jl:577-579
+                outMCMC(outPut, f"c{term.name}", [[f"c{v}" for v in range(1, len(inf["lv"].c) + 1)]])
+                outMCMC(outPut, f"varZeta{term.name}", [["varZeta"]])
         for term, inf in zip(M, info):
             outMCMC(outPut, f"var{term.name}", [[f"reg_{r}" for r in range(1, inf["nvar"] + 1)]])
         outMCMC(outPut, "varE", [["e"]])
@@ -928,13 +1072,29 @@ def runSampler(sampler: Sampler, M: list[MarkerTerm], info: dict, chainLength: i
     """samplers.runSampler! (samplers.jl:23-106): iterations run on device in batches that end on a kept iteration;
     kept samples are written in the order of samplers.jl:57-103."""
     these2Keep = list(range(burnIn + outputFreq, chainLength + 1, outputFreq))   # samplers.jl:26
+    lv = [(sid, inf["lv"]) for sid, inf in enumerate(info["sets"]) if "lv" in inf]
+
+    def run(k: int) -> None:
+        if not lv:
+            return sampler.run(k)
+        # BayesLV: one iteration per launch; after each one the host replaces the variances of the LV sets (functions.jl:446-485)
+        rng = info.setdefault("lv_rng", np.random.default_rng([getattr(sampler, "seed", 0), getattr(sampler, "chain_id", 0), 1 << 20]))
+        for _ in range(k):
+            sampler.run(1)
+            if "lv_var" not in info:
+                info["lv_var"] = {sid: np.full(m.logVar.shape, np.exp(m.logVar[0])) for sid, m in lv}
+            st = sampler.state(want_e=False)
+            for sid, m in lv:
+                m.update(st["sets"][sid]["beta"], info["lv_var"][sid], rng)
+                sampler.set_var_beta(sid, info["lv_var"][sid])
+
     done = 0
     if burnIn > 0:
-        sampler.run(min(burnIn, chainLength))
+        run(min(burnIn, chainLength))
         done = min(burnIn, chainLength)
     sampler.reset_posterior()                                                    # device-side posterior sums exclude burn-in
     for it in these2Keep:
-        sampler.run(it - done)
+        run(it - done)
         done = it
         st = sampler.state(want_e=False)
         if outPut is not None:
@@ -952,6 +1112,9 @@ def runSampler(sampler: Sampler, M: list[MarkerTerm], info: dict, chainLength: i
                     st["sets"][sid]["rc"] = rs
                     outMCMC(outPut, f"pi{term.name}", rs["piHat"].ravel())
                     outMCMC(outPut, f"annot{term.name}", rs["annot_cat"])
+                if inf["method"] == "BayesLV":                                   # samplers.jl:89-92
+                    outMCMC(outPut, f"c{term.name}", inf["lv"].c)
+                    outMCMC(outPut, f"varZeta{term.name}", inf["lv"].varZeta)
             for sid, term in enumerate(M):
                 if not info.get("tuple"):
                     outMCMC(outPut, f"var{term.name}", st["sets"][sid]["varBeta"])
@@ -964,7 +1127,7 @@ def runSampler(sampler: Sampler, M: list[MarkerTerm], info: dict, chainLength: i
         if on_sample is not None:
             on_sample(it, st)
     if done < chainLength:
-        sampler.run(chainLength - done)
+        run(chainLength - done)
 
 
 _SNP_RE = re.compile(r"SNP\(\s*([A-Za-z_]\w*)\s*,\s*([^,\)]+?)\s*(?:,\s*([^\)]+?)\s*)?\)")

@@ -1014,6 +1014,39 @@ int ngp_set_prior(ngp_handle* h, int set_id, const ngp_prior* pr)
     return NGP_OK;
 }
 
+// Replace only the per-marker prior information (lhs0 / rhs0) of a set; the chain state is kept.  GRN.jl:150-164 (sampleΛ2!) changes
+// the right-hand-side offset alpha*pMeans[g] for every gene g while the markers stay the same.
+int ngp_set_marker_summary(ngp_handle* h, int set_id, const double* lhs0, const double* rhs0)
+{
+    if (!h) return NGP_EINVAL;
+    if (set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_prior)
+        return fail(h, NGP_EINVAL, "ngp_set_marker_summary: marker set %d has no prior yet", set_id);
+    CU(cudaSetDevice(h->device));
+    SetHost& S = h->sets[set_id];
+    if (S.method == NGP_BAYESR && (lhs0 || rhs0)) return fail(h, NGP_EUNSUPPORTED, "ngp_set_marker_summary: BayesR takes no summary statistics (functions.jl:232-281)");
+    const double* src[2] = {lhs0, rhs0};
+    double** dst[2] = {&S.lhs0, &S.rhs0};
+    for (int i = 0; i < 2; ++i) {
+        if (!src[i]) { if (*dst[i]) { CU(cudaStreamSynchronize(h->stream)); cudaFree(*dst[i]); *dst[i] = nullptr; h->sets_dirty = true; } continue; }
+        if (!*dst[i]) { CU(dalloc(dst[i], S.p)); h->sets_dirty = true; }
+        CU(cpy(h, *dst[i], src[i], sizeof(double) * S.p, cudaMemcpyHostToDevice));
+    }
+    return NGP_OK;
+}
+
+// Overwrite the effect variances of one set (nvar doubles) and nothing else.  BayesLV (functions.jl:421-486) keeps the variance model of
+// the log-variances on the host: after every BayesPR sweep with one region per locus the caller replaces the device's draw by its own.
+int ngp_set_var_beta(ngp_handle* h, int set_id, const double* varBeta)
+{
+    if (!h) return NGP_EINVAL;
+    if (set_id < 0 || set_id >= NGP_MAX_SETS || !h->sets[set_id].have_prior || !h->sets[set_id].varBeta || !varBeta)
+        return fail(h, NGP_EINVAL, "ngp_set_var_beta: marker set %d has no prior yet, or NULL argument", set_id);
+    CU(cudaSetDevice(h->device));
+    SetHost& S = h->sets[set_id];
+    CU(cpy(h, S.varBeta, varBeta, sizeof(double) * S.nvar, cudaMemcpyHostToDevice));
+    return NGP_OK;
+}
+
 int ngp_set_rng(ngp_handle* h, uint64_t seed, uint32_t chain_id)
 {
     if (!h) return NGP_EINVAL;

@@ -11,6 +11,8 @@ All draws are explicit inputs (the replay-log format of oracle.OracleChain).
   bayes_b            functions.jl:157-195
   bayes_c            functions.jl:197-236
   iteration          samplers.jl:32-53
+  bayes_lv           functions.jl:421-486 (sampleBayesLV!), set-up mme.jl:418-440
+  grn_sample_lambda2 GRN.jl:150-164 (sampleΛ2!), sampleBeta GRN.jl:234-236
 """
 import numpy as np
 
@@ -259,3 +261,91 @@ def bayes_rc(X, mpm, e, varE, beta, delta, annot_cat, varBeta, piHat, logPi, ann
             piHat[a, :] = v["dir_pi"][a, :]
             logPi[a, :] = np.log(v["dir_pi"][a, :])
     return nLoci, nNonZero
+
+
+def grn_sample_lambda2(Lambda2, Xc, yCorr, var_tau, varE, pMeans, z):
+    """sampleΛ2!(Λ2,Xc,yCorr,σ2τ,σ2ϵ,pMeans), GRN.jl:150-164, statement by statement.  Xc (SNPs, individuals) row-centred (GRN.jl:23);
+    yCorr (genes, individuals); z (genes, SNPs) the standard normals behind rand(Normal(meanBeta, sqrt(lhs\σ2E))) (GRN.jl:234-236)."""
+    nGenes, nSNPs = yCorr.shape[0], Xc.shape[0]
+    for g in range(nGenes):
+        alpha = varE / var_tau[g]
+        for q in range(nSNPs):
+            yCorr[g, :] += Lambda2[g, q] * Xc[q, :]
+            RHS = Xc[q, :] @ yCorr[g, :] + alpha * pMeans[g]
+            LHS = Xc[q, :] @ Xc[q, :]
+            meanBeta = RHS / LHS
+            nowBeta = meanBeta + np.sqrt(varE / LHS) * z[g, q]
+            Lambda2[g, q] = nowBeta
+            yCorr[g, :] -= nowBeta * Xc[q, :]
+
+
+class _JuliaMath:
+    @staticmethod
+    def log(x):
+        with np.errstate(all="ignore"):
+            return float(np.log(np.float64(x)))
+
+    @staticmethod
+    def exp(x):
+        with np.errstate(all="ignore"):
+            return float(np.exp(np.float64(x)))
+
+    @staticmethod
+    def sqrt(x):
+        with np.errstate(all="ignore"):
+            return float(np.sqrt(np.float64(x)))
+
+
+def bayes_lv(X, mpm, lhs0, rhs0, beta, ycorr, varE, varBeta, M, z, u, zc):
+    """sampleBayesLV!, functions.jl:421-486, statement by statement.  M: dict with logVar, SNPVARRESID, covariates, iCpC, c, varZeta (1-list),
+    estVarZeta (the fields of mme.jl:418-440).  z (p) normals of sampleBeta, u (p, 4) the rand() calls per locus in the order of the text
+    (the 4th only when the slice is not trapped), zc (k) normals of the MvNormal draw.  Returns the trapped count."""
+    math = _JuliaMath          # log(0) = -Inf, exp overflow = Inf like Julia (no exceptions)
+    var_var = M["varZeta"][0]
+    iVarE = 1.0 / varE
+    p = len(beta)
+    for locus in range(p):                                            # regionArray = [r:r for r in 1:p]
+        ycorr += beta[locus] * X[:, locus]
+        rhs = (X[:, locus] @ ycorr) * iVarE + rhs0[locus]
+        lhs = mpm[locus] * iVarE + lhs0[locus] + 1.0 / varBeta[locus]
+        beta[locus] = rhs / lhs + math.sqrt(1.0 / lhs) * z[locus]
+        ycorr += -1.0 * beta[locus] * X[:, locus]
+    trapped = 0
+    for locus in range(p):
+        vari = float(varBeta[locus])
+        bi = float(beta[locus])
+        log_vari = float(M["logVar"][locus])
+        zeta = float(M["SNPVARRESID"][locus])
+        var_mui = log_vari - zeta
+        c1 = float(np.float64(vari) ** -1.5) * u[locus, 0]
+        c2 = math.exp(-0.5 * bi * bi / vari) * u[locus, 1]
+        c3 = math.exp(-0.5 * zeta * zeta / var_var) * u[locus, 2]
+        temp = math.sqrt(-2.0 * var_var * math.log(c3))
+        lbound = math.exp(var_mui - temp)
+        rbound = math.exp(var_mui + temp)
+        if math.exp((-2.0 / 3.0) * math.log(c1)) < rbound:
+            rbound = math.exp((-2.0 / 3.0) * math.log(c1))
+        with np.errstate(all="ignore"):
+            l1 = float(np.float64(-0.5 * bi * bi) / np.float64(math.log(c2)))
+        if l1 > lbound:
+            lbound = l1
+        if lbound >= rbound:
+            trapped += 1
+        else:
+            vari = lbound + u[locus, 3] * (rbound - lbound)
+            varBeta[locus] = vari
+            M["logVar"][locus] = math.log(vari)
+    rhsC = M["covariates"].T @ M["logVar"]
+    meanC = M["iCpC"] @ rhsC
+    cov = M["iCpC"] * var_var
+    cov = np.triu(cov) + np.triu(cov, 1).T                            # Symmetric(): the upper triangle
+    M["c"][:] = meanC + np.linalg.cholesky(cov) @ zc                  # rand(MvNormal(mean, cov)) = mean + chol(cov).L z
+    M["SNPVARRESID"][:] = M["logVar"] - M["covariates"] @ M["c"]
+    est = M["estVarZeta"]
+    if isinstance(est, float):
+        M["varZeta"][0] = est * np.var(M["logVar"], ddof=1)
+    elif est is False:
+        pass
+    elif est is True:
+        M["varZeta"][0] = np.var(M["SNPVARRESID"], ddof=1)
+    return trapped
