@@ -576,7 +576,7 @@ static int choose_geometry(ngp_handle* h, int64_t n, int store2)
             if (D < dn_min) break;
             DN = std::max(dn_min, std::min(DN, D));
             const int nt_min = refetch ? 1 : D + 2;
-            int NT = refetch ? legal_nt(h->cfg_tile_stages ? h->cfg_tile_stages : (B == 64 ? (R <= 512 ? 4 : 2) : 8)) : (h->cfg_tile_stages ? std::max(h->cfg_tile_stages, nt_min) : D + 4);
+            int NT = refetch ? legal_nt(h->cfg_tile_stages ? h->cfg_tile_stages : (B == 64 ? ((R <= 512 || store2) ? 4 : 2) : 8)) : (h->cfg_tile_stages ? std::max(h->cfg_tile_stages, nt_min) : D + 4);
             // shrink the record ring of the chain CTA, the tile ring, then the look-ahead, until both CTA roles fit
             for (;;) {
                 for (int NR = kRecStages; NR >= 2; NR >>= 1) {
@@ -1319,6 +1319,10 @@ static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, 
     if (h->R > 4 * kUpdThreads && h->B != 16) {          // more than 512 rows per CTA with blocks of 32 / 64: the instantiation with 4 row groups per updater thread
         if (variant != NGP_KV_PLAIN) return fail(h, NGP_EUNSUPPORTED, "%d rows per CTA with blocks of %d: only the plain blocked sweep is built for this geometry (use blocks of 16)", h->R, h->B);
         variant = NGP_KV_BIGR;
+    }
+    if (sharded && variant != NGP_KV_LIT) {               // the row-sharded blocked sweep is its own instantiation (SH): the one-GPU kernels do not carry its code
+        if (variant != NGP_KV_PLAIN && variant != NGP_KV_BIGR) return fail(h, NGP_EUNSUPPORTED, "row-sharded chain: the plain blocked sweep or the per-marker sweep (no profile / debug / tuple / BayesR-blocked instantiation)");
+        if (!group) variant = (variant == NGP_KV_BIGR) ? NGP_KV_SHARD_BIGR : NGP_KV_SHARD;
     }
     if (h->store2 > 0 && (variant == NGP_KV_LIT || variant == NGP_KV_TUP))   // (the blocked BayesR sweep reads 2-bit tiles like the plain one)
         return fail(h, NGP_EUNSUPPORTED, "2-bit device storage serves the blocked sweep of BayesPR / BayesB / BayesC sets (not the per-marker kernel: "

@@ -359,7 +359,10 @@ __device__ __forceinline__ void joint_step(double (&rr)[NS], const double (&bold
 // LIT: the per-marker ("literal") sweep instead of the blocked one — a separate instantiation, so that neither variant carries the other's code
 // TUP: the instantiation that also sweeps a tuple of interleaved marker sets (method 4); kept apart so that the k x k algebra does not
 //      weigh on the register allocation of the single-trait sweep
-template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false, bool BR = false>
+// SH: the blocked sweep of a row-sharded chain (system-scope REDs into every rank's accumulators, runtime arrival-count bits, rank-local
+// pre-reduction).  Compiled out of the one-GPU instantiations: its code in the dot / prep warps' loops cost the plain sweep 5 % (int8) to
+// 18 % (2-bit) through instruction-cache pressure alone (A/B of round 2).  The per-marker sweep (LIT) always carries it.
+template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false, bool BR = false, bool SH = false>
 __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -410,10 +413,11 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
     long long* prev = reinterpret_cast<long long*>(smem + L.c_prev);                        // [kSlots][B]
     NzList* cnz = reinterpret_cast<NzList*>(smem + L.c_nz);
 
-    const bool sharded = P.n_ranks > 1;
-    const int cb = P.cnt_bits;                               // arrival-count bits of the accumulators
+    constexpr bool kSh = LIT || SH;
+    const bool sharded = kSh && P.n_ranks > 1;
+    const int cb = kSh ? P.cnt_bits : kCntBits;              // arrival-count bits of the accumulators
     const long long cmask = (1LL << cb) - 1;
-    const long long arr_all = (long long)P.Tw_all;           // worker CTAs of all ranks add into every rank's accumulators
+    const long long arr_all = kSh ? (long long)P.Tw_all : (long long)Tw;     // worker CTAs of all ranks add into every rank's accumulators
     GridSync gs{&sy->err, &sy->counter, 0ull, (unsigned)P.T_all, P.bar_base, P.n_ranks};
     const int64_t row0 = (int64_t)t * R;
     const int nrow = is_chain ? 0 : (int)max((int64_t)0, min((int64_t)R, P.n - row0));    // real rows of this panel
@@ -783,7 +787,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                         // ------------------------------------------------------------------ dot warps: whole blocks, 8 in flight
                         const int dw = warp - kFirstDotWarp;
                         const int g = lane >> 2, tt = lane & 3;
-                        const long long plim = (1LL << (63 - cb)) / P.Tw_all;
+                        const long long plim = (1LL << (63 - cb)) / arr_all;
                         // refetch mode: a stage is always consumed by the same warp (the dot warps taking part divide NT), so an mbarrier
                         // waiter is never more than one fill behind
                         const int ND = !P.refetch ? kDotWarps : (NT >= 8) ? 8 : (NT >= 4) ? 4 : (NT >= 2) ? 2 : 1;
@@ -1975,10 +1979,10 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
 #undef NGP_TICK
 }
 
-template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false, bool BR = false>
+template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false, bool BR = false, bool SH = false>
 __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 {
-    gibbs_body<B, PROF, DBG, LIT, TUP, BIGR, BR>(P, (int)blockIdx.x);
+    gibbs_body<B, PROF, DBG, LIT, TUP, BIGR, BR, SH>(P, (int)blockIdx.x);
 }
 
 // All ranks of a row-sharded chain whose shards live on ONE device, as ONE cooperative grid (the only legal way to run kernels that wait
@@ -2003,7 +2007,7 @@ __global__ void __launch_bounds__(kThreads, 1) gibbs_group_kernel(const GroupPar
         for (int i = threadIdx.x; i < (int)(sizeof(Params) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    gibbs_body<B, false, false, LIT, false>(Ps, (int)blockIdx.x - Ps.cta_off);
+    gibbs_body<B, false, false, LIT, false, false, false, !LIT>(Ps, (int)blockIdx.x - Ps.cta_off);
 }
 
 }  // namespace ngp
