@@ -83,7 +83,7 @@ def translation_units() -> list[tuple[str, str, list[str]]]:
     """(object name, source file, extra flags): one instantiation of the sweep kernels per unit (csrc/ngp_kernels.h)."""
     tus = [("ngp_api", "ngp_api.cu", []), ("ngp_ingest", "ngp_ingest.cpp", [])]
     for B in (16, 32, 64):
-        for v in range(11):
+        for v in range(12):
             tus.append((f"ngp_k_gibbs_{B}_{v}", "ngp_k_gibbs.cu", [f"-DNGP_KB={B}", f"-DNGP_KV={v}"]))
     for k in range(2, 9):
         tus.append((f"ngp_k_joint_{k}", "ngp_k_joint.cu", [f"-DNGP_JK={k}"]))

@@ -553,11 +553,14 @@ static int choose_geometry(ngp_handle* h, int64_t n, int store2)
     // Blocks of 64 markers halve the number of trips round the feedback loop (list -> residual version -> dots -> sums) against blocks of
     // 32, and the chain warp steps over 64 markers anyway.  Panels of up to 512 rows: 2-bit tiles of 64 markers (16 R bytes) stay
     // resident with 12 blocks of look-ahead; int8 tiles (64 R bytes) use the refetch ring.  Larger panels (the BIGR instantiation): blocks of 64 for 2-bit tiles and for int8 panels of up to
-    // 1024 rows (refetch ring of 2 stages: C3 21.3 -> 15.3 ms/sweep), blocks of 16 beyond (sweeps in profiles/r2/tune_*.jsonl).
-    if (!B) B = (R <= 1024 || store2) ? 64 : 16;
+    // 1024 rows (refetch ring of 2 stages: C3 21.3 -> 15.3 ms/sweep); beyond, int8, a ring of ONE tile whose dots all 8 dot warps share (C5 3.24 with
+    // blocks of 16 -> 2.53 ms/sweep; sweeps in profiles/r2/tune_*.jsonl).
     const int64_t maxR = 4LL * kUpdThreads * kUpdGroups;     // residual rows the updater warps hold in registers
     if (R > maxR)
         return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA; at most %lld are supported", (long long)n, (long long)R, (long long)maxR);
+    const bool auto_B = (B == 0);
+    if (auto_B) B = 64;
+  for (;;) {                                                 // (blocks of 64, else — automatic choice only — blocks of 16 where a tile of 64 markers does not fit)
     const int dn_min = 2 * ((B == 16 ? 32 : 64) / B) - 1;    // the chain warp steps over 64 markers (32 for blocks of 16): distances inside two steps come from the records
     // Two tile-ring modes.  resident: a tile stays in shared memory until its block has been applied to e (NT >= D + 2), so the rare
     // residual update reads it there.  refetch: a tile stays only until its dots are formed (NT = 8 / 4 / 2 / 1 stages, consumed by as many
@@ -582,7 +585,9 @@ static int choose_geometry(ngp_handle* h, int64_t n, int store2)
                 for (int NR = kRecStages; NR >= 2; NR >>= 1) {
                     const int NV = h->cfg_versions ? h->cfg_versions : std::max(4, std::min(kLimbVers, D / 2 + 3));
                     SmemLayout L = smem_layout((int)R, B, NT, DN, NR, NV, store2);
-                    if ((size_t)L.total + 2048 <= cap) {
+                    // static shared memory of the kernels: 1.5 KB, + 4.1 KB in the instantiation whose dot warps share the one tile of the ring
+                    const size_t stat = 2048 + ((refetch && NT == 1 && R > 4 * kUpdThreads && B != 16) ? (size_t)kDotWarps * B * 8 + 64 : 0);
+                    if ((size_t)L.total + stat <= cap) {
                         h->n = n; h->Tw = Tw; h->R = (int)R; h->B = B; h->D = D; h->DN = DN; h->NT = NT; h->NR = NR; h->NV = NV; h->L = L;
                         h->refetch = refetch;
                         return true;
@@ -603,6 +608,9 @@ static int choose_geometry(ngp_handle* h, int64_t n, int store2)
         if (search(1)) return NGP_OK;
         if (search(0)) return NGP_OK;
     }
+    if (auto_B && B == 64) { B = 16; continue; }
+    break;
+  }
     return fail(h, NGP_EUNSUPPORTED, "n = %lld needs %lld rows per CTA: the panel tiles (block %d) do not fit in %zu bytes of shared memory",
                 (long long)n, (long long)R, B, cap);
 }
@@ -1316,9 +1324,9 @@ static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, 
     for (int s = 0; s < h->n_sets; ++s) if (((set_mask >> s) & 1) && h->sets[s].group_k) tuple_mask = true;
     int variant = tuple_mask ? NGP_KV_TUP : (P.kernel == NGP_KERNEL_LITERAL) ? NGP_KV_LIT : h->cfg_debug ? NGP_KV_DBG : h->cfg_profile ? NGP_KV_PROF : NGP_KV_PLAIN;
     if (r_blocked) variant = NGP_KV_R;
-    if (h->R > 4 * kUpdThreads && h->B != 16) {          // more than 512 rows per CTA with blocks of 32 / 64: the instantiation with 4 row groups per updater thread
+    if (h->R > 4 * kUpdThreads && h->B != 16 && variant != NGP_KV_LIT) {   // more than 512 rows per CTA with blocks of 32 / 64: the instantiation with 4 row groups per updater thread (the per-marker sweep keeps e in shared memory: any panel)
         if (variant != NGP_KV_PLAIN) return fail(h, NGP_EUNSUPPORTED, "%d rows per CTA with blocks of %d: only the plain blocked sweep is built for this geometry (use blocks of 16)", h->R, h->B);
-        variant = NGP_KV_BIGR;
+        variant = (h->refetch && h->NT == 1 && !sharded) ? NGP_KV_BIGR1 : NGP_KV_BIGR;      // one tile in the ring: its dots are shared by the 8 dot warps
     }
     if (sharded && variant != NGP_KV_LIT) {               // the row-sharded blocked sweep is its own instantiation (SH): the one-GPU kernels do not carry its code
         if (variant != NGP_KV_PLAIN && variant != NGP_KV_BIGR) return fail(h, NGP_EUNSUPPORTED, "row-sharded chain: the plain blocked sweep or the per-marker sweep (no profile / debug / tuple / BayesR-blocked instantiation)");

@@ -23,6 +23,8 @@ extern "C" const void* NGP_CAT3(ngp_kptr_gibbs_, NGP_KB, NGP_KV)(void)
     return (const void*)ngp::gibbs_kernel<NGP_KB, false, false, false, false, false, false, true>;
 #elif NGP_KV == 10
     return (const void*)ngp::gibbs_kernel<NGP_KB, false, false, false, false, true, false, true>;
+#elif NGP_KV == 11
+    return (const void*)ngp::gibbs_kernel<NGP_KB, false, false, false, false, true, false, false, true>;
 #else
     return (const void*)ngp::gibbs_kernel<NGP_KB, NGP_KV == NGP_KV_PROF, NGP_KV == NGP_KV_DBG, NGP_KV == NGP_KV_LIT, NGP_KV == NGP_KV_TUP>;
 #endif

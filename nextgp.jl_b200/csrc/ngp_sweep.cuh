@@ -362,7 +362,8 @@ __device__ __forceinline__ void joint_step(double (&rr)[NS], const double (&bold
 // SH: the blocked sweep of a row-sharded chain (system-scope REDs into every rank's accumulators, runtime arrival-count bits, rank-local
 // pre-reduction).  Compiled out of the one-GPU instantiations: its code in the dot / prep warps' loops cost the plain sweep 5 % (int8) to
 // 18 % (2-bit) through instruction-cache pressure alone (A/B of round 2).  The per-marker sweep (LIT) always carries it.
-template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false, bool BR = false, bool SH = false>
+// SHT (with BIGR): refetch ring of ONE tile whose dots all 8 dot warps share (see the dot warps).
+template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false, bool BR = false, bool SH = false, bool SHT = false>
 __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -451,6 +452,9 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
     __syncthreads();
 
     __shared__ double fx_s[2 * kMaxFxCols];          // fixed effects: [0..32) the effects, [32..64) Yi of the set being sampled
+    __shared__ long long comb[SHT ? kDotWarps * B : 1];      // SHT: [8][B] partial sums of the dot warps sharing a tile (static: only that instantiation pays)
+    __shared__ int ccnt_s[1];                                // SHT: warps that have stored their sums
+    if constexpr (SHT) { if (tid == 0) ccnt_s[0] = 0; __syncthreads(); }
     __shared__ long long step_end_clk[64];
     __shared__ unsigned long long pub_ns[kNzRing];   // instrumented kernel: global time at which a list was published (worker CTA copy / chain CTA copy)        // instrumented kernel: clock at which the chain warp finished a step
     // cycle counters, see ngp_get_profile
@@ -791,7 +795,14 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                         // refetch mode: a stage is always consumed by the same warp (the dot warps taking part divide NT), so an mbarrier
                         // waiter is never more than one fill behind
                         const int ND = !P.refetch ? kDotWarps : (NT >= 8) ? 8 : (NT >= 4) ? 4 : (NT >= 2) ? 2 : 1;
-                        const int j0 = (dw < ND) ? (int)((unsigned)(dw - (int)(gblk & (unsigned)(ND - 1))) & (unsigned)(ND - 1)) : nblk;    // first j with (gblk+j) % ND == dw
+                        // BIGR on a refetch ring of ONE tile (a tile of 64 markers x > 1024 rows: two do not fit): all 8 dot warps share every tile — warp wsub
+                        // takes the 32-row chunks wsub, wsub + 8, ... — and the last of them to finish adds up the 8 partial sums, pushes them and
+                        // frees the tile (one warp needs longer for the dots of 88 KB than their load takes: C5 int8 3.24 -> 2.53 ms/sweep).  With two
+                        // or four tiles in the ring sharing did not pay (C3 int8 14.1 -> 14.5, C5 2-bit 1.87 -> 2.05 ms: profiles/r2/tune_*_split_v1.jsonl).
+                        constexpr int W = SHT ? kDotWarps : 1;                // (the launch picks the SHT instantiation for BIGR on a refetch ring with NT == 1)
+                        const int grp = (W > 1) ? 0 : dw, wsub = (W > 1) ? dw : 0;
+                        int* ccnt = ccnt_s;
+                        const int j0 = (grp < ND) ? (int)((unsigned)(grp - (int)(gblk & (unsigned)(ND - 1))) & (unsigned)(ND - 1)) : nblk;    // first j with (gblk+j) % ND == grp
                         int tslot = (int)((gblk + (unsigned)j0) % (unsigned)NT);
                         uint32_t tph = ((gblk + (unsigned)j0) / (unsigned)NT) & 1u;
                         constexpr int CH = (MG >= 4) ? 1 : 4 / MG;          // independent accumulator chains per marker group
@@ -805,6 +816,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                 ver = vbuf[ga & (kNzRing - 1)];
                             }
                             if (tid == kFirstDotWarp * 32) NGP_TICK(14);
+                            bool pusher = true;              // (BIGR with a shared tile: only the last warp to finish pushes the sums)
                             mbar_wait(&tile_full[tslot], tph);
                             if (tid == kFirstDotWarp * 32) NGP_TICK(20);
                             if (!(dbg & 8)) {
@@ -818,10 +830,10 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                 if (P.store2) {
                                     // 2-bit tiles: one 32-bit word per lane and MMA atom, expanded to the four A registers on chip
                                     const uint32_t* tile2 = reinterpret_cast<const uint32_t*>(tile);
-                                    for (int c0 = 0; c0 < nchunk; c0 += CH) {
+                                    for (int c0 = wsub; c0 < nchunk; c0 += W * CH) {
 #pragma unroll
                                         for (int ch = 0; ch < CH; ++ch) {
-                                            const int c = c0 + ch;
+                                            const int c = c0 + ch * W;
                                             if (c < nchunk) {
                                                 const uint32_t b0 = lv[c * 64 + lane], b1 = lv[c * 64 + 32 + (lane ^ 4)];
 #pragma unroll
@@ -833,10 +845,10 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                         }
                                     }
                                 } else
-                                for (int c0 = 0; c0 < nchunk; c0 += CH) {
+                                for (int c0 = wsub; c0 < nchunk; c0 += W * CH) {
 #pragma unroll
                                     for (int ch = 0; ch < CH; ++ch) {
-                                        const int c = c0 + ch;
+                                        const int c = c0 + ch * W;
                                         if (c < nchunk) {
                                             const uint32_t b0 = lv[c * 64 + lane], b1 = lv[c * 64 + 32 + (lane ^ 4)];
 #pragma unroll
@@ -849,6 +861,63 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                                 }
                                 if (tid == kFirstDotWarp * 32) NGP_TICK(1);
                                 long long* accg = sy->acc + (size_t)(gidx & (kSlots - 1)) * kMaxB * kAccStride;
+                                if constexpr (SHT) {
+                                    long long part[MG];              // lanes tt = 0 / 1: this warp's sums of markers 16 mg + g / + 8
+#pragma unroll
+                                    for (int mg = 0; mg < MG; ++mg) {
+                                        int c4[4];
+#pragma unroll
+                                        for (int x = 0; x < 4; ++x) {
+                                            c4[x] = acc[mg][0][x];
+#pragma unroll
+                                            for (int ch = 1; ch < CH; ++ch) c4[x] += acc[mg][ch][x];
+                                        }
+                                        unsigned long long v0 = ((unsigned long long)(long long)c4[0] << (16 * tt)) + ((unsigned long long)(long long)c4[1] << (16 * tt + 8));
+                                        unsigned long long v1 = ((unsigned long long)(long long)c4[2] << (16 * tt)) + ((unsigned long long)(long long)c4[3] << (16 * tt + 8));
+                                        v0 += __shfl_xor_sync(0xffffffffu, v0, 1); v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+                                        v0 += __shfl_xor_sync(0xffffffffu, v0, 2); v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+                                        part[mg] = (long long)(tt ? v1 : v0);
+                                    }
+                                    if (W > 1) {
+                                        // (the tile is freed by the last warp, after it has read every row of sums: no warp is a tile ahead of the others)
+                                        if (tt < 2) {
+#pragma unroll
+                                            for (int mg = 0; mg < MG; ++mg) comb[wsub * B + mg * 16 + g + 8 * tt] = part[mg];
+                                        }
+                                        __syncwarp();
+                                        int old = 0;
+                                        if (lane == 0) { __threadfence_block(); old = atomicAdd(ccnt, 1); }
+                                        old = __shfl_sync(0xffffffffu, old, 0);
+                                        pusher = (old == W - 1);
+                                        if (pusher) {
+                                            __threadfence_block();
+                                            if (tt < 2) {
+#pragma unroll
+                                                for (int mg = 0; mg < MG; ++mg) {
+                                                    long long tsum = 0;
+                                                    for (int w = 0; w < W; ++w) tsum += comb[w * B + mg * 16 + g + 8 * tt];
+                                                    part[mg] = tsum;
+                                                }
+                                            }
+                                            __syncwarp();
+                                            if (lane == 0) *ccnt = 0;
+                                        }
+                                    }
+                                    if (pusher && tt < 2) {
+#pragma unroll
+                                        for (int mg = 0; mg < MG; ++mg) {
+                                            const long long sa = part[mg];
+                                            if (sa >= plim || sa <= -plim) atomicOr(&sy->err, 1);
+                                            const long long rv = (long long)((unsigned long long)sa << cb) + 1;
+                                            if (sharded && P.hier) {
+                                                red_add_u64(sy->acc2 + (size_t)(gidx & (kSlots - 1)) * kMaxB + (size_t)(mg * 16 + g + 8 * tt), rv);
+                                            } else if (sharded) {
+                                                const size_t aoff = (size_t)(gidx & (kSlots - 1)) * kMaxB * kAccStride + (size_t)(mg * 16 + g + 8 * tt) * kAccStride;
+                                                for (int r = 0; r < P.n_ranks; ++r) red_add_u64_sys(P.peer[r]->acc + aoff, rv);
+                                            } else red_add_u64(accg + (mg * 16 + g + 8 * tt) * kAccStride, rv);
+                                        }
+                                    }
+                                } else
 #pragma unroll
                                 for (int mg = 0; mg < MG; ++mg) {
                                     int c4[4];
@@ -881,7 +950,7 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
                             }
                             if constexpr (PROF) { if (tid == kFirstDotWarp * 32 && ja >= 0) { pf[28] += (long long)(global_ns() - pub_ns[(gblk + (unsigned)ja) & (kNzRing - 1)]); pf[29] += 1; } }
                             __syncwarp();
-                            if (lane == 0) { mbar_arrive(&dot_done[gidx & (kNzRing - 1)]); if (P.refetch) mbar_arrive(&tile_free[tslot]); }
+                            if (lane == 0 && pusher) { mbar_arrive(&dot_done[gidx & (kNzRing - 1)]); if (P.refetch) mbar_arrive(&tile_free[tslot]); }
                             tslot += ND;
                             while (tslot >= NT) { tslot -= NT; tph ^= 1u; }
                             if (tid == kFirstDotWarp * 32) NGP_TICK(15);
@@ -1979,10 +2048,10 @@ __device__ __forceinline__ void gibbs_body(const Params& P, const int t)
 #undef NGP_TICK
 }
 
-template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false, bool BR = false, bool SH = false>
+template <int B, bool PROF, bool DBG, bool LIT, bool TUP, bool BIGR = false, bool BR = false, bool SH = false, bool SHT = false>
 __global__ void __launch_bounds__(kThreads, 1) gibbs_kernel(const Params P)
 {
-    gibbs_body<B, PROF, DBG, LIT, TUP, BIGR, BR, SH>(P, (int)blockIdx.x);
+    gibbs_body<B, PROF, DBG, LIT, TUP, BIGR, BR, SH, SHT>(P, (int)blockIdx.x);
 }
 
 // All ranks of a row-sharded chain whose shards live on ONE device, as ONE cooperative grid (the only legal way to run kernels that wait

@@ -162,7 +162,12 @@ def test_replay_parity_many_rows_per_cta(gpu):
         _run_replay(prob, method, kw, "blocked", iters=4, max_ctas=3)
     g = gpu_sampler(prob, 2, 0.05, pi=0.3, est_pi=True, max_ctas=3)
     t = g.timing()
-    assert t["block"] == 16 and t["rows_per_cta"] > 512 and t["ctas"] == 3
+    assert t["block"] == 64 and t["rows_per_cta"] > 1024 and t["ctas"] == 3 and t["tile_stages"] == 1 and t["refetch"] == 1     # one tile, shared by the 8 dot warps
+    g.close()
+    _run_replay(prob, 2, dict(v=0.05, pi=0.3, est_pi=True), "literal", iters=3, max_ctas=3)          # the per-marker sweep takes any panel with any block size
+    _run_replay(prob, 2, dict(v=0.05, pi=0.3, est_pi=True), "blocked", iters=4, max_ctas=3, block=16)
+    g = gpu_sampler(prob, 2, 0.05, pi=0.3, est_pi=True, max_ctas=3, block=16)
+    assert g.timing()["block"] == 16
     g.close()
     for block in (32, 64):
         _run_replay(prob, 2, dict(v=0.05, pi=0.3, est_pi=True), "blocked", iters=4, max_ctas=3, block=block)
@@ -518,9 +523,12 @@ def test_oracle_parity_at_headline_rows_bayescpi(gpu):
 
 
 def test_oracle_parity_at_c5_geometry_refetch_ring(gpu):
-    """BASELINE config 5 rows: n = 200,000 x 512 markers BayesCpi: blocks of 16, 1,376+ rows per CTA (4 row groups per updater thread),
-    tiles leave shared memory after their dots (refetch ring) and changed columns are re-read from L2."""
+    """BASELINE config 5 rows: n = 200,000 x 512 markers BayesCpi, 1,376+ rows per CTA (4 row groups per updater thread): blocks of 64 on a refetch
+    ring of ONE tile whose dots the 8 dot warps share (default since the end of round 2), and the earlier default, blocks of 16;
+    changed columns are re-read from L2."""
     _native_vs_oracle_at_scale(200000, 512, "BayesC", 3, 20261021,
+                               expect=dict(block=64, tile_stages=1, refetch=1, kernel_variant=11, rows_per_cta=lambda r: r >= 1376, ctas=lambda c: c >= 140))
+    _native_vs_oracle_at_scale(200000, 512, "BayesC", 2, 20261021, block=16,
                                expect=dict(block=16, rows_per_cta=lambda r: r >= 1376, ctas=lambda c: c >= 140))
     # the same rows as 2-bit tiles: blocks of 64, 4 row groups per updater thread (the BIGR instantiation), refetch ring
     _native_vs_oracle_at_scale(200000, 512, "BayesC", 2, 20261021, storage="2bit",
