@@ -73,13 +73,14 @@ function method_id(name::String)
     name == "BayesB" && return NGP_BAYESB
     name == "BayesC" && return NGP_BAYESC
     name == "BayesR" && return NGP_BAYESR
+    name == "BayesLV" && return NGP_BAYESPR          # the single-site loop of BayesLV is BayesPR with one region per locus (b200_bayeslv_funct)
     error("$name is not on the B200 hot path (stays in Julia)")
 end
 
 """Translate one entry of the NamedTuple dictionary M returned by getMME! (mme.jl:598-601) into ngp_set_prior."""
 function set_prior!(h, set::Integer, Mset, v0::Float64)
     offs = Int64[first(r) - 1 for r in Mset.regionArray]; push!(offs, last(Mset.regionArray[end]))
-    isPR = Mset.method == "BayesPR"
+    isPR = Mset.method == "BayesPR" || Mset.method == "BayesLV"
     isR = Mset.method == "BayesR"
     pi_in = (isPR || isR) ? 0.0 : Mset.piHat[2]
     vclass = isR ? Vector{Float64}(Mset.vClass) : Float64[]
@@ -115,6 +116,45 @@ function b200_funct(h, set::Integer)
         haskey(M[mSet], :logPi) && (M[mSet].logPi .= log.(M[mSet].piHat))
         nothing
     end
+end
+
+"""BayesLV (functions.jl:421-486): the single-site loop (:431-443) is the BayesPR sweep with one region per locus — getMME! already
+sets M[pSet].regionArray = [r:r ...] (mme.jl:421), so `set_prior!` needs `method_id("BayesLV") == NGP_BAYESPR` — and runs on the device;
+the model of the log-variances (:446-485) stays the reference's own code, copied here verbatim in spirit: the closure calls
+`NextGP`'s sampleBayesLV! tail through `lv_tail!`, which the caller supplies (e.g. the body of functions.jl:446-485 cut into a function)."""
+function b200_bayeslv_funct(h, set::Integer, lv_tail!::Function)
+    return function (mSet, M, beta, delta, ycorr, varE, varBeta)
+        pos = M[mSet].pos
+        b = vec(beta[pos]); d = vec(delta[pos])
+        scratch = copy(varBeta[mSet])                 # the device appends its own scaled-inverse-chi-square draw to the sweep: discarded
+        check(h, ccall((:ngp_sweep, libngp), Cint,
+                       (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Int64}, Ptr{Cdouble}, Ptr{Cdouble}),
+                       h, set, ycorr, varE, b, d, scratch, C_NULL))
+        lv_tail!(mSet, M, beta, varBeta)              # functions.jl:446-485: slice update of varBeta[mSet][locus] / logVar, c, SNPVARRESID, varZeta
+        nothing
+    end
+end
+
+"""Run-level BayesLV: after every `ngp_run(h, 1)` push the host's variances back (the device drew its own)."""
+set_var_beta!(h, set::Integer, vb::Vector{Float64}) =
+    check(h, ccall((:ngp_set_var_beta, libngp), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}), h, set, vb))
+
+"""sampleΛ2!(Λ2,Xc,yCorr,σ2τ,σ2ϵ,pMeans) of the GRN sampler (GRN.jl:150-164) on the device.  Upload X' once (individuals x SNPs, RAW
+codes: the device centres like GRN.jl:23) as a marker set with a one-region BayesPR prior; per gene the right-hand-side offset
+α·pMeans[g] becomes rhs0 = pMeans[g]/σ2τ[g] and the improper effect prior (the reference's LHS holds no prior precision) varBeta = Inf."""
+function sample_lambda2_b200!(h, set::Integer, Λ2::Matrix{Float64}, yCorr::Matrix{Float64}, σ2τ, σ2ϵ::Float64, pMeans)
+    nGenes, nSNPs = size(Λ2)
+    ones64 = ones(Int64, nSNPs)
+    for g in 1:nGenes
+        rhs0 = fill(pMeans[g] / σ2τ[g], nSNPs)
+        check(h, ccall((:ngp_set_marker_summary, libngp), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}), h, set, C_NULL, rhs0))
+        y = yCorr[g, :]; b = Λ2[g, :]; vb = [Inf]    # rows of column-major matrices: copied (keep yCorr individuals x genes to avoid it)
+        check(h, ccall((:ngp_sweep, libngp), Cint,
+                       (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Int64}, Ptr{Cdouble}, Ptr{Cdouble}),
+                       h, set, y, σ2ϵ, b, ones64, vb, C_NULL))
+        yCorr[g, :] .= y; Λ2[g, :] .= b
+    end
+    nothing
 end
 
 """Tuple of correlated marker sets (multi-breed): sets 0..k-1 of the handle are the members, in the order of the tuple key.

@@ -47,3 +47,24 @@ def test_design_matrix_from_formula_and_columns():
     assert np.allclose(np.linalg.inv(CpC + np.eye(3) * np.min(np.abs(np.diag(CpC))) / 10000), m.iCpC)
     with pytest.raises(ValueError):
         ngp.LogVarModel(pr, 4, np.random.default_rng(0))
+
+
+def test_grn_lambda2_is_a_bayespr_sweep_with_an_improper_prior():
+    """The recipe behind api.sampleLambda2 / ngp_set_marker_summary, on the CPU: sampleΛ2! (GRN.jl:150-164) for one gene equals the BayesPR
+    loop (functions.jl:118-137) with varBeta = Inf, lhs0 = 0 and rhs0 = pMeans[g] / σ2τ[g] on every SNP (α pMeans / σ2ϵ), same normals."""
+    rng = np.random.default_rng(3)
+    n, p, nGenes = 80, 40, 3
+    X = rng.integers(0, 3, size=(n, p)).astype(np.float64); X -= X.mean(axis=0)
+    mpm = (X * X).sum(axis=0)
+    Y = rng.normal(size=(nGenes, n))
+    L2_a, yC_a = np.zeros((nGenes, p)), Y.copy()
+    L2_b, yC_b = np.zeros((nGenes, p)), Y.copy()
+    var_tau, pMeans, varE = np.array([0.3, 0.05, 1.7]), np.array([0.2, -0.1, 0.05]), 0.9
+    for sweep in range(3):
+        z = rng.normal(size=(nGenes, p))
+        RN.grn_sample_lambda2(L2_a, X.T.copy(), yC_a, var_tau, varE, pMeans, z)
+        for g in range(nGenes):
+            vb = np.array([np.inf])
+            with np.errstate(divide="ignore"):
+                RN.bayes_pr(X, mpm, np.zeros(p), np.full(p, pMeans[g] / var_tau[g]), [0, p], 0.01, 4.0, L2_b[g], yC_b[g], varE, vb, z[g], np.array([50.0]))
+        assert np.allclose(L2_a, L2_b, rtol=1e-12, atol=1e-14) and np.allclose(yC_a, yC_b, rtol=1e-11, atol=1e-13)
