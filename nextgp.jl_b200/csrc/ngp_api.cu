@@ -1771,7 +1771,8 @@ int ngp_set_joint_prior(ngp_handle* h, const ngp_joint_prior* pr)
     // j*k + b = breed b of locus j, is swept by the look-ahead kernel with the joint k x k draw in the chain warp (ngp_sweep.cuh: joint_step).
     int slot = -1;
     for (int s = 0; s < NGP_MAX_SETS; ++s) if (!h->sets[s].have_geno) { slot = s; break; }
-    if (slot >= 0 && (k == 2 || k == 4) && h->shard_world == 1 && p * k <= 0x7fffffffLL) {
+    // (panels of more than 512 rows with blocks of 32 / 64 have no tuple instantiation of the blocked sweep: the per-locus kernel serves them)
+    if (slot >= 0 && (k == 2 || k == 4) && h->shard_world == 1 && p * k <= 0x7fffffffLL && !(h->R > 4 * kUpdThreads && h->B != 16)) {
         // Every effect of a tuple changes in every sweep, so the look-ahead buys nothing but cross-Gram corrections (B changed columns per
         // block and distance): a short look-ahead served entirely from the block records is the fast geometry (C1 / C4 measurements).
         // Tw, R and B — the tile layout of the sets already uploaded — stay as they are; only the kernel's rings are re-sized.

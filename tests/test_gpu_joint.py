@@ -50,6 +50,7 @@ V3 = np.array([[0.02, 0.004, 0.002], [0.004, 0.03, -0.003], [0.002, -0.003, 0.02
     (333, 70, 2, V2, [0, 10, 70], dict(block=16, max_ctas=5)),
     (900, 200, 2, V2, [0, 64, 65, 130, 200], dict(block=64, lookahead=3)),
     (500, 48, 4, np.eye(4) * 0.02 + 0.004, [0, 20, 48], dict(min_rows=32)),
+    (3001, 64, 2, V2, [0, 30, 64], dict(max_ctas=3)),                    # 1,504 rows per CTA, blocks of 64: no tuple instantiation of the blocked sweep -> per-locus kernel
 ])
 def test_joint_native_chain_matches_oracle(gpu, n, p, k, v, regions, kw):
     probs, y = _breeds(n, p, k, 11)
