@@ -349,6 +349,7 @@ struct ngp_handle {
     int last_variant = -1;      // kernel variant of the last launch (ngp_timing.kernel_variant)
     uint64_t gblk = 0;          // blocks swept so far by the blocked kernel (numbers the list words and accumulator slots)
     bool timed = false;
+    bool dense_rings = false;   // the rings are sized for sets whose every effect changes in every sweep (apply_ring_geometry)
 };
 
 static std::string g_create_err;
@@ -615,6 +616,57 @@ static int choose_geometry(ngp_handle* h, int64_t n, int store2)
                 (long long)n, (long long)R, B, cap);
 }
 
+static int build_gram(ngp_handle* h, SetHost& S)
+{
+    const int64_t nblk = S.p_pad / h->B;
+    cudaFree(S.gx); S.gx = nullptr;
+    CU(dalloc(&S.gx, (size_t)nblk * (h->D + 1) * h->B * h->B));
+    if (h->B == 64) gram_kernel<64><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx, h->store2);
+    else if (h->B == 32) gram_kernel<32><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx, h->store2);
+    else gram_kernel<16><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx, h->store2);
+    CU(cudaGetLastError());
+    return NGP_OK;
+}
+
+static int choose_geometry(ngp_handle* h, int64_t n, int store2);
+
+// Dense-update sets.  Every effect of a BayesPR set (BayesRR, region-wise or per-locus variances) changes in every sweep, so the look-ahead
+// buys nothing but cross-Gram corrections (B changed columns per block and distance): when all marker sets of the handle are BayesPR the
+// rings are re-sized to a short look-ahead served from the block records (D = DN = 3, the tuple sweep's geometry: c4rr 15.1 -> 10.8 ms,
+// C1 0.60 -> 0.55 ms per sweep, profiles/r2/tune_c*_dense.jsonl), and back when a spike-and-slab set joins.  Tw, R, B and the tile-ring
+// mode stay; the banded Gram is laid out by look-ahead and is rebuilt.  Automatic geometry on one GPU only.
+static int apply_ring_geometry(ngp_handle* h)
+{
+    if (h->Tw == 0 || h->cfg_lookahead || h->cfg_near || h->shard_world > 1 || h->joint.active) return NGP_OK;
+    bool any = false, all_pr = true;
+    for (int s = 0; s < h->n_sets; ++s) {
+        const SetHost& S = h->sets[s];
+        if (!S.have_geno || !S.have_prior) continue;
+        any = true;
+        if (S.method != NGP_BAYESPR) all_pr = false;
+    }
+    const bool want = any && all_pr;
+    if (want == h->dense_rings) return NGP_OK;
+    const int sv_l = h->cfg_lookahead, sv_n = h->cfg_near, sv_r = h->cfg_refetch, sv_b = h->cfg_block;
+    const int Tw0 = h->Tw, R0 = h->R, D0 = h->D;
+    h->cfg_block = h->B; h->cfg_refetch = h->refetch;
+    if (want) { h->cfg_lookahead = 3; h->cfg_near = 3; }
+    const int rc = choose_geometry(h, h->n, h->store2 > 0);
+    h->cfg_lookahead = sv_l; h->cfg_near = sv_n; h->cfg_refetch = sv_r; h->cfg_block = sv_b;
+    if (rc) return rc;
+    if (h->Tw != Tw0 || h->R != R0) return fail(h, NGP_EINVAL, "internal: the tile layout changed while re-sizing the rings");
+    h->dense_rings = want;
+    h->ready_kfn = nullptr;
+    h->sets_dirty = true;
+    CU(cudaMemsetAsync(h->sync, 0, sizeof(SyncArea), h->stream));      // clean rings for the new geometry
+    h->gblk = 0;
+    if (h->D != D0)
+        for (int s = 0; s < h->n_sets; ++s)
+            if (h->sets[s].have_geno) { int rg = build_gram(h, h->sets[s]); if (rg) return rg; }
+    CU(cudaStreamSynchronize(h->stream));
+    return NGP_OK;
+}
+
 static int finish_upload(ngp_handle* h, SetHost& S)
 {
     const int64_t p_pad = S.p_pad;
@@ -625,11 +677,7 @@ static int finish_upload(ngp_handle* h, SetHost& S)
     const int64_t nblk = p_pad / h->B;
     CU(dalloc(&S.consts, (size_t)nblk * kNF * h->B));
     CU(zero(h, S.consts, 0, sizeof(double) * (size_t)nblk * kNF * h->B));
-    CU(dalloc(&S.gx, (size_t)nblk * (h->D + 1) * h->B * h->B));
-    if (h->B == 64) gram_kernel<64><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx, h->store2);
-    else if (h->B == 32) gram_kernel<32><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx, h->store2);
-    else gram_kernel<16><<<(unsigned)nblk, 256, 0, h->stream>>>(S.geno, h->Tw, h->R, nblk, h->D, S.gx, h->store2);
-    CU(cudaGetLastError());
+    { int rg = build_gram(h, S); if (rg) return rg; }
     CU(dalloc(&S.beta, p_pad));
     CU(dalloc(&S.delta, p_pad));
     CU(cudaMemsetAsync(S.beta, 0, sizeof(double) * p_pad, h->stream));
@@ -1019,7 +1067,7 @@ int ngp_set_prior(ngp_handle* h, int set_id, const ngp_prior* pr)
     CU(cudaStreamSynchronize(h->stream));
     S.have_prior = true;
     h->sets_dirty = true;
-    return NGP_OK;
+    return apply_ring_geometry(h);
 }
 
 // Replace only the per-marker prior information (lhs0 / rhs0) of a set; the chain state is kept.  GRN.jl:150-164 (sampleΛ2!) changes
@@ -1242,6 +1290,7 @@ static int launch_prepare(ngp_handle* h, int n_iter, int set_mask, int do_varE, 
     if (h->joint.active && !(h->joint.blocked_set >= 0 && set_mask == (1 << h->joint.blocked_set)))
         return fail(h, NGP_EINVAL, "this handle samples a tuple of marker sets: use ngp_run / ngp_joint_sweep");
     const bool sharded = h->shard_world > 1;
+    { int rg = apply_ring_geometry(h); if (rg) return rg; }
     if (sharded && !h->shard_attached) return fail(h, NGP_EINVAL, "row-sharded handle: call ngp_shard_attach before sampling");
     if (sharded && h->fx.n_cols) return fail(h, NGP_EUNSUPPORTED, "fixed effects besides the intercept are not available on a row-sharded handle");
     if (h->replay && h->fx.n_cols && do_mu && (!h->fx_rp_z || h->fx_replay_iters != h->replay_iters))

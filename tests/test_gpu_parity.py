@@ -155,6 +155,31 @@ def test_replay_parity_over_pipeline_geometries(gpu, geom):
     _run_replay(prob, 0, dict(v=0.02), "blocked", iters=3, block=block, min_rows=8, **geom)
 
 
+@pytest.mark.parametrize("first,then", [(0, 2), (2, 0)])
+def test_dense_sets_get_the_short_lookahead_and_back(gpu, first, then):
+    """All marker sets BayesPR (every effect changes in every sweep): the rings are re-sized to look-ahead 3 / near 3 and the banded Gram is
+    rebuilt; a spike-and-slab prior brings the default geometry back.  Either way the chain is the oracle's."""
+    prob = make_problem(1300, 700, 5)
+    kws = {0: dict(v=0.02), 2: dict(v=0.05, pi=0.2, est_pi=True)}
+    g = gpu_sampler(prob, first, **kws[first])
+    t1 = g.timing()
+    df, scale = O.marker_hyper(kws[then]["v"])
+    g.set_prior(0, then, df, scale, kws[then]["v"], pi_in=kws[then].get("pi", 0.0), est_pi=kws[then].get("est_pi", False))
+    t2 = g.timing()
+    dense, default = (t1, t2) if first == 0 else (t2, t1)
+    assert dense["lookahead"] == 3 and dense["near_depth"] == 3 and default["lookahead"] > 3
+    assert dense["block"] == default["block"] and dense["rows_per_cta"] == default["rows_per_cta"] and dense["ctas"] == default["ctas"]
+    ch, S = oracle_chain(prob, then, **kws[then])
+    g.set_rng(21, 2)
+    for _ in range(4):
+        ch.iteration(seed=21, chain=2)
+    g.run(4)
+    st = g.state()
+    assert rel(st["sets"][0]["beta"], S.beta) < TOL and rel(st["e"], ch.e) < TOL and abs(st["varE"] / ch.varE - 1) < TOL
+    assert np.array_equal(st["sets"][0]["delta"], S.delta)
+    g.close()
+
+
 def test_replay_parity_many_rows_per_cta(gpu):
     """Few CTAs => > 512 rows per worker CTA => 4 row groups per updater thread (the C5 / C3 geometry), for every block size."""
     prob = make_problem(3001, 150, 78)
