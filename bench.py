@@ -315,6 +315,8 @@ def main():
     if sharded:
         args.kernel = args.shard_kernel
         args.no_e2e = True
+    if not args.block and method == 0 and not kbreeds and not sharded and args.storage == "i8" and n > 512 * 147:
+        args.block = 16       # dense updates on panels of more than 512 rows: the choice api.getMME makes for all-BayesPR models (ngp_api.cu: apply_ring_geometry)
     s = ngp.Sampler(local, kernel=args.kernel, block=args.block, storage=args.storage)
     if args.cfg_opt >= 0:
         s.configure(L.CFG_OPT, args.cfg_opt)

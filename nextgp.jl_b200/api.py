@@ -386,8 +386,10 @@ class Sampler:
         self.n = 0
         self._keep = []
         self.configure(L.CFG_KERNEL, L.KERNEL_BLOCKED if kernel == "blocked" else L.KERNEL_LITERAL)
+        self._configured = set()
         if block:
             self.configure(L.CFG_BLOCK, block)
+            self._configured.add("block")
         if min_rows:
             self.configure(L.CFG_MIN_ROWS, min_rows)
         if max_ctas:
@@ -940,6 +942,12 @@ def getMME(sampler: Sampler, Y: np.ndarray, M: list[MarkerTerm], priorVCV: dict,
     if tuples:                                                                  # (:M1,:M2) => BayesPR(r, V): mme.jl:448-489
         return _getMME_tuple(sampler, Y, M, priorVCV, tuples, outPut, intercept, df_e, scale_e)
     info = []
+    # every marker prior BayesPR (dense updates) on panels of more than 512 rows per CTA: blocks of 16 with resident tiles beat the default
+    # blocks of 64 on the refetch ring (ngp_api.cu: apply_ring_geometry); the block size is fixed at the first upload, so say it now
+    n_rows = len(Y)
+    if (M and not sampler.sets and n_rows > 512 * 147 and "block" not in getattr(sampler, "_configured", ())
+            and all((priorVCV.get(t.name) is None) or getattr(priorVCV.get(t.name), "name", "") == "BayesPR" for t in M)):
+        sampler.configure(L.CFG_BLOCK, 16)
     for sid, term in enumerate(M):
         term.upload(sampler, sid)
         p = term.p

@@ -634,7 +634,10 @@ static int choose_geometry(ngp_handle* h, int64_t n, int store2);
 // buys nothing but cross-Gram corrections (B changed columns per block and distance): when all marker sets of the handle are BayesPR the
 // rings are re-sized to a short look-ahead served from the block records (D = DN = 3, the tuple sweep's geometry: c4rr 15.1 -> 10.8 ms,
 // C1 0.60 -> 0.55 ms per sweep, profiles/r2/tune_c*_dense.jsonl), and back when a spike-and-slab set joins.  Tw, R, B and the tile-ring
-// mode stay; the banded Gram is laid out by look-ahead and is rebuilt.  Automatic geometry on one GPU only.
+// mode stay; the banded Gram is laid out by look-ahead and is rebuilt.  Automatic geometry on one GPU only.  (Panels of more than 512 rows:
+// dense sets are better served by blocks of 16 with resident tiles — 100k x 600k BayesRR 135 ms per sweep against 206 with blocks of 64 on
+// the refetch ring, where every column is read twice — but the block size is fixed at the first upload: the host mirrors that know the priors
+// before they upload, api.getMME and bench.py, pass NGP_CFG_BLOCK = 16 for such models; see INTEGRATION.md.)
 static int apply_ring_geometry(ngp_handle* h)
 {
     if (h->Tw == 0 || h->cfg_lookahead || h->cfg_near || h->shard_world > 1 || h->joint.active) return NGP_OK;
@@ -645,7 +648,7 @@ static int apply_ring_geometry(ngp_handle* h)
         any = true;
         if (S.method != NGP_BAYESPR) all_pr = false;
     }
-    const bool want = any && all_pr;
+    const bool want = any && all_pr && h->B == 64;      // (blocks of 16 / 32 want a longer look-ahead even for dense sets: c4rr 16:4 18.4 ms, 16:8 14.0; 32:3 15.1, 32:6 11.4)
     if (want == h->dense_rings) return NGP_OK;
     const int sv_l = h->cfg_lookahead, sv_n = h->cfg_near, sv_r = h->cfg_refetch, sv_b = h->cfg_block;
     const int Tw0 = h->Tw, R0 = h->R, D0 = h->D;
