@@ -8,6 +8,13 @@
 #include <string.h>
 #include <strings.h>
 #include <vector>
+#include <thread>
+#include <atomic>
+#include <algorithm>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
 
 #include "../../include/ngp.h"
 
@@ -16,9 +23,25 @@ namespace {
 struct FileBuf {
     char* p = nullptr;
     size_t n = 0;
-    ~FileBuf() { free(p); }
+    bool mapped = false;
+    ~FileBuf() { if (mapped) munmap(p, n); else free(p); }
     int load(const char* path)
     {
+        // the file is mapped, not copied (a C3-sized text file is 120 GB); read() into a buffer only where mmap is not available
+        const int fd = open(path, O_RDONLY);
+        if (fd >= 0) {
+            struct stat st;
+            if (fstat(fd, &st) == 0 && st.st_size > 0) {
+                void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (m != MAP_FAILED) {
+                    (void)madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                    p = (char*)m; n = (size_t)st.st_size; mapped = true;
+                    close(fd);
+                    return NGP_OK;
+                }
+            }
+            close(fd);
+        }
         FILE* f = fopen(path, "rb");
         if (!f) return NGP_EINVAL;
         if (fseek(f, 0, SEEK_END) != 0) { fclose(f); return NGP_EINVAL; }
@@ -68,6 +91,62 @@ int64_t compact_columns(uint8_t* packed, int64_t ld, int64_t p_total, const uint
     return k;
 }
 
+// Fast path of the text reader: every row is "c c c ... c" with c in {0,1,2}, single spaces, no missing values (what a genotype file
+// of prepMatVec.jl:116-120 looks like unless it holds NA).  Rows are handled in blocks of 256 (= 64 output bytes = one cache line per
+// column), one block per task, tasks spread over the host threads: per column the 256 characters come from 256 sequential streams (16 KB
+// of lines in L1) and the 64 packed bytes go out as one line.  Returns false (nothing trusted) if any row is not of that form.
+bool pack_rows_fast(const std::vector<const char*>& line, const std::vector<uint32_t>& len, int64_t n, int64_t p, uint8_t* packed, int64_t ld)
+{
+    const int64_t nblk = (n + 255) / 256;
+    const size_t want = (size_t)(2 * p - 1);
+    for (int64_t i = 0; i < n; ++i) if (len[(size_t)i] != want) return false;
+    std::atomic<int64_t> next(0);
+    std::atomic<bool> ok(true);
+    unsigned T = std::thread::hardware_concurrency();
+    T = std::max(1u, std::min<unsigned>(T ? T : 1u, (unsigned)std::min<int64_t>(nblk, 64)));
+    auto work = [&]() {
+        for (;;) {
+            const int64_t b = next.fetch_add(1);
+            if (b >= nblk || !ok.load(std::memory_order_relaxed)) return;
+            const int64_t i0 = b * 256, rows = std::min<int64_t>(256, n - i0);
+            const char* L[256];
+            for (int64_t r = 0; r < 256; ++r) L[r] = line[(size_t)std::min<int64_t>(i0 + r, n - 1)];
+            const int64_t nq = (rows + 3) / 4;
+            unsigned bad = 0;
+            // separators: every odd position a space
+            for (int64_t r = 0; r < rows; ++r) {
+                const char* c = L[r];
+                unsigned acc = 0;
+                for (int64_t k = 1; k < (int64_t)want; k += 2) acc |= (unsigned)(c[k] ^ ' ');
+                bad |= acc;
+            }
+            uint8_t* out0 = packed + (i0 >> 2);
+            for (int64_t j = 0; j < p; ++j) {
+                uint8_t* out = out0 + j * ld;
+                const int64_t at = 2 * j;
+                for (int64_t q = 0; q < nq; ++q) {
+                    unsigned byte = 0;
+                    for (int64_t u = 0; u < 4; ++u) {
+                        const int64_t r = 4 * q + u;
+                        if (r < rows) {
+                            const unsigned g = (unsigned)(unsigned char)L[r][at] - (unsigned)'0';
+                            bad |= (g > 2u);
+                            byte |= (g & 3u) << (2 * u);
+                        }
+                    }
+                    out[q] = (uint8_t)byte;
+                }
+            }
+            if (bad) ok.store(false);
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    return ok.load();
+}
+
 }  // namespace
 
 extern "C" {
@@ -82,6 +161,9 @@ int ngp_read_text_genotypes(const char* path, int64_t* n_out, int64_t* p_total_o
     const char* const end = fb.p + fb.n;
     // pass 1: rows (non-empty lines) and fields of the first row; delim = ' ' exactly as CSV.read(...; delim=' ') sees it
     int64_t n = 0, p = 0;
+    std::vector<const char*> line;                      // non-empty rows: start and length (without the line end)
+    std::vector<uint32_t> llen;
+    bool fast_ok = true;
     for (const char* q = s; q < end;) {
         const char* e = (const char*)memchr(q, '\n', (size_t)(end - q));
         if (!e) e = end;
@@ -90,14 +172,22 @@ int ngp_read_text_genotypes(const char* path, int64_t* n_out, int64_t* p_total_o
         if (le > q) {
             if (n == 0) { p = 1; for (const char* c = q; c < le; ++c) if (*c == ' ') ++p; }
             ++n;
+            if (packed) { line.push_back(q); if ((size_t)(le - q) > 0xffffffffull) fast_ok = false; llen.push_back((uint32_t)(le - q)); }
         }
         q = e + 1;
     }
     *n_out = n; *p_total_out = p;
     if (!packed) return NGP_OK;                         // sizing call
     if (!keep || !p_kept || n <= 0 || p <= 0 || ld < (n + 3) / 4) return NGP_EINVAL;
-    memset(packed, 0, (size_t)ld * (size_t)p);
     memset(keep, 1, (size_t)p);
+    if (fast_ok && pack_rows_fast(line, llen, n, p, packed, ld)) {      // all codes, no missing value: nothing to drop
+        // (bytes of a column beyond ceil(n/4) are the caller's padding: zero them like the general path does)
+        const int64_t used = (n + 3) / 4;
+        if (ld > used) for (int64_t j = 0; j < p; ++j) memset(packed + j * ld + used, 0, (size_t)(ld - used));
+        *p_kept = p;
+        return NGP_OK;
+    }
+    memset(packed, 0, (size_t)ld * (size_t)p);
     int64_t i = 0;
     for (const char* q = s; q < end;) {
         const char* e = (const char*)memchr(q, '\n', (size_t)(end - q));

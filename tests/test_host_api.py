@@ -105,6 +105,43 @@ def test_native_text_reader_is_bit_exact_and_drops_columns_with_missing(tmp_path
         assert not (packed[-1] >> (2 * (n % 4))).any()
 
 
+@pytest.mark.parametrize("n,p,eol,last_eol", [(7, 5, "\n", True), (257, 33, "\n", False), (1001, 17, "\r\n", True), (513, 40, "\n", True), (256, 9, "\r\n", False)])
+def test_native_text_reader_fast_path_matches_the_general_parser(tmp_path, n, p, eol, last_eol):
+    """A file of plain 0/1/2 codes takes the threaded block reader (256 rows per task); the same data with one token spelled "2.0" takes
+    the general parser: identical packed bytes, zero padding bits, nothing dropped."""
+    from nextgp.jl_b200 import api
+    rng = np.random.default_rng(n + p)
+    codes = rng.integers(0, 3, size=(n, p))
+    codes[n - 1, 0] = 2
+    toks = codes.astype(str).astype(object)
+    f = tmp_path / "clean.txt"
+    f.write_bytes((eol.join(" ".join(r) for r in toks) + (eol if last_eol else "")).encode())
+    packed, n_read, keep = api.read_text_packed(str(f))
+    assert n_read == n and keep.all() and packed.shape == ((n + 3) // 4, p)
+    assert np.array_equal(api.unpack2(packed, n), codes.astype(np.int8))
+    if n % 4:
+        assert not (packed[-1] >> (2 * (n % 4))).any()
+    toks[n - 1, 0] = "2.0"
+    g = tmp_path / "general.txt"
+    g.write_bytes((eol.join(" ".join(r) for r in toks) + (eol if last_eol else "")).encode())
+    packed2, n2, keep2 = api.read_text_packed(str(g))
+    assert n2 == n and np.array_equal(packed, packed2) and np.array_equal(keep, keep2)
+
+
+def test_native_text_reader_falls_back_on_anything_but_plain_codes(tmp_path):
+    from nextgp.jl_b200 import api
+    f = tmp_path / "g.txt"
+    f.write_text("0 1 2\n1 3 2\n")                 # right shape, a character outside 0..2: general parser -> not a code
+    with pytest.raises(ValueError):
+        api.read_text_packed(str(f))
+    f.write_text("0 1 2\n0  12\n")                 # right length, wrong structure
+    with pytest.raises(ValueError):
+        api.read_text_packed(str(f))
+    f.write_text("0 1 2\n\n2 1 0\n")               # an empty line between rows is skipped by both paths
+    packed, n, keep = api.read_text_packed(str(f))
+    assert n == 2 and np.array_equal(api.unpack2(packed, 2), np.array([[0, 1, 2], [2, 1, 0]], dtype=np.int8))
+
+
 def test_native_text_reader_rejects_dosages_and_ragged_rows(tmp_path):
     from nextgp.jl_b200 import api
     f = tmp_path / "g.txt"
