@@ -243,18 +243,39 @@ int ngp_read_bed_genotypes(const char* path, int64_t n, int64_t p, int count_a1,
     }
     const int64_t bpc = (n + 3) / 4;
     const int tail = (int)(n & 3);                       // samples in the last byte (0 = full): padding bits are ignored
-    std::vector<uint8_t> col((size_t)bpc);
-    for (int64_t j = 0; j < p; ++j) {
-        if (fread(col.data(), 1, (size_t)bpc, f) != (size_t)bpc) { fclose(f); return NGP_EDATA; }
-        if (tail) col[(size_t)bpc - 1] |= (uint8_t)(0xff << (2 * tail));   // pad = 0b11: never "missing"
-        uint8_t* o = packed + j * ld;
-        memset(o, 0, (size_t)ld);
-        uint8_t m = 0;
-        for (int64_t b = 0; b < bpc; ++b) { o[b] = lut[col[(size_t)b]]; m |= miss[col[(size_t)b]]; }
-        if (tail) o[bpc - 1] &= (uint8_t)~(0xff << (2 * tail));            // pad rows hold code 0
-        keep[j] = m ? 0 : 1;
-    }
     fclose(f);
+    // variant-major .bed = one column of NGP_GENO_PACKED2 after the other: the file is mapped and the columns are recoded in parallel
+    FileBuf fb;
+    int rc = fb.load(path);
+    if (rc) return rc;
+    if (fb.n < 3 + (size_t)bpc * (size_t)p) return NGP_EDATA;           // truncated file
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(fb.p) + 3;
+    std::atomic<int64_t> next(0);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(4096, (1 << 20) / bpc + 1));      // ~1 MB of columns per task
+    unsigned T = std::thread::hardware_concurrency();
+    T = std::max(1u, std::min<unsigned>(T ? T : 1u, (unsigned)std::min<int64_t>((p + chunk - 1) / chunk, 64)));
+    auto work = [&]() {
+        for (;;) {
+            const int64_t j0 = next.fetch_add(chunk);
+            if (j0 >= p) return;
+            for (int64_t j = j0; j < std::min(p, j0 + chunk); ++j) {
+                const uint8_t* col = src + j * bpc;
+                uint8_t* o = packed + j * ld;
+                uint8_t m = 0;
+                for (int64_t b = 0; b < bpc - 1; ++b) { o[b] = lut[col[b]]; m |= miss[col[b]]; }
+                uint8_t last = col[bpc - 1];
+                if (tail) last |= (uint8_t)(0xff << (2 * tail));            // pad = 0b11: never "missing"
+                o[bpc - 1] = lut[last]; m |= miss[last];
+                if (tail) o[bpc - 1] &= (uint8_t)~(0xff << (2 * tail));     // pad rows hold code 0
+                if (ld > bpc) memset(o + bpc, 0, (size_t)(ld - bpc));
+                keep[j] = m ? 0 : 1;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
     *p_kept = compact_columns(packed, ld, p, keep);
     return NGP_OK;
 }
